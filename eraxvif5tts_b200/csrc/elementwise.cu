@@ -1,0 +1,480 @@
+// Memory-bound kernels of the F5-TTS path: LayerNorm + AdaLN modulation, depth-wise conv + LayerNorm, GRN, text-token
+// lookup, timestep sinusoid, CFG + Euler update, small packing helpers.  All are coalesced / vectorised, one warp per
+// token row where a row reduction is needed; HBM traffic is the roofline (algorithmic bytes per row in DESIGN.md).
+// Reference citations are relative to /root/reference/src/f5_tts/.
+#include "common.cuh"
+#include "f5b_internal.h"
+
+namespace f5b {
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm (no affine, eps) * (1 + scale[b]) + shift[b] -> bf16      AdaLayerNorm.forward model/modules.py:310-315,
+// DiTBlock ff norm :637, AdaLayerNorm_Final :331-336.  One warp per row, row cached in registers (D <= 2048).
+// ---------------------------------------------------------------------------------------------------------------
+template <int VEC>  // float4 per lane
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int64_t mod_bstride,
+                                                          int batch_mod, __nv_bfloat16* __restrict__ out, int rows,
+                                                          int rows_per_batch, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const int nvec = D >> 2;
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    v[j] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  int b = row / rows_per_batch;
+  if (batch_mod > 0) b %= batch_mod;
+  const float4* sc = scale ? reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) : nullptr;
+  const float4* sh = shift ? reinterpret_cast<const float4*>(shift + (size_t)b * mod_bstride) : nullptr;
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * D);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      float4 g = sc ? __ldg(sc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 h = sh ? __ldg(sh + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float a = (v[j].x - mean) * rstd * (1.f + g.x) + h.x;
+      const float bb = (v[j].y - mean) * rstd * (1.f + g.y) + h.y;
+      const float c = (v[j].z - mean) * rstd * (1.f + g.z) + h.z;
+      const float d = (v[j].w - mean) * rstd * (1.f + g.w) + h.w;
+      o[idx] = make_uint2(pack_bf16(a, bb), pack_bf16(c, d));
+    }
+  }
+}
+
+int ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, void* out,
+                int rows, int rows_per_batch, int D, float eps, cudaStream_t s) {
+  F5B_CHECK(rows > 0 && D > 0 && (D & 3) == 0 && D <= 2048, "f5b_ln_modulate: D=%d must be a multiple of 4 and <= 2048", D);
+  F5B_CHECK((mod_bstride & 3) == 0, "f5b_ln_modulate: modulation stride must be a multiple of 4");
+  F5B_CHECK(rows_per_batch > 0, "f5b_ln_modulate: rows_per_batch");
+  const int grid = (rows + 7) / 8;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const int nvec = D / 4;
+  if (nvec <= 32 * 2) ln_modulate_kernel<2><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
+  else if (nvec <= 32 * 4) ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
+  else if (nvec <= 32 * 8) ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
+  else ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// depth-wise Conv1d(k=7, pad 3) + bias + LayerNorm(C, affine, eps) -> bf16    ConvNeXtV2Block model/modules.py:259-262
+// (and the identical Vocos ConvNeXtBlock front).  One warp per output row; the 7 neighbour rows come from L1/L2.
+// ---------------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                                                         int B, int n, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= B * n) return;
+  const int b = row / n, pos = row - b * n;
+  const int nvec = C >> 2;
+  float4 acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    acc[j] = idx < nvec ? __ldg(reinterpret_cast<const float4*>(bias) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int p = pos + k - 3;
+    if (p < 0 || p >= n) continue;  // warp-uniform
+    const float4* xr = reinterpret_cast<const float4*>(x + ((size_t)b * n + p) * C);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        const float4 xv = xr[idx];
+        const float* wc = w + (size_t)idx * 4 * 7 + k;
+        acc[j].x += xv.x * __ldg(wc);
+        acc[j].y += xv.y * __ldg(wc + 7);
+        acc[j].z += xv.z * __ldg(wc + 14);
+        acc[j].w += xv.w * __ldg(wc + 21);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    if (lane + j * 32 < nvec) s += acc[j].x + acc[j].y + acc[j].z + acc[j].w;
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    if (lane + j * 32 < nvec) {
+      const float a = acc[j].x - mean, bb = acc[j].y - mean, c = acc[j].z - mean, d = acc[j].w - mean;
+      q += a * a + bb * bb + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w) + idx);
+      const float4 h = __ldg(reinterpret_cast<const float4*>(ln_b) + idx);
+      o[idx] = make_uint2(pack_bf16((acc[j].x - mean) * rstd * g.x + h.x, (acc[j].y - mean) * rstd * g.y + h.y),
+                          pack_bf16((acc[j].z - mean) * rstd * g.z + h.z, (acc[j].w - mean) * rstd * g.w + h.w));
+    }
+  }
+}
+
+int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B, int n,
+               int C, float eps, cudaStream_t s) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 3) == 0 && C <= 1024, "f5b_dwconv7_ln: C=%d must be a multiple of 4 and <= 1024", C);
+  const int grid = (B * n + 7) / 8;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const int nvec = C / 4;
+  if (nvec <= 32) dwconv7_ln_kernel<1><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
+  else if (nvec <= 64) dwconv7_ln_kernel<2><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
+  else if (nvec <= 128) dwconv7_ln_kernel<4><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
+  else dwconv7_ln_kernel<8><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GRN  model/modules.py:225-234: Gx = ||h||_2 over the SEQUENCE axis, Nx = Gx / (mean_c Gx + 1e-6),
+// out = gamma * (h * Nx) + beta + h.   Pass 1: deterministic column norms; pass 2: apply.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grn_colnorm_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ gx, int n,
+                                                          int C) {
+  // block: 64 channel pairs (128 channels) x 4 row lanes; grid (ceil(C/128), B)
+  __shared__ float red[4][128];
+  const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 128 + cp * 2;
+  const int b = blockIdx.y;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const __nv_bfloat16* base = h + (size_t)b * n * C + c;
+    for (int r = rl; r < n; r += 4) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (size_t)r * C);
+      const float a = __low2float(v), d = __high2float(v);
+      s0 += a * a;
+      s1 += d * d;
+    }
+  }
+  red[rl][cp * 2] = s0;
+  red[rl][cp * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < C) {
+      const float t = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+      gx[(size_t)b * C + cc] = sqrtf(t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) grn_apply_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        __nv_bfloat16* __restrict__ out, int n, int C, int rows_per_block) {
+  __shared__ float red[8];
+  __shared__ float s_mean;
+  const int b = blockIdx.y;
+  const float* g = gx + (size_t)b * C;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += g[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    s_mean = t / (float)C;
+  }
+  __syncthreads();
+  const float inv = 1.f / (s_mean + 1e-6f);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  const int pairs = C >> 1;
+  for (int r = r0; r < r1; ++r) {
+    const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(h + ((size_t)b * n + r) * C);
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * n + r) * C);
+    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+      const __nv_bfloat162 v = hr[p];
+      const float a = __low2float(v), d = __high2float(v);
+      const int c = p * 2;
+      const float ya = __ldg(gamma + c) * (a * (g[c] * inv)) + __ldg(beta + c) + a;
+      const float yd = __ldg(gamma + c + 1) * (d * (g[c + 1] * inv)) + __ldg(beta + c + 1) + d;
+      o[p] = __floats2bfloat162_rn(ya, yd);
+    }
+  }
+}
+
+int grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C, cudaStream_t s) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_grn: C=%d must be even", C);
+  auto* hh = reinterpret_cast<const __nv_bfloat16*>(h);
+  grn_colnorm_kernel<<<dim3((C + 127) / 128, B), 256, 0, s>>>(hh, ws, n, C);
+  F5B_CUDA(cudaGetLastError());
+  const int rpb = 8;
+  grn_apply_kernel<<<dim3((n + rpb - 1) / rpb, B), 256, 0, s>>>(hh, ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), n, C,
+                                                                rpb);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TextEmbedding front, model/backbones/dit.py:49-72
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void text_lookup_kernel(const int64_t* __restrict__ ids, int nt, const float* __restrict__ table,
+                                   const float* __restrict__ pos, float* __restrict__ out, uint8_t* __restrict__ mask_out,
+                                   int n, int C, int drop_text, int add_pos) {
+  const int row = blockIdx.x;  // b*n + p
+  const int b = row / n, p = row - b * n;
+  long long tok = 0;
+  if (p < nt) tok = ids[(size_t)b * nt + p] + 1;  // -1 padding -> filler 0
+  if (mask_out != nullptr && threadIdx.x == 0) mask_out[row] = (tok == 0) ? 1 : 0;
+  if (drop_text) tok = 0;
+  const float* tr = table + (size_t)tok * C;
+  const float* pr = pos + (size_t)min(p, 4095) * C;  // get_pos_embed_indices clamps to max_pos-1 (modules.py:210-219)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)row * C + c] = tr[c] + (add_pos ? pr[c] : 0.f);
+}
+
+__global__ void mask_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ mask, int C) {
+  const int row = blockIdx.x;
+  if (!mask[row]) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x[(size_t)row * C + c] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SinusPositionEmbedding(256), model/modules.py:149-161: emb = 1000 * t * exp(-ln(1e4)/(128-1) * k); cat(sin, cos)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void time_sinus_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int M) {
+  const int m = blockIdx.x;
+  const int k = threadIdx.x;  // 0..127
+  const float f = expf((float)k * -(9.210340371976184f / 127.0f));
+  const float a = 1000.0f * t[m] * f;
+  out[(size_t)m * 256 + k] = __float2bfloat16(sinf(a));
+  out[(size_t)m * 256 + 128 + k] = __float2bfloat16(cosf(a));
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = x[i];
+    out[i] = __float2bfloat16(v / (1.f + __expf(-v)));
+  }
+}
+
+__global__ void pack_bf16_kernel(const float* __restrict__ x, int ld_in, __nv_bfloat16* __restrict__ out, int ld_out, int rows,
+                                 int cols, int width) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * width) return;
+  const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
+  out[(size_t)r * ld_out + c] = __float2bfloat16(c < cols ? x[(size_t)r * ld_in + c] : 0.f);
+}
+
+// LayerNorm(D, affine, eps) with f32 and/or bf16 output (Vocos backbone.norm / final_layer_norm); one warp per row
+template <int VEC>
+__global__ void __launch_bounds__(256) ln_affine_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out_f32,
+                                                        __nv_bfloat16* __restrict__ out_bf16, int rows, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const int nvec = D >> 2;
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    v[j] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    if (lane + j * 32 < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+      const float4 h = __ldg(reinterpret_cast<const float4*>(bias) + idx);
+      float4 y;
+      y.x = (v[j].x - mean) * rstd * g.x + h.x;
+      y.y = (v[j].y - mean) * rstd * g.y + h.y;
+      y.z = (v[j].z - mean) * rstd * g.z + h.z;
+      y.w = (v[j].w - mean) * rstd * g.w + h.w;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * D)[idx] = y;
+      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D)[idx] = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    }
+  }
+}
+
+int ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
+              cudaStream_t s) {
+  F5B_CHECK(rows > 0 && D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_affine: D=%d must be a multiple of 4 and <= 1024", D);
+  const int grid = (rows + 7) / 8;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const int nvec = D / 4;
+  if (nvec <= 32) ln_affine_kernel<1><<<grid, 256, 0, s>>>(x, w, b, out_f32, o, rows, D, eps);
+  else if (nvec <= 64) ln_affine_kernel<2><<<grid, 256, 0, s>>>(x, w, b, out_f32, o, rows, D, eps);
+  else if (nvec <= 128) ln_affine_kernel<4><<<grid, 256, 0, s>>>(x, w, b, out_f32, o, rows, D, eps);
+  else ln_affine_kernel<8><<<grid, 256, 0, s>>>(x, w, b, out_f32, o, rows, D, eps);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CFG combine + Euler step: fn closure model/cfm.py:159-173 (pred + (pred - null) * cfg) and torchdiffeq's fixed-grid
+// euler update y += dt * v; also refreshes the zero-padded bf16 copy of the state that feeds the next input GEMM.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(float* __restrict__ y, const float* __restrict__ pc, const float* __restrict__ pu, float cfg,
+                                 float dt, __nv_bfloat16* __restrict__ ybf, int ld_bf, float* __restrict__ vel, int rows,
+                                 int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * ld_bf) return;
+  const int r = (int)(i / ld_bf), c = (int)(i - (int64_t)r * ld_bf);
+  float yn = 0.f;
+  if (c < C) {
+    const size_t j = (size_t)r * C + c;
+    const float p = pc[j];
+    const float v = pu ? p + (p - pu[j]) * cfg : p;
+    if (vel) vel[j] = v;
+    yn = y[j] + dt * v;
+    y[j] = yn;
+  }
+  if (ybf) ybf[i] = __float2bfloat16(yn);
+}
+
+// x_transformers RotaryEmbedding.forward_from_seq_len (call site model/backbones/dit.py:215), dim_head 64
+__global__ void rope_table_kernel(float2* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 32) return;
+  const int pos = i >> 5, j = i & 31;
+  const float inv = 1.0f / powf(10000.0f, (float)(2 * j) / 64.0f);
+  const float a = (float)pos * inv;
+  out[i] = make_float2(cosf(a), sinf(a));
+}
+
+// Vocos embed Conv1d(n_mels -> C, k=7, pad 3) as a GEMM: im2col row = [k=0..6][c], zero outside the utterance
+__global__ void im2col7_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int T, int n_mels, int ld) {
+  const int row = blockIdx.x;  // b*T + t
+  const int b = row / T, t = row - b * T;
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+    float v = 0.f;
+    if (j < 7 * n_mels) {
+      const int k = j / n_mels, c = j - k * n_mels;
+      const int p = t + k - 3;
+      if (p >= 0 && p < T) v = mel[((size_t)b * T + p) * n_mels + c];
+    }
+    out[(size_t)row * ld + j] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace f5b
+
+using namespace f5b;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int f5b_ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, void* out,
+                    int rows, int rows_per_batch, int D, float eps, f5b_stream_t stream) {
+  return ln_modulate(x, scale, shift, mod_bstride, batch_mod, out, rows, rows_per_batch, D, eps, ST(stream));
+}
+
+int f5b_dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B,
+                   int n, int C, float eps, f5b_stream_t stream) {
+  return dwconv7_ln(x, w, b, ln_w, ln_b, out, B, n, C, eps, ST(stream));
+}
+
+int f5b_grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C,
+            f5b_stream_t stream) {
+  return grn(h, gamma, beta, out, ws, B, n, C, ST(stream));
+}
+
+int f5b_text_lookup(const int64_t* ids, int nt, const float* table, const float* pos, float* out, uint8_t* mask_out, int B,
+                    int n, int C, int drop_text, int add_pos, f5b_stream_t stream) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && nt >= 0, "f5b_text_lookup: bad shape");
+  text_lookup_kernel<<<B * n, 128, 0, ST(stream)>>>(ids, nt, table, pos, out, mask_out, n, C, drop_text, add_pos);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_mask_rows_f32(float* x, const uint8_t* mask, int rows, int C, f5b_stream_t stream) {
+  mask_rows_kernel<<<rows, 128, 0, ST(stream)>>>(x, mask, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_time_sinus(const float* t, void* out, int M, f5b_stream_t stream) {
+  F5B_CHECK(M > 0, "f5b_time_sinus: M");
+  time_sinus_kernel<<<M, 128, 0, ST(stream)>>>(t, reinterpret_cast<__nv_bfloat16*>(out), M);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_silu_bf16(const float* x, void* out, int64_t n, f5b_stream_t stream) {
+  silu_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
+                  f5b_stream_t stream) {
+  return ln_affine(x, w, b, out_f32, out_bf16, rows, D, eps, ST(stream));
+}
+
+int f5b_pack_bf16(const float* x, int ld_in, void* out, int ld_out, int rows, int cols, int width, f5b_stream_t stream) {
+  F5B_CHECK(rows > 0 && cols >= 0 && cols <= width && width <= ld_out && (x != nullptr || cols == 0), "f5b_pack_bf16: bad shape");
+  const int64_t tot = (int64_t)rows * width;
+  pack_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out,
+                                                                          rows, cols, width);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float dt, void* y_bf16, int ld_bf, float* vel_out,
+                  int rows, int C, f5b_stream_t stream) {
+  F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C, "f5b_cfg_euler: bad shape");
+  const int64_t tot = (int64_t)rows * ld_bf;
+  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, cfg, dt, reinterpret_cast<__nv_bfloat16*>(y_bf16),
+                                                                          ld_bf, vel_out, rows, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_rope_table(float* out, int n, f5b_stream_t stream) {
+  rope_table_kernel<<<(n * 32 + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float2*>(out), n);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_im2col7(const float* mel, void* out, int B, int T, int n_mels, int ld, f5b_stream_t stream) {
+  F5B_CHECK(ld >= 7 * n_mels && (ld & 7) == 0, "f5b_im2col7: ld=%d must be >= 7*n_mels and a multiple of 8", ld);
+  im2col7_kernel<<<B * T, 256, 0, ST(stream)>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), T, n_mels, ld);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// Internal C++ interfaces between the translation units of libf5b200.so (the public C ABI is include/f5b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/f5b200.h"
+
+namespace f5b {
+
+int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, cudaStream_t stream);
+
+// convenience wrappers used by the model drivers
+int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
+                int act, cudaStream_t s);
+int linear_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
+               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s);
+int linear_gate_resid(const void* A, int lda, const void* W, int ldw, const float* bias, float* x, int ldc, int M, int N,
+                      int K, int rows_per_batch, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                      int batch_mod, cudaStream_t s);
+
+int ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, void* out_bf16,
+                int rows, int rows_per_batch, int D, float eps, cudaStream_t s);
+int ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
+              cudaStream_t s);
+int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16, int B, int n,
+               int C, float eps, cudaStream_t s);
+int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s);
+int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
+             int n_pad, float scale, cudaStream_t stream);
+int convpos(const void* x, const void* wpk, const float* bias, void* out, float* resid, int B, int n, int D, int groups,
+            int ksize, int mode, cudaStream_t stream);
+
+}  // namespace f5b

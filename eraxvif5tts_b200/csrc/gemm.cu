@@ -1,0 +1,238 @@
+// C[M,N] = epilogue(A[M,K] * W[N,K]^T): the one linear-layer engine of the DiT / text / vocoder stacks, a Problem
+// policy on top of tile_engine.cuh (TMA -> 128B-swizzled smem ring -> tcgen05.mma into TMEM -> fused epilogue).
+//
+// Replaces, per reference call site (paths relative to /root/reference/src/f5_tts/): nn.Linear in to_q/to_k/to_v
+// (model/modules.py:452-454, fused to one N=3D GEMM with the rotary embedding of :470-480 and the head split of
+// :457-465 in the epilogue), to_out + masked_fill + gated residual (:495-501, :635), FeedForward (:348-353, GELU-tanh
+// fused; gated residual :639), InputEmbedding.proj (model/backbones/dit.py:95), AdaLayerNorm linears (:311, :332),
+// TimestepEmbedding MLP (:727-731), proj_out (dit.py:231), ConvNeXtV2 / Vocos point-wise linears.
+#include "f5b_internal.h"
+#include "tile_engine.cuh"
+
+namespace f5b {
+
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+  if constexpr (ACT == F5B_ACT_GELU_TANH) {
+    // nn.GELU(approximate="tanh"), model/modules.py:625
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
+    return 0.5f * x * (1.0f + t);
+  } else if constexpr (ACT == F5B_ACT_GELU_ERF) {
+    return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+  } else if constexpr (ACT == F5B_ACT_SILU) {
+    return x / (1.0f + __expf(-x));
+  } else {
+    return x;
+  }
+}
+
+template <int BN_, int EPI, int ACT>
+struct LinearProblem {
+  static constexpr int BN = BN_;
+  F5bGemmArgs g;
+  int n_tiles, m_tiles, kblocks;
+
+  struct RowCtx {
+    int row, b, pos, n_base;
+    bool valid;
+  };
+
+  __device__ __forceinline__ int num_tiles() const { return n_tiles * m_tiles; }
+  __device__ __forceinline__ int num_kblocks() const { return kblocks; }
+  __device__ __forceinline__ uint32_t umma_n() const { return BN; }
+  __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
+  __device__ __forceinline__ int tile_cols(int tile) const {
+    const int left = g.N - (tile % n_tiles) * BN;
+    return left < BN ? left : BN;
+  }
+  __device__ __forceinline__ void load(int tile, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar, const CUtensorMap* tmA,
+                                       const CUtensorMap* tmB) const {
+    const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    tma_load_2d(sA, tmA, bar, kb * BK, m_blk * BM);
+    tma_load_2d(sB, tmB, bar, kb * BK, n_blk * BN);
+  }
+  __device__ __forceinline__ RowCtx row_ctx(int tile, int r) const {
+    RowCtx c;
+    const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    c.row = m_blk * BM + r;
+    c.n_base = n_blk * BN;
+    c.valid = c.row < g.M;
+    c.b = 0;
+    c.pos = c.row;
+    if constexpr (EPI == F5B_EPI_QKV_ROPE || EPI == F5B_EPI_GATE_RESID) {
+      c.b = c.row / g.rows_per_batch;
+      c.pos = c.row - c.b * g.rows_per_batch;
+    }
+    if constexpr (EPI == F5B_EPI_GATE_RESID) {
+      if (c.valid && g.lens != nullptr) {
+        const int bb = g.batch_mod > 0 ? c.b % g.batch_mod : c.b;
+        c.valid = c.pos < __ldg(g.lens + bb);
+      }
+    }
+    return c;
+  }
+
+  __device__ __forceinline__ void epilogue(const RowCtx& c, int c0, const uint32_t (&r)[32]) const {
+    if (!c.valid) return;
+    const int n0 = c.n_base + c0;
+    const int left = g.N - n0;  // > 0
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float b = 0.f;
+      if (g.bias != nullptr && i < left) b = __ldg(g.bias + n0 + i);
+      v[i] = activate<ACT>(__uint_as_float(r[i]) + b);
+    }
+    if constexpr (EPI == F5B_EPI_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)c.row * g.ldc + n0;
+      store_row32_bf16(o, v, left, (g.ldc & 7) == 0);
+    } else if constexpr (EPI == F5B_EPI_F32) {
+      if (g.addsrc != nullptr) {
+        const float* a = g.addsrc + (size_t)c.row * g.ld_add + n0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < left) v[i] += __ldg(a + i);
+      }
+      float* o = reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + n0;
+      store_row32_f32(o, v, left, (g.ldc & 3) == 0);
+      if (g.out2 != nullptr) {
+        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + (size_t)c.row * g.ldc2 + n0;
+        store_row32_bf16(o2, v, left, (g.ldc2 & 7) == 0);
+      }
+    } else if constexpr (EPI == F5B_EPI_QKV_ROPE) {
+      // head split of model/modules.py:457-465 + x_transformers.apply_rotary_pos_emb on the first rope_heads heads
+      // of q and k (:470-480): interleaved pairs (2i, 2i+1), angle pos * 10000^(-2i/64), fp32 math.
+      const int Dm = g.heads * 64;
+      const int sec = n0 / Dm;
+      const int within = n0 - sec * Dm;
+      const int head = within >> 6;
+      const int dd0 = within & 63;  // 0 or 32
+      if (sec < 2) {
+        if (head < g.rope_heads) {
+          const float2* cs = reinterpret_cast<const float2*>(g.rope) + (size_t)c.pos * 32 + (dd0 >> 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 t = __ldg(cs + i);
+            const float x0 = v[2 * i], x1 = v[2 * i + 1];
+            v[2 * i] = x0 * t.x - x1 * t.y;
+            v[2 * i + 1] = x1 * t.x + x0 * t.y;
+          }
+        }
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? g.out : g.out2);
+        __nv_bfloat16* o = base + (((size_t)c.b * g.heads + head) * g.rows_per_batch + c.pos) * 64 + dd0;
+        store_row32_bf16(o, v, 32, true);
+      } else {
+        // v transposed: [B, H, 64, n_pad] so that P.V sees a K-major B operand; lanes = consecutive positions
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out3) +
+                           (((size_t)c.b * g.heads + head) * 64 + dd0) * g.n_pad + c.pos;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[(size_t)i * g.n_pad] = __float2bfloat16(v[i]);
+      }
+    } else {  // F5B_EPI_GATE_RESID: x += gate[b] * (acc + bias); rows beyond lens[b] untouched
+      float* o = reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + n0;
+      const int bb = g.batch_mod > 0 ? c.b % g.batch_mod : c.b;
+      const float* gt = g.gate ? g.gate + (size_t)bb * g.gate_bstride + n0 : nullptr;
+      if (left >= 32 && (g.ldc & 3) == 0 && (gt == nullptr || ((g.gate_bstride & 3) == 0))) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 x = reinterpret_cast<float4*>(o)[q];
+          const float4 gg = gt ? __ldg(reinterpret_cast<const float4*>(gt) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+          x.x += gg.x * v[q * 4];
+          x.y += gg.y * v[q * 4 + 1];
+          x.z += gg.z * v[q * 4 + 2];
+          x.w += gg.w * v[q * 4 + 3];
+          reinterpret_cast<float4*>(o)[q] = x;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < left) o[i] += (gt ? __ldg(gt + i) : 1.f) * v[i];
+      }
+    }
+  }
+};
+
+template <int BN, int EPI, int ACT>
+static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F5bGemmArgs& g, cudaStream_t stream) {
+  LinearProblem<BN, EPI, ACT> p;
+  p.g = g;
+  p.m_tiles = (g.M + BM - 1) / BM;
+  p.n_tiles = (g.N + BN - 1) / BN;
+  p.kblocks = (g.K + BK - 1) / BK;
+  return launch_engine(tmA, tmB, p, p.m_tiles * p.n_tiles, stream);
+}
+
+template <int BN>
+static int dispatch(const CUtensorMap& a, const CUtensorMap& b, const F5bGemmArgs& g, cudaStream_t s) {
+#define F5B_CASE(E, A) \
+  if (g.epi == E && g.act == A) return launch_linear<BN, E, A>(a, b, g, s);
+  F5B_CASE(F5B_EPI_BF16, F5B_ACT_NONE)
+  F5B_CASE(F5B_EPI_BF16, F5B_ACT_GELU_TANH)
+  F5B_CASE(F5B_EPI_BF16, F5B_ACT_GELU_ERF)
+  F5B_CASE(F5B_EPI_BF16, F5B_ACT_SILU)
+  F5B_CASE(F5B_EPI_F32, F5B_ACT_NONE)
+  F5B_CASE(F5B_EPI_QKV_ROPE, F5B_ACT_NONE)
+  F5B_CASE(F5B_EPI_GATE_RESID, F5B_ACT_NONE)
+#undef F5B_CASE
+  set_error("f5b_gemm: unsupported epilogue/activation combination (%d, %d)", g.epi, g.act);
+  return -1;
+}
+
+int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, cudaStream_t stream) {
+  F5B_CHECK(A != nullptr && W != nullptr, "f5b_gemm: null operand");
+  F5B_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "f5b_gemm: empty problem %d x %d x %d", g.M, g.N, g.K);
+  F5B_CHECK(g.out != nullptr, "f5b_gemm: null output");
+  F5B_CHECK(lda >= g.K && ldw >= g.K && (lda & 7) == 0 && (ldw & 7) == 0,
+            "f5b_gemm: row pitches must be >= K and multiples of 8 elements (lda %d ldw %d K %d)", lda, ldw, g.K);
+  if (g.epi == F5B_EPI_QKV_ROPE) {
+    F5B_CHECK(g.rope && g.out2 && g.out3 && g.rows_per_batch > 0 && g.heads > 0 && g.N == 3 * g.heads * 64 &&
+                  g.n_pad >= g.rows_per_batch && g.M % g.rows_per_batch == 0,
+              "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d n_pad %d)", g.N, g.heads, g.rows_per_batch, g.n_pad);
+  }
+  if (g.epi == F5B_EPI_GATE_RESID) F5B_CHECK(g.rows_per_batch > 0, "f5b_gemm: rows_per_batch required");
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= sm_count()) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d(&tmA, A, 2, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda * 2, BK, BM, true)) return -1;
+  if (make_tmap_2d(&tmB, W, 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 2, BK, bn, true)) return -1;
+  return bn == 256 ? dispatch<256>(tmA, tmB, g, stream) : dispatch<128>(tmA, tmB, g, stream);
+}
+
+static F5bGemmArgs base_args(int M, int N, int K, int epi, int act, const float* bias, void* out, int ldc) {
+  F5bGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.epi = epi; g.act = act; g.bias = bias; g.out = out; g.ldc = ldc;
+  return g;
+}
+
+int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
+                int act, cudaStream_t s) {
+  F5bGemmArgs g = base_args(M, N, K, F5B_EPI_BF16, act, bias, out, ldc);
+  return gemm(A, lda, W, ldw, g, s);
+}
+
+int linear_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
+               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s) {
+  F5bGemmArgs g = base_args(M, N, K, F5B_EPI_F32, act, bias, out, ldc);
+  g.addsrc = addsrc; g.ld_add = ld_add; g.out2 = out_bf16; g.ldc2 = ld_bf16;
+  return gemm(A, lda, W, ldw, g, s);
+}
+
+int linear_gate_resid(const void* A, int lda, const void* W, int ldw, const float* bias, float* x, int ldc, int M, int N,
+                      int K, int rows_per_batch, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                      int batch_mod, cudaStream_t s) {
+  F5bGemmArgs g = base_args(M, N, K, F5B_EPI_GATE_RESID, F5B_ACT_NONE, bias, x, ldc);
+  g.rows_per_batch = rows_per_batch; g.gate = gate; g.gate_bstride = gate_bstride; g.lens = lens; g.batch_mod = batch_mod;
+  return gemm(A, lda, W, ldw, g, s);
+}
+
+}  // namespace f5b
+
+extern "C" int f5b_gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs* args, f5b_stream_t stream) {
+  if (args == nullptr) {
+    f5b::set_error("f5b_gemm: null args");
+    return -1;
+  }
+  return f5b::gemm(A, lda, W, ldw, *args, static_cast<cudaStream_t>(stream));
+}

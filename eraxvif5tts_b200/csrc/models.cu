@@ -1,0 +1,300 @@
+// Model-level drivers: the launch sequences of DiT.forward, TextEmbedding, the per-sample modulation table, and Vocos.decode.
+// Host-side only (no kernels here); every launch goes to the caller's stream, nothing is allocated, so a whole ODE step is
+// CUDA-graph capturable.  Reference citations are relative to /root/reference/src/f5_tts/.
+#include <new>
+
+#include "common.cuh"
+#include "f5b_internal.h"
+
+struct F5bDit {
+  F5bDitDesc d;
+};
+struct F5bVocos {
+  F5bVocosDesc d;
+};
+
+namespace f5b {
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int round8(int x) { return (x + 7) / 8 * 8; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off = align_up(off + count * sizeof(T));
+    return r;
+  }
+};
+
+struct DitWs {
+  float* x;
+  __nv_bfloat16 *hb, *q, *k, *vt, *ab, *fb;
+  size_t bytes;
+};
+
+static DitWs carve_dit(const F5bDitDesc& d, int B, int n, void* ws) {
+  const size_t rows = (size_t)B * n;
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads;
+  Carver c(ws);
+  DitWs w;
+  w.x = c.take<float>(rows * D);
+  w.hb = c.take<__nv_bfloat16>(rows * D);
+  w.q = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
+  w.k = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
+  w.vt = c.take<__nv_bfloat16>((size_t)B * H * 64 * round8(n));
+  w.ab = c.take<__nv_bfloat16>(rows * D);
+  w.fb = c.take<__nv_bfloat16>(rows * F);
+  w.bytes = c.off;
+  return w;
+}
+
+}  // namespace f5b
+
+using namespace f5b;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define F5B_TRY(call)        \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+extern "C" {
+
+const char* f5b_last_error(void) { return f5b::last_error(); }
+int f5b_abi_version(void) { return F5B_ABI_VERSION; }
+
+int f5b_dit_create(const F5bDitDesc* desc, F5bDit** out) {
+  F5B_CHECK(desc && out, "f5b_dit_create: null argument");
+  const F5bDitDesc& d = *desc;
+  F5B_CHECK(d.dim > 0 && d.depth > 0 && d.heads > 0, "f5b_dit_create: bad dims");
+  F5B_CHECK(d.dim_head == 64, "f5b_dit_create: dim_head must be 64 (got %d)", d.dim_head);
+  F5B_CHECK(d.heads * d.dim_head == d.dim, "f5b_dit_create: heads*dim_head (%d) must equal dim (%d)", d.heads * d.dim_head, d.dim);
+  F5B_CHECK(d.dim % 8 == 0 && d.text_dim % 8 == 0, "f5b_dit_create: dim and text_dim must be multiples of 8");
+  F5B_CHECK(d.mel_dim > 0 && d.mel_dim <= 128, "f5b_dit_create: mel_dim must be <= 128");
+  F5B_CHECK(d.convpos_groups > 0 && d.dim % d.convpos_groups == 0 && d.dim / d.convpos_groups <= 64,
+            "f5b_dit_create: conv_pos_embed needs <= 64 channels per group");
+  F5B_CHECK(d.rope_heads >= 0 && d.rope_heads <= d.heads, "f5b_dit_create: rope_heads");
+  F5B_CHECK(d.time_w0 && d.time_w2 && d.mod_w && d.text_table && d.in_wx && d.in_wct && d.cp_w1 && d.cp_w2 && d.qkv_w && d.out_w &&
+                d.ff1_w && d.ff2_w && d.proj_w,
+            "f5b_dit_create: null weight pointer");
+  F5bDit* h = new (std::nothrow) F5bDit;
+  F5B_CHECK(h != nullptr, "f5b_dit_create: out of host memory");
+  h->d = d;
+  *out = h;
+  return 0;
+}
+
+void f5b_dit_destroy(F5bDit* h) { delete h; }
+
+size_t f5b_dit_workspace_bytes(const F5bDit* h, int B, int n) {
+  if (!h || B <= 0 || n <= 0) return 0;
+  return carve_dit(h->d, B, n, nullptr).bytes;
+}
+
+// TimestepEmbedding (model/modules.py:721-731) + every AdaLayerNorm / AdaLayerNorm_Final linear (:311, :332) for M time values
+int f5b_dit_modulation(const F5bDit* h, const float* t, int M, float* mod, void* ws, f5b_stream_t stream) {
+  F5B_CHECK(h && t && mod && ws && M > 0, "f5b_dit_modulation: bad argument");
+  const F5bDitDesc& d = h->d;
+  const int D = d.dim;
+  const int mod_dim = d.depth * 6 * D + 2 * D;
+  Carver c(ws);
+  __nv_bfloat16* sin_bf = c.take<__nv_bfloat16>((size_t)M * 256);
+  __nv_bfloat16* h1 = c.take<__nv_bfloat16>((size_t)M * D);
+  __nv_bfloat16* h2 = c.take<__nv_bfloat16>((size_t)M * D);
+  cudaStream_t s = ST(stream);
+  F5B_TRY(f5b_time_sinus(t, sin_bf, M, stream));
+  F5B_TRY(linear_bf16(sin_bf, 256, d.time_w0, 256, d.time_b0, h1, D, M, D, 256, F5B_ACT_SILU, s));
+  // every consumer of the time embedding applies SiLU first (AdaLayerNorm.silu), so it is fused here
+  F5B_TRY(linear_bf16(h1, D, d.time_w2, D, d.time_b2, h2, D, M, D, D, F5B_ACT_SILU, s));
+  F5B_TRY(linear_f32(h2, D, d.mod_w, D, d.mod_b, mod, mod_dim, M, mod_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  return 0;
+}
+
+size_t f5b_dit_modulation_ws_bytes(const F5bDit* h, int M) {
+  if (!h || M <= 0) return 0;
+  return align_up((size_t)M * 256 * 2) + 2 * align_up((size_t)M * h->d.dim * 2);
+}
+
+size_t f5b_dit_text_ws_bytes(const F5bDit* h, int B, int n) {
+  if (!h || B <= 0 || n <= 0) return 0;
+  const size_t rows = (size_t)B * n;
+  const int T = h->d.text_dim;
+  return align_up(rows * T * 2) + 2 * align_up(rows * 2 * T * 2) + align_up((size_t)B * 2 * T * 4) + align_up(rows);
+}
+
+// TextEmbedding.forward, model/backbones/dit.py:49-79 with ConvNeXtV2Block model/modules.py:241-269
+int f5b_dit_text_embed(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, float* out, void* ws,
+                       f5b_stream_t stream) {
+  F5B_CHECK(h && ids && out && ws && B > 0 && n > 0 && nt > 0, "f5b_dit_text_embed: bad argument");
+  const F5bDitDesc& d = h->d;
+  const int T = d.text_dim, T2 = 2 * d.text_dim;
+  const size_t rows = (size_t)B * n;
+  Carver c(ws);
+  __nv_bfloat16* tb = c.take<__nv_bfloat16>(rows * T);
+  __nv_bfloat16* t2 = c.take<__nv_bfloat16>(rows * T2);
+  __nv_bfloat16* t3 = c.take<__nv_bfloat16>(rows * T2);
+  float* gx = c.take<float>((size_t)B * T2);
+  uint8_t* mask = c.take<uint8_t>(rows);
+  cudaStream_t s = ST(stream);
+  const bool mp = d.text_mask_padding != 0 && d.conv_layers > 0;
+  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, out, mp ? mask : nullptr, B, n, T, drop_text, d.conv_layers > 0,
+                          stream));
+  if (mp) F5B_TRY(f5b_mask_rows_f32(out, mask, (int)rows, T, stream));
+  for (int j = 0; j < d.conv_layers; ++j) {
+    F5B_TRY(dwconv7_ln(out, d.tb_dw_w + (size_t)j * T * 7, d.tb_dw_b + (size_t)j * T, d.tb_ln_w + (size_t)j * T,
+                       d.tb_ln_b + (size_t)j * T, tb, B, n, T, 1e-6f, s));
+    F5B_TRY(linear_bf16(tb, T, reinterpret_cast<const __nv_bfloat16*>(d.tb_pw1_w) + (size_t)j * T2 * T, T, d.tb_pw1_b + (size_t)j * T2,
+                        t2, T2, (int)rows, T2, T, F5B_ACT_GELU_ERF, s));
+    F5B_TRY(grn(t2, d.tb_grn_g + (size_t)j * T2, d.tb_grn_b + (size_t)j * T2, t3, gx, B, n, T2, s));
+    F5B_TRY(linear_gate_resid(t3, T2, reinterpret_cast<const __nv_bfloat16*>(d.tb_pw2_w) + (size_t)j * T * T2, T2,
+                              d.tb_pw2_b + (size_t)j * T, out, T, (int)rows, T, T2, n, nullptr, 0, nullptr, 0, s));
+    if (mp) F5B_TRY(f5b_mask_rows_f32(out, mask, (int)rows, T, stream));
+  }
+  return 0;
+}
+
+// Step-invariant part of InputEmbedding.proj (model/backbones/dit.py:91-95): [cond | text_embed] W_ct^T + bias
+int f5b_dit_input_const(const F5bDit* h, const float* cond, const float* text_embed, int B, int n, float* c0, void* ws,
+                        f5b_stream_t stream) {
+  F5B_CHECK(h && text_embed && c0 && ws && B > 0 && n > 0, "f5b_dit_input_const: bad argument");
+  const F5bDitDesc& d = h->d;
+  const int T = d.text_dim, K = 128 + T;
+  const int rows = B * n;
+  __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ws);
+  F5B_TRY(f5b_pack_bf16(cond, d.mel_dim, a, K, rows, cond ? d.mel_dim : 0, 128, stream));
+  F5B_TRY(f5b_pack_bf16(text_embed, T, a + 128, K, rows, T, T, stream));
+  F5B_TRY(linear_f32(a, K, d.in_wct, K, d.in_b, c0, d.dim, rows, d.dim, K, F5B_ACT_NONE, nullptr, 0, nullptr, 0, ST(stream)));
+  return 0;
+}
+
+// DiT.forward, model/backbones/dit.py:185-233 (time/text embeddings hoisted out: `mod`, `c0`)
+int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0, int Bf, int n, const float* mod,
+                    int64_t mod_bstride, const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes,
+                    f5b_stream_t stream) {
+  F5B_CHECK(h && x_bf16 && c0 && mod && rope && pred && ws, "f5b_dit_forward: null argument");
+  F5B_CHECK(Bx > 0 && Bf > 0 && Bf % Bx == 0 && n > 0, "f5b_dit_forward: Bf (%d) must be a multiple of Bx (%d)", Bf, Bx);
+  const F5bDitDesc& d = h->d;
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads;
+  const int n_pad = round8(n);
+  const int rows = Bf * n;
+  DitWs w = carve_dit(d, Bf, n, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+  const int batch_mod = Bx;
+
+  // InputEmbedding (dit.py:91-97): x W_x^T + c0, then conv_pos_embed(h) + h (no mask)
+  const int hrows = Bx * n;
+  for (int half = 0; half < Bf / Bx; ++half) {
+    const size_t off = (size_t)half * hrows * D;
+    F5B_TRY(linear_f32(x_bf16, 128, d.in_wx, 128, nullptr, w.x + off, D, hrows, D, 128, F5B_ACT_NONE, c0 + off, D, w.hb + off, D, s));
+  }
+  F5B_TRY(convpos(w.hb, d.cp_w1, d.cp_b1, w.ab, nullptr, Bf, n, D, d.convpos_groups, d.convpos_kernel, 0, s));
+  F5B_TRY(convpos(w.ab, d.cp_w2, d.cp_b2, nullptr, w.x, Bf, n, D, d.convpos_groups, d.convpos_kernel, 1, s));
+
+  const __nv_bfloat16* qkv_w = reinterpret_cast<const __nv_bfloat16*>(d.qkv_w);
+  const __nv_bfloat16* out_w = reinterpret_cast<const __nv_bfloat16*>(d.out_w);
+  const __nv_bfloat16* ff1_w = reinterpret_cast<const __nv_bfloat16*>(d.ff1_w);
+  const __nv_bfloat16* ff2_w = reinterpret_cast<const __nv_bfloat16*>(d.ff2_w);
+  for (int i = 0; i < d.depth; ++i) {
+    // AdaLayerNorm chunk order (model/modules.py:312): shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    const float* m = mod + (size_t)i * 6 * D;
+    F5B_TRY(ln_modulate(w.x, m + D, m, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
+    F5bGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
+    g.bias = d.qkv_b + (size_t)i * 3 * D;
+    g.out = w.q; g.out2 = w.k; g.out3 = w.vt;
+    g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H; g.n_pad = n_pad;
+    F5B_TRY(gemm(w.hb, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
+    F5B_TRY(attn_fwd(w.q, w.k, w.vt, w.ab, lens, batch_mod, Bf, H, n, n_pad, 0.125f, s));
+    F5B_TRY(linear_gate_resid(w.ab, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
+                              mod_bstride, lens, batch_mod, s));
+    F5B_TRY(ln_modulate(w.x, m + 4 * D, m + 3 * D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
+    F5B_TRY(linear_bf16(w.hb, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, w.fb, F, rows, F, D, F5B_ACT_GELU_TANH, s));
+    F5B_TRY(linear_gate_resid(w.fb, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, w.x, D, rows, D, F, n, m + 5 * D,
+                              mod_bstride, nullptr, batch_mod, s));
+  }
+  // AdaLayerNorm_Final chunk order (model/modules.py:333): scale, shift; then proj_out (dit.py:231)
+  const float* mf = mod + (size_t)d.depth * 6 * D;
+  F5B_TRY(ln_modulate(w.x, mf, mf + D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
+  F5B_TRY(linear_f32(w.hb, D, d.proj_w, D, d.proj_b, pred, d.mel_dim, rows, d.mel_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vocos.decode (third-party `vocos`)
+// ---------------------------------------------------------------------------------------------------------------
+int f5b_vocos_create(const F5bVocosDesc* desc, F5bVocos** out) {
+  F5B_CHECK(desc && out, "f5b_vocos_create: null argument");
+  const F5bVocosDesc& d = *desc;
+  F5B_CHECK(d.n_fft == 1024 && d.hop == 256, "f5b_vocos_create: only n_fft 1024 / hop 256 (vocos-mel-24khz) is built");
+  F5B_CHECK(d.dim > 0 && d.dim % 8 == 0 && d.dim <= 1024 && d.intermediate % 8 == 0 && d.ld_embed >= 7 * d.n_mels && d.ld_embed % 8 == 0,
+            "f5b_vocos_create: bad dims");
+  F5B_CHECK(d.embed_w && d.dw_w && d.pw1_w && d.pw2_w && d.gamma && d.head_w, "f5b_vocos_create: null weight pointer");
+  F5bVocos* h = new (std::nothrow) F5bVocos;
+  F5B_CHECK(h != nullptr, "f5b_vocos_create: out of host memory");
+  h->d = d;
+  *out = h;
+  return 0;
+}
+void f5b_vocos_destroy(F5bVocos* h) { delete h; }
+
+struct VocosWs {
+  float* x;
+  __nv_bfloat16 *a, *hb, *ib;
+  float *head, *frames;
+  size_t bytes;
+};
+static VocosWs carve_vocos(const F5bVocosDesc& d, int B, int T, void* ws) {
+  const size_t rows = (size_t)B * T;
+  Carver c(ws);
+  VocosWs w;
+  w.x = c.take<float>(rows * d.dim);
+  w.a = c.take<__nv_bfloat16>(rows * d.ld_embed);
+  w.hb = c.take<__nv_bfloat16>(rows * d.dim);
+  w.ib = c.take<__nv_bfloat16>(rows * d.intermediate);
+  w.head = c.take<float>(rows * (d.n_fft + 2));
+  w.frames = c.take<float>(rows * d.n_fft);
+  w.bytes = c.off;
+  return w;
+}
+size_t f5b_vocos_workspace_bytes(const F5bVocos* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return carve_vocos(h->d, B, T, nullptr).bytes;
+}
+
+int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* wav, void* ws, size_t ws_bytes,
+                     f5b_stream_t stream) {
+  F5B_CHECK(h && mel && wav && ws && B > 0 && T > 1, "f5b_vocos_decode: bad argument");
+  const F5bVocosDesc& d = h->d;
+  VocosWs w = carve_vocos(d, B, T, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_vocos_decode: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+  const int rows = B * T, C = d.dim, I = d.intermediate;
+  // backbone.embed Conv1d(n_mels, C, k=7, pad 3) as im2col + GEMM, then backbone.norm
+  F5B_TRY(f5b_im2col7(mel, w.a, B, T, d.n_mels, d.ld_embed, stream));
+  F5B_TRY(linear_f32(w.a, d.ld_embed, d.embed_w, d.ld_embed, d.embed_b, w.x, C, rows, C, 7 * d.n_mels, F5B_ACT_NONE, nullptr, 0,
+                     nullptr, 0, s));
+  F5B_TRY(ln_affine(w.x, d.norm_w, d.norm_b, w.x, nullptr, rows, C, 1e-6f, s));
+  const __nv_bfloat16* pw1 = reinterpret_cast<const __nv_bfloat16*>(d.pw1_w);
+  const __nv_bfloat16* pw2 = reinterpret_cast<const __nv_bfloat16*>(d.pw2_w);
+  for (int i = 0; i < d.num_layers; ++i) {
+    F5B_TRY(dwconv7_ln(w.x, d.dw_w + (size_t)i * C * 7, d.dw_b + (size_t)i * C, d.ln_w + (size_t)i * C, d.ln_b + (size_t)i * C, w.hb,
+                       B, T, C, 1e-6f, s));
+    F5B_TRY(linear_bf16(w.hb, C, pw1 + (size_t)i * I * C, C, d.pw1_b + (size_t)i * I, w.ib, I, rows, I, C, F5B_ACT_GELU_ERF, s));
+    // x += gamma * (pwconv2(.) + b): the gate-residual epilogue with a batch-independent gate
+    F5B_TRY(linear_gate_resid(w.ib, I, pw2 + (size_t)i * C * I, I, d.pw2_b + (size_t)i * C, w.x, C, rows, C, I, T,
+                              d.gamma + (size_t)i * C, 0, nullptr, 0, s));
+  }
+  F5B_TRY(ln_affine(w.x, d.fln_w, d.fln_b, nullptr, w.hb, rows, C, 1e-6f, s));
+  const int NO = d.n_fft + 2;
+  F5B_TRY(linear_f32(w.hb, C, d.head_w, C, d.head_b, w.head, NO, rows, NO, C, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  F5B_TRY(f5b_istft_head(w.head, NO, w.frames, wav, B, T, stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+/* f5b200 — C ABI of the B200-native F5-TTS hot path (libf5b200.so).
+ *
+ * The reference (hungkq-1724/EraXviF5TTS) has no FFI: its boundary is the Python class API
+ * F5TTSWrapper / CFM.sample / DiT.forward / MelSpec / vocoder.decode.  The Python mirror of
+ * those classes (package eraxvif5tts_b200) owns torch tensors for device memory and calls THIS library through
+ * ctypes with raw device pointers and a CUDA stream.  Every entry point below names the reference code it replaces
+ * (paths relative to /root/reference/src/f5_tts/).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types;
+ *   - return 0 on success, a negative code on failure; f5b_last_error() returns the message (thread local);
+ *   - the caller owns every buffer; the library never allocates device memory;
+ *   - every call is stream-ordered, asynchronous and CUDA-graph capturable; `stream` is a cudaStream_t;
+ *   - activations are token-major: row = b * rows_per_batch + position;
+ *   - "bf16" buffers hold __nv_bfloat16, weights are nn.Linear layout [out_features, in_features] in bf16;
+ *   - sm_100a only.  There is no CPU or generic-GPU fallback.
+ */
+#ifndef F5B200_H_
+#define F5B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F5B_ABI_VERSION 1
+
+typedef void* f5b_stream_t; /* cudaStream_t */
+
+/* ---- epilogues of the tcgen05 GEMM engine ------------------------------------------------------------------ */
+enum {
+  F5B_EPI_BF16 = 0,       /* out bf16[M,ldc]  = act(acc + bias)                                               */
+  F5B_EPI_F32 = 1,        /* out f32 [M,ldc]  = act(acc + bias) (+ addsrc[row,:])  ; optional bf16 copy in out2 */
+  F5B_EPI_QKV_ROPE = 2,   /* q,k head-major bf16 [B,H,n,64] (+ rotary on the first rope_heads heads), v transposed */
+  F5B_EPI_GATE_RESID = 3  /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
+};
+enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3 };
+
+typedef struct F5bGemmArgs {
+  int32_t M, N, K;
+  int32_t epi, act;
+  const float* bias;         /* [N] or NULL */
+  void* out;                 /* see epilogue; for QKV_ROPE: q base */
+  int32_t ldc;
+  void* out2;                /* F32: optional bf16 copy; QKV_ROPE: k base */
+  int32_t ldc2;
+  void* out3;                /* QKV_ROPE: v^T base, bf16 [B,H,64,n_pad] */
+  const float* addsrc;       /* F32: optional f32 [M,ld_add] added to the result */
+  int32_t ld_add;
+  int32_t rows_per_batch;    /* QKV_ROPE / GATE_RESID: n (positions per batch row) */
+  const float* gate;         /* GATE_RESID: f32 gate, element (b, col) at gate[b*gate_bstride + col]; NULL -> 1 */
+  int64_t gate_bstride;
+  const int32_t* lens;       /* GATE_RESID: int32 [B] valid length per batch row, or NULL (all rows valid) */
+  int32_t batch_mod;         /* gate / lens are indexed by b % batch_mod (a CFG-fused batch shares them); 0 -> b */
+  const float* rope;         /* QKV_ROPE: f32 [n, 32, 2] (cos, sin) */
+  int32_t rope_heads;        /* QKV_ROPE: heads that get the rotary embedding (pe_attn_head; H for all) */
+  int32_t heads;             /* QKV_ROPE: H (N must be 3*H*64) */
+  int32_t n_pad;             /* QKV_ROPE: row pitch of v^T (multiple of 8, >= rows_per_batch) */
+} F5bGemmArgs;
+
+const char* f5b_last_error(void);
+int f5b_abi_version(void);
+
+/* C = epilogue(A[M,K] (bf16, row pitch lda) x W[N,K]^T (bf16, row pitch ldw)).
+ * Replaces every nn.Linear on the path: to_q/to_k/to_v (model/modules.py:452-454, fused to one N=3D GEMM with the
+ * rotary embedding of :470-480 in the epilogue), to_out + masked_fill + gated residual (:495-501, :635),
+ * FeedForward (:348-353; GELU-tanh :625; gated residual :639), InputEmbedding.proj (model/backbones/dit.py:95),
+ * AdaLayerNorm linears (:311, :332), TimestepEmbedding MLP (:727-731), proj_out (dit.py:231), ConvNeXtV2 / Vocos
+ * point-wise linears (:263-267). */
+int f5b_gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs* args, f5b_stream_t stream);
+
+/* out bf16[rows,D] = LayerNorm(x f32[rows,D], eps, no affine) * (1 + scale[b,:]) + shift[b,:]
+ * (AdaLayerNorm.forward model/modules.py:310-315, DiTBlock ff norm :637, AdaLayerNorm_Final :331-336).
+ * scale/shift element (b, c) at ptr[(b % batch_mod)*mod_bstride + c] (batch_mod 0: b); NULL/NULL = plain LayerNorm. */
+int f5b_ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod,
+                    void* out_bf16, int rows, int rows_per_batch, int D, float eps, f5b_stream_t stream);
+/* LayerNorm(D, affine w/b, eps) with f32 and/or bf16 outputs (either may be NULL; out_f32 may alias x)
+ * (Vocos backbone.norm / final_layer_norm). */
+int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
+                  f5b_stream_t stream);
+
+/* Non-causal softmax(QK^T/sqrt(64))V with a per-batch key length (AttnProcessor, model/modules.py:483-493,
+ * dropout_p = 0).  q,k bf16 [B*H, n, 64]; vt bf16 [B*H, 64, n_pad]; out bf16 [B*n, H*64] token-major.
+ * lens int32 [lens_mod] (kv length of batch b = lens[b % lens_mod]) or NULL (= n).  Query rows >= len are written
+ * as zeros (the reference zeroes them after to_out, :499-501). */
+int f5b_attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B,
+                 int H, int n, int n_pad, float scale, f5b_stream_t stream);
+
+/* ConvPositionEmbedding conv layer (model/modules.py:171-176,183-185): grouped Conv1d(k, groups, pad k/2) + Mish.
+ * x bf16 [B*n, D] token-major; wpk = weights packed by f5b_pack_convpos_weight; bias f32 [D].
+ * mode 0: out_bf16[B*n, D] = mish(conv(x)+bias);  mode 1: resid_f32[B*n, D] += mish(conv(x)+bias). */
+int f5b_convpos(const void* x_bf16, const void* wpk, const float* bias, void* out_bf16, float* resid_f32, int B, int n,
+                int D, int groups, int ksize, int mode, f5b_stream_t stream);
+/* w f32 [D, D/groups, ksize] (nn.Conv1d layout) -> bf16 [groups, ksize, NP, 64], NP = roundup(D/groups, 16). */
+int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream);
+size_t f5b_convpos_packed_elems(int D, int groups, int ksize);
+
+/* Depth-wise Conv1d(k=7, pad 3, groups=C) + bias + LayerNorm(C, eps, affine) -> bf16
+ * (ConvNeXtV2Block model/modules.py:259-262; Vocos ConvNeXtBlock).  x f32 [B*n, C] token-major. */
+int f5b_dwconv7_ln(const float* x, const float* w /*[C,7]*/, const float* b, const float* ln_w, const float* ln_b,
+                   void* out_bf16, int B, int n, int C, float eps, f5b_stream_t stream);
+
+/* GRN (model/modules.py:225-234) over h bf16 [B*n, C]: Gx = ||h||_2 over the n positions of each batch row,
+ * Nx = Gx / (mean_c Gx + 1e-6), out = gamma*(h*Nx) + beta + h -> bf16.  ws f32 [B*C] scratch. */
+int f5b_grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C,
+            f5b_stream_t stream);
+
+/* TextEmbedding front (model/backbones/dit.py:49-72): ids int64 [B, nt] (-1 padded) -> +1, truncate / pad with 0 to n,
+ * drop_text -> all 0, embedding lookup (table f32 [V+1, C]) + freqs_cis[pos] (pos f32 [4096, C]) -> f32 [B*n, C].
+ * mask_out (optional, uint8 [B*n]) = (token == 0) before drop_text, for text_mask_padding. */
+int f5b_text_lookup(const int64_t* ids, int nt, const float* table, const float* pos, float* out, uint8_t* mask_out,
+                    int B, int n, int C, int drop_text, int add_pos, f5b_stream_t stream);
+/* rows with mask != 0 are set to 0 (masked_fill, dit.py:74-75) */
+int f5b_mask_rows_f32(float* x, const uint8_t* mask, int rows, int C, f5b_stream_t stream);
+
+/* SinusPositionEmbedding(256) (model/modules.py:149-161): t f32 [M] -> bf16 [M,256] = cat(sin, cos)(1000 t f_k). */
+int f5b_time_sinus(const float* t, void* out_bf16, int M, f5b_stream_t stream);
+/* silu(x f32 [n]) -> bf16 */
+int f5b_silu_bf16(const float* x, void* out_bf16, int64_t n, f5b_stream_t stream);
+/* f32 [rows, cols] (pitch ld_in) -> bf16 columns [0, width) of a [rows, ld_out] matrix; columns >= cols are zero-filled
+ * (x may be NULL when cols == 0). */
+int f5b_pack_bf16(const float* x, int ld_in, void* out_bf16, int ld_out, int rows, int cols, int width, f5b_stream_t stream);
+
+/* CFG combine + Euler update (fn closure model/cfm.py:159-173 + torchdiffeq euler):
+ * v = pc + (pc - pu) * cfg;  y += dt * v;  y_bf16[rows, ld_bf] = bf16(y) (zero padded).  All f32 [rows, C].
+ * pu may be NULL (cfg_strength < 1e-5 -> v = pc).  vel_out (optional) receives v. */
+int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float dt, void* y_bf16, int ld_bf, float* vel_out,
+                  int rows, int C, f5b_stream_t stream);
+
+/* MelSpec "vocos" (model/modules.py:83-101): wav f32 [B, L] -> log-mel f32 [B, T, n_mels] (token-major, T = 1 + L/256):
+ * reflect-pad 512, periodic Hann(1024), |rFFT1024|, fb f32 [513, n_mels], log(clamp 1e-5). */
+int f5b_melspec(const float* wav, const float* fb, const int32_t* ranges /* [n_mels,2] nonzero rows [f0,f1) of each fb column */,
+                float* out, int B, int L, int n_mels, f5b_stream_t stream);
+
+/* Vocos ISTFTHead tail: head f32 [B*T, 1026] (mag logits | phase) -> exp/clip 1e2, cos/sin, irFFT1024, Hann window,
+ * overlap-add (hop 256), divide by the window envelope, trim 512 each side -> wav f32 [B, 256*(T-1)].
+ * frames_ws f32 [B*T, 1024] scratch. */
+int f5b_istft_head(const float* head, int ld, float* frames_ws, float* wav, int B, int T, f5b_stream_t stream);
+
+/* im2col for the Vocos embed Conv1d(n_mels -> C, k=7, pad 3): mel f32 [B, T, n_mels] -> bf16 [B*T, ld] (7*n_mels <= ld) */
+int f5b_im2col7(const float* mel, void* out_bf16, int B, int T, int n_mels, int ld, f5b_stream_t stream);
+
+/* ---- model-level drivers ----------------------------------------------------------------------------------- */
+
+/* All pointers are device pointers owned by the caller and must outlive the handle.
+ * "stack" pointers hold one tensor per DiT block, contiguous: [depth, ...]. */
+typedef struct F5bDitDesc {
+  int32_t dim, depth, heads, dim_head, ff_mult, mel_dim, text_dim, conv_layers, rope_heads, text_mask_padding;
+  int32_t convpos_kernel, convpos_groups, vocab_rows;
+  /* TimestepEmbedding (model/modules.py:721-731) */
+  const void* time_w0; const float* time_b0;   /* bf16 [D,256] */
+  const void* time_w2; const float* time_b2;   /* bf16 [D,D]   */
+  /* all AdaLayerNorm linears stacked: rows [i*6D, (i+1)*6D) = block i attn_norm.linear, last 2D rows = norm_out.linear */
+  const void* mod_w; const float* mod_b;       /* bf16 [depth*6D + 2D, D] */
+  /* TextEmbedding (model/backbones/dit.py:32-79) */
+  const float* text_table;                     /* f32 [vocab_rows, text_dim] */
+  const float* text_pos;                       /* f32 [4096, text_dim] */
+  const float* tb_dw_w; const float* tb_dw_b;  /* f32 [L, text_dim, 7], [L, text_dim] */
+  const float* tb_ln_w; const float* tb_ln_b;  /* f32 [L, text_dim] */
+  const void* tb_pw1_w; const float* tb_pw1_b; /* bf16 [L, 2T, T], f32 [L, 2T] */
+  const float* tb_grn_g; const float* tb_grn_b;/* f32 [L, 2T] */
+  const void* tb_pw2_w; const float* tb_pw2_b; /* bf16 [L, T, 2T], f32 [L, T] */
+  /* InputEmbedding (dit.py:85-97): proj weight split by source, K padded */
+  const void* in_wx;                           /* bf16 [D, 128]  (x part, mel_dim cols used) */
+  const void* in_wct;                          /* bf16 [D, 128 + T] (cond part padded to 128 | text part) */
+  const float* in_b;                           /* f32 [D] */
+  const void* cp_w1; const float* cp_b1;       /* packed grouped-conv weights (f5b_pack_convpos_weight) */
+  const void* cp_w2; const float* cp_b2;
+  /* DiT blocks */
+  const void* qkv_w; const float* qkv_b;       /* bf16 [depth, 3D, D], f32 [depth, 3D] (q | k | v) */
+  const void* out_w; const float* out_b;       /* bf16 [depth, D, D] */
+  const void* ff1_w; const float* ff1_b;       /* bf16 [depth, F, D], F = ff_mult*D */
+  const void* ff2_w; const float* ff2_b;       /* bf16 [depth, D, F] */
+  const void* proj_w; const float* proj_b;     /* bf16 [mel_dim, D], f32 [mel_dim] */
+} F5bDitDesc;
+
+typedef struct F5bDit F5bDit;
+
+int f5b_dit_create(const F5bDitDesc* desc, F5bDit** out);
+void f5b_dit_destroy(F5bDit* h);
+/* bytes of f32/bf16 scratch needed for a forward over `rows` = B*n token rows */
+size_t f5b_dit_workspace_bytes(const F5bDit* h, int B, int n);
+
+/* time MLP + every AdaLN modulation for M time values at once (t identical for all batch rows in CFM.sample, so the
+ * whole schedule is one GEMM): t f32 [M] -> mod f32 [M, depth*6D + 2D].  ws: f5b_dit_modulation_ws_bytes. */
+int f5b_dit_modulation(const F5bDit* h, const float* t, int M, float* mod, void* ws, f5b_stream_t stream);
+size_t f5b_dit_modulation_ws_bytes(const F5bDit* h, int M);
+
+/* TextEmbedding.forward -> f32 [B*n, text_dim].  ws: f5b_dit_text_ws_bytes. */
+int f5b_dit_text_embed(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, float* out, void* ws,
+                       f5b_stream_t stream);
+size_t f5b_dit_text_ws_bytes(const F5bDit* h, int B, int n);
+
+/* Step-invariant part of InputEmbedding.proj: c0 f32 [B*n, D] = [cond | text_embed] W_ct^T + bias
+ * (cond f32 [B*n, mel_dim] or NULL for drop_audio_cond).  ws: B*n*(128+T)*2 bytes. */
+int f5b_dit_input_const(const F5bDit* h, const float* cond, const float* text_embed, int B, int n, float* c0, void* ws,
+                        f5b_stream_t stream);
+
+/* One DiT.forward (dit.py:185-233) over Bf fused batch rows (e.g. cond rows then uncond rows of a CFG pair).
+ *   x_bf16   bf16 [Bx*n, 128]   ODE state (zero padded); fused row b reads state row b % Bx
+ *   c0       f32  [Bf*n, D]     f5b_dit_input_const output for each fused row
+ *   mod      f32  [rows, depth*6D+2D] modulation; fused row b uses mod + (b % Bx) * mod_bstride (0 = shared)
+ *   lens     int32 [Bx] or NULL key-padding lengths (mask), shared by the fused halves
+ *   rope     f32  [n, 32, 2]
+ *   pred     f32  [Bf*n, mel_dim]
+ */
+int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0, int Bf, int n, const float* mod,
+                    int64_t mod_bstride, const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes,
+                    f5b_stream_t stream);
+
+/* rope table for n positions, dim_head 64: f32 [n, 32, 2] = (cos, sin)(pos * 10000^(-2j/64))
+ * (x_transformers RotaryEmbedding.forward_from_seq_len, call site dit.py:215) */
+int f5b_rope_table(float* out, int n, f5b_stream_t stream);
+
+/* Vocos (third-party `vocos`, charactr/vocos-mel-24khz; call sites infer/f5tts_wrapper.py:524, infer/utils_infer.py:488) */
+typedef struct F5bVocosDesc {
+  int32_t n_mels, dim, intermediate, num_layers, n_fft, hop;
+  const void* embed_w; const float* embed_b;     /* bf16 [dim, ld_embed] im2col layout (k-major: col = k*n_mels + c) */
+  int32_t ld_embed;
+  const float* norm_w; const float* norm_b;      /* f32 [dim] */
+  const float* dw_w; const float* dw_b;          /* f32 [L, dim, 7], [L, dim] */
+  const float* ln_w; const float* ln_b;          /* f32 [L, dim] */
+  const void* pw1_w; const float* pw1_b;         /* bf16 [L, I, dim], f32 [L, I] */
+  const void* pw2_w; const float* pw2_b;         /* bf16 [L, dim, I], f32 [L, dim] */
+  const float* gamma;                            /* f32 [L, dim] */
+  const float* fln_w; const float* fln_b;        /* f32 [dim] */
+  const void* head_w; const float* head_b;       /* bf16 [n_fft+2, dim], f32 [n_fft+2] */
+} F5bVocosDesc;
+typedef struct F5bVocos F5bVocos;
+int f5b_vocos_create(const F5bVocosDesc* desc, F5bVocos** out);
+void f5b_vocos_destroy(F5bVocos* h);
+size_t f5b_vocos_workspace_bytes(const F5bVocos* h, int B, int T);
+/* mel f32 [B, T, n_mels] (token-major) -> wav f32 [B, hop*(T-1)] */
+int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* wav, void* ws, size_t ws_bytes,
+                     f5b_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F5B200_H_ */
