@@ -1,0 +1,286 @@
+"""F5TTSWrapper with the reference's public surface (/root/reference/src/f5_tts/infer/f5tts_wrapper.py:28-621):
+__init__ / preprocess_reference / generate / get_current_audio_length and the attributes its callers touch
+(ref_audio_processed, ref_text, ref_audio_len, target_sample_rate, device, use_duration_predictor, model, vocoder).
+
+Differences, all host-side and documented in DESIGN.md: no network / hydra / pydub / Whisper in this image, so the checkpoint
+path is optional (random init without it), model configs are constants, reference audio may be given as a tensor, and the
+auto-transcription branch raises.  `generate(..., batch_chunks=True)` (extension) runs all text chunks of a
+request as ONE ragged sample() batch instead of the reference's serial B=1 loop."""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..model import CFM, DiT
+from ..model.utils import get_tokenizer
+from .utils_infer import chunk_text, load_checkpoint, load_vocoder, resolve_arch
+
+_CUSTOM_TRANS = str.maketrans({";": ",", "“": '"', "”": '"', "‘": "'", "’": "'"})
+
+
+def convert_char_to_pinyin(text_list, polyphone=True):
+    """model/utils.py:243-284.  With jieba + pypinyin present the reference algorithm runs unchanged; without them (this
+    image) non-CJK text takes the same character-level path the reference produces for Latin / Vietnamese script."""
+    try:
+        import jieba
+        from pypinyin import Style, lazy_pinyin
+    except ImportError:
+        jieba = None
+    out = []
+    for text in text_list:
+        text = text.translate(_CUSTOM_TRANS)
+        if jieba is None:
+            if any("㄀" <= c <= "鿿" for c in text):
+                raise RuntimeError("Chinese text needs jieba + pypinyin, which are not installed in this image")
+            out.append(list(text))
+            continue
+        char_list = []
+        for seg in jieba.cut(text):
+            seg_byte_len = len(bytes(seg, "UTF-8"))
+            if seg_byte_len == len(seg):
+                if char_list and seg_byte_len > 1 and char_list[-1] not in " :'\"":
+                    char_list.append(" ")
+                char_list.extend(seg)
+            elif polyphone and seg_byte_len == 3 * len(seg):
+                seg_ = lazy_pinyin(seg, style=Style.TONE3, tone_sandhi=True)
+                for i, c in enumerate(seg):
+                    if "㄀" <= c <= "鿿":
+                        char_list.append(" ")
+                    char_list.append(seg_[i])
+            else:
+                for c in seg:
+                    if ord(c) < 256:
+                        char_list.extend(c)
+                    elif "㄀" <= c <= "鿿":
+                        char_list.append(" ")
+                        char_list.extend(lazy_pinyin(c, style=Style.TONE3, tone_sandhi=True))
+                    else:
+                        char_list.append(c)
+        out.append(char_list)
+    return out
+
+
+def _read_wav(path: str):
+    """PCM wav -> (float32 [channels, samples], sample_rate) without torchaudio backends."""
+    try:
+        import torchaudio
+        return torchaudio.load(path)
+    except Exception:  # noqa: BLE001
+        import wave
+        with wave.open(path, "rb") as w:
+            sr, ch, sw, nf = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(nf)
+        if sw == 2:
+            a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif sw == 4:
+            a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif sw == 1:
+            a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError(f"unsupported wav sample width {sw}")
+        return torch.from_numpy(a.reshape(-1, ch).T.copy()), sr
+
+
+def _trim_silence_edges(audio: torch.Tensor, sr: int, threshold_db: float = -42.0) -> torch.Tensor:
+    """_remove_silence_edges (f5tts_wrapper.py:356-377) restated on a tensor: drop leading / trailing 1 ms... 10 ms windows whose
+    level is below the threshold (pydub measures dBFS on chunks)."""
+    x = audio[0]
+    win = max(1, sr // 100)
+    nwin = x.numel() // win
+    if nwin == 0:
+        return audio
+    rms = x[: nwin * win].reshape(nwin, win).square().mean(dim=1).sqrt()
+    db = 20.0 * torch.log10(rms.clamp(min=1e-10))
+    loud = (db > threshold_db).nonzero()
+    if loud.numel() == 0:
+        return audio
+    s, e = int(loud[0]) * win, (int(loud[-1]) + 1) * win
+    return audio[:, s:e]
+
+
+class F5TTSWrapper:
+    def __init__(self, model_name: str = "F5TTS_v1_Base", ckpt_path: Optional[str] = None, vocab_file: Optional[str] = None,
+                 vocoder_name: str = "vocos", use_local_vocoder: bool = False, vocoder_path: Optional[str] = None,
+                 device: Optional[str] = None, hf_cache_dir: Optional[str] = None, target_sample_rate: int = 24000,
+                 n_mel_channels: int = 100, hop_length: int = 256, win_length: int = 1024, n_fft: int = 1024,
+                 ode_method: str = "euler", use_ema: bool = True, use_duration_predictor: bool = False,
+                 vocab_char_map: Optional[dict] = None):
+        if device is None:
+            device = "cuda"
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("eraxvif5tts_b200 runs on a B200 only (device must be cuda); there is no CPU path")
+        self.device = device
+        self.target_sample_rate, self.n_mel_channels = target_sample_rate, n_mel_channels
+        self.hop_length, self.win_length, self.n_fft = hop_length, win_length, n_fft
+        self.mel_spec_type = vocoder_name
+        self.ode_method = ode_method
+        self.use_duration_predictor = use_duration_predictor
+        arch = resolve_arch(model_name)
+        if vocab_char_map is not None:
+            self.vocab_char_map, vocab_size = vocab_char_map, len(vocab_char_map)
+        elif vocab_file is not None:
+            self.vocab_char_map, vocab_size = get_tokenizer(vocab_file, "custom")
+        else:
+            raise ValueError("vocab_file (or vocab_char_map) is required: the reference's bundled vocab.txt is not shipped here")
+        self.model = CFM(
+            transformer=DiT(**arch, text_num_embeds=vocab_size, mel_dim=n_mel_channels),
+            mel_spec_kwargs=dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length, n_mel_channels=n_mel_channels,
+                                 target_sample_rate=target_sample_rate, mel_spec_type=vocoder_name),
+            odeint_kwargs=dict(method=ode_method), vocab_char_map=self.vocab_char_map).to(self.device)
+        if ckpt_path is not None:
+            load_checkpoint(self.model, ckpt_path, self.device, use_ema=use_ema)
+        self.has_duration_predictor = False  # DurationPredictor is out of scope
+        if self.use_duration_predictor:
+            print("Warning: Duration predictor requested but not found in model. Using fallback duration calculation.")
+            self.use_duration_predictor = False
+        self.vocoder = load_vocoder(vocoder_name=vocoder_name, is_local=use_local_vocoder or vocoder_path is not None,
+                                    local_path=vocoder_path or "", device=self.device, hf_cache_dir=hf_cache_dir)
+        self.ref_audio_processed = None
+        self.ref_text = None
+        self.ref_audio_len = None
+        self.target_rms = 0.1
+        self.cross_fade_duration = 0.15
+        self.nfe_step = 32
+        self.cfg_strength = 2.0
+        self.sway_sampling_coef = -1.0
+        self.speed = 1.0
+        self.fix_duration = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def preprocess_reference(self, ref_audio_path, ref_text: str = "", clip_short: bool = True, sample_rate: Optional[int] = None):
+        """f5tts_wrapper.py:256-354.  `ref_audio_path` may also be a float tensor / ndarray [samples] or [channels, samples]
+        (then pass `sample_rate`)."""
+        if isinstance(ref_audio_path, (str, os.PathLike)):
+            audio, sr = _read_wav(str(ref_audio_path))
+        else:
+            audio = torch.as_tensor(ref_audio_path, dtype=torch.float32)
+            if audio.ndim == 1:
+                audio = audio.unsqueeze(0)
+            sr = sample_rate or self.target_sample_rate
+        audio = audio.float()
+        if audio.shape[0] > 1:
+            audio = torch.mean(audio, dim=0, keepdim=True)
+        if clip_short and audio.shape[-1] > 12 * sr:  # the reference clips at silences found by pydub; we clip hard at 12 s
+            audio = audio[:, : 12 * sr]
+        audio = _trim_silence_edges(audio, sr)
+        audio = torch.cat((audio, torch.zeros(1, int(0.05 * sr))), dim=-1)  # + AudioSegment.silent(duration=50)
+        if not ref_text.strip():
+            raise RuntimeError("auto-transcription needs the Whisper pipeline, which is not available offline; pass ref_text")
+        if not ref_text.endswith(". ") and not ref_text.endswith("。"):
+            ref_text += " " if ref_text.endswith(".") else ". "
+        rms = torch.sqrt(torch.mean(torch.square(audio)))
+        if rms < self.target_rms:
+            audio = audio * self.target_rms / rms
+        if sr != self.target_sample_rate:
+            import torchaudio
+            audio = torchaudio.transforms.Resample(sr, self.target_sample_rate)(audio)
+        audio = audio.to(self.device)
+        self.ref_audio_processed = audio
+        self.ref_text = ref_text
+        self.ref_audio_len = audio.shape[-1] // self.hop_length
+        return audio, ref_text
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _chunk_duration(self, text_batch: str, speed: float, fix_duration):
+        local_speed = 0.3 if len(text_batch.encode("utf-8")) < 10 else speed
+        if fix_duration is not None:
+            return int(fix_duration * self.target_sample_rate / self.hop_length)
+        ref_text_len = len(self.ref_text.encode("utf-8"))
+        gen_text_len = len(text_batch.encode("utf-8"))
+        return self.ref_audio_len + int(self.ref_audio_len / ref_text_len * gen_text_len / local_speed)
+
+    def generate(self, text: str, output_path: Optional[str] = None, nfe_step: Optional[int] = None,
+                 cfg_strength: Optional[float] = None, sway_sampling_coef: Optional[float] = None, speed: Optional[float] = None,
+                 fix_duration: Optional[float] = None, cross_fade_duration: Optional[float] = None,
+                 use_duration_predictor: Optional[bool] = None, return_numpy: bool = False, return_spectrogram: bool = False,
+                 batch_chunks: bool = False, seed: Optional[int] = None):
+        """f5tts_wrapper.py:408-607."""
+        if self.ref_audio_processed is None or self.ref_text is None:
+            raise ValueError("Reference audio not preprocessed. Call preprocess_reference() first.")
+        nfe_step = nfe_step if nfe_step is not None else self.nfe_step
+        cfg_strength = cfg_strength if cfg_strength is not None else self.cfg_strength
+        sway_sampling_coef = sway_sampling_coef if sway_sampling_coef is not None else self.sway_sampling_coef
+        speed = speed if speed is not None else self.speed
+        fix_duration = fix_duration if fix_duration is not None else self.fix_duration
+        cross_fade_duration = cross_fade_duration if cross_fade_duration is not None else self.cross_fade_duration
+
+        audio_len = self.ref_audio_processed.shape[-1] / self.target_sample_rate
+        max_chars = int(len(self.ref_text.encode("utf-8")) / audio_len * (22 - audio_len))
+        text_batches = chunk_text(text, max_chars=max_chars)
+        if not text_batches:
+            raise RuntimeError("No audio generated")
+        rms = torch.sqrt(torch.mean(torch.square(self.ref_audio_processed)))
+        generated_waves, spectrograms = [], []
+
+        def finish(gen_mel):  # gen_mel [1, n, mel] (reference part still attached)
+            g = gen_mel.to(torch.float32)[:, self.ref_audio_len:, :].permute(0, 2, 1)
+            wave = self.vocoder.decode(g)
+            if rms < self.target_rms:
+                wave = wave * rms / self.target_rms
+            generated_waves.append(wave.squeeze().cpu().numpy())
+            if return_spectrogram or output_path is not None:
+                spectrograms.append(g.squeeze().cpu().numpy())
+
+        with torch.inference_mode():
+            if batch_chunks and len(text_batches) > 1:
+                texts = convert_char_to_pinyin([self.ref_text + tb for tb in text_batches])
+                durs = torch.tensor([self._chunk_duration(tb, speed, fix_duration) for tb in text_batches], dtype=torch.long)
+                cond = self.ref_audio_processed.expand(len(text_batches), -1)
+                generated, _ = self.model.sample(cond=cond, text=texts, duration=durs, steps=nfe_step, cfg_strength=cfg_strength,
+                                                 sway_sampling_coef=sway_sampling_coef, seed=seed, return_trajectory=False)
+                cond_frames = self.ref_audio_len + 1  # mel frames of the reference (1 + L // hop)
+                durs_eff = torch.maximum(durs, torch.tensor([len(t) for t in texts]).clamp(min=cond_frames) + 1)  # cfm.py:132-136
+                for i in range(len(text_batches)):
+                    finish(generated[i:i + 1, : int(min(durs_eff[i], generated.shape[1]))])
+            else:
+                for text_batch in text_batches:
+                    final_text_list = convert_char_to_pinyin([self.ref_text + text_batch])
+                    duration = self._chunk_duration(text_batch, speed, fix_duration)
+                    generated, _ = self.model.sample(cond=self.ref_audio_processed, text=final_text_list, duration=duration,
+                                                     steps=nfe_step, cfg_strength=cfg_strength,
+                                                     sway_sampling_coef=sway_sampling_coef, seed=seed, return_trajectory=False)
+                    finish(generated)
+
+        # cross-fade (f5tts_wrapper.py:542-575)
+        if cross_fade_duration <= 0:
+            final_wave = np.concatenate(generated_waves)
+        else:
+            final_wave = generated_waves[0]
+            for i in range(1, len(generated_waves)):
+                prev_wave, next_wave = final_wave, generated_waves[i]
+                cfs = min(int(cross_fade_duration * self.target_sample_rate), len(prev_wave), len(next_wave))
+                if cfs <= 0:
+                    final_wave = np.concatenate([prev_wave, next_wave])
+                    continue
+                fade_out, fade_in = np.linspace(1, 0, cfs), np.linspace(0, 1, cfs)
+                overlap = prev_wave[-cfs:] * fade_out + next_wave[:cfs] * fade_in
+                final_wave = np.concatenate([prev_wave[:-cfs], overlap, next_wave[cfs:]])
+        combined_spectrogram = np.concatenate(spectrograms, axis=1) if spectrograms else None
+        if output_path is not None:
+            output_dir = os.path.dirname(output_path)
+            if output_dir and not os.path.exists(output_dir):
+                os.makedirs(output_dir)
+            _write_wav(output_path, final_wave, self.target_sample_rate)
+            if not return_numpy:
+                return output_path
+        if return_spectrogram:
+            return final_wave, self.target_sample_rate, combined_spectrogram
+        return final_wave, self.target_sample_rate
+
+    def get_current_audio_length(self):
+        if self.ref_audio_processed is None:
+            return 0
+        return self.ref_audio_processed.shape[-1] / self.target_sample_rate
+
+
+def _write_wav(path: str, wave_f32: np.ndarray, sr: int):
+    import wave
+    pcm = (np.clip(wave_f32, -1.0, 1.0) * 32767.0).astype("<i2")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(pcm.tobytes())

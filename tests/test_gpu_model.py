@@ -1,0 +1,165 @@
+"""GPU parity tests of the product path (through the C ABI) against the CPU oracle and the golden vectors that the REAL
+reference modules produced (tests/golden/, generator oracle/gen_golden.py).
+
+Tolerances (BASELINE.json north_star): bf16 tensor-core path -> max |error| <= 2e-2 on the DiT velocity field,
+mean |error| <= 1e-2 on the final log-mel.  The oracle is fp32; weights are bf16-exact so only arithmetic differs."""
+import pytest
+import torch
+
+from oracle import f5_oracle as O
+from oracle.weights import synthetic_inputs
+
+from helpers import build_cfm, build_vocos, maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL = 2e-2
+MEL_MEAN_TOL = 1e-2
+
+
+def _cfg(d):
+    return O.DiTConfig(**d)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "tiny_v1"])
+def test_dit_forward_matches_reference_golden(golden, tag):
+    g = golden(f"dit_{tag}.pt")
+    cfg = _cfg(g["cfg"])
+    model, sd = build_cfm(cfg, g["seed"])
+    tr = model.transformer
+    n = g["x"].shape[1]
+    eng = tr.engine()
+    te = eng.text_embed(g["text"], n, False)
+    tu = eng.text_embed(g["text"], n, True)
+    torch.cuda.synchronize()
+    assert maxabs(te, g["text_cond"]) < 3e-2 * max(1.0, float(g["text_cond"].abs().max()))
+    assert maxabs(tu, g["text_unc"]) < 3e-2 * max(1.0, float(g["text_unc"].abs().max()))
+    dev = "cuda"
+    for name, (da, dt, m) in dict(cond=(False, False, g["mask"]), uncond=(True, True, g["mask"]), nomask=(False, False, None)).items():
+        out = tr(x=g["x"].to(dev), cond=g["cond"].to(dev), text=g["text"].to(dev), time=g["time"].to(dev), drop_audio_cond=da,
+                 drop_text=dt, mask=None if m is None else m.to(dev))
+        torch.cuda.synchronize()
+        ref = g["out"][name]
+        assert out.shape == ref.shape
+        assert torch.isfinite(out).all()
+        assert maxabs(out, ref) <= VEL_TOL, (name, maxabs(out, ref))
+
+
+def _ref_noise(duration, mel_dim, seed):
+    y0 = []
+    for dur in duration.tolist():
+        torch.manual_seed(seed)
+        y0.append(torch.randn(int(dur), mel_dim))
+    return torch.nn.utils.rnn.pad_sequence(y0, padding_value=0, batch_first=True)
+
+
+@pytest.mark.parametrize("tag", ["tiny_b2", "tiny_b1", "tiny_mid"])
+def test_cfm_sample_matches_reference_golden(golden, tag):
+    g = golden(f"sample_{tag}.pt")
+    cfg = _cfg(g["cfg"])
+    model, sd = build_cfm(cfg, g["seed"], method=g["method"])
+    noise = _ref_noise(g["duration"], cfg.mel_dim, g["sample_seed"])
+    out, traj = model.sample(cond=g["cond"].cuda(), text=g["text"].cuda(), duration=g["duration"].cuda(), lens=g["lens"].cuda(),
+                             steps=g["steps"], cfg_strength=g["cfg_strength"], sway_sampling_coef=g["sway"], seed=g["sample_seed"],
+                             noise=noise)
+    torch.cuda.synchronize()
+    assert out.shape == g["out"].shape and traj.shape[0] == g["steps"] + 1
+    assert maxabs(traj[0], noise) == 0.0
+    # first ODE state: one velocity evaluation scaled by dt
+    assert maxabs(traj[1], g["traj_1"]) <= VEL_TOL
+    err = (out.cpu() - g["out"]).abs()
+    assert float(err.mean()) <= MEL_MEAN_TOL, float(err.mean())
+    assert float(err.max()) <= 0.15, float(err.max())
+
+
+@pytest.mark.parametrize("name,cfg,B,n,ragged", [
+    ("base_width", O.DiTConfig(depth=2), 2, 200, True),
+    ("small_width", O.DiTConfig(dim=768, heads=12, depth=2), 2, 150, True),
+    ("v1_allheads", O.DiTConfig(depth=1, pe_attn_head=None, text_mask_padding=True), 1, 130, False),
+])
+def test_dit_forward_real_widths_vs_oracle(name, cfg, B, n, ragged):
+    model, sd = build_cfm(cfg, 0)
+    cond, text, _, _ = synthetic_inputs(cfg, B, n, n, seed=5)
+    cond[:, n // 2:] = 0
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, n, cfg.mel_dim, generator=g)
+    time = torch.tensor(0.41)
+    mask = None
+    if ragged:
+        lens = torch.tensor([n, n - 37][:B])
+        mask = torch.arange(n)[None, :] < lens[:, None]
+    for da, dt in ((False, False), (True, True)):
+        ref = O.dit_forward(sd, cfg, x, cond, text, time, da, dt, mask)
+        out = model.transformer(x=x.cuda(), cond=cond.cuda(), text=text.cuda(), time=time.cuda(), drop_audio_cond=da, drop_text=dt,
+                                mask=None if mask is None else mask.cuda())
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        assert maxabs(out, ref) <= VEL_TOL * max(1.0, float(ref.abs().max())), (name, da, maxabs(out, ref), float(ref.abs().max()))
+
+
+def test_cfm_sample_base_width_fused_cfg_vs_oracle():
+    cfg = O.DiTConfig(depth=2)
+    model, sd = build_cfm(cfg, 0)
+    cond, text, duration, lens = synthetic_inputs(cfg, 2, 60, [150, 131], seed=1234)
+    noise = _ref_noise(duration, cfg.mel_dim, 0)
+    ref_out, ref_traj = O.cfm_sample(sd, cfg, cond, text, duration, lens=lens, steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=0)
+    out, traj = model.sample(cond=cond.cuda(), text=text.cuda(), duration=duration.cuda(), lens=lens.cuda(), steps=4, cfg_strength=2.0,
+                             sway_sampling_coef=-1.0, seed=0, noise=noise)
+    torch.cuda.synchronize()
+    assert maxabs(traj[1], ref_traj[1]) <= VEL_TOL
+    err = (out.cpu() - ref_out).abs()
+    assert float(err.mean()) <= MEL_MEAN_TOL and float(err.max()) <= 0.15, (float(err.mean()), float(err.max()))
+
+
+def test_melspec_matches_reference_golden(golden):
+    from eraxvif5tts_b200.model import MelSpec
+    g = golden("melspec.pt")
+    mel = MelSpec().cuda()(g["wav"].cuda())
+    torch.cuda.synchronize()
+    assert mel.shape == g["mel"].shape
+    assert maxabs(mel, g["mel"]) < 2e-3
+    assert float((mel.cpu() - g["mel"]).abs().mean()) < 1e-4
+
+
+@pytest.mark.parametrize("vc,T", [(O.VocosConfig.tiny(), 12), (O.VocosConfig(), 40)])
+def test_vocos_decode_vs_oracle(vc, T):
+    voc, vsd = build_vocos(vc)
+    g = torch.Generator().manual_seed(2)
+    mel = (torch.randn(2, vc.n_mels, T, generator=g) * 2.0 - 1.5).clamp(-11.5, 5.0)
+    ref = O.vocos_decode(vsd, vc, mel)
+    wav = voc.decode(mel.cuda())
+    torch.cuda.synchronize()
+    assert wav.shape == ref.shape == (2, 256 * (T - 1))
+    assert torch.isfinite(wav).all()
+    scale = float(ref.abs().max())
+    assert maxabs(wav, ref) <= 5e-2 * scale, (maxabs(wav, ref), scale)
+    assert float((wav.cpu() - ref).abs().mean()) <= 1e-2 * scale
+
+
+def test_wrapper_generate_end_to_end(tmp_path):
+    """F5TTSWrapper.generate: chunking, duration rule, sample, vocoder, rms rescale, cross-fade; serial vs batched chunks."""
+    from eraxvif5tts_b200.infer import F5TTSWrapper
+    yaml_path = tmp_path / "custom_tiny.yaml"
+    yaml_path.write_text("model:\n  backbone: DiT\n  arch:\n    dim: 128\n    depth: 2\n    heads: 2\n    ff_mult: 2\n    text_dim: 64\n"
+                         "    text_mask_padding: False\n    conv_layers: 2\n    pe_attn_head: 1\n")
+    vocab = {c: i for i, c in enumerate(" abcdefghijklmnopqrstuvwxyz.,!?")}
+    torch.manual_seed(0)
+    w = F5TTSWrapper(model_name=str(yaml_path), vocab_char_map=vocab, device="cuda")
+    # give the zero-initialised AdaLN / proj_out tensors values so the model output is not identically zero
+    with torch.no_grad():
+        for p in w.model.parameters():
+            if float(p.abs().max()) == 0.0:
+                p.normal_(0, 0.02)
+    w.model.transformer.invalidate()
+    with pytest.raises(ValueError):
+        w.generate("hello")
+    ref = 0.05 * torch.randn(24000 * 2)
+    w.preprocess_reference(ref, "this is a reference.", sample_rate=24000)
+    assert w.ref_audio_len == w.ref_audio_processed.shape[-1] // 256
+    text = "the quick brown fox jumps over the lazy dog. " * 6
+    wave, sr = w.generate(text, nfe_step=2, return_numpy=True, seed=0)
+    assert sr == 24000 and wave.ndim == 1 and wave.size > 24000 and bool((wave == wave).all())
+    wave_b, _ = w.generate(text, nfe_step=2, return_numpy=True, seed=0, batch_chunks=True)
+    assert abs(wave_b.size - wave.size) <= 256 * 4
+    out = w.generate("short text here.", output_path=str(tmp_path / "o.wav"), nfe_step=2)
+    assert out.endswith("o.wav") and (tmp_path / "o.wav").stat().st_size > 1000

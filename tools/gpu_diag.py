@@ -165,7 +165,10 @@ def small_kernels():
     B, n, D = 3, 77, 1024
     x = torch.randn(B * n, D, device=dev, generator=g) * 2 + 0.3
     mod = torch.randn(B, 6 * D, device=dev, generator=g) * 0.2
-    out = ops.ln_modulate(x, mod[:, D:], mod[:, 0:], 6 * D, 0, n)
+    out = torch.empty(B * n, D, dtype=bf16, device=dev)
+    lib = L.load()
+    L.check(lib.f5b_ln_modulate(x.data_ptr(), mod.data_ptr() + 4 * D, mod.data_ptr(), 6 * D, 0, out.data_ptr(), B * n, n, D, 1e-6,
+                                L.stream()), "f5b_ln_modulate")
     ref = F.layer_norm(x, (D,), eps=1e-6).view(B, n, D) * (1 + mod[:, None, D:2 * D]) + mod[:, None, :D]
     report("ln_modulate", rel=relerr(out.view(B, n, D), ref))
     # dwconv + LN
