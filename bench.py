@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the F5-TTS hot path (BASELINE.json: mel-frames/s and RTF, F5TTS_Base, NFE=32, CFG).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one full pass of the hot path over one batch of synthetic utterances: CFM.sample (text embedding, 32 Euler steps x
+{cond, uncond} DiT forwards fused as one 2B batch, CFG + Euler updates) + Vocos decode of the generated frames.
+  value : total mel frames (ref + gen, what the DiT processes) per second, inputs already resident in HBM (CUDA events).
+  e2e   : the same metric through the public API with HOST buffers (pinned reference waveform + token ids -> device, MelSpec,
+          sample, vocoder, audio back to the host), host<->device copies inside the timed region.
+  roofline     : dominant kernel class, algorithmic FLOPs / CUDA-event time measured live over the timed steps.
+  cpu_baseline : the oracle (CPU fp32 restatement of the reference) timed on this box's host cores on a bounded sample.
+--impl reference times the reference's CPU implementation of the path (the oracle port; /root/reference cannot travel to the GPU
+box) with all host threads on the same workload / metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (arch kwargs, batch, ref frames, total frames, description)  — SURVEY.md §8d
+    "cfg2": (dict(dim=1024, depth=22, heads=16), 16, 563, 1875, "F5TTS_Base bf16 batch=16 x 20 s utterances (ref 6 s + gen 14 s), NFE=32 sway -1 CFG 2"),
+    "cfg1": (dict(dim=1024, depth=22, heads=16), 1, 376, 940, "F5TTS_Base one ~10 s utterance (ref 376 + gen 564 frames), NFE=32 Euler CFG 2"),
+    "cfg3": (dict(dim=768, depth=12, heads=12), 32, 750, 1376, "F5TTS_Small pruned to 12 blocks, batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
+}
+NFE, CFG, SWAY = 32, 2.0, -1.0
+
+
+def dit_flops_per_forward(cfg, B, n):
+    """algorithmic FLOPs of one DiT.forward over B x n tokens: 2MNK per GEMM, 4 n D per token attention."""
+    D, F = cfg.dim, cfg.ff_mult * cfg.dim
+    per_tok_block = 2 * D * 3 * D + 2 * D * D + 2 * 2 * D * F + 4 * n * D
+    cpg = D // 16
+    outside = 2 * (2 * cfg.mel_dim + cfg.text_dim) * D + 2 * 2 * D * cpg * 31 + 2 * D * cfg.mel_dim
+    return B * n * (cfg.depth * per_tok_block + outside)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons during the timed region (NVML; nvidia-smi CLI as a fallback)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        while not self.stop_flag:
+            try:
+                if self.nv is not None:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit and nm != "gpu_idle":
+                            self.reasons.add(nm)
+                else:
+                    import subprocess
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.sw_power_cap,"
+                                        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(int(o[0]))
+                    self.max_mhz = int(o[1])
+                    for nm, v in zip(("sw_power_cap", "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"), o[2:]):
+                        if "Active" in v and "Not" not in v:
+                            self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+class Arch:
+    """model.arch constants of the workload (configs/F5TTS_Base.yaml:25-34 / F5TTS_Small.yaml)"""
+    ff_mult, mel_dim, text_dim, conv_layers, text_num_embeds, pe_attn_head, text_mask_padding = 2, 100, 512, 4, 2545, 1, False
+
+    def __init__(self, dim, depth, heads):
+        self.dim, self.depth, self.heads = dim, depth, heads
+
+
+def make_inputs(arch, B, ref_frames, total, seed):
+    """SURVEY.md §8d synthetic workload: log-mel-like reference mel / 0.1*randn reference audio, random token ids (-1 padded)."""
+    g = torch.Generator().manual_seed(seed)
+    cond = (torch.randn(B, ref_frames, arch.mel_dim, generator=g) * 2.0 - 1.5).clamp(-11.5, 5.0)
+    nt = max(2, int(0.16 * total))
+    text = torch.randint(0, arch.text_num_embeds, (B, nt), generator=g)
+    for b in range(B):
+        text[b, max(1, int(nt * (0.6 + 0.4 * (b + 1) / B))):] = -1
+    duration = torch.full((B,), total, dtype=torch.long)
+    lens = torch.full((B,), ref_frames, dtype=torch.long)
+    wav = 0.1 * torch.randn(B, 256 * (ref_frames - 1), generator=g)  # MelSpec gives 1 + L // 256 = ref_frames frames
+    return cond, text, duration, lens, wav
+
+
+def build_product_models(arch, dev):
+    """random-init F5TTS DiT + Vocos exactly as the reference constructs them (torch default init), with the zero-initialised
+    AdaLN / proj_out tensors re-drawn N(0, 0.02) so the network output is not identically zero (checkpoints are not available)."""
+    from eraxvif5tts_b200.model import CFM, DiT
+    from eraxvif5tts_b200.vocoder import Vocos
+    torch.manual_seed(0)
+    tr = DiT(dim=arch.dim, depth=arch.depth, heads=arch.heads, ff_mult=arch.ff_mult, mel_dim=arch.mel_dim, text_num_embeds=arch.text_num_embeds,
+             text_dim=arch.text_dim, text_mask_padding=arch.text_mask_padding, conv_layers=arch.conv_layers, pe_attn_head=arch.pe_attn_head)
+    model = CFM(transformer=tr, mel_spec_kwargs=dict(n_fft=1024, hop_length=256, win_length=1024, n_mel_channels=arch.mel_dim,
+                                                     target_sample_rate=24000, mel_spec_type="vocos"), odeint_kwargs=dict(method="euler"))
+    with torch.no_grad():
+        for p_ in model.parameters():
+            if float(p_.abs().max()) == 0.0:
+                p_.normal_(0, 0.02)
+    voc = Vocos()
+    with torch.no_grad():
+        voc.head.out.weight.mul_(0.5)  # keep exp(mag) in a log-mel-like range
+    return model.to(dev).eval(), voc.to(dev).eval()
+
+
+def cpu_port_measure(arch, ref_frames, total, steps, warmup, quiet=False):
+    """The CPU arm: oracle (fp32 torch restatement of the reference) on the host cores, bounded sample = ONE utterance of the
+    workload x ONE Euler step (cond + uncond DiT forwards) per timed step, + one text-embedding pair + one Vocos decode;
+    frames/s is extrapolated to the full NFE (the 32 steps are identical work)."""
+    from oracle import f5_oracle as O
+    from oracle.weights import make_dit_state_dict, make_vocos_state_dict, synthetic_inputs
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.DiTConfig(dim=arch.dim, depth=arch.depth, heads=arch.heads)
+    sd = make_dit_state_dict(cfg, 0)
+    vc = O.VocosConfig()
+    vsd = make_vocos_state_dict(vc, 1)
+    cond, text, duration, lens = synthetic_inputs(cfg, 1, ref_frames, total, seed=1234)
+    n = total
+    step_cond = torch.nn.functional.pad(cond, (0, 0, 0, n - ref_frames))
+    y = torch.randn(1, n, cfg.mel_dim)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        te_c = O.text_embedding(sd, cfg, text, n, False)
+        te_u = O.text_embedding(sd, cfg, text, n, True)
+        t_embed = time.perf_counter() - t0
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            t = torch.tensor(0.3)
+            pred = O.dit_forward(sd, cfg, y, step_cond, text, t, False, False, None, text_embed=te_c)
+            null = O.dit_forward(sd, cfg, y, step_cond, text, t, True, True, None, text_embed=te_u)
+            y = y + 0.03 * (pred + (pred - null) * CFG)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        t0 = time.perf_counter()
+        O.vocos_decode(vsd, vc, y[:, ref_frames:].permute(0, 2, 1))
+        t_voc = time.perf_counter() - t0
+    pair = sum(times) / len(times)
+    per_utt = NFE * pair + t_embed + t_voc
+    return dict(value=total / per_utt, pair_s=pair, embed_s=t_embed, vocos_s=t_voc, per_utterance_s=per_utt,
+                cores=torch.get_num_threads(),
+                sample=f"1 utterance ({total} frames) x 1 of {NFE} Euler steps (cond+uncond forward) per timed step, mean of {len(times)}; "
+                       f"+1 text-embedding pair +1 Vocos decode; extrapolated x{NFE} steps")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with CUDA events during the timed region")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    arch_kw, B, ref_frames, total, desc = WORKLOADS[args.workload]
+    cfg = Arch(**arch_kw)
+    frames_per_step = B * total
+    gen_frames_per_step = B * (total - ref_frames)
+    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": total, "ref_frames": ref_frames,
+              "nfe": NFE, "cfg_strength": CFG, "sway_sampling_coef": SWAY, "ode": "euler", "vocoder": "vocos-mel-24khz (random init)",
+              "parallelism": f"dp{world} (utterance batch sharded, no collective on the sampling path)",
+              "l2": "no flush: one DiT forward streams ~1.4 GB of activations + 0.65 GB of weights, >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_port_measure(cfg, ref_frames, total, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "mel_frames_per_sec", "value": r["value"], "unit": "mel-frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["pair_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "rtf": r["per_utterance_s"] / ((total - ref_frames) * 256 / 24000.0), "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------------------ ours
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from eraxvif5tts_b200 import _lib as L
+    L.load()
+    model, voc = build_product_models(cfg, dev)
+    cond, text, duration, lens, wav = make_inputs(cfg, B, ref_frames, total, 1234 + rank)
+    cond_d, text_d, dur_d, lens_d = cond.to(dev), text.to(dev), duration.to(dev), lens.to(dev)
+    wav_h, text_h = wav.pin_memory(), text.pin_memory()
+    gen_len = 256 * (total - ref_frames - 1)
+    audio_h = torch.empty(B, gen_len, dtype=torch.float32).pin_memory()
+
+    def step_device():
+        out, _ = model.sample(cond=cond_d, text=text_d, duration=dur_d, lens=lens_d, steps=NFE, cfg_strength=CFG,
+                              sway_sampling_coef=SWAY, seed=0, return_trajectory=False)
+        return voc.decode(out[:, ref_frames:].permute(0, 2, 1))
+
+    def step_e2e():
+        w = wav_h.to(dev, non_blocking=True)
+        t = text_h.to(dev, non_blocking=True)
+        out, _ = model.sample(cond=w, text=t, duration=dur_d, steps=NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=0,
+                              return_trajectory=False)
+        a = voc.decode(out[:, ref_frames:].permute(0, 2, 1))
+        audio_h.copy_(a, non_blocking=True)
+        torch.cuda.synchronize()
+        return audio_h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.prof_reset(not args.no_profile)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        a = step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = L.prof_read()
+    L.prof_reset(False)
+    assert torch.isfinite(a).all(), "non-finite audio"
+    # e2e through the public API with host buffers
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback"
+    peak_gbs = peaks.get("hbm_gbs", 6650.0)
+
+    kinds = {}
+    for k, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        d = {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps}
+        if v["ms"] > 0:
+            if v["flops"] > 0:
+                d["tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            d["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            d["share"] = v["ms"] / sum(x["ms"] for x in prof.values())
+        kinds[k] = d
+    roofline = None
+    timed = {k: v for k, v in prof.items() if v["ms"] > 0}
+    if timed:
+        top = max(timed, key=lambda k: timed[k]["ms"])
+        v = timed[top]
+        if v["flops"] > 0:
+            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                        "traffic": None, "peak_source": peak_src, "launches": v["launches"], "avg_launch_ms": v["ms"] / v["launches"],
+                        "flops_per_launch": v["flops"] / v["launches"]}
+        else:
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                        "traffic": None, "peak_source": peak_src, "launches": v["launches"], "avg_launch_ms": v["ms"] / v["launches"]}
+
+    total_frames = frames_per_step * args.steps * world
+    value = total_frames / (ms * 1e-3)
+    e2e_value = total_frames / e2e_s
+    launches = sum(v["launches"] for v in prof.values())
+    fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE
+    line = {"metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": wav_h.numel() * 4 + text_h.numel() * 8,
+                    "d2h_bytes_per_step": audio_h.numel() * 4, "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": launches,
+            "rtf": (ms * 1e-3 / args.steps) / (gen_frames_per_step * 256 / 24000.0),
+            "gen_frames_per_sec": gen_frames_per_step * args.steps * world / (ms * 1e-3),
+            "dit_tflops_per_gpu": fwd_flops / (ms * 1e-3 / args.steps) / 1e12,
+            "roofline": roofline, "kernels": kinds}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_measure(cfg, ref_frames, total, 2, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

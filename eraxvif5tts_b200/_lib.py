@@ -76,6 +76,8 @@ SIGNATURES = {
     "f5b_vocos_create": (C.c_int, [C.POINTER(VocosDesc), C.POINTER(vp)]),
     "f5b_vocos_destroy": (None, [vp]),
     "f5b_vocos_workspace_bytes": (sz, [vp, C.c_int, C.c_int]),
+    "f5b_prof_reset": (None, [C.c_int]),
+    "f5b_prof_read": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5b_vocos_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
 }
 
@@ -99,6 +101,21 @@ def load() -> C.CDLL:
         raise F5bError("libf5b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+KERNEL_KINDS = ("gemm", "attention", "convpos", "norm", "elementwise", "spectral")
+
+
+def prof_reset(enable: bool) -> None:
+    load().f5b_prof_reset(int(enable))
+
+
+def prof_read() -> dict:
+    """{kind: dict(launches, ms, flops, bytes)} since the last prof_reset (device-synchronising)."""
+    buf = (C.c_double * (4 * len(KERNEL_KINDS)))()
+    check(load().f5b_prof_read(buf, len(KERNEL_KINDS)), "f5b_prof_read")
+    return {k: dict(launches=int(buf[4 * i]), ms=buf[4 * i + 1], flops=buf[4 * i + 2], bytes=buf[4 * i + 3])
+            for i, k in enumerate(KERNEL_KINDS)}
 
 
 def check(rc: int, what: str = "") -> None:

@@ -274,6 +274,7 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int3
   F5B_CHECK(q && k && vt && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && n_pad >= n && (n_pad & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d n_pad %d", B, H, n,
             n_pad);
+  LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t bh = (uint64_t)B * H;
   if (make_tmap_3d(&tmQ, q, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BQ, 1, true)) return -1;

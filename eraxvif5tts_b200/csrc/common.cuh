@@ -38,6 +38,17 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
                  bool swizzle128);
 int sm_count();
 
+// ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline leg) ------------------------
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_CONVPOS = 2, K_NORM = 3, K_ELEMENTWISE = 4, K_SPECTRAL = 5, K_NUM = 6 };
+// RAII: counts the launch(es) of one host-side launcher and, when profiling is on, brackets them with events on `s`.
+struct LaunchScope {
+  int kind;
+  cudaStream_t s;
+  int slot;
+  LaunchScope(int kind, cudaStream_t s, double flops, double bytes, int launches = 1);
+  ~LaunchScope();
+};
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -120,6 +120,7 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
   F5B_CHECK(cpg <= 64 && (D & 7) == 0, "f5b_convpos: channels per group %d must be <= 64 and D a multiple of 8", cpg);
   F5B_CHECK(mode == 0 ? out != nullptr : resid != nullptr, "f5b_convpos: null output for mode %d", mode);
   const int NP = round16(cpg);
+  LaunchScope scope(K_CONVPOS, stream, 2.0 * B * n * (double)D * cpg * ksize, (double)B * n * D * (mode == 0 ? 4.0 : 10.0));
   CUtensorMap tmA, tmB;
   if (make_tmap_3d(&tmA, x, 2, (uint64_t)D, (uint64_t)n, (uint64_t)B, (uint64_t)D * 2, (uint64_t)n * D * 2, 64, BM, 1, true))
     return -1;
@@ -153,6 +154,7 @@ int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ks
   F5B_CHECK(w && wpk && groups > 0 && D % groups == 0 && D / groups <= 64, "f5b_pack_convpos_weight: bad shape");
   const int cpg = D / groups, NP = round16(cpg);
   const int64_t tot = (int64_t)groups * ksize * NP * 64;
+  LaunchScope scope(K_ELEMENTWISE, static_cast<cudaStream_t>(stream), 0, 6.0 * tot);
   pack_convpos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, reinterpret_cast<__nv_bfloat16*>(wpk), D, groups, ksize, cpg, NP);
   F5B_CUDA(cudaGetLastError());

@@ -66,6 +66,7 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int64_t 
   F5B_CHECK((mod_bstride & 3) == 0, "f5b_ln_modulate: modulation stride must be a multiple of 4");
   F5B_CHECK(rows_per_batch > 0, "f5b_ln_modulate: rows_per_batch");
   const int grid = (rows + 7) / 8;
+  LaunchScope scope(K_NORM, s, 0, 6.0 * rows * D);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = D / 4;
   if (nvec <= 32 * 2) ln_modulate_kernel<2><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
@@ -144,6 +145,7 @@ int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w
                int C, float eps, cudaStream_t s) {
   F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 3) == 0 && C <= 1024, "f5b_dwconv7_ln: C=%d must be a multiple of 4 and <= 1024", C);
   const int grid = (B * n + 7) / 8;
+  LaunchScope scope(K_NORM, s, 0, 6.0 * B * n * C);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = C / 4;
   if (nvec <= 32) dwconv7_ln_kernel<1><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(const __nv_bfloat16* __r
 int grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C, cudaStream_t s) {
   F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_grn: C=%d must be even", C);
   auto* hh = reinterpret_cast<const __nv_bfloat16*>(h);
+  LaunchScope scope(K_ELEMENTWISE, s, 0, 6.0 * B * n * C, 2);
   grn_colnorm_kernel<<<dim3((C + 127) / 128, B), 256, 0, s>>>(hh, ws, n, C);
   F5B_CUDA(cudaGetLastError());
   const int rpb = 8;
@@ -334,6 +337,7 @@ int ln_affine(const float* x, const float* w, const float* b, float* out_f32, vo
               cudaStream_t s) {
   F5B_CHECK(rows > 0 && D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_affine: D=%d must be a multiple of 4 and <= 1024", D);
   const int grid = (rows + 7) / 8;
+  LaunchScope scope(K_NORM, s, 0, (4.0 + (out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) * rows * D);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   const int nvec = D / 4;
   if (nvec <= 32) ln_affine_kernel<1><<<grid, 256, 0, s>>>(x, w, b, out_f32, o, rows, D, eps);
@@ -416,12 +420,14 @@ int f5b_grn(const void* h, const float* gamma, const float* beta, void* out, flo
 int f5b_text_lookup(const int64_t* ids, int nt, const float* table, const float* pos, float* out, uint8_t* mask_out, int B,
                     int n, int C, int drop_text, int add_pos, f5b_stream_t stream) {
   F5B_CHECK(B > 0 && n > 0 && C > 0 && nt >= 0, "f5b_text_lookup: bad shape");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * B * n * C);
   text_lookup_kernel<<<B * n, 128, 0, ST(stream)>>>(ids, nt, table, pos, out, mask_out, n, C, drop_text, add_pos);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
 
 int f5b_mask_rows_f32(float* x, const uint8_t* mask, int rows, int C, f5b_stream_t stream) {
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 1.0 * rows);
   mask_rows_kernel<<<rows, 128, 0, ST(stream)>>>(x, mask, C);
   F5B_CUDA(cudaGetLastError());
   return 0;
@@ -429,12 +435,14 @@ int f5b_mask_rows_f32(float* x, const uint8_t* mask, int rows, int C, f5b_stream
 
 int f5b_time_sinus(const float* t, void* out, int M, f5b_stream_t stream) {
   F5B_CHECK(M > 0, "f5b_time_sinus: M");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 516.0 * M);
   time_sinus_kernel<<<M, 128, 0, ST(stream)>>>(t, reinterpret_cast<__nv_bfloat16*>(out), M);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
 
 int f5b_silu_bf16(const float* x, void* out, int64_t n, f5b_stream_t stream) {
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * n);
   silu_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
   F5B_CUDA(cudaGetLastError());
   return 0;
@@ -448,6 +456,7 @@ int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32
 int f5b_pack_bf16(const float* x, int ld_in, void* out, int ld_out, int rows, int cols, int width, f5b_stream_t stream) {
   F5B_CHECK(rows > 0 && cols >= 0 && cols <= width && width <= ld_out && (x != nullptr || cols == 0), "f5b_pack_bf16: bad shape");
   const int64_t tot = (int64_t)rows * width;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * rows * cols + 2.0 * tot);
   pack_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out,
                                                                           rows, cols, width);
   F5B_CUDA(cudaGetLastError());
@@ -458,6 +467,7 @@ int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float d
                   int rows, int C, f5b_stream_t stream) {
   F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C, "f5b_cfg_euler: bad shape");
   const int64_t tot = (int64_t)rows * ld_bf;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
   cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, cfg, dt, reinterpret_cast<__nv_bfloat16*>(y_bf16),
                                                                           ld_bf, vel_out, rows, C);
   F5B_CUDA(cudaGetLastError());
@@ -465,6 +475,7 @@ int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float d
 }
 
 int f5b_rope_table(float* out, int n, f5b_stream_t stream) {
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 256.0 * n);
   rope_table_kernel<<<(n * 32 + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float2*>(out), n);
   F5B_CUDA(cudaGetLastError());
   return 0;
@@ -472,6 +483,7 @@ int f5b_rope_table(float* out, int n, f5b_stream_t stream) {
 
 int f5b_im2col7(const float* mel, void* out, int B, int T, int n_mels, int ld, f5b_stream_t stream) {
   F5B_CHECK(ld >= 7 * n_mels && (ld & 7) == 0, "f5b_im2col7: ld=%d must be >= 7*n_mels and a multiple of 8", ld);
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (double)B * T * (4.0 * n_mels + 2.0 * ld));
   im2col7_kernel<<<B * T, 256, 0, ST(stream)>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), T, n_mels, ld);
   F5B_CUDA(cudaGetLastError());
   return 0;

@@ -191,6 +191,8 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
               "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d n_pad %d)", g.N, g.heads, g.rows_per_batch, g.n_pad);
   }
   if (g.epi == F5B_EPI_GATE_RESID) F5B_CHECK(g.rows_per_batch > 0, "f5b_gemm: rows_per_batch required");
+  const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? 2.0 : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
+  LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
   const int m_tiles = (g.M + BM - 1) / BM;
   const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= sm_count()) ? 256 : 128;
   CUtensorMap tmA, tmB;

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -76,6 +77,44 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
   return 0;
 }
 
+// ---------------------------------------------------------------- launch accounting / profiling
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;          // pairs (start, stop)
+  std::vector<int> ev_kind;
+  size_t used = 0;
+  unsigned long long launches[K_NUM] = {0};
+  double flops[K_NUM] = {0}, bytes[K_NUM] = {0};
+};
+static ProfState g_prof;
+static std::mutex g_prof_mu;
+
+LaunchScope::LaunchScope(int kind_, cudaStream_t s_, double fl, double by, int n) : kind(kind_), s(s_), slot(-1) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.launches[kind] += n;
+  g_prof.flops[kind] += fl;
+  g_prof.bytes[kind] += by;
+  if (!g_prof.on) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;  // no events inside a capture
+  if (g_prof.used + 2 > g_prof.ev.size()) {
+    const size_t add = 4096;
+    for (size_t i = 0; i < add; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      g_prof.ev.push_back(e);
+    }
+    g_prof.ev_kind.resize(g_prof.ev.size() / 2);
+  }
+  slot = (int)(g_prof.used / 2);
+  g_prof.ev_kind[slot] = kind;
+  cudaEventRecord(g_prof.ev[g_prof.used], s);
+  g_prof.used += 2;
+}
+LaunchScope::~LaunchScope() {
+  if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], s);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -88,3 +127,40 @@ int sm_count() {
 }
 
 }  // namespace f5b
+
+extern "C" {
+
+// Profiling / accounting interface used by bench.py (not on the product path).
+void f5b_prof_reset(int enable) {
+  std::lock_guard<std::mutex> lk(f5b::g_prof_mu);
+  f5b::g_prof.on = enable != 0;
+  f5b::g_prof.used = 0;
+  for (int k = 0; k < f5b::K_NUM; ++k) {
+    f5b::g_prof.launches[k] = 0;
+    f5b::g_prof.flops[k] = 0;
+    f5b::g_prof.bytes[k] = 0;
+  }
+}
+
+// out[k*4 + {0,1,2,3}] = launches, device milliseconds (sum of event-bracketed launches; 0 if profiling was off),
+// algorithmic FLOPs, algorithmic bytes of kernel class k (f5b::KernelKind order).  Synchronises the device.
+int f5b_prof_read(double* out, int n_kinds) {
+  using namespace f5b;
+  F5B_CHECK(out != nullptr && n_kinds == K_NUM, "f5b_prof_read: expected %d kinds", (int)K_NUM);
+  F5B_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms[K_NUM] = {0};
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) == cudaSuccess) ms[g_prof.ev_kind[i / 2]] += t;
+  }
+  for (int k = 0; k < K_NUM; ++k) {
+    out[k * 4 + 0] = (double)g_prof.launches[k];
+    out[k * 4 + 1] = ms[k];
+    out[k * 4 + 2] = g_prof.flops[k];
+    out[k * 4 + 3] = g_prof.bytes[k];
+  }
+  return 0;
+}
+
+}  // extern "C"

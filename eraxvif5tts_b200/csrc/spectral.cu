@@ -132,6 +132,7 @@ int f5b_melspec(const float* wav, const float* fb, const int32_t* ranges, float*
   F5B_CHECK(wav && fb && ranges && out, "f5b_melspec: null pointer");
   F5B_CHECK(B > 0 && L > NFFT / 2 && n_mels > 0, "f5b_melspec: need L > 512 samples (reflect padding), got B %d L %d", B, L);
   const int T = 1 + L / HOP;
+  LaunchScope scope(K_SPECTRAL, static_cast<cudaStream_t>(stream), 0, (double)B * T * (HOP * 4.0 + n_mels * 4.0));
   melspec_kernel<<<dim3(T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(wav, fb, ranges, out, L, T, n_mels);
   F5B_CUDA(cudaGetLastError());
   return 0;
@@ -141,6 +142,7 @@ int f5b_istft_head(const float* head, int ld, float* frames_ws, float* wav, int 
   F5B_CHECK(head && frames_ws && wav, "f5b_istft_head: null pointer");
   F5B_CHECK(B > 0 && T > 1 && ld >= NFFT + 2, "f5b_istft_head: bad shape B %d T %d ld %d", B, T, ld);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LaunchScope scope(K_SPECTRAL, s, 0, (double)B * T * ((NFFT + 2) * 4.0 + HOP * 4.0), 2);
   istft_frames_kernel<<<B * T, 256, 0, s>>>(head, frames_ws, ld);
   F5B_CUDA(cudaGetLastError());
   const int out_len = HOP * (T - 1);

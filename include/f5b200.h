@@ -236,6 +236,14 @@ size_t f5b_vocos_workspace_bytes(const F5bVocos* h, int B, int T);
 int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* wav, void* ws, size_t ws_bytes,
                      f5b_stream_t stream);
 
+/* ---- launch accounting / per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg) ------------
+ * kernel classes: 0 gemm, 1 attention, 2 convpos, 3 norm (LN / dwconv+LN), 4 elementwise, 5 spectral.
+ * f5b_prof_reset(enable): zero the counters; enable != 0 additionally brackets every launch with CUDA events on its stream.
+ * f5b_prof_read(out, 6): out[k*4+{0,1,2,3}] = launches, device ms, algorithmic FLOPs, algorithmic bytes. Synchronises. */
+#define F5B_NUM_KERNEL_KINDS 6
+void f5b_prof_reset(int enable);
+int f5b_prof_read(double* out, int n_kinds);
+
 #ifdef __cplusplus
 }
 #endif
