@@ -22,6 +22,7 @@ __device__ __forceinline__ float mish(float x) {
 template <int MODE>
 struct ConvPosProblem {
   static constexpr int BN = 64;
+  static constexpr int STORE = STORE_DIRECT;
   int B, n, D, groups, cpg, NP, ksize, pad, n_tiles_seq;
   const float* bias;
   __nv_bfloat16* out;
@@ -38,6 +39,9 @@ struct ConvPosProblem {
   __device__ __forceinline__ uint32_t umma_n() const { return NP; }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return NP * 128; }
   __device__ __forceinline__ int tile_cols(int) const { return cpg; }
+  __device__ __forceinline__ int out_col0(int) const { return 0; }
+  __device__ __forceinline__ int out_row0(int) const { return 0; }
+  __device__ __forceinline__ void compute(const RowCtx&, int, const uint32_t (&)[32], float (&)[32]) const {}
   __device__ __forceinline__ void decode(int tile, int& b, int& nt, int& g) const {
     g = tile % groups;
     const int t2 = tile / groups;
@@ -129,10 +133,10 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
   const int total = B * nts * groups;
   if (mode == 0) {
     ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
-    return launch_engine(tmA, tmB, p, total, stream);
+    return launch_engine(tmA, tmB, tmA, p, total, stream);
   }
   ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
-  return launch_engine(tmA, tmB, p, total, stream);
+  return launch_engine(tmA, tmB, tmA, p, total, stream);
 }
 
 }  // namespace f5b

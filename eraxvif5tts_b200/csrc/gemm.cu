@@ -14,10 +14,9 @@ namespace f5b {
 template <int ACT>
 __device__ __forceinline__ float activate(float x) {
   if constexpr (ACT == F5B_ACT_GELU_TANH) {
-    // nn.GELU(approximate="tanh"), model/modules.py:625
-    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    const float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
-    return 0.5f * x * (1.0f + t);
+    // nn.GELU(approximate="tanh"), model/modules.py:625; tanh on the SFU (tanh.approx, rel. error ~2^-11 << bf16 output)
+    const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+    return 0.5f * x * (1.0f + tanh_approx(u));
   } else if constexpr (ACT == F5B_ACT_GELU_ERF) {
     return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
   } else if constexpr (ACT == F5B_ACT_SILU) {
@@ -30,12 +29,14 @@ __device__ __forceinline__ float activate(float x) {
 template <int BN_, int EPI, int ACT>
 struct LinearProblem {
   static constexpr int BN = BN_;
+  static constexpr int STORE = (EPI == F5B_EPI_BF16) ? STORE_BF16 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
   F5bGemmArgs g;
   int n_tiles, m_tiles, kblocks;
 
   struct RowCtx {
     int row, b, pos, n_base;
     bool valid;
+    const float* gate;
   };
 
   __device__ __forceinline__ int num_tiles() const { return n_tiles * m_tiles; }
@@ -46,6 +47,8 @@ struct LinearProblem {
     const int left = g.N - (tile % n_tiles) * BN;
     return left < BN ? left : BN;
   }
+  __device__ __forceinline__ int out_col0(int tile) const { return (tile % n_tiles) * BN; }
+  __device__ __forceinline__ int out_row0(int tile) const { return (tile / n_tiles) * BM; }
   __device__ __forceinline__ void load(int tile, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar, const CUtensorMap* tmA,
                                        const CUtensorMap* tmB) const {
     const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -60,39 +63,73 @@ struct LinearProblem {
     c.valid = c.row < g.M;
     c.b = 0;
     c.pos = c.row;
+    c.gate = nullptr;
     if constexpr (EPI == F5B_EPI_QKV_ROPE || EPI == F5B_EPI_GATE_RESID) {
       c.b = c.row / g.rows_per_batch;
       c.pos = c.row - c.b * g.rows_per_batch;
     }
     if constexpr (EPI == F5B_EPI_GATE_RESID) {
-      if (c.valid && g.lens != nullptr) {
-        const int bb = g.batch_mod > 0 ? c.b % g.batch_mod : c.b;
-        c.valid = c.pos < __ldg(g.lens + bb);
-      }
+      const int bb = g.batch_mod > 0 ? c.b % g.batch_mod : c.b;
+      if (c.valid && g.lens != nullptr) c.valid = c.pos < __ldg(g.lens + bb);
+      if (g.gate != nullptr) c.gate = g.gate + (size_t)bb * g.gate_bstride;
     }
     return c;
   }
 
+  // STORE_BF16 / STORE_F32ADD: final values of 32 consecutive columns (the engine stages + TMA-stores them)
+  __device__ __forceinline__ void compute(const RowCtx& c, int c0, const uint32_t (&r)[32], float (&v)[32]) const {
+    const int n0 = c.n_base + c0;
+    const int left = g.N - n0;  // > 0
+    float b[32];
+    load_bias32(g.bias, n0, left, b);
+    if constexpr (EPI == F5B_EPI_GATE_RESID) {
+      // x += gate[b] * (acc + bias); rows at or beyond lens[b] contribute 0 (masked_fill, model/modules.py:499-501)
+      if (!c.valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        return;
+      }
+      if (c.gate != nullptr) {
+        float gt[32];
+        load_bias32(c.gate, n0, left, gt);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gt[i] * (__uint_as_float(r[i]) + b[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + b[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(__uint_as_float(r[i]) + b[i]);
+    }
+  }
+
+  // STORE_DIRECT epilogues
   __device__ __forceinline__ void epilogue(const RowCtx& c, int c0, const uint32_t (&r)[32]) const {
     if (!c.valid) return;
     const int n0 = c.n_base + c0;
     const int left = g.N - n0;  // > 0
     float v[32];
+    {
+      float b[32];
+      load_bias32(g.bias, n0, left, b);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float b = 0.f;
-      if (g.bias != nullptr && i < left) b = __ldg(g.bias + n0 + i);
-      v[i] = activate<ACT>(__uint_as_float(r[i]) + b);
+      for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(__uint_as_float(r[i]) + b[i]);
     }
-    if constexpr (EPI == F5B_EPI_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)c.row * g.ldc + n0;
-      store_row32_bf16(o, v, left, (g.ldc & 7) == 0);
-    } else if constexpr (EPI == F5B_EPI_F32) {
+    if constexpr (EPI == F5B_EPI_F32) {
       if (g.addsrc != nullptr) {
         const float* a = g.addsrc + (size_t)c.row * g.ld_add + n0;
+        if (left >= 32 && (g.ld_add & 3) == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < left) v[i] += __ldg(a + i);
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a) + q);
+            v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < left) v[i] += __ldg(a + i);
+        }
       }
       float* o = reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + n0;
       store_row32_f32(o, v, left, (g.ldc & 3) == 0);
@@ -110,13 +147,15 @@ struct LinearProblem {
       const int dd0 = within & 63;  // 0 or 32
       if (sec < 2) {
         if (head < g.rope_heads) {
-          const float2* cs = reinterpret_cast<const float2*>(g.rope) + (size_t)c.pos * 32 + (dd0 >> 1);
+          const float4* cs = reinterpret_cast<const float4*>(g.rope) + (size_t)c.pos * 16 + (dd0 >> 2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 t = __ldg(cs + i);
-            const float x0 = v[2 * i], x1 = v[2 * i + 1];
-            v[2 * i] = x0 * t.x - x1 * t.y;
-            v[2 * i + 1] = x1 * t.x + x0 * t.y;
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(cs + i);  // (cos, sin) of two consecutive frequency pairs
+            const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+            v[4 * i] = x0 * t.x - x1 * t.y;
+            v[4 * i + 1] = x1 * t.x + x0 * t.y;
+            v[4 * i + 2] = x2 * t.z - x3 * t.w;
+            v[4 * i + 3] = x3 * t.z + x2 * t.w;
           }
         }
         __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? g.out : g.out2);
@@ -129,38 +168,27 @@ struct LinearProblem {
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[(size_t)i * g.n_pad] = __float2bfloat16(v[i]);
       }
-    } else {  // F5B_EPI_GATE_RESID: x += gate[b] * (acc + bias); rows beyond lens[b] untouched
-      float* o = reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + n0;
-      const int bb = g.batch_mod > 0 ? c.b % g.batch_mod : c.b;
-      const float* gt = g.gate ? g.gate + (size_t)bb * g.gate_bstride + n0 : nullptr;
-      if (left >= 32 && (g.ldc & 3) == 0 && (gt == nullptr || ((g.gate_bstride & 3) == 0))) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 x = reinterpret_cast<float4*>(o)[q];
-          const float4 gg = gt ? __ldg(reinterpret_cast<const float4*>(gt) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-          x.x += gg.x * v[q * 4];
-          x.y += gg.y * v[q * 4 + 1];
-          x.z += gg.z * v[q * 4 + 2];
-          x.w += gg.w * v[q * 4 + 3];
-          reinterpret_cast<float4*>(o)[q] = x;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < left) o[i] += (gt ? __ldg(gt + i) : 1.f) * v[i];
-      }
     }
   }
 };
 
 template <int BN, int EPI, int ACT>
 static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F5bGemmArgs& g, cudaStream_t stream) {
-  LinearProblem<BN, EPI, ACT> p;
+  using P = LinearProblem<BN, EPI, ACT>;
+  P p;
   p.g = g;
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.N + BN - 1) / BN;
   p.kblocks = (g.K + BK - 1) / BK;
-  return launch_engine(tmA, tmB, p, p.m_tiles * p.n_tiles, stream);
+  CUtensorMap tmC = tmA;
+  if constexpr (P::STORE == STORE_BF16) {
+    F5B_CHECK((g.ldc & 7) == 0, "f5b_gemm: bf16 output pitch %d must be a multiple of 8", g.ldc);
+    if (make_tmap_2d(&tmC, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, 32, true)) return -1;
+  } else if constexpr (P::STORE == STORE_F32ADD) {
+    F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
+    if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
+  }
+  return launch_engine(tmA, tmB, tmC, p, p.m_tiles * p.n_tiles, stream);
 }
 
 template <int BN>
@@ -190,7 +218,10 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
                   g.n_pad >= g.rows_per_batch && g.M % g.rows_per_batch == 0,
               "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d n_pad %d)", g.N, g.heads, g.rows_per_batch, g.n_pad);
   }
-  if (g.epi == F5B_EPI_GATE_RESID) F5B_CHECK(g.rows_per_batch > 0, "f5b_gemm: rows_per_batch required");
+  if (g.epi == F5B_EPI_GATE_RESID)
+    F5B_CHECK(g.rows_per_batch > 0 && (g.gate_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.gate) & 15) == 0,
+              "f5b_gemm: GATE_RESID needs rows_per_batch > 0 and a 16-byte aligned gate with a stride that is a multiple of 4");
+  if (g.bias != nullptr) F5B_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "f5b_gemm: bias must be 16-byte aligned");
   const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? 2.0 : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
   LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
   const int m_tiles = (g.M + BM - 1) / BM;

@@ -1,15 +1,20 @@
 // The tcgen05 tile engine shared by the linear GEMM (gemm.cu) and the grouped position-embedding convolution
 // (convpos.cu).
 //
-// sm_100a design: persistent warp-specialised kernel, one CTA per SM, 192 threads.
+// sm_100a design: persistent warp-specialised kernel, one CTA per SM, 320 threads.
 //   warp 0      : TMA producer — A tile [128 x 64] and B tile [umma_n x 64] (both K-major bf16) land in a ring of
 //                 128B-swizzled shared-memory stages, mbarrier complete_tx.
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected thread), UMMA 128 x N x 16 (kind::f16, bf16 in,
 //                 fp32 accumulate in TMEM), accumulator double-buffered (2 x BN columns) so the epilogue of tile i
 //                 overlaps the main loop of tile i+1.
-//   warps 2..5  : epilogue — tcgen05.ld 32x32b (thread = accumulator row), problem-specific fused math, global stores.
+//   warps 2..9  : epilogue — two warps per TMEM lane quadrant, each taking alternate column granules:
+//                 tcgen05.ld 32x32b (thread = accumulator row) -> problem-specific fused math -> one of
+//                   STORE_DIRECT : per-thread vectorised global stores (scatter epilogues: QKV head split, conv);
+//                   STORE_BF16   : bf16 tile -> 128B-swizzled per-warp staging smem -> TMA store (coalesced, async);
+//                   STORE_F32ADD : f32 tile -> staging smem -> TMA reduce-add: the residual stream x += tile is
+//                                  accumulated in L2, x is never read into the SM.
 // A "Problem" policy supplies the tile -> coordinate mapping (which TMA boxes feed k-block kb of tile t) and the
-// epilogue, so the same pipeline serves  C = A W^T  and the 31-tap implicit-GEMM convolution.
+// epilogue math, so the same pipeline serves  C = A W^T  and the 31-tap implicit-GEMM convolution.
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +22,9 @@ namespace f5b {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int ENGINE_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int ENGINE_THREADS = 64 + EPI_WARPS * 32;
+enum { STORE_DIRECT = 0, STORE_BF16 = 1, STORE_F32ADD = 2 };
 
 template <int BN>
 struct EngCfg {
@@ -25,13 +32,20 @@ struct EngCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t STAGING_BYTES = EPI_WARPS * 4096;  // one [32 rows x 128 B] tile per epilogue warp
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// store 8 consecutive 16-byte chunks (this lane's 128-byte row) into a [32 x 128 B] SWIZZLE_128B staging tile
+__device__ __forceinline__ void stage_store16(uint8_t* stg, int lane, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+}
 
 template <class P>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1)
-engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const P p) {
+engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmC, const P p) {
   constexpr int BN = P::BN;
   using Cfg = EngCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -39,7 +53,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -51,6 +66,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if constexpr (P::STORE != STORE_DIRECT) prefetch_tmap(&tmC);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -60,7 +76,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], 4);
+        mbar_init(&tempty[s], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -122,26 +138,92 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     __syncwarp();
   } else {
+    const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;   // which of the two warps of the quadrant
+    uint8_t* stg = staging + ew * 4096;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int ncols = p.tile_cols(tile);  // warp-uniform
       typename P::RowCtx ctx = p.row_ctx(tile, quad * 32 + lane);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_base + acc * BN;
+      if constexpr (P::STORE == STORE_DIRECT) {
 #pragma unroll 1
-      for (int c = 0; c * 32 < ncols; ++c) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        p.epilogue(ctx, c * 32, r);
+        for (int c = half; c * 32 < ncols; c += 2) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_ld_wait();
+          p.epilogue(ctx, c * 32, r);
+        }
+      } else if constexpr (P::STORE == STORE_BF16) {
+        // 64-column granules: two TMEM chunks -> one [32 x 64] bf16 staging tile -> one TMA store
+#pragma unroll 1
+        for (int g = half; g * 64 < ncols; g += 2) {
+          if (lane == 0) bulk_wait_read0();  // the previous store has drained the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = g * 64 + cc * 32;
+            if (c0 < ncols) {  // warp-uniform
+              uint32_t r[32];
+              tmem_ld32(t_acc + c0, r);
+              tmem_ld_wait();
+              float v[32];
+              p.compute(ctx, c0, r, v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                stage_store16(stg, lane, cc * 4 + q, pk);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, p.out_col0(tile) + g * 64, p.out_row0(tile) + quad * 32);
+            bulk_commit();
+          }
+        }
+      } else {
+        // 32-column f32 granules -> TMA reduce-add into the residual stream
+#pragma unroll 1
+        for (int g = half; g * 32 < ncols; g += 2) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + g * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          p.compute(ctx, g * 32, r, v);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            stage_store16(stg, lane, q,
+                          make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]),
+                                     __float_as_uint(v[q * 4 + 3])));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmC, stg, p.out_col0(tile) + g * 32, p.out_row0(tile) + quad * 32);
+            bulk_commit();
+          }
+        }
       }
       __syncwarp();
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if constexpr (P::STORE != STORE_DIRECT) {
+      if (lane == 0) bulk_wait0();
     }
   }
   tc_fence_before();
@@ -153,7 +235,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 template <class P>
-static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const P& p, int total_tiles, cudaStream_t stream) {
+static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const P& p, int total_tiles,
+                         cudaStream_t stream) {
   using Cfg = EngCfg<P::BN>;
   static bool configured = false;
   auto kern = engine_kernel<P>;
@@ -162,7 +245,7 @@ static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const P
     configured = true;
   }
   const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  kern<<<grid, ENGINE_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, ENGINE_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -194,6 +277,24 @@ __device__ __forceinline__ void store_row32_f32(float* o, const float (&v)[32], 
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (i < ncols_left) o[i] = v[i];
+  }
+}
+
+// bias for 32 consecutive columns (vectorised when the whole chunk is in range)
+__device__ __forceinline__ void load_bias32(const float* bias, int n0, int left, float (&b)[32]) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.f;
+  } else if (left >= 32) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(b4 + q);
+      b[q * 4] = t.x; b[q * 4 + 1] = t.y; b[q * 4 + 2] = t.z; b[q * 4 + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = i < left ? __ldg(bias + n0 + i) : 0.f;
   }
 }
 

@@ -261,6 +261,67 @@ def bench_gemm(M, N, K, iters=20):
     report(f"bench_gemm_{M}x{N}x{K}", ms=ms, tflops=2 * M * N * K / ms / 1e9, cublas_ms=ms2, cublas_tflops=2 * M * N * K / ms2 / 1e9)
 
 
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_epilogues(B=32, n=1875, D=1024):
+    """every GEMM flavour of one DiT block at the cfg-2 in-situ shape (2B x n rows)"""
+    M, H, F_ = B * n, D // 64, 2 * D
+    n_pad = (n + 7) // 8 * 8
+    h = torch.randn(M, D, device=dev).to(bf16)
+    fb = torch.randn(M, F_, device=dev).to(bf16)
+    wqkv = (torch.randn(3 * D, D, device=dev) / 32).to(bf16)
+    wo = (torch.randn(D, D, device=dev) / 32).to(bf16)
+    w1 = (torch.randn(F_, D, device=dev) / 32).to(bf16)
+    w2 = (torch.randn(D, F_, device=dev) / 45).to(bf16)
+    bq, bo, b1 = torch.randn(3 * D, device=dev), torch.randn(D, device=dev), torch.randn(F_, device=dev)
+    rope = torch.randn(n, 32, 2, device=dev)
+    q = torch.empty(B, H, n, 64, dtype=bf16, device=dev)
+    k = torch.empty_like(q)
+    vt = torch.empty(B, H, 64, n_pad, dtype=bf16, device=dev)
+    x = torch.randn(M, D, device=dev)
+    gate = torch.randn(D, device=dev) * 0.1
+    lens = torch.full((B // 2,), n, dtype=torch.int32, device=dev)
+    ob = torch.empty(M, F_, dtype=bf16, device=dev)
+    o3 = torch.empty(M, 3 * D, dtype=bf16, device=dev)
+    o1 = torch.empty(M, D, dtype=bf16, device=dev)
+    cases = {
+        "qkv_rope": (lambda: ops.gemm(h, wqkv, epi=L.EPI_QKV_ROPE, bias=bq, out=q, out2=k, out3=vt, rows_per_batch=n, rope=rope, rope_heads=1,
+                                       heads=H, n_pad=n_pad), 2.0 * M * 3 * D * D),
+        "qkv_plain_bf16": (lambda: ops.gemm(h, wqkv, epi=L.EPI_BF16, bias=bq, out=o3), 2.0 * M * 3 * D * D),
+        "out_gate_resid": (lambda: ops.gemm(h, wo, epi=L.EPI_GATE_RESID, bias=bo, out=x, rows_per_batch=n, gate=gate, gate_bstride=0, lens=lens,
+                                             batch_mod=B // 2), 2.0 * M * D * D),
+        "out_plain_bf16": (lambda: ops.gemm(h, wo, epi=L.EPI_BF16, bias=bo, out=o1), 2.0 * M * D * D),
+        "ff1_gelu": (lambda: ops.gemm(h, w1, epi=L.EPI_BF16, act=L.ACT_GELU_TANH, bias=b1, out=ob), 2.0 * M * F_ * D),
+        "ff1_plain": (lambda: ops.gemm(h, w1, epi=L.EPI_BF16, bias=b1, out=ob), 2.0 * M * F_ * D),
+        "ff2_gate_resid": (lambda: ops.gemm(fb, w2, epi=L.EPI_GATE_RESID, bias=bo, out=x, rows_per_batch=n, gate=gate, gate_bstride=0),
+                           2.0 * M * D * F_),
+        "ff2_plain_bf16": (lambda: ops.gemm(fb, w2, epi=L.EPI_BF16, bias=bo, out=o1), 2.0 * M * D * F_),
+        "cublas_qkv": (lambda: torch.matmul(h, wqkv.t(), out=o3), 2.0 * M * 3 * D * D),
+        "cublas_ff2": (lambda: torch.matmul(fb, w2.t(), out=o1), 2.0 * M * D * F_),
+    }
+    for name, (fn, fl) in cases.items():
+        ms = _time(fn)
+        report(f"epi_{name}", ms=ms, tflops=fl / ms / 1e9)
+    xx = torch.randn(M, D, device=dev)
+    mod = torch.randn(6 * D, device=dev)
+    hb = torch.empty(M, D, dtype=bf16, device=dev)
+    lib = L.load()
+    ms = _time(lambda: L.check(lib.f5b_ln_modulate(xx.data_ptr(), mod.data_ptr() + 4 * D, mod.data_ptr(), 0, 0, hb.data_ptr(), M, n, D, 1e-6,
+                                                   L.stream()), "ln"))
+    report("epi_ln_modulate", ms=ms, gbs=M * D * 6 / ms / 1e6)
+
+
 def bench_attn(B, H, n, iters=10):
     n_pad = (n + 7) // 8 * 8
     q = torch.randn(B, H, n, 64, device=dev).to(bf16)
@@ -311,6 +372,11 @@ def main():
     run("convpos_128", lambda: convpos_case(2, 96, 128))
     run("small", small_kernels)
     run("spectral", spectral)
+    if "--epi" in sys.argv:
+        run("bench_epilogues", bench_epilogues)
+        run("bench_attn32", lambda: bench_attn(32, 16, 1875))
+        finish()
+        return
     run("bench_gemm_qkv", lambda: bench_gemm(30000, 3072, 1024))
     run("bench_gemm_ff2", lambda: bench_gemm(30000, 1024, 2048))
     run("bench_gemm_big", lambda: bench_gemm(8192, 8192, 8192, 5))
