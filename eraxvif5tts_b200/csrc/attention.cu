@@ -5,11 +5,13 @@
 // sm_100a design (one CTA = one 128-query tile of one (batch, head); two CTAs co-resident per SM so that one CTA's
 // softmax overlaps the other's tensor work):
 //   warp 4 (one elected lane): TMA producer + tcgen05.mma issuer.
-//       S[128 x 128] = Q K_j^T   (Q, K_j K-major bf16 tiles, 128B swizzle, fp32 accumulator in TMEM columns 0..127)
-//       O_j[128 x 64] = P_j V_j  (P_j written to swizzled smem by the softmax warps, V^T K-major from the QKV
-//                                 epilogue's transposed store; accumulator in TMEM columns 128..191)
-//   warps 0..3: online softmax, thread = query row (tcgen05.ld 32x32b -> no cross-lane reductions); running max / sum
-//       and the fp32 O accumulator live in registers; exp2 with the 1/sqrt(d)*log2(e) scale folded in.
+//       S[128 x 128]  = Q K_j^T    (Q, K_j K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM columns 0..127)
+//       O[128 x 80]  += P_j V'_j   (P_j written to swizzled smem by the softmax warps; V' = V^T from the QKV epilogue's
+//                                   transposed store plus a constant row of ones, so column 64 of O accumulates the softmax
+//                                   row sum on the tensor pipe; accumulator stays resident in TMEM columns 128..207)
+//   warps 0..3: online softmax, thread = query row (tcgen05.ld 32x32b -> no cross-lane reductions), exp2 with the
+//       1/sqrt(d)*log2(e) scale folded in.  The running maximum is updated lazily: O (and with it the row sum) is rescaled in
+//       TMEM only when a row's maximum grew by more than 2^8, so most KV tiles cost no accumulator round trip.
 //   K is double-buffered, V single-buffered (its reload hides behind the next tile's softmax).
 //   Key-padding is a per-batch length bound: KV tiles past len[b] are never loaded, the last tile is masked by index.
 #include "common.cuh"
@@ -20,12 +22,16 @@ namespace f5b {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_THREADS = 160;
+constexpr int ATT_NV = 80;                                  // 64 value columns + the ones row + zero padding to N % 16 == 0
 constexpr uint32_t ATT_Q_BYTES = ATT_BQ * 64 * 2;          // 16 KB
 constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 16 KB per stage, 2 stages
-constexpr uint32_t ATT_V_BYTES = 64 * ATT_BKV * 2;         // 16 KB (two [64 d x 64 kv] chunks)
+constexpr uint32_t ATT_VC_BYTES = ATT_NV * 128;            // one 64-kv chunk of V': 80 rows x 128 B = 10 KB
+constexpr uint32_t ATT_V_BYTES = 2 * ATT_VC_BYTES;         // 20 KB
+constexpr uint32_t ATT_V_TX = 2 * 64 * 128;                // bytes TMA writes per tile (the 64 real rows of both chunks)
 constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 32 KB (two [128 q x 64 kv] atoms)
 constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + ATT_P_BYTES + 1024 + 128;
-constexpr uint32_t ATT_TMEM_COLS = 256;  // S: 128, O_j: 64
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S: 128, O: 80
+constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -33,6 +39,28 @@ struct AttnParams {
   int lens_mod, B, H, n;
   float scale_log2;
 };
+
+template <bool MASKED>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* atom, int cbase, int rx) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = fmaf(__uint_as_float(s[q * 8 + i]), sl2, -mb);
+      e[i] = ex2_approx(x);
+      if constexpr (MASKED) {
+        if (q * 8 + i >= lim) e[i] = 0.f;
+      }
+    }
+    uint4 pk;
+    pk.x = pack_bf16(e[0], e[1]);
+    pk.y = pack_bf16(e[2], e[3]);
+    pk.z = pack_bf16(e[4], e[5]);
+    pk.w = pack_bf16(e[6], e[7]);
+    *reinterpret_cast<uint4*>(atom + (((cbase + q) ^ rx) << 4)) = pk;
+  }
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -93,6 +121,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  } else {
+    // constant rows 64..79 of both V' chunks: row 64 = ones (bf16 1.0), rows 65..79 = 0.  128 threads x 2 x 16 B x 8.
+    const int t = threadIdx.x;  // 0..127
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint8_t* base = sV + c * ATT_VC_BYTES + 64 * 128;
+      const uint32_t one2 = 0x3F803F80u;
+      const uint32_t v = (t < 8) ? one2 : 0u;  // the first 8 x 16 B = row 64 (identical chunks, swizzle-invariant)
+      *reinterpret_cast<uint4*>(base + t * 16) = make_uint4(v, v, v, v);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -104,15 +143,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc_s = idesc_bf16(128, ATT_BKV, 0, 0);
-      const uint32_t idesc_o = idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_o = idesc_bf16(128, ATT_NV, 0, 0);
       // prologue loads
       mbar_arrive_expect_tx(bar_q, ATT_Q_BYTES);
       tma_load_3d(sQ, &tmQ, bar_q, 0, q0, bh);
       mbar_arrive_expect_tx(&bar_k[0], ATT_K_BYTES);
       tma_load_3d(sK, &tmK, &bar_k[0], 0, 0, bh);
-      mbar_arrive_expect_tx(bar_v, ATT_V_BYTES);
+      mbar_arrive_expect_tx(bar_v, ATT_V_TX);
       tma_load_3d(sV, &tmV, bar_v, 0, 0, bh);
-      tma_load_3d(sV + 8192, &tmV, bar_v, 64, 0, bh);
+      tma_load_3d(sV + ATT_VC_BYTES, &tmV, bar_v, 64, 0, bh);
       if (T > 1) {
         mbar_arrive_expect_tx(&bar_k[1], ATT_K_BYTES);
         tma_load_3d(sK + ATT_K_BYTES, &tmK, &bar_k[1], 0, ATT_BKV, bh);
@@ -129,7 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(bar_s);
       for (int j = 0; j < T; ++j) {
         const uint32_t ph = j & 1;
-        mbar_wait(bar_p, ph);  // P_j in smem, S_j consumed
+        mbar_wait(bar_p, ph);  // P_j in smem, S_j consumed, O rescaled if needed
         tc_fence_after();
         // K buffer (j&1) is free (S_j retired before the softmax warps saw bar_s): prefetch K_{j+2}
         if (j + 2 < T) {
@@ -141,12 +180,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t a = p_addr + (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t bb = v_addr + (kk >> 2) * 8192 + (kk & 3) * 32;
-          umma_bf16(tmem_O, smem_desc_sw128(a, 1024, 16), smem_desc_sw128(bb, 1024, 16), idesc_o, kk != 0);
+          const uint32_t bb = v_addr + (kk >> 2) * ATT_VC_BYTES + (kk & 3) * 32;
+          umma_bf16(tmem_O, smem_desc_sw128(a, 1024, 16), smem_desc_sw128(bb, 1024, 16), idesc_o, (j | kk) != 0);
         }
         umma_commit(bar_o);
         if (j + 1 < T) {
-          // S_{j+1} queues behind P_j V_j on the tensor pipe; it overlaps the O_j accumulation of the softmax warps
+          // S_{j+1} queues behind P_j V_j on the tensor pipe
           const int nb = (j + 1) & 1;
           mbar_wait(&bar_k[nb], ((j + 1) >> 1) & 1);
           tc_fence_after();
@@ -158,9 +197,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(bar_s);
           // V buffer is free once P_j V_j retired
           mbar_wait(bar_o, ph);
-          mbar_arrive_expect_tx(bar_v, ATT_V_BYTES);
+          mbar_arrive_expect_tx(bar_v, ATT_V_TX);
           tma_load_3d(sV, &tmV, bar_v, (j + 1) * ATT_BKV, 0, bh);
-          tma_load_3d(sV + 8192, &tmV, bar_v, (j + 1) * ATT_BKV + 64, 0, bh);
+          tma_load_3d(sV + ATT_VC_BYTES, &tmV, bar_v, (j + 1) * ATT_BKV + 64, 0, bh);
         }
       }
     }
@@ -168,10 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     const int r = warp * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_used = -INFINITY;  // log2-domain maximum the exponentials are taken against
     const float sl2 = p.scale_log2;
     uint8_t* p_row = sP + r * 128;
     const int rx = r & 7;
@@ -181,85 +217,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int valid = min(ATT_BKV, kvlen - j * ATT_BKV);  // CTA-uniform, >= 1
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      // pass 1: row max
+      // pass 1: row max (raw scores)
       float m_tile = -INFINITY;
+      if (valid == ATT_BKV) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= valid) break;
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, s);
-        tmem_ld_wait();
-        const int lim = valid - c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < lim) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
-      }
-      const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = ex2_approx((m_run - m_new) * sl2);
-      const float mb = m_new * sl2;
-      // pass 2: P = exp2(S*sl2 - mb), row sum, bf16 -> swizzled smem
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        const int lim = valid - c * 32;  // may be <= 0 -> all zeros
-        if (lim > 0) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
           tmem_ld32(tmem_S + lane_addr + c * 32, s);
           tmem_ld_wait();
-        }
-        float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = 0.f;
-          if (i < lim) e = ex2_approx(__uint_as_float(s[i]) * sl2 - mb);
-          pv[i] = e;
-          rs += e;
+          for (int i = 0; i < 32; i += 2) m_tile = fmaxf(fmaxf(m_tile, __uint_as_float(s[i])), __uint_as_float(s[i + 1]));
         }
-        uint8_t* atom = p_row + (c >> 1) * 16384;
+      } else {
+#pragma unroll 1
+        for (int c = 0; c * 32 < valid; ++c) {
+          uint32_t s[32];
+          tmem_ld32(tmem_S + lane_addr + c * 32, s);
+          tmem_ld_wait();
+          const int lim = valid - c * 32;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = (c & 1) * 4 + q;
-          uint4 pk;
-          pk.x = pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]);
-          pk.y = pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]);
-          pk.z = pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]);
-          pk.w = pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(atom + ((ch ^ rx) << 4)) = pk;
+          for (int i = 0; i < 32; ++i)
+            if (i < lim) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
         }
       }
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
+      const float mt = m_tile * sl2;
+      // lazy rescale (warp-uniform decision; tcgen05.ld/st are warp-collective)
+      if (j == 0) {
+        m_used = mt;
+      } else if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
+        const float m_new = fmaxf(m_used, mt);
+        const float f = ex2_approx(m_used - m_new);
+        m_used = m_new;
+        mbar_wait(bar_o, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_addr + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st32(tmem_O + lane_addr + c * 32, o);
+        }
+        tmem_st_wait();
+      }
+      // pass 2: P = exp2(S*sl2 - m_used) -> bf16 -> swizzled smem
+      const float mb = m_used;
+      if (valid == ATT_BKV) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld32(tmem_S + lane_addr + c * 32, s);
+          tmem_ld_wait();
+          softmax_chunk<false>(s, sl2, mb, 32, p_row + (c >> 1) * 16384, (c & 1) * 4, rx);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          const int lim = valid - c * 32;  // may be <= 0 -> all zeros
+          if (lim > 0) {
+            tmem_ld32(tmem_S + lane_addr + c * 32, s);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[i] = 0u;
+          }
+          softmax_chunk<true>(s, sl2, mb, lim, p_row + (c >> 1) * 16384, (c & 1) * 4, rx);
+        }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
-      // O_j
-      mbar_wait(bar_o, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_addr + c * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(o[i]);
-      }
-      tc_fence_before();
     }
+    // epilogue: O[:, :64] / O[:, 64]
+    mbar_wait(bar_o, (T - 1) & 1);
+    tc_fence_after();
     const int pos = q0 + r;
-    if (pos < p.n) {
-      const bool live = pos < kvlen;
-      const float inv = live ? 1.f / l_run : 0.f;
-      uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.n + pos) * D + h * 64);
+    float inv;
+    {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_addr + 64, o);
+      tmem_ld_wait();
+      inv = (pos < kvlen) ? 1.f / __uint_as_float(o[0]) : 0.f;
+    }
+    __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 pk;
-        pk.x = pack_bf16(o_acc[q * 8 + 0] * inv, o_acc[q * 8 + 1] * inv);
-        pk.y = pack_bf16(o_acc[q * 8 + 2] * inv, o_acc[q * 8 + 3] * inv);
-        pk.z = pack_bf16(o_acc[q * 8 + 4] * inv, o_acc[q * 8 + 5] * inv);
-        pk.w = pack_bf16(o_acc[q * 8 + 6] * inv, o_acc[q * 8 + 7] * inv);
-        o[q] = pk;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_addr + c * 32, o);
+      tmem_ld_wait();
+      if (pos < p.n) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(orow + c * 32)[q] = pk;
+        }
       }
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
