@@ -1,0 +1,161 @@
+"""CPU tests: host-side logic of the drop-in classes, state_dict key compatibility with the reference, C-ABI symbol export,
+and the utterance sharding (gloo, world_size 2).  No CUDA compute is called."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from eraxvif5tts_b200 import build, _lib
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "f5b200.h")).read()
+    declared = set(re.findall(r"\b(f5b_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/f5b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().f5b_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    from eraxvif5tts_b200 import _lib, ops
+    with pytest.raises(_lib.F5bError):
+        ops.ln_modulate(torch.zeros(4, 64), None, None, 0, 0, 4)  # CPU tensor must be rejected, not computed
+    from eraxvif5tts_b200.infer import F5TTSWrapper
+    with pytest.raises(RuntimeError):
+        F5TTSWrapper(model_name="F5TTS_Base", vocab_char_map={"a": 0}, device="cpu")
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "eraxvif5tts_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{fn} imports the oracle"
+
+
+def test_state_dict_keys_match_reference_layout():
+    """SURVEY.md §10 key list (taken from the real reference modules; oracle.weights mirrors it)."""
+    from eraxvif5tts_b200.model import DiT
+    from oracle.f5_oracle import DiTConfig
+    from oracle.weights import dit_key_shapes
+    cfg = DiTConfig.tiny()
+    d = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim, text_num_embeds=cfg.text_num_embeds,
+            text_dim=cfg.text_dim, text_mask_padding=False, conv_layers=cfg.conv_layers, pe_attn_head=1)
+    ours = {k: tuple(v.shape) for k, v in d.state_dict().items()}
+    ref = {k[len("transformer."):]: tuple(s) for k, s, _ in dit_key_shapes(cfg)}
+    ref["rotary_embed.inv_freq"] = (32,)
+    assert ours == ref
+    # AdaLN-zero init (dit.py:162-172)
+    assert float(d.norm_out.linear.weight.abs().max()) == 0 and float(d.proj_out.weight.abs().max()) == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/f5_tts"), reason="reference tree only in the build container")
+def test_state_dict_keys_match_live_reference():
+    from eraxvif5tts_b200.model import DiT
+    from oracle import ref_shim
+    ref = ref_shim.load()
+    kw = dict(dim=128, depth=2, heads=2, ff_mult=2, mel_dim=100, text_num_embeds=40, text_dim=64, text_mask_padding=False, conv_layers=2,
+              pe_attn_head=1)
+    a = {k: tuple(v.shape) for k, v in DiT(**kw).state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.dit.DiT(**kw).state_dict().items()}
+    assert a == b
+
+
+def test_vocos_keys_match_upstream_layout():
+    from eraxvif5tts_b200 import Vocos
+    from oracle.f5_oracle import VocosConfig
+    from oracle.weights import vocos_key_shapes
+    vc = VocosConfig()
+    ours = {k: tuple(v.shape) for k, v in Vocos().state_dict().items()}
+    ref = {k: tuple(s) for k, s, _ in vocos_key_shapes(vc)}
+    ref["head.istft.window"] = (1024,)
+    assert ours == ref
+
+
+def test_chunk_text_and_tokenizer(tmp_path):
+    from eraxvif5tts_b200.infer.utils_infer import chunk_text, resolve_arch
+    from eraxvif5tts_b200.model.utils import get_tokenizer, lens_to_mask, list_str_to_idx, mask_from_frac_lengths
+    chunks = chunk_text("One. Two, three! Four? Five; six: seven.", max_chars=12)
+    assert all(len(c.encode()) <= 12 for c in chunks) and "".join(chunks).replace(" ", "") == "One.Two,three!Four?Five;six:seven."
+    assert chunk_text("", 10) == []
+    vf = tmp_path / "vocab.txt"
+    vf.write_text(" \na\nb\nc\n", encoding="utf-8")
+    m, n = get_tokenizer(str(vf), "custom")
+    assert n == 4 and m[" "] == 0 and m["c"] == 3  # first line is a literal space
+    idx = list_str_to_idx(["ab c", "zz"], m)
+    assert idx.tolist() == [[1, 2, 0, 3], [0, 0, -1, -1]]  # unknown -> 0, pad -1
+    assert lens_to_mask(torch.tensor([1, 3])).tolist() == [[True, False, False], [True, True, True]]
+    torch.manual_seed(0)
+    mk = mask_from_frac_lengths(torch.tensor([10, 20]), torch.tensor([0.5, 1.0]))
+    assert mk.shape == (2, 20) and int(mk[0].sum()) == 5 and int(mk[1].sum()) == 20
+    assert resolve_arch("F5TTS_Base")["depth"] == 22 and resolve_arch("F5TTS_Small")["dim"] == 768
+    with pytest.raises(ValueError):
+        resolve_arch("nope")
+
+
+def test_melspec_filterbank_matches_torchaudio():
+    import torchaudio
+    from eraxvif5tts_b200.model.modules import MelSpec, melscale_fbanks_htk
+    fb = torchaudio.functional.melscale_fbanks(513, 0.0, 12000.0, 100, 24000, norm=None, mel_scale="htk")
+    assert (melscale_fbanks_htk(513, 0.0, 12000.0, 100, 24000) - fb).abs().max() < 1e-6
+    m = MelSpec()
+    r = m.fb_ranges
+    for j in range(100):  # every non-zero of column j lies inside [f0, f1)
+        nzr = (fb[:, j] > 0).nonzero().flatten()
+        assert int(r[j, 0]) <= int(nzr.min()) and int(nzr.max()) < int(r[j, 1])
+
+
+def test_cfm_forward_is_loud_about_training():
+    from eraxvif5tts_b200.model import CFM, DiT
+    m = CFM(transformer=DiT(dim=128, depth=1, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_num_embeds=10), mel_spec_kwargs={})
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 8, 100), torch.zeros(1, 3, dtype=torch.long))
+
+
+def test_shard_indices_cover_everything_once():
+    from eraxvif5tts_b200.parallel import shard_indices
+    for n, w, bs in ((256, 8, 16), (10, 4, 3), (3, 8, 16), (0, 2, 4)):
+        seen = []
+        for r in range(w):
+            for b in shard_indices(n, r, w, bs):
+                assert len(b) <= bs
+                seen += b
+        assert sorted(seen) == list(range(n))
+    assert shard_indices(256, 1, 8, 16)[0] == list(range(16, 32))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from eraxvif5tts_b200.parallel import shard_indices, gather_counts, max_over_ranks
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+r = dist.get_rank()
+mine = shard_indices(37, r, 2, 4)
+cnt = sum(len(b) for b in mine)
+counts = gather_counts(cnt)
+t = max_over_ranks(1.0 + r)
+dist.barrier()
+assert sum(counts) == 37 and t == 2.0, (counts, t)
+print("rank", r, "ok", counts)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=29731))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok [19, 18]" in o or "ok [20, 17]" in o for o in outs), outs
