@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libf5b200.so")
+LIB_PATH = os.environ.get("F5B_LIB") or os.path.join(_PKG, "lib", "libf5b200.so")  # F5B_LIB: kernel-variant experiments
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 

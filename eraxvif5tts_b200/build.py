@@ -36,6 +36,7 @@ def _headers_mtime() -> float:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
+    extra = os.environ.get("F5B_NVCC_EXTRA", "").split()  # e.g. -DATT_TRACE for the instrumented attention build
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hm = _headers_mtime()
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(so):
         src, obj = so
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

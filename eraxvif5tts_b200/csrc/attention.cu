@@ -2,35 +2,37 @@
 // Replaces AttnProcessor's mask expansion + F.scaled_dot_product_attention + head merge
 // (/root/reference/src/f5_tts/model/modules.py:483-493; dropout_p = 0, see DESIGN.md "oracle adjustments").
 //
-// sm_100a design (one CTA = one 128-query tile of one (batch, head); two CTAs co-resident per SM so that one CTA's
-// softmax overlaps the other's tensor work):
-//   warp 4 (one elected lane): TMA producer + tcgen05.mma issuer.
-//       S[128 x 128]  = Q K_j^T    (Q, K_j K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM columns 0..127)
-//       O[128 x 80]  += P_j V'_j   (P_j written to swizzled smem by the softmax warps; V' = V^T from the QKV epilogue's
-//                                   transposed store plus a constant row of ones, so column 64 of O accumulates the softmax
-//                                   row sum on the tensor pipe; accumulator stays resident in TMEM columns 128..207)
+// sm_100a design (one CTA = one 128-query tile of one (batch, head); two CTAs co-resident per SM):
+//   warp 4 (one elected lane): TMA producer + tcgen05.mma issuer.  KV is consumed in tiles of 64 keys:
+//       S_j[128 x 64] = Q K_j^T    (K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM, DOUBLE-buffered: S_{j+1}
+//                                   and S_{j+2} are computed while the softmax warps still work on S_j)
+//       O[128 x 80]  += P_j V'_j   (P_j written to swizzled smem (double-buffered) by the softmax warps; V' = V^T from the
+//                                   QKV epilogue's transposed store plus a constant row of ones, so column 64 of O
+//                                   accumulates the softmax row sum on the tensor pipe; O stays resident in TMEM)
 //   warps 0..3: online softmax, thread = query row (tcgen05.ld 32x32b -> no cross-lane reductions), exp2 with the
 //       1/sqrt(d)*log2(e) scale folded in.  The running maximum is updated lazily: O (and with it the row sum) is rescaled in
-//       TMEM only when a row's maximum grew by more than 2^8, so most KV tiles cost no accumulator round trip.
-//   K is double-buffered, V single-buffered (its reload hides behind the next tile's softmax).
-//   Key-padding is a per-batch length bound: KV tiles past len[b] are never loaded, the last tile is masked by index.
+//       TMEM only when a row's maximum grew by more than 2^8, so most KV tiles cost no accumulator round trip and the
+//       softmax warps never wait for the tensor pipe in steady state (the kernel is MUFU.EX2-bound).
+//   K and V' live in 3-stage TMA rings.  Key-padding is a per-batch length bound: KV tiles past len[b] are never loaded,
+//   the last tile is masked by index.
 #include "common.cuh"
 #include "f5b_internal.h"
 
 namespace f5b {
 
 constexpr int ATT_BQ = 128;
-constexpr int ATT_BKV = 128;
-constexpr int ATT_THREADS = 160;
+constexpr int ATT_BKV = 64;
+constexpr int ATT_SM_WARPS = 4;   // softmax warps: one per TMEM lane quadrant, thread = query row
+constexpr int ATT_THREADS = (ATT_SM_WARPS + 1) * 32;
 constexpr int ATT_NV = 80;                                  // 64 value columns + the ones row + zero padding to N % 16 == 0
+constexpr int ATT_KV_STAGES = 3;
 constexpr uint32_t ATT_Q_BYTES = ATT_BQ * 64 * 2;          // 16 KB
-constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 16 KB per stage, 2 stages
-constexpr uint32_t ATT_VC_BYTES = ATT_NV * 128;            // one 64-kv chunk of V': 80 rows x 128 B = 10 KB
-constexpr uint32_t ATT_V_BYTES = 2 * ATT_VC_BYTES;         // 20 KB
-constexpr uint32_t ATT_V_TX = 2 * 64 * 128;                // bytes TMA writes per tile (the 64 real rows of both chunks)
-constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 32 KB (two [128 q x 64 kv] atoms)
-constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + ATT_P_BYTES + 1024 + 128;
-constexpr uint32_t ATT_TMEM_COLS = 256;  // S: 128, O: 80
+constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage
+constexpr uint32_t ATT_V_BYTES = ATT_NV * 128;             // 10 KB per stage: 80 rows x (64 kv x 2 B)
+constexpr uint32_t ATT_V_TX = 64 * 128;                    // bytes TMA writes per V' tile (the 64 real rows)
+constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer, 2 buffers
+constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + ATT_KV_STAGES * (ATT_K_BYTES + ATT_V_BYTES) + 2 * ATT_P_BYTES + 1024 + 256;
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S0: 0..63, S1: 64..127, O: 128..207
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
@@ -38,17 +40,36 @@ struct AttnParams {
   const int32_t* lens;
   int lens_mod, B, H, n;
   float scale_log2;
+  long long* trace;  // debug only (ATT_TRACE builds)
 };
 
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel. error 7.5e-5, far below
+// the bf16 rounding of P): a fixed fraction of the exponentials is computed this way so the MUFU pipe, the bottleneck of the
+// softmax, gets fewer of them.  Valid for x <= ~100; inputs below -126 are clamped (result 2^-126 instead of 0).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517143756151199f, 0.24261081218719482f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef ATT_POLY_MASK
+#define ATT_POLY_MASK 0x00  // which of every 8 consecutive columns use exp2_poly (bit i = column i).  Measured on B200
+                            // (profiles/r01_attention_notes.md): 0x00 577, 0x88 543, 0x92 518, 0xAA 486 TFLOP/s — the softmax warps
+                            // are issue/latency-bound, not MUFU-bound, at d_head 64, so the offload is off.
+#endif
+
 template <bool MASKED>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* atom, int cbase, int rx) {
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float x = fmaf(__uint_as_float(s[q * 8 + i]), sl2, -mb);
-      e[i] = ex2_approx(x);
+      e[i] = ((ATT_POLY_MASK >> i) & 1) ? exp2_poly(x) : ex2_approx(x);
       if constexpr (MASKED) {
         if (q * 8 + i >= lim) e[i] = 0.f;
       }
@@ -58,8 +79,36 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2
     pk.y = pack_bf16(e[2], e[3]);
     pk.z = pack_bf16(e[4], e[5]);
     pk.w = pack_bf16(e[6], e[7]);
-    *reinterpret_cast<uint4*>(atom + (((cbase + q) ^ rx) << 4)) = pk;
+    *reinterpret_cast<uint4*>(prow + (((cbase + q) ^ rx) << 4)) = pk;
   }
+}
+
+// named barrier shared by the two softmax warps of one TMEM lane quadrant (ids 1..4, 64 threads)
+__device__ __forceinline__ void pair_sync(int quad) {
+  if (quad == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+  else if (quad == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+  else if (quad == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+  else asm volatile("bar.sync 4, 64;" ::: "memory");
+}
+
+// row maximum of the first `valid` of 32 raw scores (4 independent chains when the chunk is full)
+__device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
+  if (valid >= 32) {
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      m0 = fmaxf(fmaxf(m0, __uint_as_float(a[i])), __uint_as_float(a[i + 1]));
+      m1 = fmaxf(fmaxf(m1, __uint_as_float(a[i + 2])), __uint_as_float(a[i + 3]));
+      m2 = fmaxf(fmaxf(m2, __uint_as_float(a[i + 4])), __uint_as_float(a[i + 5]));
+      m3 = fmaxf(fmaxf(m3, __uint_as_float(a[i + 6])), __uint_as_float(a[i + 7]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < valid) m = fmaxf(m, __uint_as_float(a[i]));
+  return m;
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -70,16 +119,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_Q_BYTES;
-  uint8_t* sV = sK + 2 * ATT_K_BYTES;
-  uint8_t* sP = sV + ATT_V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + ATT_P_BYTES);
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_K_BYTES;
+  uint8_t* sP = sV + ATT_KV_STAGES * ATT_V_BYTES;  // offset 16K + 24K + 30K = 70K: 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;  // [2]
-  uint64_t* bar_v = bars + 3;
-  uint64_t* bar_s = bars + 4;
-  uint64_t* bar_p = bars + 5;
-  uint64_t* bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_k = bars + 1;   // [3] K_j landed
+  uint64_t* bar_v = bars + 4;   // [3] V'_j landed
+  uint64_t* bar_s = bars + 7;   // [2] S_j in TMEM
+  uint64_t* bar_p = bars + 9;   // [2] P_j in smem, S_j consumed (128 arrivals)
+  uint64_t* bar_pv = bars + 11; // [2] P_j V'_j retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,101 +154,93 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
 
-  if (warp == 4) {
+  if (warp == ATT_SM_WARPS) {
     if (lane == 0) {
       prefetch_tmap(&tmQ);
       prefetch_tmap(&tmK);
       prefetch_tmap(&tmV);
       mbar_init(bar_q, 1);
-      mbar_init(&bar_k[0], 1);
-      mbar_init(&bar_k[1], 1);
-      mbar_init(bar_v, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
-      mbar_init(bar_o, 1);
+      for (int i = 0; i < ATT_KV_STAGES; ++i) {
+        mbar_init(&bar_k[i], 1);
+        mbar_init(&bar_v[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], ATT_SM_WARPS * 32);
+        mbar_init(&bar_pv[i], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
-  } else {
-    // constant rows 64..79 of both V' chunks: row 64 = ones (bf16 1.0), rows 65..79 = 0.  128 threads x 2 x 16 B x 8.
+  } else if (warp < 4) {
+    // constant rows 64..79 of every V' stage: row 64 = ones (bf16 1.0), rows 65..79 = 0   (3 x 2 KB, 128 threads x 16 B)
     const int t = threadIdx.x;  // 0..127
+    const uint32_t v = (t < 8) ? 0x3F803F80u : 0u;  // first 8 x 16 B = row 64 (identical chunks, swizzle-invariant)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint8_t* base = sV + c * ATT_VC_BYTES + 64 * 128;
-      const uint32_t one2 = 0x3F803F80u;
-      const uint32_t v = (t < 8) ? one2 : 0u;  // the first 8 x 16 B = row 64 (identical chunks, swizzle-invariant)
-      *reinterpret_cast<uint4*>(base + t * 16) = make_uint4(v, v, v, v);
-    }
+    for (int st = 0; st < ATT_KV_STAGES; ++st)
+      *reinterpret_cast<uint4*>(sV + st * ATT_V_BYTES + 64 * 128 + t * 16) = make_uint4(v, v, v, v);
     fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == ATT_SM_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_s = idesc_bf16(128, ATT_BKV, 0, 0);
       const uint32_t idesc_o = idesc_bf16(128, ATT_NV, 0, 0);
-      // prologue loads
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      auto load_k = [&](int j) {
+        const int st = j % ATT_KV_STAGES;
+        mbar_arrive_expect_tx(&bar_k[st], ATT_K_BYTES);
+        tma_load_3d(sK + st * ATT_K_BYTES, &tmK, &bar_k[st], 0, j * ATT_BKV, bh);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % ATT_KV_STAGES;
+        mbar_arrive_expect_tx(&bar_v[st], ATT_V_TX);
+        tma_load_3d(sV + st * ATT_V_BYTES, &tmV, &bar_v[st], j * ATT_BKV, 0, bh);
+      };
+      auto issue_s = [&](int j) {
+        const int st = j % ATT_KV_STAGES;
+        mbar_wait(&bar_k[st], (j / ATT_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t kb = k_addr + st * ATT_K_BYTES;
+        const uint32_t d = tmem_base + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d, smem_desc_sw128(q_addr + k * 32, 1024, 16), smem_desc_sw128(kb + k * 32, 1024, 16), idesc_s, k != 0);
+        umma_commit(&bar_s[j & 1]);
+      };
+      // prologue
       mbar_arrive_expect_tx(bar_q, ATT_Q_BYTES);
       tma_load_3d(sQ, &tmQ, bar_q, 0, q0, bh);
-      mbar_arrive_expect_tx(&bar_k[0], ATT_K_BYTES);
-      tma_load_3d(sK, &tmK, &bar_k[0], 0, 0, bh);
-      mbar_arrive_expect_tx(bar_v, ATT_V_TX);
-      tma_load_3d(sV, &tmV, bar_v, 0, 0, bh);
-      tma_load_3d(sV + ATT_VC_BYTES, &tmV, bar_v, 64, 0, bh);
-      if (T > 1) {
-        mbar_arrive_expect_tx(&bar_k[1], ATT_K_BYTES);
-        tma_load_3d(sK + ATT_K_BYTES, &tmK, &bar_k[1], 0, ATT_BKV, bh);
-      }
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-      // S_0
+      for (int j = 0; j < ATT_KV_STAGES && j < T; ++j) load_k(j);
+      for (int j = 0; j < 2 && j < T; ++j) load_v(j);
       mbar_wait(bar_q, 0);
-      mbar_wait(&bar_k[0], 0);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_S, smem_desc_sw128(q_addr + k * 32, 1024, 16), smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s,
-                  k != 0);
-      umma_commit(bar_s);
+      issue_s(0);
+      if (T > 1) issue_s(1);
       for (int j = 0; j < T; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(bar_p, ph);  // P_j in smem, S_j consumed, O rescaled if needed
+        const int pb = j & 1;
+        mbar_wait(&bar_p[pb], (j >> 1) & 1);  // P_j in smem, S_j consumed, O rescaled if needed
         tc_fence_after();
-        // K buffer (j&1) is free (S_j retired before the softmax warps saw bar_s): prefetch K_{j+2}
+        const int vst = j % ATT_KV_STAGES;
+        mbar_wait(&bar_v[vst], (j / ATT_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t pa = p_addr + pb * ATT_P_BYTES;
+        const uint32_t vb = v_addr + vst * ATT_V_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(vb + kk * 32, 1024, 16), idesc_o, (j | kk) != 0);
+        umma_commit(&bar_pv[pb]);
+        if (j + 2 < T) issue_s(j + 2);  // S buffer pb is free (softmax consumed S_j before arriving on bar_p)
+        if (j + ATT_KV_STAGES < T) load_k(j + ATT_KV_STAGES);  // K stage of tile j is free (S_j retired long ago)
         if (j + 2 < T) {
-          mbar_arrive_expect_tx(&bar_k[j & 1], ATT_K_BYTES);
-          tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], 0, (j + 2) * ATT_BKV, bh);
-        }
-        mbar_wait(bar_v, ph);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t a = p_addr + (kk >> 2) * 16384 + (kk & 3) * 32;
-          const uint32_t bb = v_addr + (kk >> 2) * ATT_VC_BYTES + (kk & 3) * 32;
-          umma_bf16(tmem_O, smem_desc_sw128(a, 1024, 16), smem_desc_sw128(bb, 1024, 16), idesc_o, (j | kk) != 0);
-        }
-        umma_commit(bar_o);
-        if (j + 1 < T) {
-          // S_{j+1} queues behind P_j V_j on the tensor pipe
-          const int nb = (j + 1) & 1;
-          mbar_wait(&bar_k[nb], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint32_t kb_addr = k_addr + nb * ATT_K_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_S, smem_desc_sw128(q_addr + k * 32, 1024, 16), smem_desc_sw128(kb_addr + k * 32, 1024, 16),
-                      idesc_s, k != 0);
-          umma_commit(bar_s);
-          // V buffer is free once P_j V_j retired
-          mbar_wait(bar_o, ph);
-          mbar_arrive_expect_tx(bar_v, ATT_V_TX);
-          tma_load_3d(sV, &tmV, bar_v, (j + 1) * ATT_BKV, 0, bh);
-          tma_load_3d(sV + ATT_VC_BYTES, &tmV, bar_v, (j + 1) * ATT_BKV + 64, 0, bh);
+          // V' stage (j+2)%3 was last read by P_{j-1} V'_{j-1}
+          if (j >= 1) mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          load_v(j + 2);
         }
       }
     }
@@ -209,37 +250,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     float m_used = -INFINITY;  // log2-domain maximum the exponentials are taken against
     const float sl2 = p.scale_log2;
-    uint8_t* p_row = sP + r * 128;
     const int rx = r & 7;
+#ifdef ATT_TRACE
+    long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define ATT_MARK(i) { const long long tn = clock64(); tr[i] += tn - tprev; tprev = tn; }
+#else
+#define ATT_MARK(i)
+#endif
 
     for (int j = 0; j < T; ++j) {
-      const uint32_t ph = j & 1;
+      const int pb = j & 1;
+      const uint32_t tS = tmem_base + lane_addr + pb * 64;
+      uint8_t* p_row = sP + pb * ATT_P_BYTES + r * 128;
       const int valid = min(ATT_BKV, kvlen - j * ATT_BKV);  // CTA-uniform, >= 1
-      mbar_wait(bar_s, ph);
+      mbar_wait(&bar_s[pb], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max (raw scores)
-      float m_tile = -INFINITY;
-      if (valid == ATT_BKV) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld32(tmem_S + lane_addr + c * 32, s);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) m_tile = fmaxf(fmaxf(m_tile, __uint_as_float(s[i])), __uint_as_float(s[i + 1]));
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c * 32 < valid; ++c) {
-          uint32_t s[32];
-          tmem_ld32(tmem_S + lane_addr + c * 32, s);
-          tmem_ld_wait();
-          const int lim = valid - c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < lim) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
-        }
-      }
+      ATT_MARK(0)
+      uint32_t s0[32], s1[32];
+      tmem_ld32(tS, s0);
+      tmem_ld32(tS + 32, s1);
+      tmem_ld_wait();
+      ATT_MARK(1)
+      const float m_tile = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32)));
       const float mt = m_tile * sl2;
       // lazy rescale (warp-uniform decision; tcgen05.ld/st are warp-collective)
       if (j == 0) {
@@ -248,7 +281,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float m_new = fmaxf(m_used, mt);
         const float f = ex2_approx(m_used - m_new);
         m_used = m_new;
-        mbar_wait(bar_o, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+        mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V'_{j-1} has landed in O
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
@@ -261,37 +294,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_st_wait();
       }
-      // pass 2: P = exp2(S*sl2 - m_used) -> bf16 -> swizzled smem
-      const float mb = m_used;
+      ATT_MARK(2)
+      // the P buffer was last read by P_{j-2} V'_{j-2}: already retired, because bar_s[pb] (S_j) was committed by the same
+      // thread after P_{j-2} V'_{j-2} was issued and tcgen05.commit covers every earlier MMA of that thread
+      ATT_MARK(3)
+      // P = exp2(S*sl2 - m_used) -> bf16 -> swizzled smem
       if (valid == ATT_BKV) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld32(tmem_S + lane_addr + c * 32, s);
-          tmem_ld_wait();
-          softmax_chunk<false>(s, sl2, mb, 32, p_row + (c >> 1) * 16384, (c & 1) * 4, rx);
-        }
+        softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
+        softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
       } else {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          const int lim = valid - c * 32;  // may be <= 0 -> all zeros
-          if (lim > 0) {
-            tmem_ld32(tmem_S + lane_addr + c * 32, s);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = 0u;
-          }
-          softmax_chunk<true>(s, sl2, mb, lim, p_row + (c >> 1) * 16384, (c & 1) * 4, rx);
-        }
+        softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
+        softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
       }
+      ATT_MARK(4)
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(&bar_p[pb]);
+      ATT_MARK(5)
     }
+#ifdef ATT_TRACE
+    if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 5 && lane == 0) {
+      for (int i = 0; i < 6; ++i) p.trace[warp * 8 + i] = tr[i];
+      p.trace[warp * 8 + 6] = T;
+    }
+#endif
     // epilogue: O[:, :64] / O[:, 64]
-    mbar_wait(bar_o, (T - 1) & 1);
+    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
     const int pos = q0 + r;
     float inv;
@@ -323,11 +351,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == ATT_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
 }
+
+long long* g_attn_trace = nullptr;
 
 int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
              int n_pad, float scale, cudaStream_t stream) {
@@ -339,7 +369,7 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int3
   const uint64_t bh = (uint64_t)B * H;
   if (make_tmap_3d(&tmQ, q, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BQ, 1, true)) return -1;
   if (make_tmap_3d(&tmK, k, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BKV, 1, true)) return -1;
-  if (make_tmap_3d(&tmV, vt, 2, (uint64_t)n, 64, bh, (uint64_t)n_pad * 2, (uint64_t)n_pad * 128, 64, 64, 1, true)) return -1;
+  if (make_tmap_3d(&tmV, vt, 2, (uint64_t)n, 64, bh, (uint64_t)n_pad * 2, (uint64_t)n_pad * 128, ATT_BKV, 64, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
@@ -353,6 +383,7 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int3
   p.H = H;
   p.n = n;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
   attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   F5B_CUDA(cudaGetLastError());
@@ -365,3 +396,5 @@ extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* vt, void* 
                             int H, int n, int n_pad, float scale, f5b_stream_t stream) {
   return f5b::attn_fwd(q, k, vt, out, lens, lens_mod, B, H, n, n_pad, scale, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }
