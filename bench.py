@@ -217,6 +217,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=dev)
     from eraxvif5tts_b200 import _lib as L
     L.load()
@@ -252,7 +253,13 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    L.prof_reset(not args.no_profile)
+    # Launch-bound workloads (small fused batch) replay one captured CUDA graph per ODE step; per-launch CUDA events cannot be
+    # recorded inside a replay, so for those the kernel breakdown comes from one extra eager, event-bracketed step after the
+    # timed region.  GPU-bound workloads (cfg2, cfg3) are event-bracketed live inside the timed region.
+    from eraxvif5tts_b200.model import cfm as cfm_mod
+    graph_mode = os.environ.get("F5B_CUDA_GRAPH", "") != "0" and (2 * B * total <= cfm_mod.GRAPH_MAX_ROWS or os.environ.get("F5B_CUDA_GRAPH") == "1")
+    live_profile = (not args.no_profile) and not graph_mode
+    L.prof_reset(live_profile)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -262,6 +269,13 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     prof = L.prof_read()
+    launches_timed = sum(v["launches"] for v in prof.values())
+    prof_steps = args.steps
+    if graph_mode and not args.no_profile:
+        L.prof_reset(True)
+        step_device()
+        prof = L.prof_read()
+        prof_steps = 1
     L.prof_reset(False)
     assert torch.isfinite(a).all(), "non-finite audio"
     # e2e through the public API with host buffers
@@ -296,7 +310,7 @@ def main():
     for k, v in prof.items():
         if v["launches"] == 0:
             continue
-        d = {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps}
+        d = {"launches_per_step": v["launches"] / prof_steps, "ms_per_step": v["ms"] / prof_steps}
         if v["ms"] > 0:
             if v["flops"] > 0:
                 d["tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
@@ -321,7 +335,9 @@ def main():
     total_frames = frames_per_step * args.steps * world
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / e2e_s
-    launches = sum(v["launches"] for v in prof.values())
+    launches = launches_timed
+    config["cuda_graph"] = ("one captured graph per ODE step (replayed 32x per sample); kernel breakdown from one extra eager step"
+                            if graph_mode else "off (GPU-bound batch; launches are event-bracketed live in the timed region)")
     fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE
     line = {"metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -76,6 +76,9 @@ SIGNATURES = {
     "f5b_vocos_create": (C.c_int, [C.POINTER(VocosDesc), C.POINTER(vp)]),
     "f5b_vocos_destroy": (None, [vp]),
     "f5b_vocos_workspace_bytes": (sz, [vp, C.c_int, C.c_int]),
+    "f5b_cfg_euler_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
+    "f5b_prof_enabled": (C.c_int, []),
+    "f5b_prof_add": (None, [C.POINTER(C.c_double), C.c_int]),
     "f5b_prof_reset": (None, [C.c_int]),
     "f5b_prof_read": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5b_vocos_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
@@ -116,6 +119,18 @@ def prof_read() -> dict:
     check(load().f5b_prof_read(buf, len(KERNEL_KINDS)), "f5b_prof_read")
     return {k: dict(launches=int(buf[4 * i]), ms=buf[4 * i + 1], flops=buf[4 * i + 2], bytes=buf[4 * i + 3])
             for i, k in enumerate(KERNEL_KINDS)}
+
+
+def prof_raw() -> list:
+    """raw counters without synchronising semantics beyond prof_read's (used to diff launches around a graph capture)"""
+    buf = (C.c_double * (4 * len(KERNEL_KINDS)))()
+    check(load().f5b_prof_read(buf, len(KERNEL_KINDS)), "f5b_prof_read")
+    return list(buf)
+
+
+def prof_add(delta: list) -> None:
+    buf = (C.c_double * (4 * len(KERNEL_KINDS)))(*delta)
+    load().f5b_prof_add(buf, len(KERNEL_KINDS))
 
 
 def check(rc: int, what: str = "") -> None:

@@ -353,10 +353,14 @@ int ln_affine(const float* x, const float* w, const float* b, float* out_f32, vo
 // euler update y += dt * v; also refreshes the zero-padded bf16 copy of the state that feeds the next input GEMM.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void cfg_euler_kernel(float* __restrict__ y, const float* __restrict__ pc, const float* __restrict__ pu, float cfg,
-                                 float dt, __nv_bfloat16* __restrict__ ybf, int ld_bf, float* __restrict__ vel, int rows,
-                                 int C) {
+                                 float dt, const float* __restrict__ dev_params, __nv_bfloat16* __restrict__ ybf, int ld_bf,
+                                 float* __restrict__ vel, int rows, int C) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * ld_bf) return;
+  if (dev_params != nullptr) {  // (cfg, dt) live in device memory so a captured CUDA graph can be replayed for every ODE step
+    cfg = __ldg(dev_params);
+    dt = __ldg(dev_params + 1);
+  }
   const int r = (int)(i / ld_bf), c = (int)(i - (int64_t)r * ld_bf);
   float yn = 0.f;
   if (c < C) {
@@ -468,8 +472,19 @@ int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float d
   F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C, "f5b_cfg_euler: bad shape");
   const int64_t tot = (int64_t)rows * ld_bf;
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
-  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, cfg, dt, reinterpret_cast<__nv_bfloat16*>(y_bf16),
-                                                                          ld_bf, vel_out, rows, C);
+  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, cfg, dt, nullptr,
+                                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_cfg_euler_dev(float* y, const float* pc, const float* pu, const float* params_dev, void* y_bf16, int ld_bf, float* vel_out,
+                      int rows, int C, f5b_stream_t stream) {
+  F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C && params_dev != nullptr, "f5b_cfg_euler_dev: bad argument");
+  const int64_t tot = (int64_t)rows * ld_bf;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
+  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, 0.f, 0.f, params_dev,
+                                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -37,6 +38,34 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Encoding a tensor map costs a few microseconds of host time; the hot loops re-use a small set of (pointer, shape) pairs
+// (same workspace, same weights every ODE step), so encoded maps are cached.  Key = every input of the encode call.
+struct TmapKey {
+  uint64_t v[10];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(k);
+  if (it == g_tmaps.end()) return false;
+  *out = it->second;
+  return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmaps.size() > 65536) g_tmaps.clear();
+  g_tmaps.emplace(k, m);
+}
+
 static CUtensorMapDataType dtype_of(int elt_bytes) {
   return elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 }
@@ -47,6 +76,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inn
   F5B_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   F5B_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16B aligned", base);
   F5B_CHECK(row_stride_bytes % 16 == 0, "TMA row stride %llu not a multiple of 16", (unsigned long long)row_stride_bytes);
+  const TmapKey key = {{2, (uint64_t)(uintptr_t)base, (uint64_t)elt_bytes, inner, outer, 0, row_stride_bytes, 0,
+                        ((uint64_t)box_inner << 32) | box_outer, (uint64_t)swizzle128}};
+  if (tmap_lookup(key, out)) return 0;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -56,6 +88,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inn
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   F5B_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (dims %llu x %llu, stride %llu, box %u x %u)", (int)r,
             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer);
+  tmap_store(key, *out);
   return 0;
 }
 
@@ -66,6 +99,9 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
   F5B_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   F5B_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16B aligned", base);
   F5B_CHECK(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA strides must be multiples of 16");
+  const TmapKey key = {{3, (uint64_t)(uintptr_t)base, (uint64_t)elt_bytes, d0, d1, d2, stride1_bytes, stride2_bytes,
+                        ((uint64_t)b0 << 40) | ((uint64_t)b1 << 20) | b2, (uint64_t)swizzle128}};
+  if (tmap_lookup(key, out)) return 0;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {b0, b1, b2};
@@ -74,6 +110,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   F5B_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  tmap_store(key, *out);
   return 0;
 }
 
@@ -141,6 +178,18 @@ void f5b_prof_reset(int enable) {
     f5b::g_prof.bytes[k] = 0;
   }
 }
+
+// add (launches, -, flops, bytes) per kind: a replayed CUDA graph re-issues launches the LaunchScope only saw at capture time
+void f5b_prof_add(const double* delta, int n_kinds) {
+  if (delta == nullptr || n_kinds != f5b::K_NUM) return;
+  std::lock_guard<std::mutex> lk(f5b::g_prof_mu);
+  for (int k = 0; k < f5b::K_NUM; ++k) {
+    f5b::g_prof.launches[k] += (unsigned long long)delta[k * 4 + 0];
+    f5b::g_prof.flops[k] += delta[k * 4 + 2];
+    f5b::g_prof.bytes[k] += delta[k * 4 + 3];
+  }
+}
+int f5b_prof_enabled(void) { return f5b::g_prof.on ? 1 : 0; }
 
 // out[k*4 + {0,1,2,3}] = launches, device milliseconds (sum of event-bracketed launches; 0 if profiling was off),
 // algorithmic FLOPs, algorithmic bytes of kernel class k (f5b::KernelKind order).  Synchronises the device.

@@ -9,6 +9,7 @@ re-designed for the B200 path:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import torch
@@ -16,11 +17,16 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.utils.rnn import pad_sequence
 
+from .. import _lib as L
 from .. import ops
 from .modules import MelSpec
 from .utils import default, exists, lens_to_mask, list_str_to_idx, list_str_to_tensor
 
 f32, bf16 = torch.float32, torch.bfloat16
+
+# Replay one captured CUDA graph per ODE step when the fused batch is small enough to be launch-bound (the reference's own
+# serial B=1 chunk loop).  F5B_CUDA_GRAPH=0 disables, =1 forces it for every shape.
+GRAPH_MAX_ROWS = 16384
 
 
 class CFM(nn.Module):
@@ -122,12 +128,17 @@ class CFM(nn.Module):
 
         # ---- step-invariant work -------------------------------------------------------------------------------------
         use_cfg = cfg_strength >= 1e-5
+        Bf = 2 * batch if use_cfg else batch
+        genv = os.environ.get("F5B_CUDA_GRAPH", "")
+        use_graph = (method == "euler" and genv != "0" and (genv == "1" or Bf * n <= GRAPH_MAX_ROWS)
+                     and not L.load().f5b_prof_enabled())
+        sess = eng.step_session(batch, Bf, n, lens32 is not None) if use_graph else None
+        c0 = sess["c0"] if use_graph else torch.empty(Bf, n, eng.dim, dtype=f32, device=device)
         te_c = eng.text_embed(text, n, False)
-        c0 = eng.input_const(step_cond, te_c)
+        eng.input_const(step_cond, te_c, out=c0[:batch])
         if use_cfg:
             te_u = eng.text_embed(text, n, True)
-            c0 = torch.cat((c0, eng.input_const(None, te_u)), dim=0)
-        Bf = c0.shape[0]
+            eng.input_const(None, te_u, out=c0[batch:])
         dt = t[1:] - t[:-1]
         if method == "euler":
             times = t[:-1]
@@ -136,19 +147,33 @@ class CFM(nn.Module):
         mod = eng.modulation(times)  # [evals, mod_dim]
         dt_host = dt.tolist()
 
-        y = y0.contiguous()
         rows = batch * n
-        yb = torch.empty(rows, 128, dtype=bf16, device=device)
+        if use_graph:
+            y, yb, pred = sess["y"], sess["yb"], sess["pred"]
+            y.copy_(y0)
+            if lens32 is not None:
+                sess["lens"].copy_(lens32)
+            lens32 = sess["lens"]
+        else:
+            y = y0.contiguous()
+            yb = torch.empty(rows, 128, dtype=bf16, device=device)
+            pred = torch.empty(Bf, n, self.num_channels, dtype=f32, device=device)
         ops.pack_bf16(y.view(rows, self.num_channels), yb, self.num_channels, 128)
-        pred = torch.empty(Bf, n, self.num_channels, dtype=f32, device=device)
         pc = pred[:batch]
         pu = pred[batch:] if use_cfg else None
         traj = [y.clone()] if return_trajectory else None
         ymid = torch.empty_like(y) if method == "midpoint" else None
+        if use_graph:
+            # per step: [modulation row | cfg | dt] -> stepbuf (one small D2D copy), then replay the captured step
+            table = torch.cat((mod, torch.full((steps, 1), float(cfg_strength), device=device), dt.unsqueeze(1)), dim=1).contiguous()
 
         # ---- ODE loop (fn closure cfm.py:159-173 + torchdiffeq fixed-grid solver) ---------------------------------------
         for i in range(steps):
-            if method == "euler":
+            if use_graph:
+                sess["stepbuf"].copy_(table[i], non_blocking=True)
+                sess["graph"].replay()
+                L.prof_add(sess["delta"])
+            elif method == "euler":
                 eng.forward(yb, batch, c0, Bf, n, mod[i], 0, lens32, pred)
                 ops.cfg_euler(y, pc, pu, cfg_strength, dt_host[i], yb)
             else:
@@ -161,6 +186,8 @@ class CFM(nn.Module):
                 traj.append(y.clone())
         self.transformer.clear_cache()
 
+        if use_graph:
+            y = y.clone()  # the session buffer is reused by the next call
         trajectory = torch.stack(traj) if return_trajectory else y.unsqueeze(0)
         out = torch.where(cond_mask, cond, y)
         if exists(vocoder):

@@ -129,6 +129,10 @@ int f5b_pack_bf16(const float* x, int ld_in, void* out_bf16, int ld_out, int row
 int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float dt, void* y_bf16, int ld_bf, float* vel_out,
                   int rows, int C, f5b_stream_t stream);
 
+/* same, with (cfg, dt) read from device memory params_dev[0..1]: lets one captured CUDA graph serve every ODE step */
+int f5b_cfg_euler_dev(float* y, const float* pc, const float* pu, const float* params_dev, void* y_bf16, int ld_bf, float* vel_out,
+                      int rows, int C, f5b_stream_t stream);
+
 /* MelSpec "vocos" (model/modules.py:83-101): wav f32 [B, L] -> log-mel f32 [B, T, n_mels] (token-major, T = 1 + L/256):
  * reflect-pad 512, periodic Hann(1024), |rFFT1024|, fb f32 [513, n_mels], log(clamp 1e-5). */
 int f5b_melspec(const float* wav, const float* fb, const int32_t* ranges /* [n_mels,2] nonzero rows [f0,f1) of each fb column */,
@@ -243,6 +247,9 @@ int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* w
 #define F5B_NUM_KERNEL_KINDS 6
 void f5b_prof_reset(int enable);
 int f5b_prof_read(double* out, int n_kinds);
+int f5b_prof_enabled(void);
+/* add per-kind (launches, unused, flops, bytes) — used when a captured CUDA graph is replayed */
+void f5b_prof_add(const double* delta, int n_kinds);
 
 #ifdef __cplusplus
 }

@@ -163,3 +163,24 @@ def test_wrapper_generate_end_to_end(tmp_path):
     assert abs(wave_b.size - wave.size) <= 256 * 4
     out = w.generate("short text here.", output_path=str(tmp_path / "o.wav"), nfe_step=2)
     assert out.endswith("o.wav") and (tmp_path / "o.wav").stat().st_size > 1000
+
+
+def test_cuda_graph_step_matches_eager_launches(monkeypatch):
+    """the captured-graph ODE step (launch-bound small batches) must be bit-identical to the eager launch sequence,
+    on first use (capture) and on replay with new inputs"""
+    cfg = O.DiTConfig.tiny()
+    model, sd = build_cfm(cfg, 0)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("F5B_CUDA_GRAPH", mode)
+        res = []
+        for seed in (1234, 77):
+            cond, text, duration, lens = synthetic_inputs(cfg, 2, 40, [96, 83], seed=seed)
+            out, traj = model.sample(cond=cond.cuda(), text=text.cuda(), duration=duration.cuda(), lens=lens.cuda(), steps=3,
+                                     cfg_strength=2.0, sway_sampling_coef=-1.0, seed=0)
+            res.append((out.clone(), traj.clone()))
+        outs[mode] = res
+    torch.cuda.synchronize()
+    for (o0, t0), (o1, t1) in zip(outs["0"], outs["1"]):
+        assert torch.equal(o0, o1) and torch.equal(t0, t1)
+    assert not torch.equal(outs["1"][0][0], outs["1"][1][0])
