@@ -23,6 +23,7 @@ template <int MODE>
 struct ConvPosProblem {
   static constexpr int BN = 64;
   static constexpr int STORE = STORE_DIRECT;
+  static constexpr int CLUSTER = 1;
   int B, n, D, groups, cpg, NP, ksize, pad, n_tiles_seq;
   const float* bias;
   __nv_bfloat16* out;
@@ -34,7 +35,8 @@ struct ConvPosProblem {
     bool valid;
   };
 
-  __device__ __forceinline__ int num_tiles() const { return B * n_tiles_seq * groups; }
+  __device__ __forceinline__ int num_units() const { return B * n_tiles_seq * groups; }
+  __device__ __forceinline__ int unit_tile(int unit, uint32_t) const { return unit; }
   __device__ __forceinline__ int num_kblocks() const { return ksize; }
   __device__ __forceinline__ uint32_t umma_n() const { return NP; }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return NP * 128; }
@@ -49,7 +51,7 @@ struct ConvPosProblem {
     b = t2 / n_tiles_seq;
   }
   __device__ __forceinline__ void load(int tile, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar, const CUtensorMap* tmA,
-                                       const CUtensorMap* tmB) const {
+                                       const CUtensorMap* tmB, uint32_t) const {
     int b, nt, g;
     decode(tile, b, nt, g);
     tma_load_3d(sA, tmA, bar, g * cpg, nt * BM + kb - pad, b);

@@ -30,6 +30,7 @@ template <int BN_, int EPI, int ACT>
 struct LinearProblem {
   static constexpr int BN = BN_;
   static constexpr int STORE = (EPI == F5B_EPI_BF16) ? STORE_BF16 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
+  static constexpr int CLUSTER = 2;  // CTA pairs on vertically adjacent tiles share the weight tile through TMA multicast
   F5bGemmArgs g;
   int n_tiles, m_tiles, kblocks;
 
@@ -39,7 +40,12 @@ struct LinearProblem {
     const float* gate;
   };
 
-  __device__ __forceinline__ int num_tiles() const { return n_tiles * m_tiles; }
+  // work unit = (pair of vertically adjacent m-blocks, n-block); CTA `rank` of the cluster takes m-block 2*mp + rank
+  __device__ __forceinline__ int num_units() const { return n_tiles * ((m_tiles + 1) / 2); }
+  __device__ __forceinline__ int unit_tile(int unit, uint32_t rank) const {
+    const int mp = unit / n_tiles, n_blk = unit - mp * n_tiles;
+    return (2 * mp + (int)rank) * n_tiles + n_blk;  // may address an m-block past the end: loads zero-fill, stores clip
+  }
   __device__ __forceinline__ int num_kblocks() const { return kblocks; }
   __device__ __forceinline__ uint32_t umma_n() const { return BN; }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
@@ -50,10 +56,11 @@ struct LinearProblem {
   __device__ __forceinline__ int out_col0(int tile) const { return (tile % n_tiles) * BN; }
   __device__ __forceinline__ int out_row0(int tile) const { return (tile / n_tiles) * BM; }
   __device__ __forceinline__ void load(int tile, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar, const CUtensorMap* tmA,
-                                       const CUtensorMap* tmB) const {
+                                       const CUtensorMap* tmB, uint32_t rank) const {
     const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
     tma_load_2d(sA, tmA, bar, kb * BK, m_blk * BM);
-    tma_load_2d(sB, tmB, bar, kb * BK, n_blk * BN);
+    // this CTA fetches rows [rank*BN/2, +BN/2) of the weight tile and multicasts them to both CTAs of the pair
+    tma_load_2d_mcast(sB + rank * (EngCfg<BN>::B_BYTES / 2), tmB, bar, kb * BK, n_blk * BN + (int)rank * (BN / 2), (uint16_t)0x3);
   }
   __device__ __forceinline__ RowCtx row_ctx(int tile, int r) const {
     RowCtx c;
@@ -188,7 +195,7 @@ static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
     F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
     if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
   }
-  return launch_engine(tmA, tmB, tmC, p, p.m_tiles * p.n_tiles, stream);
+  return launch_engine(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
 }
 
 template <int BN>
@@ -228,7 +235,7 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= sm_count()) ? 256 : 128;
   CUtensorMap tmA, tmB;
   if (make_tmap_2d(&tmA, A, 2, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda * 2, BK, BM, true)) return -1;
-  if (make_tmap_2d(&tmB, W, 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 2, BK, bn, true)) return -1;
+  if (make_tmap_2d(&tmB, W, 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 2, BK, bn / 2, true)) return -1;  // half tile per CTA
   return bn == 256 ? dispatch<256>(tmA, tmB, g, stream) : dispatch<128>(tmA, tmB, g, stream);
 }
 

@@ -3,7 +3,10 @@
 //
 // sm_100a design: persistent warp-specialised kernel, one CTA per SM, 320 threads.
 //   warp 0      : TMA producer — A tile [128 x 64] and B tile [umma_n x 64] (both K-major bf16) land in a ring of
-//                 128B-swizzled shared-memory stages, mbarrier complete_tx.
+//                 128B-swizzled shared-memory stages, mbarrier complete_tx.  With P::CLUSTER == 2 two CTAs that work on
+//                 vertically adjacent output tiles (same weight columns) form a cluster: each loads HALF of the B tile and
+//                 TMA-multicasts it into both CTAs' stages, which cuts the L2 -> SM traffic per FLOP by a third (the
+//                 linear GEMMs ran at the ~12 TB/s L2 cap without it); stage release is a multicast tcgen05.commit.
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected thread), UMMA 128 x N x 16 (kind::f16, bf16 in,
 //                 fp32 accumulate in TMEM), accumulator double-buffered (2 x BN columns) so the epilogue of tile i
 //                 overlaps the main loop of tile i+1.
@@ -62,6 +65,10 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int CL = P::CLUSTER;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int unit0 = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;      // first work unit of this CTA (cluster)
+  const int ustride = (CL > 1) ? (int)(gridDim.x / CL) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -72,7 +79,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], 1);
+        mbar_init(&empty[s], CL);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
@@ -85,10 +92,11 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total = p.num_tiles();
+  const int total = p.num_units();  // work units: tiles, or vertical tile pairs when CL == 2
   const int kblocks = p.num_kblocks();
 
   if (warp == 0) {
@@ -96,12 +104,13 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = Cfg::A_BYTES + p.b_tx_bytes();
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int unit = unit0; unit < total; unit += ustride) {
+        const int tile = p.unit_tile(unit, crank);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], tx);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          p.load(tile, kb, sa, sa + Cfg::A_BYTES, &full[stage], &tmA, &tmB);
+          p.load(tile, kb, sa, sa + Cfg::A_BYTES, &full[stage], &tmA, &tmB, crank);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -113,7 +122,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      for (int unit = unit0; unit < total; unit += ustride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -130,7 +139,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 1024, 16);
             umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -144,7 +154,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint8_t* stg = staging + ew * 4096;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int unit = unit0; unit < total; unit += ustride, ++it) {
+      const int tile = p.unit_tile(unit, crank);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ncols = p.tile_cols(tile);  // warp-uniform
@@ -228,6 +239,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -235,7 +247,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 template <class P>
-static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const P& p, int total_tiles,
+static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const P& p, int total_units,
                          cudaStream_t stream) {
   using Cfg = EngCfg<P::BN>;
   static bool configured = false;
@@ -244,8 +256,27 @@ static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     F5B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  kern<<<grid, ENGINE_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  constexpr int CL = P::CLUSTER;
+  const int max_clusters = sm_count() / CL;
+  const int nclusters = total_units < max_clusters ? total_units : max_clusters;
+  if constexpr (CL == 1) {
+    kern<<<nclusters, ENGINE_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nclusters * CL);
+    cfg.blockDim = dim3(ENGINE_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    F5B_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
+  }
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
