@@ -31,7 +31,10 @@ constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage
 constexpr uint32_t ATT_V_BYTES = ATT_NV * 128;             // 10 KB per stage: 80 rows x (64 kv x 2 B)
 constexpr uint32_t ATT_V_TX = 64 * 128;                    // bytes TMA writes per V' tile (the 64 real rows)
 constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer, 2 buffers
-constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + ATT_KV_STAGES * (ATT_K_BYTES + ATT_V_BYTES) + 2 * ATT_P_BYTES + 1024 + 256;
+#ifndef ATT_EXTRA_SMEM
+#define ATT_EXTRA_SMEM 0  // experiments: pad shared memory to force one CTA per SM
+#endif
+constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + ATT_KV_STAGES * (ATT_K_BYTES + ATT_V_BYTES) + 2 * ATT_P_BYTES + 1024 + 256 + ATT_EXTRA_SMEM;
 constexpr uint32_t ATT_TMEM_COLS = 256;  // S0: 0..63, S1: 64..127, O: 128..207
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
@@ -272,39 +275,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(tS + 32, s1);
       tmem_ld_wait();
       ATT_MARK(1)
-      const float m_tile = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32)));
-      const float mt = m_tile * sl2;
-      // lazy rescale (warp-uniform decision; tcgen05.ld/st are warp-collective)
-      if (j == 0) {
-        m_used = mt;
-      } else if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
-        const float m_new = fmaxf(m_used, mt);
-        const float f = ex2_approx(m_used - m_new);
-        m_used = m_new;
-        mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V'_{j-1} has landed in O
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_addr + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-          tmem_st32(tmem_O + lane_addr + c * 32, o);
-        }
-        tmem_st_wait();
-      }
+      // The exponentials are taken against the running reference maximum m_used, which only moves when a row maximum grows
+      // by more than 2^8 (lazy rescale).  They are therefore issued SPECULATIVELY, before this tile's maximum is known: the
+      // max reduction (FMNMX3) has no consumer inside the block and fills the issue slots in the shadow of the MUFU
+      // instructions.  In the rare case that the check fails, O is rescaled in TMEM and the tile's P is recomputed.
+      if (j == 0) m_used = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
       ATT_MARK(2)
-      // the P buffer was last read by P_{j-2} V'_{j-2}: already retired, because bar_s[pb] (S_j) was committed by the same
-      // thread after P_{j-2} V'_{j-2} was issued and tcgen05.commit covers every earlier MMA of that thread
-      ATT_MARK(3)
-      // P = exp2(S*sl2 - m_used) -> bf16 -> swizzled smem
+      uint8_t* p_row_ = p_row;
       if (valid == ATT_BKV) {
-        softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
-        softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
+        softmax_chunk<false>(s0, sl2, m_used, 32, p_row_, 0, rx);
+        softmax_chunk<false>(s1, sl2, m_used, 32, p_row_, 4, rx);
       } else {
-        softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
-        softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
+        softmax_chunk<true>(s0, sl2, m_used, valid, p_row_, 0, rx);
+        softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row_, 4, rx);
+      }
+      ATT_MARK(3)
+      if (j > 0) {
+        const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
+        // warp-uniform decision; tcgen05.ld/st are warp-collective
+        if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
+          const float m_new = fmaxf(m_used, mt);
+          const float f = ex2_approx(m_used - m_new);
+          m_used = m_new;
+          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V'_{j-1} has landed in O
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tmem_O + lane_addr + c * 32, o);
+          }
+          tmem_st_wait();
+          if (valid == ATT_BKV) {
+            softmax_chunk<false>(s0, sl2, m_used, 32, p_row_, 0, rx);
+            softmax_chunk<false>(s1, sl2, m_used, 32, p_row_, 4, rx);
+          } else {
+            softmax_chunk<true>(s0, sl2, m_used, valid, p_row_, 0, rx);
+            softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row_, 4, rx);
+          }
+        }
       }
       ATT_MARK(4)
       fence_proxy_async_smem();
