@@ -2,19 +2,20 @@
 // Replaces AttnProcessor's mask expansion + F.scaled_dot_product_attention + head merge
 // (/root/reference/src/f5_tts/model/modules.py:483-493; dropout_p = 0, see DESIGN.md "oracle adjustments").
 //
-// sm_100a design (one CTA = one 128-query tile of one (batch, head); two CTAs co-resident per SM):
+// sm_100a design (one CTA = one 128-query tile of one (batch, head); the kernel is latency-bound per CTA — measured: one
+// resident CTA/SM 320 TFLOP/s, two 577 — so it is built for THREE co-resident CTAs: 72 KB smem, 128 TMEM columns, <= 112 regs):
 //   warp 4 (one elected lane): TMA producer + tcgen05.mma issuer.  KV is consumed in tiles of 64 keys:
-//       S_j[128 x 64] = Q K_j^T    (K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM, DOUBLE-buffered: S_{j+1}
-//                                   and S_{j+2} are computed while the softmax warps still work on S_j)
-//       O[128 x 80]  += P_j V'_j   (P_j written to swizzled smem (double-buffered) by the softmax warps; V' = V^T from the
-//                                   QKV epilogue's transposed store plus a constant row of ones, so column 64 of O
-//                                   accumulates the softmax row sum on the tensor pipe; O stays resident in TMEM)
+//       S_j[128 x 64] = Q K_j^T    (K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM columns 0..63).  The softmax
+//                                   threads pull S_j into registers and release the buffer at once (bar_sfree), so S_{j+1} is
+//                                   computed while the exponentials of tile j run.
+//       O[128 x 64]  += P_j V_j    (P_j written to swizzled smem, double-buffered, by the softmax warps; V^T K-major from the
+//                                   QKV epilogue's transposed store; O stays resident in TMEM columns 64..127)
 //   warps 0..3: online softmax, thread = query row (tcgen05.ld 32x32b -> no cross-lane reductions), exp2 with the
-//       1/sqrt(d)*log2(e) scale folded in.  The running maximum is updated lazily: O (and with it the row sum) is rescaled in
-//       TMEM only when a row's maximum grew by more than 2^8, so most KV tiles cost no accumulator round trip and the
-//       softmax warps never wait for the tensor pipe in steady state (the kernel is MUFU.EX2-bound).
-//   K and V' live in 3-stage TMA rings.  Key-padding is a per-batch length bound: KV tiles past len[b] are never loaded,
-//   the last tile is masked by index.
+//       1/sqrt(d)*log2(e) scale folded in, row sum in a register.  The running maximum is updated lazily: O and the row sum
+//       are rescaled only when a row's maximum grew by more than 2^8, and the exponentials are issued speculatively
+//       before the tile's maximum is known (the rare miss rescales O in TMEM and recomputes the tile's P).
+//   K lives in a 2-stage TMA ring, V in one stage (its reload hides behind the next tile's softmax).  Key-padding is a per-batch
+//   length bound: KV tiles past len[b] are never loaded, the last tile is masked by index.
 #include "common.cuh"
 #include "f5b_internal.h"
 
@@ -22,20 +23,17 @@ namespace f5b {
 
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
-constexpr int ATT_SM_WARPS = 4;   // softmax warps: one per TMEM lane quadrant, thread = query row
-constexpr int ATT_THREADS = (ATT_SM_WARPS + 1) * 32;
-constexpr int ATT_NV = 80;                                  // 64 value columns + the ones row + zero padding to N % 16 == 0
-constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_THREADS = 160;
+constexpr int ATT_CTAS_PER_SM = 3;
 constexpr uint32_t ATT_Q_BYTES = ATT_BQ * 64 * 2;          // 16 KB
-constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage
-constexpr uint32_t ATT_V_BYTES = ATT_NV * 128;             // 10 KB per stage: 80 rows x (64 kv x 2 B)
-constexpr uint32_t ATT_V_TX = 64 * 128;                    // bytes TMA writes per V' tile (the 64 real rows)
+constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage, 2 stages
+constexpr uint32_t ATT_V_BYTES = 64 * ATT_BKV * 2;         // 8 KB, 1 stage: [64 d rows x 64 kv]
 constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer, 2 buffers
 #ifndef ATT_EXTRA_SMEM
-#define ATT_EXTRA_SMEM 0  // experiments: pad shared memory to force one CTA per SM
+#define ATT_EXTRA_SMEM 0  // experiments: pad shared memory to lower the number of resident CTAs
 #endif
-constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + ATT_KV_STAGES * (ATT_K_BYTES + ATT_V_BYTES) + 2 * ATT_P_BYTES + 1024 + 256 + ATT_EXTRA_SMEM;
-constexpr uint32_t ATT_TMEM_COLS = 256;  // S0: 0..63, S1: 64..127, O: 128..207
+constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + 2 * ATT_P_BYTES + 1024 + 128 + ATT_EXTRA_SMEM;
+constexpr uint32_t ATT_TMEM_COLS = 128;  // S: 0..63, O: 64..127
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
@@ -46,37 +44,23 @@ struct AttnParams {
   long long* trace;  // debug only (ATT_TRACE builds)
 };
 
-// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel. error 7.5e-5, far below
-// the bf16 rounding of P): a fixed fraction of the exponentials is computed this way so the MUFU pipe, the bottleneck of the
-// softmax, gets fewer of them.  Valid for x <= ~100; inputs below -126 are clamped (result 2^-126 instead of 0).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05517143756151199f, 0.24261081218719482f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999281167984009f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-#ifndef ATT_POLY_MASK
-#define ATT_POLY_MASK 0x00  // which of every 8 consecutive columns use exp2_poly (bit i = column i).  Measured on B200
-                            // (profiles/r01_attention_notes.md): 0x00 577, 0x88 543, 0x92 518, 0xAA 486 TFLOP/s — the softmax warps
-                            // are issue/latency-bound, not MUFU-bound, at d_head 64, so the offload is off.
-#endif
-
+// P chunk: 32 columns -> exp2 -> bf16 -> swizzled smem row; returns the chunk's row-sum contribution
 template <bool MASKED>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx) {
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx) {
+  float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float x = fmaf(__uint_as_float(s[q * 8 + i]), sl2, -mb);
-      e[i] = ((ATT_POLY_MASK >> i) & 1) ? exp2_poly(x) : ex2_approx(x);
+      e[i] = ex2_approx(x);
       if constexpr (MASKED) {
         if (q * 8 + i >= lim) e[i] = 0.f;
       }
     }
+    sum0 += (e[0] + e[1]) + (e[2] + e[3]);
+    sum1 += (e[4] + e[5]) + (e[6] + e[7]);
     uint4 pk;
     pk.x = pack_bf16(e[0], e[1]);
     pk.y = pack_bf16(e[2], e[3]);
@@ -84,14 +68,7 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], float sl2
     pk.w = pack_bf16(e[6], e[7]);
     *reinterpret_cast<uint4*>(prow + (((cbase + q) ^ rx) << 4)) = pk;
   }
-}
-
-// named barrier shared by the two softmax warps of one TMEM lane quadrant (ids 1..4, 64 threads)
-__device__ __forceinline__ void pair_sync(int quad) {
-  if (quad == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-  else if (quad == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-  else if (quad == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-  else asm volatile("bar.sync 4, 64;" ::: "memory");
+  return sum0 + sum1;
 }
 
 // row maximum of the first `valid` of 32 raw scores (4 independent chains when the chunk is full)
@@ -114,7 +91,7 @@ __device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
   return m;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -122,16 +99,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_Q_BYTES;
-  uint8_t* sV = sK + ATT_KV_STAGES * ATT_K_BYTES;
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_V_BYTES;  // offset 16K + 24K + 30K = 70K: 1024-aligned
+  uint8_t* sV = sK + 2 * ATT_K_BYTES;
+  uint8_t* sP = sV + ATT_V_BYTES;  // 16K + 16K + 8K = 40K: 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;   // [3] K_j landed
-  uint64_t* bar_v = bars + 4;   // [3] V'_j landed
-  uint64_t* bar_s = bars + 7;   // [2] S_j in TMEM
-  uint64_t* bar_p = bars + 9;   // [2] P_j in smem, S_j consumed (128 arrivals)
-  uint64_t* bar_pv = bars + 11; // [2] P_j V'_j retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* bar_k = bars + 1;      // [2] K_j landed
+  uint64_t* bar_v = bars + 3;      // V_j landed
+  uint64_t* bar_s = bars + 4;      // S_j in TMEM
+  uint64_t* bar_sfree = bars + 5;  // S_j pulled into registers by all 128 softmax threads
+  uint64_t* bar_p = bars + 6;      // [2] P_j in smem (128 arrivals)
+  uint64_t* bar_pv = bars + 8;     // P_j V_j retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,93 +135,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
 
-  if (warp == ATT_SM_WARPS) {
+  if (warp == 4) {
     if (lane == 0) {
       prefetch_tmap(&tmQ);
       prefetch_tmap(&tmK);
       prefetch_tmap(&tmV);
       mbar_init(bar_q, 1);
-      for (int i = 0; i < ATT_KV_STAGES; ++i) {
-        mbar_init(&bar_k[i], 1);
-        mbar_init(&bar_v[i], 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&bar_s[i], 1);
-        mbar_init(&bar_p[i], ATT_SM_WARPS * 32);
-        mbar_init(&bar_pv[i], 1);
-      }
+      mbar_init(&bar_k[0], 1);
+      mbar_init(&bar_k[1], 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_sfree, 128);
+      mbar_init(&bar_p[0], 128);
+      mbar_init(&bar_p[1], 128);
+      mbar_init(bar_pv, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
-  } else if (warp < 4) {
-    // constant rows 64..79 of every V' stage: row 64 = ones (bf16 1.0), rows 65..79 = 0   (3 x 2 KB, 128 threads x 16 B)
-    const int t = threadIdx.x;  // 0..127
-    const uint32_t v = (t < 8) ? 0x3F803F80u : 0u;  // first 8 x 16 B = row 64 (identical chunks, swizzle-invariant)
-#pragma unroll
-    for (int st = 0; st < ATT_KV_STAGES; ++st)
-      *reinterpret_cast<uint4*>(sV + st * ATT_V_BYTES + 64 * 128 + t * 16) = make_uint4(v, v, v, v);
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 64;
 
-  if (warp == ATT_SM_WARPS) {
+  if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc_s = idesc_bf16(128, ATT_BKV, 0, 0);
-      const uint32_t idesc_o = idesc_bf16(128, ATT_NV, 0, 0);
+      const uint32_t idesc = idesc_bf16(128, 64, 0, 0);  // S and O tiles are both 128 x 64
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
       auto load_k = [&](int j) {
-        const int st = j % ATT_KV_STAGES;
-        mbar_arrive_expect_tx(&bar_k[st], ATT_K_BYTES);
-        tma_load_3d(sK + st * ATT_K_BYTES, &tmK, &bar_k[st], 0, j * ATT_BKV, bh);
+        mbar_arrive_expect_tx(&bar_k[j & 1], ATT_K_BYTES);
+        tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], 0, j * ATT_BKV, bh);
       };
       auto load_v = [&](int j) {
-        const int st = j % ATT_KV_STAGES;
-        mbar_arrive_expect_tx(&bar_v[st], ATT_V_TX);
-        tma_load_3d(sV + st * ATT_V_BYTES, &tmV, &bar_v[st], j * ATT_BKV, 0, bh);
+        mbar_arrive_expect_tx(bar_v, ATT_V_BYTES);
+        tma_load_3d(sV, &tmV, bar_v, j * ATT_BKV, 0, bh);
       };
       auto issue_s = [&](int j) {
-        const int st = j % ATT_KV_STAGES;
-        mbar_wait(&bar_k[st], (j / ATT_KV_STAGES) & 1);
+        mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t kb = k_addr + st * ATT_K_BYTES;
-        const uint32_t d = tmem_base + (j & 1) * 64;
+        const uint32_t kb = k_addr + (j & 1) * ATT_K_BYTES;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(d, smem_desc_sw128(q_addr + k * 32, 1024, 16), smem_desc_sw128(kb + k * 32, 1024, 16), idesc_s, k != 0);
-        umma_commit(&bar_s[j & 1]);
+          umma_bf16(tmem_base, smem_desc_sw128(q_addr + k * 32, 1024, 16), smem_desc_sw128(kb + k * 32, 1024, 16), idesc, k != 0);
+        umma_commit(bar_s);
       };
       // prologue
       mbar_arrive_expect_tx(bar_q, ATT_Q_BYTES);
       tma_load_3d(sQ, &tmQ, bar_q, 0, q0, bh);
-      for (int j = 0; j < ATT_KV_STAGES && j < T; ++j) load_k(j);
-      for (int j = 0; j < 2 && j < T; ++j) load_v(j);
+      load_k(0);
+      if (T > 1) load_k(1);
+      load_v(0);
       mbar_wait(bar_q, 0);
       issue_s(0);
-      if (T > 1) issue_s(1);
       for (int j = 0; j < T; ++j) {
-        const int pb = j & 1;
-        mbar_wait(&bar_p[pb], (j >> 1) & 1);  // P_j in smem, S_j consumed, O rescaled if needed
+        // S_j sits in registers: its TMEM buffer and K stage are free -> S_{j+1} overlaps the exponentials of tile j
+        mbar_wait(bar_sfree, j & 1);
         tc_fence_after();
-        const int vst = j % ATT_KV_STAGES;
-        mbar_wait(&bar_v[vst], (j / ATT_KV_STAGES) & 1);
+        if (j + 1 < T) issue_s(j + 1);
+        if (j + 2 < T) load_k(j + 2);  // stage j&1 held K_j
+        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);  // P_j in smem (and O rescaled if needed)
         tc_fence_after();
-        const uint32_t pa = p_addr + pb * ATT_P_BYTES;
-        const uint32_t vb = v_addr + vst * ATT_V_BYTES;
+        mbar_wait(bar_v, j & 1);
+        tc_fence_after();
+        const uint32_t pa = p_addr + (j & 1) * ATT_P_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(vb + kk * 32, 1024, 16), idesc_o, (j | kk) != 0);
-        umma_commit(&bar_pv[pb]);
-        if (j + 2 < T) issue_s(j + 2);  // S buffer pb is free (softmax consumed S_j before arriving on bar_p)
-        if (j + ATT_KV_STAGES < T) load_k(j + ATT_KV_STAGES);  // K stage of tile j is free (S_j retired long ago)
-        if (j + 2 < T) {
-          // V' stage (j+2)%3 was last read by P_{j-1} V'_{j-1}
-          if (j >= 1) mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          load_v(j + 2);
+          umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(v_addr + kk * 32, 1024, 16), idesc, (j | kk) != 0);
+        umma_commit(bar_pv);
+        if (j + 1 < T) {
+          mbar_wait(bar_pv, j & 1);  // the single V stage is free once P_j V_j retired
+          load_v(j + 1);
         }
       }
     }
@@ -252,6 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = warp * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     float m_used = -INFINITY;  // log2-domain maximum the exponentials are taken against
+    float l_run = 0.f;         // row sum of exp2(s - m_used)
     const float sl2 = p.scale_log2;
     const int rx = r & 7;
 #ifdef ATT_TRACE
@@ -263,33 +227,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
 
     for (int j = 0; j < T; ++j) {
-      const int pb = j & 1;
-      const uint32_t tS = tmem_base + lane_addr + pb * 64;
-      uint8_t* p_row = sP + pb * ATT_P_BYTES + r * 128;
+      uint8_t* p_row = sP + (j & 1) * ATT_P_BYTES + r * 128;
       const int valid = min(ATT_BKV, kvlen - j * ATT_BKV);  // CTA-uniform, >= 1
-      mbar_wait(&bar_s[pb], (j >> 1) & 1);
+      mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_MARK(0)
       uint32_t s0[32], s1[32];
-      tmem_ld32(tS, s0);
-      tmem_ld32(tS + 32, s1);
+      tmem_ld32(tmem_base + lane_addr, s0);
+      tmem_ld32(tmem_base + lane_addr + 32, s1);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_sfree);
       ATT_MARK(1)
-      // The exponentials are taken against the running reference maximum m_used, which only moves when a row maximum grows
-      // by more than 2^8 (lazy rescale).  They are therefore issued SPECULATIVELY, before this tile's maximum is known: the
-      // max reduction (FMNMX3) has no consumer inside the block and fills the issue slots in the shadow of the MUFU
-      // instructions.  In the rare case that the check fails, O is rescaled in TMEM and the tile's P is recomputed.
       if (j == 0) m_used = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
-      ATT_MARK(2)
-      uint8_t* p_row_ = p_row;
+      // bar_s(j) was committed after P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing
+      // thread), so the P buffer (j & 1) is free.  Exponentials are speculative w.r.t. this tile's maximum (see header).
+      float ts;
       if (valid == ATT_BKV) {
-        softmax_chunk<false>(s0, sl2, m_used, 32, p_row_, 0, rx);
-        softmax_chunk<false>(s1, sl2, m_used, 32, p_row_, 4, rx);
+        ts = softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
+        ts += softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
       } else {
-        softmax_chunk<true>(s0, sl2, m_used, valid, p_row_, 0, rx);
-        softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row_, 4, rx);
+        ts = softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
+        ts += softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
       }
-      ATT_MARK(3)
+      ATT_MARK(2)
       if (j > 0) {
         const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
         // warp-uniform decision; tcgen05.ld/st are warp-collective
@@ -297,10 +258,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float m_new = fmaxf(m_used, mt);
           const float f = ex2_approx(m_used - m_new);
           m_used = m_new;
-          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V'_{j-1} has landed in O
+          l_run *= f;
+          mbar_wait(bar_pv, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 3; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
             tmem_ld32(tmem_O + lane_addr + c * 32, o);
             tmem_ld_wait();
@@ -310,19 +272,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
           if (valid == ATT_BKV) {
-            softmax_chunk<false>(s0, sl2, m_used, 32, p_row_, 0, rx);
-            softmax_chunk<false>(s1, sl2, m_used, 32, p_row_, 4, rx);
+            ts = softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
+            ts += softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
           } else {
-            softmax_chunk<true>(s0, sl2, m_used, valid, p_row_, 0, rx);
-            softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row_, 4, rx);
+            ts = softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
+            ts += softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
           }
         }
       }
-      ATT_MARK(4)
+      l_run += ts;
+      ATT_MARK(3)
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[pb]);
-      ATT_MARK(5)
+      mbar_arrive(&bar_p[j & 1]);
+      ATT_MARK(4)
     }
 #ifdef ATT_TRACE
     if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 5 && lane == 0) {
@@ -330,17 +293,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       p.trace[warp * 8 + 6] = T;
     }
 #endif
-    // epilogue: O[:, :64] / O[:, 64]
-    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    // epilogue: O / l
+    mbar_wait(bar_pv, (T - 1) & 1);
     tc_fence_after();
     const int pos = q0 + r;
-    float inv;
-    {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_addr + 64, o);
-      tmem_ld_wait();
-      inv = (pos < kvlen) ? 1.f / __uint_as_float(o[0]) : 0.f;
-    }
+    const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -363,7 +320,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == ATT_SM_WARPS) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
