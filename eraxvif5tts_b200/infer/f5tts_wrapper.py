@@ -27,6 +27,8 @@ def convert_char_to_pinyin(text_list, polyphone=True):
     try:
         import jieba
         from pypinyin import Style, lazy_pinyin
+        if not hasattr(jieba, "cut"):
+            jieba = None
     except ImportError:
         jieba = None
     out = []

@@ -226,7 +226,9 @@ class DiTEngine:
         if n not in self._rope:
             inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=self.device).float() / 64))
             fr = torch.outer(torch.arange(n, device=self.device).float(), inv)
-            self._rope = {n: torch.stack((fr.cos(), fr.sin()), dim=-1).contiguous()}
+            if len(self._rope) >= 64:
+                self._rope.pop(next(iter(self._rope)))  # captured graphs keep their own reference (step_session)
+            self._rope[n] = torch.stack((fr.cos(), fr.sin()), dim=-1).contiguous()
         return self._rope[n]
 
     # ---- CUDA-graph step sessions (launch-bound regimes: small batches, e.g. the reference's serial B=1 chunks) ----
@@ -247,9 +249,9 @@ class DiTEngine:
             y=torch.zeros(Bx, n, mel, dtype=f32, device=dev), yb=torch.zeros(Bx * n, 128, dtype=bf16, device=dev),
             c0=torch.zeros(Bf, n, self.dim, dtype=f32, device=dev), pred=torch.zeros(Bf, n, mel, dtype=f32, device=dev),
             stepbuf=torch.zeros(self.mod_dim + 2, dtype=f32, device=dev),
-            lens=torch.full((Bx,), n, dtype=torch.int32, device=dev) if masked else None, graph=None, delta=None)
-        self.rope_table(n)
-        self.workspace(self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n))
+            lens=torch.full((Bx,), n, dtype=torch.int32, device=dev) if masked else None, graph=None, delta=None,
+            rope=self.rope_table(n), ws=None)  # the graph bakes these pointers in: the session keeps them alive
+        sess["ws"] = self.workspace(self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n))
         pc, pu = sess["pred"][:Bx], (sess["pred"][Bx:] if Bf > Bx else None)
         params = sess["stepbuf"][self.mod_dim:]
 

@@ -159,3 +159,59 @@ def test_two_rank_sharding_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok [19, 18]" in o or "ok [20, 17]" in o for o in outs), outs
+
+
+def _tiny_cfm():
+    from eraxvif5tts_b200.model import CFM, DiT
+    return CFM(transformer=DiT(dim=128, depth=3, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_num_embeds=10), mel_spec_kwargs={})
+
+
+def test_load_checkpoint_formats(tmp_path):
+    """reference checkpoint layouts (infer/f5tts_wrapper.py:201-254, model/trainer.py:521-598, model_pruning/*): .safetensors flat
+    EMA dict, .pt with ema_model_state_dict (ema_model. prefix + initted/step), .pt with model_state_dict (+ DDP 'module.' prefix,
+    legacy mel keys), pruned .pt with pruning_info"""
+    from safetensors.torch import save_file
+    from eraxvif5tts_b200.infer.utils_infer import load_checkpoint
+    torch.manual_seed(0)
+    src = _tiny_cfm()
+    with torch.no_grad():
+        for p in src.parameters():
+            p.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+
+    def check(path, **kw):
+        m = _tiny_cfm()
+        load_checkpoint(m, str(path), "cpu", **kw)
+        for k, v in sd.items():
+            assert torch.equal(m.state_dict()[k], v), k
+
+    ema = {"ema_model." + k: v for k, v in sd.items()}
+    ema.update({"initted": torch.tensor(True), "step": torch.tensor(7)})
+    save_file({k: v.contiguous() for k, v in ema.items() if k not in ("initted", "step")}, str(tmp_path / "m.safetensors"))
+    check(tmp_path / "m.safetensors", use_ema=True)
+    torch.save({"ema_model_state_dict": ema, "model_state_dict": {k: torch.zeros_like(v) for k, v in sd.items()}, "update": 5},
+               tmp_path / "ema.pt")
+    check(tmp_path / "ema.pt", use_ema=True)
+    legacy = {"module." + k: v for k, v in sd.items()}
+    legacy["mel_spec.mel_stft.mel_scale.fb"] = torch.zeros(3)
+    legacy["mel_spec.mel_stft.spectrogram.window"] = torch.zeros(3)
+    torch.save({"model_state_dict": legacy}, tmp_path / "plain.pt")
+    check(tmp_path / "plain.pt", use_ema=False)
+    torch.save({"model_state_dict": sd, "pruning_info": {"kept_blocks": [0, 1, 2], "original_depth": 5}}, tmp_path / "pruned.pt")
+    check(tmp_path / "pruned.pt", use_ema=False)
+
+
+def test_convert_char_to_pinyin_latin_path():
+    from eraxvif5tts_b200.infer.f5tts_wrapper import convert_char_to_pinyin
+    out = convert_char_to_pinyin(["Xin chào; “thế giới”"])
+    assert out[0] == list('Xin chào, "thế giới"')
+
+
+def test_wrapper_duration_rule_matches_reference_formula():
+    """f5tts_wrapper.py:498-503: duration = ref_len + int(ref_len / ref_bytes * gen_bytes / speed), speed 0.3 for < 10 bytes"""
+    from eraxvif5tts_b200.infer.f5tts_wrapper import F5TTSWrapper
+    w = F5TTSWrapper.__new__(F5TTSWrapper)
+    w.ref_text, w.ref_audio_len, w.target_sample_rate, w.hop_length = "abcdefghij. ", 200, 24000, 256
+    assert w._chunk_duration("x" * 24, 1.0, None) == 200 + int(200 / 12 * 24 / 1.0)
+    assert w._chunk_duration("short", 1.0, None) == 200 + int(200 / 12 * 5 / 0.3)
+    assert w._chunk_duration("anything", 1.0, 2.0) == int(2.0 * 24000 / 256)
