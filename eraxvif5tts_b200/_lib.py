@@ -77,6 +77,8 @@ SIGNATURES = {
     "f5b_vocos_destroy": (None, [vp]),
     "f5b_vocos_workspace_bytes": (sz, [vp, C.c_int, C.c_int]),
     "f5b_cfg_euler_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
+    "f5b_fm_prepare": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_masked_mse": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "f5b_prof_enabled": (C.c_int, []),
     "f5b_prof_add": (None, [C.POINTER(C.c_double), C.c_int]),
     "f5b_prof_reset": (None, [C.c_int]),

@@ -399,6 +399,60 @@ __global__ void im2col7_kernel(const float* __restrict__ mel, __nv_bfloat16* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Flow-matching training inputs and loss (CFM.forward, model/cfm.py:255-283):
+//   phi = (1 - t) x0 + t x1,  flow = x1 - x0,  cond = where(span_mask, 0, x1);   loss = mean over masked rows of (pred - flow)^2
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void fm_prepare_kernel(const float* __restrict__ x1, const float* __restrict__ x0, const float* __restrict__ time,
+                                  const uint8_t* __restrict__ span, float* __restrict__ phi, float* __restrict__ flow,
+                                  float* __restrict__ cond, int n, int C, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t row = i / C;
+  const int b = (int)(row / n);
+  const float t = time[b];
+  const float a = x1[i], z = x0[i];
+  phi[i] = (1.f - t) * z + t * a;
+  flow[i] = a - z;
+  cond[i] = span[row] ? 0.f : a;
+}
+
+__global__ void __launch_bounds__(256) masked_mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ flow,
+                                                                 const uint8_t* __restrict__ mask, float* __restrict__ partial,
+                                                                 int rows, int C) {
+  __shared__ float red[2][8];
+  float s = 0.f, cnt = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    if (!mask[r]) continue;  // block-uniform
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float d = pred[(size_t)r * C + c] - flow[(size_t)r * C + c];
+      s += d * d;
+      cnt += 1.f;
+    }
+  }
+  s = warp_sum(s);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    partial[blockIdx.x * 2] = a;
+    partial[blockIdx.x * 2 + 1] = b;
+  }
+}
+__global__ void masked_mse_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;  // fixed summation order: deterministic
+    for (int i = 0; i < nblk; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    out[0] = (float)(a / (b > 0.0 ? b : 1.0));
+    out[1] = (float)b;
+  }
+}
+
 }  // namespace f5b
 
 using namespace f5b;
@@ -485,6 +539,28 @@ int f5b_cfg_euler_dev(float* y, const float* pc, const float* pu, const float* p
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
   cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, 0.f, 0.f, params_dev,
                                                                           reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_fm_prepare(const float* x1, const float* x0, const float* time, const uint8_t* span_mask, float* phi, float* flow, float* cond,
+                   int B, int n, int C, f5b_stream_t stream) {
+  F5B_CHECK(x1 && x0 && time && span_mask && phi && flow && cond && B > 0 && n > 0 && C > 0, "f5b_fm_prepare: bad argument");
+  const int64_t tot = (int64_t)B * n * C;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 20.0 * tot);
+  fm_prepare_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x1, x0, time, span_mask, phi, flow, cond, n, C, tot);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_masked_mse(const float* pred, const float* flow, const uint8_t* mask, float* ws /*[2*1024]*/, float* out2, int rows, int C,
+                   f5b_stream_t stream) {
+  F5B_CHECK(pred && flow && mask && ws && out2 && rows > 0 && C > 0, "f5b_masked_mse: bad argument");
+  const int nblk = rows < 1024 ? rows : 1024;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * rows * C, 2);
+  masked_mse_partial_kernel<<<nblk, 256, 0, ST(stream)>>>(pred, flow, mask, ws, rows, C);
+  F5B_CUDA(cudaGetLastError());
+  masked_mse_final_kernel<<<1, 32, 0, ST(stream)>>>(ws, nblk, out2);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -195,7 +195,59 @@ class CFM(nn.Module):
             out = vocoder(out)
         return out, trajectory
 
-    def forward(self, inp, text, *, lens=None, noise_scheduler=None):
-        """Flow-matching training loss (cfm.py:210-283).  The backward kernels (dgrad / wgrad, attention backward, fused AdamW +
-        NCCL all-reduce) are scheduled for the next round (DESIGN.md "Out of scope this round"); fail loudly rather than fall back."""
-        raise NotImplementedError("CFM.forward (training) is not built yet: only the inference path runs on the CUDA library")
+    @torch.no_grad()
+    def forward(self, inp, text, *, lens=None, noise_scheduler=None, draws: dict | None = None):
+        """Flow-matching training loss, FORWARD ONLY (cfm.py:210-283): returns (loss, cond, pred) like the reference, computed by
+        the CUDA library, but carries no autograd graph — the backward kernels (dgrad / wgrad, attention backward, fused AdamW +
+        NCCL gradient all-reduce) are scheduled for the next round.  Usable for validation loss today.
+        `draws` (extension) fixes the random choices for parity tests: rand_span_mask, x0, time, drop_audio_cond, drop_text."""
+        from random import random
+        from .utils import mask_from_frac_lengths
+        eng = self.transformer.engine()
+        device = eng.device
+        inp = inp.to(device)
+        if inp.ndim == 2:
+            inp = self.mel_spec.forward_token_major(inp)
+            assert inp.shape[-1] == self.num_channels
+        x1 = inp.to(f32).contiguous()
+        batch, seq_len = x1.shape[:2]
+        if isinstance(text, list):
+            if exists(self.vocab_char_map):
+                text = list_str_to_idx(text, self.vocab_char_map).to(device)
+            else:
+                text = list_str_to_tensor(text).to(device)
+            assert text.shape[0] == batch
+        text = text.to(device)
+        if not exists(lens):
+            lens = torch.full((batch,), seq_len, device=device)
+        lens = lens.to(device)
+        mask = lens_to_mask(lens, length=seq_len)
+        draws = draws or {}
+        if "rand_span_mask" in draws:
+            rand_span_mask = draws["rand_span_mask"].to(device)
+        else:
+            frac_lengths = torch.zeros((batch,), device=device).float().uniform_(*self.frac_lengths_mask)
+            rand_span_mask = mask_from_frac_lengths(lens, frac_lengths)
+        rand_span_mask = rand_span_mask & mask
+        x0 = draws["x0"].to(device=device, dtype=f32).contiguous() if "x0" in draws else torch.randn_like(x1)
+        time = draws["time"].to(device=device, dtype=f32).contiguous() if "time" in draws else torch.rand((batch,), dtype=f32, device=device)
+        if "drop_audio_cond" in draws:
+            drop_audio_cond, drop_text = bool(draws["drop_audio_cond"]), bool(draws["drop_text"])
+        else:
+            drop_audio_cond = random() < self.audio_drop_prob  # per BATCH, Python RNG (cfm.py:266-271)
+            if random() < self.cond_drop_prob:
+                drop_audio_cond, drop_text = True, True
+            else:
+                drop_text = False
+        lib = L.load()
+        phi, flow, cond = torch.empty_like(x1), torch.empty_like(x1), torch.empty_like(x1)
+        span_u8 = rand_span_mask.to(torch.uint8).contiguous()
+        L.check(lib.f5b_fm_prepare(x1.data_ptr(), x0.data_ptr(), time.data_ptr(), span_u8.data_ptr(), phi.data_ptr(), flow.data_ptr(),
+                                   cond.data_ptr(), batch, seq_len, self.num_channels, L.stream()), "f5b_fm_prepare")
+        # no mask is passed to the transformer in training (cfm.py:275-277)
+        pred = self.transformer(x=phi, cond=cond, text=text, time=time, drop_audio_cond=drop_audio_cond, drop_text=drop_text)
+        ws = torch.empty(2048, dtype=f32, device=device)
+        out2 = torch.empty(2, dtype=f32, device=device)
+        L.check(lib.f5b_masked_mse(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), ws.data_ptr(), out2.data_ptr(), batch * seq_len,
+                                   self.num_channels, L.stream()), "f5b_masked_mse")
+        return out2[0], cond, pred

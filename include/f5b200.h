@@ -133,6 +133,15 @@ int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float d
 int f5b_cfg_euler_dev(float* y, const float* pc, const float* pu, const float* params_dev, void* y_bf16, int ld_bf, float* vel_out,
                       int rows, int C, f5b_stream_t stream);
 
+/* Flow-matching training inputs (CFM.forward, model/cfm.py:255-266): phi = (1-t) x0 + t x1, flow = x1 - x0,
+ * cond = where(span_mask, 0, x1).  x1, x0 f32 [B, n, C]; time f32 [B]; span_mask uint8 [B*n]. */
+int f5b_fm_prepare(const float* x1, const float* x0, const float* time, const uint8_t* span_mask, float* phi, float* flow, float* cond,
+                   int B, int n, int C, f5b_stream_t stream);
+/* Flow-matching loss (cfm.py:280-283): out2[0] = mean over rows with mask != 0 of (pred - flow)^2, out2[1] = element count.
+ * Deterministic two-pass reduction; ws f32 [2048]. */
+int f5b_masked_mse(const float* pred, const float* flow, const uint8_t* mask, float* ws, float* out2, int rows, int C,
+                   f5b_stream_t stream);
+
 /* MelSpec "vocos" (model/modules.py:83-101): wav f32 [B, L] -> log-mel f32 [B, T, n_mels] (token-major, T = 1 + L/256):
  * reflect-pad 512, periodic Hann(1024), |rFFT1024|, fb f32 [513, n_mels], log(clamp 1e-5). */
 int f5b_melspec(const float* wav, const float* fb, const int32_t* ranges /* [n_mels,2] nonzero rows [f0,f1) of each fb column */,

@@ -184,3 +184,28 @@ def test_cuda_graph_step_matches_eager_launches(monkeypatch):
     for (o0, t0), (o1, t1) in zip(outs["0"], outs["1"]):
         assert torch.equal(o0, o1) and torch.equal(t0, t1)
     assert not torch.equal(outs["1"][0][0], outs["1"][1][0])
+
+
+def test_cfm_forward_loss_vs_oracle():
+    """CFM.forward (flow-matching loss, forward only) with the random draws pinned: per-row times, span mask, CFG drops"""
+    cfg = O.DiTConfig.tiny()
+    model, sd = build_cfm(cfg, 0)
+    g = torch.Generator().manual_seed(5)
+    B, n = 3, 77
+    x1 = (torch.randn(B, n, cfg.mel_dim, generator=g) * 2 - 1.5).clamp(-11.5, 5)
+    x0 = torch.randn(B, n, cfg.mel_dim, generator=g)
+    time = torch.rand(B, generator=g)
+    text = torch.randint(0, cfg.text_num_embeds, (B, 12), generator=g)
+    lens = torch.tensor([77, 60, 33])
+    span = torch.zeros(B, n, dtype=torch.bool)
+    span[0, 20:70] = True
+    span[1, 5:55] = True
+    span[2, 10:30] = True
+    for da, dt in ((False, False), (True, False), (True, True)):
+        ref_loss, ref_cond, ref_pred = O.cfm_loss(sd, cfg, x1, text, span & (torch.arange(n)[None] < lens[:, None]), x0, time, da, dt)
+        loss, cond, pred = model(x1.cuda(), text.cuda(), lens=lens.cuda(),
+                                 draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=da, drop_text=dt))
+        torch.cuda.synchronize()
+        assert maxabs(cond, ref_cond) == 0.0
+        assert maxabs(pred, ref_pred) <= VEL_TOL
+        assert abs(float(loss) - float(ref_loss)) <= 2e-2 * float(ref_loss), (float(loss), float(ref_loss))

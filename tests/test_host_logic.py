@@ -115,10 +115,12 @@ def test_melspec_filterbank_matches_torchaudio():
         assert int(r[j, 0]) <= int(nzr.min()) and int(nzr.max()) < int(r[j, 1])
 
 
-def test_cfm_forward_is_loud_about_training():
+def test_cfm_forward_needs_cuda():
+    """CFM.forward (loss, forward only) has no CPU path either"""
+    from eraxvif5tts_b200 import _lib
     from eraxvif5tts_b200.model import CFM, DiT
     m = CFM(transformer=DiT(dim=128, depth=1, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_num_embeds=10), mel_spec_kwargs={})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.F5bError):
         m(torch.zeros(1, 8, 100), torch.zeros(1, 3, dtype=torch.long))
 
 
