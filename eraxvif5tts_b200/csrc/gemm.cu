@@ -152,29 +152,22 @@ struct LinearProblem {
       const int within = n0 - sec * Dm;
       const int head = within >> 6;
       const int dd0 = within & 63;  // 0 or 32
-      if (sec < 2) {
-        if (head < g.rope_heads) {
-          const float4* cs = reinterpret_cast<const float4*>(g.rope) + (size_t)c.pos * 16 + (dd0 >> 2);
+      if (sec < 2 && head < g.rope_heads) {
+        const float4* cs = reinterpret_cast<const float4*>(g.rope) + (size_t)c.pos * 16 + (dd0 >> 2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = __ldg(cs + i);  // (cos, sin) of two consecutive frequency pairs
-            const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
-            v[4 * i] = x0 * t.x - x1 * t.y;
-            v[4 * i + 1] = x1 * t.x + x0 * t.y;
-            v[4 * i + 2] = x2 * t.z - x3 * t.w;
-            v[4 * i + 3] = x3 * t.z + x2 * t.w;
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(cs + i);  // (cos, sin) of two consecutive frequency pairs
+          const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+          v[4 * i] = x0 * t.x - x1 * t.y;
+          v[4 * i + 1] = x1 * t.x + x0 * t.y;
+          v[4 * i + 2] = x2 * t.z - x3 * t.w;
+          v[4 * i + 3] = x3 * t.z + x2 * t.w;
         }
-        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? g.out : g.out2);
-        __nv_bfloat16* o = base + (((size_t)c.b * g.heads + head) * g.rows_per_batch + c.pos) * 64 + dd0;
-        store_row32_bf16(o, v, 32, true);
-      } else {
-        // v transposed: [B, H, 64, n_pad] so that P.V sees a K-major B operand; lanes = consecutive positions
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out3) +
-                           (((size_t)c.b * g.heads + head) * 64 + dd0) * g.n_pad + c.pos;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[(size_t)i * g.n_pad] = __float2bfloat16(v[i]);
       }
+      // q, k and v all head-major [B, H, n, 64]: the attention kernel reads v as an MN-major operand, no transposed copy
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? g.out : (sec == 1 ? g.out2 : g.out3));
+      __nv_bfloat16* o = base + (((size_t)c.b * g.heads + head) * g.rows_per_batch + c.pos) * 64 + dd0;
+      store_row32_bf16(o, v, 32, true);
     }
   }
 };
@@ -222,7 +215,7 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
             "f5b_gemm: row pitches must be >= K and multiples of 8 elements (lda %d ldw %d K %d)", lda, ldw, g.K);
   if (g.epi == F5B_EPI_QKV_ROPE) {
     F5B_CHECK(g.rope && g.out2 && g.out3 && g.rows_per_batch > 0 && g.heads > 0 && g.N == 3 * g.heads * 64 &&
-                  g.n_pad >= g.rows_per_batch && g.M % g.rows_per_batch == 0,
+                  g.M % g.rows_per_batch == 0,
               "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d n_pad %d)", g.N, g.heads, g.rows_per_batch, g.n_pad);
   }
   if (g.epi == F5B_EPI_GATE_RESID)

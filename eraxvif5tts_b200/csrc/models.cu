@@ -45,7 +45,7 @@ static DitWs carve_dit(const F5bDitDesc& d, int B, int n, void* ws) {
   w.hb = c.take<__nv_bfloat16>(rows * D);
   w.q = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
   w.k = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
-  w.vt = c.take<__nv_bfloat16>((size_t)B * H * 64 * round8(n));
+  w.vt = c.take<__nv_bfloat16>(rows * (size_t)H * 64);  // v, head-major like q and k
   w.ab = c.take<__nv_bfloat16>(rows * D);
   w.fb = c.take<__nv_bfloat16>(rows * F);
   w.bytes = c.off;

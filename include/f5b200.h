@@ -33,7 +33,7 @@ typedef void* f5b_stream_t; /* cudaStream_t */
 enum {
   F5B_EPI_BF16 = 0,       /* out bf16[M,ldc]  = act(acc + bias)                                               */
   F5B_EPI_F32 = 1,        /* out f32 [M,ldc]  = act(acc + bias) (+ addsrc[row,:])  ; optional bf16 copy in out2 */
-  F5B_EPI_QKV_ROPE = 2,   /* q,k head-major bf16 [B,H,n,64] (+ rotary on the first rope_heads heads), v transposed */
+  F5B_EPI_QKV_ROPE = 2,   /* q,k,v head-major bf16 [B,H,n,64] (+ rotary on the first rope_heads heads of q and k) */
   F5B_EPI_GATE_RESID = 3  /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
 };
 enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3 };
@@ -46,7 +46,7 @@ typedef struct F5bGemmArgs {
   int32_t ldc;
   void* out2;                /* F32: optional bf16 copy; QKV_ROPE: k base */
   int32_t ldc2;
-  void* out3;                /* QKV_ROPE: v^T base, bf16 [B,H,64,n_pad] */
+  void* out3;                /* QKV_ROPE: v base, bf16 [B,H,n,64] */
   const float* addsrc;       /* F32: optional f32 [M,ld_add] added to the result */
   int32_t ld_add;
   int32_t rows_per_batch;    /* QKV_ROPE / GATE_RESID: n (positions per batch row) */
@@ -57,7 +57,7 @@ typedef struct F5bGemmArgs {
   const float* rope;         /* QKV_ROPE: f32 [n, 32, 2] (cos, sin) */
   int32_t rope_heads;        /* QKV_ROPE: heads that get the rotary embedding (pe_attn_head; H for all) */
   int32_t heads;             /* QKV_ROPE: H (N must be 3*H*64) */
-  int32_t n_pad;             /* QKV_ROPE: row pitch of v^T (multiple of 8, >= rows_per_batch) */
+  int32_t n_pad;             /* unused (kept for ABI stability) */
 } F5bGemmArgs;
 
 const char* f5b_last_error(void);
@@ -82,10 +82,11 @@ int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32
                   f5b_stream_t stream);
 
 /* Non-causal softmax(QK^T/sqrt(64))V with a per-batch key length (AttnProcessor, model/modules.py:483-493,
- * dropout_p = 0).  q,k bf16 [B*H, n, 64]; vt bf16 [B*H, 64, n_pad]; out bf16 [B*n, H*64] token-major.
+ * dropout_p = 0).  q,k,v bf16 [B*H, n, 64] (v is consumed as an MN-major tcgen05 operand); out bf16 [B*n, H*64] token-major;
+ * n_pad is ignored.
  * lens int32 [lens_mod] (kv length of batch b = lens[b % lens_mod]) or NULL (= n).  Query rows >= len are written
  * as zeros (the reference zeroes them after to_out, :499-501). */
-int f5b_attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B,
+int f5b_attn_fwd(const void* q, const void* k, const void* v, void* out, const int32_t* lens, int lens_mod, int B,
                  int H, int n, int n_pad, float scale, f5b_stream_t stream);
 
 /* ConvPositionEmbedding conv layer (model/modules.py:171-176,183-185): grouped Conv1d(k, groups, pad k/2) + Mish.

@@ -9,7 +9,7 @@ n_pad = (n + 7) // 8 * 8
 dev = "cuda"
 q = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
 k = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
-vt = torch.randn(B, H, 64, n_pad, device=dev).to(torch.bfloat16)
+vt = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
 out = torch.empty(B * n, H * 64, dtype=torch.bfloat16, device=dev)
 tr = torch.zeros(64, dtype=torch.int64, device=dev)
 lib.f5b_debug_set_attn_trace(tr.data_ptr())

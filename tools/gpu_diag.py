@@ -112,7 +112,7 @@ def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     rope = torch.stack((fr.cos(), fr.sin()), dim=-1).contiguous()  # [n,32,2]
     q = torch.full((B, H, n, 64), float("nan"), dtype=bf16, device=dev)
     k = torch.full((B, H, n, 64), float("nan"), dtype=bf16, device=dev)
-    vt = torch.zeros((B, H, 64, n_pad), dtype=bf16, device=dev)
+    vt = torch.zeros((B, H, n, 64), dtype=bf16, device=dev)
     ops.gemm(h, w, epi=L.EPI_QKV_ROPE, bias=bias, out=q, out2=k, out3=vt, rows_per_batch=n, rope=rope, rope_heads=rope_heads, heads=H,
              n_pad=n_pad)
     torch.cuda.synchronize()
@@ -121,7 +121,7 @@ def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     qr, kr, vr = qkv[0].clone(), qkv[1].clone(), qkv[2]
     qr[:, :rope_heads] = rope_ref(qr[:, :rope_heads], fr2)
     kr[:, :rope_heads] = rope_ref(kr[:, :rope_heads], fr2)
-    report(f"qkv_rope_B{B}H{H}n{n}", q_rel=relerr(q, qr), k_rel=relerr(k, kr), vt_rel=relerr(vt[..., :n], vr.transpose(-1, -2)))
+    report(f"qkv_rope_B{B}H{H}n{n}", q_rel=relerr(q, qr), k_rel=relerr(k, kr), vt_rel=relerr(vt, vr))
     # attention on the kernel's own (bf16) q, k, v
     lens = None
     if lens_list is not None:
@@ -129,7 +129,7 @@ def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     out = torch.full((B * n, D), float("nan"), dtype=bf16, device=dev)
     ops.attn_fwd(q, k, vt, out, lens, 0, B, H, n, n_pad)
     torch.cuda.synchronize()
-    qf, kf, vf = q.float(), k.float(), vt[..., :n].float().transpose(-1, -2)
+    qf, kf, vf = q.float(), k.float(), vt.float()
     s = qf @ kf.transpose(-1, -2) / 8.0
     if lens is not None:
         km = torch.arange(n, device=dev)[None, :] < lens[:, None]
@@ -288,7 +288,7 @@ def bench_epilogues(B=32, n=1875, D=1024):
     rope = torch.randn(n, 32, 2, device=dev)
     q = torch.empty(B, H, n, 64, dtype=bf16, device=dev)
     k = torch.empty_like(q)
-    vt = torch.empty(B, H, 64, n_pad, dtype=bf16, device=dev)
+    vt = torch.empty(B, H, n, 64, dtype=bf16, device=dev)
     x = torch.randn(M, D, device=dev)
     gate = torch.randn(D, device=dev) * 0.1
     lens = torch.full((B // 2,), n, dtype=torch.int32, device=dev)
@@ -326,7 +326,7 @@ def bench_attn(B, H, n, iters=10):
     n_pad = (n + 7) // 8 * 8
     q = torch.randn(B, H, n, 64, device=dev).to(bf16)
     k = torch.randn(B, H, n, 64, device=dev).to(bf16)
-    vt = torch.randn(B, H, 64, n_pad, device=dev).to(bf16)
+    vt = torch.randn(B, H, n, 64, device=dev).to(bf16)
     out = torch.empty(B * n, H * 64, dtype=bf16, device=dev)
     for _ in range(3):
         ops.attn_fwd(q, k, vt, out, None, 0, B, H, n, n_pad)
@@ -339,7 +339,7 @@ def bench_attn(B, H, n, iters=10):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = 4.0 * B * H * n * n * 64
-    v = vt[..., :n].transpose(-1, -2).contiguous()
+    v = vt
     for _ in range(3):
         F.scaled_dot_product_attention(q, k, v)
     e0.record()

@@ -7,7 +7,7 @@ n_pad = (n + 7) // 8 * 8
 dev = "cuda"
 q = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
 k = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
-vt = torch.randn(B, H, 64, n_pad, device=dev).to(torch.bfloat16)
+vt = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
 out = torch.empty(B * n, H * 64, dtype=torch.bfloat16, device=dev)
 for _ in range(3):
     ops.attn_fwd(q, k, vt, out, None, 0, B, H, n, n_pad)
