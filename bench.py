@@ -257,7 +257,10 @@ def main():
     # recorded inside a replay, so for those the kernel breakdown comes from one extra eager, event-bracketed step after the
     # timed region.  GPU-bound workloads (cfg2, cfg3) are event-bracketed live inside the timed region.
     from eraxvif5tts_b200.model import cfm as cfm_mod
-    graph_mode = os.environ.get("F5B_CUDA_GRAPH", "") != "0" and (2 * B * total <= cfm_mod.GRAPH_MAX_ROWS or os.environ.get("F5B_CUDA_GRAPH") == "1")
+    graphs_on = os.environ.get("F5B_CUDA_GRAPH", "") != "0" and (2 * B * total <= cfm_mod.GRAPH_MAX_ROWS or os.environ.get("F5B_CUDA_GRAPH") == "1")
+    # GPU-bound batches (>= 16k fused rows): bracket every launch with CUDA events live in the timed region (this turns the graph
+    # replay off for that region; the un-profiled e2e leg below uses it).  Launch-bound batches: time the graph path, profile after.
+    graph_mode = graphs_on and (2 * B * total <= 16384 or args.no_profile)
     live_profile = (not args.no_profile) and not graph_mode
     L.prof_reset(live_profile)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -24,9 +24,10 @@ from .utils import default, exists, lens_to_mask, list_str_to_idx, list_str_to_t
 
 f32, bf16 = torch.float32, torch.bfloat16
 
-# Replay one captured CUDA graph per ODE step when the fused batch is small enough to be launch-bound (the reference's own
-# serial B=1 chunk loop).  F5B_CUDA_GRAPH=0 disables, =1 forces it for every shape.
-GRAPH_MAX_ROWS = 16384
+# One captured CUDA graph per ODE step (164 kernel launches + the CFG/Euler update), replayed for every step and every later
+# sample() call of the same shape: decisive for launch-bound small batches (the reference's serial B=1 chunk loop: 8.2k -> 13.1k
+# frames/s) and still worth ~1 % at batch 16.  F5B_CUDA_GRAPH=0 disables it; per-launch event profiling disables it too.
+GRAPH_MAX_ROWS = 1 << 30
 
 
 class CFM(nn.Module):
