@@ -48,7 +48,7 @@ SIGNATURES = {
     "f5b_gemm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.POINTER(GemmArgs), vp]),
     "f5b_ln_modulate": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, vp]),
-    "f5b_attn_fwd": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_attn_fwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_convpos": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos_packed_elems": (sz, [C.c_int, C.c_int, C.c_int]),

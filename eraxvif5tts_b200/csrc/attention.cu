@@ -168,11 +168,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
       auto load_k = [&](int j) {
         mbar_arrive_expect_tx(&bar_k[j & 1], ATT_K_BYTES);
-        tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], 0, j * ATT_BKV, bh);
+        tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], h * 64, j * ATT_BKV, b);
       };
       auto load_v = [&](int j) {
         mbar_arrive_expect_tx(bar_v, ATT_V_BYTES);
-        tma_load_3d(sV, &tmV, bar_v, 0, j * ATT_BKV, bh);
+        tma_load_3d(sV, &tmV, bar_v, h * 64, j * ATT_BKV, b);
       };
       auto issue_s = [&](int j) {
         mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
@@ -185,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       // prologue
       mbar_arrive_expect_tx(bar_q, ATT_Q_BYTES);
-      tma_load_3d(sQ, &tmQ, bar_q, 0, q0, bh);
+      tma_load_3d(sQ, &tmQ, bar_q, h * 64, q0, b);
       load_k(0);
       if (T > 1) load_k(1);
       load_v(0);
@@ -332,17 +332,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 long long* g_attn_trace = nullptr;
 
-int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
-             int n_pad, float scale, cudaStream_t stream) {
-  F5B_CHECK(q && k && vt && out, "f5b_attn_fwd: null pointer");
-  F5B_CHECK(B > 0 && H > 0 && n > 0, "f5b_attn_fwd: bad shape B %d H %d n %d", B, H, n);
-  (void)n_pad;
+int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
+             float scale, cudaStream_t stream) {
+  F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
+  F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
+  // q, k, v are token-major matrices [B*n, ld] (e.g. the three column sections of the fused QKV GEMM output); head h of
+  // batch row b is the strided box (cols h*64.., rows b*n + pos) — TMA gathers it, no head-major copy exists
   CUtensorMap tmQ, tmK, tmV;
-  const uint64_t bh = (uint64_t)B * H;
-  if (make_tmap_3d(&tmQ, q, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BQ, 1, true)) return -1;
-  if (make_tmap_3d(&tmK, k, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BKV, 1, true)) return -1;
-  if (make_tmap_3d(&tmV, vt, 2, 64, (uint64_t)n, bh, 128, (uint64_t)n * 128, 64, ATT_BKV, 1, true)) return -1;  // v head-major like k
+  const uint64_t hw = (uint64_t)H * 64, pitch = (uint64_t)ld * 2;
+  if (make_tmap_3d(&tmQ, q, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, ATT_BQ, 1, true)) return -1;
+  if (make_tmap_3d(&tmK, k, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, ATT_BKV, 1, true)) return -1;
+  if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, ATT_BKV, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
@@ -365,9 +366,9 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* out, const int3
 
 }  // namespace f5b
 
-extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* vt, void* out, const int32_t* lens, int lens_mod, int B,
-                            int H, int n, int n_pad, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, vt, out, lens, lens_mod, B, H, n, n_pad, scale, static_cast<cudaStream_t>(stream));
+extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod,
+                            int B, int H, int n, float scale, f5b_stream_t stream) {
+  return f5b::attn_fwd(q, k, v, ld, out, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }

@@ -29,7 +29,7 @@ __device__ __forceinline__ float activate(float x) {
 template <int BN_, int EPI, int ACT>
 struct LinearProblem {
   static constexpr int BN = BN_;
-  static constexpr int STORE = (EPI == F5B_EPI_BF16) ? STORE_BF16 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
+  static constexpr int STORE = (EPI == F5B_EPI_BF16 || EPI == F5B_EPI_QKV_ROPE) ? STORE_BF16 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
   static constexpr int CLUSTER = 2;  // CTA pairs on vertically adjacent tiles share the weight tile through TMA multicast
   F5bGemmArgs g;
   int n_tiles, m_tiles, kblocks;
@@ -108,6 +108,26 @@ struct LinearProblem {
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(__uint_as_float(r[i]) + b[i]);
+      if constexpr (EPI == F5B_EPI_QKV_ROPE) {
+        // x_transformers.apply_rotary_pos_emb on the first rope_heads heads of q and k (model/modules.py:470-480): interleaved
+        // pairs (2i, 2i+1), angle pos * 10000^(-2i/64), fp32 math.  Output stays token-major [rows, 3D] (q | k | v); the
+        // attention kernel addresses heads through strided TMA boxes, so no head-split scatter exists.
+        const int Dm = g.heads * 64;
+        const int sec = n0 / Dm;
+        const int within = n0 - sec * Dm;
+        if (sec < 2 && (within >> 6) < g.rope_heads) {
+          const float4* cs = reinterpret_cast<const float4*>(g.rope) + (size_t)c.pos * 16 + ((within & 63) >> 2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(cs + i);  // (cos, sin) of two consecutive frequency pairs
+            const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+            v[4 * i] = x0 * t.x - x1 * t.y;
+            v[4 * i + 1] = x1 * t.x + x0 * t.y;
+            v[4 * i + 2] = x2 * t.z - x3 * t.w;
+            v[4 * i + 3] = x3 * t.z + x2 * t.w;
+          }
+        }
+      }
     }
   }
 
@@ -144,30 +164,6 @@ struct LinearProblem {
         __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + (size_t)c.row * g.ldc2 + n0;
         store_row32_bf16(o2, v, left, (g.ldc2 & 7) == 0);
       }
-    } else if constexpr (EPI == F5B_EPI_QKV_ROPE) {
-      // head split of model/modules.py:457-465 + x_transformers.apply_rotary_pos_emb on the first rope_heads heads
-      // of q and k (:470-480): interleaved pairs (2i, 2i+1), angle pos * 10000^(-2i/64), fp32 math.
-      const int Dm = g.heads * 64;
-      const int sec = n0 / Dm;
-      const int within = n0 - sec * Dm;
-      const int head = within >> 6;
-      const int dd0 = within & 63;  // 0 or 32
-      if (sec < 2 && head < g.rope_heads) {
-        const float4* cs = reinterpret_cast<const float4*>(g.rope) + (size_t)c.pos * 16 + (dd0 >> 2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldg(cs + i);  // (cos, sin) of two consecutive frequency pairs
-          const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
-          v[4 * i] = x0 * t.x - x1 * t.y;
-          v[4 * i + 1] = x1 * t.x + x0 * t.y;
-          v[4 * i + 2] = x2 * t.z - x3 * t.w;
-          v[4 * i + 3] = x3 * t.z + x2 * t.w;
-        }
-      }
-      // q, k and v all head-major [B, H, n, 64]: the attention kernel reads v as an MN-major operand, no transposed copy
-      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(sec == 0 ? g.out : (sec == 1 ? g.out2 : g.out3));
-      __nv_bfloat16* o = base + (((size_t)c.b * g.heads + head) * g.rows_per_batch + c.pos) * 64 + dd0;
-      store_row32_bf16(o, v, 32, true);
     }
   }
 };
@@ -214,9 +210,8 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   F5B_CHECK(lda >= g.K && ldw >= g.K && (lda & 7) == 0 && (ldw & 7) == 0,
             "f5b_gemm: row pitches must be >= K and multiples of 8 elements (lda %d ldw %d K %d)", lda, ldw, g.K);
   if (g.epi == F5B_EPI_QKV_ROPE) {
-    F5B_CHECK(g.rope && g.out2 && g.out3 && g.rows_per_batch > 0 && g.heads > 0 && g.N == 3 * g.heads * 64 &&
-                  g.M % g.rows_per_batch == 0,
-              "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d n_pad %d)", g.N, g.heads, g.rows_per_batch, g.n_pad);
+    F5B_CHECK(g.rope && g.rows_per_batch > 0 && g.heads > 0 && g.N == 3 * g.heads * 64 && g.M % g.rows_per_batch == 0,
+              "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d)", g.N, g.heads, g.rows_per_batch);
   }
   if (g.epi == F5B_EPI_GATE_RESID)
     F5B_CHECK(g.rows_per_batch > 0 && (g.gate_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.gate) & 15) == 0,

@@ -32,7 +32,7 @@ struct Carver {
 
 struct DitWs {
   float* x;
-  __nv_bfloat16 *hb, *q, *k, *vt, *ab, *fb;
+  __nv_bfloat16 *hb, *qkv, *ab, *fb;
   size_t bytes;
 };
 
@@ -43,9 +43,7 @@ static DitWs carve_dit(const F5bDitDesc& d, int B, int n, void* ws) {
   DitWs w;
   w.x = c.take<float>(rows * D);
   w.hb = c.take<__nv_bfloat16>(rows * D);
-  w.q = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
-  w.k = c.take<__nv_bfloat16>(rows * (size_t)H * 64);
-  w.vt = c.take<__nv_bfloat16>(rows * (size_t)H * 64);  // v, head-major like q and k
+  w.qkv = c.take<__nv_bfloat16>(rows * (size_t)H * 64 * 3);  // token-major [rows, 3D]: q | k | v
   w.ab = c.take<__nv_bfloat16>(rows * D);
   w.fb = c.take<__nv_bfloat16>(rows * F);
   w.bytes = c.off;
@@ -179,7 +177,6 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
   F5B_CHECK(Bx > 0 && Bf > 0 && Bf % Bx == 0 && n > 0, "f5b_dit_forward: Bf (%d) must be a multiple of Bx (%d)", Bf, Bx);
   const F5bDitDesc& d = h->d;
   const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads;
-  const int n_pad = round8(n);
   const int rows = Bf * n;
   DitWs w = carve_dit(d, Bf, n, ws);
   F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
@@ -207,10 +204,10 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
     memset(&g, 0, sizeof(g));
     g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
     g.bias = d.qkv_b + (size_t)i * 3 * D;
-    g.out = w.q; g.out2 = w.k; g.out3 = w.vt;
-    g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H; g.n_pad = n_pad;
+    g.out = w.qkv; g.ldc = 3 * D;
+    g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
     F5B_TRY(gemm(w.hb, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
-    F5B_TRY(attn_fwd(w.q, w.k, w.vt, w.ab, lens, batch_mod, Bf, H, n, n_pad, 0.125f, s));
+    F5B_TRY(attn_fwd(w.qkv, w.qkv + D, w.qkv + 2 * D, 3 * D, w.ab, lens, batch_mod, Bf, H, n, 0.125f, s));
     F5B_TRY(linear_gate_resid(w.ab, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
                               mod_bstride, lens, batch_mod, s));
     F5B_TRY(ln_modulate(w.x, m + 4 * D, m + 3 * D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));

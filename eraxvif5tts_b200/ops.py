@@ -72,10 +72,14 @@ def ln_affine(x, w, b, eps=1e-6, out_f32=None, out_bf16=None):
             "f5b_ln_affine")
 
 
-def attn_fwd(q, k, vt, out, lens, lens_mod, B, H, n, n_pad, scale=0.125):
+def attn_fwd(q, k, v, ld, out, lens, lens_mod, B, H, n, scale=0.125):
+    """q, k, v: bf16 views into token-major [B*n, ld] matrices (column 0 of each = head 0)"""
     lib = L.load()
-    _chk(q, bf16, "q"); _chk(k, bf16, "k"); _chk(vt, bf16, "vt"); _chk(out, bf16, "out"); _chk(lens, torch.int32, "lens")
-    L.check(lib.f5b_attn_fwd(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), L.ptr(lens), lens_mod, B, H, n, n_pad, scale,
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        if not t.is_cuda or t.dtype != bf16:
+            raise L.F5bError(f"{nm}: expected a CUDA bf16 tensor")
+    _chk(lens, torch.int32, "lens")
+    L.check(lib.f5b_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), L.ptr(lens), lens_mod, B, H, n, scale,
                              L.stream()), "f5b_attn_fwd")
     return out
 

@@ -33,7 +33,7 @@ typedef void* f5b_stream_t; /* cudaStream_t */
 enum {
   F5B_EPI_BF16 = 0,       /* out bf16[M,ldc]  = act(acc + bias)                                               */
   F5B_EPI_F32 = 1,        /* out f32 [M,ldc]  = act(acc + bias) (+ addsrc[row,:])  ; optional bf16 copy in out2 */
-  F5B_EPI_QKV_ROPE = 2,   /* q,k,v head-major bf16 [B,H,n,64] (+ rotary on the first rope_heads heads of q and k) */
+  F5B_EPI_QKV_ROPE = 2,   /* out bf16[M,ldc] = acc + bias with rotary embedding on the first rope_heads heads of the q and k sections */
   F5B_EPI_GATE_RESID = 3  /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
 };
 enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3 };
@@ -42,14 +42,14 @@ typedef struct F5bGemmArgs {
   int32_t M, N, K;
   int32_t epi, act;
   const float* bias;         /* [N] or NULL */
-  void* out;                 /* see epilogue; for QKV_ROPE: q base */
+  void* out;                 /* see epilogue */
   int32_t ldc;
-  void* out2;                /* F32: optional bf16 copy; QKV_ROPE: k base */
+  void* out2;                /* F32: optional bf16 copy */
   int32_t ldc2;
-  void* out3;                /* QKV_ROPE: v base, bf16 [B,H,n,64] */
+  void* out3;                /* unused (kept for ABI stability) */
   const float* addsrc;       /* F32: optional f32 [M,ld_add] added to the result */
   int32_t ld_add;
-  int32_t rows_per_batch;    /* QKV_ROPE / GATE_RESID: n (positions per batch row) */
+  int32_t rows_per_batch;    /* QKV_ROPE / GATE_RESID: n (positions per batch row; position = row % n) */
   const float* gate;         /* GATE_RESID: f32 gate, element (b, col) at gate[b*gate_bstride + col]; NULL -> 1 */
   int64_t gate_bstride;
   const int32_t* lens;       /* GATE_RESID: int32 [B] valid length per batch row, or NULL (all rows valid) */
@@ -81,13 +81,14 @@ int f5b_ln_modulate(const float* x, const float* scale, const float* shift, int6
 int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
                   f5b_stream_t stream);
 
-/* Non-causal softmax(QK^T/sqrt(64))V with a per-batch key length (AttnProcessor, model/modules.py:483-493,
- * dropout_p = 0).  q,k,v bf16 [B*H, n, 64] (v is consumed as an MN-major tcgen05 operand); out bf16 [B*n, H*64] token-major;
- * n_pad is ignored.
- * lens int32 [lens_mod] (kv length of batch b = lens[b % lens_mod]) or NULL (= n).  Query rows >= len are written
- * as zeros (the reference zeroes them after to_out, :499-501). */
-int f5b_attn_fwd(const void* q, const void* k, const void* v, void* out, const int32_t* lens, int lens_mod, int B,
-                 int H, int n, int n_pad, float scale, f5b_stream_t stream);
+/* Non-causal softmax(QK^T/sqrt(64))V with a per-batch key length (AttnProcessor, model/modules.py:457-493, dropout_p = 0).
+ * q, k, v: bf16 token-major matrices [B*n, ld] whose columns [h*64, h*64+64) belong to head h — typically the three column
+ * sections of the fused QKV GEMM output (q = base, k = base + D, v = base + 2D, ld = 3D); heads are gathered by strided TMA
+ * boxes, v is consumed as an MN-major tcgen05 operand.  out bf16 [B*n, H*64] token-major.
+ * lens int32 [lens_mod] (kv length of batch b = lens[b % lens_mod]) or NULL (= n).  Query rows >= len are written as zeros
+ * (the reference zeroes them after to_out, :499-501). */
+int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod, int B, int H,
+                 int n, float scale, f5b_stream_t stream);
 
 /* ConvPositionEmbedding conv layer (model/modules.py:171-176,183-185): grouped Conv1d(k, groups, pad k/2) + Mish.
  * x bf16 [B*n, D] token-major; wpk = weights packed by f5b_pack_convpos_weight; bias f32 [D].

@@ -5,16 +5,14 @@ from eraxvif5tts_b200 import ops, _lib as L
 lib = L.load()
 lib.f5b_debug_set_attn_trace.argtypes = [ctypes.c_void_p]
 B, H, n = 8, 16, 1875
-n_pad = (n + 7) // 8 * 8
 dev = "cuda"
-q = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
-k = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
-vt = torch.randn(B, H, n, 64, device=dev).to(torch.bfloat16)
+D = H * 64
+qkv = torch.randn(B * n, 3 * D, device=dev).to(torch.bfloat16)
 out = torch.empty(B * n, H * 64, dtype=torch.bfloat16, device=dev)
 tr = torch.zeros(64, dtype=torch.int64, device=dev)
 lib.f5b_debug_set_attn_trace(tr.data_ptr())
 for _ in range(3):
-    ops.attn_fwd(q, k, vt, out, None, 0, B, H, n, n_pad)
+    ops.attn_fwd(qkv, qkv[:, D:], qkv[:, 2 * D:], 3 * D, out, None, 0, B, H, n)
 torch.cuda.synchronize()
 t = tr.cpu().view(8, 8)
 names = ["wait bar_s", "LDTM+wait", "max/rescale", "wait bar_pv(P buf)", "exp+pack+STS", "fence+arrive"]

@@ -102,7 +102,6 @@ def rope_ref(t, pos_freqs):
 
 def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     D = H * 64
-    n_pad = (n + 7) // 8 * 8
     g = torch.Generator(device=dev).manual_seed(11)
     h = (torch.randn(B * n, D, device=dev, generator=g)).to(bf16)
     w = (torch.randn(3 * D, D, device=dev, generator=g) / math.sqrt(D)).to(bf16)
@@ -110,26 +109,24 @@ def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=dev).float() / 64))
     fr = torch.outer(torch.arange(n, device=dev).float(), inv)
     rope = torch.stack((fr.cos(), fr.sin()), dim=-1).contiguous()  # [n,32,2]
-    q = torch.full((B, H, n, 64), float("nan"), dtype=bf16, device=dev)
-    k = torch.full((B, H, n, 64), float("nan"), dtype=bf16, device=dev)
-    vt = torch.zeros((B, H, n, 64), dtype=bf16, device=dev)
-    ops.gemm(h, w, epi=L.EPI_QKV_ROPE, bias=bias, out=q, out2=k, out3=vt, rows_per_batch=n, rope=rope, rope_heads=rope_heads, heads=H,
-             n_pad=n_pad)
+    qkv_out = torch.full((B * n, 3 * D), float("nan"), dtype=bf16, device=dev)  # token-major q | k | v
+    ops.gemm(h, w, epi=L.EPI_QKV_ROPE, bias=bias, out=qkv_out, rows_per_batch=n, rope=rope, rope_heads=rope_heads, heads=H)
     torch.cuda.synchronize()
     qkv = (h.float() @ w.float().t() + bias).view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)  # [3,B,H,n,64]
     fr2 = torch.stack((fr, fr), dim=-1).flatten(-2)  # [n,64]
     qr, kr, vr = qkv[0].clone(), qkv[1].clone(), qkv[2]
     qr[:, :rope_heads] = rope_ref(qr[:, :rope_heads], fr2)
     kr[:, :rope_heads] = rope_ref(kr[:, :rope_heads], fr2)
-    report(f"qkv_rope_B{B}H{H}n{n}", q_rel=relerr(q, qr), k_rel=relerr(k, kr), vt_rel=relerr(vt, vr))
+    got = qkv_out.view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)
+    report(f"qkv_rope_B{B}H{H}n{n}", q_rel=relerr(got[0], qr), k_rel=relerr(got[1], kr), vt_rel=relerr(got[2], vr))
     # attention on the kernel's own (bf16) q, k, v
     lens = None
     if lens_list is not None:
         lens = torch.tensor(lens_list, dtype=torch.int32, device=dev)
     out = torch.full((B * n, D), float("nan"), dtype=bf16, device=dev)
-    ops.attn_fwd(q, k, vt, out, lens, 0, B, H, n, n_pad)
+    ops.attn_fwd(qkv_out, qkv_out[:, D:], qkv_out[:, 2 * D:], 3 * D, out, lens, 0, B, H, n)
     torch.cuda.synchronize()
-    qf, kf, vf = q.float(), k.float(), vt.float()
+    qf, kf, vf = got[0].float(), got[1].float(), got[2].float()
     s = qf @ kf.transpose(-1, -2) / 8.0
     if lens is not None:
         km = torch.arange(n, device=dev)[None, :] < lens[:, None]
@@ -286,9 +283,6 @@ def bench_epilogues(B=32, n=1875, D=1024):
     w2 = (torch.randn(D, F_, device=dev) / 45).to(bf16)
     bq, bo, b1 = torch.randn(3 * D, device=dev), torch.randn(D, device=dev), torch.randn(F_, device=dev)
     rope = torch.randn(n, 32, 2, device=dev)
-    q = torch.empty(B, H, n, 64, dtype=bf16, device=dev)
-    k = torch.empty_like(q)
-    vt = torch.empty(B, H, n, 64, dtype=bf16, device=dev)
     x = torch.randn(M, D, device=dev)
     gate = torch.randn(D, device=dev) * 0.1
     lens = torch.full((B // 2,), n, dtype=torch.int32, device=dev)
@@ -296,8 +290,8 @@ def bench_epilogues(B=32, n=1875, D=1024):
     o3 = torch.empty(M, 3 * D, dtype=bf16, device=dev)
     o1 = torch.empty(M, D, dtype=bf16, device=dev)
     cases = {
-        "qkv_rope": (lambda: ops.gemm(h, wqkv, epi=L.EPI_QKV_ROPE, bias=bq, out=q, out2=k, out3=vt, rows_per_batch=n, rope=rope, rope_heads=1,
-                                       heads=H, n_pad=n_pad), 2.0 * M * 3 * D * D),
+        "qkv_rope": (lambda: ops.gemm(h, wqkv, epi=L.EPI_QKV_ROPE, bias=bq, out=o3, rows_per_batch=n, rope=rope, rope_heads=1, heads=H),
+                     2.0 * M * 3 * D * D),
         "qkv_plain_bf16": (lambda: ops.gemm(h, wqkv, epi=L.EPI_BF16, bias=bq, out=o3), 2.0 * M * 3 * D * D),
         "out_gate_resid": (lambda: ops.gemm(h, wo, epi=L.EPI_GATE_RESID, bias=bo, out=x, rows_per_batch=n, gate=gate, gate_bstride=0, lens=lens,
                                              batch_mod=B // 2), 2.0 * M * D * D),
@@ -323,31 +317,14 @@ def bench_epilogues(B=32, n=1875, D=1024):
 
 
 def bench_attn(B, H, n, iters=10):
-    n_pad = (n + 7) // 8 * 8
-    q = torch.randn(B, H, n, 64, device=dev).to(bf16)
-    k = torch.randn(B, H, n, 64, device=dev).to(bf16)
-    vt = torch.randn(B, H, n, 64, device=dev).to(bf16)
-    out = torch.empty(B * n, H * 64, dtype=bf16, device=dev)
-    for _ in range(3):
-        ops.attn_fwd(q, k, vt, out, None, 0, B, H, n, n_pad)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.attn_fwd(q, k, vt, out, None, 0, B, H, n, n_pad)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    D = H * 64
+    qkv = torch.randn(B * n, 3 * D, device=dev).to(bf16)
+    out = torch.empty(B * n, D, dtype=bf16, device=dev)
+    fn = lambda: ops.attn_fwd(qkv, qkv[:, D:], qkv[:, 2 * D:], 3 * D, out, None, 0, B, H, n)
+    ms = _time(fn, iters)
     fl = 4.0 * B * H * n * n * 64
-    v = vt
-    for _ in range(3):
-        F.scaled_dot_product_attention(q, k, v)
-    e0.record()
-    for _ in range(iters):
-        F.scaled_dot_product_attention(q, k, v)
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1) / iters
+    q, k, v = (t.contiguous() for t in qkv.view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4))
+    ms2 = _time(lambda: F.scaled_dot_product_attention(q, k, v), iters)
     report(f"bench_attn_B{B}H{H}n{n}", ms=ms, tflops=fl / ms / 1e9, sdpa_ms=ms2, sdpa_tflops=fl / ms2 / 1e9)
 
 
