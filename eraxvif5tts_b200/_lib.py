@@ -79,6 +79,8 @@ SIGNATURES = {
     "f5b_cfg_euler_dev": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "f5b_fm_prepare": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_masked_mse": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+    "f5b_grad_sumsq": (C.c_int, [vp, i64, vp, vp, vp]),
+    "f5b_adamw_ema_step": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, C.c_int, vp, f32, f32, f32, vp]),
     "f5b_prof_enabled": (C.c_int, []),
     "f5b_prof_add": (None, [C.POINTER(C.c_double), C.c_int]),
     "f5b_prof_reset": (None, [C.c_int]),

@@ -44,3 +44,21 @@ def max_over_ranks(value: float, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t)
+
+
+def allreduce_flat_(flat, group=None) -> float:
+    """Gradient averaging of data-parallel training (DDP all-reduce behind accelerator.backward, trainer.py:1280) over ONE flat
+    buffer: a single NCCL all-reduce (NVLink / NVSwitch, NVLS when available) instead of per-bucket hooks.  Sums in place and
+    returns the factor (1 / world) the optimizer kernel folds into its gradient scale."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / dist.get_world_size(group)
+
+
+def broadcast_flat_(flat, src: int = 0, group=None) -> None:
+    """initial parameter broadcast of accelerator.prepare (trainer.py:324)"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat, src=src, group=group)

@@ -251,6 +251,17 @@ size_t f5b_vocos_workspace_bytes(const F5bVocos* h, int B, int T);
 int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* wav, void* ws, size_t ws_bytes,
                      f5b_stream_t stream);
 
+/* ---- optimizer step (trainer.py:1280-1287, 1321): clip_grad_norm_ + torch.optim.AdamW + EMA lerp, one fused pass ------------
+ * f5b_grad_sumsq: out[0] = sum(g^2) over a flat f32 gradient buffer (deterministic two-pass; ws f32 [1024]).
+ * f5b_adamw_ema_step over flat f32 buffers p, g, m, v (+ optional ema, + optional bf16 copy of the new p):
+ *   g' = g * grad_scale * min(1, max_norm / (sqrt(grad_sumsq[0]) * grad_scale + 1e-6))      (grad_sumsq NULL or max_norm <= 0: no clip)
+ *   p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ *   ema += (1 - ema_decay) * (p - ema)   when ema != NULL and ema_decay >= 0. */
+int f5b_grad_sumsq(const float* g, int64_t n, float* ws, float* out, f5b_stream_t stream);
+int f5b_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, const float* grad_sumsq, float max_norm, float grad_scale,
+                       float ema_decay, f5b_stream_t stream);
+
 /* ---- launch accounting / per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg) ------------
  * kernel classes: 0 gemm, 1 attention, 2 convpos, 3 norm (LN / dwconv+LN), 4 elementwise, 5 spectral.
  * f5b_prof_reset(enable): zero the counters; enable != 0 additionally brackets every launch with CUDA events on its stream.

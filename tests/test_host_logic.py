@@ -139,13 +139,19 @@ def test_shard_indices_cover_everything_once():
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
-from eraxvif5tts_b200.parallel import shard_indices, gather_counts, max_over_ranks
+from eraxvif5tts_b200.parallel import shard_indices, gather_counts, max_over_ranks, allreduce_flat_, broadcast_flat_
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 r = dist.get_rank()
 mine = shard_indices(37, r, 2, 4)
 cnt = sum(len(b) for b in mine)
 counts = gather_counts(cnt)
 t = max_over_ranks(1.0 + r)
+g = torch.full((1000,), float(r + 1))
+scale = allreduce_flat_(g)
+assert scale == 0.5 and bool((g * scale == 1.5).all())
+w = torch.full((10,), float(r))
+broadcast_flat_(w, src=1)
+assert bool((w == 1.0).all())
 dist.barrier()
 assert sum(counts) == 37 and t == 2.0, (counts, t)
 print("rank", r, "ok", counts)
@@ -217,3 +223,23 @@ def test_wrapper_duration_rule_matches_reference_formula():
     assert w._chunk_duration("x" * 24, 1.0, None) == 200 + int(200 / 12 * 24 / 1.0)
     assert w._chunk_duration("short", 1.0, None) == 200 + int(200 / 12 * 5 / 0.3)
     assert w._chunk_duration("anything", 1.0, 2.0) == int(2.0 * 24000 / 256)
+
+
+def test_lr_and_ema_schedules_match_torch_and_ema_pytorch_rules():
+    """WarmupLinearDecay == SequentialLR(LinearLR, LinearLR) of trainer.py:1179-1188; EmaSchedule == ema_pytorch defaults"""
+    from torch.optim.lr_scheduler import LinearLR, SequentialLR
+    from eraxvif5tts_b200.optim import EmaSchedule, WarmupLinearDecay
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=7.5e-5)
+    w, total = 5, 20
+    sch = SequentialLR(opt, [LinearLR(opt, 1e-8, 1.0, w), LinearLR(opt, 1.0, 1e-8, total - w)], milestones=[w])
+    ours = WarmupLinearDecay(7.5e-5, w, total)
+    for u in range(total):
+        assert abs(opt.param_groups[0]["lr"] - ours.lr(u)) <= 1e-12 + 1e-6 * ours.lr(u), u
+        opt.step()
+        sch.step()
+    e = EmaSchedule()
+    assert e.decay_for_call(2) is None and e.decay_for_call(1) == "copy" and e.decay_for_call(101) == "copy"
+    d = e.decay_for_call(111)  # step 110 -> epoch 9
+    assert abs(d - (1 - (1 + 9) ** (-2 / 3))) < 1e-12
+    assert e.decay_for_call(10 ** 8 + 1) == 0.9999
