@@ -100,6 +100,194 @@ struct ConvPosProblem {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Halo variant (the one that runs): the per-tap A tiles of an output tile are the SAME activation rows shifted by one row per
+// tap, and the [NP x 64] weight slab of a tap is the same for every position tile of a group.  So one CTA work unit is a
+// SUPER-TILE of up to 4 x 128 consecutive positions of one (batch row, group):
+//   * its halo [4*128 + k - 1 rows x 64 channels] is fetched ONCE (4 TMA boxes of 136 rows, contiguous in smem);
+//   * tap t of sub-tile s is fed to tcgen05.mma through a shared-memory descriptor whose start address is simply advanced by
+//     (128 s + t) rows — measured on B200: the 128B swizzle is a function of the absolute smem address, so a start that is not
+//     1024-byte aligned needs NO descriptor base offset (setting it corrupts the result);
+//   * each tap's weight slab is streamed once per super-tile and feeds 4 x 4 MMAs (one barrier round trip per 512 tensor
+//     clocks instead of per 128), accumulating into 4 x 64 TMEM columns, double-buffered across super-tiles (512 columns).
+// The per-tap implicit GEMM on the generic engine (above) ran at the L2 -> SM cap with the tensor pipe 19 % busy.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HALO_SUB = 4;
+constexpr int HALO_BOX_ROWS = 136;                       // 17 x 8 rows: every box starts on a 1024-byte swizzle boundary
+constexpr int HALO_BOXES = 4;                            // 544 rows >= 4*128 + 30
+constexpr uint32_t HALO_A_BYTES = HALO_BOXES * HALO_BOX_ROWS * 128;  // 68 KB
+constexpr int HALO_B_STAGES = 8;
+constexpr uint32_t HALO_B_BYTES = 64 * 128;              // 8 KB per stage (NP <= 64 rows)
+constexpr uint32_t HALO_SMEM = 2 * HALO_A_BYTES + HALO_B_STAGES * HALO_B_BYTES + 1024 + 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(ENGINE_THREADS, 1)
+convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvPosProblem<MODE> p,
+                    const int n_super) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * HALO_A_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + HALO_B_STAGES * HALO_B_BYTES);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + HALO_B_STAGES;
+  uint64_t* tfull = b_empty + HALO_B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], EPI_WARPS);
+      }
+      for (int i = 0; i < HALO_B_STAGES; ++i) {
+        mbar_init(&b_full[i], 1);
+        mbar_init(&b_empty[i], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.B * n_super * p.groups;  // super-tiles
+  const int ks = p.ksize;
+  // super-tile u -> (b, st, g), g fastest; number of live 128-row sub-tiles
+  auto decode_super = [&](int u, int& b, int& st, int& g, int& nsub) {
+    g = u % p.groups;
+    const int t2 = u / p.groups;
+    st = t2 % n_super;
+    b = t2 / n_super;
+    const int left = p.n - st * HALO_SUB * BM;
+    nsub = min(HALO_SUB, (left + BM - 1) / BM);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < total; u += gridDim.x, ++it) {
+        int b, st, g, nsub;
+        decode_super(u, b, st, g, nsub);
+        const int ab = it & 1;
+        const int rows = nsub * BM + ks - 1;
+        const int nbox = (rows + HALO_BOX_ROWS - 1) / HALO_BOX_ROWS;
+        mbar_wait(&a_empty[ab], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[ab], nbox * HALO_BOX_ROWS * 128);
+        for (int q = 0; q < nbox; ++q)
+          tma_load_3d(sA + ab * HALO_A_BYTES + q * HALO_BOX_ROWS * 128, &tmA, &a_full[ab], g * p.cpg,
+                      st * HALO_SUB * BM - p.pad + q * HALO_BOX_ROWS, b);
+        for (int k = 0; k < ks; ++k) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], p.NP * 128);
+          tma_load_2d(sB + stage * HALO_B_BYTES, &tmB, &b_full[stage], 0, (g * ks + k) * p.NP);
+          if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BM, p.NP, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < total; u += gridDim.x, ++it) {
+        int b, st, g, nsub;
+        decode_super(u, b, st, g, nsub);
+        const int acc = it & 1, ab = it & 1;
+        const uint32_t ph2 = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], ph2 ^ 1);
+        mbar_wait(&a_full[ab], ph2);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + ab * HALO_A_BYTES);
+        for (int k = 0; k < ks; ++k) {
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sB + stage * HALO_B_BYTES);
+          for (int sblk = 0; sblk < nsub; ++sblk) {
+            const uint32_t d_tmem = tmem_base + acc * (HALO_SUB * 64) + sblk * 64;
+            const uint32_t a_addr = a_base + (sblk * BM + k) * 128;  // sub-tile sblk, shifted down by k rows for tap k
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(d_tmem, smem_desc_sw128(a_addr + kk * 32, 1024, 16), smem_desc_sw128(b_addr + kk * 32, 1024, 16), idesc,
+                        (k | kk) != 0);
+          }
+          umma_commit(&b_empty[stage]);
+          if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&a_empty[ab]);
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int chunks = (p.cpg + 31) / 32;
+    int it = 0;
+    for (int u = blockIdx.x; u < total; u += gridDim.x, ++it) {
+      int b, st, g, nsub;
+      decode_super(u, b, st, g, nsub);
+      const int acc = it & 1;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int w = half; w < nsub * chunks; w += 2) {  // (sub-tile, 32-column chunk) pairs, alternating between the warp pair
+        const int sblk = w / chunks, c = w - sblk * chunks;
+        const int tile = (b * p.n_tiles_seq + st * HALO_SUB + sblk) * p.groups + g;
+        const auto ctx = p.row_ctx(tile, quad * 32 + lane);
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + lane_base + acc * (HALO_SUB * 64) + sblk * 64 + c * 32, r);
+        tmem_ld_wait();
+        p.epilogue(ctx, c * 32, r);
+      }
+      __syncwarp();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int g_convpos_halo = 1;  // 0: per-tap loads on the generic engine (kept for A/B measurements), 1: super-tile halo kernel
+
+template <int MODE>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPosProblem<MODE>& p, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = convpos_halo_kernel<MODE>;
+  if (!configured) {
+    F5B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HALO_SMEM));
+    configured = true;
+  }
+  const int n_super = (p.n + HALO_SUB * BM - 1) / (HALO_SUB * BM);
+  const int total = p.B * n_super * p.groups;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, ENGINE_THREADS, HALO_SMEM, stream>>>(tmA, tmB, p, n_super);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void pack_convpos_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int D, int groups, int ksize,
                                     int cpg, int NP) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,11 +316,21 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
   const int NP = round16(cpg);
   LaunchScope scope(K_CONVPOS, stream, 2.0 * B * n * (double)D * cpg * ksize, (double)B * n * D * (mode == 0 ? 4.0 : 10.0));
   CUtensorMap tmA, tmB;
-  if (make_tmap_3d(&tmA, x, 2, (uint64_t)D, (uint64_t)n, (uint64_t)B, (uint64_t)D * 2, (uint64_t)n * D * 2, 64, BM, 1, true))
+  const bool halo = g_convpos_halo != 0 && HALO_SUB * BM + ksize - 1 <= HALO_BOXES * HALO_BOX_ROWS;
+  if (make_tmap_3d(&tmA, x, 2, (uint64_t)D, (uint64_t)n, (uint64_t)B, (uint64_t)D * 2, (uint64_t)n * D * 2, 64, halo ? HALO_BOX_ROWS : BM, 1,
+                   true))
     return -1;
   if (make_tmap_2d(&tmB, wpk, 2, 64, (uint64_t)groups * ksize * NP, 128, 64, NP, true)) return -1;
   const int nts = (n + BM - 1) / BM;
   const int total = B * nts * groups;
+  if (halo) {
+    if (mode == 0) {
+      ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+      return launch_halo(tmA, tmB, p, stream);
+    }
+    ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+    return launch_halo(tmA, tmB, p, stream);
+  }
   if (mode == 0) {
     ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
     return launch_engine(tmA, tmB, tmA, p, total, stream);
@@ -168,3 +366,5 @@ int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ks
 }
 
 }  // extern "C"
+
+extern "C" void f5b_debug_convpos_mode(int halo) { f5b::g_convpos_halo = halo; }
