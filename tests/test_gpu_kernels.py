@@ -58,7 +58,8 @@ def test_qkv_rope_and_attention(D, B, H, n, lens, rh):
     _check(D)
 
 
-@pytest.mark.parametrize("B,n,Dm", [(2, 300, 1024), (2, 200, 768), (2, 96, 128), (1, 31, 1024)])
+@pytest.mark.parametrize("B,n,Dm", [(2, 300, 1024), (2, 200, 768), (2, 96, 128), (1, 31, 1024), (2, 1875, 1024), (1, 513, 1024),
+                                     (3, 640, 768), (1, 4096, 1024)])
 def test_convpos(D, B, n, Dm):
     D.convpos_case(B, n, Dm)
     _check(D)
