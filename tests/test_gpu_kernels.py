@@ -79,3 +79,38 @@ def test_spectral(D):
     D.RES.clear()
     assert r["melspec"]["abs"] < 1e-3 and r["melspec"]["mean_abs"] < 1e-5
     assert r["istft"]["abs"] < 1e-4 * max(1.0, r["istft"]["ref_max"])
+
+
+def test_gemm_random_shape_sweep(D):
+    """seeded sweep over ragged M / N / K (tails in every dimension, N and K multiples of 8 as the TMA pitch rule requires),
+    all store paths: bf16 TMA store, f32 direct, gated residual TMA reduce-add"""
+    import random
+    import torch
+    rng = random.Random(1234)
+    for it in range(24):
+        M = rng.choice([1, 7, 127, 128, 129, 255, 257, 1000, rng.randint(1, 3000)])
+        N = 8 * rng.randint(1, 160)
+        K = 8 * rng.randint(1, 140)
+        kind = it % 3
+        if kind == 0:
+            D.gemm_case(M, N, K, "bf16", rng.choice([0, 1, 2, 3]))
+        elif kind == 1:
+            D.gemm_case(M, N, K, "f32", 0)
+        else:
+            n = rng.choice([1, 3, 50, 333])
+            B = max(1, M // n)
+            D.gemm_gate_case(B, n, 4 * ((N + 3) // 4), K)
+        torch.cuda.synchronize()
+    _check(D)
+
+
+def test_attention_random_sweep(D):
+    import random
+    rng = random.Random(7)
+    for it in range(10):
+        B = rng.randint(1, 3)
+        H = rng.choice([1, 2, 5, 12, 16])
+        n = rng.choice([1, 2, 63, 64, 65, 127, 128, 129, 191, 200, 500, 1000])
+        lens = None if it % 2 == 0 else [rng.randint(1, n) for _ in range(B)]
+        D.qkv_attn_case(B, H, n, lens, rope_heads=rng.choice([0, 1, H]))
+    _check(D)

@@ -115,8 +115,9 @@ def qkv_attn_case(B, H, n, lens_list=None, rope_heads=1):
     qkv = (h.float() @ w.float().t() + bias).view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)  # [3,B,H,n,64]
     fr2 = torch.stack((fr, fr), dim=-1).flatten(-2)  # [n,64]
     qr, kr, vr = qkv[0].clone(), qkv[1].clone(), qkv[2]
-    qr[:, :rope_heads] = rope_ref(qr[:, :rope_heads], fr2)
-    kr[:, :rope_heads] = rope_ref(kr[:, :rope_heads], fr2)
+    if rope_heads > 0:
+        qr[:, :rope_heads] = rope_ref(qr[:, :rope_heads], fr2)
+        kr[:, :rope_heads] = rope_ref(kr[:, :rope_heads], fr2)
     got = qkv_out.view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)
     report(f"qkv_rope_B{B}H{H}n{n}", q_rel=relerr(got[0], qr), k_rel=relerr(got[1], kr), vt_rel=relerr(got[2], vr))
     # attention on the kernel's own (bf16) q, k, v
