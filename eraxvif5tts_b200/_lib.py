@@ -46,6 +46,7 @@ SIGNATURES = {
     "f5b_last_error": (C.c_char_p, []),
     "f5b_abi_version": (C.c_int, []),
     "f5b_gemm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.POINTER(GemmArgs), vp]),
+    "f5b_gemm_tn": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_ln_modulate": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, vp]),
     "f5b_attn_fwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),

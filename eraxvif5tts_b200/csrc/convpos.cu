@@ -39,6 +39,9 @@ struct ConvPosProblem {
   __device__ __forceinline__ int unit_tile(int unit, uint32_t) const { return unit; }
   __device__ __forceinline__ int num_kblocks() const { return ksize; }
   __device__ __forceinline__ uint32_t umma_n() const { return NP; }
+  __device__ __forceinline__ uint32_t idesc() const { return idesc_bf16(BM, umma_n(), 0, 0); }
+  __device__ __forceinline__ uint64_t a_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
+  __device__ __forceinline__ uint64_t b_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return NP * 128; }
   __device__ __forceinline__ int tile_cols(int) const { return cpg; }
   __device__ __forceinline__ int out_col0(int) const { return 0; }

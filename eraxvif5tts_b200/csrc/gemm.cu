@@ -48,6 +48,9 @@ struct LinearProblem {
   }
   __device__ __forceinline__ int num_kblocks() const { return kblocks; }
   __device__ __forceinline__ uint32_t umma_n() const { return BN; }
+  __device__ __forceinline__ uint32_t idesc() const { return idesc_bf16(BM, umma_n(), 0, 0); }
+  __device__ __forceinline__ uint64_t a_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
+  __device__ __forceinline__ uint64_t b_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
   __device__ __forceinline__ int tile_cols(int tile) const {
     const int left = g.N - (tile % n_tiles) * BN;

@@ -118,7 +118,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(BM, p.umma_n(), 0, 0);
+      const uint32_t idesc = p.idesc();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -135,9 +135,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 1024, 16);
-            const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 1024, 16);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
           }
           if constexpr (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
           else umma_commit(&empty[stage]);
@@ -280,6 +278,13 @@ static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- operand descriptors for UMMA K-step k (16 elements of the reduction dimension) of one [rows x 64] bf16 stage tile ------
+// K-major tile (reduction dim contiguous): rows of 128 B, 8-row groups 1024 B apart; a K-step advances the start by 32 B.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k) { return smem_desc_sw128(tile_addr + k * 32, 1024, 16); }
+// MN-major tile (the M / N dim contiguous): 64-wide chunks of [64 reduction rows x 128 B] 8192 B apart (LBO); inside a chunk the
+// 8-row groups are 1024 B apart (SBO); a K-step = 16 reduction rows = 2048 B.  (Form verified by the attention kernel's P.V.)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k) { return smem_desc_sw128(tile_addr + k * 2048, 1024, 8192); }
 
 // ---- shared epilogue helpers: 32 consecutive columns of one accumulator row ------------------------------------
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* o, const float (&v)[32], int ncols_left, bool vec_ok) {

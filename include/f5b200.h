@@ -71,6 +71,14 @@ int f5b_abi_version(void);
  * point-wise linears (:263-267). */
 int f5b_gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs* args, f5b_stream_t stream);
 
+/* Transposed-operand GEMM (backward of nn.Linear; groundwork of the training step, trainer.py:1280):
+ *   C[m,n] (+)= sum_k A(m,k) B(n,k),  A(m,k) = A[m*lda + k] (a_mn_major 0) or A[k*lda + m] (a_mn_major 1), same for B.
+ *   dgrad dX = dY W:      f5b_gemm_tn(dY, N, 0, W, K, 1, dX, ...)       wgrad dW = dY^T X: f5b_gemm_tn(dY, N, 1, X, K, 1, dW, ..., splits)
+ * out: bf16 [M, ldc] overwritten (out_f32_accumulate 0) or f32 [M, ldc] accumulated with TMA reduce-add (1; required for
+ * splits > 1, which cuts the reduction into `splits` ranges processed by different CTAs).  A, B bf16. */
+int f5b_gemm_tn(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* out, int ldc,
+                int out_f32_accumulate, int M, int N, int K, int splits, f5b_stream_t stream);
+
 /* out bf16[rows,D] = LayerNorm(x f32[rows,D], eps, no affine) * (1 + scale[b,:]) + shift[b,:]
  * (AdaLayerNorm.forward model/modules.py:310-315, DiTBlock ff norm :637, AdaLayerNorm_Final :331-336).
  * scale/shift element (b, c) at ptr[(b % batch_mod)*mod_bstride + c] (batch_mod 0: b); NULL/NULL = plain LayerNorm. */
