@@ -175,6 +175,61 @@ def cpu_port_measure(arch, ref_frames, total, steps, warmup, quiet=False):
                        f"+1 text-embedding pair +1 Vocos decode; extrapolated x{NFE} steps")
 
 
+def torch_eager_gpu_measure(arch, B, ref_frames, total, dev, steps=3, warmup=2):
+    """Second comparator of SURVEY.md §8d (opt-in, --torch-eager-gpu): the oracle's DiT forward run as stock PyTorch eager in bf16
+    on the same B200 — cuBLAS linears, F.scaled_dot_product_attention (flash / cuDNN; no key mask, the favourable case for the
+    library path), cuDNN grouped conv.  Bounded sample = the full batch x ONE Euler step (cond + uncond forward) per timed step,
+    extrapolated to the 32 identical steps.  It is a baseline leg: nothing here is on the product path."""
+    import torch.nn.functional as F
+    from oracle import f5_oracle as O
+    from oracle.weights import make_dit_state_dict, synthetic_inputs
+    cfg = O.DiTConfig(dim=arch.dim, depth=arch.depth, heads=arch.heads)
+    sd_cpu = make_dit_state_dict(cfg, 0)
+    cond, text, duration, lens = synthetic_inputs(cfg, B, ref_frames, total, seed=1234)
+    with torch.no_grad():
+        te_c = O.text_embedding(sd_cpu, cfg, text[:1], total, False).expand(B, -1, -1).to(dev, torch.bfloat16)
+        te_u = O.text_embedding(sd_cpu, cfg, text[:1], total, True).expand(B, -1, -1).to(dev, torch.bfloat16)
+    sd = {k: v.to(dev, torch.bfloat16) for k, v in sd_cpu.items()}
+    rope_cpu, attn_cpu = O.rotary_freqs, O.attention
+
+    def attention_sdpa(sd_, cfg_, p, x, mask, rope):
+        b, n, _ = x.shape
+        H, d = cfg_.heads, cfg_.dim_head
+        q = F.linear(x, sd_[p + "to_q.weight"], sd_[p + "to_q.bias"]).view(b, n, H, d).transpose(1, 2)
+        k = F.linear(x, sd_[p + "to_k.weight"], sd_[p + "to_k.bias"]).view(b, n, H, d).transpose(1, 2)
+        v = F.linear(x, sd_[p + "to_v.weight"], sd_[p + "to_v.bias"]).view(b, n, H, d).transpose(1, 2)
+        pn = cfg_.pe_attn_head if cfg_.pe_attn_head is not None else H
+        q = torch.cat((O.apply_rotary(q[:, :pn], rope), q[:, pn:]), dim=1)
+        k = torch.cat((O.apply_rotary(k[:, :pn], rope), k[:, pn:]), dim=1)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, H * d)
+        return F.linear(o, sd_[p + "to_out.0.weight"], sd_[p + "to_out.0.bias"])
+
+    O.rotary_freqs = lambda n, d=64, theta=10000.0: rope_cpu(n, d, theta).to(dev)
+    O.attention = attention_sdpa
+    try:
+        step_cond = F.pad(cond, (0, 0, 0, total - ref_frames)).to(dev, torch.bfloat16)
+        y = torch.randn(B, total, cfg.mel_dim, device=dev, dtype=torch.bfloat16)
+        t = torch.tensor(0.3, device=dev, dtype=torch.bfloat16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    e0.record()
+                pred = O.dit_forward(sd, cfg, y, step_cond, text, t, False, False, None, text_embed=te_c)
+                null = O.dit_forward(sd, cfg, y, step_cond, text, t, True, True, None, text_embed=te_u)
+                y = y + 0.03 * (pred + (pred - null) * CFG)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        O.rotary_freqs, O.attention = rope_cpu, attn_cpu
+    pair_ms = e0.elapsed_time(e1) / steps
+    return {"value": B * total / (NFE * pair_ms * 1e-3), "unit": "mel-frames/s", "ms_per_euler_step": pair_ms, "dtype": "bf16",
+            "sample": f"full batch ({B} x {total} frames) x 1 of {NFE} Euler steps (cond+uncond DiT forward) per timed step, mean of {steps}; "
+                      f"x{NFE} extrapolated; MelSpec / text embedding / Vocos excluded (they favour this arm)",
+            "kernels": "torch eager: cuBLAS linears, SDPA without key mask, cuDNN grouped conv"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +239,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with CUDA events during the timed region")
+    ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the oracle as stock PyTorch eager bf16 on this GPU (second comparator)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -363,6 +419,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_port_measure(cfg, ref_frames, total, 2, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if world == 1 and args.torch_eager_gpu:
+        line["torch_eager_gpu"] = torch_eager_gpu_measure(cfg, B, ref_frames, total, dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

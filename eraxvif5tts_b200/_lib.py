@@ -50,6 +50,9 @@ SIGNATURES = {
     "f5b_ln_modulate": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, vp]),
     "f5b_attn_fwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_attn_fwd_lse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_attn_bwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp,
+                               C.c_int, vp]),
     "f5b_convpos": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos_packed_elems": (sz, [C.c_int, C.c_int, C.c_int]),

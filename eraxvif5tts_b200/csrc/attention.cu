@@ -39,6 +39,7 @@ constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
   __nv_bfloat16* out;
+  float* lse;  // optional [B, H, n]: log2-domain log-sum-exp of the scaled scores (training); +inf for padded query rows
   const int32_t* lens;
   int lens_mod, B, H, n;
   float scale_log2;
@@ -130,6 +131,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.n + pos) * D + h * 64);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.lse != nullptr) p.lse[(size_t)bh * p.n + pos] = INFINITY;
       }
     }
     return;
@@ -302,6 +304,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const int pos = q0 + r;
     const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
+    if (p.lse != nullptr && pos < p.n) p.lse[(size_t)bh * p.n + pos] = (pos < kvlen) ? m_used + log2f(l_run) : INFINITY;
     __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -332,8 +335,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 long long* g_attn_trace = nullptr;
 
-int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
-             float scale, cudaStream_t stream) {
+int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
+             int n, float scale, cudaStream_t stream) {
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
@@ -351,6 +354,7 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, con
   }
   AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
   p.lens = lens;
   p.lens_mod = lens_mod;
   p.B = B;
@@ -368,7 +372,12 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, con
 
 extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod,
                             int B, int H, int n, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, v, ld, out, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
+  return f5b::attn_fwd(q, k, v, ld, out, nullptr, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens,
+                                int lens_mod, int B, int H, int n, float scale, f5b_stream_t stream) {
+  return f5b::attn_fwd(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }

@@ -1,0 +1,440 @@
+// Flash-style attention BACKWARD for the DiT blocks (training path, CFM.forward -> loss.backward in the reference,
+// /root/reference/src/f5_tts/model/cfm.py:210-283 driving AttnProcessor /root/reference/src/f5_tts/model/modules.py:442-503
+// through autograd; dropout_p = 0, DESIGN.md "oracle adjustments").
+//
+//   given  Q, K, V (token-major bf16, the fused QKV GEMM output), dO, the forward's log2-sum-exp L and delta = rowsum(dO . O):
+//     P  = exp2(Q K^T * c - L)            c = scale * log2(e), keys >= len[b] masked
+//     dV = P^T dO          dP = dO V^T          dS = scale * P . (dP - delta)
+//     dK = dS^T Q          dQ = dS K
+//
+// sm_100a design: one CTA owns one 128-key tile of one (batch, head) and walks the 128-query tiles.  Everything is computed in the
+// TRANSPOSED orientation (TMEM lane = key), so that P^T and dS^T come out of the softmax threads row-major in exactly the
+// layout the tcgen05 A operand wants, and all five products run without a single transposed copy:
+//     S^T  = K   Q^T    A = K   (K-major)   B = Q   (K-major)        TMEM cols   0..127
+//     dP^T = V   dO^T   A = V   (K-major)   B = dO  (K-major)        TMEM cols 128..255
+//     dV  += P^T  dO    A = P^T (K-major)   B = dO  (MN-major)       TMEM cols 256..319   (resident for the whole CTA)
+//     dK  += dS^T Q     A = dS^T(K-major)   B = Q   (MN-major)       TMEM cols 320..383   (resident)
+//     dQ_j = dS   K     A = dS^T tile read MN-MAJOR, B = K (MN-major)  TMEM cols 384..447 -> fp32 red.add into the dQ workspace
+//   warp 0: TMA producer (K, V once; Q_j, dO_j double-buffered) + per-tile L / delta staging; warp 1: tcgen05.mma issuer;
+//   warps 2..9: 256 softmax threads (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+// dK and dV leave as bf16 straight into the dQKV matrix the QKV dgrad/wgrad GEMMs consume (RoPE's transpose applied to dK on the
+// way out); dQ is accumulated across the key-tile CTAs in fp32 and converted (+ RoPE transpose) by attn_dq_finish_kernel.
+#include "common.cuh"
+#include "f5b_internal.h"
+
+namespace f5b {
+
+constexpr int AB_T = 128;                       // query tile == key tile
+constexpr int AB_THREADS = 320;
+constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
+constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
+constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
+constexpr uint32_t AB_TMEM_COLS = 512;
+
+struct AttnBwdParams {
+  const float* lse;     // [B, H, n] log2 domain; +inf for padded query rows
+  const float* delta;   // [B, H, n]
+  float* dq;            // [B*n, H*64] fp32, zero-initialised
+  __nv_bfloat16* dqkv;  // [B*n, ld_d]: dK at column H*64, dV at 2*H*64
+  int ld_d;
+  const int32_t* lens;
+  int lens_mod, B, H, n;
+  float scale, scale_log2;
+  const float* rope;    // [n, 32] (cos, sin)
+  int rope_heads;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AB_TILE;
+  uint8_t* sQ = sV + AB_TILE;        // 2 stages
+  uint8_t* sdO = sQ + 2 * AB_TILE;   // 2 stages
+  uint8_t* sPT = sdO + 2 * AB_TILE;
+  uint8_t* sdST = sPT + AB_PT;
+  float* sL = reinterpret_cast<float*>(sdST + AB_PT);  // [2][128]
+  float* sDl = sL + 2 * AB_T;                          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * AB_T);
+  uint64_t* bar_kv = bars + 0;
+  uint64_t* bar_qdo = bars + 1;   // [2] Q_j, dO_j landed
+  uint64_t* bar_ld = bars + 3;    // [2] L_j, delta_j staged (32 arrivals)
+  uint64_t* bar_sdp = bars + 5;   // S^T_j and dP^T_j in TMEM
+  uint64_t* bar_pds = bars + 6;   // P^T_j, dS^T_j in smem; S / dP / dQ TMEM drained (256 arrivals)
+  uint64_t* bar_dq = bars + 7;    // dV, dK, dQ_j products retired
+  uint64_t* bar_free = bars + 8;  // [2] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * AB_T;
+  const int bh = blockIdx.y;
+  const int b = bh / p.H;
+  const int h = bh - b * p.H;
+  int kvlen = p.n;
+  if (p.lens != nullptr) kvlen = min(p.n, __ldg(p.lens + (p.lens_mod > 0 ? b % p.lens_mod : b)));
+  const int D = p.H * 64;
+
+  if (kvlen <= 0 || k0 >= kvlen) {
+    // masked keys receive no gradient
+    if (warp >= 2) {
+      const int t = threadIdx.x - 64;  // 0..255
+      const int row = t >> 1, half = t & 1;
+      const int pos = k0 + row;
+      if (pos < p.n) {
+        __nv_bfloat16* base = p.dqkv + ((size_t)b * p.n + pos) * p.ld_d + h * 64 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          reinterpret_cast<uint4*>(base + D)[i] = make_uint4(0u, 0u, 0u, 0u);
+          reinterpret_cast<uint4*>(base + 2 * D)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    return;
+  }
+  const int Tq = (kvlen + AB_T - 1) / AB_T;  // query rows >= len carry dO = 0 and L = +inf: skipped
+
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(bar_kv, 1);
+      mbar_init(&bar_qdo[0], 1);
+      mbar_init(&bar_qdo[1], 1);
+      mbar_init(&bar_ld[0], 32);
+      mbar_init(&bar_ld[1], 32);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, 256);
+      mbar_init(bar_dq, 1);
+      mbar_init(&bar_free[0], 1);
+      mbar_init(&bar_free[1], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, AB_TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------------ producer
+    if (lane == 0) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmK);
+      prefetch_tmap(&tmV);
+      prefetch_tmap(&tmdO);
+      mbar_arrive_expect_tx(bar_kv, 2 * AB_TILE);
+      tma_load_3d(sK, &tmK, bar_kv, h * 64, k0, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * 64, k0, b);
+    }
+    const size_t row0 = (size_t)bh * p.n;
+    for (int j = 0; j < Tq; ++j) {
+      const int st = j & 1;
+      if (j >= 2) mbar_wait(&bar_free[st], ((j >> 1) - 1) & 1);  // tile j-2 retired (a per-stage barrier cannot run a phase ahead)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bar_qdo[st], 2 * AB_TILE);
+        tma_load_3d(sQ + st * AB_TILE, &tmQ, &bar_qdo[st], h * 64, j * AB_T, b);
+        tma_load_3d(sdO + st * AB_TILE, &tmdO, &bar_qdo[st], h * 64, j * AB_T, b);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + lane;
+        const int pos = j * AB_T + r;
+        sL[st * AB_T + r] = pos < p.n ? __ldg(p.lse + row0 + pos) : INFINITY;
+        sDl[st * AB_T + r] = pos < p.n ? __ldg(p.delta + row0 + pos) : 0.f;
+      }
+      mbar_arrive(&bar_ld[st]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t id_sq = idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
+      const uint32_t id_acc = idesc_bf16(128, 64, 0, 1);   // dV, dK: B is MN-major
+      const uint32_t id_dq = idesc_bf16(128, 64, 1, 1);    // dQ: A (dS^T tile) and B (K) both MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
+      const uint32_t pt_addr = smem_u32(sPT), ds_addr = smem_u32(sdST);
+      auto issue_sdp = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&bar_qdo[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_S, smem_desc_sw128(k_addr + k * 32, 1024, 16), smem_desc_sw128(qa + k * 32, 1024, 16), id_sq, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_dP, smem_desc_sw128(v_addr + k * 32, 1024, 16), smem_desc_sw128(da + k * 32, 1024, 16), id_sq, k != 0);
+        umma_commit(bar_sdp);
+      };
+      mbar_wait(bar_kv, 0);
+      issue_sdp(0);
+      for (int j = 0; j < Tq; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_pds, j & 1);
+        tc_fence_after();
+        const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 queries of the tile, 16 per step
+          const uint32_t aoff = (kk >> 2) * (AB_PT / 2) + (kk & 3) * 32;
+          umma_bf16(tm_dV, smem_desc_sw128(pt_addr + aoff, 1024, 16), smem_desc_sw128(da + kk * 2048, 1024, 8192), id_acc, (j | kk) != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t aoff = (kk >> 2) * (AB_PT / 2) + (kk & 3) * 32;
+          umma_bf16(tm_dK, smem_desc_sw128(ds_addr + aoff, 1024, 16), smem_desc_sw128(qa + kk * 2048, 1024, 8192), id_acc, (j | kk) != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // reduction over the 128 keys: dS^T rows are the K dimension here (MN-major A, 2 q-atoms)
+          umma_bf16(tm_dQ, smem_desc_sw128(ds_addr + kk * 2048, 1024, AB_PT / 2), smem_desc_sw128(k_addr + kk * 2048, 1024, 8192), id_dq,
+                    kk != 0);
+        umma_commit(bar_dq);
+        umma_commit(&bar_free[st]);
+        if (j + 1 < Tq) issue_sdp(j + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------------ softmax / gradient threads
+    const int lq = warp & 3;          // TMEM lane quarter this warp may touch
+    const int ch = (warp - 2) >> 2;   // column half
+    const int r = lq * 32 + lane;     // TMEM lane: key row (S^T, dP^T, dV, dK) or query row (dQ)
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const int rx = r & 7;
+    const bool key_ok = (k0 + r) < kvlen;
+    const float c2 = p.scale_log2, sc = p.scale;
+    uint8_t* pt_row = sPT + ch * (AB_PT / 2) + r * 128;
+    uint8_t* ds_row = sdST + ch * (AB_PT / 2) + r * 128;
+
+    auto drain_dq = [&](int j) {
+      mbar_wait(bar_dq, j & 1);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld32(tm_dQ + lane_addr + ch * 32, a);
+      tmem_ld_wait();
+      const int pos = j * AB_T + r;
+      if (pos < p.n) {
+        float* dst = p.dq + ((size_t)b * p.n + pos) * D + h * 64 + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          red_add_v4(dst + 4 * i, __uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]),
+                     __uint_as_float(a[4 * i + 3]));
+      }
+    };
+
+    for (int j = 0; j < Tq; ++j) {
+      const int st = j & 1;
+      if (j > 0) drain_dq(j - 1);  // also: products of tile j-1 retired -> the P^T / dS^T buffers are free
+      mbar_wait(&bar_ld[st], (j >> 1) & 1);
+      mbar_wait(bar_sdp, j & 1);
+      tc_fence_after();
+      const float4* L4 = reinterpret_cast<const float4*>(sL + st * AB_T + ch * 64);
+      const float4* D4 = reinterpret_cast<const float4*>(sDl + st * AB_T + ch * 64);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[32], g[32];
+        tmem_ld32(tm_S + lane_addr + ch * 64 + c * 32, s);
+        tmem_ld32(tm_dP + lane_addr + ch * 64 + c * 32, g);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int i4 = 0; i4 < 2; ++i4) {
+            const float4 l = L4[c * 8 + q * 2 + i4];
+            const float4 dl = D4[c * 8 + q * 2 + i4];
+            const float ls[4] = {l.x, l.y, l.z, l.w};
+            const float ds[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = q * 8 + i4 * 4 + i;
+              float pe = ex2_approx(fmaf(__uint_as_float(s[e]), c2, -ls[i]));
+              if (!key_ok) pe = 0.f;
+              pv[i4 * 4 + i] = pe;
+              dv[i4 * 4 + i] = pe * (__uint_as_float(g[e]) - ds[i]) * sc;
+            }
+          }
+          uint4 pk, dk;
+          pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]); pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
+          dk.x = pack_bf16(dv[0], dv[1]); dk.y = pack_bf16(dv[2], dv[3]); dk.z = pack_bf16(dv[4], dv[5]); dk.w = pack_bf16(dv[6], dv[7]);
+          const int chunk = ((c * 4 + q) ^ rx) << 4;
+          *reinterpret_cast<uint4*>(pt_row + chunk) = pk;
+          *reinterpret_cast<uint4*>(ds_row + chunk) = dk;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+    }
+    drain_dq(Tq - 1);
+    // dV, dK of this key tile (all products retired: bar_dq of the last tile)
+    const int pos = k0 + r;
+    {
+      uint32_t a[32];
+      tmem_ld32(tm_dV + lane_addr + ch * 32, a);
+      tmem_ld_wait();
+      if (pos < p.n) {
+        __nv_bfloat16* o = p.dqkv + ((size_t)b * p.n + pos) * p.ld_d + 2 * D + h * 64 + ch * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(a[q * 8 + 0]), __uint_as_float(a[q * 8 + 1]));
+          pk.y = pack_bf16(__uint_as_float(a[q * 8 + 2]), __uint_as_float(a[q * 8 + 3]));
+          pk.z = pack_bf16(__uint_as_float(a[q * 8 + 4]), __uint_as_float(a[q * 8 + 5]));
+          pk.w = pack_bf16(__uint_as_float(a[q * 8 + 6]), __uint_as_float(a[q * 8 + 7]));
+          reinterpret_cast<uint4*>(o)[q] = pk;
+        }
+      }
+      tmem_ld32(tm_dK + lane_addr + ch * 32, a);
+      tmem_ld_wait();
+      if (pos < p.n) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
+        if (h < p.rope_heads) {
+          // transpose of the forward rotation (y0 = x0 c - x1 s, y1 = x1 c + x0 s)
+          const float4* cs = reinterpret_cast<const float4*>(p.rope) + (size_t)pos * 16 + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(cs + i);
+            const float y0 = v[4 * i], y1 = v[4 * i + 1], y2 = v[4 * i + 2], y3 = v[4 * i + 3];
+            v[4 * i] = y0 * t.x + y1 * t.y;
+            v[4 * i + 1] = y1 * t.x - y0 * t.y;
+            v[4 * i + 2] = y2 * t.z + y3 * t.w;
+            v[4 * i + 3] = y3 * t.z - y2 * t.w;
+          }
+        }
+        __nv_bfloat16* o = p.dqkv + ((size_t)b * p.n + pos) * p.ld_d + D + h * 64 + ch * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+          pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+          pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+          pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+          reinterpret_cast<uint4*>(o)[q] = pk;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AB_TMEM_COLS);
+  }
+}
+
+// delta[b, h, pos] = sum_c dO[row, h*64 + c] * O[row, h*64 + c]   (one warp per token row, all heads)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int ld, float* __restrict__ delta,
+                                  int B, int H, int n) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * n) return;
+  const int b = row / n, pos = row - b * n;
+  const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(o + (size_t)row * ld);
+  const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(dout + (size_t)row * ld);
+  for (int h = 0; h < H; ++h) {
+    const float2 a = __bfloat1622float2(po[h * 32 + lane]);
+    const float2 g = __bfloat1622float2(pd[h * 32 + lane]);
+    float s = a.x * g.x + a.y * g.y;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) delta[((size_t)b * H + h) * n + pos] = s;
+  }
+}
+
+// dQ fp32 accumulator -> bf16 columns [0, D) of dQKV, with the transpose of RoPE on the first rope_heads heads
+__global__ void attn_dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, int ld_d, const float* __restrict__ rope,
+                                      int rope_heads, long long rows, int n, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 consecutive columns
+  const int per_row = D >> 3;
+  if (i >= rows * per_row) return;
+  const long long row = i / per_row;
+  const int c0 = (int)(i - row * per_row) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(dq + row * D + c0);
+  const float4 c = *reinterpret_cast<const float4*>(dq + row * D + c0 + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  if ((c0 >> 6) < rope_heads) {
+    const int pos = (int)(row % n);
+    const float4* cs = reinterpret_cast<const float4*>(rope) + (size_t)pos * 16 + ((c0 & 63) >> 2);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 t = __ldg(cs + k);
+      const float y0 = v[4 * k], y1 = v[4 * k + 1], y2 = v[4 * k + 2], y3 = v[4 * k + 3];
+      v[4 * k] = y0 * t.x + y1 * t.y;
+      v[4 * k + 1] = y1 * t.x - y0 * t.y;
+      v[4 * k + 2] = y2 * t.z + y3 * t.w;
+      v[4 * k + 3] = y3 * t.z - y2 * t.w;
+    }
+  }
+  uint4 pk;
+  pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]); pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dqkv + row * ld_d + c0) = pk;
+}
+
+int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
+             float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
+             const float* rope, int rope_heads, cudaStream_t stream) {
+  F5B_CHECK(q && k && v && out && dout && lse && delta && dq_ws && dqkv, "f5b_attn_bwd: null pointer");
+  F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0 && ld_o >= H * 64 && (ld_o & 7) == 0 && ld_d >= 3 * H * 64 && (ld_d & 7) == 0,
+            "f5b_attn_bwd: bad shape B %d H %d n %d ld %d ld_o %d ld_d %d", B, H, n, ld, ld_o, ld_d);
+  F5B_CHECK(rope_heads == 0 || rope != nullptr, "f5b_attn_bwd: rope table missing");
+  const int D = H * 64;
+  const long long rows = (long long)B * n;
+  LaunchScope scope(K_ATTN, stream, 10.0 * B * H * (double)n * n * 64, 2.0 * 8 * B * H * (double)n * 64 + 4.0 * rows * D * 2, 3);
+  F5B_CUDA(cudaMemsetAsync(dq_ws, 0, sizeof(float) * rows * D, stream));
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                    reinterpret_cast<const __nv_bfloat16*>(dout), ld_o, delta, B, H, n);
+  F5B_CUDA(cudaGetLastError());
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  const uint64_t hw = (uint64_t)H * 64, pitch = (uint64_t)ld * 2, pitch_o = (uint64_t)ld_o * 2;
+  if (make_tmap_3d(&tmQ, q, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
+  if (make_tmap_3d(&tmK, k, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
+  if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
+  if (make_tmap_3d(&tmdO, dout, 2, hw, (uint64_t)n, (uint64_t)B, pitch_o, (uint64_t)n * pitch_o, 64, AB_T, 1, true)) return -1;
+  static bool configured = false;
+  if (!configured) {
+    F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
+    configured = true;
+  }
+  AttnBwdParams p;
+  p.lse = lse;
+  p.delta = delta;
+  p.dq = dq_ws;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.ld_d = ld_d;
+  p.lens = lens;
+  p.lens_mod = lens_mod;
+  p.B = B;
+  p.H = H;
+  p.n = n;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.rope = rope;
+  p.rope_heads = rope_heads;
+  dim3 grid((n + AB_T - 1) / AB_T, B * H);
+  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  F5B_CUDA(cudaGetLastError());
+  const long long items = rows * (D >> 3);
+  attn_dq_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(dq_ws, p.dqkv, ld_d, rope, rope_heads, rows, n, D);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace f5b
+
+extern "C" int f5b_attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o,
+                            const float* lse, float* delta_ws, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod,
+                            int B, int H, int n, float scale, const float* rope, int rope_heads, f5b_stream_t stream) {
+  return f5b::attn_bwd(q, k, v, ld, out, dout, ld_o, lse, delta_ws, dq_ws, dqkv, ld_d, lens, lens_mod, B, H, n, scale, rope, rope_heads,
+                       static_cast<cudaStream_t>(stream));
+}

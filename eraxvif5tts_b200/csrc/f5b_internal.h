@@ -24,8 +24,11 @@ int ln_affine(const float* x, const float* w, const float* b, float* out_f32, vo
 int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16, int B, int n,
                int C, float eps, cudaStream_t s);
 int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s);
-int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod, int B, int H, int n,
-             float scale, cudaStream_t stream);
+int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
+             int n, float scale, cudaStream_t stream);
+int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
+             float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
+             const float* rope, int rope_heads, cudaStream_t stream);
 int convpos(const void* x, const void* wpk, const float* bias, void* out, float* resid, int B, int n, int D, int groups,
             int ksize, int mode, cudaStream_t stream);
 

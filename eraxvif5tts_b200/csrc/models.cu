@@ -207,7 +207,7 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
     g.out = w.qkv; g.ldc = 3 * D;
     g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
     F5B_TRY(gemm(w.hb, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
-    F5B_TRY(attn_fwd(w.qkv, w.qkv + D, w.qkv + 2 * D, 3 * D, w.ab, lens, batch_mod, Bf, H, n, 0.125f, s));
+    F5B_TRY(attn_fwd(w.qkv, w.qkv + D, w.qkv + 2 * D, 3 * D, w.ab, nullptr, lens, batch_mod, Bf, H, n, 0.125f, s));
     F5B_TRY(linear_gate_resid(w.ab, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
                               mod_bstride, lens, batch_mod, s));
     F5B_TRY(ln_modulate(w.x, m + 4 * D, m + 3 * D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));

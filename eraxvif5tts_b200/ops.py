@@ -166,3 +166,31 @@ def time_sinus(t):
     out = torch.empty(t.numel(), 256, dtype=bf16, device=t.device)
     L.check(lib.f5b_time_sinus(t.data_ptr(), out.data_ptr(), t.numel(), L.stream()), "f5b_time_sinus")
     return out
+
+
+def attn_fwd_lse(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale=0.125):
+    """training forward: attn_fwd + per-row log2-sum-exp lse f32 [B, H, n]"""
+    lib = L.load()
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        if not t.is_cuda or t.dtype != bf16:
+            raise L.F5bError(f"{nm}: expected a CUDA bf16 tensor")
+    _chk(lse, f32, "lse"); _chk(lens, torch.int32, "lens")
+    L.check(lib.f5b_attn_fwd_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), lse.data_ptr(), L.ptr(lens), lens_mod,
+                                 B, H, n, scale, L.stream()), "f5b_attn_fwd_lse")
+    return out
+
+
+def attn_bwd(q, k, v, ld, out, dout, lse, dqkv, lens, lens_mod, B, H, n, scale=0.125, rope=None, rope_heads=0):
+    """dqkv bf16 [B*n, 3*H*64] = gradient of the fused (pre-RoPE) QKV projection output"""
+    lib = L.load()
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != bf16:
+            raise L.F5bError(f"{nm}: expected a CUDA bf16 tensor")
+    _chk(out, bf16, "out"); _chk(dout, bf16, "dout"); _chk(lse, f32, "lse"); _chk(dqkv, bf16, "dqkv"); _chk(rope, f32, "rope")
+    _chk(lens, torch.int32, "lens")
+    delta = torch.empty(B * H * n, dtype=f32, device=out.device)
+    dq_ws = torch.empty(B * n, H * 64, dtype=f32, device=out.device)
+    L.check(lib.f5b_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), dout.data_ptr(), out.shape[-1], lse.data_ptr(),
+                             delta.data_ptr(), dq_ws.data_ptr(), dqkv.data_ptr(), dqkv.shape[-1], L.ptr(lens), lens_mod, B, H, n, scale,
+                             L.ptr(rope), rope_heads, L.stream()), "f5b_attn_bwd")
+    return dqkv

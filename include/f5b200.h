@@ -97,6 +97,18 @@ int f5b_ln_affine(const float* x, const float* w, const float* b, float* out_f32
  * (the reference zeroes them after to_out, :499-501). */
 int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod, int B, int H,
                  int n, float scale, f5b_stream_t stream);
+/* Training forward: as f5b_attn_fwd, and also writes lse f32 [B, H, n] = log2(sum_j exp2(s_ij * scale * log2 e)) per query row
+ * (+inf for query rows >= len, whose output is zero and which therefore take no gradient). */
+int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod,
+                     int B, int H, int n, float scale, f5b_stream_t stream);
+/* Attention backward (autograd of AttnProcessor's SDPA + RoPE under CFM.forward, model/cfm.py:210-283 / model/modules.py:470-493;
+ * dropout_p = 0).  q, k, v, ld as in the forward (post-RoPE values); out / dout bf16 [B*n, ld_o] (forward output, its gradient);
+ * lse from f5b_attn_fwd_lse; delta_ws f32 [B*H*n] and dq_ws f32 [B*n, H*64] are workspaces.  Writes dqkv bf16 [B*n, ld_d] =
+ * (dq | dk | dv) at columns 0, H*64, 2*H*64, i.e. the gradient of the fused QKV projection's output: the transpose of the RoPE
+ * rotation is applied to dq and dk of the first rope_heads heads (rope = f5b_rope_table).  Masked keys get zero gradient. */
+int f5b_attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
+                 float* delta_ws, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n,
+                 float scale, const float* rope, int rope_heads, f5b_stream_t stream);
 
 /* ConvPositionEmbedding conv layer (model/modules.py:171-176,183-185): grouped Conv1d(k, groups, pad k/2) + Mish.
  * x bf16 [B*n, D] token-major; wpk = weights packed by f5b_pack_convpos_weight; bias f32 [D].
