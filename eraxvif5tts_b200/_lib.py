@@ -34,6 +34,14 @@ class DitDesc(C.Structure):
                                   "qkv_w", "qkv_b", "out_w", "out_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b", "proj_w", "proj_b")]
 
 
+class DitGrads(C.Structure):
+    """F5bDitGrads: f32 gradient buffers (NULL = skip)"""
+    _fields_ = [(k, vp) for k in ("time_w0", "time_b0", "time_w2", "time_b2", "mod_w", "mod_b", "text_table", "tb_dw_w", "tb_dw_b",
+                                  "tb_ln_w", "tb_ln_b", "tb_pw1_w", "tb_pw1_b", "tb_grn_g", "tb_grn_b", "tb_pw2_w", "tb_pw2_b",
+                                  "in_wx", "in_wct", "in_b", "cp_w1", "cp_b1", "cp_w2", "cp_b2", "qkv_w", "qkv_b", "out_w", "out_b",
+                                  "ff1_w", "ff1_b", "ff2_w", "ff2_b", "proj_w", "proj_b")]
+
+
 class VocosDesc(C.Structure):
     _fields_ = [(k, i32) for k in ("n_mels", "dim", "intermediate", "num_layers", "n_fft", "hop")] + \
                [("embed_w", vp), ("embed_b", vp), ("ld_embed", i32)] + \
@@ -53,8 +61,18 @@ SIGNATURES = {
     "f5b_attn_fwd_lse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_attn_bwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp,
                                C.c_int, vp]),
+    "f5b_gate_add": (C.c_int, [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_gate_bwd": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_act_fwd": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+    "f5b_act_bwd": (C.c_int, [vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_ln_modulate_bwd": (C.c_int, [vp, vp, vp, i64, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_mse_grad": (C.c_int, [vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp]),
+    "f5b_dit_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
+    "f5b_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, sz, vp]),
+    "f5b_dit_train_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
     "f5b_convpos": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_pack_convpos_weight_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos_packed_elems": (sz, [C.c_int, C.c_int, C.c_int]),
     "f5b_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_grn": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),

@@ -77,10 +77,11 @@ struct ConvPosProblem {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       float bb = 0.f;
-      if (i < left) bb = __ldg(bias + c.ch0 + c0 + i);
-      v[i] = mish(__uint_as_float(r[i]) + bb);
+      if (bias != nullptr && i < left) bb = __ldg(bias + c.ch0 + c0 + i);
+      const float t = __uint_as_float(r[i]) + bb;
+      v[i] = MODE == 2 ? t : mish(t);  // mode 2: pre-activation output (training forward / transposed conv of the backward)
     }
-    if constexpr (MODE == 0) {
+    if constexpr (MODE == 0 || MODE == 2) {
       store_row32_bf16(out + c.row_off + c0, v, left, ((D | cpg) & 7) == 0);
     } else {
       float* o = resid + c.row_off + c0;
@@ -292,7 +293,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 }
 
 __global__ void pack_convpos_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int D, int groups, int ksize,
-                                    int cpg, int NP) {
+                                    int cpg, int NP, int transpose_flip) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tot = (int64_t)groups * ksize * NP * 64;
   if (i >= tot) return;
@@ -303,7 +304,9 @@ __global__ void pack_convpos_kernel(const float* __restrict__ w, __nv_bfloat16* 
   const int k = (int)(t % ksize);
   const int g = (int)(t / ksize);
   float v = 0.f;
-  if (co < cpg && ci < cpg) v = w[((size_t)(g * cpg + co) * cpg + ci) * ksize + k];
+  if (co < cpg && ci < cpg)
+    // transpose_flip: the conv that maps an output gradient back to the input (swap in/out channel, reverse the taps)
+    v = transpose_flip ? w[((size_t)(g * cpg + ci) * cpg + co) * ksize + (ksize - 1 - k)] : w[((size_t)(g * cpg + co) * cpg + ci) * ksize + k];
   wpk[i] = __float2bfloat16(v);
 }
 
@@ -311,13 +314,13 @@ static inline int round16(int x) { return (x + 15) / 16 * 16; }
 
 int convpos(const void* x, const void* wpk, const float* bias, void* out, float* resid, int B, int n, int D, int groups,
             int ksize, int mode, cudaStream_t stream) {
-  F5B_CHECK(x && wpk && bias, "f5b_convpos: null pointer");
+  F5B_CHECK(x && wpk && (bias || mode == 2), "f5b_convpos: null pointer");
   F5B_CHECK(B > 0 && n > 0 && D > 0 && groups > 0 && D % groups == 0 && (ksize & 1) == 1, "f5b_convpos: bad shape");
   const int cpg = D / groups;
   F5B_CHECK(cpg <= 64 && (D & 7) == 0, "f5b_convpos: channels per group %d must be <= 64 and D a multiple of 8", cpg);
-  F5B_CHECK(mode == 0 ? out != nullptr : resid != nullptr, "f5b_convpos: null output for mode %d", mode);
+  F5B_CHECK(mode >= 0 && mode <= 2 && (mode != 1 ? out != nullptr : resid != nullptr), "f5b_convpos: null output for mode %d", mode);
   const int NP = round16(cpg);
-  LaunchScope scope(K_CONVPOS, stream, 2.0 * B * n * (double)D * cpg * ksize, (double)B * n * D * (mode == 0 ? 4.0 : 10.0));
+  LaunchScope scope(K_CONVPOS, stream, 2.0 * B * n * (double)D * cpg * ksize, (double)B * n * D * (mode != 1 ? 4.0 : 10.0));
   CUtensorMap tmA, tmB;
   const bool halo = g_convpos_halo != 0 && HALO_SUB * BM + ksize - 1 <= HALO_BOXES * HALO_BOX_ROWS;
   if (make_tmap_3d(&tmA, x, 2, (uint64_t)D, (uint64_t)n, (uint64_t)B, (uint64_t)D * 2, (uint64_t)n * D * 2, 64, halo ? HALO_BOX_ROWS : BM, 1,
@@ -331,11 +334,19 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
       ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
       return launch_halo(tmA, tmB, p, stream);
     }
+    if (mode == 2) {
+      ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+      return launch_halo(tmA, tmB, p, stream);
+    }
     ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
     return launch_halo(tmA, tmB, p, stream);
   }
   if (mode == 0) {
     ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+    return launch_engine(tmA, tmB, tmA, p, total, stream);
+  }
+  if (mode == 2) {
+    ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
     return launch_engine(tmA, tmB, tmA, p, total, stream);
   }
   ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
@@ -356,16 +367,22 @@ size_t f5b_convpos_packed_elems(int D, int groups, int ksize) {
   return (size_t)groups * ksize * f5b::round16(D / groups) * 64;
 }
 
-int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream) {
+static int pack_convpos(const float* w, void* wpk, int D, int groups, int ksize, int transpose_flip, f5b_stream_t stream) {
   using namespace f5b;
   F5B_CHECK(w && wpk && groups > 0 && D % groups == 0 && D / groups <= 64, "f5b_pack_convpos_weight: bad shape");
   const int cpg = D / groups, NP = round16(cpg);
   const int64_t tot = (int64_t)groups * ksize * NP * 64;
   LaunchScope scope(K_ELEMENTWISE, static_cast<cudaStream_t>(stream), 0, 6.0 * tot);
   pack_convpos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(wpk), D, groups, ksize, cpg, NP);
+      w, reinterpret_cast<__nv_bfloat16*>(wpk), D, groups, ksize, cpg, NP, transpose_flip);
   F5B_CUDA(cudaGetLastError());
   return 0;
+}
+int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream) {
+  return pack_convpos(w, wpk, D, groups, ksize, 0, stream);
+}
+int f5b_pack_convpos_weight_t(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream) {
+  return pack_convpos(w, wpk, D, groups, ksize, 1, stream);
 }
 
 }  // extern "C"

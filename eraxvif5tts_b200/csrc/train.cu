@@ -1,0 +1,326 @@
+// Training-step drivers: DiT.forward in training form (activations kept) and its hand-written backward — the autograd graph the
+// reference builds under CFM.forward / accelerator.backward (/root/reference/src/f5_tts/model/cfm.py:210-283,
+// /root/reference/src/f5_tts/model/trainer.py:1271-1287) as explicit launch sequences.  Host-side only; every launch goes to the
+// caller's stream and nothing is allocated.  Dropout is 0 (DESIGN.md "oracle adjustments").
+#include "common.cuh"
+#include "f5b_internal.h"
+
+struct F5bDit {
+  F5bDitDesc d;
+};
+
+namespace f5b {
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off = align_up(off + count * sizeof(T));
+    return r;
+  }
+};
+
+typedef __nv_bfloat16 bf;
+
+struct BlockSave {
+  float *x_in, *x_mid, *lse;
+  bf *a, *qkv, *o, *z1, *f, *h1, *u, *z2;
+};
+
+constexpr int MAX_DEPTH = 64;
+
+struct TrainWs {
+  // time / modulation chain (M = B rows)
+  bf *sin_bf, *a1, *h1, *a2, *h2, *dmod_bf, *tb1, *tb2;
+  float *mod, *dmod, *dh2;
+  // input embedding
+  bf *a_x, *a_ct, *hb0, *u1, *c1, *u2;
+  float* h0;
+  BlockSave blk[MAX_DEPTH];
+  float* x_fin;
+  bf* hbF;
+  // backward scratch
+  float *dx, *delta, *dq_ws;
+  bf *t1, *t2, *t3, *tF, *xcol, *dact;
+  size_t bytes;
+};
+
+static TrainWs carve_train(const F5bDitDesc& d, int B, int n, void* ws) {
+  const size_t rows = (size_t)B * n;
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads, T = d.text_dim;
+  const size_t mod_dim = (size_t)d.depth * 6 * D + 2 * D;
+  Carver c(ws);
+  TrainWs w;
+  w.sin_bf = c.take<bf>((size_t)B * 256);
+  w.a1 = c.take<bf>((size_t)B * D);
+  w.h1 = c.take<bf>((size_t)B * D);
+  w.a2 = c.take<bf>((size_t)B * D);
+  w.h2 = c.take<bf>((size_t)B * D);
+  w.tb1 = c.take<bf>((size_t)B * D);
+  w.tb2 = c.take<bf>((size_t)B * D);
+  w.dh2 = c.take<float>((size_t)B * D);
+  w.mod = c.take<float>(B * mod_dim);
+  w.dmod = c.take<float>(B * mod_dim);
+  w.dmod_bf = c.take<bf>(B * mod_dim);
+  w.a_x = c.take<bf>(rows * 128);
+  w.a_ct = c.take<bf>(rows * (128 + T));
+  w.h0 = c.take<float>(rows * D);
+  w.hb0 = c.take<bf>(rows * D);
+  w.u1 = c.take<bf>(rows * D);
+  w.c1 = c.take<bf>(rows * D);
+  w.u2 = c.take<bf>(rows * D);
+  float* x_next = c.take<float>(rows * D);
+  for (int i = 0; i < d.depth && i < MAX_DEPTH; ++i) {
+    BlockSave& s = w.blk[i];
+    s.x_in = x_next;
+    s.x_mid = c.take<float>(rows * D);
+    s.lse = c.take<float>((size_t)B * H * n);
+    s.a = c.take<bf>(rows * D);
+    s.qkv = c.take<bf>(rows * 3 * D);
+    s.o = c.take<bf>(rows * D);
+    s.z1 = c.take<bf>(rows * D);
+    s.f = c.take<bf>(rows * D);
+    s.h1 = c.take<bf>(rows * F);
+    s.u = c.take<bf>(rows * F);
+    s.z2 = c.take<bf>(rows * D);
+    x_next = c.take<float>(rows * D);
+  }
+  w.x_fin = x_next;
+  w.hbF = c.take<bf>(rows * D);
+  w.dx = c.take<float>(rows * D);
+  w.delta = c.take<float>((size_t)B * H * n);
+  w.dq_ws = c.take<float>(rows * D);
+  w.t1 = c.take<bf>(rows * D);
+  w.t2 = c.take<bf>(rows * D);
+  w.t3 = c.take<bf>(rows * 3 * D);
+  w.tF = c.take<bf>(rows * F);
+  w.xcol = c.take<bf>(rows * (size_t)(D / d.convpos_groups) * d.convpos_kernel);
+  w.dact = c.take<bf>(rows * (128 + T));
+  w.bytes = c.off;
+  return w;
+}
+
+// Xcol[r, ci*ks + k] = x[b, t + k - pad, g*cpg + ci]  (zero outside the utterance): the conv weight gradient of group g is then the
+// plain product dY_g^T Xcol, landing directly in nn.Conv1d's [co][ci][k] order
+__global__ void im2col_convpos_kernel(const bf* __restrict__ x, bf* __restrict__ out, int n, int D, int g, int cpg, int ks) {
+  const size_t row = blockIdx.x;
+  const int b = (int)(row / n), t = (int)(row - (size_t)b * n);
+  const int cols = cpg * ks, pad = ks / 2;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const int ci = j / ks, k = j - ci * ks;
+    const int p = t + k - pad;
+    out[row * cols + j] = (p >= 0 && p < n) ? x[((size_t)b * n + p) * D + g * cpg + ci] : __float2bfloat16(0.f);
+  }
+}
+
+static int pick_splits(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int kblocks = (K + 63) / 64;
+  int s = (4 * sm_count() + tiles - 1) / tiles;
+  if (s > kblocks) s = kblocks;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace f5b
+
+using namespace f5b;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define F5B_TRY(call)           \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// dX[rows, K_in] (bf16) = dY[rows, N_out] W[N_out, K_in]
+static int dgrad(const void* dY, int ldy, const void* W, int k_in, void* dX, int ldx, int rows, int n_out, f5b_stream_t s) {
+  return f5b_gemm_tn(dY, ldy, 0, W, k_in, 1, dX, ldx, 0, rows, k_in, n_out, 1, s);
+}
+// dW[N_out, K_in] (f32, accumulated) += dY[rows, N_out]^T X[rows, K_in]
+static int wgrad(const void* dY, int ldy, const void* X, int ldx, float* dW, int ldw, int rows, int n_out, int k_in, f5b_stream_t s) {
+  if (dW == nullptr) return 0;
+  return f5b_gemm_tn(dY, ldy, 1, X, ldx, 1, dW, ldw, 1, n_out, k_in, rows, pick_splits(n_out, k_in, rows), s);
+}
+
+extern "C" {
+
+size_t f5b_dit_train_ws_bytes(const F5bDit* h, int B, int n) {
+  if (!h || B <= 0 || n <= 0 || h->d.depth > MAX_DEPTH) return 0;
+  return carve_train(h->d, B, n, nullptr).bytes;
+}
+
+// DiT.forward (model/backbones/dit.py:185-233) in training form: per-sample time values, activations saved for the backward.
+//   x f32 [B*n, mel] (phi_t), cond f32 [B*n, mel] or NULL (drop_audio_cond), text_embed f32 [B*n, T] (TextEmbedding output),
+//   time f32 [B], lens int32 [B] or NULL, rope f32 [n, 32, 2]  ->  pred f32 [B*n, mel]
+int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, const float* text_embed, const float* time, int B, int n,
+                          const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes, f5b_stream_t stream) {
+  F5B_CHECK(h && x && text_embed && time && rope && pred && ws && B > 0 && n > 0, "f5b_dit_train_forward: bad argument");
+  const F5bDitDesc& d = h->d;
+  F5B_CHECK(d.depth <= MAX_DEPTH && d.dim <= 1024, "f5b_dit_train_forward: depth <= %d and dim <= 1024 supported", MAX_DEPTH);
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads, T = d.text_dim, mel = d.mel_dim;
+  const int rows = B * n;
+  const int64_t mod_dim = (int64_t)d.depth * 6 * D + 2 * D;
+  TrainWs w = carve_train(d, B, n, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_train_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+
+  // TimestepEmbedding (model/modules.py:721-731) + all AdaLN linears (:311, :332); pre-activations kept
+  F5B_TRY(f5b_time_sinus(time, w.sin_bf, B, stream));
+  F5B_TRY(linear_bf16(w.sin_bf, 256, d.time_w0, 256, d.time_b0, w.a1, D, B, D, 256, F5B_ACT_NONE, s));
+  F5B_TRY(f5b_act_fwd(w.a1, w.h1, (int64_t)B * D, F5B_ACT_SILU, stream));
+  F5B_TRY(linear_bf16(w.h1, D, d.time_w2, D, d.time_b2, w.a2, D, B, D, D, F5B_ACT_NONE, s));
+  F5B_TRY(f5b_act_fwd(w.a2, w.h2, (int64_t)B * D, F5B_ACT_SILU, stream));
+  F5B_TRY(linear_f32(w.h2, D, d.mod_w, D, d.mod_b, w.mod, (int)mod_dim, B, (int)mod_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+
+  // InputEmbedding (dit.py:91-97)
+  const int KC = 128 + T;
+  F5B_TRY(f5b_pack_bf16(x, mel, w.a_x, 128, rows, mel, 128, stream));
+  F5B_TRY(f5b_pack_bf16(cond, mel, w.a_ct, KC, rows, cond ? mel : 0, 128, stream));
+  F5B_TRY(f5b_pack_bf16(text_embed, T, w.a_ct + 128, KC, rows, T, T, stream));
+  F5B_TRY(linear_f32(w.a_ct, KC, d.in_wct, KC, d.in_b, w.h0, D, rows, D, KC, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  F5B_TRY(linear_f32(w.a_x, 128, d.in_wx, 128, nullptr, w.h0, D, rows, D, 128, F5B_ACT_NONE, w.h0, D, w.hb0, D, s));
+  F5B_TRY(convpos(w.hb0, d.cp_w1, d.cp_b1, w.u1, nullptr, B, n, D, d.convpos_groups, d.convpos_kernel, 2, s));
+  F5B_TRY(f5b_act_fwd(w.u1, w.c1, (int64_t)rows * D, F5B_ACT_MISH, stream));
+  F5B_TRY(convpos(w.c1, d.cp_w2, d.cp_b2, w.u2, nullptr, B, n, D, d.convpos_groups, d.convpos_kernel, 2, s));
+  F5B_TRY(f5b_act_fwd(w.u2, w.t1, (int64_t)rows * D, F5B_ACT_MISH, stream));
+  F5B_TRY(f5b_gate_add(w.h0, w.t1, nullptr, 0, nullptr, w.blk[0].x_in, B, n, D, stream));
+
+  const bf* qkv_w = reinterpret_cast<const bf*>(d.qkv_w);
+  const bf* out_w = reinterpret_cast<const bf*>(d.out_w);
+  const bf* ff1_w = reinterpret_cast<const bf*>(d.ff1_w);
+  const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
+  for (int i = 0; i < d.depth; ++i) {
+    const BlockSave& b = w.blk[i];
+    float* x_out = (i + 1 < d.depth) ? w.blk[i + 1].x_in : w.x_fin;
+    const float* m = w.mod + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (modules.py:312)
+    F5B_TRY(ln_modulate(b.x_in, m + D, m, mod_dim, 0, b.a, rows, n, D, 1e-6f, s));
+    F5bGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
+    g.bias = d.qkv_b + (size_t)i * 3 * D;
+    g.out = b.qkv; g.ldc = 3 * D;
+    g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
+    F5B_TRY(gemm(b.a, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
+    F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s));
+    F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
+    F5B_TRY(f5b_gate_add(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, B, n, D, stream));
+    F5B_TRY(ln_modulate(b.x_mid, m + 4 * D, m + 3 * D, mod_dim, 0, b.f, rows, n, D, 1e-6f, s));
+    F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
+    F5B_TRY(f5b_act_fwd(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, stream));
+    F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
+    F5B_TRY(f5b_gate_add(b.x_mid, b.z2, m + 5 * D, mod_dim, nullptr, x_out, B, n, D, stream));
+  }
+  const float* mf = w.mod + (size_t)d.depth * 6 * D;  // AdaLayerNorm_Final: scale, shift (modules.py:333)
+  F5B_TRY(ln_modulate(w.x_fin, mf, mf + D, mod_dim, 0, w.hbF, rows, n, D, 1e-6f, s));
+  F5B_TRY(linear_f32(w.hbF, D, d.proj_w, D, d.proj_b, pred, mel, rows, mel, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  return 0;
+}
+
+// Backward of f5b_dit_train_forward.  dpred bf16 [B*n, 128] (columns >= mel zero; f5b_mse_grad).  Gradients are ACCUMULATED into
+// the f32 buffers of `g` (zero them first; NULL members are skipped).  cp_w1_t / cp_w2_t: conv_pos_embed weights packed by
+// f5b_pack_convpos_weight_t.  dtext_bf16 (optional) receives d loss / d text_embed as bf16 [B*n, T].
+int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* gr,
+                           void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                           f5b_stream_t stream) {
+  F5B_CHECK(h && dpred_bf16 && cp_w1_t && cp_w2_t && gr && rope && ws && B > 0 && n > 0, "f5b_dit_train_backward: bad argument");
+  const F5bDitDesc& d = h->d;
+  F5B_CHECK(d.depth <= MAX_DEPTH && d.dim <= 1024, "f5b_dit_train_backward: depth <= %d and dim <= 1024 supported", MAX_DEPTH);
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads, T = d.text_dim, mel = d.mel_dim;
+  const int rows = B * n;
+  const int64_t mod_dim = (int64_t)d.depth * 6 * D + 2 * D;
+  TrainWs w = carve_train(d, B, n, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_train_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+  const F5bDitGrads& g = *gr;
+  const bf* qkv_w = reinterpret_cast<const bf*>(d.qkv_w);
+  const bf* out_w = reinterpret_cast<const bf*>(d.out_w);
+  const bf* ff1_w = reinterpret_cast<const bf*>(d.ff1_w);
+  const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
+  auto off = [](float* p, size_t o) { return p ? p + o : nullptr; };
+
+  F5B_CUDA(cudaMemsetAsync(w.dmod, 0, sizeof(float) * B * mod_dim, s));
+
+  // proj_out + AdaLayerNorm_Final
+  F5B_TRY(f5b_act_bwd(dpred_bf16, nullptr, nullptr, g.proj_b, rows, mel, 128, F5B_ACT_NONE, stream));
+  F5B_TRY(wgrad(dpred_bf16, 128, w.hbF, D, g.proj_w, D, rows, mel, D, stream));
+  F5B_TRY(dgrad(dpred_bf16, 128, d.proj_w, D, w.t1, D, rows, mel, stream));
+  float* dmf = w.dmod + (size_t)d.depth * 6 * D;
+  F5B_TRY(f5b_ln_modulate_bwd(w.t1, w.x_fin, w.mod + (size_t)d.depth * 6 * D, mod_dim, w.dx, 0, dmf, dmf + D, B, n, D, 1e-6f, stream));
+
+  for (int i = d.depth - 1; i >= 0; --i) {
+    const BlockSave& b = w.blk[i];
+    const float* m = w.mod + (size_t)i * 6 * D;
+    float* dm = w.dmod + (size_t)i * 6 * D;
+    // ---- x_out = x_mid + gate_mlp * (W2 gelu(W1 f + b1) + b2),  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
+    F5B_TRY(f5b_gate_bwd(w.dx, b.z2, m + 5 * D, mod_dim, nullptr, w.t1, dm + 5 * D, off(g.ff2_b, (size_t)i * D), B, n, D, stream));
+    F5B_TRY(wgrad(w.t1, D, b.u, F, off(g.ff2_w, (size_t)i * D * F), F, rows, D, F, stream));
+    F5B_TRY(dgrad(w.t1, D, ff2_w + (size_t)i * D * F, F, w.tF, F, rows, D, stream));
+    F5B_TRY(f5b_act_bwd(w.tF, b.h1, w.tF, off(g.ff1_b, (size_t)i * F), rows, F, F, F5B_ACT_GELU_TANH, stream));
+    F5B_TRY(wgrad(w.tF, F, b.f, D, off(g.ff1_w, (size_t)i * F * D), D, rows, F, D, stream));
+    F5B_TRY(dgrad(w.tF, F, ff1_w + (size_t)i * F * D, D, w.t1, D, rows, F, stream));
+    F5B_TRY(f5b_ln_modulate_bwd(w.t1, b.x_mid, m + 4 * D, mod_dim, w.dx, 1, dm + 4 * D, dm + 3 * D, B, n, D, 1e-6f, stream));
+    // ---- x_mid = x_in + gate_msa * mask(Wo attn(rope(Wqkv a + b)) + bo),  a = LN(x_in) (1 + scale_msa) + shift_msa
+    F5B_TRY(f5b_gate_bwd(w.dx, b.z1, m + 2 * D, mod_dim, lens, w.t1, dm + 2 * D, off(g.out_b, (size_t)i * D), B, n, D, stream));
+    F5B_TRY(wgrad(w.t1, D, b.o, D, off(g.out_w, (size_t)i * D * D), D, rows, D, D, stream));
+    F5B_TRY(dgrad(w.t1, D, out_w + (size_t)i * D * D, D, w.t2, D, rows, D, stream));
+    F5B_TRY(attn_bwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, w.t2, D, b.lse, w.delta, w.dq_ws, w.t3, 3 * D, lens, 0, B, H, n, 0.125f,
+                     rope, d.rope_heads, s));
+    F5B_TRY(f5b_act_bwd(w.t3, nullptr, nullptr, off(g.qkv_b, (size_t)i * 3 * D), rows, 3 * D, 3 * D, F5B_ACT_NONE, stream));
+    F5B_TRY(wgrad(w.t3, 3 * D, b.a, D, off(g.qkv_w, (size_t)i * 3 * D * D), D, rows, 3 * D, D, stream));
+    F5B_TRY(dgrad(w.t3, 3 * D, qkv_w + (size_t)i * 3 * D * D, D, w.t1, D, rows, 3 * D, stream));
+    F5B_TRY(f5b_ln_modulate_bwd(w.t1, b.x_in, m + D, mod_dim, w.dx, 1, dm + D, dm, B, n, D, 1e-6f, stream));
+  }
+
+  // ---- InputEmbedding: x0 = h0 + mish(conv2(mish(conv1(h0)))),  h0 = [x | cond | text] W^T + b
+  const int G = d.convpos_groups, cpg = D / G, ks = d.convpos_kernel, ccols = cpg * ks;
+  F5B_TRY(f5b_gate_bwd(w.dx, nullptr, nullptr, 0, nullptr, w.t1, nullptr, nullptr, B, n, D, stream));       // bf16(dx)
+  F5B_TRY(f5b_act_bwd(w.t1, w.u2, w.t2, g.cp_b2, rows, D, D, F5B_ACT_MISH, stream));                         // d u2
+  if (g.cp_w2)
+    for (int gi = 0; gi < G; ++gi) {
+      im2col_convpos_kernel<<<rows, 256, 0, s>>>(w.c1, w.xcol, n, D, gi, cpg, ks);
+      F5B_CUDA(cudaGetLastError());
+      F5B_TRY(wgrad(w.t2 + gi * cpg, D, w.xcol, ccols, g.cp_w2 + (size_t)gi * cpg * ccols, ccols, rows, cpg, ccols, stream));
+    }
+  F5B_TRY(convpos(w.t2, cp_w2_t, nullptr, w.t1, nullptr, B, n, D, G, ks, 2, s));                             // d c1
+  F5B_TRY(f5b_act_bwd(w.t1, w.u1, w.t2, g.cp_b1, rows, D, D, F5B_ACT_MISH, stream));                         // d u1
+  if (g.cp_w1)
+    for (int gi = 0; gi < G; ++gi) {
+      im2col_convpos_kernel<<<rows, 256, 0, s>>>(w.hb0, w.xcol, n, D, gi, cpg, ks);
+      F5B_CUDA(cudaGetLastError());
+      F5B_TRY(wgrad(w.t2 + gi * cpg, D, w.xcol, ccols, g.cp_w1 + (size_t)gi * cpg * ccols, ccols, rows, cpg, ccols, stream));
+    }
+  F5B_TRY(convpos(w.t2, cp_w1_t, nullptr, w.t1, nullptr, B, n, D, G, ks, 2, s));                             // conv path of d h0
+  F5B_TRY(f5b_gate_add(w.dx, w.t1, nullptr, 0, nullptr, w.dx, B, n, D, stream));                             // d h0 = dx + conv path
+  F5B_TRY(f5b_gate_bwd(w.dx, nullptr, nullptr, 0, nullptr, w.t1, nullptr, g.in_b, B, n, D, stream));         // bf16(d h0), d bias
+  const int KC = 128 + T;
+  F5B_TRY(wgrad(w.t1, D, w.a_x, 128, g.in_wx, 128, rows, D, 128, stream));
+  F5B_TRY(wgrad(w.t1, D, w.a_ct, KC, g.in_wct, KC, rows, D, KC, stream));
+  if (dtext_bf16 != nullptr) {
+    // d text_embed = d h0 W_ct[:, 128:]  (the text columns of the input projection)
+    F5B_TRY(f5b_gemm_tn(w.t1, D, 0, reinterpret_cast<const bf*>(d.in_wct) + 128, KC, 1, dtext_bf16, T, 0, rows, T, D, 1, stream));
+  }
+
+  // ---- modulation + time MLP: mod = silu(a2) Wm^T + bm, a2 = silu(a1) W2^T + b2, a1 = sinus(t) W0^T + b0
+  F5B_TRY(f5b_pack_bf16(w.dmod, (int)mod_dim, w.dmod_bf, (int)mod_dim, B, (int)mod_dim, (int)mod_dim, stream));
+  F5B_TRY(f5b_act_bwd(w.dmod_bf, nullptr, nullptr, g.mod_b, B, (int)mod_dim, (int)mod_dim, F5B_ACT_NONE, stream));
+  F5B_TRY(wgrad(w.dmod_bf, (int)mod_dim, w.h2, D, g.mod_w, D, B, (int)mod_dim, D, stream));
+  F5B_CUDA(cudaMemsetAsync(w.dh2, 0, sizeof(float) * B * D, s));
+  {
+    const int kb = ((int)mod_dim + 63) / 64;
+    F5B_TRY(f5b_gemm_tn(w.dmod_bf, (int)mod_dim, 0, d.mod_w, D, 1, w.dh2, D, 1, B, D, (int)mod_dim, kb < 32 ? kb : 32, stream));
+  }
+  F5B_TRY(f5b_pack_bf16(w.dh2, D, w.tb1, D, B, D, D, stream));
+  F5B_TRY(f5b_act_bwd(w.tb1, w.a2, w.tb1, g.time_b2, B, D, D, F5B_ACT_SILU, stream));                        // d a2
+  F5B_TRY(wgrad(w.tb1, D, w.h1, D, g.time_w2, D, B, D, D, stream));
+  F5B_TRY(dgrad(w.tb1, D, d.time_w2, D, w.tb2, D, B, D, stream));
+  F5B_TRY(f5b_act_bwd(w.tb2, w.a1, w.tb2, g.time_b0, B, D, D, F5B_ACT_SILU, stream));                        // d a1
+  F5B_TRY(wgrad(w.tb2, D, w.sin_bf, 256, g.time_w0, 256, B, D, 256, stream));
+  return 0;
+}
+
+}  // extern "C"

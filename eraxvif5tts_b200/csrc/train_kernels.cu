@@ -1,0 +1,337 @@
+// Backward-pass building blocks of the training step (autograd of CFM.forward, /root/reference/src/f5_tts/model/cfm.py:210-283,
+// through DiTBlock /root/reference/src/f5_tts/model/modules.py:627-641): everything that is not a GEMM or attention.
+// All of these are HBM-bound row / column sweeps; the per-batch-row modulation gradients and bias gradients are column
+// reductions done in the same sweep that produces the tensor the next GEMM consumes (one pass over the activation, fp32 atomics
+// for the few thousand column sums).
+#include "common.cuh"
+#include "f5b_internal.h"
+
+namespace f5b {
+
+constexpr int CT_ROWS = 64;     // rows per CTA of the column-thread kernels
+constexpr int CT_THREADS = 256; // each thread owns column pairs {2t, 2t+1} + k*512
+
+__device__ __forceinline__ float act_eval(int act, float x) {
+  if (act == F5B_ACT_GELU_TANH) {
+    const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+    return 0.5f * x * (1.0f + tanh_approx(u));
+  } else if (act == F5B_ACT_GELU_ERF) {
+    return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+  } else if (act == F5B_ACT_SILU) {
+    return x / (1.0f + __expf(-x));
+  } else if (act == F5B_ACT_MISH) {
+    const float sp = x > 20.f ? x : log1pf(__expf(x));
+    return x * tanhf(sp);
+  }
+  return x;
+}
+__device__ __forceinline__ float act_grad(int act, float x) {
+  if (act == F5B_ACT_GELU_TANH) {
+    const float k = 0.7978845608028654f;
+    const float u = k * x * fmaf(0.044715f * x, x, 1.0f);
+    const float t = tanhf(u);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * fmaf(3.0f * 0.044715f * x, x, 1.0f);
+  } else if (act == F5B_ACT_GELU_ERF) {
+    return 0.5f * (1.0f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  } else if (act == F5B_ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return s * (1.0f + x * (1.0f - s));
+  } else if (act == F5B_ACT_MISH) {
+    const float sp = x > 20.f ? x : log1pf(__expf(x));
+    const float t = tanhf(sp);
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return t + x * (1.0f - t * t) * s;
+  }
+  return 1.0f;
+}
+
+// out[r, :] = x[r, :] + gate[b, :] * z[r, :]   (rows with pos >= len[b] keep x: the reference zeroes the attention branch there,
+// model/modules.py:499-501).  The un-fused training form of the gate-residual GEMM epilogue: z is kept for the gate gradient.
+__global__ void gate_add_kernel(const float* x, const __nv_bfloat16* __restrict__ z, const float* __restrict__ gate,
+                                int64_t gate_bstride, const int32_t* __restrict__ lens, float* out, int n, int C) {  // out may alias x
+  const int b = blockIdx.y;
+  const int pos = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pos >= n) return;
+  const size_t row = (size_t)b * n + pos;
+  const bool live = lens == nullptr || pos < __ldg(lens + b);
+  const float* g = gate ? gate + (size_t)b * gate_bstride : nullptr;
+  for (int c = (threadIdx.x & 31) * 2; c < C; c += 64) {
+    float2 v = *reinterpret_cast<const float2*>(x + row * C + c);
+    if (live) {
+      const float2 zz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(z + row * C + c));
+      const float g0 = g ? __ldg(g + c) : 1.f, g1 = g ? __ldg(g + c + 1) : 1.f;
+      v.x = fmaf(g0, zz.x, v.x);
+      v.y = fmaf(g1, zz.y, v.y);
+    }
+    *reinterpret_cast<float2*>(out + row * C + c) = v;
+  }
+}
+
+// dz[r, :] = bf16(gate[b, :] * dx[r, :]) (0 on masked rows);  dgate[b, :] += sum_r dx[r, :] * z[r, :];  dbias[:] += sum_r dz[r, :]
+__global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
+                                                              const float* __restrict__ gate, int64_t gate_bstride,
+                                                              const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ dz,
+                                                              float* __restrict__ dgate, float* __restrict__ dbias, int n, int C) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * CT_ROWS;
+  const int p1 = min(n, p0 + CT_ROWS);
+  const int live_end = lens ? min(p1, __ldg(lens + b)) : p1;
+  const float* g = gate ? gate + (size_t)b * gate_bstride : nullptr;
+  for (int c = threadIdx.x * 2; c < C; c += 2 * CT_THREADS) {
+    const float g0 = g ? __ldg(g + c) : 1.f, g1 = g ? __ldg(g + c + 1) : 1.f;
+    float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int pos = p0; pos < p1; ++pos) {
+      const size_t off = ((size_t)b * n + pos) * C + c;
+      float2 o = make_float2(0.f, 0.f);
+      if (pos < live_end) {
+        const float2 d = *reinterpret_cast<const float2*>(dx + off);
+        if (z != nullptr) {
+          const float2 zz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(z + off));
+          a0 = fmaf(d.x, zz.x, a0);
+          a1 = fmaf(d.y, zz.y, a1);
+        }
+        o.x = g0 * d.x;
+        o.y = g1 * d.y;
+        s0 += o.x;
+        s1 += o.y;
+      }
+      *reinterpret_cast<uint32_t*>(dz + off) = pack_bf16(o.x, o.y);
+    }
+    if (dgate && z != nullptr) {
+      atomicAdd(dgate + (size_t)b * gate_bstride + c, a0);
+      atomicAdd(dgate + (size_t)b * gate_bstride + c + 1, a1);
+    }
+    if (dbias) {
+      atomicAdd(dbias + c, s0);
+      atomicAdd(dbias + c + 1, s1);
+    }
+  }
+}
+
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n2, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(h)[i]);
+  reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(act_eval(act, v.x), act_eval(act, v.y));
+}
+
+// dh[r, :] = bf16(du[r, :] * act'(h[r, :]));  dbias[:] += sum_r dh[r, :]      (act NONE + dh NULL = plain column sum of du)
+__global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16* du, const __nv_bfloat16* __restrict__ h,
+                                                             __nv_bfloat16* dh /* may alias du */, float* __restrict__ dbias, int64_t rows,
+                                                             int C, int ld, int act) {
+  const int64_t r0 = (int64_t)blockIdx.x * CT_ROWS;
+  const int64_t r1 = min(rows, r0 + CT_ROWS);
+  for (int c = threadIdx.x * 2; c < C; c += 2 * CT_THREADS) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; ++r) {
+      const size_t off = (size_t)r * ld + c;
+      float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(du + off));
+      if (h != nullptr) {
+        const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + off));
+        d.x *= act_grad(act, hv.x);
+        d.y *= act_grad(act, hv.y);
+      }
+      if (dh != nullptr) {
+        const uint32_t pk = pack_bf16(d.x, d.y);
+        *reinterpret_cast<uint32_t*>(dh + off) = pk;
+        d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));  // the bias sees what the GEMMs see
+      }
+      s0 += d.x;
+      s1 += d.y;
+    }
+    if (dbias) {
+      atomicAdd(dbias + c, s0);
+      atomicAdd(dbias + c + 1, s1);
+    }
+  }
+}
+
+// Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine; AdaLayerNorm model/modules.py:310-315):
+//   dshift[b] += sum_r dy;  dscale[b] += sum_r dy * xhat;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b])
+// One warp per row (row and statistics recomputed from the saved fp32 x), 8 rows per warp, column sums staged in shared memory.
+template <int VEC>
+__global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
+                                                         int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
+                                                         int D, float eps) {
+  extern __shared__ float ln_acc[];  // [2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int nvec = D >> 2;
+  for (int i = threadIdx.x; i < 2 * D; i += 256) ln_acc[i] = 0.f;
+  __syncthreads();
+  float4 a_sc[VEC], a_sh[VEC], one_sc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    a_sc[j] = a_sh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int idx = lane + j * 32;
+    one_sc[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale != nullptr && idx < nvec) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) + idx);
+      one_sc[j] = make_float4(1.f + s.x, 1.f + s.y, 1.f + s.z, 1.f + s.w);
+    }
+  }
+  const int p0 = blockIdx.x * 64 + warp * 8;
+  for (int pos = p0; pos < min(n, p0 + 8); ++pos) {
+    const size_t row = (size_t)b * n + pos;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const uint2* dr = reinterpret_cast<const uint2*>(dy + row * D);
+    float4 v[VEC], g[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int idx = lane + j * 32;
+      v[j] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+      const uint2 d = idx < nvec ? dr[idx] : make_uint2(0u, 0u);
+      const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
+      const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+      g[j] = make_float4(d0.x, d0.y, d1.x, d1.y);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      if (lane + j * 32 < nvec) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      if (lane + j * 32 < nvec) {
+        v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;  // xhat
+        a_sh[j].x += g[j].x; a_sh[j].y += g[j].y; a_sh[j].z += g[j].z; a_sh[j].w += g[j].w;
+        a_sc[j].x = fmaf(g[j].x, v[j].x, a_sc[j].x); a_sc[j].y = fmaf(g[j].y, v[j].y, a_sc[j].y);
+        a_sc[j].z = fmaf(g[j].z, v[j].z, a_sc[j].z); a_sc[j].w = fmaf(g[j].w, v[j].w, a_sc[j].w);
+        g[j].x *= one_sc[j].x; g[j].y *= one_sc[j].y; g[j].z *= one_sc[j].z; g[j].w *= one_sc[j].w;
+        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+        s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
+      }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    float4* o = reinterpret_cast<float4*>(dx + row * D);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        float4 r;
+        r.x = rstd * (g[j].x - s1 - v[j].x * s2);
+        r.y = rstd * (g[j].y - s1 - v[j].y * s2);
+        r.z = rstd * (g[j].z - s1 - v[j].z * s2);
+        r.w = rstd * (g[j].w - s1 - v[j].w * s2);
+        if (accumulate) {
+          const float4 p = o[idx];
+          r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+        }
+        o[idx] = r;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      float* sc = ln_acc + idx * 4;
+      float* sh = ln_acc + D + idx * 4;
+      atomicAdd(sc, a_sc[j].x); atomicAdd(sc + 1, a_sc[j].y); atomicAdd(sc + 2, a_sc[j].z); atomicAdd(sc + 3, a_sc[j].w);
+      atomicAdd(sh, a_sh[j].x); atomicAdd(sh + 1, a_sh[j].y); atomicAdd(sh + 2, a_sh[j].z); atomicAdd(sh + 3, a_sh[j].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += 256) {
+    if (dscale) atomicAdd(dscale + (size_t)b * mod_bstride + i, ln_acc[i]);
+    if (dshift) atomicAdd(dshift + (size_t)b * mod_bstride + i, ln_acc[D + i]);
+  }
+}
+
+// d loss / d pred of the flow-matching loss (cfm.py:280-283): 2 (pred - flow) / (count * C) on masked rows, bf16 [rows, ld] zero padded
+__global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ flow, const uint8_t* __restrict__ mask,
+                                const float* __restrict__ loss2, __nv_bfloat16* __restrict__ out, int64_t rows, int C, int ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t r = i / ld;
+  const int c = (int)(i - r * ld);
+  float v = 0.f;
+  if (c < C && mask[r]) v = 2.f * (pred[r * C + c] - flow[r * C + c]) / fmaxf(loss2[1], 1.f);
+  out[i] = __float2bfloat16(v);
+}
+
+}  // namespace f5b
+
+using namespace f5b;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, float* out, int B,
+                 int n, int C, f5b_stream_t stream) {
+  F5B_CHECK(x && z_bf16 && out && B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_gate_add: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 10.0 * B * n * C);
+  gate_add_kernel<<<dim3((n + 7) / 8, B), 256, 0, ST(stream)>>>(x, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens,
+                                                               out, n, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                 float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream) {
+  F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_gate_bwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * B * n * C);
+  gate_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), CT_THREADS, 0, ST(stream)>>>(
+      dx, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16), dgate, dbias,
+      n, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_stream_t stream) {
+  F5B_CHECK(h_bf16 && out_bf16 && count > 0 && (count & 1) == 0, "f5b_act_fwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * count);
+  act_fwd_kernel<<<(unsigned)((count / 2 + 255) / 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16),
+                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 2, act);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
+                f5b_stream_t stream) {
+  F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 1) == 0 && (ld & 1) == 0 && ld >= C, "f5b_act_bwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * rows * C);
+  act_bwd_kernel<<<(unsigned)((rows + CT_ROWS - 1) / CT_ROWS), CT_THREADS, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<__nv_bfloat16*>(dh_bf16),
+      dbias, rows, C, ld, act);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,
+                        float* dscale, float* dshift, int B, int n, int D, float eps, f5b_stream_t stream) {
+  F5B_CHECK(dy_bf16 && x && dx && B > 0 && n > 0, "f5b_ln_modulate_bwd: bad argument");
+  F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_modulate_bwd: D=%d must be a multiple of 4 and <= 1024", D);
+  LaunchScope scope(K_NORM, ST(stream), 0, (accumulate ? 14.0 : 10.0) * B * n * D);
+  const dim3 grid((n + 63) / 64, B);
+  const size_t sm = 2 * (size_t)D * sizeof(float);
+  auto* d = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+  const int nvec = D / 4;
+  if (nvec <= 64) ln_mod_bwd_kernel<2><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
+  else if (nvec <= 128) ln_mod_bwd_kernel<4><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
+  else ln_mod_bwd_kernel<8><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_mse_grad(const float* pred, const float* flow, const uint8_t* mask, const float* loss2, void* out_bf16, int64_t rows, int C, int ld,
+                 f5b_stream_t stream) {
+  F5B_CHECK(pred && flow && mask && loss2 && out_bf16 && rows > 0 && C > 0 && ld >= C, "f5b_mse_grad: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * rows * C + 2.0 * rows * ld);
+  mse_grad_kernel<<<(unsigned)((rows * ld + 255) / 256), 256, 0, ST(stream)>>>(pred, flow, mask, loss2, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                               rows, C, ld);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

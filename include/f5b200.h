@@ -36,7 +36,7 @@ enum {
   F5B_EPI_QKV_ROPE = 2,   /* out bf16[M,ldc] = acc + bias with rotary embedding on the first rope_heads heads of the q and k sections */
   F5B_EPI_GATE_RESID = 3  /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
 };
-enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3 };
+enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3, F5B_ACT_MISH = 4 /* f5b_act_fwd/bwd only */ };
 
 typedef struct F5bGemmArgs {
   int32_t M, N, K;
@@ -112,11 +112,15 @@ int f5b_attn_bwd(const void* q, const void* k, const void* v, int ld, const void
 
 /* ConvPositionEmbedding conv layer (model/modules.py:171-176,183-185): grouped Conv1d(k, groups, pad k/2) + Mish.
  * x bf16 [B*n, D] token-major; wpk = weights packed by f5b_pack_convpos_weight; bias f32 [D].
- * mode 0: out_bf16[B*n, D] = mish(conv(x)+bias);  mode 1: resid_f32[B*n, D] += mish(conv(x)+bias). */
+ * mode 0: out_bf16[B*n, D] = mish(conv(x)+bias);  mode 1: resid_f32[B*n, D] += mish(conv(x)+bias);
+ * mode 2: out_bf16 = conv(x)+bias without the activation (bias may be NULL) — the training forward keeps the pre-activation,
+ * and the backward's input gradient is the same conv with weights packed by f5b_pack_convpos_weight_t. */
 int f5b_convpos(const void* x_bf16, const void* wpk, const float* bias, void* out_bf16, float* resid_f32, int B, int n,
                 int D, int groups, int ksize, int mode, f5b_stream_t stream);
 /* w f32 [D, D/groups, ksize] (nn.Conv1d layout) -> bf16 [groups, ksize, NP, 64], NP = roundup(D/groups, 16). */
 int f5b_pack_convpos_weight(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream);
+/* same packing of the TRANSPOSED conv (in/out channels of each group swapped, taps reversed): conv(dy, W^T) = d loss / d x */
+int f5b_pack_convpos_weight_t(const float* w, void* wpk, int D, int groups, int ksize, f5b_stream_t stream);
 size_t f5b_convpos_packed_elems(int D, int groups, int ksize);
 
 /* Depth-wise Conv1d(k=7, pad 3, groups=C) + bias + LayerNorm(C, eps, affine) -> bf16
@@ -245,6 +249,28 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
                     int64_t mod_bstride, const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes,
                     f5b_stream_t stream);
 
+/* ---- training step: DiT.forward with saved activations + hand-written backward (CFM.forward / accelerator.backward,
+ * model/cfm.py:210-283, model/trainer.py:1271-1287; dropout 0) ------------------------------------------------------------------
+ * F5bDitGrads: f32 gradient buffers, one per F5bDitDesc tensor and of the same shape, except that the conv_pos_embed weight
+ * gradients use nn.Conv1d's [D, D/groups, k] layout and the bf16 weights get f32 gradients.  NULL members are skipped. */
+typedef struct F5bDitGrads {
+  float *time_w0, *time_b0, *time_w2, *time_b2, *mod_w, *mod_b;
+  float *text_table, *tb_dw_w, *tb_dw_b, *tb_ln_w, *tb_ln_b, *tb_pw1_w, *tb_pw1_b, *tb_grn_g, *tb_grn_b, *tb_pw2_w, *tb_pw2_b;
+  float *in_wx, *in_wct, *in_b, *cp_w1, *cp_b1, *cp_w2, *cp_b2;
+  float *qkv_w, *qkv_b, *out_w, *out_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b, *proj_w, *proj_b;
+} F5bDitGrads;
+size_t f5b_dit_train_ws_bytes(const F5bDit* h, int B, int n);
+/* x f32 [B*n, mel] (phi_t), cond f32 [B*n, mel] or NULL (drop_audio_cond), text_embed f32 [B*n, T], time f32 [B] (per sample),
+ * lens int32 [B] or NULL, rope f32 [n, 32, 2] -> pred f32 [B*n, mel]; every activation the backward needs stays in ws. */
+int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, const float* text_embed, const float* time, int B, int n,
+                          const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes, f5b_stream_t stream);
+/* dpred bf16 [B*n, 128] (f5b_mse_grad).  Gradients are ACCUMULATED into g (zero the buffers first).  cp_w1_t / cp_w2_t: the
+ * conv_pos_embed weights packed by f5b_pack_convpos_weight_t.  dtext_bf16 (optional): d loss / d text_embed, bf16 [B*n, T].
+ * ws must be the workspace the forward ran in. */
+int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* g,
+                           void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                           f5b_stream_t stream);
+
 /* rope table for n positions, dim_head 64: f32 [n, 32, 2] = (cos, sin)(pos * 10000^(-2j/64))
  * (x_transformers RotaryEmbedding.forward_from_seq_len, call site dit.py:215) */
 int f5b_rope_table(float* out, int n, f5b_stream_t stream);
@@ -270,6 +296,26 @@ size_t f5b_vocos_workspace_bytes(const F5bVocos* h, int B, int T);
 /* mel f32 [B, T, n_mels] (token-major) -> wav f32 [B, hop*(T-1)] */
 int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* wav, void* ws, size_t ws_bytes,
                      f5b_stream_t stream);
+
+/* ---- backward-pass building blocks (autograd of CFM.forward -> DiT, model/cfm.py:210-283; DiTBlock model/modules.py:627-641) ----
+ * Un-fused training form of the gated residual: out = x + gate[b] * z (rows >= lens[b] keep x, :499-501); z bf16 [B*n, C]. */
+int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, float* out, int B,
+                 int n, int C, f5b_stream_t stream);
+/* ... and its backward: dz = bf16(gate[b] * dx) (0 on rows >= lens[b]); dgate[b] += sum_r dx * z; dbias += sum_r dz (NULL = skip) */
+int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                 float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream);
+/* out = act(h) on `count` bf16 elements;  dh = bf16(du * act'(h)) over [rows, C] (pitch ld) with dbias[C] += column sums of dh.
+ * h NULL: dh = du (dh may be NULL too: plain column sum = bias gradient of a Linear). */
+int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_stream_t stream);
+int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
+                f5b_stream_t stream);
+/* Backward of f5b_ln_modulate: dx (+)= LN-backward(dy * (1 + scale[b])), dscale[b] += sum_r dy * xhat, dshift[b] += sum_r dy.
+ * x is the saved fp32 input (statistics are recomputed); scale NULL = plain LayerNorm; D <= 1024. */
+int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,
+                        float* dscale, float* dshift, int B, int n, int D, float eps, f5b_stream_t stream);
+/* d loss / d pred of f5b_masked_mse: 2 (pred - flow) / loss2[1] on masked rows -> bf16 [rows, ld] (columns >= C zero) */
+int f5b_mse_grad(const float* pred, const float* flow, const uint8_t* mask, const float* loss2, void* out_bf16, int64_t rows, int C,
+                 int ld, f5b_stream_t stream);
 
 /* ---- optimizer step (trainer.py:1280-1287, 1321): clip_grad_norm_ + torch.optim.AdamW + EMA lerp, one fused pass ------------
  * f5b_grad_sumsq: out[0] = sum(g^2) over a flat f32 gradient buffer (deterministic two-pass; ws f32 [1024]).
