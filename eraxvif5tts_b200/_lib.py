@@ -70,6 +70,13 @@ SIGNATURES = {
     "f5b_dit_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
     "f5b_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, sz, vp]),
     "f5b_dit_train_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
+    "f5b_dit_text_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
+    "f5b_dit_text_embed_train": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "f5b_dit_text_embed_backward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
+    "f5b_ln_affine_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_grn_gelu_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_dwconv7_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_text_lookup_bwd": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),

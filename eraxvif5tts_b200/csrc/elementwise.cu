@@ -85,7 +85,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
-                                                         int B, int n, int C, float eps) {
+                                                         int B, int n, int C, float eps, float* __restrict__ y_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= B * n) return;
@@ -118,7 +118,10 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < VEC; ++j)
-    if (lane + j * 32 < nvec) s += acc[j].x + acc[j].y + acc[j].z + acc[j].w;
+    if (lane + j * 32 < nvec) {
+      s += acc[j].x + acc[j].y + acc[j].z + acc[j].w;
+      if (y_out != nullptr) reinterpret_cast<float4*>(y_out + (size_t)row * C)[lane + j * 32] = acc[j];  // training: keep the conv output
+    }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
@@ -142,16 +145,16 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
 }
 
 int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B, int n,
-               int C, float eps, cudaStream_t s) {
+               int C, float eps, cudaStream_t s, float* y_out) {
   F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 3) == 0 && C <= 1024, "f5b_dwconv7_ln: C=%d must be a multiple of 4 and <= 1024", C);
   const int grid = (B * n + 7) / 8;
   LaunchScope scope(K_NORM, s, 0, 6.0 * B * n * C);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = C / 4;
-  if (nvec <= 32) dwconv7_ln_kernel<1><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
-  else if (nvec <= 64) dwconv7_ln_kernel<2><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
-  else if (nvec <= 128) dwconv7_ln_kernel<4><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
-  else dwconv7_ln_kernel<8><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps);
+  if (nvec <= 32) dwconv7_ln_kernel<1><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else if (nvec <= 64) dwconv7_ln_kernel<2><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else if (nvec <= 128) dwconv7_ln_kernel<4><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else dwconv7_ln_kernel<8><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -22,7 +22,7 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int64_t 
 int ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
               cudaStream_t s);
 int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16, int B, int n,
-               int C, float eps, cudaStream_t s);
+               int C, float eps, cudaStream_t s, float* y_out = nullptr);
 int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s);
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
              int n, float scale, cudaStream_t stream);

@@ -118,6 +118,41 @@ __global__ void im2col_convpos_kernel(const bf* __restrict__ x, bf* __restrict__
   }
 }
 
+struct TextSave {
+  float *h_in, *y;
+  bf *tb, *p1, *t2, *t3;
+};
+struct TextWs {
+  TextSave L[16];
+  float *gx, *stats, *dh, *dy;
+  bf *dz, *d2, *dtb;
+  size_t bytes;
+};
+static TextWs carve_text(const F5bDitDesc& d, int B, int n, void* ws) {
+  const size_t rows = (size_t)B * n;
+  const int T = d.text_dim, T2 = 2 * d.text_dim;
+  Carver c(ws);
+  TextWs w;
+  for (int j = 0; j < d.conv_layers && j < 16; ++j) {
+    TextSave& s = w.L[j];
+    s.h_in = c.take<float>(rows * T);
+    s.y = c.take<float>(rows * T);
+    s.tb = c.take<bf>(rows * T);
+    s.p1 = c.take<bf>(rows * T2);
+    s.t2 = c.take<bf>(rows * T2);
+    s.t3 = c.take<bf>(rows * T2);
+  }
+  w.gx = c.take<float>((size_t)B * T2);
+  w.stats = c.take<float>((size_t)B * 3 * T2);
+  w.dh = c.take<float>(rows * T);
+  w.dy = c.take<float>(rows * T);
+  w.dz = c.take<bf>(rows * T);
+  w.d2 = c.take<bf>(rows * T2);
+  w.dtb = c.take<bf>(rows * T);
+  w.bytes = c.off;
+  return w;
+}
+
 static int pick_splits(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
   const int kblocks = (K + 63) / 64;
@@ -320,6 +355,76 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
   F5B_TRY(dgrad(w.tb1, D, d.time_w2, D, w.tb2, D, B, D, stream));
   F5B_TRY(f5b_act_bwd(w.tb2, w.a1, w.tb2, g.time_b0, B, D, D, F5B_ACT_SILU, stream));                        // d a1
   F5B_TRY(wgrad(w.tb2, D, w.sin_bf, 256, g.time_w0, 256, B, D, 256, stream));
+  return 0;
+}
+
+size_t f5b_dit_text_train_ws_bytes(const F5bDit* h, int B, int n) {
+  if (!h || B <= 0 || n <= 0 || h->d.conv_layers > 16) return 0;
+  return carve_text(h->d, B, n, nullptr).bytes;
+}
+
+// TextEmbedding.forward (model/backbones/dit.py:49-79) in training form: un-fused GELU, every ConvNeXtV2Block input kept
+int f5b_dit_text_embed_train(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, float* out, void* ws,
+                             size_t ws_bytes, f5b_stream_t stream) {
+  F5B_CHECK(h && ids && out && ws && B > 0 && n > 0 && nt > 0, "f5b_dit_text_embed_train: bad argument");
+  const F5bDitDesc& d = h->d;
+  F5B_CHECK(d.conv_layers <= 16 && d.text_dim <= 1024, "f5b_dit_text_embed_train: conv_layers <= 16, text_dim <= 1024");
+  F5B_CHECK(!(d.text_mask_padding && d.conv_layers > 0), "f5b_dit_text_embed_train: text_mask_padding is not built for training");
+  const int T = d.text_dim, T2 = 2 * d.text_dim;
+  const size_t rows = (size_t)B * n;
+  TextWs w = carve_text(d, B, n, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_text_embed_train: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+  float* first = d.conv_layers > 0 ? w.L[0].h_in : out;
+  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, first, nullptr, B, n, T, drop_text, d.conv_layers > 0, stream));
+  for (int j = 0; j < d.conv_layers; ++j) {
+    const TextSave& L = w.L[j];
+    float* h_out = (j + 1 < d.conv_layers) ? w.L[j + 1].h_in : out;
+    F5B_TRY(dwconv7_ln(L.h_in, d.tb_dw_w + (size_t)j * T * 7, d.tb_dw_b + (size_t)j * T, d.tb_ln_w + (size_t)j * T, d.tb_ln_b + (size_t)j * T,
+                       L.tb, B, n, T, 1e-6f, s, L.y));
+    F5B_TRY(linear_bf16(L.tb, T, reinterpret_cast<const bf*>(d.tb_pw1_w) + (size_t)j * T2 * T, T, d.tb_pw1_b + (size_t)j * T2, L.p1, T2,
+                        (int)rows, T2, T, F5B_ACT_NONE, s));
+    F5B_TRY(f5b_act_fwd(L.p1, L.t2, (int64_t)rows * T2, F5B_ACT_GELU_ERF, stream));
+    F5B_TRY(grn(L.t2, d.tb_grn_g + (size_t)j * T2, d.tb_grn_b + (size_t)j * T2, L.t3, w.gx, B, n, T2, s));
+    F5B_CUDA(cudaMemcpyAsync(h_out, L.h_in, rows * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    F5B_TRY(linear_gate_resid(L.t3, T2, reinterpret_cast<const bf*>(d.tb_pw2_w) + (size_t)j * T * T2, T2, d.tb_pw2_b + (size_t)j * T, h_out,
+                              T, (int)rows, T, T2, n, nullptr, 0, nullptr, 0, s));
+  }
+  return 0;
+}
+
+// ... and its backward: dtext bf16 [B*n, T] (f5b_dit_train_backward) -> gradients of the table and the ConvNeXtV2 blocks
+int f5b_dit_text_embed_backward(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, const void* dtext_bf16,
+                                const F5bDitGrads* gr, void* ws, size_t ws_bytes, f5b_stream_t stream) {
+  F5B_CHECK(h && ids && dtext_bf16 && gr && ws && B > 0 && n > 0 && nt > 0, "f5b_dit_text_embed_backward: bad argument");
+  const F5bDitDesc& d = h->d;
+  F5B_CHECK(d.conv_layers <= 16 && d.text_dim <= 1024, "f5b_dit_text_embed_backward: conv_layers <= 16, text_dim <= 1024");
+  const int T = d.text_dim, T2 = 2 * d.text_dim;
+  const int rows = B * n;
+  TextWs w = carve_text(d, B, n, ws);
+  F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_text_embed_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+  cudaStream_t s = ST(stream);
+  const F5bDitGrads& g = *gr;
+  auto off = [](float* p, size_t o) { return p ? p + o : nullptr; };
+  F5B_CUDA(cudaMemsetAsync(w.dh, 0, sizeof(float) * (size_t)rows * T, s));
+  F5B_TRY(f5b_gate_add(w.dh, dtext_bf16, nullptr, 0, nullptr, w.dh, B, n, T, stream));  // fp32 running gradient
+  for (int j = d.conv_layers - 1; j >= 0; --j) {
+    const TextSave& L = w.L[j];
+    const bf* w1 = reinterpret_cast<const bf*>(d.tb_pw1_w) + (size_t)j * T2 * T;
+    const bf* w2 = reinterpret_cast<const bf*>(d.tb_pw2_w) + (size_t)j * T * T2;
+    F5B_TRY(f5b_gate_bwd(w.dh, nullptr, nullptr, 0, nullptr, w.dz, nullptr, off(g.tb_pw2_b, (size_t)j * T), B, n, T, stream));
+    F5B_TRY(wgrad(w.dz, T, L.t3, T2, off(g.tb_pw2_w, (size_t)j * T * T2), T2, rows, T, T2, stream));
+    F5B_TRY(dgrad(w.dz, T, w2, T2, w.d2, T2, rows, T, stream));
+    F5B_TRY(f5b_grn_gelu_bwd(w.d2, L.t2, L.p1, d.tb_grn_g + (size_t)j * T2, w.d2, off(g.tb_grn_g, (size_t)j * T2),
+                             off(g.tb_grn_b, (size_t)j * T2), off(g.tb_pw1_b, (size_t)j * T2), w.stats, B, n, T2, stream));
+    F5B_TRY(wgrad(w.d2, T2, L.tb, T, off(g.tb_pw1_w, (size_t)j * T2 * T), T, rows, T2, T, stream));
+    F5B_TRY(dgrad(w.d2, T2, w1, T, w.dtb, T, rows, T2, stream));
+    F5B_TRY(f5b_ln_affine_bwd(w.dtb, L.y, d.tb_ln_w + (size_t)j * T, w.dy, 0, off(g.tb_ln_w, (size_t)j * T), off(g.tb_ln_b, (size_t)j * T), B,
+                              n, T, 1e-6f, stream));
+    F5B_TRY(f5b_dwconv7_bwd(w.dy, L.h_in, d.tb_dw_w + (size_t)j * T * 7, w.dh, off(g.tb_dw_w, (size_t)j * T * 7),
+                            off(g.tb_dw_b, (size_t)j * T), B, n, T, stream));
+  }
+  if (g.text_table) F5B_TRY(f5b_text_lookup_bwd(w.dh, ids, nt, g.text_table, B, n, T, drop_text, stream));
   return 0;
 }
 

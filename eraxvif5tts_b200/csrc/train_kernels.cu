@@ -155,7 +155,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                                          const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
                                                          int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
-                                                         int D, float eps) {
+                                                         int D, float eps, int affine) {
   extern __shared__ float ln_acc[];  // [2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     one_sc[j] = make_float4(1.f, 1.f, 1.f, 1.f);
     if (scale != nullptr && idx < nvec) {
       const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) + idx);
-      one_sc[j] = make_float4(1.f + s.x, 1.f + s.y, 1.f + s.z, 1.f + s.w);
+      const float o1 = affine ? 0.f : 1.f;  // affine: `scale` is LayerNorm's weight itself
+      one_sc[j] = make_float4(o1 + s.x, o1 + s.y, o1 + s.z, o1 + s.w);
     }
   }
   const int p0 = blockIdx.x * 64 + warp * 8;
@@ -260,6 +261,168 @@ __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __r
   out[i] = __float2bfloat16(v);
 }
 
+// ---- GRN backward (model/modules.py:225-234) fused with the GELU(erf) backward in front of it (ConvNeXtV2Block :263-265) ----
+// t3 = gamma * t2 * nx + beta + t2,  nx[b,c] = gx[b,c] / (mean_c gx[b,:] + 1e-6),  gx[b,c] = ||t2[b,:,c]||_2,  t2 = gelu(p1)
+// stats[b][0..2][C]: pass 1 writes (sum t2^2, sum dt3*t2, sum dt3); the per-batch-row kernel turns them into (mult, coef):
+//   dt2 = dt3 * mult + t2 * coef,  mult = gamma*nx + 1,  coef = (gamma*S/(m+eps) - A) / gx,  A = mean_c(gamma*S*gx) / (m+eps)^2
+__global__ void __launch_bounds__(256) grn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ d3, const __nv_bfloat16* __restrict__ t2,
+                                                            float* __restrict__ stats, int n, int C) {
+  __shared__ float red[3][4][128];
+  const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 128 + cp * 2;
+  const int b = blockIdx.y;
+  float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f, r0 = 0.f, r1 = 0.f;
+  if (c < C) {
+    const size_t base = (size_t)b * n * C + c;
+    for (int r = rl; r < n; r += 4) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(t2 + base + (size_t)r * C));
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d3 + base + (size_t)r * C));
+      q0 = fmaf(t.x, t.x, q0); q1 = fmaf(t.y, t.y, q1);
+      s0 = fmaf(d.x, t.x, s0); s1 = fmaf(d.y, t.y, s1);
+      r0 += d.x; r1 += d.y;
+    }
+  }
+  red[0][rl][cp * 2] = q0; red[0][rl][cp * 2 + 1] = q1;
+  red[1][rl][cp * 2] = s0; red[1][rl][cp * 2 + 1] = s1;
+  red[2][rl][cp * 2] = r0; red[2][rl][cp * 2 + 1] = r1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < C)
+      for (int k = 0; k < 3; ++k)
+        stats[((size_t)b * 3 + k) * C + cc] = red[k][0][threadIdx.x] + red[k][1][threadIdx.x] + red[k][2][threadIdx.x] + red[k][3][threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(256) grn_bwd_mid_kernel(float* __restrict__ stats, const float* __restrict__ gamma,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  __shared__ float red[2][8];
+  __shared__ float sh[2];
+  const int b = blockIdx.x;
+  float* Q = stats + (size_t)b * 3 * C;
+  float* S = Q + C;
+  float* R = S + C;
+  float sg = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) sg += sqrtf(Q[c]);
+  sg = warp_sum(sg);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = sg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[0][i];
+    sh[0] = 1.f / (t / (float)C + 1e-6f);
+  }
+  __syncthreads();
+  const float inv = sh[0];
+  float sa = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) sa += gamma[c] * S[c] * sqrtf(Q[c]);
+  sa = warp_sum(sa);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = sa;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[1][i];
+    sh[1] = t / (float)C * inv * inv;
+  }
+  __syncthreads();
+  const float A = sh[1];
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float gx = sqrtf(Q[c]);
+    const float nx = gx * inv;
+    if (dgamma) atomicAdd(dgamma + c, S[c] * nx);
+    if (dbeta) atomicAdd(dbeta + c, R[c]);
+    const float coef = gx > 0.f ? (gamma[c] * S[c] * inv - A) / gx : 0.f;
+    Q[c] = gamma[c] * nx + 1.f;  // mult
+    S[c] = coef;
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) grn_bwd_apply_kernel(const __nv_bfloat16* d3, const __nv_bfloat16* __restrict__ t2,
+                                                                   const __nv_bfloat16* __restrict__ p1, const float* __restrict__ stats,
+                                                                   __nv_bfloat16* dp1 /* may alias d3 */, float* __restrict__ dbias, int n,
+                                                                   int C) {
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * CT_ROWS, r1 = min(n, r0 + CT_ROWS);
+  const float* mult = stats + (size_t)b * 3 * C;
+  const float* coef = mult + C;
+  for (int c = threadIdx.x * 2; c < C; c += 2 * CT_THREADS) {
+    const float m0 = mult[c], m1 = mult[c + 1], k0 = coef[c], k1 = coef[c + 1];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      const size_t off = ((size_t)b * n + r) * C + c;
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d3 + off));
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(t2 + off));
+      const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p1 + off));
+      const float g0 = (d.x * m0 + t.x * k0) * act_grad(F5B_ACT_GELU_ERF, p.x);
+      const float g1 = (d.y * m1 + t.y * k1) * act_grad(F5B_ACT_GELU_ERF, p.y);
+      const uint32_t pk = pack_bf16(g0, g1);
+      *reinterpret_cast<uint32_t*>(dp1 + off) = pk;
+      const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+      s0 += rr.x;
+      s1 += rr.y;
+    }
+    if (dbias) {
+      atomicAdd(dbias + c, s0);
+      atomicAdd(dbias + c + 1, s1);
+    }
+  }
+}
+
+// depth-wise Conv1d(k=7, pad 3) backward: dx[b,p,c] += sum_k w[c,k] dy[b,p-k+3,c];  dw[c,k] += sum dy[b,p,c] x[b,p+k-3,c];  db[c] += sum dy
+__global__ void __launch_bounds__(256) dwconv7_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                                                          float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int n, int C) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * CT_ROWS, p1 = min(n, p0 + CT_ROWS);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float wk[7], aw[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { wk[k] = __ldg(w + (size_t)c * 7 + k); aw[k] = 0.f; }
+    float ab = 0.f;
+    const size_t base = (size_t)b * n * C + c;
+    for (int p = p0; p < p1; ++p) {
+      const float g = dy[base + (size_t)p * C];
+      ab += g;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int q = p + k - 3;   // x position paired with dy[p] under tap k
+        if (q >= 0 && q < n) aw[k] = fmaf(g, x[base + (size_t)q * C], aw[k]);
+        const int r = p - k + 3;   // dy position that reaches x[p] through tap k
+        if (r >= 0 && r < n) acc = fmaf(wk[k], dy[base + (size_t)r * C], acc);
+      }
+      dx[base + (size_t)p * C] += acc;
+    }
+    if (dw)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) atomicAdd(dw + (size_t)c * 7 + k, aw[k]);
+    if (db) atomicAdd(db + c, ab);
+  }
+}
+
+// nn.Embedding backward of TextEmbedding (model/backbones/dit.py:49-60): dtable[token(row)] += dh[row]; consecutive rows that hit
+// the same token (the filler tail of every utterance) are summed in registers before the atomic
+__global__ void __launch_bounds__(256) text_lookup_bwd_kernel(const float* __restrict__ dh, const int64_t* __restrict__ ids, int nt,
+                                                              float* __restrict__ dtable, int n, int C, int drop_text) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * CT_ROWS, p1 = min(n, p0 + CT_ROWS);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    long long cur = -1;
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      long long tok = 0;
+      if (p < nt && !drop_text) tok = ids[(size_t)b * nt + p] + 1;
+      if (tok != cur) {
+        if (cur >= 0) atomicAdd(dtable + (size_t)cur * C + c, acc);
+        cur = tok;
+        acc = 0.f;
+      }
+      acc += dh[((size_t)b * n + p) * C + c];
+    }
+    if (cur >= 0) atomicAdd(dtable + (size_t)cur * C + c, acc);
+  }
+}
+
 }  // namespace f5b
 
 using namespace f5b;
@@ -308,8 +471,8 @@ int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* d
   return 0;
 }
 
-int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,
-                        float* dscale, float* dshift, int B, int n, int D, float eps, f5b_stream_t stream) {
+static int ln_bwd_launch(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,
+                         float* dscale, float* dshift, int B, int n, int D, float eps, int affine, f5b_stream_t stream) {
   F5B_CHECK(dy_bf16 && x && dx && B > 0 && n > 0, "f5b_ln_modulate_bwd: bad argument");
   F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_modulate_bwd: D=%d must be a multiple of 4 and <= 1024", D);
   LaunchScope scope(K_NORM, ST(stream), 0, (accumulate ? 14.0 : 10.0) * B * n * D);
@@ -317,9 +480,55 @@ int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale,
   const size_t sm = 2 * (size_t)D * sizeof(float);
   auto* d = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const int nvec = D / 4;
-  if (nvec <= 64) ln_mod_bwd_kernel<2><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
-  else if (nvec <= 128) ln_mod_bwd_kernel<4><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
-  else ln_mod_bwd_kernel<8><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps);
+  if (nvec <= 64) ln_mod_bwd_kernel<2><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
+  else if (nvec <= 128) ln_mod_bwd_kernel<4><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
+  else ln_mod_bwd_kernel<8><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,
+                        float* dscale, float* dshift, int B, int n, int D, float eps, f5b_stream_t stream) {
+  return ln_bwd_launch(dy_bf16, x, scale, mod_bstride, dx, accumulate, dscale, dshift, B, n, D, eps, 0, stream);
+}
+/* backward of LayerNorm(D, affine): dx = LN-backward(dy * w), dw += sum dy * xhat, db += sum dy */
+int f5b_ln_affine_bwd(const void* dy_bf16, const float* x, const float* w, float* dx, int accumulate, float* dw, float* db, int B,
+                      int n, int D, float eps, f5b_stream_t stream) {
+  F5B_CHECK(w != nullptr, "f5b_ln_affine_bwd: null weight");
+  return ln_bwd_launch(dy_bf16, x, w, 0, dx, accumulate, dw, db, B, n, D, eps, 1, stream);
+}
+
+int f5b_grn_gelu_bwd(const void* dt3_bf16, const void* t2_bf16, const void* p1_bf16, const float* gamma, void* dp1_bf16, float* dgamma,
+                     float* dbeta, float* dbias1, float* stats_ws, int B, int n, int C, f5b_stream_t stream) {
+  F5B_CHECK(dt3_bf16 && t2_bf16 && p1_bf16 && gamma && dp1_bf16 && stats_ws && B > 0 && n > 0 && C > 0 && (C & 1) == 0,
+            "f5b_grn_gelu_bwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * B * n * C, 3);
+  auto* d3 = reinterpret_cast<const __nv_bfloat16*>(dt3_bf16);
+  auto* t2 = reinterpret_cast<const __nv_bfloat16*>(t2_bf16);
+  grn_bwd_stats_kernel<<<dim3((C + 127) / 128, B), 256, 0, ST(stream)>>>(d3, t2, stats_ws, n, C);
+  F5B_CUDA(cudaGetLastError());
+  grn_bwd_mid_kernel<<<B, 256, 0, ST(stream)>>>(stats_ws, gamma, dgamma, dbeta, C);
+  F5B_CUDA(cudaGetLastError());
+  grn_bwd_apply_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), CT_THREADS, 0, ST(stream)>>>(
+      d3, t2, reinterpret_cast<const __nv_bfloat16*>(p1_bf16), stats_ws, reinterpret_cast<__nv_bfloat16*>(dp1_bf16), dbias1, n, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_dwconv7_bwd(const float* dy, const float* x, const float* w, float* dx_accum, float* dw, float* db, int B, int n, int C,
+                    f5b_stream_t stream) {
+  F5B_CHECK(dy && x && w && dx_accum && B > 0 && n > 0 && C > 0, "f5b_dwconv7_bwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 16.0 * B * n * C);
+  dwconv7_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), 256, 0, ST(stream)>>>(dy, x, w, dx_accum, dw, db, n, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int drop_text,
+                        f5b_stream_t stream) {
+  F5B_CHECK(dh && ids && dtable && B > 0 && n > 0 && C > 0 && nt > 0, "f5b_text_lookup_bwd: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * B * n * C);
+  text_lookup_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), 256, 0, ST(stream)>>>(dh, ids, nt, dtable, n, C, drop_text);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

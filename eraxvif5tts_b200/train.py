@@ -141,10 +141,6 @@ class TrainEngine:
         d.cp_w1, d.cp_w2 = self.cp["w1"].data_ptr(), self.cp["w2"].data_ptr()
         gr.in_wx, gr.in_wct = self.g_in_wx.data_ptr(), self.g_in_wct.data_ptr()
         gr.cp_w1, gr.cp_w2 = self.g[self.offsets["_cp_w1"]:].data_ptr(), self.g[self.offsets["_cp_w2"]:].data_ptr()
-        # TextEmbedding parameters: backward not built yet -> their gradient stays zero
-        for k in ("text_table", "tb_dw_w", "tb_dw_b", "tb_ln_w", "tb_ln_b", "tb_pw1_w", "tb_pw1_b", "tb_grn_g", "tb_grn_b", "tb_pw2_w",
-                  "tb_pw2_b"):
-            setattr(gr, k, None)
         self.desc, self.grads = d, gr
         h = L.vp()
         L.check(self.lib.f5b_dit_create(C.byref(d), C.byref(h)), "f5b_dit_create")
@@ -245,9 +241,9 @@ class TrainEngine:
         L.check(lib.f5b_fm_prepare(x1.data_ptr(), x0.data_ptr(), time.data_ptr(), span_u8.data_ptr(), phi.data_ptr(), flow.data_ptr(),
                                    cond.data_ptr(), B, n, C_, s), "f5b_fm_prepare")
         te = torch.empty(B * n, self.T, dtype=f32, device=dev)
-        tws = torch.empty(lib.f5b_dit_text_ws_bytes(self.handle, B, n), dtype=torch.uint8, device=dev)
-        L.check(lib.f5b_dit_text_embed(self.handle, text.data_ptr(), text.shape[1], B, n, int(drop_text), te.data_ptr(), tws.data_ptr(), s),
-                "f5b_dit_text_embed")
+        tws = torch.empty(lib.f5b_dit_text_train_ws_bytes(self.handle, B, n), dtype=torch.uint8, device=dev)
+        L.check(lib.f5b_dit_text_embed_train(self.handle, text.data_ptr(), text.shape[1], B, n, int(drop_text), te.data_ptr(),
+                                             tws.data_ptr(), tws.numel(), s), "f5b_dit_text_embed_train")
         nbytes = lib.f5b_dit_train_ws_bytes(self.handle, B, n)
         ws = self.workspace(nbytes)
         rope = self.rope_table(n)
@@ -263,10 +259,12 @@ class TrainEngine:
         dpred = torch.empty(B * n, 128, dtype=bf16, device=dev)
         L.check(lib.f5b_mse_grad(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), out2.data_ptr(), dpred.data_ptr(), B * n, C_, 128, s),
                 "f5b_mse_grad")
-        self.dtext = torch.empty(B * n, self.T, dtype=bf16, device=dev)
+        dtext = torch.empty(B * n, self.T, dtype=bf16, device=dev)
         L.check(lib.f5b_dit_train_backward(self.handle, dpred.data_ptr(), self.cp["w1_t"].data_ptr(), self.cp["w2_t"].data_ptr(),
-                                           C.byref(self.grads), self.dtext.data_ptr(), B, n, None, rope.data_ptr(), ws.data_ptr(),
+                                           C.byref(self.grads), dtext.data_ptr(), B, n, None, rope.data_ptr(), ws.data_ptr(),
                                            ws.numel(), s), "f5b_dit_train_backward")
+        L.check(lib.f5b_dit_text_embed_backward(self.handle, text.data_ptr(), text.shape[1], B, n, int(drop_text), dtext.data_ptr(),
+                                                C.byref(self.grads), tws.data_ptr(), tws.numel(), s), "f5b_dit_text_embed_backward")
         return out2[0], cond, pred
 
     def _fold_split_grads(self):

@@ -271,6 +271,25 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
                            void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
                            f5b_stream_t stream);
 
+/* TextEmbedding.forward in training form (every ConvNeXtV2Block input kept in ws) and its backward: dtext_bf16 [B*n, T] is the
+ * gradient f5b_dit_train_backward returns; fills g->text_table and g->tb_*.  text_mask_padding is not supported here. */
+size_t f5b_dit_text_train_ws_bytes(const F5bDit* h, int B, int n);
+int f5b_dit_text_embed_train(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, float* out, void* ws,
+                             size_t ws_bytes, f5b_stream_t stream);
+int f5b_dit_text_embed_backward(const F5bDit* h, const int64_t* ids, int nt, int B, int n, int drop_text, const void* dtext_bf16,
+                                const F5bDitGrads* g, void* ws, size_t ws_bytes, f5b_stream_t stream);
+/* building blocks of the above */
+int f5b_ln_affine_bwd(const void* dy_bf16, const float* x, const float* w, float* dx, int accumulate, float* dw, float* db, int B,
+                      int n, int D, float eps, f5b_stream_t stream);
+/* GRN (model/modules.py:225-234) + the GELU(erf) in front of it, backward: dp1 = d(t3)/d(p1) applied to dt3 (may alias), with
+ * dgamma / dbeta / dbias1 accumulated; stats_ws f32 [B, 3, C] */
+int f5b_grn_gelu_bwd(const void* dt3_bf16, const void* t2_bf16, const void* p1_bf16, const float* gamma, void* dp1_bf16, float* dgamma,
+                     float* dbeta, float* dbias1, float* stats_ws, int B, int n, int C, f5b_stream_t stream);
+int f5b_dwconv7_bwd(const float* dy, const float* x, const float* w, float* dx_accum, float* dw, float* db, int B, int n, int C,
+                    f5b_stream_t stream);
+int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int drop_text,
+                        f5b_stream_t stream);
+
 /* rope table for n positions, dim_head 64: f32 [n, 32, 2] = (cos, sin)(pos * 10000^(-2j/64))
  * (x_transformers RotaryEmbedding.forward_from_seq_len, call site dit.py:215) */
 int f5b_rope_table(float* out, int n, f5b_stream_t stream);

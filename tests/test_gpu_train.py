@@ -72,7 +72,7 @@ def test_backward_vs_oracle_autograd(da, dt):
     torch.cuda.synchronize()
     assert maxabs(pred, ref_pred) <= 2e-2
     assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
-    worst = _compare(model, ref, skip_prefix=TEXT_PARAMS)
+    worst = _compare(model, ref)
     print("worst gradients (fro err, cos, key):", worst[:5])
 
 
