@@ -123,10 +123,14 @@ extern "C" int f5b_gemm_tn(const void* A, int lda, int a_mn_major, const void* B
   F5B_CHECK(out_f32_accumulate ? (ldc & 3) == 0 : (ldc & 7) == 0, "f5b_gemm_tn: bad output pitch %d", ldc);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   LaunchScope scope(K_GEMM, s, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (out_f32_accumulate ? 8.0 : 2.0) * M * N);
-#define F5B_GRAD_CASE(AM, BMj)                                                                                          \
-  if ((a_mn_major != 0) == AM && (b_mn_major != 0) == BMj)                                                               \
-    return out_f32_accumulate ? launch_grad<128, AM, BMj, STORE_F32ADD>(A, lda, B, ldb, out, ldc, M, N, K, splits, s)  \
-                              : launch_grad<128, AM, BMj, STORE_BF16>(A, lda, B, ldb, out, ldc, M, N, K, splits, s);
+#define F5B_GRAD_CASE(AM, BMj)                                                                                            \
+  if ((a_mn_major != 0) == AM && (b_mn_major != 0) == BMj) {                                                               \
+    if (N >= 256)  /* wide tiles: half the operand traffic per flop */                                                     \
+      return out_f32_accumulate ? launch_grad<256, AM, BMj, STORE_F32ADD>(A, lda, B, ldb, out, ldc, M, N, K, splits, s)  \
+                                : launch_grad<256, AM, BMj, STORE_BF16>(A, lda, B, ldb, out, ldc, M, N, K, splits, s);   \
+    return out_f32_accumulate ? launch_grad<128, AM, BMj, STORE_F32ADD>(A, lda, B, ldb, out, ldc, M, N, K, splits, s)    \
+                              : launch_grad<128, AM, BMj, STORE_BF16>(A, lda, B, ldb, out, ldc, M, N, K, splits, s);     \
+  }
   F5B_GRAD_CASE(false, false)
   F5B_GRAD_CASE(false, true)
   F5B_GRAD_CASE(true, false)

@@ -47,6 +47,7 @@ struct TrainWs {
   // backward scratch
   float *dx, *delta, *dq_ws;
   bf *t1, *t2, *t3, *tF, *xcol, *dact;
+  float* cpw_tmp;
   size_t bytes;
 };
 
@@ -101,21 +102,32 @@ static TrainWs carve_train(const F5bDitDesc& d, int B, int n, void* ws) {
   w.tF = c.take<bf>(rows * F);
   w.xcol = c.take<bf>(rows * (size_t)(D / d.convpos_groups) * d.convpos_kernel);
   w.dact = c.take<bf>(rows * (128 + T));
+  w.cpw_tmp = c.take<float>((size_t)D * (D / d.convpos_groups) * d.convpos_kernel);
   w.bytes = c.off;
   return w;
 }
 
-// Xcol[r, ci*ks + k] = x[b, t + k - pad, g*cpg + ci]  (zero outside the utterance): the conv weight gradient of group g is then the
-// plain product dY_g^T Xcol, landing directly in nn.Conv1d's [co][ci][k] order
+// Xcol[r, k*cpg + ci] = x[b, t + k - pad, g*cpg + ci]  (zero outside the utterance; 16-byte chunks): the conv weight gradient of group
+// g is then the plain product dY_g^T Xcol in [co][k][ci] order; conv_wgrad_fold_kernel adds it into nn.Conv1d's [co][ci][k] layout
 __global__ void im2col_convpos_kernel(const bf* __restrict__ x, bf* __restrict__ out, int n, int D, int g, int cpg, int ks) {
   const size_t row = blockIdx.x;
   const int b = (int)(row / n), t = (int)(row - (size_t)b * n);
-  const int cols = cpg * ks, pad = ks / 2;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
-    const int ci = j / ks, k = j - ci * ks;
+  const int c8n = cpg >> 3, pad = ks / 2;
+  for (int j = threadIdx.x; j < ks * c8n; j += blockDim.x) {
+    const int k = j / c8n, c8 = j - k * c8n;
     const int p = t + k - pad;
-    out[row * cols + j] = (p >= 0 && p < n) ? x[((size_t)b * n + p) * D + g * cpg + ci] : __float2bfloat16(0.f);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p >= 0 && p < n) v = *reinterpret_cast<const uint4*>(x + ((size_t)b * n + p) * D + g * cpg + c8 * 8);
+    *reinterpret_cast<uint4*>(out + row * (size_t)(cpg * ks) + k * cpg + c8 * 8) = v;
   }
+}
+__global__ void conv_wgrad_fold_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int D, int cpg, int ks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index into dw [D][cpg][ks]
+  if (i >= D * cpg * ks) return;
+  const int k = i % ks;
+  const int t = i / ks;
+  const int ci = t % cpg, co = t / cpg;
+  dw[i] += tmp[((size_t)co * ks + k) * cpg + ci];
 }
 
 struct TextSave {
@@ -154,7 +166,8 @@ static TextWs carve_text(const F5bDitDesc& d, int B, int n, void* ws) {
 }
 
 static int pick_splits(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int bn = N >= 256 ? 256 : 128;  // f5b_gemm_tn's tile width
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   const int kblocks = (K + 63) / 64;
   int s = (4 * sm_count() + tiles - 1) / tiles;
   if (s > kblocks) s = kblocks;
@@ -313,22 +326,30 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
 
   // ---- InputEmbedding: x0 = h0 + mish(conv2(mish(conv1(h0)))),  h0 = [x | cond | text] W^T + b
   const int G = d.convpos_groups, cpg = D / G, ks = d.convpos_kernel, ccols = cpg * ks;
+  F5B_CHECK((cpg & 7) == 0, "f5b_dit_train_backward: channels per conv group must be a multiple of 8");
+  // grouped-conv weight gradient: per group, im2col of the layer input (k-major) and one split-K wgrad GEMM into a [co][k][ci] buffer
+  auto conv_wgrad = [&](const bf* dy, const bf* xin, float* dw) -> int {
+    if (dw == nullptr) return 0;
+    F5B_CUDA(cudaMemsetAsync(w.cpw_tmp, 0, sizeof(float) * (size_t)D * ccols, s));
+    for (int gi = 0; gi < G; ++gi) {
+      {
+        LaunchScope scope(K_ELEMENTWISE, s, 0, 4.0 * rows * ccols);
+        im2col_convpos_kernel<<<rows, 256, 0, s>>>(xin, w.xcol, n, D, gi, cpg, ks);
+        F5B_CUDA(cudaGetLastError());
+      }
+      F5B_TRY(wgrad(dy + gi * cpg, D, w.xcol, ccols, w.cpw_tmp + (size_t)gi * cpg * ccols, ccols, rows, cpg, ccols, stream));
+    }
+    LaunchScope scope(K_ELEMENTWISE, s, 0, 12.0 * D * ccols);
+    conv_wgrad_fold_kernel<<<(D * ccols + 255) / 256, 256, 0, s>>>(w.cpw_tmp, dw, D, cpg, ks);
+    F5B_CUDA(cudaGetLastError());
+    return 0;
+  };
   F5B_TRY(f5b_gate_bwd(w.dx, nullptr, nullptr, 0, nullptr, w.t1, nullptr, nullptr, B, n, D, stream));       // bf16(dx)
   F5B_TRY(f5b_act_bwd(w.t1, w.u2, w.t2, g.cp_b2, rows, D, D, F5B_ACT_MISH, stream));                         // d u2
-  if (g.cp_w2)
-    for (int gi = 0; gi < G; ++gi) {
-      im2col_convpos_kernel<<<rows, 256, 0, s>>>(w.c1, w.xcol, n, D, gi, cpg, ks);
-      F5B_CUDA(cudaGetLastError());
-      F5B_TRY(wgrad(w.t2 + gi * cpg, D, w.xcol, ccols, g.cp_w2 + (size_t)gi * cpg * ccols, ccols, rows, cpg, ccols, stream));
-    }
+  F5B_TRY(conv_wgrad(w.t2, w.c1, g.cp_w2));
   F5B_TRY(convpos(w.t2, cp_w2_t, nullptr, w.t1, nullptr, B, n, D, G, ks, 2, s));                             // d c1
   F5B_TRY(f5b_act_bwd(w.t1, w.u1, w.t2, g.cp_b1, rows, D, D, F5B_ACT_MISH, stream));                         // d u1
-  if (g.cp_w1)
-    for (int gi = 0; gi < G; ++gi) {
-      im2col_convpos_kernel<<<rows, 256, 0, s>>>(w.hb0, w.xcol, n, D, gi, cpg, ks);
-      F5B_CUDA(cudaGetLastError());
-      F5B_TRY(wgrad(w.t2 + gi * cpg, D, w.xcol, ccols, g.cp_w1 + (size_t)gi * cpg * ccols, ccols, rows, cpg, ccols, stream));
-    }
+  F5B_TRY(conv_wgrad(w.t2, w.hb0, g.cp_w1));
   F5B_TRY(convpos(w.t2, cp_w1_t, nullptr, w.t1, nullptr, B, n, D, G, ks, 2, s));                             // conv path of d h0
   F5B_TRY(f5b_gate_add(w.dx, w.t1, nullptr, 0, nullptr, w.dx, B, n, D, stream));                             // d h0 = dx + conv path
   F5B_TRY(f5b_gate_bwd(w.dx, nullptr, nullptr, 0, nullptr, w.t1, nullptr, g.in_b, B, n, D, stream));         // bf16(d h0), d bias

@@ -29,7 +29,7 @@ __device__ __forceinline__ float act_grad(int act, float x) {
   if (act == F5B_ACT_GELU_TANH) {
     const float k = 0.7978845608028654f;
     const float u = k * x * fmaf(0.044715f * x, x, 1.0f);
-    const float t = tanhf(u);
+    const float t = tanh_approx(u);
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * fmaf(3.0f * 0.044715f * x, x, 1.0f);
   } else if (act == F5B_ACT_GELU_ERF) {
     return 0.5f * (1.0f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -117,63 +117,68 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat1
 }
 
 // dh[r, :] = bf16(du[r, :] * act'(h[r, :]));  dbias[:] += sum_r dh[r, :]      (act NONE + dh NULL = plain column sum of du)
+// thread = 4 adjacent columns (8-byte accesses), 64 rows per CTA
 __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16* du, const __nv_bfloat16* __restrict__ h,
                                                              __nv_bfloat16* dh /* may alias du */, float* __restrict__ dbias, int64_t rows,
                                                              int C, int ld, int act) {
   const int64_t r0 = (int64_t)blockIdx.x * CT_ROWS;
   const int64_t r1 = min(rows, r0 + CT_ROWS);
-  for (int c = threadIdx.x * 2; c < C; c += 2 * CT_THREADS) {
-    float s0 = 0.f, s1 = 0.f;
+  for (int c = threadIdx.x * 4; c < C; c += 4 * CT_THREADS) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int64_t r = r0; r < r1; ++r) {
       const size_t off = (size_t)r * ld + c;
-      float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(du + off));
+      const uint2 dv = *reinterpret_cast<const uint2*>(du + off);
+      const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv.x));
+      const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv.y));
+      float d[4] = {d01.x, d01.y, d23.x, d23.y};
       if (h != nullptr) {
-        const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + off));
-        d.x *= act_grad(act, hv.x);
-        d.y *= act_grad(act, hv.y);
+        const uint2 hv = *reinterpret_cast<const uint2*>(h + off);
+        const float2 h01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hv.x));
+        const float2 h23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hv.y));
+        d[0] *= act_grad(act, h01.x); d[1] *= act_grad(act, h01.y); d[2] *= act_grad(act, h23.x); d[3] *= act_grad(act, h23.y);
       }
       if (dh != nullptr) {
-        const uint32_t pk = pack_bf16(d.x, d.y);
-        *reinterpret_cast<uint32_t*>(dh + off) = pk;
-        d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));  // the bias sees what the GEMMs see
+        uint2 pk;
+        pk.x = pack_bf16(d[0], d[1]);
+        pk.y = pack_bf16(d[2], d[3]);
+        *reinterpret_cast<uint2*>(dh + off) = pk;
+        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));  // the bias sees what the GEMMs see
+        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        d[0] = r01.x; d[1] = r01.y; d[2] = r23.x; d[3] = r23.y;
       }
-      s0 += d.x;
-      s1 += d.y;
+      s[0] += d[0]; s[1] += d[1]; s[2] += d[2]; s[3] += d[3];
     }
     if (dbias) {
-      atomicAdd(dbias + c, s0);
-      atomicAdd(dbias + c + 1, s1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dbias + c + i, s[i]);
     }
   }
 }
 
 // Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine; AdaLayerNorm model/modules.py:310-315):
 //   dshift[b] += sum_r dy;  dscale[b] += sum_r dy * xhat;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b])
-// One warp per row (row and statistics recomputed from the saved fp32 x), 8 rows per warp, column sums staged in shared memory.
+// One warp per row (row and statistics recomputed from the saved fp32 x), 8 rows per warp.  The two column sums live in a
+// per-warp shared-memory slice (plain load-add-store, no atomics, no 64-register accumulator -> 3 CTAs / SM); the 8 slices are
+// folded at the end and leave as one fp32 atomic per column per CTA.
 template <int VEC>
 __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                                          const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
                                                          int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
                                                          int D, float eps, int affine) {
-  extern __shared__ float ln_acc[];  // [2][D]
+  extern __shared__ float4 ln_acc4[];  // [8 warps][2][D/4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int nvec = D >> 2;
-  for (int i = threadIdx.x; i < 2 * D; i += 256) ln_acc[i] = 0.f;
-  __syncthreads();
-  float4 a_sc[VEC], a_sh[VEC], one_sc[VEC];
+  float4* my_sc = ln_acc4 + (size_t)warp * 2 * nvec;
+  float4* my_sh = my_sc + nvec;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    a_sc[j] = a_sh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int idx = lane + j * 32;
-    one_sc[j] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (scale != nullptr && idx < nvec) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) + idx);
-      const float o1 = affine ? 0.f : 1.f;  // affine: `scale` is LayerNorm's weight itself
-      one_sc[j] = make_float4(o1 + s.x, o1 + s.y, o1 + s.z, o1 + s.w);
-    }
+    if (idx < nvec) my_sc[idx] = my_sh[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const float4* scv = scale ? reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) : nullptr;
+  const float o1 = affine ? 0.f : 1.f;  // affine: `scale` is LayerNorm's weight itself
   const int p0 = blockIdx.x * 64 + warp * 8;
   for (int pos = p0; pos < min(n, p0 + 8); ++pos) {
     const size_t row = (size_t)b * n + pos;
@@ -202,16 +207,26 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j)
-      if (lane + j * 32 < nvec) {
+    for (int j = 0; j < VEC; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
         v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;  // xhat
-        a_sh[j].x += g[j].x; a_sh[j].y += g[j].y; a_sh[j].z += g[j].z; a_sh[j].w += g[j].w;
-        a_sc[j].x = fmaf(g[j].x, v[j].x, a_sc[j].x); a_sc[j].y = fmaf(g[j].y, v[j].y, a_sc[j].y);
-        a_sc[j].z = fmaf(g[j].z, v[j].z, a_sc[j].z); a_sc[j].w = fmaf(g[j].w, v[j].w, a_sc[j].w);
-        g[j].x *= one_sc[j].x; g[j].y *= one_sc[j].y; g[j].z *= one_sc[j].z; g[j].w *= one_sc[j].w;
+        float4 a = my_sh[idx];
+        a.x += g[j].x; a.y += g[j].y; a.z += g[j].z; a.w += g[j].w;
+        my_sh[idx] = a;
+        a = my_sc[idx];
+        a.x = fmaf(g[j].x, v[j].x, a.x); a.y = fmaf(g[j].y, v[j].y, a.y); a.z = fmaf(g[j].z, v[j].z, a.z); a.w = fmaf(g[j].w, v[j].w, a.w);
+        my_sc[idx] = a;
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (scv != nullptr) {
+          const float4 sc = __ldg(scv + idx);
+          m = make_float4(o1 + sc.x, o1 + sc.y, o1 + sc.z, o1 + sc.w);
+        }
+        g[j].x *= m.x; g[j].y *= m.y; g[j].z *= m.z; g[j].w *= m.w;
         s1 += g[j].x + g[j].y + g[j].z + g[j].w;
         s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
       }
+    }
     s1 = warp_sum(s1) / (float)D;
     s2 = warp_sum(s2) / (float)D;
     float4* o = reinterpret_cast<float4*>(dx + row * D);
@@ -232,20 +247,17 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const int idx = lane + j * 32;
-    if (idx < nvec) {
-      float* sc = ln_acc + idx * 4;
-      float* sh = ln_acc + D + idx * 4;
-      atomicAdd(sc, a_sc[j].x); atomicAdd(sc + 1, a_sc[j].y); atomicAdd(sc + 2, a_sc[j].z); atomicAdd(sc + 3, a_sc[j].w);
-      atomicAdd(sh, a_sh[j].x); atomicAdd(sh + 1, a_sh[j].y); atomicAdd(sh + 2, a_sh[j].z); atomicAdd(sh + 3, a_sh[j].w);
-    }
-  }
   __syncthreads();
+  const float* acc = reinterpret_cast<const float*>(ln_acc4);
   for (int i = threadIdx.x; i < D; i += 256) {
-    if (dscale) atomicAdd(dscale + (size_t)b * mod_bstride + i, ln_acc[i]);
-    if (dshift) atomicAdd(dshift + (size_t)b * mod_bstride + i, ln_acc[D + i]);
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+      a += acc[(size_t)w8 * 2 * D + i];
+      c += acc[(size_t)w8 * 2 * D + D + i];
+    }
+    if (dscale) atomicAdd(dscale + (size_t)b * mod_bstride + i, a);
+    if (dshift) atomicAdd(dshift + (size_t)b * mod_bstride + i, c);
   }
 }
 
@@ -462,7 +474,7 @@ int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_
 
 int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
                 f5b_stream_t stream) {
-  F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 1) == 0 && (ld & 1) == 0 && ld >= C, "f5b_act_bwd: bad argument");
+  F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 3) == 0 && (ld & 3) == 0 && ld >= C, "f5b_act_bwd: C and ld must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * rows * C);
   act_bwd_kernel<<<(unsigned)((rows + CT_ROWS - 1) / CT_ROWS), CT_THREADS, 0, ST(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<__nv_bfloat16*>(dh_bf16),
@@ -477,7 +489,14 @@ static int ln_bwd_launch(const void* dy_bf16, const float* x, const float* scale
   F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_modulate_bwd: D=%d must be a multiple of 4 and <= 1024", D);
   LaunchScope scope(K_NORM, ST(stream), 0, (accumulate ? 14.0 : 10.0) * B * n * D);
   const dim3 grid((n + 63) / 64, B);
-  const size_t sm = 2 * (size_t)D * sizeof(float);
+  const size_t sm = 16 * (size_t)D * sizeof(float);  // 8 per-warp slices of (dscale, dshift)
+  static bool configured = false;
+  if (!configured) {
+    F5B_CUDA(cudaFuncSetAttribute(ln_mod_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
+    F5B_CUDA(cudaFuncSetAttribute(ln_mod_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
+    F5B_CUDA(cudaFuncSetAttribute(ln_mod_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
+    configured = true;
+  }
   auto* d = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const int nvec = D / 4;
   if (nvec <= 64) ln_mod_bwd_kernel<2><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
