@@ -28,7 +28,8 @@ constexpr int AB_T = 128;                       // query tile == key tile
 constexpr int AB_THREADS = 320;
 constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
-constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
+constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
+constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
 constexpr uint32_t AB_TMEM_COLS = 512;
 
 struct AttnBwdParams {
@@ -50,7 +51,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const __grid_constant__ CUtensorMap tmdQ, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -60,7 +62,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sdO = sQ + 2 * AB_TILE;   // 2 stages
   uint8_t* sPT = sdO + 2 * AB_TILE;
   uint8_t* sdST = sPT + AB_PT;
-  float* sL = reinterpret_cast<float*>(sdST + AB_PT);  // [2][128]
+  uint8_t* sStg = sdST + AB_PT;                         // [8][4096]
+  float* sL = reinterpret_cast<float*>(sStg + AB_STG);  // [2][128]
   float* sDl = sL + 2 * AB_T;                          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * AB_T);
   uint64_t* bar_kv = bars + 0;
@@ -70,7 +73,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_pds = bars + 6;   // P^T_j, dS^T_j in smem; S / dP / dQ TMEM drained (256 arrivals)
   uint64_t* bar_dq = bars + 7;    // dV, dK, dQ_j products retired
   uint64_t* bar_free = bars + 8;  // [2] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_sfree = bars + 10;  // S^T_j / dP^T_j pulled into registers by all 256 threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +117,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar_dq, 1);
       mbar_init(&bar_free[0], 1);
       mbar_init(&bar_free[1], 1);
+      mbar_init(bar_sfree, 256);
       fence_barrier_init();
     }
     __syncwarp();
@@ -178,6 +183,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_sdp(0);
       for (int j = 0; j < Tq; ++j) {
         const int st = j & 1;
+        // S^T / dP^T of the next tile as soon as this tile's scores sit in registers (overlaps the exponentials)
+        mbar_wait(bar_sfree, j & 1);
+        tc_fence_after();
+        if (j + 1 < Tq) issue_sdp(j + 1);
         mbar_wait(bar_pds, j & 1);
         tc_fence_after();
         const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
@@ -197,7 +206,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     kk != 0);
         umma_commit(bar_dq);
         umma_commit(&bar_free[st]);
-        if (j + 1 < Tq) issue_sdp(j + 1);
       }
     }
     __syncwarp();
@@ -213,61 +221,77 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* pt_row = sPT + ch * (AB_PT / 2) + r * 128;
     uint8_t* ds_row = sdST + ch * (AB_PT / 2) + r * 128;
 
+    // dQ_j leaves through a swizzled per-warp staging box and ONE bulk TMA reduce-add (fp32, accumulated in L2 at full-line
+    // granularity; rows past the utterance are clipped by the 3-D tensor map).  Per-thread red.global of the same data had every
+    // warp instruction scatter 32 half-sectors across 32 rows and made the L2 atomic unit the kernel's bottleneck.
+    uint8_t* my_stg = sStg + (warp - 2) * 4096;
     auto drain_dq = [&](int j) {
       mbar_wait(bar_dq, j & 1);
       tc_fence_after();
       uint32_t a[32];
       tmem_ld32(tm_dQ + lane_addr + ch * 32, a);
       tmem_ld_wait();
-      const int pos = j * AB_T + r;
-      if (pos < p.n) {
-        float* dst = p.dq + ((size_t)b * p.n + pos) * D + h * 64 + ch * 32;
+      if (lane == 0) bulk_wait_read0();  // the previous box has been read out of the staging buffer
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          red_add_v4(dst + 4 * i, __uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]),
-                     __uint_as_float(a[4 * i + 3]));
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(my_stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmdQ, my_stg, h * 64 + ch * 32, j * AB_T + lq * 32, b);
+        bulk_commit();
       }
     };
 
     for (int j = 0; j < Tq; ++j) {
       const int st = j & 1;
-      if (j > 0) drain_dq(j - 1);  // also: products of tile j-1 retired -> the P^T / dS^T buffers are free
       mbar_wait(&bar_ld[st], (j >> 1) & 1);
       mbar_wait(bar_sdp, j & 1);
       tc_fence_after();
+      // pull this thread's 64 scores and 64 dP values into registers and hand the TMEM buffers back at once: the tensor pipe
+      // computes S^T / dP^T of tile j+1 (and then the three products of tile j-1 .. j) while the exponentials below run
+      uint32_t s0[32], s1[32], g0[32], g1[32];
+      tmem_ld32(tm_S + lane_addr + ch * 64, s0);
+      tmem_ld32(tm_S + lane_addr + ch * 64 + 32, s1);
+      tmem_ld32(tm_dP + lane_addr + ch * 64, g0);
+      tmem_ld32(tm_dP + lane_addr + ch * 64 + 32, g1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_sfree);
       const float4* L4 = reinterpret_cast<const float4*>(sL + st * AB_T + ch * 64);
       const float4* D4 = reinterpret_cast<const float4*>(sDl + st * AB_T + ch * 64);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], g[32];
-        tmem_ld32(tm_S + lane_addr + ch * 64 + c * 32, s);
-        tmem_ld32(tm_dP + lane_addr + ch * 64 + c * 32, g);
-        tmem_ld_wait();
+      uint32_t ppk[32], dpk[32];  // P^T and dS^T rows of this thread, packed bf16
+      auto half = [&](const uint32_t (&sv)[32], const uint32_t (&gv)[32], int c) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float pv[8], dv[8];
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 l = L4[c * 8 + q4];
+          const float4 dl = D4[c * 8 + q4];
+          const float ls[4] = {l.x, l.y, l.z, l.w};
+          const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
+          float pv[4], dv[4];
 #pragma unroll
-          for (int i4 = 0; i4 < 2; ++i4) {
-            const float4 l = L4[c * 8 + q * 2 + i4];
-            const float4 dl = D4[c * 8 + q * 2 + i4];
-            const float ls[4] = {l.x, l.y, l.z, l.w};
-            const float ds[4] = {dl.x, dl.y, dl.z, dl.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int e = q * 8 + i4 * 4 + i;
-              float pe = ex2_approx(fmaf(__uint_as_float(s[e]), c2, -ls[i]));
-              if (!key_ok) pe = 0.f;
-              pv[i4 * 4 + i] = pe;
-              dv[i4 * 4 + i] = pe * (__uint_as_float(g[e]) - ds[i]) * sc;
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int e = q4 * 4 + i;
+            float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
+            if (!key_ok) pe = 0.f;
+            pv[i] = pe;
+            dv[i] = pe * (__uint_as_float(gv[e]) - dls[i]) * sc;
           }
-          uint4 pk, dk;
-          pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]); pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
-          dk.x = pack_bf16(dv[0], dv[1]); dk.y = pack_bf16(dv[2], dv[3]); dk.z = pack_bf16(dv[4], dv[5]); dk.w = pack_bf16(dv[6], dv[7]);
-          const int chunk = ((c * 4 + q) ^ rx) << 4;
-          *reinterpret_cast<uint4*>(pt_row + chunk) = pk;
-          *reinterpret_cast<uint4*>(ds_row + chunk) = dk;
+          ppk[c * 16 + q4 * 2] = pack_bf16(pv[0], pv[1]);
+          ppk[c * 16 + q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
+          dpk[c * 16 + q4 * 2] = pack_bf16(dv[0], dv[1]);
+          dpk[c * 16 + q4 * 2 + 1] = pack_bf16(dv[2], dv[3]);
         }
+      };
+      half(s0, g0, 0);
+      half(s1, g1, 1);
+      if (j > 0) drain_dq(j - 1);  // products of tile j-1 retired: dQ_{j-1} leaves, and the P^T / dS^T buffers are free
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int chunk = (q ^ rx) << 4;
+        *reinterpret_cast<uint4*>(pt_row + chunk) = make_uint4(ppk[q * 4], ppk[q * 4 + 1], ppk[q * 4 + 2], ppk[q * 4 + 3]);
+        *reinterpret_cast<uint4*>(ds_row + chunk) = make_uint4(dpk[q * 4], dpk[q * 4 + 1], dpk[q * 4 + 2], dpk[q * 4 + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -323,6 +347,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+    if (lane == 0) bulk_wait0();  // dQ reductions of this warp have landed before the CTA retires its shared memory
     tc_fence_before();
   }
   tc_fence_before();
@@ -395,12 +420,13 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(out),
                                                                     reinterpret_cast<const __nv_bfloat16*>(dout), ld_o, delta, B, H, n);
   F5B_CUDA(cudaGetLastError());
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
   const uint64_t hw = (uint64_t)H * 64, pitch = (uint64_t)ld * 2, pitch_o = (uint64_t)ld_o * 2;
   if (make_tmap_3d(&tmQ, q, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmK, k, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmdO, dout, 2, hw, (uint64_t)n, (uint64_t)B, pitch_o, (uint64_t)n * pitch_o, 64, AB_T, 1, true)) return -1;
+  if (make_tmap_3d(&tmdQ, dq_ws, 4, hw, (uint64_t)n, (uint64_t)B, hw * 4, (uint64_t)n * hw * 4, 32, 32, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
@@ -422,7 +448,7 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.rope = rope;
   p.rope_heads = rope_heads;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
-  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   F5B_CUDA(cudaGetLastError());
   const long long items = rows * (D >> 3);
   attn_dq_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(dq_ws, p.dqkv, ld_d, rope, rope_heads, rows, n, D);

@@ -17,7 +17,8 @@ for ki, V in enumerate(rows[2:]):
             print(f"  {h} [{u}] = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 blocks = src.split('"Kernel Name"')
-for blk in blocks[1:2]:
+bsel = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+for blk in blocks[bsel:bsel + 1]:
     rows = list(csv.reader(io.StringIO('"Kernel Name"' + blk)))
     H = rows[1]; idx = {h: i for i, h in enumerate(H)}
     data = [r for r in rows[2:] if len(r) == len(H)]
