@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16
 
 // Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine; AdaLayerNorm model/modules.py:310-315):
 //   dshift[b] += sum_r dy;  dscale[b] += sum_r dy * xhat;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b])
-// One warp per row (row and statistics recomputed from the saved fp32 x), 8 rows per warp.  The two column sums live in a
+// One warp per row (row and statistics recomputed from the saved fp32 x), 4 rows per warp.  The two column sums live in a
 // per-warp shared-memory slice (plain load-add-store, no atomics, no 64-register accumulator -> 3 CTAs / SM); the 8 slices are
 // folded at the end and leave as one fp32 atomic per column per CTA.
 template <int VEC>
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
   }
   const float4* scv = scale ? reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) : nullptr;
   const float o1 = affine ? 0.f : 1.f;  // affine: `scale` is LayerNorm's weight itself
-  const int p0 = blockIdx.x * 64 + warp * 8;
-  for (int pos = p0; pos < min(n, p0 + 8); ++pos) {
+  const int p0 = blockIdx.x * 32 + warp * 4;
+  for (int pos = p0; pos < min(n, p0 + 4); ++pos) {
     const size_t row = (size_t)b * n + pos;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + row * D);
@@ -488,7 +488,7 @@ static int ln_bwd_launch(const void* dy_bf16, const float* x, const float* scale
   F5B_CHECK(dy_bf16 && x && dx && B > 0 && n > 0, "f5b_ln_modulate_bwd: bad argument");
   F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024, "f5b_ln_modulate_bwd: D=%d must be a multiple of 4 and <= 1024", D);
   LaunchScope scope(K_NORM, ST(stream), 0, (accumulate ? 14.0 : 10.0) * B * n * D);
-  const dim3 grid((n + 63) / 64, B);
+  const dim3 grid((n + 31) / 32, B);
   const size_t sm = 16 * (size_t)D * sizeof(float);  // 8 per-warp slices of (dscale, dshift)
   static bool configured = false;
   if (!configured) {
