@@ -16,7 +16,8 @@
 //     dK  += dS^T Q     A = dS^T(K-major)   B = Q   (MN-major)       TMEM cols 320..383   (resident)
 //     dQ_j = dS   K     A = dS^T tile read MN-MAJOR, B = K (MN-major)  TMEM cols 384..447 -> fp32 red.add into the dQ workspace
 //   warp 0: TMA producer (K, V once; Q_j, dO_j double-buffered) + per-tile L / delta staging; warp 1: tcgen05.mma issuer;
-//   warps 2..9: 256 softmax threads (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+//   warps 2..9: 256 softmax threads (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4);
+//   warps 10..13: dQ drain (one per TMEM lane quarter): TMEM -> swizzled staging -> bulk TMA reduce-add, off the softmax path.
 // dK and dV leave as bf16 straight into the dQKV matrix the QKV dgrad/wgrad GEMMs consume (RoPE's transpose applied to dK on the
 // way out); dQ is accumulated across the key-tile CTAs in fp32 and converted (+ RoPE transpose) by attn_dq_finish_kernel.
 #include "common.cuh"
@@ -25,7 +26,7 @@
 namespace f5b {
 
 constexpr int AB_T = 128;                       // query tile == key tile
-constexpr int AB_THREADS = 320;
+constexpr int AB_THREADS = 448;
 constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
 constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
@@ -43,6 +44,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const float* rope;    // [n, 32] (cos, sin)
   int rope_heads;
+  long long* trace;     // debug only (AB_TRACE builds)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -74,7 +76,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_dq = bars + 7;    // dV, dK, dQ_j products retired
   uint64_t* bar_free = bars + 8;  // [2] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
   uint64_t* bar_sfree = bars + 10;  // S^T_j / dP^T_j pulled into registers by all 256 threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_dqfree = bars + 11;  // dQ_j pulled out of TMEM by the 4 drain warps (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,7 +91,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (kvlen <= 0 || k0 >= kvlen) {
     // masked keys receive no gradient
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 10) {
       const int t = threadIdx.x - 64;  // 0..255
       const int row = t >> 1, half = t & 1;
       const int pos = k0 + row;
@@ -118,6 +121,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bar_free[0], 1);
       mbar_init(&bar_free[1], 1);
       mbar_init(bar_sfree, 256);
+      mbar_init(bar_dqfree, 128);
       fence_barrier_init();
     }
     __syncwarp();
@@ -154,7 +158,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int r = i * 32 + lane;
         const int pos = j * AB_T + r;
         sL[st * AB_T + r] = pos < p.n ? __ldg(p.lse + row0 + pos) : INFINITY;
-        sDl[st * AB_T + r] = pos < p.n ? __ldg(p.delta + row0 + pos) : 0.f;
+        sDl[st * AB_T + r] = pos < p.n ? __ldg(p.delta + row0 + pos) * p.scale : 0.f;  // pre-scaled: dS = P (dP scale - delta scale)
       }
       mbar_arrive(&bar_ld[st]);
     }
@@ -181,14 +185,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       mbar_wait(bar_kv, 0);
       issue_sdp(0);
+#ifdef AB_TRACE
+      long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+#define AB_MARK(i) { const long long tn = clock64(); tr[i] += tn - tprev; tprev = tn; }
+#else
+#define AB_MARK(i)
+#endif
       for (int j = 0; j < Tq; ++j) {
         const int st = j & 1;
         // S^T / dP^T of the next tile as soon as this tile's scores sit in registers (overlaps the exponentials)
         mbar_wait(bar_sfree, j & 1);
         tc_fence_after();
+        AB_MARK(0)
         if (j + 1 < Tq) issue_sdp(j + 1);
+        AB_MARK(1)
         mbar_wait(bar_pds, j & 1);
         tc_fence_after();
+        AB_MARK(2)
         const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 queries of the tile, 16 per step
@@ -200,20 +214,71 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t aoff = (kk >> 2) * (AB_PT / 2) + (kk & 3) * 32;
           umma_bf16(tm_dK, smem_desc_sw128(ds_addr + aoff, 1024, 16), smem_desc_sw128(qa + kk * 2048, 1024, 8192), id_acc, (j | kk) != 0);
         }
+        if (j > 0) {
+          mbar_wait(bar_dqfree, (j - 1) & 1);  // dQ_{j-1} has left TMEM
+          tc_fence_after();
+        }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // reduction over the 128 keys: dS^T rows are the K dimension here (MN-major A, 2 q-atoms)
           umma_bf16(tm_dQ, smem_desc_sw128(ds_addr + kk * 2048, 1024, AB_PT / 2), smem_desc_sw128(k_addr + kk * 2048, 1024, 8192), id_dq,
                     kk != 0);
         umma_commit(bar_dq);
         umma_commit(&bar_free[st]);
+        AB_MARK(3)
+#ifdef AB_TRACE
+        mbar_wait(bar_dq, j & 1);  // measurement only: serialises the issue loop
+        AB_MARK(4)
+#endif
       }
+#ifdef AB_TRACE
+      if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 37) {
+        for (int i = 0; i < 5; ++i) p.trace[i] = tr[i];
+        p.trace[6] = Tq;
+      }
+#endif
     }
     __syncwarp();
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------------------------------------ dQ drain warps
+    // dQ_j leaves through a swizzled staging box and bulk TMA reduce-adds (fp32, accumulated in L2 at full-line granularity; rows
+    // past the utterance are clipped by the 3-D tensor map).  Per-thread red.global of the same data scattered 32 half-sectors
+    // per warp instruction; draining from the softmax warps put ~1000 cycles per tile on the critical path.
+    const int lq = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    uint8_t* my_stg = sStg + (warp - 10) * 8192;  // two [32 rows x 32 f32] SW128 boxes
+    for (int j = 0; j < Tq; ++j) {
+      mbar_wait(bar_dq, j & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      tmem_ld32(tm_dQ + lane_addr, a0);
+      tmem_ld32(tm_dQ + lane_addr + 32, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_dqfree);
+      if (lane == 0) bulk_wait_read0();  // the previous boxes have been read out of the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int sw = (q ^ (lane & 7)) << 4;
+        *reinterpret_cast<uint4*>(my_stg + lane * 128 + sw) = make_uint4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
+        *reinterpret_cast<uint4*>(my_stg + 4096 + lane * 128 + sw) = make_uint4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+#ifndef AB_EXPERIMENT_NO_DQ_REDUCE
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmdQ, my_stg, h * 64, j * AB_T + lq * 32, b);
+        tma_reduce_add_3d(&tmdQ, my_stg + 4096, h * 64 + 32, j * AB_T + lq * 32, b);
+        bulk_commit();
+      }
+#endif
+    }
+    if (lane == 0) bulk_wait0();  // the reductions have landed before the CTA retires its shared memory
   } else {
     // ------------------------------------------------------------------------------------------------ softmax / gradient threads
     const int lq = warp & 3;          // TMEM lane quarter this warp may touch
     const int ch = (warp - 2) >> 2;   // column half
-    const int r = lq * 32 + lane;     // TMEM lane: key row (S^T, dP^T, dV, dK) or query row (dQ)
+    const int r = lq * 32 + lane;     // TMEM lane: key row (S^T, dP^T, dV, dK)
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
     const int rx = r & 7;
     const bool key_ok = (k0 + r) < kvlen;
@@ -221,44 +286,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* pt_row = sPT + ch * (AB_PT / 2) + r * 128;
     uint8_t* ds_row = sdST + ch * (AB_PT / 2) + r * 128;
 
-    // dQ_j leaves through a swizzled per-warp staging box and ONE bulk TMA reduce-add (fp32, accumulated in L2 at full-line
-    // granularity; rows past the utterance are clipped by the 3-D tensor map).  Per-thread red.global of the same data had every
-    // warp instruction scatter 32 half-sectors across 32 rows and made the L2 atomic unit the kernel's bottleneck.
-    uint8_t* my_stg = sStg + (warp - 2) * 4096;
-    auto drain_dq = [&](int j) {
-      mbar_wait(bar_dq, j & 1);
-      tc_fence_after();
-      uint32_t a[32];
-      tmem_ld32(tm_dQ + lane_addr + ch * 32, a);
-      tmem_ld_wait();
-      if (lane == 0) bulk_wait_read0();  // the previous box has been read out of the staging buffer
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(my_stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_3d(&tmdQ, my_stg, h * 64 + ch * 32, j * AB_T + lq * 32, b);
-        bulk_commit();
-      }
-    };
-
     for (int j = 0; j < Tq; ++j) {
       const int st = j & 1;
       mbar_wait(&bar_ld[st], (j >> 1) & 1);
       mbar_wait(bar_sdp, j & 1);
       tc_fence_after();
-      // pull this thread's 64 scores and 64 dP values into registers and hand the TMEM buffers back at once: the tensor pipe
-      // computes S^T / dP^T of tile j+1 (and then the three products of tile j-1 .. j) while the exponentials below run
-      uint32_t s0[32], s1[32], g0[32], g1[32];
-      tmem_ld32(tm_S + lane_addr + ch * 64, s0);
-      tmem_ld32(tm_S + lane_addr + ch * 64 + 32, s1);
-      tmem_ld32(tm_dP + lane_addr + ch * 64, g0);
-      tmem_ld32(tm_dP + lane_addr + ch * 64 + 32, g1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar_sfree);
       const float4* L4 = reinterpret_cast<const float4*>(sL + st * AB_T + ch * 64);
       const float4* D4 = reinterpret_cast<const float4*>(sDl + st * AB_T + ch * 64);
       uint32_t ppk[32], dpk[32];  // P^T and dS^T rows of this thread, packed bf16
@@ -266,17 +298,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 l = L4[c * 8 + q4];
-          const float4 dl = D4[c * 8 + q4];
+          const float4 dl = D4[c * 8 + q4];  // delta * scale
           const float ls[4] = {l.x, l.y, l.z, l.w};
           const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
           float pv[4], dv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int e = q4 * 4 + i;
-            float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
-            if (!key_ok) pe = 0.f;
-            pv[i] = pe;
-            dv[i] = pe * (__uint_as_float(gv[e]) - dls[i]) * sc;
+            pv[i] = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
+            dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]), sc, -dls[i]);
           }
           ppk[c * 16 + q4 * 2] = pack_bf16(pv[0], pv[1]);
           ppk[c * 16 + q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
@@ -284,9 +314,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           dpk[c * 16 + q4 * 2 + 1] = pack_bf16(dv[2], dv[3]);
         }
       };
-      half(s0, g0, 0);
-      half(s1, g1, 1);
-      if (j > 0) drain_dq(j - 1);  // products of tile j-1 retired: dQ_{j-1} leaves, and the P^T / dS^T buffers are free
+      // the scores are pulled into registers in two halves; once the second half is in, the TMEM buffers go back to the tensor
+      // pipe, which computes S^T / dP^T of tile j+1 while the exponentials run
+      {
+        uint32_t sv[32], gv[32];
+        tmem_ld32(tm_S + lane_addr + ch * 64, sv);
+        tmem_ld32(tm_dP + lane_addr + ch * 64, gv);
+        tmem_ld_wait();
+        half(sv, gv, 0);
+      }
+      {
+        uint32_t sv[32], gv[32];
+        tmem_ld32(tm_S + lane_addr + ch * 64 + 32, sv);
+        tmem_ld32(tm_dP + lane_addr + ch * 64 + 32, gv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_sfree);
+        half(sv, gv, 1);
+      }
+      if (!key_ok) {  // masked key row (tail of the utterance): no probability mass, no gradient
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ppk[i] = dpk[i] = 0u;
+      }
+      if (j > 0) mbar_wait(bar_dq, (j - 1) & 1);  // products of tile j-1 retired: the P^T / dS^T buffers are free
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int chunk = (q ^ rx) << 4;
@@ -297,7 +347,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(bar_pds);
     }
-    drain_dq(Tq - 1);
+    mbar_wait(bar_dq, (Tq - 1) & 1);
+    tc_fence_after();
     // dV, dK of this key tile (all products retired: bar_dq of the last tile)
     const int pos = k0 + r;
     {
@@ -347,7 +398,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (lane == 0) bulk_wait0();  // dQ reductions of this warp have landed before the CTA retires its shared memory
     tc_fence_before();
   }
   tc_fence_before();
@@ -406,6 +456,8 @@ __global__ void attn_dq_finish_kernel(const float* __restrict__ dq, __nv_bfloat1
   *reinterpret_cast<uint4*>(dqkv + row * ld_d + c0) = pk;
 }
 
+long long* g_attn_bwd_trace = nullptr;
+
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
              const float* rope, int rope_heads, cudaStream_t stream) {
@@ -447,6 +499,7 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.scale_log2 = scale * 1.4426950408889634f;
   p.rope = rope;
   p.rope_heads = rope_heads;
+  p.trace = g_attn_bwd_trace;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
   attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   F5B_CUDA(cudaGetLastError());
@@ -464,3 +517,5 @@ extern "C" int f5b_attn_bwd(const void* q, const void* k, const void* v, int ld,
   return f5b::attn_bwd(q, k, v, ld, out, dout, ld_o, lse, delta_ws, dq_ws, dqkv, ld_d, lens, lens_mod, B, H, n, scale, rope, rope_heads,
                        static_cast<cudaStream_t>(stream));
 }
+
+extern "C" void f5b_debug_set_attn_bwd_trace(long long* buf) { f5b::g_attn_bwd_trace = buf; }
