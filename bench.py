@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the F5-TTS hot path (BASELINE.json: mel-frames/s and RTF, F5TTS_Base, NFE=32, CFG).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" = one full pass of the hot path over one batch of synthetic utterances: CFM.sample (text embedding, 32 Euler steps x
@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg2": (dict(dim=1024, depth=22, heads=16), 16, 563, 1875, "F5TTS_Base bf16 batch=16 x 20 s utterances (ref 6 s + gen 14 s), NFE=32 sway -1 CFG 2"),
     "cfg1": (dict(dim=1024, depth=22, heads=16), 1, 376, 940, "F5TTS_Base one ~10 s utterance (ref 376 + gen 564 frames), NFE=32 Euler CFG 2"),
     "cfg3": (dict(dim=768, depth=12, heads=12), 32, 750, 1376, "F5TTS_Small pruned to 12 blocks, batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
+    # training step: ref_frames unused
+    "cfg5": (dict(dim=1024, depth=22, heads=16), 32, 0, 1200, "F5TTS_Base one optimizer step on 32 x 1200 frames per GPU: CFM.forward + backward + "
+             "gradient all-reduce + clip + AdamW + EMA, bf16 operands / fp32 master, dropout 0"),
 }
 NFE, CFG, SWAY = 32, 2.0, -1.0
 
@@ -90,6 +93,31 @@ class ClockSampler(threading.Thread):
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+class _StdoutToStderr:
+    """NCCL prints its version banner on stdout when the first communicator is created; the contract is ONE JSON line on stdout.
+    Redirect fd 1 to fd 2 at the OS level around process-group creation + the first collective."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def init_nccl(dev):
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    with _StdoutToStderr():
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)  # forces communicator creation (and the banner) now
+        torch.cuda.synchronize()
 
 
 class Arch:
@@ -229,6 +257,153 @@ def torch_eager_gpu_measure(arch, B, ref_frames, total, dev, steps=3, warmup=2):
                       f"x{NFE} extrapolated; MelSpec / text embedding / Vocos excluded (they favour this arm)",
             "kernels": "torch eager: cuBLAS linears, SDPA without key mask, cuDNN grouped conv"}
 
+def cpu_train_measure(arch, n, steps, warmup):
+    """CPU arm of the training step: torch autograd over the oracle's fp32 CFM.forward for ONE utterance of the workload
+    (forward + backward; the optimizer is negligible next to them), all host threads."""
+    from oracle import f5_oracle as O
+    from oracle.weights import make_dit_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.DiTConfig(dim=arch.dim, depth=arch.depth, heads=arch.heads)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in make_dit_state_dict(cfg, 0).items()}
+    g = torch.Generator().manual_seed(1234)
+    x1 = (torch.randn(1, n, cfg.mel_dim, generator=g) * 2 - 1.5).clamp(-11.5, 5)
+    x0 = torch.randn(1, n, cfg.mel_dim, generator=g)
+    text = torch.randint(0, cfg.text_num_embeds, (1, int(0.16 * n)), generator=g)
+    span = torch.zeros(1, n, dtype=torch.bool)
+    span[0, n // 4: n // 4 + int(0.85 * n) // 1] = True
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _, _ = O.cfm_loss(sd, cfg, x1, text, span, x0, torch.tensor([0.4]), False, False)
+        loss.backward()
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return dict(value=n / per, step_s=per, cores=torch.get_num_threads(),
+                sample=f"1 utterance ({n} frames) forward + backward (torch autograd over the fp32 oracle), mean of {len(times)}")
+
+
+def run_train(args, cfg, B, n, desc, rank, local_rank, world):
+    """--workload cfg5: one data-parallel optimizer step per timed step"""
+    import torch.distributed as dist
+    config = {"workload": f"cfg5: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
+              "parallelism": f"dp{world} (batch sharded; ONE flat fp32 gradient all-reduce per step over NCCL)",
+              "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_train_measure(cfg, n, max(1, min(args.steps, 2)), 1)
+        print(json.dumps({"impl": "reference", "metric": "train_mel_frames_per_sec", "value": r["value"], "unit": "mel-frames/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        init_nccl(dev)
+    from eraxvif5tts_b200 import _lib as L
+    from eraxvif5tts_b200.train import TrainEngine
+    L.load()
+    model, _ = build_product_models(cfg, dev)
+    eng = TrainEngine(model, with_ema=(rank == 0))  # EMA only on the main process (trainer.py:179-181)
+    if world > 1:
+        eng.broadcast_params(0)
+    g = torch.Generator().manual_seed(1234 + rank)
+    mel_h = (torch.randn(B, n, cfg.mel_dim, generator=g) * 2 - 1.5).clamp(-11.5, 5).pin_memory()
+    text_h = torch.randint(0, cfg.text_num_embeds, (B, int(0.16 * n)), generator=g).pin_memory()
+    mel_d, text_d = mel_h.to(dev), text_h.to(dev)
+    loss_h = torch.zeros(1).pin_memory()
+
+    def step(mel, text):
+        eng.zero_grad()
+        loss, _, _ = eng.loss_and_grads(mel, text)
+        scale = eng.allreduce_grads()
+        eng.step(grad_scale=scale)
+        return loss
+
+    def step_e2e():
+        loss = step(mel_h.to(dev, non_blocking=True), text_h.to(dev, non_blocking=True))
+        loss_h.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        loss = step(mel_d, text_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.prof_reset(not args.no_profile)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(mel_d, text_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = L.prof_read()
+    L.prof_reset(False)
+    assert torch.isfinite(loss).all(), "non-finite loss"
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    kinds = {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tot_ms,
+                 **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {}),
+                 **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} if v["ms"] > 0 else {})} for k, v in prof.items() if v["launches"]}
+    roofline = None
+    timed = {k: v for k, v in prof.items() if v["ms"] > 0 and v["flops"] > 0}
+    if timed:
+        top = max(timed, key=lambda k: timed[k]["ms"])
+        v = timed[top]
+        ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback", "launches": v["launches"],
+                    "avg_launch_ms": v["ms"] / v["launches"], "flops_per_launch": v["flops"] / v["launches"]}
+    frames = B * n * args.steps * world
+    step_flops = 3 * dit_flops_per_forward(cfg, B, n)
+    line = {"metric": "train_mel_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config, "clocks": sampler.summary(),
+            "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s", "h2d_bytes_per_step": mel_h.numel() * 4 + text_h.numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": sum(v["launches"] for v in prof.values()),
+            "model_tflops_per_gpu": step_flops / (ms * 1e-3 / args.steps) / 1e12, "params": eng.n,
+            "loss": float(loss), "roofline": roofline, "kernels": kinds}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_train_measure(cfg, n, 1, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -236,7 +411,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3: inference; cfg5: the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with CUDA events during the timed region")
     ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the oracle as stock PyTorch eager bf16 on this GPU (second comparator)")
@@ -248,6 +424,8 @@ def main():
 
     arch_kw, B, ref_frames, total, desc = WORKLOADS[args.workload]
     cfg = Arch(**arch_kw)
+    if args.workload == "cfg5":
+        return run_train(args, cfg, B, total, desc, rank, local_rank, world)
     frames_per_step = B * total
     gen_frames_per_step = B * (total - ref_frames)
     config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": total, "ref_frames": ref_frames,
@@ -273,8 +451,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line there)
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)  # keeps NCCL's version banner off stdout (one JSON line there)
     from eraxvif5tts_b200 import _lib as L
     L.load()
     model, voc = build_product_models(cfg, dev)

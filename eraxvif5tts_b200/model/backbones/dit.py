@@ -380,7 +380,7 @@ class DiT(nn.Module):
     @torch.no_grad()
     def forward(self, x, cond, text, time, drop_audio_cond, drop_text, mask=None, cache=False):
         """x, cond [b, n, mel]; text int [b, nt]; time [] or [b]; mask bool [b, n] (a prefix / key-padding mask as built by
-        lens_to_mask, cfm.py:152-153) -> [b, n, mel].  Inference only (training backward is not built this round)."""
+        lens_to_mask, cfm.py:152-153) -> [b, n, mel].  No autograd graph: the training step is `train.TrainEngine`."""
         eng = self.engine()
         b, n = x.shape[0], x.shape[1]
         time = time.to(device=eng.device, dtype=f32)

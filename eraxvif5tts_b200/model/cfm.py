@@ -198,9 +198,9 @@ class CFM(nn.Module):
 
     @torch.no_grad()
     def forward(self, inp, text, *, lens=None, noise_scheduler=None, draws: dict | None = None):
-        """Flow-matching training loss, FORWARD ONLY (cfm.py:210-283): returns (loss, cond, pred) like the reference, computed by
-        the CUDA library, but carries no autograd graph — the backward kernels (dgrad / wgrad, attention backward, fused AdamW +
-        NCCL gradient all-reduce) are scheduled for the next round.  Usable for validation loss today.
+        """Flow-matching loss (cfm.py:210-283): returns (loss, cond, pred) like the reference, computed by the CUDA library.  The
+        tensors carry no autograd graph: training goes through `eraxvif5tts_b200.train.TrainEngine.loss_and_grads`, which runs this
+        same forward in its activation-saving form followed by the hand-written backward.
         `draws` (extension) fixes the random choices for parity tests: rand_span_mask, x0, time, drop_audio_cond, drop_text."""
         from random import random
         from .utils import mask_from_frac_lengths

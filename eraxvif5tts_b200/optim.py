@@ -1,8 +1,9 @@
 """Optimizer step of the reference's training loop (/root/reference/src/f5_tts/model/trainer.py:316-323, 1179-1188, 1280-1287, 1321)
 re-designed around FLAT fp32 buffers: every parameter / gradient / Adam moment / EMA weight is a view into one contiguous
 buffer, so gradient averaging is ONE NCCL all-reduce over NVLink and clip + AdamW + EMA is ONE fused HBM-bound kernel
-(`f5b_adamw_ema_step`).  The backward pass that fills the gradient buffer is not built yet: until then the
-step is driven with externally supplied gradients (tests do exactly that against torch.optim.AdamW)."""
+(`f5b_adamw_ema_step`).  `FlatAdamW` is the stand-alone optimizer over any module's parameters (gradients supplied by the caller;
+tests drive it against torch.optim.AdamW); the training step proper (`train.TrainEngine`) uses the same kernels over buffers laid
+out in kernel order and fills the gradient buffer with the hand-written backward."""
 from __future__ import annotations
 
 import math
