@@ -320,10 +320,13 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     text_h = torch.randint(0, cfg.text_num_embeds, (B, int(0.16 * n)), generator=g).pin_memory()
     mel_d, text_d = mel_h.to(dev), text_h.to(dev)
     loss_h = torch.zeros(1).pin_memory()
+    overlap = world > 1 and os.environ.get("F5B_ALLREDUCE_OVERLAP", "1") != "0"
+    config["allreduce"] = ("bucketed (4 groups of blocks), launched under the remaining backward" if overlap else
+                           "one flat all-reduce after the backward") if world > 1 else "none (1 GPU)"
 
     def step(mel, text):
         eng.zero_grad()
-        loss, _, _ = eng.loss_and_grads(mel, text)
+        loss, _, _ = eng.loss_and_grads(mel, text, overlap_allreduce=overlap)
         scale = eng.allreduce_grads()
         eng.step(grad_scale=scale)
         return loss

@@ -272,9 +272,9 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
 // Backward of f5b_dit_train_forward.  dpred bf16 [B*n, 128] (columns >= mel zero; f5b_mse_grad).  Gradients are ACCUMULATED into
 // the f32 buffers of `g` (zero them first; NULL members are skipped).  cp_w1_t / cp_w2_t: conv_pos_embed weights packed by
 // f5b_pack_convpos_weight_t.  dtext_bf16 (optional) receives d loss / d text_embed as bf16 [B*n, T].
-int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* gr,
-                           void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
-                           f5b_stream_t stream) {
+static int train_backward_impl(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* gr,
+                               void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                               int parts, int blk_lo, int blk_hi, f5b_stream_t stream) {
   F5B_CHECK(h && dpred_bf16 && cp_w1_t && cp_w2_t && gr && rope && ws && B > 0 && n > 0, "f5b_dit_train_backward: bad argument");
   const F5bDitDesc& d = h->d;
   F5B_CHECK(d.depth <= MAX_DEPTH && d.dim <= 1024, "f5b_dit_train_backward: depth <= %d and dim <= 1024 supported", MAX_DEPTH);
@@ -291,16 +291,18 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
   const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
   auto off = [](float* p, size_t o) { return p ? p + o : nullptr; };
 
-  F5B_CUDA(cudaMemsetAsync(w.dmod, 0, sizeof(float) * B * mod_dim, s));
+  F5B_CHECK(blk_lo >= 0 && blk_hi <= d.depth && blk_lo <= blk_hi, "f5b_dit_train_backward: bad block range [%d, %d)", blk_lo, blk_hi);
+  if (parts & 1) {
+    F5B_CUDA(cudaMemsetAsync(w.dmod, 0, sizeof(float) * B * mod_dim, s));
+    // proj_out + AdaLayerNorm_Final
+    F5B_TRY(f5b_act_bwd(dpred_bf16, nullptr, nullptr, g.proj_b, rows, mel, 128, F5B_ACT_NONE, stream));
+    F5B_TRY(wgrad(dpred_bf16, 128, w.hbF, D, g.proj_w, D, rows, mel, D, stream));
+    F5B_TRY(dgrad(dpred_bf16, 128, d.proj_w, D, w.t1, D, rows, mel, stream));
+    float* dmf = w.dmod + (size_t)d.depth * 6 * D;
+    F5B_TRY(f5b_ln_modulate_bwd(w.t1, w.x_fin, w.mod + (size_t)d.depth * 6 * D, mod_dim, w.dx, 0, dmf, dmf + D, B, n, D, 1e-6f, stream));
+  }
 
-  // proj_out + AdaLayerNorm_Final
-  F5B_TRY(f5b_act_bwd(dpred_bf16, nullptr, nullptr, g.proj_b, rows, mel, 128, F5B_ACT_NONE, stream));
-  F5B_TRY(wgrad(dpred_bf16, 128, w.hbF, D, g.proj_w, D, rows, mel, D, stream));
-  F5B_TRY(dgrad(dpred_bf16, 128, d.proj_w, D, w.t1, D, rows, mel, stream));
-  float* dmf = w.dmod + (size_t)d.depth * 6 * D;
-  F5B_TRY(f5b_ln_modulate_bwd(w.t1, w.x_fin, w.mod + (size_t)d.depth * 6 * D, mod_dim, w.dx, 0, dmf, dmf + D, B, n, D, 1e-6f, stream));
-
-  for (int i = d.depth - 1; i >= 0; --i) {
+  for (int i = ((parts & 2) ? blk_hi : 0) - 1; i >= ((parts & 2) ? blk_lo : 0); --i) {
     const BlockSave& b = w.blk[i];
     const float* m = w.mod + (size_t)i * 6 * D;
     float* dm = w.dmod + (size_t)i * 6 * D;
@@ -324,6 +326,7 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
     F5B_TRY(f5b_ln_modulate_bwd(w.t1, b.x_in, m + D, mod_dim, w.dx, 1, dm + D, dm, B, n, D, 1e-6f, stream));
   }
 
+  if (!(parts & 4)) return 0;
   // ---- InputEmbedding: x0 = h0 + mish(conv2(mish(conv1(h0)))),  h0 = [x | cond | text] W^T + b
   const int G = d.convpos_groups, cpg = D / G, ks = d.convpos_kernel, ccols = cpg * ks;
   F5B_CHECK((cpg & 7) == 0, "f5b_dit_train_backward: channels per conv group must be a multiple of 8");
@@ -377,6 +380,21 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
   F5B_TRY(f5b_act_bwd(w.tb2, w.a1, w.tb2, g.time_b0, B, D, D, F5B_ACT_SILU, stream));                        // d a1
   F5B_TRY(wgrad(w.tb2, D, w.sin_bf, 256, g.time_w0, 256, B, D, 256, stream));
   return 0;
+}
+
+int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* gr,
+                           void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                           f5b_stream_t stream) {
+  return train_backward_impl(h, dpred_bf16, cp_w1_t, cp_w2_t, gr, dtext_bf16, B, n, lens, rope, ws, ws_bytes, 7, 0, h ? h->d.depth : 0, stream);
+}
+
+// The same backward in pieces, so that the host can start the gradient all-reduce of finished blocks while earlier blocks are
+// still being differentiated: parts bit 0 = head (proj_out, final AdaLN), bit 1 = blocks [blk_lo, blk_hi) in descending order,
+// bit 2 = tail (input embedding, modulation / time MLP).  Pieces must be issued head, blocks from depth down to 0, tail.
+int f5b_dit_train_backward_part(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* gr,
+                                void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                                int parts, int blk_lo, int blk_hi, f5b_stream_t stream) {
+  return train_backward_impl(h, dpred_bf16, cp_w1_t, cp_w2_t, gr, dtext_bf16, B, n, lens, rope, ws, ws_bytes, parts, blk_lo, blk_hi, stream);
 }
 
 size_t f5b_dit_text_train_ws_bytes(const F5bDit* h, int B, int n) {

@@ -147,6 +147,19 @@ class TrainEngine:
         self.handle = h
         self._ws = None
         self._rope = {}
+        # gradient segments that are complete once a block has been differentiated (stacked [depth, ...] tensors) and the rest
+        F = dit.ff_mult * D
+        self._stacked = [("qkv_w", 3 * D * D), ("qkv_b", 3 * D), ("out_w", D * D), ("out_b", D), ("ff1_w", F * D), ("ff1_b", F),
+                         ("ff2_w", D * F), ("ff2_b", D)]
+        covered = sorted((self.offsets[k], self.offsets[k] + dit.depth * per) for k, per in self._stacked)
+        self._rest, pos = [], 0
+        for a, b in covered:
+            if a > pos:
+                self._rest.append((pos, a))
+            pos = b
+        if pos < self.n:
+            self._rest.append((pos, self.n))
+        self._pending = None
         self.refresh_packed()
 
     def __del__(self):
@@ -199,10 +212,14 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------------------ forward + backward
     @torch.no_grad()
-    def loss_and_grads(self, inp, text, *, lens=None, draws: dict | None = None):
+    def loss_and_grads(self, inp, text, *, lens=None, draws: dict | None = None, overlap_allreduce: bool = False, group=None,
+                       buckets: int = 4):
         """CFM.forward (cfm.py:210-283) followed by loss.backward(): returns (loss, cond, pred) and ACCUMULATES d loss / d theta into
         the flat gradient buffer (= every parameter's .grad).  `draws` fixes the random choices (rand_span_mask, x0, time,
-        drop_audio_cond, drop_text) for parity tests."""
+        drop_audio_cond, drop_text) for parity tests.
+        overlap_allreduce (use on the LAST micro-batch of an update, world > 1): the backward is issued in `buckets` groups of blocks
+        from the top of the network down, and the NCCL all-reduce of each group's finished gradient segments is launched while the
+        groups below are still being differentiated (DDP's bucketed overlap); `allreduce_grads()` then only waits."""
         from .model.utils import exists, lens_to_mask, list_str_to_idx, list_str_to_tensor, mask_from_frac_lengths
         cfm, lib, dev = self.cfm, self.lib, self.device
         inp = inp.to(dev)
@@ -260,11 +277,38 @@ class TrainEngine:
         L.check(lib.f5b_mse_grad(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), out2.data_ptr(), dpred.data_ptr(), B * n, C_, 128, s),
                 "f5b_mse_grad")
         dtext = torch.empty(B * n, self.T, dtype=bf16, device=dev)
-        L.check(lib.f5b_dit_train_backward(self.handle, dpred.data_ptr(), self.cp["w1_t"].data_ptr(), self.cp["w2_t"].data_ptr(),
-                                           C.byref(self.grads), dtext.data_ptr(), B, n, None, rope.data_ptr(), ws.data_ptr(),
-                                           ws.numel(), s), "f5b_dit_train_backward")
+        import torch.distributed as dist
+        overlap = overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+        def part(parts, lo, hi):
+            L.check(lib.f5b_dit_train_backward_part(self.handle, dpred.data_ptr(), self.cp["w1_t"].data_ptr(), self.cp["w2_t"].data_ptr(),
+                                                    C.byref(self.grads), dtext.data_ptr(), B, n, None, rope.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), parts, lo, hi, s), "f5b_dit_train_backward_part")
+
+        works = []
+        if overlap:
+            depth = self.dit.depth
+            nb = max(1, min(buckets, depth))
+            bounds = [round(depth * (nb - k) / nb) for k in range(nb + 1)]  # depth ... 0
+            part(1, 0, 0)
+            for k in range(nb):
+                hi, lo = bounds[k], bounds[k + 1]
+                if hi <= lo:
+                    continue
+                part(2, lo, hi)
+                for name, per in self._stacked:  # these blocks' gradients are final: reduce them under the remaining backward
+                    o = self.offsets[name]
+                    works.append(dist.all_reduce(self.g[o + lo * per:o + hi * per], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            part(4, 0, 0)
+        else:
+            part(7, 0, self.dit.depth)
         L.check(lib.f5b_dit_text_embed_backward(self.handle, text.data_ptr(), text.shape[1], B, n, int(drop_text), dtext.data_ptr(),
                                                 C.byref(self.grads), tws.data_ptr(), tws.numel(), s), "f5b_dit_text_embed_backward")
+        if overlap:
+            self._fold_split_grads()
+            for a, b in self._rest:
+                works.append(dist.all_reduce(self.g[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            self._pending = (works, 1.0 / dist.get_world_size(group))
         return out2[0], cond, pred
 
     def _fold_split_grads(self):
@@ -281,6 +325,12 @@ class TrainEngine:
     def allreduce_grads(self, group=None) -> float:
         """DDP's gradient averaging (trainer.py:1280 via accelerate) as ONE flat all-reduce; returns the scale still to apply"""
         from .parallel import allreduce_flat_
+        if self._pending is not None:  # launched under the backward (loss_and_grads(overlap_allreduce=True)): just wait
+            works, scale = self._pending
+            self._pending = None
+            for w in works:
+                w.wait()
+            return scale
         self._fold_split_grads()
         return allreduce_flat_(self.g, group)
 

@@ -271,6 +271,13 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
                            void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
                            f5b_stream_t stream);
 
+/* The same backward in pieces (parts bit 0 = head: proj_out + final AdaLN; bit 1 = blocks [blk_lo, blk_hi) in descending order;
+ * bit 2 = tail: input embedding + modulation / time MLP), issued head -> blocks from depth down to 0 -> tail, so the host can start
+ * the gradient all-reduce of finished blocks (DDP's bucketed overlap, trainer.py:1280) while earlier blocks are differentiated. */
+int f5b_dit_train_backward_part(const F5bDit* h, const void* dpred_bf16, const void* cp_w1_t, const void* cp_w2_t, const F5bDitGrads* g,
+                                void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
+                                int parts, int blk_lo, int blk_hi, f5b_stream_t stream);
+
 /* TextEmbedding.forward in training form (every ConvNeXtV2Block input kept in ws) and its backward: dtext_bf16 [B*n, T] is the
  * gradient f5b_dit_train_backward returns; fills g->text_table and g->tb_*.  text_mask_padding is not supported here. */
 size_t f5b_dit_text_train_ws_bytes(const F5bDit* h, int B, int n);

@@ -103,3 +103,23 @@ def test_gradient_accumulation_and_step_changes_loss():
     # the inference engine sees the updated weights (re-packed lazily)
     out = model.transformer(x=x1.cuda(), cond=x1.cuda(), text=text.cuda(), time=time.cuda(), drop_audio_cond=False, drop_text=False)
     assert torch.isfinite(out).all()
+
+
+def test_backward_other_widths():
+    """non-power-of-two width (dim 384 = 6 heads, 24 channels per conv group, text_dim 96, pe on ALL heads): the F5TTS_Small-like
+    code paths of the LN / conv / attention backward"""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig.tiny(dim=384, heads=6, depth=1, text_dim=96, conv_layers=1, pe_attn_head=None)
+    model, sd = build_cfm(cfg, 3)
+    eng = TrainEngine(model)
+    B, n = 2, 200
+    x1, x0, time, text, span = _draws(cfg, B, n, 21)
+    ref_loss, ref_pred, ref = _oracle_grads(sd, cfg, x1, text, span, x0, time, False, False)
+    eng.zero_grad()
+    loss, cond, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False,
+                                                                               drop_text=False))
+    eng._fold_split_grads()
+    torch.cuda.synchronize()
+    assert maxabs(pred, ref_pred) <= 2e-2
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    _compare(model, ref)

@@ -38,7 +38,7 @@ def shard(r):
 
 x1, text, dr = shard(rank)
 eng.zero_grad()
-eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dr)
+eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dr, overlap_allreduce=os.environ.get("F5B_ALLREDUCE_OVERLAP", "1") != "0", buckets=2)
 scale = eng.allreduce_grads()
 avg = eng.g * scale
 ok = True
