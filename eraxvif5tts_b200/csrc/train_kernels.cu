@@ -68,6 +68,7 @@ __global__ void gate_add_kernel(const float* x, const __nv_bfloat16* __restrict_
 }
 
 // dz[r, :] = bf16(gate[b, :] * dx[r, :]) (0 on masked rows);  dgate[b, :] += sum_r dx[r, :] * z[r, :];  dbias[:] += sum_r dz[r, :]
+// thread = 4 adjacent columns (16-byte fp32 / 8-byte bf16 accesses), 64 rows per CTA
 __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
                                                               const float* __restrict__ gate, int64_t gate_bstride,
                                                               const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ dz,
@@ -77,43 +78,57 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
   const int p1 = min(n, p0 + CT_ROWS);
   const int live_end = lens ? min(p1, __ldg(lens + b)) : p1;
   const float* g = gate ? gate + (size_t)b * gate_bstride : nullptr;
-  for (int c = threadIdx.x * 2; c < C; c += 2 * CT_THREADS) {
-    const float g0 = g ? __ldg(g + c) : 1.f, g1 = g ? __ldg(g + c + 1) : 1.f;
-    float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+  for (int c = threadIdx.x * 4; c < C; c += 4 * CT_THREADS) {
+    float gv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (g) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(g + c));
+      gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w;
+    }
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int pos = p0; pos < p1; ++pos) {
       const size_t off = ((size_t)b * n + pos) * C + c;
-      float2 o = make_float2(0.f, 0.f);
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
       if (pos < live_end) {
-        const float2 d = *reinterpret_cast<const float2*>(dx + off);
+        const float4 d4 = *reinterpret_cast<const float4*>(dx + off);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
         if (z != nullptr) {
-          const float2 zz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(z + off));
-          a0 = fmaf(d.x, zz.x, a0);
-          a1 = fmaf(d.y, zz.y, a1);
+          const uint2 zz = *reinterpret_cast<const uint2*>(z + off);
+          const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.x));
+          const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.y));
+          a[0] = fmaf(d[0], z01.x, a[0]); a[1] = fmaf(d[1], z01.y, a[1]); a[2] = fmaf(d[2], z23.x, a[2]); a[3] = fmaf(d[3], z23.y, a[3]);
         }
-        o.x = g0 * d.x;
-        o.y = g1 * d.y;
-        s0 += o.x;
-        s1 += o.y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[i] = gv[i] * d[i];
+          s[i] += o[i];
+        }
       }
-      *reinterpret_cast<uint32_t*>(dz + off) = pack_bf16(o.x, o.y);
+      *reinterpret_cast<uint2*>(dz + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
     }
     if (dgate && z != nullptr) {
-      atomicAdd(dgate + (size_t)b * gate_bstride + c, a0);
-      atomicAdd(dgate + (size_t)b * gate_bstride + c + 1, a1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dgate + (size_t)b * gate_bstride + c + i, a[i]);
     }
     if (dbias) {
-      atomicAdd(dbias + c, s0);
-      atomicAdd(dbias + c + 1, s1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dbias + c + i, s[i]);
     }
   }
 }
 
-__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n2, int act) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n2) return;
-  const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(h)[i]);
-  reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(act_eval(act, v.x), act_eval(act, v.y));
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n8, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 elements (16-byte accesses)
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(h)[i];
+  const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&in[k]));
+    o[k] = pack_bf16(act_eval(act, f.x), act_eval(act, f.y));
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // dh[r, :] = bf16(du[r, :] * act'(h[r, :]));  dbias[:] += sum_r dh[r, :]      (act NONE + dh NULL = plain column sum of du)
@@ -158,9 +173,10 @@ __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16
 
 // Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine; AdaLayerNorm model/modules.py:310-315):
 //   dshift[b] += sum_r dy;  dscale[b] += sum_r dy * xhat;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b])
-// One warp per row (row and statistics recomputed from the saved fp32 x), 4 rows per warp.  The two column sums live in a
-// per-warp shared-memory slice (plain load-add-store, no atomics, no 64-register accumulator -> 3 CTAs / SM); the 8 slices are
-// folded at the end and leave as one fp32 atomic per column per CTA.
+// One warp per row, 4 rows per warp.  The row is NOT cached in registers: it is streamed four times (mean; variance; the two
+// projections + column sums; output) and passes 2-4 hit L1, which keeps the kernel at ~48 registers -> 5 CTAs / SM of loads in
+// flight instead of 2 (the register-resident version ran at 2.8 TB/s, latency-bound).  The column sums live in a per-warp
+// shared-memory slice (plain load-add-store), folded at the end into one fp32 atomic per column per CTA.
 template <int VEC>
 __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                                          const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
@@ -184,47 +200,51 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     const size_t row = (size_t)b * n + pos;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + row * D);
-    float4 v[VEC], g[VEC];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
-      v[j] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += v[j].x + v[j].y + v[j].z + v[j].w;
-      const uint2 d = idx < nvec ? dr[idx] : make_uint2(0u, 0u);
-      const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
-      const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
-      g[j] = make_float4(d0.x, d0.y, d1.x, d1.y);
+      if (idx < nvec) {
+        const float4 v = __ldg(xr + idx);
+        s += (v.x + v.y) + (v.z + v.w);
+      }
     }
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j)
-      if (lane + j * 32 < nvec) {
-        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-        q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    for (int j = 0; j < VEC; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        const float4 v = __ldg(xr + idx);
+        const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       }
+    }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
       if (idx < nvec) {
-        v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;  // xhat
+        const float4 v = __ldg(xr + idx);
+        const uint2 d = __ldg(dr + idx);
+        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
+        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd, xh2 = (v.z - mean) * rstd, xh3 = (v.w - mean) * rstd;
         float4 a = my_sh[idx];
-        a.x += g[j].x; a.y += g[j].y; a.z += g[j].z; a.w += g[j].w;
+        a.x += d0.x; a.y += d0.y; a.z += d1.x; a.w += d1.y;
         my_sh[idx] = a;
         a = my_sc[idx];
-        a.x = fmaf(g[j].x, v[j].x, a.x); a.y = fmaf(g[j].y, v[j].y, a.y); a.z = fmaf(g[j].z, v[j].z, a.z); a.w = fmaf(g[j].w, v[j].w, a.w);
+        a.x = fmaf(d0.x, xh0, a.x); a.y = fmaf(d0.y, xh1, a.y); a.z = fmaf(d1.x, xh2, a.z); a.w = fmaf(d1.y, xh3, a.w);
         my_sc[idx] = a;
         float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
         if (scv != nullptr) {
           const float4 sc = __ldg(scv + idx);
           m = make_float4(o1 + sc.x, o1 + sc.y, o1 + sc.z, o1 + sc.w);
         }
-        g[j].x *= m.x; g[j].y *= m.y; g[j].z *= m.z; g[j].w *= m.w;
-        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
-        s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
+        const float g0 = d0.x * m.x, g1 = d0.y * m.y, g2 = d1.x * m.z, g3 = d1.y * m.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * xh0 + g1 * xh1) + (g2 * xh2 + g3 * xh3);
       }
     }
     s1 = warp_sum(s1) / (float)D;
@@ -234,14 +254,23 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
       if (idx < nvec) {
+        const float4 v = __ldg(xr + idx);
+        const uint2 d = __ldg(dr + idx);
+        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
+        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (scv != nullptr) {
+          const float4 sc = __ldg(scv + idx);
+          m = make_float4(o1 + sc.x, o1 + sc.y, o1 + sc.z, o1 + sc.w);
+        }
         float4 r;
-        r.x = rstd * (g[j].x - s1 - v[j].x * s2);
-        r.y = rstd * (g[j].y - s1 - v[j].y * s2);
-        r.z = rstd * (g[j].z - s1 - v[j].z * s2);
-        r.w = rstd * (g[j].w - s1 - v[j].w * s2);
+        r.x = rstd * (d0.x * m.x - s1 - (v.x - mean) * rstd * s2);
+        r.y = rstd * (d0.y * m.y - s1 - (v.y - mean) * rstd * s2);
+        r.z = rstd * (d1.x * m.z - s1 - (v.z - mean) * rstd * s2);
+        r.w = rstd * (d1.y * m.w - s1 - (v.w - mean) * rstd * s2);
         if (accumulate) {
-          const float4 p = o[idx];
-          r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+          const float4 pz = o[idx];
+          r.x += pz.x; r.y += pz.y; r.z += pz.z; r.w += pz.w;
         }
         o[idx] = r;
       }
@@ -454,7 +483,7 @@ int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t 
 
 int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
                  float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream) {
-  F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_gate_bwd: bad argument");
+  F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 3) == 0 && (gate_bstride & 3) == 0, "f5b_gate_bwd: C and the gate stride must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * B * n * C);
   gate_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), CT_THREADS, 0, ST(stream)>>>(
       dx, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16), dgate, dbias,
@@ -464,10 +493,10 @@ int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t
 }
 
 int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_stream_t stream) {
-  F5B_CHECK(h_bf16 && out_bf16 && count > 0 && (count & 1) == 0, "f5b_act_fwd: bad argument");
+  F5B_CHECK(h_bf16 && out_bf16 && count > 0 && (count & 7) == 0, "f5b_act_fwd: count must be a multiple of 8");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * count);
-  act_fwd_kernel<<<(unsigned)((count / 2 + 255) / 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16),
-                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 2, act);
+  act_fwd_kernel<<<(unsigned)((count / 8 + 255) / 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16),
+                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 8, act);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
