@@ -243,3 +243,88 @@ def test_lr_and_ema_schedules_match_torch_and_ema_pytorch_rules():
     d = e.decay_for_call(111)  # step 110 -> epoch 9
     assert abs(d - (1 - (1 + 9) ** (-2 / 3))) < 1e-12
     assert e.decay_for_call(10 ** 8 + 1) == 0.9999
+
+
+class _FakeFrames:
+    def __init__(self, lens):
+        self.lens = lens
+
+    def __len__(self):
+        return len(self.lens)
+
+    def get_frame_len(self, i):
+        return self.lens[i]
+
+
+def _load_reference_dataset_module():
+    """the reference's dataset.py executed with its heavy imports stubbed (only DynamicBatchSampler / collate_fn are used)"""
+    import importlib.util
+    import sys
+    import types
+    path = "/root/reference/src/f5_tts/model/dataset.py"
+    if not os.path.exists(path):
+        return None
+    stubs = {}
+    for name in ("torchaudio", "datasets", "f5_tts", "f5_tts.model", "f5_tts.model.modules", "f5_tts.model.utils", "tqdm"):
+        if name not in sys.modules:
+            stubs[name] = types.ModuleType(name)
+    stubs.get("datasets", sys.modules.get("datasets")).Dataset = getattr(sys.modules.get("datasets"), "Dataset", object)
+    stubs.get("datasets", sys.modules.get("datasets")).load_from_disk = lambda *a, **k: None
+    if "f5_tts.model.modules" in stubs:
+        stubs["f5_tts.model.modules"].MelSpec = object
+    if "f5_tts.model.utils" in stubs:
+        stubs["f5_tts.model.utils"].default = lambda v, d: v if v is not None else d
+    if "tqdm" in stubs:
+        stubs["tqdm"].tqdm = lambda it, **k: it
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_dataset", path)
+        mod = importlib.util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(mod)
+        except Exception:  # noqa: BLE001  (an import the stubs do not cover)
+            return None
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_dynamic_batch_sampler_and_collate():
+    from torch.utils.data import SequentialSampler
+    from eraxvif5tts_b200.data import DynamicBatchSampler, collate_fn, collate_token_major, shard_batches
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(50, 3000, (500,), generator=g).tolist() + [5000]  # one utterance above the budget
+    src = _FakeFrames(lens)
+    bs = DynamicBatchSampler(SequentialSampler(src), frames_threshold=3200, max_samples=8, random_seed=666)
+    flat = [i for b in bs.batches for i in b]
+    assert sorted(flat) == list(range(500)) and 500 not in flat          # everything that fits, exactly once
+    assert all(sum(lens[i] for i in b) <= 3200 and 1 <= len(b) <= 8 for b in bs.batches)
+    assert [lens[i] for i in flat] == sorted(lens[:500])                 # length-sorted packing (high padding efficiency)
+    bs.set_epoch(3)
+    e3 = list(bs)
+    bs.set_epoch(3)
+    assert e3 == list(bs)
+    bs.set_epoch(4)
+    assert e3 != list(bs) and sorted(map(tuple, e3)) == sorted(map(tuple, bs.batches))
+    shards = [shard_batches(e3, r, 4) for r in range(4)]
+    assert len({len(s) for s in shards}) == 1 and sum(len(s) for s in shards) == len(e3) // 4 * 4
+    assert not set(map(tuple, shards[0])) & set(map(tuple, shards[1]))
+    ref = _load_reference_dataset_module()
+    if ref is not None:  # identical batches and epoch order as the reference class
+        rb = ref.DynamicBatchSampler(SequentialSampler(src), frames_threshold=3200, max_samples=8, random_seed=666)
+        assert rb.batches == bs.batches
+        rb.set_epoch(3)
+        assert list(rb) == e3
+    items = [dict(mel_spec=torch.randn(1, 100, t, generator=g), text="x" * (t // 10)) for t in (120, 77, 301)]
+    a, b = collate_fn(items), collate_token_major(items, pin=False)
+    assert a["mel"].shape == (3, 100, 301) and b["mel"].shape == (3, 301, 100)
+    assert torch.equal(a["mel"].permute(0, 2, 1), b["mel"]) and torch.equal(a["mel_lengths"], b["mel_lengths"])
+    assert a["text"] == b["text"] and a["text_lengths"].tolist() == [12, 7, 30]
+    if ref is not None:
+        r = ref.collate_fn(items)
+        assert torch.equal(r["mel"], a["mel"]) and torch.equal(r["mel_lengths"], a["mel_lengths"]) and r["text"] == a["text"]
