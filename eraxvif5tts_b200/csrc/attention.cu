@@ -25,15 +25,21 @@ namespace f5b {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
 constexpr int ATT_THREADS = 160;
-constexpr int ATT_CTAS_PER_SM = 3;
+#ifndef ATT_CTAS
+#define ATT_CTAS 3
+#endif
+constexpr int ATT_CTAS_PER_SM = ATT_CTAS;
 constexpr uint32_t ATT_Q_BYTES = ATT_BQ * 64 * 2;          // 16 KB
 constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage, 2 stages
 constexpr uint32_t ATT_V_BYTES = ATT_BKV * 64 * 2;         // 8 KB, 1 stage: [64 kv rows x 64 d]
 constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer, 2 buffers
+#ifndef ATT_P_TMEM
+#define ATT_P_TMEM 0  // 1: P goes to tensor memory (aliasing the score columns) and feeds P.V as a TMEM A operand
+#endif
 #ifndef ATT_EXTRA_SMEM
 #define ATT_EXTRA_SMEM 0  // experiments: pad shared memory to lower the number of resident CTAs
 #endif
-constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + 2 * ATT_P_BYTES + 1024 + 128 + ATT_EXTRA_SMEM;
+constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + (ATT_P_TMEM ? 0 : 2 * ATT_P_BYTES) + 1024 + 128 + ATT_EXTRA_SMEM;
 constexpr uint32_t ATT_TMEM_COLS = 128;  // S: 0..63, O: 64..127
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
@@ -73,6 +79,31 @@ __device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl
   return sum0 + sum1;
 }
 
+// same, P kept in registers (16 packed bf16 pairs) for the tensor-memory path
+template <bool MASKED>
+__device__ __forceinline__ float softmax_chunk_reg(const uint32_t (&s)[32], float sl2, float mb, int lim, uint32_t* pk) {
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = fmaf(__uint_as_float(s[q * 8 + i]), sl2, -mb);
+      e[i] = ex2_approx(x);
+      if constexpr (MASKED) {
+        if (q * 8 + i >= lim) e[i] = 0.f;
+      }
+    }
+    sum0 += (e[0] + e[1]) + (e[2] + e[3]);
+    sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+    pk[q * 4 + 0] = pack_bf16(e[0], e[1]);
+    pk[q * 4 + 1] = pack_bf16(e[2], e[3]);
+    pk[q * 4 + 2] = pack_bf16(e[4], e[5]);
+    pk[q * 4 + 3] = pack_bf16(e[6], e[7]);
+  }
+  return sum0 + sum1;
+}
+
 // row maximum of the first `valid` of 32 raw scores (4 independent chains when the chunk is full)
 __device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
   if (valid >= 32) {
@@ -103,7 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = sQ + ATT_Q_BYTES;
   uint8_t* sV = sK + 2 * ATT_K_BYTES;
   uint8_t* sP = sV + ATT_V_BYTES;  // 16K + 16K + 8K = 40K: 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (ATT_P_TMEM ? 0 : 2 * ATT_P_BYTES));
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;      // [2] K_j landed
   uint64_t* bar_v = bars + 3;      // V_j landed
@@ -193,6 +224,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       load_v(0);
       mbar_wait(bar_q, 0);
       issue_s(0);
+#if ATT_P_TMEM
+      for (int j = 0; j < T; ++j) {
+        // P_j sits in tensor memory (over the score columns): O += P_j V_j with the A operand read from TMEM, THEN S_{j+1} into
+        // the same columns (the tensor pipe executes one thread's MMAs in order, so the overwrite follows the read)
+        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        mbar_wait(bar_v, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(tmem_O, tmem_base + kk * 8, smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv, (j | kk) != 0);
+        umma_commit(bar_pv);
+        if (j + 1 < T) issue_s(j + 1);
+        if (j + 2 < T) load_k(j + 2);  // S_j retired long ago (its scores were consumed before P_j was written)
+        if (j + 1 < T) {
+          mbar_wait(bar_pv, j & 1);  // the single V stage is free once P_j V_j retired
+          load_v(j + 1);
+        }
+      }
+    }
+#else
       for (int j = 0; j < T; ++j) {
         // S_j sits in registers: its TMEM buffer and K stage are free -> S_{j+1} overlaps the exponentials of tile j
         mbar_wait(bar_sfree, j & 1);
@@ -216,6 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+#endif
     __syncwarp();
   } else {
     const int r = warp * 32 + lane;  // query row in tile == TMEM lane
@@ -246,6 +299,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(bar_sfree);
       ATT_MARK(1)
       if (j == 0) m_used = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
+#if ATT_P_TMEM
+      // exponentials are speculative w.r.t. this tile's maximum (see header); P stays in registers until it is final
+      uint32_t ppk[32];
+      float ts;
+      auto make_p = [&]() {
+        if (valid == ATT_BKV) {
+          ts = softmax_chunk_reg<false>(s0, sl2, m_used, 32, ppk);
+          ts += softmax_chunk_reg<false>(s1, sl2, m_used, 32, ppk + 16);
+        } else {
+          ts = softmax_chunk_reg<true>(s0, sl2, m_used, valid, ppk);
+          ts += softmax_chunk_reg<true>(s1, sl2, m_used, valid - 32, ppk + 16);
+        }
+      };
+      make_p();
+      ATT_MARK(2)
+      if (j > 0) {
+        const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
+        if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
+          const float m_new = fmaxf(m_used, mt);
+          const float f = ex2_approx(m_used - m_new);
+          m_used = m_new;
+          l_run *= f;
+          mbar_wait(bar_pv, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tmem_O + lane_addr + c * 32, o);
+          }
+          tmem_st_wait();
+          make_p();
+        }
+      }
+      // P_j -> tensor memory, over the first 32 of the 64 score columns (S_j is in registers; S_{j+1} is issued after P_j V_j)
+      tmem_st32(tmem_base + lane_addr, ppk);
+      tmem_st_wait();
+#else
       // bar_s(j) was committed after P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing
       // thread), so the P buffer (j & 1) is free.  Exponentials are speculative w.r.t. this tile's maximum (see header).
       float ts;
@@ -286,9 +380,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+#endif
       l_run += ts;
       ATT_MARK(3)
+#if !ATT_P_TMEM
       fence_proxy_async_smem();
+#endif
       tc_fence_before();
       mbar_arrive(&bar_p[j & 1]);
       ATT_MARK(4)
