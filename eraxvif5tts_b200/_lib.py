@@ -136,6 +136,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.f5b_abi_version() != 1:
         raise F5bError("libf5b200.so ABI version mismatch; rebuild")
+    if os.environ.get("F5B_ATTN_VARIANT"):  # kernel A/B switch for experiments (0 = default)
+        lib.f5b_debug_attn_variant(int(os.environ["F5B_ATTN_VARIANT"]))
     _lib = lib
     return lib
 
