@@ -62,6 +62,7 @@ SIGNATURES = {
     "f5b_attn_bwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp,
                                C.c_int, vp]),
     "f5b_gate_add": (C.c_int, [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_gate_add_ln_modulate": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_gate_bwd": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_act_fwd": (C.c_int, [vp, vp, i64, C.c_int, vp]),
     "f5b_act_bwd": (C.c_int, [vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp]),

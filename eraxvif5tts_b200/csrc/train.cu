@@ -242,11 +242,17 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
   const bf* out_w = reinterpret_cast<const bf*>(d.out_w);
   const bf* ff1_w = reinterpret_cast<const bf*>(d.ff1_w);
   const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
+  // the gated residual of each branch is fused with the AdaLN of the next one (f5b_gate_add_ln_modulate): the first AdaLN of block
+  // 0 runs alone, the last gated residual feeds AdaLayerNorm_Final
+  {
+    const float* m0 = w.mod;
+    F5B_TRY(ln_modulate(w.blk[0].x_in, m0 + D, m0, mod_dim, 0, w.blk[0].a, rows, n, D, 1e-6f, s));
+  }
   for (int i = 0; i < d.depth; ++i) {
     const BlockSave& b = w.blk[i];
-    float* x_out = (i + 1 < d.depth) ? w.blk[i + 1].x_in : w.x_fin;
+    const bool last = i + 1 == d.depth;
+    float* x_out = last ? w.x_fin : w.blk[i + 1].x_in;
     const float* m = w.mod + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (modules.py:312)
-    F5B_TRY(ln_modulate(b.x_in, m + D, m, mod_dim, 0, b.a, rows, n, D, 1e-6f, s));
     F5bGemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
@@ -256,15 +262,19 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
     F5B_TRY(gemm(b.a, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
     F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s));
     F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
-    F5B_TRY(f5b_gate_add(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, B, n, D, stream));
-    F5B_TRY(ln_modulate(b.x_mid, m + 4 * D, m + 3 * D, mod_dim, 0, b.f, rows, n, D, 1e-6f, s));
+    // x_mid = x_in + gate_msa * mask(z1);  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
+    F5B_TRY(f5b_gate_add_ln_modulate(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D, 1e-6f,
+                                     stream));
     F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
     F5B_TRY(f5b_act_fwd(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, stream));
     F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
-    F5B_TRY(f5b_gate_add(b.x_mid, b.z2, m + 5 * D, mod_dim, nullptr, x_out, B, n, D, stream));
+    // x_out = x_mid + gate_mlp * z2;  next AdaLN: block i+1's (shift_msa, scale_msa) or AdaLayerNorm_Final's (scale, shift; :333)
+    const float* mn = w.mod + (size_t)(i + 1) * 6 * D;
+    const float* nscale = last ? mn : mn + D;
+    const float* nshift = last ? mn + D : mn;
+    bf* nout = last ? w.hbF : w.blk[i + 1].a;
+    F5B_TRY(f5b_gate_add_ln_modulate(b.x_mid, b.z2, m + 5 * D, mod_dim, nullptr, x_out, nscale, nshift, mod_dim, nout, B, n, D, 1e-6f, stream));
   }
-  const float* mf = w.mod + (size_t)d.depth * 6 * D;  // AdaLayerNorm_Final: scale, shift (modules.py:333)
-  F5B_TRY(ln_modulate(w.x_fin, mf, mf + D, mod_dim, 0, w.hbF, rows, n, D, 1e-6f, s));
   F5B_TRY(linear_f32(w.hbF, D, d.proj_w, D, d.proj_b, pred, mel, rows, mel, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
   return 0;
 }

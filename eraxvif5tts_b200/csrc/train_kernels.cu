@@ -464,6 +464,69 @@ __global__ void __launch_bounds__(256) text_lookup_bwd_kernel(const float* __res
   }
 }
 
+// x_out = x + gate[b] * z (rows >= lens[b] keep x)  AND  out = LN(x_out) * (1 + scale[b]) + shift[b] in one sweep: the gated
+// residual of one branch and the AdaLN of the next share the read of the residual stream (training forward; inference has both
+// fused into GEMM epilogues).  One warp per row, the row lives in registers (D <= 1024).
+template <int VEC>
+__global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ z,
+                                                          const float* __restrict__ gate, int64_t gate_bstride,
+                                                          const int32_t* __restrict__ lens, float* __restrict__ x_out,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          int64_t mod_bstride, __nv_bfloat16* __restrict__ out, int n, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int pos = blockIdx.x * 8 + warp;
+  if (pos >= n) return;
+  const size_t row = (size_t)b * n + pos;
+  const bool live = lens == nullptr || pos < __ldg(lens + b);
+  const int nvec = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const uint2* zr = reinterpret_cast<const uint2*>(z + row * D);
+  const float4* gv = gate ? reinterpret_cast<const float4*>(gate + (size_t)b * gate_bstride) : nullptr;
+  float4* xo = reinterpret_cast<float4*>(x_out + row * D);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < nvec) {
+      v[j] = xr[idx];
+      if (live) {
+        const uint2 zz = zr[idx];
+        const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.x));
+        const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.y));
+        const float4 g = gv ? __ldg(gv + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+        v[j].x = fmaf(g.x, z01.x, v[j].x); v[j].y = fmaf(g.y, z01.y, v[j].y);
+        v[j].z = fmaf(g.z, z23.x, v[j].z); v[j].w = fmaf(g.w, z23.y, v[j].w);
+      }
+      xo[idx] = v[j];
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    if (lane + j * 32 < nvec) {
+      const float a0 = v[j].x - mean, a1 = v[j].y - mean, a2 = v[j].z - mean, a3 = v[j].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_bstride);
+  uint2* o = reinterpret_cast<uint2*>(out + row * D);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(sc + idx), h = __ldg(sh + idx);
+      o[idx] = make_uint2(pack_bf16((v[j].x - mean) * rstd * (1.f + g.x) + h.x, (v[j].y - mean) * rstd * (1.f + g.y) + h.y),
+                          pack_bf16((v[j].z - mean) * rstd * (1.f + g.z) + h.z, (v[j].w - mean) * rstd * (1.f + g.w) + h.w));
+    }
+  }
+}
+
 }  // namespace f5b
 
 using namespace f5b;
@@ -477,6 +540,24 @@ int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t 
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 10.0 * B * n * C);
   gate_add_kernel<<<dim3((n + 7) / 8, B), 256, 0, ST(stream)>>>(x, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens,
                                                                out, n, C);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_gate_add_ln_modulate(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                             float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B, int n,
+                             int D, float eps, f5b_stream_t stream) {
+  F5B_CHECK(x && z_bf16 && x_out && scale && shift && out_bf16 && B > 0 && n > 0, "f5b_gate_add_ln_modulate: bad argument");
+  F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024 && (gate_bstride & 3) == 0 && (mod_bstride & 3) == 0,
+            "f5b_gate_add_ln_modulate: D=%d must be a multiple of 4 and <= 1024, strides multiples of 4", D);
+  LaunchScope scope(K_NORM, ST(stream), 0, 12.0 * B * n * D);
+  const dim3 grid((n + 7) / 8, B);
+  auto* zz = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
+  auto* oo = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const int nvec = D / 4;
+  if (nvec <= 64) gate_add_ln_kernel<2><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
+  else if (nvec <= 128) gate_add_ln_kernel<4><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
+  else gate_add_ln_kernel<8><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

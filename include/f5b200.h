@@ -327,6 +327,11 @@ int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* w
  * Un-fused training form of the gated residual: out = x + gate[b] * z (rows >= lens[b] keep x, :499-501); z bf16 [B*n, C]. */
 int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, float* out, int B,
                  int n, int C, f5b_stream_t stream);
+/* the same fused with the LayerNorm-modulate that consumes x_out (one read of the residual stream instead of two):
+ * x_out = x + gate[b] * z;  out_bf16 = LN(x_out) * (1 + scale[b]) + shift[b].  D <= 1024. */
+int f5b_gate_add_ln_modulate(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                             float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B, int n,
+                             int D, float eps, f5b_stream_t stream);
 /* ... and its backward: dz = bf16(gate[b] * dx) (0 on rows >= lens[b]); dgate[b] += sum_r dx * z; dbias += sum_r dz (NULL = skip) */
 int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
                  float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream);
