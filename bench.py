@@ -292,7 +292,8 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     import torch.distributed as dist
     config = {"workload": f"cfg5: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
               "parallelism": f"dp{world} (batch sharded; ONE flat fp32 gradient all-reduce per step over NCCL)",
-              "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2"}
+              "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2",
+              "profiling": "timed region un-instrumented; kernel classes / roofline from 2 extra event-bracketed steps"}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -346,7 +347,9 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    L.prof_reset(not args.no_profile)
+    # the timed region runs WITHOUT per-launch event bracketing (about 780 event pairs per step cost ~3 % here); the kernel-class
+    # breakdown and the roofline come from extra bracketed steps right after it
+    L.prof_reset(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -355,6 +358,13 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launches_per_step = 0
+    prof_steps = 2
+    if not args.no_profile:
+        L.prof_reset(True)
+        for _ in range(prof_steps):
+            loss = step(mel_d, text_d)
+        barrier()
     prof = L.prof_read()
     L.prof_reset(False)
     assert torch.isfinite(loss).all(), "non-finite loss"
@@ -380,7 +390,7 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
         peaks = json.load(open(pk_path))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    kinds = {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tot_ms,
+    kinds = {k: {"launches_per_step": v["launches"] / prof_steps, "ms_per_step": v["ms"] / prof_steps, "share": v["ms"] / tot_ms,
                  **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {}),
                  **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} if v["ms"] > 0 else {})} for k, v in prof.items() if v["launches"]}
     roofline = None
@@ -399,7 +409,7 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": sampler.summary(),
             "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s", "h2d_bytes_per_step": mel_h.numel() * 4 + text_h.numel() * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps},
-            "gpu_launches": sum(v["launches"] for v in prof.values()),
+            "gpu_launches": int(sum(v["launches"] for v in prof.values()) / prof_steps * args.steps),
             "model_tflops_per_gpu": step_flops / (ms * 1e-3 / args.steps) / 1e12, "params": eng.n,
             "loss": float(loss), "roofline": roofline, "kernels": kinds}
     if world == 1 and not args.no_cpu_baseline:
