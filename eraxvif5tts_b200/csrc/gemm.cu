@@ -49,6 +49,7 @@ struct LinearProblem {
   __device__ __forceinline__ int num_kblocks() const { return kblocks; }
   __device__ __forceinline__ uint32_t umma_n() const { return BN; }
   __device__ __forceinline__ uint32_t idesc() const { return idesc_bf16(BM, umma_n(), 0, 0); }
+  __device__ __forceinline__ uint32_t idesc2() const { return idesc_bf16(2 * BM, umma_n(), 0, 0); }  // CTA pair: 256 rows
   __device__ __forceinline__ uint64_t a_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint64_t b_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
@@ -64,6 +65,13 @@ struct LinearProblem {
     tma_load_2d(sA, tmA, bar, kb * BK, m_blk * BM);
     // this CTA fetches rows [rank*BN/2, +BN/2) of the weight tile and multicasts them to both CTAs of the pair
     tma_load_2d_mcast(sB + rank * (EngCfg<BN>::B_BYTES / 2), tmB, bar, kb * BK, n_blk * BN + (int)rank * (BN / 2), (uint16_t)0x3);
+  }
+  // CTA-pair mode: this CTA stages its own A rows and rows [rank*BN/2, +BN/2) of the weight tile; both complete on the leader's barrier
+  __device__ __forceinline__ void load2(int tile, int kb, uint8_t* sA, uint8_t* sB, uint32_t leader_bar, const CUtensorMap* tmA,
+                                        const CUtensorMap* tmB, uint32_t rank) const {
+    const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    tma_load_2d_2sm(sA, tmA, leader_bar, kb * BK, m_blk * BM);
+    tma_load_2d_2sm(sB, tmB, leader_bar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
   }
   __device__ __forceinline__ RowCtx row_ctx(int tile, int r) const {
     RowCtx c;
@@ -171,6 +179,8 @@ struct LinearProblem {
   }
 };
 
+int g_gemm_pair_mode = 1;  // 1 (default): 256-wide tiles run as tcgen05 CTA pairs (cta_group::2); 0: two cta_group::1 tiles + weight multicast
+
 template <int BN, int EPI, int ACT>
 static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F5bGemmArgs& g, cudaStream_t stream) {
   using P = LinearProblem<BN, EPI, ACT>;
@@ -186,6 +196,9 @@ static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
   } else if constexpr (P::STORE == STORE_F32ADD) {
     F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
     if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
+  }
+  if constexpr (BN == 256) {
+    if (g_gemm_pair_mode) return launch_engine<P, true>(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
   }
   return launch_engine(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
 }
@@ -267,3 +280,5 @@ extern "C" int f5b_gemm(const void* A, int lda, const void* W, int ldw, const F5
   }
   return f5b::gemm(A, lda, W, ldw, *args, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" void f5b_debug_gemm_pair_mode(int v) { f5b::g_gemm_pair_mode = v; }

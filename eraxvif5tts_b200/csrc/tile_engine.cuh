@@ -40,17 +40,34 @@ struct EngCfg {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// CTA-pair mode (cta_group::2): each CTA stages A [128 x 64] and HALF of the B tile [BN/2 x 64] per k-block
+template <int BN>
+struct EngCfg2 {
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : 8;
+  static constexpr uint32_t STAGING_BYTES = EPI_WARPS * 4096;
+  static constexpr uint32_t TMEM_COLS = EngCfg<BN>::TMEM_COLS;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
+template <bool TWOSM, int BN> struct EngCfgSel { using type = EngCfg<BN>; };
+template <int BN> struct EngCfgSel<true, BN> { using type = EngCfg2<BN>; };
+
 // store 8 consecutive 16-byte chunks (this lane's 128-byte row) into a [32 x 128 B] SWIZZLE_128B staging tile
 __device__ __forceinline__ void stage_store16(uint8_t* stg, int lane, int chunk, uint4 v) {
   *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
 }
 
-template <class P>
+// TWOSM: the two CTAs of the cluster form one tcgen05 CTA pair: a 256-row x BN tile per pair, the MMA issued by the leader CTA
+// reads each operand half from each CTA's shared memory, so the shared-memory port of an SM sees half the operand traffic per flop
+// (with cta_group::1 and a 128 x 256 tile the TMA fills + MMA operand reads add up to ~192 B/clk against a 128 B/clk port).
+template <class P, bool TWOSM = false>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1)
 engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmC, const P p) {
   constexpr int BN = P::BN;
-  using Cfg = EngCfg<BN>;
+  using Cfg = typename EngCfgSel<TWOSM, BN>::type;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -79,16 +96,17 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], CL);
+        mbar_init(&empty[s], TWOSM ? 1 : CL);  // pair mode: ONE multicast commit of the leader arrives in each CTA
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], EPI_WARPS);
+        mbar_init(&tempty[s], TWOSM ? 2 * EPI_WARPS : EPI_WARPS);  // pair mode: both CTAs' epilogue warps report to the leader
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if constexpr (TWOSM) tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -108,17 +126,26 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int tile = p.unit_tile(unit, crank);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], tx);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          p.load(tile, kb, sa, sa + Cfg::A_BYTES, &full[stage], &tmA, &tmB, crank);
+          if constexpr (TWOSM) {
+            // both CTAs' loads complete on the LEADER's barrier (it alone issues the MMAs); bytes that land before the leader's
+            // expect_tx only drive the pending count negative for a moment
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            p.load2(tile, kb, sa, sa + Cfg::A_BYTES, mapa_u32(&full[stage], 0), &tmA, &tmB, crank);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], tx);
+            p.load(tile, kb, sa, sa + Cfg::A_BYTES, &full[stage], &tmA, &tmB, crank);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = p.idesc();
+    if (lane == 0 && (!TWOSM || crank == 0)) {
+      uint32_t idesc;
+      if constexpr (TWOSM) idesc = p.idesc2();
+      else idesc = p.idesc();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -135,13 +162,16 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+            if constexpr (TWOSM) umma_bf16_2sm(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
           }
-          if constexpr (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
+          if constexpr (TWOSM) umma_commit2_mcast(&empty[stage], (uint16_t)0x3);
+          else if constexpr (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
           else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (TWOSM) umma_commit2_mcast(&tfull[acc], (uint16_t)0x3);
+        else umma_commit(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -229,7 +259,10 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       __syncwarp();
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (TWOSM) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader CTA issues the next MMAs into this buffer
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     if constexpr (P::STORE != STORE_DIRECT) {
       if (lane == 0) bulk_wait0();
@@ -240,16 +273,18 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (TWOSM) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <class P>
+template <class P, bool TWOSM = false>
 static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const P& p, int total_units,
                          cudaStream_t stream) {
-  using Cfg = EngCfg<P::BN>;
+  using Cfg = typename EngCfgSel<TWOSM, P::BN>::type;
+  static_assert(!TWOSM || P::CLUSTER == 2, "pair mode needs a 2-CTA cluster");
   static bool configured = false;
-  auto kern = engine_kernel<P>;
+  auto kern = engine_kernel<P, TWOSM>;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     configured = true;
