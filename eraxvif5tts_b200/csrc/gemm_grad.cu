@@ -17,19 +17,47 @@ struct GradArgs {
   float* bias_unused;
 };
 
-template <int BN_, bool A_MN, bool B_MN, int STORE_>
+// PAIR: the unit is a vertical PAIR of m-blocks run by a 2-CTA cluster as one tcgen05 CTA pair (cta_group::2, 256 x BN tile):
+// g.m_tiles is then padded to even (the block past the end loads zeros and its stores are clipped).
+template <int BN_, bool A_MN, bool B_MN, int STORE_, bool PAIR = false>
 struct GradProblem {
   static constexpr int BN = BN_;
   static constexpr int STORE = STORE_;   // STORE_BF16 or STORE_F32ADD
-  static constexpr int CLUSTER = 1;
+  static constexpr int CLUSTER = PAIR ? 2 : 1;
   GradArgs g;
 
   struct RowCtx {
     int row, n_base;
     bool valid;
   };
-  __device__ __forceinline__ int num_units() const { return g.m_tiles * g.n_tiles * g.splits; }
-  __device__ __forceinline__ int unit_tile(int unit, uint32_t) const { return unit; }
+  __device__ __forceinline__ int num_units() const { return (PAIR ? g.m_tiles / 2 : g.m_tiles) * g.n_tiles * g.splits; }
+  __device__ __forceinline__ int unit_tile(int unit, uint32_t rank) const {
+    if constexpr (!PAIR) return unit;
+    const int n_blk = unit % g.n_tiles, t = unit / g.n_tiles;
+    const int mp = t % (g.m_tiles / 2), split = t / (g.m_tiles / 2);
+    return (split * g.m_tiles + 2 * mp + (int)rank) * g.n_tiles + n_blk;
+  }
+  __device__ __forceinline__ uint32_t idesc2() const { return idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0); }
+  // pair mode: own A rows + this CTA's half of the B tile, both completing on the leader CTA's barrier
+  __device__ __forceinline__ void load2(int unit, int kb, uint8_t* sA, uint8_t* sB, uint32_t leader_bar, const CUtensorMap* tmA,
+                                        const CUtensorMap* tmB, uint32_t rank) const {
+    int split, m_blk, n_blk;
+    decode(unit, split, m_blk, n_blk);
+    const int k0 = (split * g.kb_per_split + kb) * BK;
+    if constexpr (A_MN) {
+#pragma unroll
+      for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sA + c * 8192, tmA, leader_bar, m_blk * BM + c * 64, k0);
+    } else {
+      tma_load_2d_2sm(sA, tmA, leader_bar, k0, m_blk * BM);
+    }
+    const int n0 = n_blk * BN + (int)rank * (BN / 2);
+    if constexpr (B_MN) {
+#pragma unroll
+      for (int c = 0; c < BN / 128; ++c) tma_load_2d_2sm(sB + c * 8192, tmB, leader_bar, n0 + c * 64, k0);
+    } else {
+      tma_load_2d_2sm(sB, tmB, leader_bar, k0, n0);  // tensor map box: BN/2 rows
+    }
+  }
   __device__ __forceinline__ int num_kblocks() const { return g.kb_per_split; }
   __device__ __forceinline__ uint32_t umma_n() const { return BN; }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
@@ -80,13 +108,14 @@ struct GradProblem {
   __device__ __forceinline__ void epilogue(const RowCtx&, int, const uint32_t (&)[32]) const {}
 };
 
-template <int BN, bool A_MN, bool B_MN, int STORE>
+template <int BN, bool A_MN, bool B_MN, int STORE, bool PAIR = false>
 static int launch_grad(const void* A, int lda, const void* B, int ldb, void* out, int ldc, int M, int N, int K, int splits,
                        cudaStream_t stream) {
-  using P = GradProblem<BN, A_MN, B_MN, STORE>;
+  using P = GradProblem<BN, A_MN, B_MN, STORE, PAIR>;
   P p;
   p.g.M = M; p.g.N = N; p.g.K = K;
   p.g.m_tiles = (M + BM - 1) / BM;
+  if (PAIR) p.g.m_tiles = (p.g.m_tiles + 1) / 2 * 2;
   p.g.n_tiles = (N + BN - 1) / BN;
   const int kblocks = (K + BK - 1) / BK;
   p.g.splits = splits;
@@ -100,15 +129,18 @@ static int launch_grad(const void* A, int lda, const void* B, int ldb, void* out
   if (B_MN) {
     if (make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64, true)) return -1;
   } else {
-    if (make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN, true)) return -1;
+    if (make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, PAIR ? BN / 2 : BN, true)) return -1;
   }
   if (STORE == STORE_BF16) {
     if (make_tmap_2d(&tmC, out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32, true)) return -1;
   } else {
     if (make_tmap_2d(&tmC, out, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, true)) return -1;
   }
-  return launch_engine(tmA, tmB, tmC, p, p.g.m_tiles * p.g.n_tiles * splits, stream);
+  const int units = (PAIR ? p.g.m_tiles / 2 : p.g.m_tiles) * p.g.n_tiles * splits;
+  return launch_engine<P, PAIR>(tmA, tmB, tmC, p, units, stream);
 }
+
+int g_grad_pair_mode = 1;  // 1 (default): 256-wide tiles with at least two m-blocks run as tcgen05 CTA pairs
 
 }  // namespace f5b
 
@@ -125,6 +157,9 @@ extern "C" int f5b_gemm_tn(const void* A, int lda, int a_mn_major, const void* B
   LaunchScope scope(K_GEMM, s, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (out_f32_accumulate ? 8.0 : 2.0) * M * N);
 #define F5B_GRAD_CASE(AM, BMj)                                                                                            \
   if ((a_mn_major != 0) == AM && (b_mn_major != 0) == BMj) {                                                               \
+    if (N >= 256 && M > 128 && g_grad_pair_mode)  /* wide tiles as CTA pairs */                                             \
+      return out_f32_accumulate ? launch_grad<256, AM, BMj, STORE_F32ADD, true>(A, lda, B, ldb, out, ldc, M, N, K, splits, s)  \
+                                : launch_grad<256, AM, BMj, STORE_BF16, true>(A, lda, B, ldb, out, ldc, M, N, K, splits, s);   \
     if (N >= 256)  /* wide tiles: half the operand traffic per flop */                                                     \
       return out_f32_accumulate ? launch_grad<256, AM, BMj, STORE_F32ADD>(A, lda, B, ldb, out, ldc, M, N, K, splits, s)  \
                                 : launch_grad<256, AM, BMj, STORE_BF16>(A, lda, B, ldb, out, ldc, M, N, K, splits, s);   \
@@ -138,3 +173,5 @@ extern "C" int f5b_gemm_tn(const void* A, int lda, int a_mn_major, const void* B
 #undef F5B_GRAD_CASE
   return -1;
 }
+
+extern "C" void f5b_debug_grad_pair_mode(int v) { f5b::g_grad_pair_mode = v; }
