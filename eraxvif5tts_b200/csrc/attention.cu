@@ -351,7 +351,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ts += softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
       }
       ATT_MARK(2)
-      if (j > 0) {
+      // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
+      // sum: the 64-way maximum is only evaluated when that cheap necessary condition holds for some row of the warp
+      if (j > 0 && __any_sync(0xffffffffu, ts > 256.0f)) {
         const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
         // warp-uniform decision; tcgen05.ld/st are warp-collective
         if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
