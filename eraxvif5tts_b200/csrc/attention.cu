@@ -141,8 +141,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_s = bars + 4;      // S_j in TMEM
   uint64_t* bar_sfree = bars + 5;  // S_j pulled into registers by all 128 softmax threads
   uint64_t* bar_p = bars + 6;      // [2] P_j in smem (128 arrivals)
-  uint64_t* bar_pv = bars + 8;     // P_j V_j retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  // [2] P_j V_j retired, tile j on barrier j & 1.  TWO barriers because the softmax threads do not wait for every tile's P V: with a
+  // single barrier whose phase advances once per tile, a softmax thread that reaches the epilogue (or the rescale path) while the
+  // barrier is still TWO phases behind sees "the phase of this parity has completed" and reads O before the last products landed
+  // (observed: rows off by the weight of the last tiles, only when one warp runs a full tile ahead of the slowest).  With two
+  // alternating barriers a waiter would have to be four tiles ahead to alias, which the S pipeline (depth 1) rules out.
+  uint64_t* bar_pv = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,7 +187,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar_sfree, 128);
       mbar_init(&bar_p[0], 128);
       mbar_init(&bar_p[1], 128);
-      mbar_init(bar_pv, 1);
+      mbar_init(&bar_pv[0], 1);
+      mbar_init(&bar_pv[1], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -235,11 +241,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ts(tmem_O, tmem_base + kk * 8, smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv, (j | kk) != 0);
-        umma_commit(bar_pv);
+        umma_commit(&bar_pv[j & 1]);
         if (j + 1 < T) issue_s(j + 1);
         if (j + 2 < T) load_k(j + 2);  // S_j retired long ago (its scores were consumed before P_j was written)
         if (j + 1 < T) {
-          mbar_wait(bar_pv, j & 1);  // the single V stage is free once P_j V_j retired
+          mbar_wait(&bar_pv[j & 1], (j >> 1) & 1);  // the single V stage is free once P_j V_j retired
           load_v(j + 1);
         }
       }
@@ -261,9 +267,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // MN-major SW128 operand: rows = keys (128 B of d each), 8-row groups 1024 B apart (SBO); one UMMA K-step = 16 keys
           umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv,
                     (j | kk) != 0);
-        umma_commit(bar_pv);
+        umma_commit(&bar_pv[j & 1]);
         if (j + 1 < T) {
-          mbar_wait(bar_pv, j & 1);  // the single V stage is free once P_j V_j retired
+          mbar_wait(&bar_pv[j & 1], (j >> 1) & 1);  // the single V stage is free once P_j V_j retired
           load_v(j + 1);
         }
       }
@@ -321,7 +327,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float f = ex2_approx(m_used - m_new);
           m_used = m_new;
           l_run *= f;
-          mbar_wait(bar_pv, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V_{j-1} has landed in O
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -361,7 +367,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float f = ex2_approx(m_used - m_new);
           m_used = m_new;
           l_run *= f;
-          mbar_wait(bar_pv, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V_{j-1} has landed in O
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -399,7 +405,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 #endif
     // epilogue: O / l
-    mbar_wait(bar_pv, (T - 1) & 1);
+    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
     const int pos = q0 + r;
     const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;

@@ -66,24 +66,6 @@ def _run(B, H, n, lens, rope_heads, seed=0):
     valid = torch.ones(B, n, dtype=torch.bool, device=dev) if keymask is None else keymask
     tol = 2e-2 + 2e-2 * o.detach().abs().max().item()
     fwd_err = (out.float().reshape(B, n, D) - o.detach()).abs() * valid[:, :, None]
-    if not fwd_err.max().item() <= tol:
-        # Known intermittent issue: in the FIRST CUDA process on a fresh box this forward check has failed a
-        # few times for the 1 x 16 x 1200 case and never in any later process; 100 back-to-back runs are bit-identical.  Report
-        # where, re-run once, and only fail if the re-run is wrong too (a deterministic bug), so that a transient does not abort
-        # the whole GPU tier under `pytest -x`.
-        import warnings
-        rows = torch.nonzero(fwd_err.amax(dim=(0, 2)) > tol).flatten()
-        heads = sorted(set((torch.nonzero(fwd_err.amax(dim=(0, 1)) > tol).flatten() // 64).tolist()))
-        first = out.clone()
-        ops.attn_fwd_lse(qkv_post[:, :D], qkv_post[:, D:], qkv_post[:, 2 * D:], 3 * D, out, lse, lens_t, 0, B, H, n)
-        ops.attn_bwd(qkv_post[:, :D], qkv_post[:, D:], qkv_post[:, 2 * D:], 3 * D, out, dout, lse, dqkv, lens_t, 0, B, H, n,
-                     rope=table.reshape(n, 64), rope_heads=rope_heads)
-        torch.cuda.synchronize()
-        msg = (f"FWD MISMATCH B{B} H{H} n{n}: max err {fwd_err.max().item():.4f} rows {rows[:12].tolist()} (n={rows.numel()}) heads {heads}; "
-               f"re-run identical to first: {torch.equal(first, out)}")
-        print(msg)
-        warnings.warn(msg)
-        fwd_err = (out.float().reshape(B, n, D) - o.detach()).abs() * valid[:, :, None]
     assert fwd_err.max().item() <= tol
     vm = valid[:, None, :].expand(B, H, n)
     assert (lse[vm] - lse_ref[vm]).abs().max() < 2e-2
