@@ -123,3 +123,41 @@ def test_backward_other_widths():
     assert maxabs(pred, ref_pred) <= 2e-2
     assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
     _compare(model, ref)
+
+
+def test_ragged_lens_and_raw_audio_batches():
+    """what the data path hands over: zero-padded ragged batches with `lens`, and raw-audio batches (2-D input -> GPU MelSpec)"""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig.tiny()
+    model, sd = build_cfm(cfg, 0)
+    eng = TrainEngine(model)
+    B, n = 3, 120
+    x1, x0, time, text, span = _draws(cfg, B, n, 31)
+    lens = torch.tensor([n, 61, 7])
+    x1 = x1 * (torch.arange(n)[None, :, None] < lens[:, None, None])  # collate pads with zeros
+    mask = torch.arange(n)[None] < lens[:, None]
+    ref_loss, ref_pred, ref = _oracle_grads(sd, cfg, x1, text, span & mask, x0, time, False, False)
+    eng.zero_grad()
+    loss, cond, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), lens=lens.cuda(),
+                                          draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False, drop_text=False))
+    eng._fold_split_grads()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    _compare(model, ref)
+    # raw audio: [b, nw] -> MelSpec on the GPU -> the same step; the loss must match the oracle fed with the oracle's mel
+    g = torch.Generator().manual_seed(5)
+    wav = 0.1 * torch.randn(2, 256 * 63, generator=g)
+    mel = O.melspec(wav).permute(0, 2, 1).contiguous()  # [b, T, 100]
+    T = mel.shape[1]
+    x0 = torch.randn(2, T, cfg.mel_dim, generator=g)
+    time = torch.rand(2, generator=g)
+    text = torch.randint(0, cfg.text_num_embeds, (2, 10), generator=g)
+    span = torch.zeros(2, T, dtype=torch.bool)
+    span[:, 10:50] = True
+    ref_loss, _, _ = O.cfm_loss(sd, cfg, mel, text, span, x0, time, False, False)
+    eng.zero_grad()
+    loss, _, _ = eng.loss_and_grads(wav.cuda(), text.cuda(), draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False,
+                                                                         drop_text=False))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * float(ref_loss)
+    assert torch.isfinite(eng.g).all() and float(eng.g.abs().max()) > 0
