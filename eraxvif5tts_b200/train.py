@@ -368,6 +368,65 @@ class TrainEngine:
         L.check(self.lib.f5b_grad_sumsq(self.g.data_ptr(), self.n, self._red.data_ptr(), self._sumsq.data_ptr(), L.stream()), "f5b_grad_sumsq")
         return self._sumsq.sqrt() * grad_scale
 
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def checkpoint(self, update: int, scheduler_state: dict | None = None) -> dict:
+        """The reference's training checkpoint (Trainer.save_checkpoint, trainer.py:521-530): `model_state_dict`,
+        `optimizer_state_dict` in torch.optim.AdamW's layout (parameters numbered in `model.parameters()` order, per-parameter
+        `step` / `exp_avg` / `exp_avg_sq`), `ema_model_state_dict` in ema_pytorch's layout (`ema_model.` prefix + `initted`, `step`),
+        `scheduler_state_dict`, `update` — so the reference's loaders and tools keep working on checkpoints written here."""
+        cfm = self.cfm
+        where = {id(p): (o, s) for p, o, s in self.params}
+        plist = list(cfm.parameters())
+        state = {}
+        for i, p in enumerate(plist):
+            o, n_ = where[id(p)]
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[o:o + n_].view_as(p).clone(),
+                        "exp_avg_sq": self.v[o:o + n_].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(plist)))}
+        ck = dict(model_state_dict={k: v.detach().clone() for k, v in cfm.state_dict().items()},
+                  optimizer_state_dict={"state": state, "param_groups": [group]},
+                  scheduler_state_dict=scheduler_state or {}, update=update)
+        if self.ema is not None:
+            ema = {"initted": torch.tensor(self.ema_calls > 0), "step": torch.tensor(self.ema_calls)}
+            names = {id(p): k for k, p in cfm.named_parameters()}
+            for k, v in cfm.state_dict().items():
+                ema["ema_model." + k] = v.detach().clone()
+            for p, o, n_ in self.params:
+                ema["ema_model." + names[id(p)]] = self.ema[o:o + n_].view_as(p).clone()
+            ck["ema_model_state_dict"] = ema
+        return ck
+
+    def save_checkpoint(self, path: str, update: int, scheduler_state: dict | None = None) -> None:
+        torch.save(self.checkpoint(update, scheduler_state), path)
+
+    @torch.no_grad()
+    def load_checkpoint(self, ckpt) -> int:
+        """resume from a checkpoint in the reference's format (trainer.py:600-690): weights, Adam moments, EMA; returns `update`"""
+        if isinstance(ckpt, str):
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=True)
+        cfm = self.cfm
+        sd = ckpt["model_state_dict"]
+        names = {id(p): k for k, p in cfm.named_parameters()}
+        plist = list(cfm.parameters())
+        index = {id(p): i for i, p in enumerate(plist)}
+        opt = ckpt.get("optimizer_state_dict", {}).get("state", {})
+        ema = ckpt.get("ema_model_state_dict")
+        for p, o, n_ in self.params:
+            k = names[id(p)]
+            self.p[o:o + n_].copy_(sd[k].reshape(-1))
+            st = opt.get(index[id(p)]) or opt.get(str(index[id(p)]))
+            if st is not None:
+                self.m[o:o + n_].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + n_].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count = int(float(st["step"]))
+            if self.ema is not None and ema is not None and ("ema_model." + k) in ema:
+                self.ema[o:o + n_].copy_(ema["ema_model." + k].reshape(-1))
+        if ema is not None and "step" in ema:
+            self.ema_calls = int(ema["step"])
+        self.sync_from_master()
+        return int(ckpt.get("update", ckpt.get("step", 0)))
+
     def ema_state_dict(self) -> dict:
         names = {id(p): k for k, p in self.dit.named_parameters()}
         return {"ema_model.transformer." + names[id(p)]: self.ema[o:o + s].view_as(p).clone() for p, o, s in self.params}

@@ -161,3 +161,48 @@ def test_ragged_lens_and_raw_audio_batches():
     torch.cuda.synchronize()
     assert abs(float(loss) - float(ref_loss)) <= 2e-2 * float(ref_loss)
     assert torch.isfinite(eng.g).all() and float(eng.g.abs().max()) > 0
+
+
+def test_training_checkpoint_round_trip_in_reference_format(tmp_path):
+    """save -> keep training -> load restores weights, Adam moments and EMA bit for bit; the file has the reference Trainer's
+    keys (trainer.py:521-530), its optimizer state loads into torch.optim.AdamW, and the inference loader reads both weight sets"""
+    from eraxvif5tts_b200.train import TrainEngine
+    from eraxvif5tts_b200.infer.utils_infer import load_checkpoint
+    cfg = O.DiTConfig.tiny()
+    model, sd = build_cfm(cfg, 0)
+    eng = TrainEngine(model, lr=1e-3, with_ema=True)
+    B, n = 2, 64
+    x1, x0, time, text, span = _draws(cfg, B, n, 3)
+    dr = dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False, drop_text=False)
+    for _ in range(3):
+        eng.zero_grad()
+        eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dr)
+        eng.step()
+    path = str(tmp_path / "model_3.pt")
+    eng.save_checkpoint(path, update=3, scheduler_state={"last_epoch": 3})
+    snap = (eng.p.clone(), eng.m.clone(), eng.v.clone(), eng.ema.clone(), eng.step_count, eng.ema_calls)
+    for _ in range(2):
+        eng.zero_grad()
+        eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dr)
+        eng.step()
+    assert not torch.equal(eng.p, snap[0])
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "ema_model_state_dict", "scheduler_state_dict", "update"}
+    assert {"initted", "step"} <= set(ck["ema_model_state_dict"]) and all(
+        k.startswith("ema_model.") for k in ck["ema_model_state_dict"] if k not in ("initted", "step"))
+    assert eng.load_checkpoint(path) == 3
+    torch.cuda.synchronize()
+    assert torch.equal(eng.p, snap[0]) and torch.equal(eng.m, snap[1]) and torch.equal(eng.v, snap[2]) and torch.equal(eng.ema, snap[3])
+    assert (eng.step_count, eng.ema_calls) == snap[4:]
+    assert torch.equal(eng.mirror.float(), eng.p.bfloat16().float())
+    # torch's own optimizer accepts the state
+    ref_opt = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone().cpu()) for p in model.parameters()], lr=1e-3)
+    ref_opt.load_state_dict(ck["optimizer_state_dict"])
+    # the reference-style inference loader reads the online and the EMA weights (f5tts_wrapper.py:224-249)
+    m2, _ = build_cfm(cfg, 1)
+    load_checkpoint(m2, path, "cuda", use_ema=False)
+    k0 = "transformer.transformer_blocks.0.attn.to_q.weight"
+    assert torch.equal(dict(m2.named_parameters())[k0].cpu(), ck["model_state_dict"][k0])
+    m3, _ = build_cfm(cfg, 1)
+    load_checkpoint(m3, path, "cuda", use_ema=True)
+    assert torch.equal(dict(m3.named_parameters())[k0].cpu(), ck["ema_model_state_dict"]["ema_model." + k0])
