@@ -51,7 +51,13 @@ def _compare(model, ref, skip_prefix=None, fro_tol=4e-2, cos_tol=0.999):
         cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
         worst.append((fro, cos, k))
     worst.sort(reverse=True)
-    bad = [w for w in worst if w[0] > fro_tol or w[1] < cos_tol]
+    # softmax attention is invariant to adding one vector to every key (q.(k + c) shifts a row's scores by a constant), so the exact
+    # gradient of to_k.bias is ZERO for every head without RoPE: what autograd and the kernels return there is rounding noise around
+    # a tiny signal from the RoPE head, and gets a correspondingly looser bar
+    def ok(w):
+        loose = w[2].endswith("attn.to_k.bias")
+        return w[0] <= (0.15 if loose else fro_tol) and w[1] >= (0.99 if loose else cos_tol)
+    bad = [w for w in worst if not ok(w)]
     assert not bad, bad[:8]
     return worst
 
@@ -206,3 +212,36 @@ def test_training_checkpoint_round_trip_in_reference_format(tmp_path):
     m3, _ = build_cfm(cfg, 1)
     load_checkpoint(m3, path, "cuda", use_ema=True)
     assert torch.equal(dict(m3.named_parameters())[k0].cpu(), ck["ema_model_state_dict"]["ema_model." + k0])
+
+
+def test_backward_base_width_vs_oracle_autograd_on_gpu():
+    """F5TTS_Base widths (D 1024, 16 heads, 64 channels per conv group, text_dim 512, 4 ConvNeXt blocks) at a realistic length: the
+    CTA-pair gradient GEMMs, the attention backward with many key tiles and the grouped-conv weight gradient at the sizes cfg-5 uses.
+    Oracle autograd runs in fp32 on the same GPU."""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig(depth=2)
+    model, sd = build_cfm(cfg, 0)
+    dev = torch.device("cuda", 0)
+    eng = TrainEngine(model)
+    B, n = 2, 700
+    x1, x0, time, text, span = _draws(cfg, B, n, 17)
+    leaf = {k: v.to(dev).clone().float().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    full = {k: v.to(dev) for k, v in sd.items()}
+    full.update(leaf)
+    rope_cpu = O.rotary_freqs
+    O.rotary_freqs = lambda n_, d=64, theta=10000.0: rope_cpu(n_, d, theta).to(dev)
+    try:
+        ref_loss, _, ref_pred = O.cfm_loss(full, cfg, x1.to(dev), text.to(dev), span.to(dev), x0.to(dev), time.to(dev), False, False)
+        ref_loss.backward()
+    finally:
+        O.rotary_freqs = rope_cpu
+    ref = {k: v.grad.cpu() for k, v in leaf.items() if v.grad is not None}
+    eng.zero_grad()
+    loss, cond, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False,
+                                                                               drop_text=False))
+    eng._fold_split_grads()
+    torch.cuda.synchronize()
+    assert maxabs(pred, ref_pred.detach()) <= 2e-2 * max(1.0, float(ref_pred.abs().max()))
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * float(ref_loss)
+    worst = _compare(model, ref)
+    print("worst gradients at Base width (fro err, cos, key):", worst[:4])
