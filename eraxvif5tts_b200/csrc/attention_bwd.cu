@@ -12,7 +12,7 @@
 // layout the tcgen05 A operand wants, and all five products run without a single transposed copy:
 //     S^T  = K   Q^T    A = K   (K-major)   B = Q   (K-major)        TMEM cols   0..127
 //     dP^T = V   dO^T   A = V   (K-major)   B = dO  (K-major)        TMEM cols 128..255
-//     dV  += P^T  dO    A = P^T (K-major)   B = dO  (MN-major)       TMEM cols 256..319   (resident for the whole CTA)
+//     dV  += P^T  dO    A = P^T (TMEM, 448..511) B = dO (MN-major)     TMEM cols 256..319   (resident for the whole CTA)
 //     dK  += dS^T Q     A = dS^T(K-major)   B = Q   (MN-major)       TMEM cols 320..383   (resident)
 //     dQ_j = dS   K     A = dS^T tile read MN-MAJOR, B = K (MN-major)  TMEM cols 384..447 -> fp32 red.add into the dQ workspace
 //   warp 0: TMA producer (K, V once; Q_j, dO_j double-buffered) + per-tile L / delta staging; warp 1: tcgen05.mma issuer;
@@ -30,7 +30,7 @@ constexpr int AB_THREADS = 448;
 constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
 constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
-constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
+constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + AB_PT /*dS^T*/ + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
 constexpr uint32_t AB_TMEM_COLS = 512;
 
 struct AttnBwdParams {
@@ -62,8 +62,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = sK + AB_TILE;
   uint8_t* sQ = sV + AB_TILE;        // 2 stages
   uint8_t* sdO = sQ + 2 * AB_TILE;   // 2 stages
-  uint8_t* sPT = sdO + 2 * AB_TILE;
-  uint8_t* sdST = sPT + AB_PT;
+  uint8_t* sdST = sdO + 2 * AB_TILE;
   uint8_t* sStg = sdST + AB_PT;                         // [8][4096]
   float* sL = reinterpret_cast<float*>(sStg + AB_STG);  // [2][128]
   float* sDl = sL + 2 * AB_T;                          // [2][128]
@@ -131,7 +130,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384,
+                 tm_PT = tmem_base + 448;  // P^T as bf16 pairs: 64 columns = 128 queries (A operand of dV, read from tensor memory)
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------------ producer
@@ -169,7 +169,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t id_acc = idesc_bf16(128, 64, 0, 1);   // dV, dK: B is MN-major
       const uint32_t id_dq = idesc_bf16(128, 64, 1, 1);    // dQ: A (dS^T tile) and B (K) both MN-major
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
-      const uint32_t pt_addr = smem_u32(sPT), ds_addr = smem_u32(sdST);
+      const uint32_t ds_addr = smem_u32(sdST);
       auto issue_sdp = [&](int j) {
         const int st = j & 1;
         mbar_wait(&bar_qdo[st], (j >> 1) & 1);
@@ -206,8 +206,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 queries of the tile, 16 per step
-          const uint32_t aoff = (kk >> 2) * (AB_PT / 2) + (kk & 3) * 32;
-          umma_bf16(tm_dV, smem_desc_sw128(pt_addr + aoff, 1024, 16), smem_desc_sw128(da + kk * 2048, 1024, 8192), id_acc, (j | kk) != 0);
+          // A = P^T from TENSOR MEMORY (lane = key, a K-step of 16 queries = 8 packed columns): no P^T stores / operand reads on the
+          // shared-memory port, which is what bounds this kernel
+          umma_bf16_ts(tm_dV, tm_PT + kk * 8, smem_desc_sw128(da + kk * 2048, 1024, 8192), id_acc, (j | kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -283,7 +284,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int rx = r & 7;
     const bool key_ok = (k0 + r) < kvlen;
     const float c2 = p.scale_log2, sc = p.scale;
-    uint8_t* pt_row = sPT + ch * (AB_PT / 2) + r * 128;
     uint8_t* ds_row = sdST + ch * (AB_PT / 2) + r * 128;
 
     for (int j = 0; j < Tq; ++j) {
@@ -340,9 +340,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int chunk = (q ^ rx) << 4;
-        *reinterpret_cast<uint4*>(pt_row + chunk) = make_uint4(ppk[q * 4], ppk[q * 4 + 1], ppk[q * 4 + 2], ppk[q * 4 + 3]);
         *reinterpret_cast<uint4*>(ds_row + chunk) = make_uint4(dpk[q * 4], dpk[q * 4 + 1], dpk[q * 4 + 2], dpk[q * 4 + 3]);
       }
+      tmem_st32(tm_PT + lane_addr + ch * 32, ppk);  // this thread's 64 probabilities (its key row, its column half)
+      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_pds);
