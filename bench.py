@@ -313,7 +313,11 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     from eraxvif5tts_b200.train import TrainEngine
     L.load()
     model, _ = build_product_models(cfg, dev)
-    eng = TrainEngine(model, with_ema=(rank == 0))  # EMA only on the main process (trainer.py:179-181)
+    train_dropout = float(os.environ.get("F5B_TRAIN_DROPOUT", "0"))  # cfg-5 is quoted at dropout 0 (parity setting); 0.1 = the reference's training default
+    eng = TrainEngine(model, with_ema=(rank == 0), dropout=train_dropout)  # EMA only on the main process (trainer.py:179-181)
+    config["dropout"] = train_dropout
+    if train_dropout > 0:
+        config["workload"] = config["workload"].replace("dropout 0", f"dropout {train_dropout:g} (FeedForward + to_out sites)")
     if world > 1:
         eng.broadcast_params(0)
     g = torch.Generator().manual_seed(1234 + rank)

@@ -33,3 +33,17 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
             int ksize, int mode, cudaStream_t stream);
 
 }  // namespace f5b
+
+// The training drivers' dropout-aware forms of four sweeps (train_kernels.cu).  site 0 = FeedForward's Dropout after GELU
+// (model/modules.py:342-353), site 1 = the Dropout behind attention's to_out (:436-440); the mask is a function of
+// (f5b_train_set_dropout's seed, layer, site, element).  With p = 0 they are the public f5b_* sweeps.
+extern "C" {
+int f5b_act_fwd_site(const void* h_bf16, void* out_bf16, int64_t count, int act, int layer, int site, f5b_stream_t stream);
+int f5b_act_bwd_site(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act, int layer,
+                     int site, f5b_stream_t stream);
+int f5b_gate_add_ln_modulate_site(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                                  float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B,
+                                  int n, int D, float eps, int layer, int site, f5b_stream_t stream);
+int f5b_gate_bwd_site(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                      float* dgate, float* dbias, int B, int n, int C, int layer, int site, f5b_stream_t stream);
+}

@@ -263,10 +263,11 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
     F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s));
     F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
     // x_mid = x_in + gate_msa * mask(z1);  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
-    F5B_TRY(f5b_gate_add_ln_modulate(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D, 1e-6f,
-                                     stream));
+    // (train mode: to_out's Dropout sits between z1 and the gate -- site 1; FeedForward's follows the GELU -- site 0)
+    F5B_TRY(f5b_gate_add_ln_modulate_site(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D,
+                                          1e-6f, i, 1, stream));
     F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
-    F5B_TRY(f5b_act_fwd(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, stream));
+    F5B_TRY(f5b_act_fwd_site(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, i, 0, stream));
     F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
     // x_out = x_mid + gate_mlp * z2;  next AdaLN: block i+1's (shift_msa, scale_msa) or AdaLayerNorm_Final's (scale, shift; :333)
     const float* mn = w.mod + (size_t)(i + 1) * 6 * D;
@@ -320,12 +321,12 @@ static int train_backward_impl(const F5bDit* h, const void* dpred_bf16, const vo
     F5B_TRY(f5b_gate_bwd(w.dx, b.z2, m + 5 * D, mod_dim, nullptr, w.t1, dm + 5 * D, off(g.ff2_b, (size_t)i * D), B, n, D, stream));
     F5B_TRY(wgrad(w.t1, D, b.u, F, off(g.ff2_w, (size_t)i * D * F), F, rows, D, F, stream));
     F5B_TRY(dgrad(w.t1, D, ff2_w + (size_t)i * D * F, F, w.tF, F, rows, D, stream));
-    F5B_TRY(f5b_act_bwd(w.tF, b.h1, w.tF, off(g.ff1_b, (size_t)i * F), rows, F, F, F5B_ACT_GELU_TANH, stream));
+    F5B_TRY(f5b_act_bwd_site(w.tF, b.h1, w.tF, off(g.ff1_b, (size_t)i * F), rows, F, F, F5B_ACT_GELU_TANH, i, 0, stream));
     F5B_TRY(wgrad(w.tF, F, b.f, D, off(g.ff1_w, (size_t)i * F * D), D, rows, F, D, stream));
     F5B_TRY(dgrad(w.tF, F, ff1_w + (size_t)i * F * D, D, w.t1, D, rows, F, stream));
     F5B_TRY(f5b_ln_modulate_bwd(w.t1, b.x_mid, m + 4 * D, mod_dim, w.dx, 1, dm + 4 * D, dm + 3 * D, B, n, D, 1e-6f, stream));
     // ---- x_mid = x_in + gate_msa * mask(Wo attn(rope(Wqkv a + b)) + bo),  a = LN(x_in) (1 + scale_msa) + shift_msa
-    F5B_TRY(f5b_gate_bwd(w.dx, b.z1, m + 2 * D, mod_dim, lens, w.t1, dm + 2 * D, off(g.out_b, (size_t)i * D), B, n, D, stream));
+    F5B_TRY(f5b_gate_bwd_site(w.dx, b.z1, m + 2 * D, mod_dim, lens, w.t1, dm + 2 * D, off(g.out_b, (size_t)i * D), B, n, D, i, 1, stream));
     F5B_TRY(wgrad(w.t1, D, b.o, D, off(g.out_w, (size_t)i * D * D), D, rows, D, D, stream));
     F5B_TRY(dgrad(w.t1, D, out_w + (size_t)i * D * D, D, w.t2, D, rows, D, stream));
     F5B_TRY(attn_bwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, w.t2, D, b.lse, w.delta, w.dq_ws, w.t3, 3 * D, lens, 0, B, H, n, 0.125f,

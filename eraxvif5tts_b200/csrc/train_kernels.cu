@@ -11,6 +11,28 @@ namespace f5b {
 constexpr int CT_ROWS = 64;     // rows per CTA of the column-thread kernels
 constexpr int CT_THREADS = 256; // each thread owns column pairs {2t, 2t+1} + k*512
 
+// Dropout (train mode of the reference's DiT: FeedForward's Dropout after GELU, model/modules.py:342-353, and the Dropout behind
+// attention's to_out, :436-440).  Counter-based: the keep decision of element idx is a pure function of (key, idx), so the backward
+// regenerates the forward's mask instead of storing it.  One splitmix64 hash serves 4 consecutive elements (16 bits each).
+// thr16 == 0 switches it off.  (The dropout inside F.scaled_dot_product_attention, :490, is not built.)
+struct Drop {
+  uint32_t thr16;  // drop if lane bits < thr16 (= p * 65536)
+  float scale;     // 1 / (1 - p)
+  uint64_t key;
+};
+__device__ __forceinline__ uint64_t drop_hash(uint64_t key, uint64_t idx4) {
+  uint64_t z = idx4 * 0x9E3779B97F4A7C15ull + key;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// multipliers (0 or 1/(1-p)) of the 4 consecutive elements starting at element index idx (a multiple of 4)
+__device__ __forceinline__ void drop_mult4(const Drop& d, uint64_t idx, float (&m)[4]) {
+  const uint64_t z = drop_hash(d.key, idx >> 2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m[k] = ((uint32_t)(z >> (16 * k)) & 0xFFFFu) >= d.thr16 ? d.scale : 0.f;
+}
+
 __device__ __forceinline__ float act_eval(int act, float x) {
   if (act == F5B_ACT_GELU_TANH) {
     const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
@@ -72,7 +94,8 @@ __global__ void gate_add_kernel(const float* x, const __nv_bfloat16* __restrict_
 __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
                                                               const float* __restrict__ gate, int64_t gate_bstride,
                                                               const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ dz,
-                                                              float* __restrict__ dgate, float* __restrict__ dbias, int n, int C) {
+                                                              float* __restrict__ dgate, float* __restrict__ dbias, int n, int C,
+                                                              const Drop dr) {
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * CT_ROWS;
   const int p1 = min(n, p0 + CT_ROWS);
@@ -91,7 +114,13 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
       float o[4] = {0.f, 0.f, 0.f, 0.f};
       if (pos < live_end) {
         const float4 d4 = *reinterpret_cast<const float4*>(dx + off);
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        if (dr.thr16) {  // z went through dropout before the gate: d(x_out)/d(z) = gate * mask / (1 - p)
+          float m[4];
+          drop_mult4(dr, off, m);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] *= m[i];
+        }
         if (z != nullptr) {
           const uint2 zz = *reinterpret_cast<const uint2*>(z + off);
           const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.x));
@@ -117,16 +146,24 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
   }
 }
 
-__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n8, int act) {
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n8, int act, const Drop dr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 elements (16-byte accesses)
   if (i >= n8) return;
   const uint4 v = reinterpret_cast<const uint4*>(h)[i];
   const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  if (dr.thr16) {
+    float a[4], c[4];
+    drop_mult4(dr, (uint64_t)i * 8, a);
+    drop_mult4(dr, (uint64_t)i * 8 + 4, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = a[k]; m[4 + k] = c[k]; }
+  }
   uint32_t o[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&in[k]));
-    o[k] = pack_bf16(act_eval(act, f.x), act_eval(act, f.y));
+    o[k] = pack_bf16(act_eval(act, f.x) * m[2 * k], act_eval(act, f.y) * m[2 * k + 1]);
   }
   reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -135,7 +172,7 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat1
 // thread = 4 adjacent columns (8-byte accesses), 64 rows per CTA
 __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16* du, const __nv_bfloat16* __restrict__ h,
                                                              __nv_bfloat16* dh /* may alias du */, float* __restrict__ dbias, int64_t rows,
-                                                             int C, int ld, int act) {
+                                                             int C, int ld, int act, const Drop dr) {
   const int64_t r0 = (int64_t)blockIdx.x * CT_ROWS;
   const int64_t r1 = min(rows, r0 + CT_ROWS);
   for (int c = threadIdx.x * 4; c < C; c += 4 * CT_THREADS) {
@@ -152,6 +189,12 @@ __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16
         const float2 h01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hv.x));
         const float2 h23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hv.y));
         d[0] *= act_grad(act, h01.x); d[1] *= act_grad(act, h01.y); d[2] *= act_grad(act, h23.x); d[3] *= act_grad(act, h23.y);
+        if (dr.thr16) {  // the forward's mask (requires ld == C: the element index is the forward's)
+          float m[4];
+          drop_mult4(dr, off, m);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] *= m[i];
+        }
       }
       if (dh != nullptr) {
         uint2 pk;
@@ -472,7 +515,8 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
                                                           const float* __restrict__ gate, int64_t gate_bstride,
                                                           const int32_t* __restrict__ lens, float* __restrict__ x_out,
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
-                                                          int64_t mod_bstride, __nv_bfloat16* __restrict__ out, int n, int D, float eps) {
+                                                          int64_t mod_bstride, __nv_bfloat16* __restrict__ out, int n, int D, float eps,
+                                                          const Drop dr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int pos = blockIdx.x * 8 + warp;
@@ -496,7 +540,12 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
         const uint2 zz = zr[idx];
         const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.x));
         const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.y));
-        const float4 g = gv ? __ldg(gv + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 g = gv ? __ldg(gv + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (dr.thr16) {
+          float m[4];
+          drop_mult4(dr, (uint64_t)row * D + (uint64_t)idx * 4, m);
+          g.x *= m[0]; g.y *= m[1]; g.z *= m[2]; g.w *= m[3];
+        }
         v[j].x = fmaf(g.x, z01.x, v[j].x); v[j].y = fmaf(g.y, z01.y, v[j].y);
         v[j].z = fmaf(g.z, z23.x, v[j].z); v[j].w = fmaf(g.w, z23.y, v[j].w);
       }
@@ -532,6 +581,18 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
 using namespace f5b;
 #define ST(s) static_cast<cudaStream_t>(s)
 
+namespace f5b {
+static float g_drop_p = 0.f;
+static uint64_t g_drop_seed = 0;
+static Drop drop_off() { return Drop{0u, 1.f, 0ull}; }
+static Drop drop_for(int layer, int site) {
+  if (!(g_drop_p > 0.f)) return drop_off();
+  uint32_t thr = (uint32_t)(g_drop_p * 65536.0f + 0.5f);
+  if (thr > 65535u) thr = 65535u;
+  return Drop{thr, 65536.0f / (65536.0f - (float)thr), g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull};
+}
+}  // namespace f5b
+
 extern "C" {
 
 int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, float* out, int B,
@@ -544,9 +605,9 @@ int f5b_gate_add(const float* x, const void* z_bf16, const float* gate, int64_t 
   return 0;
 }
 
-int f5b_gate_add_ln_modulate(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
-                             float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B, int n,
-                             int D, float eps, f5b_stream_t stream) {
+static int gate_add_ln_launch(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                              float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B, int n,
+                              int D, float eps, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(x && z_bf16 && x_out && scale && shift && out_bf16 && B > 0 && n > 0, "f5b_gate_add_ln_modulate: bad argument");
   F5B_CHECK(D > 0 && (D & 3) == 0 && D <= 1024 && (gate_bstride & 3) == 0 && (mod_bstride & 3) == 0,
             "f5b_gate_add_ln_modulate: D=%d must be a multiple of 4 and <= 1024, strides multiples of 4", D);
@@ -555,42 +616,88 @@ int f5b_gate_add_ln_modulate(const float* x, const void* z_bf16, const float* ga
   auto* zz = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
   auto* oo = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   const int nvec = D / 4;
-  if (nvec <= 64) gate_add_ln_kernel<2><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
-  else if (nvec <= 128) gate_add_ln_kernel<4><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
-  else gate_add_ln_kernel<8><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps);
+  if (nvec <= 64) gate_add_ln_kernel<2><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
+  else if (nvec <= 128) gate_add_ln_kernel<4><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
+  else gate_add_ln_kernel<8><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
 
-int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
-                 float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream) {
+int f5b_gate_add_ln_modulate(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                             float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B, int n,
+                             int D, float eps, f5b_stream_t stream) {
+  return gate_add_ln_launch(x, z_bf16, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, out_bf16, B, n, D, eps, drop_off(), stream);
+}
+
+static int gate_bwd_launch(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                           float* dgate, float* dbias, int B, int n, int C, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 3) == 0 && (gate_bstride & 3) == 0, "f5b_gate_bwd: C and the gate stride must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * B * n * C);
   gate_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), CT_THREADS, 0, ST(stream)>>>(
       dx, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16), dgate, dbias,
-      n, C);
+      n, C, dr);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
+int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                 float* dgate, float* dbias, int B, int n, int C, f5b_stream_t stream) {
+  return gate_bwd_launch(dx, z_bf16, gate, gate_bstride, lens, dz_bf16, dgate, dbias, B, n, C, drop_off(), stream);
+}
 
-int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_stream_t stream) {
+static int act_fwd_launch(const void* h_bf16, void* out_bf16, int64_t count, int act, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(h_bf16 && out_bf16 && count > 0 && (count & 7) == 0, "f5b_act_fwd: count must be a multiple of 8");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * count);
   act_fwd_kernel<<<(unsigned)((count / 8 + 255) / 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16),
-                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 8, act);
+                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 8, act, dr);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
+int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_stream_t stream) {
+  return act_fwd_launch(h_bf16, out_bf16, count, act, drop_off(), stream);
+}
 
-int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
-                f5b_stream_t stream) {
+static int act_bwd_launch(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
+                          const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 3) == 0 && (ld & 3) == 0 && ld >= C, "f5b_act_bwd: C and ld must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * rows * C);
   act_bwd_kernel<<<(unsigned)((rows + CT_ROWS - 1) / CT_ROWS), CT_THREADS, 0, ST(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<__nv_bfloat16*>(dh_bf16),
-      dbias, rows, C, ld, act);
+      dbias, rows, C, ld, act, dr);
   F5B_CUDA(cudaGetLastError());
   return 0;
+}
+int f5b_act_bwd(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
+                f5b_stream_t stream) {
+  return act_bwd_launch(du_bf16, h_bf16, dh_bf16, dbias, rows, C, ld, act, drop_off(), stream);
+}
+
+/* train-mode dropout of the DiT blocks for the f5b_dit_train_* drivers (FeedForward's Dropout after GELU and the Dropout behind
+ * to_out; p = 0 switches it off).  The keep decision is a pure function of (seed, block, site, element): call it once per
+ * optimizer micro-step with a fresh seed, BEFORE f5b_dit_train_forward, and leave it unchanged until the matching backward. */
+int f5b_train_set_dropout(float p, uint64_t seed) {
+  F5B_CHECK(p >= 0.f && p < 1.f, "f5b_train_set_dropout: p must be in [0, 1)");
+  g_drop_p = p;
+  g_drop_seed = seed;
+  return 0;
+}
+/* the training drivers' versions of the four sweeps: site 0 = FeedForward dropout, site 1 = attention-output dropout */
+int f5b_act_fwd_site(const void* h_bf16, void* out_bf16, int64_t count, int act, int layer, int site, f5b_stream_t stream) {
+  return act_fwd_launch(h_bf16, out_bf16, count, act, drop_for(layer, site), stream);
+}
+int f5b_act_bwd_site(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act, int layer,
+                     int site, f5b_stream_t stream) {
+  F5B_CHECK(ld == C || !(g_drop_p > 0.f), "f5b_act_bwd_site: dropout needs a dense [rows, C] tensor");
+  return act_bwd_launch(du_bf16, h_bf16, dh_bf16, dbias, rows, C, ld, act, drop_for(layer, site), stream);
+}
+int f5b_gate_add_ln_modulate_site(const float* x, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens,
+                                  float* x_out, const float* scale, const float* shift, int64_t mod_bstride, void* out_bf16, int B,
+                                  int n, int D, float eps, int layer, int site, f5b_stream_t stream) {
+  return gate_add_ln_launch(x, z_bf16, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, out_bf16, B, n, D, eps,
+                            drop_for(layer, site), stream);
+}
+int f5b_gate_bwd_site(const float* dx, const void* z_bf16, const float* gate, int64_t gate_bstride, const int32_t* lens, void* dz_bf16,
+                      float* dgate, float* dbias, int B, int n, int C, int layer, int site, f5b_stream_t stream) {
+  return gate_bwd_launch(dx, z_bf16, gate, gate_bstride, lens, dz_bf16, dgate, dbias, B, n, C, drop_for(layer, site), stream);
 }
 
 static int ln_bwd_launch(const void* dy_bf16, const float* x, const float* scale, int64_t mod_bstride, float* dx, int accumulate,

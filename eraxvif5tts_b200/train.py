@@ -72,8 +72,12 @@ class TrainEngine:
     """One data-parallel replica of the training step for a `CFM` whose transformer is a `DiT`."""
 
     def __init__(self, cfm, lr: float = 7.5e-5, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0, with_ema=False,
-                 ema_schedule: EmaSchedule | None = None):
+                 ema_schedule: EmaSchedule | None = None, dropout: float = 0.0):
+        """dropout: the DiT's train-mode dropout (the reference builds DiT(dropout=0.1), model/backbones/dit.py:132), applied after
+        FeedForward's GELU and behind attention's to_out (modules.py:342-353, :436-440); SDPA's internal dropout is not built.
+        0 (default) is the setting the gradient-parity tests run at."""
         self.cfm, self.dit = cfm, cfm.transformer
+        self.dropout = float(dropout)
         dit = self.dit
         dev = dit.proj_out.weight.device
         if dev.type != "cuda":
@@ -265,6 +269,9 @@ class TrainEngine:
         ws = self.workspace(nbytes)
         rope = self.rope_table(n)
         pred = torch.empty(B, n, C_, dtype=f32, device=dev)
+        # the dropout masks of this micro-step are a function of this seed; the backward below regenerates them
+        seed = int(draws["dropout_seed"]) if "dropout_seed" in draws else int(torch.randint(0, 2 ** 62, (1,)).item())
+        L.check(lib.f5b_train_set_dropout(self.dropout, seed), "f5b_train_set_dropout")
         # no mask is passed to the transformer in training (cfm.py:275-277)
         L.check(lib.f5b_dit_train_forward(self.handle, phi.data_ptr(), None if drop_audio_cond else cond.data_ptr(), te.data_ptr(),
                                           time.data_ptr(), B, n, None, rope.data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel(), s),

@@ -271,6 +271,13 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
                            void* dtext_bf16, int B, int n, const int32_t* lens, const float* rope, void* ws, size_t ws_bytes,
                            f5b_stream_t stream);
 
+/* Train-mode dropout of the DiT blocks (reference: DiT(dropout=0.1), model/backbones/dit.py:132; FeedForward's Dropout after GELU,
+ * model/modules.py:342-353, and the Dropout behind attention's to_out, :436-440).  p = 0 (the default) switches it off.  The keep
+ * decision is a counter-based hash of (seed, block, site, element) -- the backward regenerates the forward's mask -- so call this
+ * once per micro-step with a fresh seed BEFORE f5b_dit_train_forward and leave it untouched until the matching backward returns.
+ * The dropout inside scaled_dot_product_attention (:490) is not built: the attention kernels always run with p = 0. */
+int f5b_train_set_dropout(float p, uint64_t seed);
+
 /* The same backward in pieces (parts bit 0 = head: proj_out + final AdaLN; bit 1 = blocks [blk_lo, blk_hi) in descending order;
  * bit 2 = tail: input embedding + modulation / time MLP), issued head -> blocks from depth down to 0 -> tail, so the host can start
  * the gradient all-reduce of finished blocks (DDP's bucketed overlap, trainer.py:1280) while earlier blocks are differentiated. */

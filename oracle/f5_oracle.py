@@ -233,8 +233,34 @@ def apply_rotary(t: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
     return (tf * freqs.cos() + rot * freqs.sin()).to(t.dtype)
 
 
-def attention(sd, cfg: DiTConfig, p, x, mask, rope):
-    """AttnProcessor.__call__, model/modules.py:442-503 (dropout_p forced to 0.0; reference :490 says 0.1)."""
+def dropout_multipliers(p: float, seed: int, layer: int, site: int, shape) -> torch.Tensor:
+    """The product's train-mode dropout masks (include/f5b200.h: f5b_train_set_dropout), restated so that autograd through this
+    oracle sees the SAME masks as the CUDA path: torch's nn.Dropout (modules.py:349, :439) draws from Philox, whose stream is an
+    implementation detail no other implementation can reproduce, so the mask generator is the one thing on this path that is
+    defined by the product (a splitmix64 hash of (seed, layer, site, element // 4), 16 bits per element) and only its
+    distribution -- Bernoulli(1 - p) keeps scaled by 1 / (1 - p) -- by the reference.  site 0 = FeedForward's Dropout,
+    site 1 = the Dropout behind to_out.  Returns a float32 tensor of `shape` holding 0 or 1 / (1 - p)."""
+    import numpy as np
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    assert numel % 4 == 0
+    thr = min(65535, int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
+    M = (1 << 64) - 1
+    key = np.uint64((int(seed) * 0xD1342543DE82EF95 + (layer * 8 + site + 1) * 0x9E3779B97F4A7C15) & M)
+    with np.errstate(over="ignore"):
+        z = np.arange(numel // 4, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + key
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    lanes = np.stack([(z >> np.uint64(16 * k)) & np.uint64(0xFFFF) for k in range(4)], axis=1).reshape(-1)
+    scale = np.float32(65536.0) / (np.float32(65536.0) - np.float32(thr))
+    return torch.from_numpy(np.where(lanes >= thr, scale, np.float32(0.0)).astype(np.float32)).reshape(tuple(shape))
+
+
+def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None):
+    """AttnProcessor.__call__, model/modules.py:442-503 (dropout_p forced to 0.0; reference :490 says 0.1).
+    drop: optional callable applied to to_out's result (the Dropout of to_out, :439-440) before the padding mask."""
     b, n, _ = x.shape
     H, d = cfg.heads, cfg.dim_head
     q = F.linear(x, sd[p + "to_q.weight"], sd[p + "to_q.bias"]).view(b, n, H, d).transpose(1, 2)
@@ -249,28 +275,37 @@ def attention(sd, cfg: DiTConfig, p, x, mask, rope):
     o = torch.softmax(s.float(), dim=-1).to(v.dtype) @ v
     o = o.transpose(1, 2).reshape(b, n, H * d)
     o = F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
+    if drop is not None:
+        o = drop(o)
     if mask is not None:
         o = o.masked_fill(~mask.unsqueeze(-1), 0.0)
     return o
 
 
-def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope):
+def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope, dropout=None):
     """DiTBlock.forward, model/modules.py:627-641 with AdaLayerNorm :310-315 (chunk order
-    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) and FeedForward(GELU tanh) :342-353."""
+    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) and FeedForward(GELU tanh) :342-353.
+    dropout: None (eval) or (p, seed) -- train mode with the masks of dropout_multipliers."""
+    def drop(site):
+        if dropout is None or not dropout[0] > 0:
+            return None
+        return lambda a: a * dropout_multipliers(dropout[0], dropout[1], i, site, a.shape).to(a.device)
     p = f"transformer.transformer_blocks.{i}."
     D = cfg.dim
     emb = F.linear(F.silu(t), sd[p + "attn_norm.linear.weight"], sd[p + "attn_norm.linear.bias"])
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = torch.chunk(emb, 6, dim=1)
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_msa[:, None]) + shift_msa[:, None]
-    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope)
+    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope, drop(1))
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
     h = F.gelu(F.linear(h, sd[p + "ff.ff.0.0.weight"], sd[p + "ff.ff.0.0.bias"]), approximate="tanh")
+    if drop(0) is not None:
+        h = drop(0)(h)
     h = F.linear(h, sd[p + "ff.ff.2.weight"], sd[p + "ff.ff.2.bias"])
     return x + gate_mlp.unsqueeze(1) * h
 
 
 def dit_forward(sd, cfg: DiTConfig, x, cond, text, time, drop_audio_cond, drop_text, mask=None,
-                text_embed=None, return_hidden=False):
+                text_embed=None, return_hidden=False, dropout=None):
     """DiT.forward, model/backbones/dit.py:185-233 (final AdaLN chunk order is (scale, shift),
     model/modules.py:331-336)."""
     b, n = x.shape[:2]
@@ -283,7 +318,7 @@ def dit_forward(sd, cfg: DiTConfig, x, cond, text, time, drop_audio_cond, drop_t
     rope = rotary_freqs(n, cfg.dim_head)
     hidden = [h]
     for i in range(cfg.depth):
-        h = dit_block(sd, cfg, i, h, t, mask, rope)
+        h = dit_block(sd, cfg, i, h, t, mask, rope, dropout)
         if return_hidden:
             hidden.append(h)
     emb = F.linear(F.silu(t), sd["transformer.norm_out.linear.weight"], sd["transformer.norm_out.linear.bias"])
@@ -376,12 +411,12 @@ def cfm_sample(sd, cfg: DiTConfig, cond, text, duration, *, lens=None, steps=32,
 # CFM.forward loss (model/cfm.py:210-283), deterministic form: the random draws are arguments
 # --------------------------------------------------------------------------------------
 
-def cfm_loss(sd, cfg: DiTConfig, x1, text, rand_span_mask, x0, time, drop_audio_cond, drop_text):
+def cfm_loss(sd, cfg: DiTConfig, x1, text, rand_span_mask, x0, time, drop_audio_cond, drop_text, dropout=None):
     t = time[:, None, None]
     phi = (1 - t) * x0 + t * x1
     flow = x1 - x0
     cond = torch.where(rand_span_mask[..., None], torch.zeros_like(x1), x1)
-    pred = dit_forward(sd, cfg, phi, cond, text, time, drop_audio_cond, drop_text, mask=None)
+    pred = dit_forward(sd, cfg, phi, cond, text, time, drop_audio_cond, drop_text, mask=None, dropout=dropout)
     loss = F.mse_loss(pred, flow, reduction="none")[rand_span_mask]
     return loss.mean(), cond, pred
 

@@ -26,11 +26,11 @@ def _draws(cfg, B, n, seed):
     return x1, x0, time, text, span
 
 
-def _oracle_grads(sd, cfg, x1, text, span, x0, time, da, dt):
+def _oracle_grads(sd, cfg, x1, text, span, x0, time, da, dt, dropout=None):
     leaf = {k: v.clone().float().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
     full = dict(sd)
     full.update(leaf)
-    loss, _, pred = O.cfm_loss(full, cfg, x1, text, span, x0, time, da, dt)
+    loss, _, pred = O.cfm_loss(full, cfg, x1, text, span, x0, time, da, dt, dropout=dropout)
     loss.backward()
     return float(loss), pred.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}
 
@@ -80,6 +80,47 @@ def test_backward_vs_oracle_autograd(da, dt):
     assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
     worst = _compare(model, ref)
     print("worst gradients (fro err, cos, key):", worst[:5])
+
+
+def test_backward_with_dropout_vs_oracle_autograd():
+    """train-mode dropout (p = 0.1 as the reference trains, and a heavy p = 0.5): the oracle applies the SAME masks
+    (oracle.dropout_multipliers restates the product's counter-based generator), so forward, loss and every gradient are judged
+    at the bars of the p = 0 test; the same seed reproduces the step, another seed changes it, and p = 0 is the
+    eval-mode forward."""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig.tiny()
+    B, n = 3, 152
+    x1, x0, time, text, span = _draws(cfg, B, n, 21)
+    base = dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False, drop_text=False)
+    preds = {}
+    for p, seed in ((0.1, 1234), (0.5, 99)):
+        model, sd = build_cfm(cfg, 0)
+        eng = TrainEngine(model, dropout=p)
+        ref_loss, ref_pred, ref = _oracle_grads(sd, cfg, x1, text, span, x0, time, False, False, dropout=(p, seed))
+        eng.zero_grad()
+        loss, _, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=seed))
+        eng._fold_split_grads()
+        torch.cuda.synchronize()
+        assert maxabs(pred, ref_pred) <= 2e-2
+        assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+        _compare(model, ref)
+        g1 = eng.g.clone()
+        eng.zero_grad()
+        _, _, pred2 = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=seed))
+        eng._fold_split_grads()
+        # same seed, same masks: the forward repeats bit for bit; the backward's split-K / reduce-add sums are order-dependent
+        assert torch.equal(pred, pred2)
+        assert float((g1 - eng.g).norm()) <= 1e-3 * float(g1.norm())
+        _, _, pred3 = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=seed + 1))
+        assert maxabs(pred3, pred) > 1e-3
+        preds[p] = pred
+    # the masks matter (the p = 0.5 forward is far from the eval forward) and p = 0 is exactly the eval forward
+    model, sd = build_cfm(cfg, 0)
+    e0 = TrainEngine(model, dropout=0.0)
+    _, _, pa = e0.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=1))
+    _, _, pb = e0.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=2))
+    assert torch.equal(pa, pb)
+    assert maxabs(preds[0.5], pa) > 1e-2
 
 
 def test_gradient_accumulation_and_step_changes_loss():

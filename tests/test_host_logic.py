@@ -328,3 +328,20 @@ def test_dynamic_batch_sampler_and_collate():
     if ref is not None:
         r = ref.collate_fn(items)
         assert torch.equal(r["mel"], a["mel"]) and torch.equal(r["mel_lengths"], a["mel_lengths"]) and r["text"] == a["text"]
+
+
+def test_dropout_mask_statistics():
+    """keep rate of the generator the kernels and the oracle share: Bernoulli(1 - p) per element, kept values scaled by 1 / (1 - p),
+    no visible correlation between sites / layers / neighbouring elements"""
+    from oracle import f5_oracle as _O
+    for p in (0.1, 0.5):
+        a = _O.dropout_multipliers(p, 7, 3, 0, (64, 4096))
+        b = _O.dropout_multipliers(p, 7, 3, 1, (64, 4096))
+        keep_a, keep_b = (a > 0).float(), (b > 0).float()
+        assert abs(float(keep_a.mean()) - (1 - p)) < 3e-3
+        assert abs(float(a.mean()) - 1.0) < 6e-3
+        assert float(a.max()) == pytest.approx(1 / (1 - p), rel=1e-4)
+        both = float((keep_a * keep_b).mean())
+        assert abs(both - (1 - p) ** 2) < 4e-3
+        nb = float((keep_a[:, 1:] * keep_a[:, :-1]).mean())
+        assert abs(nb - (1 - p) ** 2) < 4e-3
