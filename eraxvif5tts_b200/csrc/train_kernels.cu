@@ -345,6 +345,64 @@ __global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __r
   out[i] = __float2bfloat16(v);
 }
 
+// ---- distillation losses (train/distil_reload.py:1066-1093): with m = rand_span_mask [rows], cnt = max(sum m, 1) FRAMES (the
+// channel axis is summed, not averaged -- unlike CFM.forward's loss):
+//   student = sum m (p - flow)^2 / cnt;  distill = sum m (p - T)^2 / cnt  (or |p - T| for "l1");  spec_l1 = sum m |p - T| / cnt
+//   total = (1 - alpha) student + alpha distill + w spec_l1        (T = the teacher's prediction, detached)
+__global__ void __launch_bounds__(256) distill_loss_partial_kernel(const float* __restrict__ pred, const float* __restrict__ flow,
+                                                                   const float* __restrict__ teacher, const uint8_t* __restrict__ mask,
+                                                                   float* __restrict__ partial, int rows, int C) {
+  __shared__ float red[3][8];
+  float s = 0.f, d2 = 0.f, d1 = 0.f, cnt = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    if (!mask[r]) continue;  // block-uniform
+    if (threadIdx.x == 0) cnt += 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float p = pred[(size_t)r * C + c];
+      const float a = p - flow[(size_t)r * C + c], b = p - teacher[(size_t)r * C + c];
+      s += a * a;
+      d2 += b * b;
+      d1 += fabsf(b);
+    }
+  }
+  s = warp_sum(s); d2 = warp_sum(d2); d1 = warp_sum(d1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = d2; red[2][threadIdx.x >> 5] = d1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; c += red[2][i]; }
+    partial[blockIdx.x * 4] = a; partial[blockIdx.x * 4 + 1] = b; partial[blockIdx.x * 4 + 2] = c; partial[blockIdx.x * 4 + 3] = cnt;
+  }
+}
+// out5 = (total, student, distill, spec_l1, cnt)
+__global__ void distill_loss_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ out, int l1, float alpha, float w) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0, n = 0.0;  // fixed summation order: deterministic
+    for (int i = 0; i < nblk; ++i) { a += partial[4 * i]; b += partial[4 * i + 1]; c += partial[4 * i + 2]; n += partial[4 * i + 3]; }
+    const double cnt = n > 1.0 ? n : 1.0;
+    const double student = a / cnt, distill = (l1 ? c : b) / cnt, spec = w > 0.f ? c / cnt : 0.0;
+    out[0] = (float)((1.0 - alpha) * student + alpha * distill + w * spec);
+    out[1] = (float)student; out[2] = (float)distill; out[3] = (float)spec; out[4] = (float)cnt;
+  }
+}
+// d total / d pred, bf16 [rows, ld] zero padded
+__global__ void distill_grad_kernel(const float* __restrict__ pred, const float* __restrict__ flow, const float* __restrict__ teacher,
+                                    const uint8_t* __restrict__ mask, const float* __restrict__ out5, __nv_bfloat16* __restrict__ out,
+                                    int64_t rows, int C, int ld, int l1, float alpha, float w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t r = i / ld;
+  const int c = (int)(i - r * ld);
+  float v = 0.f;
+  if (c < C && mask[r]) {
+    const float p = pred[r * C + c];
+    const float a = p - flow[r * C + c], b = p - teacher[r * C + c];
+    const float sg = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
+    v = ((1.f - alpha) * 2.f * a + alpha * (l1 ? sg : 2.f * b) + w * sg) / out5[4];
+  }
+  out[i] = __float2bfloat16(v);
+}
+
 // ---- GRN backward (model/modules.py:225-234) fused with the GELU(erf) backward in front of it (ConvNeXtV2Block :263-265) ----
 // t3 = gamma * t2 * nx + beta + t2,  nx[b,c] = gx[b,c] / (mean_c gx[b,:] + 1e-6),  gx[b,c] = ||t2[b,:,c]||_2,  t2 = gelu(p1)
 // stats[b][0..2][C]: pass 1 writes (sum t2^2, sum dt3*t2, sum dt3); the per-batch-row kernel turns them into (mult, coef):
@@ -775,6 +833,27 @@ int f5b_mse_grad(const float* pred, const float* flow, const uint8_t* mask, cons
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * rows * C + 2.0 * rows * ld);
   mse_grad_kernel<<<(unsigned)((rows * ld + 255) / 256), 256, 0, ST(stream)>>>(pred, flow, mask, loss2, reinterpret_cast<__nv_bfloat16*>(out_bf16),
                                                                                rows, C, ld);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_distill_loss(const float* pred, const float* flow, const float* teacher, const uint8_t* mask, float* ws /*[4*1024]*/, float* out5,
+                     int rows, int C, int l1, float alpha, float spec_l1_weight, f5b_stream_t stream) {
+  F5B_CHECK(pred && flow && teacher && mask && ws && out5 && rows > 0 && C > 0, "f5b_distill_loss: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * rows * C);
+  const int nblk = rows < 1024 ? rows : 1024;
+  distill_loss_partial_kernel<<<nblk, 256, 0, ST(stream)>>>(pred, flow, teacher, mask, ws, rows, C);
+  F5B_CUDA(cudaGetLastError());
+  distill_loss_final_kernel<<<1, 32, 0, ST(stream)>>>(ws, nblk, out5, l1, alpha, spec_l1_weight);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+int f5b_distill_grad(const float* pred, const float* flow, const float* teacher, const uint8_t* mask, const float* out5, void* out_bf16,
+                     int64_t rows, int C, int ld, int l1, float alpha, float spec_l1_weight, f5b_stream_t stream) {
+  F5B_CHECK(pred && flow && teacher && mask && out5 && out_bf16 && rows > 0 && C > 0 && ld >= C, "f5b_distill_grad: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * rows * C + 2.0 * rows * ld);
+  distill_grad_kernel<<<(unsigned)((rows * ld + 255) / 256), 256, 0, ST(stream)>>>(
+      pred, flow, teacher, mask, out5, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, C, ld, l1, alpha, spec_l1_weight);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

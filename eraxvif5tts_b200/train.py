@@ -78,6 +78,7 @@ class TrainEngine:
         0 (default) is the setting the gradient-parity tests run at."""
         self.cfm, self.dit = cfm, cfm.transformer
         self.dropout = float(dropout)
+        self.last_losses = None
         dit = self.dit
         dev = dit.proj_out.weight.device
         if dev.type != "cuda":
@@ -217,13 +218,18 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------------ forward + backward
     @torch.no_grad()
     def loss_and_grads(self, inp, text, *, lens=None, draws: dict | None = None, overlap_allreduce: bool = False, group=None,
-                       buckets: int = 4):
+                       buckets: int = 4, distill: dict | None = None):
         """CFM.forward (cfm.py:210-283) followed by loss.backward(): returns (loss, cond, pred) and ACCUMULATES d loss / d theta into
         the flat gradient buffer (= every parameter's .grad).  `draws` fixes the random choices (rand_span_mask, x0, time,
         drop_audio_cond, drop_text) for parity tests.
         overlap_allreduce (use on the LAST micro-batch of an update, world > 1): the backward is issued in `buckets` groups of blocks
         from the top of the network down, and the NCCL all-reduce of each group's finished gradient segments is launched while the
-        groups below are still being differentiated (DDP's bucketed overlap); `allreduce_grads()` then only waits."""
+        groups below are still being differentiated (DDP's bucketed overlap); `allreduce_grads()` then only waits.
+        distill = dict(teacher=<CFM or DiT>, alpha=0.5, loss_type="mse" | "l1", spec_l1_weight=0.0): the distillation step of
+        train/distil_reload.py:1044-1093 in one launch sequence -- the frozen teacher's inference forward (always conditioned:
+        drop_audio_cond = drop_text = False) on the same (x_t, cond, text, time), then the student's train forward, and
+        total = (1 - alpha) student + alpha distill + spec_l1_weight spec_l1 differentiated w.r.t. the student.  Returns the total
+        loss; `self.last_losses` holds the device tensor (total, student, distill, spec_l1, masked frames)."""
         from .model.utils import exists, lens_to_mask, list_str_to_idx, list_str_to_tensor, mask_from_frac_lengths
         cfm, lib, dev = self.cfm, self.lib, self.device
         inp = inp.to(dev)
@@ -276,13 +282,30 @@ class TrainEngine:
         L.check(lib.f5b_dit_train_forward(self.handle, phi.data_ptr(), None if drop_audio_cond else cond.data_ptr(), te.data_ptr(),
                                           time.data_ptr(), B, n, None, rope.data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel(), s),
                 "f5b_dit_train_forward")
-        red = torch.empty(2048, dtype=f32, device=dev)
-        out2 = torch.empty(2, dtype=f32, device=dev)
-        L.check(lib.f5b_masked_mse(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), red.data_ptr(), out2.data_ptr(), B * n, C_, s),
-                "f5b_masked_mse")
         dpred = torch.empty(B * n, 128, dtype=bf16, device=dev)
-        L.check(lib.f5b_mse_grad(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), out2.data_ptr(), dpred.data_ptr(), B * n, C_, 128, s),
-                "f5b_mse_grad")
+        if distill is None:
+            red = torch.empty(2048, dtype=f32, device=dev)
+            out2 = torch.empty(2, dtype=f32, device=dev)
+            L.check(lib.f5b_masked_mse(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), red.data_ptr(), out2.data_ptr(), B * n, C_, s),
+                    "f5b_masked_mse")
+            L.check(lib.f5b_mse_grad(pred.data_ptr(), flow.data_ptr(), span_u8.data_ptr(), out2.data_ptr(), dpred.data_ptr(), B * n, C_, 128,
+                                     s), "f5b_mse_grad")
+            self.last_losses = out2
+        else:
+            teacher = distill["teacher"]
+            teacher = getattr(teacher, "transformer", teacher)
+            kind = distill.get("loss_type", "mse")
+            if kind not in ("mse", "l1"):
+                raise ValueError(f"Unsupported distill_loss_type: {kind}")  # distil_reload.py:1077
+            alpha, w = float(distill.get("alpha", 0.5)), float(distill.get("spec_l1_weight", 0.0))
+            tpred = teacher(x=phi, cond=cond, text=text, time=time, drop_audio_cond=False, drop_text=False).to(f32).contiguous()
+            red = torch.empty(4096, dtype=f32, device=dev)
+            out2 = torch.empty(5, dtype=f32, device=dev)
+            L.check(lib.f5b_distill_loss(pred.data_ptr(), flow.data_ptr(), tpred.data_ptr(), span_u8.data_ptr(), red.data_ptr(),
+                                         out2.data_ptr(), B * n, C_, int(kind == "l1"), alpha, w, s), "f5b_distill_loss")
+            L.check(lib.f5b_distill_grad(pred.data_ptr(), flow.data_ptr(), tpred.data_ptr(), span_u8.data_ptr(), out2.data_ptr(),
+                                         dpred.data_ptr(), B * n, C_, 128, int(kind == "l1"), alpha, w, s), "f5b_distill_grad")
+            self.last_losses = out2
         dtext = torch.empty(B * n, self.T, dtype=bf16, device=dev)
         import torch.distributed as dist
         overlap = overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1

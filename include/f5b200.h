@@ -355,6 +355,17 @@ int f5b_ln_modulate_bwd(const void* dy_bf16, const float* x, const float* scale,
 int f5b_mse_grad(const float* pred, const float* flow, const uint8_t* mask, const float* loss2, void* out_bf16, int64_t rows, int C,
                  int ld, f5b_stream_t stream);
 
+/* Distillation losses, train/distil_reload.py:1066-1093 (teacher prediction T detached; m = rand_span_mask; cnt = max(sum m, 1)
+ * FRAMES -- the channel axis is summed, unlike CFM.forward's mean): student = sum m (p - flow)^2 / cnt; distill = sum m (p - T)^2 / cnt
+ * (l1 != 0: sum m |p - T| / cnt); spec_l1 = sum m |p - T| / cnt when spec_l1_weight > 0, else 0;
+ * total = (1 - alpha) student + alpha distill + spec_l1_weight spec_l1.  out5 = (total, student, distill, spec_l1, cnt).
+ * ws: 4 * 1024 floats.  f5b_distill_grad writes d total / d pred as bf16 [rows, ld] (columns >= C zero), the input of
+ * f5b_dit_train_backward. */
+int f5b_distill_loss(const float* pred, const float* flow, const float* teacher, const uint8_t* mask, float* ws, float* out5, int rows,
+                     int C, int l1, float alpha, float spec_l1_weight, f5b_stream_t stream);
+int f5b_distill_grad(const float* pred, const float* flow, const float* teacher, const uint8_t* mask, const float* out5, void* out_bf16,
+                     int64_t rows, int C, int ld, int l1, float alpha, float spec_l1_weight, f5b_stream_t stream);
+
 /* ---- optimizer step (trainer.py:1280-1287, 1321): clip_grad_norm_ + torch.optim.AdamW + EMA lerp, one fused pass ------------
  * f5b_grad_sumsq: out[0] = sum(g^2) over a flat f32 gradient buffer (deterministic two-pass; ws f32 [1024]).
  * f5b_adamw_ema_step over flat f32 buffers p, g, m, v (+ optional ema, + optional bf16 copy of the new p):

@@ -421,6 +421,34 @@ def cfm_loss(sd, cfg: DiTConfig, x1, text, rand_span_mask, x0, time, drop_audio_
     return loss.mean(), cond, pred
 
 
+def distill_losses(student_sd, student_cfg: DiTConfig, teacher_sd, teacher_cfg: DiTConfig, x1, text, rand_span_mask, x0, time,
+                   drop_audio_cond, drop_text, alpha=0.5, loss_type="mse", spec_l1_weight=0.0, dropout=None):
+    """One distillation step's losses, train/distil_reload.py:1044-1093 (the step is inline in that script's loop, not a function,
+    so this restatement is checked by reading, not by calling the reference): teacher forward without gradient and always
+    conditioned (:1054-1057), student forward with the CFG drops (:1060-1065), and -- unlike CFM.forward -- losses summed over
+    channels and divided by the number of masked FRAMES (:1069-1071, :1092-1093).  Returns (total, student, distill, spec_l1, pred)."""
+    t = time[:, None, None]
+    xt = (1 - t) * x0 + t * x1
+    flow = x1 - x0
+    cond = torch.where(rand_span_mask[..., None], torch.zeros_like(x1), x1)
+    with torch.no_grad():
+        teacher = dit_forward(teacher_sd, teacher_cfg, xt, cond, text, time, False, False, mask=None)
+    pred = dit_forward(student_sd, student_cfg, xt, cond, text, time, drop_audio_cond, drop_text, mask=None, dropout=dropout)
+    m = rand_span_mask.unsqueeze(-1)
+    cnt = rand_span_mask.sum().clamp(min=1)
+    student = (F.mse_loss(pred, flow, reduction="none") * m).sum() / cnt
+    if loss_type == "mse":
+        full = F.mse_loss(pred, teacher, reduction="none")
+    elif loss_type == "l1":
+        full = F.l1_loss(pred, teacher, reduction="none")
+    else:
+        raise ValueError(f"Unsupported distill_loss_type: {loss_type}")
+    distill = (full * m).sum() / cnt
+    spec = (F.l1_loss(pred, teacher, reduction="none") * m).sum() / cnt if spec_l1_weight > 0 else torch.zeros(())
+    total = (1.0 - alpha) * student + alpha * distill + spec * spec_l1_weight
+    return total, student, distill, spec, pred
+
+
 # --------------------------------------------------------------------------------------
 # Vocos (third-party package `vocos`, config charactr/vocos-mel-24khz; SURVEY.md §9.B; unpinned)
 # --------------------------------------------------------------------------------------

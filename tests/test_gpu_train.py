@@ -123,6 +123,41 @@ def test_backward_with_dropout_vs_oracle_autograd():
     assert maxabs(preds[0.5], pa) > 1e-2
 
 
+@pytest.mark.parametrize("kind,w,da,dt", [("mse", 0.0, False, False), ("l1", 0.0, True, True), ("mse", 0.3, True, False)])
+def test_distillation_step_vs_oracle_autograd(kind, w, da, dt):
+    """train/distil_reload.py:1044-1093: frozen deeper teacher + pruned student in one launch sequence; the four losses and every
+    student gradient against autograd through the oracle's restatement (same bars as the plain training step)."""
+    from eraxvif5tts_b200.train import TrainEngine
+    tcfg, scfg = O.DiTConfig.tiny(depth=3), O.DiTConfig.tiny()
+    teacher, tsd = build_cfm(tcfg, 5)
+    student, ssd = build_cfm(scfg, 0)
+    eng = TrainEngine(student)
+    B, n = 3, 136
+    x1, x0, time, text, span = _draws(scfg, B, n, 31)
+    leaf = {k: v.clone().float().requires_grad_(True) for k, v in ssd.items() if v.is_floating_point()}
+    full = dict(ssd)
+    full.update(leaf)
+    total, st, di, sp, ref_pred = O.distill_losses(full, scfg, tsd, tcfg, x1, text, span, x0, time, da, dt, alpha=0.4, loss_type=kind,
+                                                   spec_l1_weight=w)
+    total.backward()
+    ref = {k: v.grad for k, v in leaf.items() if v.grad is not None}
+    eng.zero_grad()
+    loss, _, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=da,
+                                                                            drop_text=dt),
+                                       distill=dict(teacher=teacher, alpha=0.4, loss_type=kind, spec_l1_weight=w))
+    eng._fold_split_grads()
+    torch.cuda.synchronize()
+    got = eng.last_losses.cpu()
+    assert maxabs(pred, ref_pred.detach()) <= 2e-2
+    for g, r in zip(got[:4], (total, st, di, sp)):
+        assert abs(float(g) - float(r)) <= 2e-2 * abs(float(r)) + 1e-6, (got, float(total), float(st), float(di), float(sp))
+    assert float(got[4]) == float(span.sum())
+    assert float(loss) == float(got[0])
+    # the l1 terms' gradient is sign(p - T): where |p - T| is within the bf16 forward noise the sign is a coin flip, so those
+    # runs get a wider Frobenius bar on top of the cosine check
+    _compare(student, ref, fro_tol=4e-2 if kind == "mse" and w == 0 else 0.12, cos_tol=0.999 if kind == "mse" and w == 0 else 0.992)
+
+
 def test_gradient_accumulation_and_step_changes_loss():
     """two backward passes accumulate; a few fused AdamW steps on one batch drive the loss down (end-to-end sanity of the step)"""
     from eraxvif5tts_b200.train import TrainEngine
