@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libf5b200.so")
-UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_ts", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "models"]
+UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_ts", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -388,6 +388,27 @@ int f5b_prof_enabled(void);
 /* add per-kind (launches, unused, flops, bytes) — used when a captured CUDA graph is replayed */
 void f5b_prof_add(const double* delta, int n_kinds);
 
+/* ---- monotonic alignment search + duration predictor (the duration side of train/distil_reload.py) ---- */
+
+/* viterbi_vectorized_alignment, model/alignment_utils.py:154-212.  sim fp32 [B, nt, T] (token x frame similarity) -> align fp32
+ * [B, nt, T] of 0 / 1 (bit-exact: the recurrence path[n,t] = sim[n,t] + max(path[n-1,t], path[n,t-1]) and the backtracking rule
+ * "segment of token n starts at the last j < curr with path[n,j+1] - path[n,j] > 0" use the reference's fp32 operations).
+ * path_ws: fp32 [B, nt, T] scratch that holds path_prob on return.  durations (optional): int32 [B, nt] = align.sum(-1)
+ * (get_durations_from_alignment, :123-133). */
+int f5b_align_viterbi(const float* sim, float* path_ws, float* align, int32_t* durations, int B, int nt, int T, f5b_stream_t stream);
+/* windowed_monotonic_alignment, model/alignment_utils.py:214-257; window = max(2, int(T * window_size)) computed by the caller.
+ * err int32 [B]: set to 1 for a batch item whose search window came out empty (the reference's torch.argmax raises there). */
+int f5b_align_window(const float* sim, float* align, int32_t* durations, int32_t* err, int B, int nt, int T, int window,
+                     f5b_stream_t stream);
+/* DurationPredictor.forward / .phoneme_forward in eval mode, model/duration_predictor.py:27-66 (g = None): embedding of
+ * ids + id_shift (1 for text tokens padded with -1, 0 for phoneme indices) -> * mask -> Conv1d(Cin, F, k) -> ReLU -> GroupNorm(1, F)
+ * -> * mask -> Conv1d(F, F, k) -> ReLU -> GroupNorm(1, F) -> * mask -> Conv1d(F, 1, 1) -> * mask.  All fp32, nn.Conv1d weight
+ * layouts [out, in, k]; ids int64 [B, nt]; mask fp32 [B, nt]; h1_ws fp32 [B, nt, F]; out fp32 [B, nt] (= the reference's [B, 1, nt]). */
+int f5b_duration_predictor(const int64_t* ids, int id_shift, const float* mask, const float* table, int vocab_rows, const float* conv1_w,
+                           const float* conv1_b, const float* norm1_w, const float* norm1_b, const float* conv2_w, const float* conv2_b,
+                           const float* norm2_w, const float* norm2_b, const float* proj_w, const float* proj_b, float* h1_ws, float* out,
+                           int B, int nt, int Cin, int F, int ksize, f5b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

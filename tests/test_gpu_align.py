@@ -1,0 +1,94 @@
+"""GPU alignment search + duration predictor (csrc/align.cu) through the reference-named Python API, against the oracle and the
+reference-generated golden outputs.  Alignments are index work: bit-exact.  The predictor is fp32: 1e-4 absolute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import align_oracle as A
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "align_golden.pt")
+
+
+def test_golden_cases_bit_exact():
+    from eraxvif5tts_b200.model import alignment_utils as U
+    gold = torch.load(GOLD)
+    for c in gold["cases"]:
+        sim = c["sim"].cuda()
+        al, dur = U.viterbi_vectorized_alignment(sim, return_durations=True)
+        assert torch.equal(al.cpu(), c["viterbi"]), tuple(sim.shape)
+        assert torch.equal(dur.cpu().long(), c["viterbi"].sum(-1).long())
+        assert torch.equal(U.get_durations_from_alignment(al).cpu(), c["viterbi"].sum(-1))
+        if c["window"] is not None:
+            aw = U.monotonic_alignment_search(sim, algorithm="window")
+            assert torch.equal(aw.cpu(), c["window"]), tuple(sim.shape)
+        assert torch.equal(U.monotonic_alignment_search(sim).cpu(), c["viterbi"])
+
+
+@pytest.mark.parametrize("b,nt,T,kind", [(3, 37, 410, "randn"), (2, 150, 1200, "band"), (1, 1100, 48, "randn"), (2, 64, 64, "pos"),
+                                        (1, 300, 30, "randn"), (2, 1, 17, "randn"), (1, 5, 1, "randn")])
+def test_against_oracle(b, nt, T, kind):
+    from eraxvif5tts_b200.model import alignment_utils as U
+    g = torch.Generator().manual_seed(b * 1000 + nt + T)
+    sim = torch.randn(b, nt, T, generator=g)
+    if kind == "pos":
+        sim = sim.abs()
+    if kind == "band":
+        n_idx = torch.arange(nt)[:, None].float() / nt
+        t_idx = torch.arange(T)[None, :].float() / T
+        sim = 3.0 * torch.exp(-((n_idx - t_idx) ** 2) * 200.0)[None] + 0.3 * sim
+    ref_al, ref_dur = A.viterbi_alignment(sim.numpy())
+    al, dur = U.viterbi_vectorized_alignment(sim.cuda(), return_durations=True)
+    assert np.array_equal(al.cpu().numpy(), ref_al)
+    assert np.array_equal(dur.cpu().numpy(), ref_dur)
+    try:
+        ref_w, ref_wd = A.windowed_alignment(sim.numpy())
+    except IndexError:
+        with pytest.raises(IndexError):
+            U.windowed_monotonic_alignment(sim.cuda())
+    else:
+        aw, dw = U.windowed_monotonic_alignment(sim.cuda(), return_durations=True)
+        assert np.array_equal(aw.cpu().numpy(), ref_w)
+        assert np.array_equal(dw.cpu().numpy(), ref_wd)
+
+
+def test_path_prob_bit_exact_and_dtype_preserved():
+    from eraxvif5tts_b200 import _lib as L
+    sim = torch.randn(2, 40, 333, generator=torch.Generator().manual_seed(5))
+    d = sim.cuda()
+    path, al = torch.empty_like(d), torch.empty_like(d)
+    L.check(L.load().f5b_align_viterbi(d.data_ptr(), path.data_ptr(), al.data_ptr(), None, 2, 40, 333, L.stream()), "viterbi")
+    assert np.array_equal(path.cpu().numpy(), A.viterbi_path_prob(sim.numpy()))
+    from eraxvif5tts_b200.model import alignment_utils as U
+    assert U.viterbi_vectorized_alignment(d.half()).dtype == torch.float16
+    with pytest.raises(ValueError):
+        U.monotonic_alignment_search(d, algorithm="nope")
+    with pytest.raises(L.F5bError):
+        U.viterbi_vectorized_alignment(sim)  # CPU tensor: no fallback
+
+
+def test_duration_predictor_golden_and_oracle():
+    from eraxvif5tts_b200.model import DurationPredictor
+    d = torch.load(GOLD)["dp"]
+    dp = DurationPredictor(*d["args"])
+    dp.load_state_dict(d["state_dict"])
+    dp = dp.cuda().eval()
+    out = dp(d["ids"].cuda(), d["mask"].cuda())
+    assert out.shape == d["out"].shape
+    assert float((out.cpu() - d["out"]).abs().max()) <= 1e-4
+    pout = dp.phoneme_forward((d["ids"] + 1).cuda(), d["mask"].cuda())
+    assert float((pout.cpu() - d["phoneme_out"]).abs().max()) <= 1e-4
+    # the wrapper's configuration (f5tts_wrapper-dur_pred.py:196): DurationPredictor(vocab, 512, 32, 3, 0.5), longer text
+    torch.manual_seed(3)
+    big = DurationPredictor(2545, 512, 32, 3, 0.5).eval()
+    ids = torch.randint(0, 2545, (4, 300))
+    lens = torch.tensor([300, 257, 31, 2])
+    mask = (torch.arange(300)[None] < lens[:, None]).int()
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, -1))
+    ref = A.duration_predictor(big.state_dict(), ids, mask, 1)
+    got = big.cuda()(ids.cuda(), mask.cuda())
+    assert float((got.cpu() - ref).abs().max()) <= 1e-4
+    with pytest.raises(NotImplementedError):
+        big.train()(ids.cuda(), mask.cuda())
