@@ -19,8 +19,9 @@ __global__ void __launch_bounds__(VT_THREADS) viterbi_forward_kernel(const float
   const int b = blockIdx.x, i = threadIdx.x;
   const float* S = sim + (size_t)b * nt * T;
   float* P = path + (size_t)b * nt * T;
-  for (int r0 = 0; r0 < nt; r0 += VT_THREADS) {
-    const int rows = min(VT_THREADS, nt - r0);
+  const int chunk = blockDim.x;  // rows swept together (<= VT_THREADS)
+  for (int r0 = 0; r0 < nt; r0 += chunk) {
+    const int rows = min(chunk, nt - r0);
     const int n = r0 + i;
     const bool mine = i < rows;
     float left = 0.f;
@@ -254,7 +255,8 @@ int f5b_align_viterbi(const float* sim, float* path_ws, float* align, int32_t* d
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 16.0 * B * nt * T);
   F5B_CUDA(cudaMemsetAsync(align, 0, sizeof(float) * (size_t)B * nt * T, ST(stream)));
   if (durations) F5B_CUDA(cudaMemsetAsync(durations, 0, sizeof(int32_t) * (size_t)B * nt, ST(stream)));
-  viterbi_forward_kernel<<<B, VT_THREADS, 0, ST(stream)>>>(sim, path_ws, nt, T);
+  const int threads = nt >= VT_THREADS ? VT_THREADS : (nt + 31) / 32 * 32;  // fewer warps = cheaper per-diagonal barrier
+  viterbi_forward_kernel<<<B, threads, 0, ST(stream)>>>(sim, path_ws, nt, T);
   F5B_CUDA(cudaGetLastError());
   viterbi_backtrack_kernel<<<B, 256, 0, ST(stream)>>>(path_ws, align, durations, nt, T);
   F5B_CUDA(cudaGetLastError());
