@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the F5-TTS hot path (BASELINE.json: mel-frames/s and RTF, F5TTS_Base, NFE=32, CFG).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg3d18|cfg5|cfg5b] [--ragged]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" = one full pass of the hot path over one batch of synthetic utterances: CFM.sample (text embedding, 32 Euler steps x
@@ -33,9 +33,12 @@ WORKLOADS = {
     "cfg2": (dict(dim=1024, depth=22, heads=16), 16, 563, 1875, "F5TTS_Base bf16 batch=16 x 20 s utterances (ref 6 s + gen 14 s), NFE=32 sway -1 CFG 2"),
     "cfg1": (dict(dim=1024, depth=22, heads=16), 1, 376, 940, "F5TTS_Base one ~10 s utterance (ref 376 + gen 564 frames), NFE=32 Euler CFG 2"),
     "cfg3": (dict(dim=768, depth=12, heads=12), 32, 750, 1376, "F5TTS_Small pruned to 12 blocks, batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
+    "cfg3d18": (dict(dim=768, depth=18, heads=12), 32, 750, 1376, "F5TTS_Small un-pruned (18 blocks), batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
     # training step: ref_frames unused
     "cfg5": (dict(dim=1024, depth=22, heads=16), 32, 0, 1200, "F5TTS_Base one optimizer step on 32 x 1200 frames per GPU: CFM.forward + backward + "
              "gradient all-reduce + clip + AdamW + EMA, bf16 operands / fp32 master, dropout 0"),
+    "cfg5b": (dict(dim=1024, depth=22, heads=16), 64, 0, 600, "F5TTS_Base one optimizer step on 64 x 600 frames per GPU: CFM.forward + backward + "
+              "gradient all-reduce + clip + AdamW + EMA, bf16 operands / fp32 master, dropout 0"),
 }
 NFE, CFG, SWAY = 32, 2.0, -1.0
 
@@ -290,7 +293,7 @@ def cpu_train_measure(arch, n, steps, warmup):
 def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     """--workload cfg5: one data-parallel optimizer step per timed step"""
     import torch.distributed as dist
-    config = {"workload": f"cfg5: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
+    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
               "parallelism": f"dp{world} (batch sharded; ONE flat fp32 gradient all-reduce per step over NCCL)",
               "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2",
               "profiling": "timed region un-instrumented; kernel classes / roofline from 2 extra event-bracketed steps"}
@@ -429,8 +432,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3: inference; cfg5: the training step")
+                    help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3, cfg3d18: inference; cfg5, cfg5b: the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ragged", action="store_true", help="inference workloads: per-utterance durations U[0.8, 1] x the nominal length "
+                    "(SURVEY.md 8d's ragged cfg-2 variant, U[1500, 1875]); the value counts un-padded frames")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with CUDA events during the timed region")
     ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the oracle as stock PyTorch eager bf16 on this GPU (second comparator)")
     args = ap.parse_args()
@@ -441,7 +446,7 @@ def main():
 
     arch_kw, B, ref_frames, total, desc = WORKLOADS[args.workload]
     cfg = Arch(**arch_kw)
-    if args.workload == "cfg5":
+    if args.workload.startswith("cfg5"):
         return run_train(args, cfg, B, total, desc, rank, local_rank, world)
     frames_per_step = B * total
     gen_frames_per_step = B * (total - ref_frames)
@@ -473,6 +478,13 @@ def main():
     L.load()
     model, voc = build_product_models(cfg, dev)
     cond, text, duration, lens, wav = make_inputs(cfg, B, ref_frames, total, 1234 + rank)
+    if args.ragged:
+        duration = torch.randint(int(0.8 * total), total + 1, (B,), generator=torch.Generator().manual_seed(4321))
+        duration[0] = total  # the padded length stays the nominal one
+        frames_per_step = int(duration.sum())
+        gen_frames_per_step = int((duration - ref_frames).sum())
+        config["ragged"] = (f"durations U[{int(0.8 * total)}, {total}] (same draw on every rank), padded to {total}; value and e2e count "
+                            f"the {frames_per_step} un-padded frames per step; roofline FLOPs count what the kernels execute")
     cond_d, text_d, dur_d, lens_d = cond.to(dev), text.to(dev), duration.to(dev), lens.to(dev)
     wav_h, text_h = wav.pin_memory(), text.pin_memory()
     gen_len = 256 * (total - ref_frames - 1)
