@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the F5-TTS hot path (BASELINE.json: mel-frames/s and RTF, F5TTS_Base, NFE=32, CFG).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg3d18|cfg5|cfg5b] [--ragged]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg3d18|cfg4|cfg5|cfg5b] [--ragged]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" = one full pass of the hot path over one batch of synthetic utterances: CFM.sample (text embedding, 32 Euler steps x
@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg2": (dict(dim=1024, depth=22, heads=16), 16, 563, 1875, "F5TTS_Base bf16 batch=16 x 20 s utterances (ref 6 s + gen 14 s), NFE=32 sway -1 CFG 2"),
     "cfg1": (dict(dim=1024, depth=22, heads=16), 1, 376, 940, "F5TTS_Base one ~10 s utterance (ref 376 + gen 564 frames), NFE=32 Euler CFG 2"),
     "cfg3": (dict(dim=768, depth=12, heads=12), 32, 750, 1376, "F5TTS_Small pruned to 12 blocks, batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
+    # a fixed job of 256 cfg-2 utterances = 16 batches of 16, rank-strided over the GPUs (strong scaling)
+    "cfg4": (dict(dim=1024, depth=22, heads=16), 16, 563, 1875, "256 utterances of cfg-2's shape = 16 batches of 16 per step, rank-strided over the GPUs "
+             "(strong scaling, no collective on the sampling path)"),
     "cfg3d18": (dict(dim=768, depth=18, heads=12), 32, 750, 1376, "F5TTS_Small un-pruned (18 blocks), batch=32 streaming chunks (ref 8 s + 626 gen frames)"),
     # training step: ref_frames unused
     "cfg5": (dict(dim=1024, depth=22, heads=16), 32, 0, 1200, "F5TTS_Base one optimizer step on 32 x 1200 frames per GPU: CFM.forward + backward + "
@@ -432,7 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3, cfg3d18: inference; cfg5, cfg5b: the training step")
+                    help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3, cfg3d18, cfg4 (fixed 256-utterance job, strong scaling): inference; cfg5, cfg5b: the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ragged", action="store_true", help="inference workloads: per-utterance durations U[0.8, 1] x the nominal length "
                     "(SURVEY.md 8d's ragged cfg-2 variant, U[1500, 1875]); the value counts un-padded frames")
@@ -448,8 +451,13 @@ def main():
     cfg = Arch(**arch_kw)
     if args.workload.startswith("cfg5"):
         return run_train(args, cfg, B, total, desc, rank, local_rank, world)
-    frames_per_step = B * total
-    gen_frames_per_step = B * (total - ref_frames)
+    reps = 1
+    if args.workload == "cfg4":
+        if 16 % world:
+            raise SystemExit("cfg4 splits 16 batches over the ranks: --gpus must divide 16")
+        reps = 16 // world  # batches this rank samples per step
+    frames_per_step = reps * B * total
+    gen_frames_per_step = reps * B * (total - ref_frames)
     config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": total, "ref_frames": ref_frames,
               "nfe": NFE, "cfg_strength": CFG, "sway_sampling_coef": SWAY, "ode": "euler", "vocoder": "vocos-mel-24khz (random init)",
               "parallelism": f"dp{world} (utterance batch sharded, no collective on the sampling path)",
@@ -491,18 +499,21 @@ def main():
     audio_h = torch.empty(B, gen_len, dtype=torch.float32).pin_memory()
 
     def step_device():
-        out, _ = model.sample(cond=cond_d, text=text_d, duration=dur_d, lens=lens_d, steps=NFE, cfg_strength=CFG,
-                              sway_sampling_coef=SWAY, seed=0, return_trajectory=False)
-        return voc.decode(out[:, ref_frames:].permute(0, 2, 1))
+        for _ in range(reps):
+            out, _ = model.sample(cond=cond_d, text=text_d, duration=dur_d, lens=lens_d, steps=NFE, cfg_strength=CFG,
+                                  sway_sampling_coef=SWAY, seed=0, return_trajectory=False)
+            a = voc.decode(out[:, ref_frames:].permute(0, 2, 1))
+        return a
 
     def step_e2e():
-        w = wav_h.to(dev, non_blocking=True)
-        t = text_h.to(dev, non_blocking=True)
-        out, _ = model.sample(cond=w, text=t, duration=dur_d, steps=NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=0,
-                              return_trajectory=False)
-        a = voc.decode(out[:, ref_frames:].permute(0, 2, 1))
-        audio_h.copy_(a, non_blocking=True)
-        torch.cuda.synchronize()
+        for _ in range(reps):
+            w = wav_h.to(dev, non_blocking=True)
+            t = text_h.to(dev, non_blocking=True)
+            out, _ = model.sample(cond=w, text=t, duration=dur_d, steps=NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=0,
+                                  return_trajectory=False)
+            a = voc.decode(out[:, ref_frames:].permute(0, 2, 1))
+            audio_h.copy_(a, non_blocking=True)
+            torch.cuda.synchronize()
         return audio_h
 
     def barrier():
@@ -610,13 +621,14 @@ def main():
     launches = launches_timed
     config["cuda_graph"] = ("one captured graph per ODE step (replayed 32x per sample); kernel breakdown from one extra eager step"
                             if graph_mode else "off (GPU-bound batch; launches are event-bracketed live in the timed region)")
-    fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE
+    fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE * reps
     line = {"metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": wav_h.numel() * 4 + text_h.numel() * 8,
-                    "d2h_bytes_per_step": audio_h.numel() * 4, "ms_per_step": e2e_s * 1e3 / args.steps},
+            "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": reps * (wav_h.numel() * 4 + text_h.numel() * 8),
+                    "d2h_bytes_per_step": reps * audio_h.numel() * 4, "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": launches,
             "rtf": (ms * 1e-3 / args.steps) / (gen_frames_per_step * 256 / 24000.0),
             "gen_frames_per_sec": gen_frames_per_step * args.steps * world / (ms * 1e-3),
