@@ -71,6 +71,8 @@ SIGNATURES = {
     "f5b_dit_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
     "f5b_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, sz, vp]),
     "f5b_dit_train_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
+    "f5b_crossfade_append": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp]),
+    "f5b_pcm16": (C.c_int, [vp, vp, C.c_int64, vp]),
     "f5b_align_viterbi": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_align_window": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_duration_predictor": (C.c_int, [vp, C.c_int] + [vp] * 2 + [C.c_int] + [vp] * 12 + [C.c_int] * 5 + [vp]),

@@ -456,6 +456,36 @@ __global__ void masked_mse_final_kernel(const float* __restrict__ partial, int n
   }
 }
 
+// One fold step of the chunk cross-fade (infer/f5tts_wrapper.py:556-572, infer/utils_infer.py:519-543): the last cfs samples of the
+// accumulated wave are blended with the first cfs of the next chunk, fade_out = linspace(1, 0, cfs), fade_in = linspace(0, 1, cfs)
+// evaluated in fp64 as numpy does (start + t * step, last point exact), and the rest of the chunk is appended.
+__global__ void crossfade_append_kernel(float* __restrict__ acc, int64_t acc_len, const float* __restrict__ next, int64_t next_len, int cfs) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= next_len) return;
+  const int64_t o = acc_len - cfs + t;
+  if (t < cfs) {
+    double fo, fi;
+    if (cfs == 1) { fo = 1.0; fi = 0.0; }
+    else if (t == cfs - 1) { fo = 0.0; fi = 1.0; }
+    else {
+      // numpy: arange(num) * step + start, each operation rounded separately (no FMA contraction)
+      fo = __dadd_rn(__dmul_rn((double)t, -1.0 / (double)(cfs - 1)), 1.0);
+      fi = __dmul_rn((double)t, 1.0 / (double)(cfs - 1));
+    }
+    acc[o] = (float)__dadd_rn(__dmul_rn((double)acc[o], fo), __dmul_rn((double)next[t], fi));
+  } else {
+    acc[o] = next[t];
+  }
+}
+// np.int16(x * 32767) (socket_server.py:54, finetune_gradio.py:704): fp32 product, truncation toward zero; saturated instead of
+// wrapping for |x| > 1
+__global__ void pcm16_kernel(const float* __restrict__ x, int16_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = __float2int_rz(x[i] * 32767.f);
+  out[i] = (int16_t)max(-32768, min(32767, v));
+}
+
 }  // namespace f5b
 
 using namespace f5b;
@@ -520,6 +550,21 @@ int f5b_pack_bf16(const float* x, int ld_in, void* out, int ld_out, int rows, in
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * rows * cols + 2.0 * tot);
   pack_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out,
                                                                           rows, cols, width);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int f5b_crossfade_append(float* acc, int64_t acc_len, const float* next, int64_t next_len, int cfs, f5b_stream_t stream) {
+  F5B_CHECK(acc && next && acc_len >= 0 && next_len > 0 && cfs >= 0 && cfs <= acc_len && cfs <= next_len, "f5b_crossfade_append: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * next_len);
+  crossfade_append_kernel<<<(unsigned)((next_len + 255) / 256), 256, 0, ST(stream)>>>(acc, acc_len, next, next_len, cfs);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+int f5b_pcm16(const float* x, int16_t* out, int64_t n, f5b_stream_t stream) {
+  F5B_CHECK(x && out && n > 0, "f5b_pcm16: bad argument");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * n);
+  pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, out, n);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

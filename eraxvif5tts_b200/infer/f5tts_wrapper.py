@@ -198,8 +198,12 @@ class F5TTSWrapper:
                  cfg_strength: Optional[float] = None, sway_sampling_coef: Optional[float] = None, speed: Optional[float] = None,
                  fix_duration: Optional[float] = None, cross_fade_duration: Optional[float] = None,
                  use_duration_predictor: Optional[bool] = None, return_numpy: bool = False, return_spectrogram: bool = False,
-                 batch_chunks: bool = False, seed: Optional[int] = None):
-        """f5tts_wrapper.py:408-607."""
+                 batch_chunks: bool = False, seed: Optional[int] = None, device_crossfade: bool = False, return_pcm16: bool = False):
+        """f5tts_wrapper.py:408-607.  Beyond the reference (SURVEY.md 8f-1): batch_chunks samples all chunks as one ragged batch;
+        device_crossfade keeps the chunk waveforms on the GPU and cross-fades them there (float32 result; the reference's numpy
+        fold returns float64 after the first blend); return_pcm16 (implies device_crossfade) returns np.int16(wave * 32767)
+        packed on the device, as the socket server streams it (socket_server.py:54)."""
+        device_crossfade = device_crossfade or return_pcm16
         if self.ref_audio_processed is None or self.ref_text is None:
             raise ValueError("Reference audio not preprocessed. Call preprocess_reference() first.")
         nfe_step = nfe_step if nfe_step is not None else self.nfe_step
@@ -222,7 +226,7 @@ class F5TTSWrapper:
             wave = self.vocoder.decode(g)
             if rms < self.target_rms:
                 wave = wave * rms / self.target_rms
-            generated_waves.append(wave.squeeze().cpu().numpy())
+            generated_waves.append(wave.reshape(-1) if device_crossfade else wave.squeeze().cpu().numpy())
             if return_spectrogram or output_path is not None:
                 spectrograms.append(g.squeeze().cpu().numpy())
 
@@ -247,7 +251,12 @@ class F5TTSWrapper:
                     finish(generated)
 
         # cross-fade (f5tts_wrapper.py:542-575)
-        if cross_fade_duration <= 0:
+        if device_crossfade:
+            from .. import ops
+            final_dev = ops.crossfade_concat(generated_waves, int(cross_fade_duration * self.target_sample_rate) if cross_fade_duration > 0 else 0)
+            pcm = ops.pcm16(final_dev).cpu().numpy() if return_pcm16 else None
+            final_wave = final_dev.cpu().numpy() if (pcm is None or output_path is not None) else None
+        elif cross_fade_duration <= 0:
             final_wave = np.concatenate(generated_waves)
         else:
             final_wave = generated_waves[0]
@@ -268,6 +277,8 @@ class F5TTSWrapper:
             _write_wav(output_path, final_wave, self.target_sample_rate)
             if not return_numpy:
                 return output_path
+        if return_pcm16:
+            final_wave = pcm
         if return_spectrogram:
             return final_wave, self.target_sample_rate, combined_spectrogram
         return final_wave, self.target_sample_rate

@@ -194,3 +194,31 @@ def attn_bwd(q, k, v, ld, out, dout, lse, dqkv, lens, lens_mod, B, H, n, scale=0
                              delta.data_ptr(), dq_ws.data_ptr(), dqkv.data_ptr(), dqkv.shape[-1], L.ptr(lens), lens_mod, B, H, n, scale,
                              L.ptr(rope), rope_heads, L.stream()), "f5b_attn_bwd")
     return dqkv
+
+
+def crossfade_concat(waves, cross_fade_samples: int):
+    """Cross-fade concatenation of 1-D fp32 CUDA waveforms with the fold of infer/f5tts_wrapper.py:549-575 (each step blends
+    min(cross_fade_samples, len(accumulated), len(next)) samples), on the device: K - 1 small launches, no host round trip."""
+    if not waves:
+        raise ValueError("no waves")
+    waves = [w.reshape(-1).contiguous() for w in waves]
+    for w in waves:
+        _chk(w, torch.float32, "wave")
+    out = torch.empty(sum(w.numel() for w in waves), dtype=torch.float32, device=waves[0].device)
+    n = waves[0].numel()
+    out[:n].copy_(waves[0])
+    lib = L.load()
+    for w in waves[1:]:
+        cfs = max(0, min(int(cross_fade_samples), n, w.numel()))
+        L.check(lib.f5b_crossfade_append(out.data_ptr(), n, w.data_ptr(), w.numel(), cfs, L.stream()), "f5b_crossfade_append")
+        n = n - cfs + w.numel()
+    return out[:n]
+
+
+def pcm16(wave):
+    """np.int16(wave * 32767) (socket_server.py:54) on the device, saturating"""
+    w = wave.reshape(-1).contiguous()
+    _chk(w, torch.float32, "wave")
+    out = torch.empty(w.numel(), dtype=torch.int16, device=w.device)
+    L.check(L.load().f5b_pcm16(w.data_ptr(), out.data_ptr(), w.numel(), L.stream()), "f5b_pcm16")
+    return out.view(wave.shape)

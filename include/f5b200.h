@@ -388,6 +388,14 @@ int f5b_prof_enabled(void);
 /* add per-kind (launches, unused, flops, bytes) — used when a captured CUDA graph is replayed */
 void f5b_prof_add(const double* delta, int n_kinds);
 
+/* ---- on-device chunk cross-fade + PCM packing ---- */
+/* One fold step of the cross-fade of generated chunks (infer/f5tts_wrapper.py:556-572, infer/utils_infer.py:519-543): blends
+ * acc[acc_len - cfs, acc_len) with next[0, cfs) using numpy's linspace(1, 0, cfs) / linspace(0, 1, cfs) in fp64 and appends
+ * next[cfs, next_len); the accumulated length becomes acc_len - cfs + next_len (acc must have room).  cfs = 0: plain append. */
+int f5b_crossfade_append(float* acc, int64_t acc_len, const float* next, int64_t next_len, int cfs, f5b_stream_t stream);
+/* np.int16(x * 32767) (socket_server.py:54): fp32 product truncated toward zero, saturated to the int16 range. */
+int f5b_pcm16(const float* x, int16_t* out, int64_t n, f5b_stream_t stream);
+
 /* ---- monotonic alignment search + duration predictor (the duration side of train/distil_reload.py) ---- */
 
 /* viterbi_vectorized_alignment, model/alignment_utils.py:154-212.  sim fp32 [B, nt, T] (token x frame similarity) -> align fp32

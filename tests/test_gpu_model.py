@@ -3,6 +3,7 @@ reference modules produced (tests/golden/, generator oracle/gen_golden.py).
 
 Tolerances (BASELINE.json north_star): bf16 tensor-core path -> max |error| <= 2e-2 on the DiT velocity field,
 mean |error| <= 1e-2 on the final log-mel.  The oracle is fp32; weights are bf16-exact so only arithmetic differs."""
+import numpy as np
 import pytest
 import torch
 
@@ -161,8 +162,42 @@ def test_wrapper_generate_end_to_end(tmp_path):
     assert sr == 24000 and wave.ndim == 1 and wave.size > 24000 and bool((wave == wave).all())
     wave_b, _ = w.generate(text, nfe_step=2, return_numpy=True, seed=0, batch_chunks=True)
     assert abs(wave_b.size - wave.size) <= 256 * 4
+    # on-device cross-fade / PCM packing against the host fold of the same run (same seed -> same chunk waves)
+    wave_d, _ = w.generate(text, nfe_step=2, return_numpy=True, seed=0, device_crossfade=True)
+    assert wave_d.dtype == np.float32 and wave_d.shape == wave.shape
+    assert np.array_equal(wave_d, wave.astype(np.float32))
+    pcm, _ = w.generate(text, nfe_step=2, return_numpy=True, seed=0, return_pcm16=True)
+    assert pcm.dtype == np.int16 and np.array_equal(pcm, np.int16(np.clip(wave_d * np.float32(32767), -32768, 32767)))
     out = w.generate("short text here.", output_path=str(tmp_path / "o.wav"), nfe_step=2)
     assert out.endswith("o.wav") and (tmp_path / "o.wav").stat().st_size > 1000
+
+
+def test_device_crossfade_fold_matches_numpy_fold():
+    """ops.crossfade_concat against the reference's numpy fold (f5tts_wrapper.py:549-575), including chunks shorter than the fade
+    (chained blends) and cfs = 1 / 0: the fp64 blend rounded to fp32 once must equal the numpy result cast to fp32"""
+    from eraxvif5tts_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for lens, cf in (((5000, 9000, 4100), 3600), ((5000, 7000, 4100), 3600), ((900, 400, 120, 3000), 500), ((10, 2, 7), 1), ((64, 64), 0),
+                     ((3000,), 3600), ((2000, 50, 60, 2000), 3600), ((4000, 1000, 1000, 1000, 2500), 500)):
+        waves = [torch.randn(n, generator=g) * 0.3 for n in lens]
+        final = waves[0].numpy()
+        for nxt in waves[1:]:
+            nxt = nxt.numpy()
+            cfs = min(cf, len(final), len(nxt))
+            if cfs <= 0:
+                final = np.concatenate([final, nxt])
+                continue
+            overlap = final[-cfs:] * np.linspace(1, 0, cfs) + nxt[:cfs] * np.linspace(0, 1, cfs)
+            final = np.concatenate([final[:-cfs], overlap, nxt[cfs:]])
+        got = ops.crossfade_concat([w_.cuda() for w_ in waves], cf).cpu().numpy()
+        assert got.shape == final.shape, (lens, cf)
+        if all(n >= 2 * cf for n in lens[1:-1]):  # no sample is blended twice: one fp64 blend, rounded to fp32 once
+            assert np.array_equal(got, final.astype(np.float32)), (lens, cf)
+        else:  # chained blends: the device keeps the running wave in fp32 between folds, numpy in fp64
+            assert float(np.abs(got - final).max()) <= 1e-6, (lens, cf)
+    x = torch.tensor([0.0, 0.5, -0.5, 0.99999, -1.0, 1.0, 1.7, -2.0, 3.0517578e-05, -3.0517578e-05])
+    want = np.int16(np.clip(x.numpy() * np.float32(32767), -32768, 32767))
+    assert np.array_equal(ops.pcm16(x.cuda()).cpu().numpy(), want)
 
 
 def test_cuda_graph_step_matches_eager_launches(monkeypatch):
