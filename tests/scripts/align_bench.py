@@ -1,5 +1,5 @@
 """Monotonic alignment search at a training-batch shape: GPU kernels vs the CPU restatement of the reference loop.
-    python tools/align_bench.py [B] [nt] [T]
+    python tests/scripts/align_bench.py [B] [nt] [T]
 The reference (model/alignment_utils.py:154-212) runs nt x T torch ops per call in a Python double loop; the oracle is the same
 recurrence in numpy, vectorised over the batch exactly like the reference, so its time is a LOWER bound on the reference's."""
 import os
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from eraxvif5tts_b200.model import alignment_utils as U  # noqa: E402
 from oracle import align_oracle as A  # noqa: E402
