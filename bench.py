@@ -263,6 +263,70 @@ def torch_eager_gpu_measure(arch, B, ref_frames, total, dev, steps=3, warmup=2):
                       f"x{NFE} extrapolated; MelSpec / text embedding / Vocos excluded (they favour this arm)",
             "kernels": "torch eager: cuBLAS linears, SDPA without key mask, cuDNN grouped conv"}
 
+def torch_eager_gpu_train_measure(arch, B, n, dev, steps=3, warmup=2):
+    """Second comparator for the training step (opt-in, --torch-eager-gpu): the oracle's CFM.forward under torch.autocast(bf16) with
+    torch autograd, F.scaled_dot_product_attention, clip_grad_norm_ and fused torch.optim.AdamW on the same B200 -- what the
+    reference's Trainer runs per step (accelerate bf16 mixed precision), minus DDP / EMA / text-embedding backward (they favour
+    this arm).  A baseline leg: nothing here is on the product path."""
+    import torch.nn.functional as F
+    from oracle import f5_oracle as O
+    from oracle.weights import make_dit_state_dict
+    cfg = O.DiTConfig(dim=arch.dim, depth=arch.depth, heads=arch.heads)
+    sd_cpu = make_dit_state_dict(cfg, 0)
+    g = torch.Generator().manual_seed(1234)
+    x1 = (torch.randn(B, n, cfg.mel_dim, generator=g) * 2 - 1.5).clamp(-11.5, 5).to(dev)
+    text = torch.randint(0, cfg.text_num_embeds, (B, int(0.16 * n)), generator=g)
+    with torch.no_grad():
+        te = O.text_embedding(sd_cpu, cfg, text[:1], n, False).expand(B, -1, -1).to(dev)
+    sd = {k: (v.to(dev).requires_grad_(True) if v.is_floating_point() else v.to(dev)) for k, v in sd_cpu.items()}
+    params = [v for k, v in sd.items() if v.requires_grad and k.startswith("transformer.") and not k.startswith("transformer.text_embed.")]
+    opt = torch.optim.AdamW(params, lr=7.5e-5, betas=(0.9, 0.98), weight_decay=0.01, fused=True)
+    rope_cpu, attn_cpu = O.rotary_freqs, O.attention
+
+    def attention_sdpa(sd_, cfg_, p, x, mask, rope, drop=None):
+        b, m, _ = x.shape
+        H, d = cfg_.heads, cfg_.dim_head
+        q = F.linear(x, sd_[p + "to_q.weight"], sd_[p + "to_q.bias"]).view(b, m, H, d).transpose(1, 2)
+        k = F.linear(x, sd_[p + "to_k.weight"], sd_[p + "to_k.bias"]).view(b, m, H, d).transpose(1, 2)
+        v = F.linear(x, sd_[p + "to_v.weight"], sd_[p + "to_v.bias"]).view(b, m, H, d).transpose(1, 2)
+        pn = cfg_.pe_attn_head if cfg_.pe_attn_head is not None else H
+        q = torch.cat((O.apply_rotary(q[:, :pn], rope), q[:, pn:]), dim=1)
+        k = torch.cat((O.apply_rotary(k[:, :pn], rope), k[:, pn:]), dim=1)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, m, H * d)
+        return F.linear(o, sd_[p + "to_out.0.weight"], sd_[p + "to_out.0.bias"])
+
+    O.rotary_freqs = lambda m, d=64, theta=10000.0: rope_cpu(m, d, theta).to(dev)
+    O.attention = attention_sdpa
+    try:
+        span = torch.zeros(B, n, dtype=torch.bool, device=dev)
+        span[:, n // 8: n // 8 + int(0.8 * n)] = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            x0 = torch.randn_like(x1)
+            time_ = torch.rand(B, device=dev)
+            t = time_[:, None, None]
+            phi, flow = (1 - t) * x0 + t * x1, x1 - x0
+            cond = torch.where(span[..., None], torch.zeros_like(x1), x1)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                pred = O.dit_forward(sd, cfg, phi, cond, text, time_, False, False, None, text_embed=te)
+            loss = F.mse_loss(pred.float(), flow, reduction="none")[span].mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        O.rotary_freqs, O.attention = rope_cpu, attn_cpu
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B * n / (ms * 1e-3), "unit": "mel-frames/s", "ms_per_step": ms, "dtype": "bf16 autocast, fp32 master",
+            "peak_alloc_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "loss": float(loss.detach()),
+            "sample": f"full batch ({B} x {n} frames), forward + backward + clip + fused AdamW per timed step, mean of {steps}",
+            "kernels": "torch eager autograd: cuBLAS linears, SDPA (flash) forward / backward, cuDNN grouped conv, fused AdamW"}
+
 def cpu_train_measure(arch, n, steps, warmup):
     """CPU arm of the training step: torch autograd over the oracle's fp32 CFM.forward for ONE utterance of the workload
     (forward + backward; the optimizer is negligible next to them), all host threads."""
@@ -425,6 +489,12 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_train_measure(cfg, n, 1, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if world == 1 and args.torch_eager_gpu:
+        eng.release()
+        del eng, model
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        line["torch_eager_gpu"] = torch_eager_gpu_train_measure(cfg, B, n, dev)
     print(json.dumps(line))
 
 

@@ -197,6 +197,10 @@ class TrainEngine:
         self.refresh_packed()
         self.dit.invalidate()
 
+    def release(self):
+        """drop the activation workspace (tens of GB at training batch sizes); the next loss_and_grads re-allocates it"""
+        self._ws = None
+
     def workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
