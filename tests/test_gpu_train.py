@@ -2,6 +2,8 @@
 restatement of CFM.forward (oracle.cfm_loss, pinned to the reference modules by tests/test_oracle_golden.py), same weights, same
 random draws.  Tolerance: activations and the gradients flowing between kernels are bf16, so every parameter gradient is judged
 by its relative Frobenius error (<= 4e-2) and its cosine similarity (>= 0.999) with the autograd gradient; the loss itself to 2 %."""
+import os
+
 import pytest
 import torch
 
@@ -321,3 +323,63 @@ def test_backward_base_width_vs_oracle_autograd_on_gpu():
     assert abs(float(loss) - float(ref_loss)) <= 2e-2 * float(ref_loss)
     worst = _compare(model, ref)
     print("worst gradients at Base width (fro err, cos, key):", worst[:4])
+
+
+class _ToyDataset(torch.utils.data.Dataset):
+    """items shaped like the reference's CustomDataset (dataset.py:92-135): mel_spec [n_mels, T], text"""
+
+    def __init__(self, n_items=22, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.lens = [int(x) for x in torch.randint(40, 120, (n_items,), generator=g)]
+        self.mels = [(torch.randn(100, L_, generator=g) * 2 - 1.5).clamp(-11.5, 5) for L_ in self.lens]
+        self.texts = ["".join(chr(97 + int(c)) for c in torch.randint(0, 26, (max(3, L_ // 8),), generator=g)) for L_ in self.lens]
+
+    def get_frame_len(self, index):
+        return self.lens[index]
+
+    def __len__(self):
+        return len(self.lens)
+
+    def __getitem__(self, index):
+        return dict(mel_spec=self.mels[index], text=self.texts[index])
+
+
+def test_trainer_loop_checkpoints_and_resume(tmp_path):
+    """model.Trainer: the reference's loop shape (frame batching, accumulation incl. the trailing partial window, warm-up / decay,
+    checkpoint rotation, resume from model_last.pt) over TrainEngine"""
+    from eraxvif5tts_b200.model import Trainer
+    cfg = O.DiTConfig.tiny()
+    ds = _ToyDataset()
+
+    def make():
+        model, _ = build_cfm(cfg, 0)
+        model.vocab_char_map = {chr(97 + i): i for i in range(26)}
+        return Trainer(model, epochs=2, learning_rate=2e-3, weight_decay=0.0, num_warmup_updates=2, save_per_updates=3,
+                       keep_last_n_checkpoints=1, checkpoint_path=str(tmp_path / "ck"), batch_size_per_gpu=400, batch_size_type="frame",
+                       max_samples=8, grad_accumulation_steps=2, last_per_updates=4)
+    tr = make()
+    import math
+    from eraxvif5tts_b200.data import DynamicBatchSampler
+    per_epoch = len(DynamicBatchSampler(torch.utils.data.SequentialSampler(ds), 400, max_samples=8))
+    updates = tr.train(ds, num_workers=0, resumable_with_seed=666)
+    assert updates == math.ceil(per_epoch / 2) * 2 and len(tr.losses) == updates
+    assert all(math.isfinite(x) for x in tr.losses)
+    assert sum(tr.losses[-3:]) < sum(tr.losses[:3])  # it learns the toy set
+    files = sorted(os.listdir(tmp_path / "ck"))
+    assert "model_last.pt" in files and len([f for f in files if f != "model_last.pt"]) == 1, files
+    ck = torch.load(tmp_path / "ck" / "model_last.pt", map_location="cpu", weights_only=True)
+    assert ck["update"] == updates and {"model_state_dict", "optimizer_state_dict", "ema_model_state_dict"} <= set(ck)
+    # resume: everything is already trained -> no further update, weights equal the checkpoint's
+    tr2 = make()
+    assert tr2.load_checkpoint() == updates
+    assert tr2.train(ds, num_workers=0, resumable_with_seed=666) == updates and not tr2.losses
+    w = dict(tr2.model.named_parameters())["transformer.proj_out.weight"]
+    assert torch.equal(w.detach().cpu(), ck["model_state_dict"]["transformer.proj_out.weight"])
+    # "sample" batching, one epoch, no accumulation
+    model, _ = build_cfm(cfg, 0)
+    model.vocab_char_map = {chr(97 + i): i for i in range(26)}
+    tr3 = Trainer(model, epochs=1, learning_rate=1e-3, num_warmup_updates=1, save_per_updates=1000, checkpoint_path=str(tmp_path / "ck3"),
+                  batch_size_per_gpu=6, batch_size_type="sample", keep_last_n_checkpoints=0)
+    assert tr3.train(ds, num_workers=0) == math.ceil(len(ds) / 6)
+    with pytest.raises(NotImplementedError):
+        Trainer(model, epochs=1, learning_rate=1e-3, duration_predictor=object())
