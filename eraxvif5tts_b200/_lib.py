@@ -42,6 +42,12 @@ class DitGrads(C.Structure):
                                   "ff1_w", "ff1_b", "ff2_w", "ff2_b", "proj_w", "proj_b")]
 
 
+class DurPredParams(C.Structure):
+    """F5bDurPredParams: fp32 parameter (or gradient) pointers of the DurationPredictor"""
+    _fields_ = [(k, vp) for k in ("table", "conv1_w", "conv1_b", "norm1_w", "norm1_b", "conv2_w", "conv2_b", "norm2_w", "norm2_b",
+                                  "proj_w", "proj_b")]
+
+
 class VocosDesc(C.Structure):
     _fields_ = [(k, i32) for k in ("n_mels", "dim", "intermediate", "num_layers", "n_fft", "hop")] + \
                [("embed_w", vp), ("embed_b", vp), ("ld_embed", i32)] + \
@@ -76,6 +82,8 @@ SIGNATURES = {
     "f5b_align_viterbi": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_align_window": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_duration_predictor": (C.c_int, [vp, C.c_int] + [vp] * 2 + [C.c_int] + [vp] * 12 + [C.c_int] * 5 + [vp]),
+    "f5b_duration_predictor_train_forward": (C.c_int, [vp, C.c_int, vp, vp, C.c_float, C.c_uint64, vp, vp, vp, vp, vp] + [C.c_int] * 5 + [vp]),
+    "f5b_duration_predictor_backward": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_uint64, vp, vp, vp, vp, vp] + [C.c_int] * 5 + [vp]),
     "f5b_distill_loss": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
     "f5b_distill_grad": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
     "f5b_train_set_dropout": (C.c_int, [C.c_float, C.c_uint64]),

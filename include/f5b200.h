@@ -417,6 +417,23 @@ int f5b_duration_predictor(const int64_t* ids, int id_shift, const float* mask, 
                            const float* norm2_w, const float* norm2_b, const float* proj_w, const float* proj_b, float* h1_ws, float* out,
                            int B, int nt, int Cin, int F, int ksize, f5b_stream_t stream);
 
+/* DurationPredictor in TRAIN mode (nn.Dropout(p_dropout) after each GroupNorm, duration_predictor.py:16, 36-41) and its backward,
+ * for the duration loss of train/distil_reload.py:1096-1124 (logw vs log(attn.sum(2) + 1e-6)).  The same pointer struct carries the
+ * parameters and (non-const in effect) their gradient buffers, which the backward ACCUMULATES into (zero them first).
+ * The dropout masks are the counter-based generator of f5b_train_set_dropout (site 0 / 1 = first / second Dropout, element index in
+ * [B, nt, F] order), regenerated by the backward from (p_dropout, seed).  h1 / a / c / dpre1 workspaces: fp32 [B, nt, F]; stats [B, 4].
+ * dlogw fp32 [B, nt] = d loss / d out.  B * nt * F must be a multiple of 4; F <= 64. */
+typedef struct F5bDurPredParams {
+  const float *table, *conv1_w, *conv1_b, *norm1_w, *norm1_b, *conv2_w, *conv2_b, *norm2_w, *norm2_b, *proj_w, *proj_b;
+} F5bDurPredParams;
+int f5b_duration_predictor_train_forward(const int64_t* ids, int id_shift, const float* mask, const F5bDurPredParams* p, float p_dropout,
+                                         uint64_t seed, float* h1_ws, float* a_ws, float* c_ws, float* stats_ws, float* out, int B, int nt,
+                                         int Cin, int F, int ksize, f5b_stream_t stream);
+int f5b_duration_predictor_backward(const float* dlogw, const int64_t* ids, int id_shift, const float* mask, const F5bDurPredParams* p,
+                                    const F5bDurPredParams* grads, float p_dropout, uint64_t seed, const float* h1_ws, const float* a_ws,
+                                    const float* c_ws, const float* stats_ws, float* dpre1_ws, int B, int nt, int Cin, int F, int ksize,
+                                    f5b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,14 +71,33 @@ def windowed_alignment(sim: np.ndarray, window_size=0.2):
     return align, align.sum(-1).astype(np.int64)
 
 
-def duration_predictor(sd: dict, ids: torch.Tensor, mask: torch.Tensor, id_shift: int = 1) -> torch.Tensor:
-    """sd: DurationPredictor.state_dict(); ids int [b, nt]; mask [b, nt] -> [b, 1, nt] (dropout = identity: eval mode)"""
+def duration_predictor(sd: dict, ids: torch.Tensor, mask: torch.Tensor, id_shift: int = 1, dropout=None) -> torch.Tensor:
+    """sd: DurationPredictor.state_dict(); ids int [b, nt]; mask [b, nt] -> [b, 1, nt].  dropout None: eval mode (identity);
+    (p, seed): train mode with the product's counter-based masks (f5_oracle.dropout_multipliers, layer 0, site 0 / 1, element index
+    in [b, nt, F] order) so that autograd here sees the masks the CUDA path used."""
+    def drop(x, site):
+        if dropout is None or not dropout[0] > 0:
+            return x
+        from .f5_oracle import dropout_multipliers
+        b, f, nt = x.shape
+        return x * dropout_multipliers(dropout[0], dropout[1], 0, site, (b, nt, f)).transpose(1, 2)
     k = sd["conv_1.weight"].shape[-1]
     x = F.embedding(ids + id_shift, sd["text_embed.weight"].float()).transpose(1, 2)
     m = mask.float().unsqueeze(1)
     x = F.conv1d(x * m, sd["conv_1.weight"].float(), sd["conv_1.bias"].float(), padding=k // 2)
-    x = F.group_norm(torch.relu(x), 1, sd["norm_1.weight"].float(), sd["norm_1.bias"].float(), eps=1e-5)
+    x = drop(F.group_norm(torch.relu(x), 1, sd["norm_1.weight"].float(), sd["norm_1.bias"].float(), eps=1e-5), 0)
     x = F.conv1d(x * m, sd["conv_2.weight"].float(), sd["conv_2.bias"].float(), padding=k // 2)
-    x = F.group_norm(torch.relu(x), 1, sd["norm_2.weight"].float(), sd["norm_2.bias"].float(), eps=1e-5)
+    x = drop(F.group_norm(torch.relu(x), 1, sd["norm_2.weight"].float(), sd["norm_2.bias"].float(), eps=1e-5), 1)
     x = F.conv1d(x * m, sd["proj.weight"].float(), sd["proj.bias"].float())
     return x * m
+
+
+def duration_loss(logw: torch.Tensor, attn: torch.Tensor, mask: torch.Tensor, per_item: bool = False) -> torch.Tensor:
+    """train/distil_reload.py:1104-1115, written as the script writes it: logw [b, 1, nt] minus logw_ [b, nt] broadcasts to
+    [b, b, nt] (cross terms between batch items for b > 1 -- the reference's literal behaviour).  per_item=True: the intended loss."""
+    m = mask.float()
+    logw_ = torch.log(attn.float().sum(dim=2) + 1e-6) * m
+    if per_item:
+        logw_ = logw_.unsqueeze(1)
+    l_length = torch.sum((logw - logw_) ** 2, [1, 2]) / torch.sum(m)
+    return torch.sum(l_length.float())

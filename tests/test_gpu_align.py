@@ -92,3 +92,51 @@ def test_duration_predictor_golden_and_oracle():
     assert float((got.cpu() - ref).abs().max()) <= 1e-4
     with pytest.raises(NotImplementedError):
         big.train()(ids.cuda(), mask.cuda())
+
+
+@pytest.mark.parametrize("train,per_item", [(False, False), (True, False), (True, True)])
+def test_duration_predictor_training_step_vs_oracle_autograd(train, per_item):
+    """loss_and_grads (train-mode forward with the shared dropout masks, duration loss of distil_reload.py:1096-1124, hand-written
+    backward) against torch autograd through the oracle: loss to 1e-4 relative, every parameter gradient to 2e-3 (fp32, different
+    summation order).  Then a few SGD steps on one batch must drive the loss down."""
+    from eraxvif5tts_b200.model import DurationPredictor, alignment_utils as U
+    torch.manual_seed(11)
+    dp = DurationPredictor(60, 48, 32, 3, 0.5).cuda()
+    with torch.no_grad():
+        for p in dp.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    dp.train(train)
+    b, nt, T = 3, 28, 150
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, 60, (b, nt), generator=g)
+    lens = torch.tensor([28, 19, 7])
+    mask = (torch.arange(nt)[None] < lens[:, None]).int()
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, -1))
+    attn = U.viterbi_vectorized_alignment(torch.randn(b, nt, T, generator=g).cuda()).cpu()
+    seed = 77
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in dp.state_dict().items()}
+    logw_ref = A.duration_predictor(sd, ids, mask, 1, dropout=(0.5, seed) if train else None)
+    loss_ref = A.duration_loss(logw_ref, attn, mask, per_item=per_item)
+    loss_ref.backward()
+    loss, logw = dp.loss_and_grads(ids.cuda(), mask.cuda(), attn=attn.cuda(), seed=seed, per_item=per_item)
+    assert float((logw.cpu() - logw_ref.detach()).abs().max()) <= 1e-4
+    assert abs(float(loss) - float(loss_ref.detach())) <= 1e-4 * abs(float(loss_ref.detach()))
+    for k, p in dp.named_parameters():
+        r = sd[k].grad
+        assert r is not None, k
+        err = float((p.grad.cpu() - r).norm()) / (float(r.norm()) + 1e-12)
+        assert err <= 2e-3, (k, err)
+    # gradients accumulate
+    g0 = {k: p.grad.clone() for k, p in dp.named_parameters()}
+    dp.loss_and_grads(ids.cuda(), mask.cuda(), attn=attn.cuda(), seed=seed, per_item=per_item)
+    for k, p in dp.named_parameters():
+        assert torch.allclose(p.grad, 2 * g0[k], rtol=1e-3, atol=1e-6 + 1e-4 * float(g0[k].abs().max())), k
+    dp.eval()
+    opt = torch.optim.SGD(dp.parameters(), lr=0.02)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad(set_to_none=False)
+        l_, _ = dp.loss_and_grads(ids.cuda(), mask.cuda(), attn=attn.cuda(), per_item=True)
+        opt.step()
+        losses.append(float(l_))
+    assert losses[-1] < 0.8 * losses[0], losses
