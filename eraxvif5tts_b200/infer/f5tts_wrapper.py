@@ -134,7 +134,10 @@ class F5TTSWrapper:
             odeint_kwargs=dict(method=ode_method), vocab_char_map=self.vocab_char_map).to(self.device)
         if ckpt_path is not None:
             load_checkpoint(self.model, ckpt_path, self.device, use_ema=use_ema)
-        self.has_duration_predictor = False  # DurationPredictor is out of scope
+        # the duration-predictor variant of the wrapper (model/f5tts_wrapper-dur_pred.py:166-230): attach one with
+        # attach_duration_predictor(); checkpoints that bundle it are not auto-detected
+        self.has_duration_predictor = False
+        self.duration_predictor, self._dp_tokenizer = None, None
         if self.use_duration_predictor:
             print("Warning: Duration predictor requested but not found in model. Using fallback duration calculation.")
             self.use_duration_predictor = False
@@ -186,10 +189,48 @@ class F5TTSWrapper:
         return audio, ref_text
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _chunk_duration(self, text_batch: str, speed: float, fix_duration):
+    def attach_duration_predictor(self, duration_predictor, tokenizer=None, use: bool = True):
+        """model/f5tts_wrapper-dur_pred.py:169-230.  `tokenizer(text) -> (ids: list[int], is_phoneme: bool)` turns a text chunk into
+        the predictor's input; the reference phonemizes with espeak (alignment_utils.py:39-58, not available offline) and calls
+        phoneme_forward.  Default: the model's own character tokenizer (vocab_char_map) and DurationPredictor.forward, the input
+        the predictor is trained on in train/distil_reload.py:1096-1110."""
+        self.duration_predictor = duration_predictor.to(self.device).eval()
+        self._dp_tokenizer = tokenizer
+        self.has_duration_predictor = True
+        self.use_duration_predictor = bool(use)
+
+    def calculate_duration_with_predictor(self, text_input, local_speed=1.0):
+        """model/f5tts_wrapper-dur_pred.py:441-519: ref frames + int(sum(exp(clamp(logw, -20, 20))) / local_speed), falling back to
+        the text-length ratio when the predictor path raises"""
+        if not self.has_duration_predictor:
+            raise ValueError("Duration predictor not available")
+        try:
+            if self._dp_tokenizer is not None:
+                ids, is_phoneme = self._dp_tokenizer(text_input)
+                ids = torch.tensor([list(ids)], dtype=torch.long, device=self.device)
+            else:
+                from ..model.utils import list_str_to_idx
+                ids = list_str_to_idx([text_input], self.vocab_char_map).to(self.device)
+                is_phoneme = False
+            mask = torch.ones_like(ids)
+            fwd = self.duration_predictor.phoneme_forward if is_phoneme else self.duration_predictor
+            log_durations = fwd(ids, mask)
+            if log_durations.dim() == 3 and log_durations.size(1) == 1:
+                log_durations = log_durations.squeeze(1)
+            durations = torch.exp(torch.clamp(log_durations, -20, 20)).sum(dim=1)
+            return self.ref_audio_len + int(durations[0].item() / local_speed)
+        except Exception as e:  # the reference falls back to the ratio rule on any failure (:504-519)
+            print(f"Error in duration prediction: {e}")
+            text_len = len(text_input.encode("utf-8")) if isinstance(text_input, str) else sum(len(str(t).encode("utf-8")) for t in text_input)
+            ref_text_len = len(self.ref_text.encode("utf-8"))
+            return self.ref_audio_len + int(self.ref_audio_len / ref_text_len * text_len / local_speed)
+
+    def _chunk_duration(self, text_batch: str, speed: float, fix_duration, use_predictor: bool = False):
         local_speed = 0.3 if len(text_batch.encode("utf-8")) < 10 else speed
         if fix_duration is not None:
             return int(fix_duration * self.target_sample_rate / self.hop_length)
+        if use_predictor:
+            return self.calculate_duration_with_predictor(text_batch, local_speed)
         ref_text_len = len(self.ref_text.encode("utf-8"))
         gen_text_len = len(text_batch.encode("utf-8"))
         return self.ref_audio_len + int(self.ref_audio_len / ref_text_len * gen_text_len / local_speed)
@@ -212,6 +253,8 @@ class F5TTSWrapper:
         speed = speed if speed is not None else self.speed
         fix_duration = fix_duration if fix_duration is not None else self.fix_duration
         cross_fade_duration = cross_fade_duration if cross_fade_duration is not None else self.cross_fade_duration
+        use_predictor = use_duration_predictor if use_duration_predictor is not None else self.use_duration_predictor
+        can_use_predictor = bool(use_predictor and self.has_duration_predictor)
 
         audio_len = self.ref_audio_processed.shape[-1] / self.target_sample_rate
         max_chars = int(len(self.ref_text.encode("utf-8")) / audio_len * (22 - audio_len))
@@ -233,7 +276,7 @@ class F5TTSWrapper:
         with torch.inference_mode():
             if batch_chunks and len(text_batches) > 1:
                 texts = convert_char_to_pinyin([self.ref_text + tb for tb in text_batches])
-                durs = torch.tensor([self._chunk_duration(tb, speed, fix_duration) for tb in text_batches], dtype=torch.long)
+                durs = torch.tensor([self._chunk_duration(tb, speed, fix_duration, can_use_predictor) for tb in text_batches], dtype=torch.long)
                 cond = self.ref_audio_processed.expand(len(text_batches), -1)
                 generated, _ = self.model.sample(cond=cond, text=texts, duration=durs, steps=nfe_step, cfg_strength=cfg_strength,
                                                  sway_sampling_coef=sway_sampling_coef, seed=seed, return_trajectory=False)
@@ -244,7 +287,7 @@ class F5TTSWrapper:
             else:
                 for text_batch in text_batches:
                     final_text_list = convert_char_to_pinyin([self.ref_text + text_batch])
-                    duration = self._chunk_duration(text_batch, speed, fix_duration)
+                    duration = self._chunk_duration(text_batch, speed, fix_duration, can_use_predictor)
                     generated, _ = self.model.sample(cond=self.ref_audio_processed, text=final_text_list, duration=duration,
                                                      steps=nfe_step, cfg_strength=cfg_strength,
                                                      sway_sampling_coef=sway_sampling_coef, seed=seed, return_trajectory=False)

@@ -170,6 +170,25 @@ def test_wrapper_generate_end_to_end(tmp_path):
     assert pcm.dtype == np.int16 and np.array_equal(pcm, np.int16(np.clip(wave_d * np.float32(32767), -32768, 32767)))
     out = w.generate("short text here.", output_path=str(tmp_path / "o.wav"), nfe_step=2)
     assert out.endswith("o.wav") and (tmp_path / "o.wav").stat().st_size > 1000
+    # duration-predictor variant of the wrapper (model/f5tts_wrapper-dur_pred.py): chunk duration = ref frames + predicted frames / speed
+    from eraxvif5tts_b200.model import DurationPredictor
+    torch.manual_seed(1)
+    dp = DurationPredictor(len(vocab), 32, 16, 3, 0.5)
+    with torch.no_grad():
+        dp.proj.bias.fill_(1.0)  # exp(1) = 2.7 frames per character
+    w.attach_duration_predictor(dp)
+    chunk = "hello there, general."
+    d = w.calculate_duration_with_predictor(chunk, 1.0)
+    from oracle import align_oracle as A
+    from eraxvif5tts_b200.model.utils import list_str_to_idx
+    ids = list_str_to_idx([chunk], vocab)
+    want = w.ref_audio_len + int(torch.exp(torch.clamp(A.duration_predictor(dp.cpu().state_dict(), ids, torch.ones_like(ids), 1), -20, 20)).sum())
+    dp.cuda()
+    assert abs(d - want) <= 1
+    wave_p, _ = w.generate(chunk, nfe_step=2, return_numpy=True, seed=0)
+    assert abs(wave_p.size - 256 * (d - w.ref_audio_len - 1)) <= 256 * 2
+    wave_r, _ = w.generate(chunk, nfe_step=2, return_numpy=True, seed=0, use_duration_predictor=False)
+    assert wave_r.size != wave_p.size
 
 
 def test_device_crossfade_fold_matches_numpy_fold():
