@@ -128,3 +128,109 @@ def load_model(model_cls, model_cfg, ckpt_path, mel_spec_type=mel_spec_type, voc
     if ckpt_path:
         model = load_checkpoint(model, ckpt_path, device, use_ema=use_ema)
     return model
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# infer_process / infer_batch_process (utils_infer.py:366-563): the call sites the reference's api.py, CLI, Gradio app and socket
+# server go through.  Same arguments and yields; `batch_chunks` (extension) samples all chunks as ONE ragged batch
+# instead of the reference's thread pool of B=1 sample() calls, and the cross-fade fold runs on the device.
+
+def infer_process(ref_audio, ref_text, gen_text, model_obj, vocoder, mel_spec_type=mel_spec_type, show_info=print, progress=None,
+                  target_rms=target_rms, cross_fade_duration=cross_fade_duration, nfe_step=nfe_step, cfg_strength=cfg_strength,
+                  sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration, device="cuda", batch_chunks=True):
+    """utils_infer.py:366-410.  ref_audio: a wav path, or (audio [channels, samples], sample_rate)."""
+    if isinstance(ref_audio, (str, os.PathLike)):
+        from .f5tts_wrapper import _read_wav
+        audio, sr = _read_wav(str(ref_audio))
+    else:
+        audio, sr = ref_audio
+        audio = torch.as_tensor(audio, dtype=torch.float32)
+        if audio.ndim == 1:
+            audio = audio.unsqueeze(0)
+    max_chars = int(len(ref_text.encode("utf-8")) / (audio.shape[-1] / sr) * (22 - audio.shape[-1] / sr))
+    gen_text_batches = chunk_text(gen_text, max_chars=max_chars)
+    show_info(f"Generating audio in {len(gen_text_batches)} batches...")
+    return next(infer_batch_process((audio, sr), ref_text, gen_text_batches, model_obj, vocoder, mel_spec_type=mel_spec_type,
+                                    progress=progress, target_rms=target_rms, cross_fade_duration=cross_fade_duration, nfe_step=nfe_step,
+                                    cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, speed=speed,
+                                    fix_duration=fix_duration, device=device, batch_chunks=batch_chunks))
+
+
+def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocoder, mel_spec_type="vocos", progress=None, target_rms=0.1,
+                        cross_fade_duration=0.15, nfe_step=32, cfg_strength=2.0, sway_sampling_coef=-1, speed=1, fix_duration=None,
+                        device="cuda", streaming=False, chunk_size=2048, batch_chunks=True, seed=None):
+    """utils_infer.py:417-563 (a generator, like the reference).  streaming=False yields (final_wave, sample_rate,
+    combined_spectrogram) once; streaming=True yields (chunk of <= chunk_size samples, sample_rate) per piece, text chunk by text
+    chunk.  `progress` is accepted for signature compatibility (tqdm wrappers are control plane)."""
+    import numpy as np
+    from .. import ops
+    from .f5tts_wrapper import convert_char_to_pinyin
+    if mel_spec_type != "vocos":
+        raise NotImplementedError("only the vocos mel / vocoder pair is built (BigVGAN is an absent submodule of the reference)")
+    audio, sr = ref_audio
+    audio = torch.as_tensor(audio, dtype=torch.float32)
+    if audio.ndim == 1:
+        audio = audio.unsqueeze(0)
+    if audio.shape[0] > 1:
+        audio = torch.mean(audio, dim=0, keepdim=True)
+    rms = torch.sqrt(torch.mean(torch.square(audio)))
+    if rms < target_rms:
+        audio = audio * target_rms / rms
+    if sr != target_sample_rate:
+        import torchaudio
+        audio = torchaudio.transforms.Resample(sr, target_sample_rate)(audio)
+    audio = audio.to(device)
+    if len(ref_text[-1].encode("utf-8")) == 1:
+        ref_text = ref_text + " "
+    ref_audio_len = audio.shape[-1] // hop_length
+
+    def chunk_duration(gen_text):
+        local_speed = 0.3 if len(gen_text.encode("utf-8")) < 10 else speed
+        if fix_duration is not None:
+            return int(fix_duration * target_sample_rate / hop_length)
+        ref_text_len, gen_text_len = len(ref_text.encode("utf-8")), len(gen_text.encode("utf-8"))
+        return ref_audio_len + int(ref_audio_len / ref_text_len * gen_text_len / local_speed)
+
+    def finish(gen_mel):  # [1, n, mel] with the reference part attached -> (wave on the device, mel [mel, n_gen] on the host)
+        g = gen_mel.to(torch.float32)[:, ref_audio_len:, :].permute(0, 2, 1)
+        wave = vocoder.decode(g)
+        if rms < target_rms:
+            wave = wave * rms / target_rms
+        return wave.reshape(-1), g[0].cpu().numpy()
+
+    def sample(texts, durations):
+        with torch.inference_mode():
+            out, _ = model_obj.sample(cond=audio.expand(len(texts), -1) if len(texts) > 1 else audio, text=convert_char_to_pinyin(texts),
+                                      duration=durations, steps=nfe_step, cfg_strength=cfg_strength,
+                                      sway_sampling_coef=sway_sampling_coef, seed=seed, return_trajectory=False)
+        return out
+
+    def results():
+        """(wave, mel) per text chunk, in order"""
+        if batch_chunks and len(gen_text_batches) > 1 and not streaming:
+            texts = [ref_text + t for t in gen_text_batches]
+            durs = torch.tensor([chunk_duration(t) for t in gen_text_batches], dtype=torch.long)
+            out = sample(texts, durs.to(device))
+            cond_frames = ref_audio_len + 1
+            durs_eff = torch.maximum(durs, torch.tensor([len(t) for t in convert_char_to_pinyin(texts)]).clamp(min=cond_frames) + 1)
+            for i in range(len(texts)):
+                yield finish(out[i:i + 1, : int(min(durs_eff[i], out.shape[1]))])
+        else:
+            for t in gen_text_batches:
+                yield finish(sample([ref_text + t], chunk_duration(t)))
+
+    if streaming:
+        for wave, _ in results():
+            w = wave.cpu().numpy()
+            for j in range(0, len(w), chunk_size):
+                yield w[j:j + chunk_size], target_sample_rate
+        return
+    waves, mels = [], []
+    for wave, mel in results():
+        waves.append(wave)
+        mels.append(mel)
+    if not waves:
+        yield None, target_sample_rate, None
+        return
+    final = ops.crossfade_concat(waves, int(cross_fade_duration * target_sample_rate) if cross_fade_duration > 0 else 0)
+    yield final.cpu().numpy(), target_sample_rate, np.concatenate(mels, axis=1)

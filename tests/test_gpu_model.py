@@ -170,6 +170,22 @@ def test_wrapper_generate_end_to_end(tmp_path):
     assert pcm.dtype == np.int16 and np.array_equal(pcm, np.int16(np.clip(wave_d * np.float32(32767), -32768, 32767)))
     out = w.generate("short text here.", output_path=str(tmp_path / "o.wav"), nfe_step=2)
     assert out.endswith("o.wav") and (tmp_path / "o.wav").stat().st_size > 1000
+    # utils_infer.infer_process / infer_batch_process (the call sites of the reference's api.py / CLI / socket server)
+    from eraxvif5tts_b200.infer import utils_infer as UI
+    ref_in = (ref.unsqueeze(0), 24000)
+    wave_i, sr_i, spec_i = UI.infer_process(ref_in, "this is a reference. ", text, w.model, w.vocoder, nfe_step=2, batch_chunks=False,
+                                            show_info=lambda *_: None)
+    assert sr_i == 24000 and wave_i.ndim == 1 and np.isfinite(wave_i).all() and spec_i.shape[0] == 100
+    wave_j, _, spec_j = UI.infer_process(ref_in, "this is a reference. ", text, w.model, w.vocoder, nfe_step=2, batch_chunks=True,
+                                         show_info=lambda *_: None)
+    assert abs(wave_j.size - wave_i.size) <= 256 * 4 and abs(spec_j.shape[1] - spec_i.shape[1]) <= 4
+    chunks = chunk_chars = UI.chunk_text(text, max_chars=int(len("this is a reference. ".encode()) / 2.0 * (22 - 2.0)))
+    pieces = list(UI.infer_batch_process(ref_in, "this is a reference. ", chunks, w.model, w.vocoder, nfe_step=2, streaming=True,
+                                         chunk_size=2048))
+    assert all(sr_ == 24000 and 0 < len(c_) <= 2048 for c_, sr_ in pieces)
+    cfs = int(0.15 * 24000)
+    assert sum(len(c_) for c_, _ in pieces) == wave_i.size + (len(chunks) - 1) * cfs
+    assert next(UI.infer_batch_process(ref_in, "this is a reference. ", [], w.model, w.vocoder))[0] is None
     # duration-predictor variant of the wrapper (model/f5tts_wrapper-dur_pred.py): chunk duration = ref frames + predicted frames / speed
     from eraxvif5tts_b200.model import DurationPredictor
     torch.manual_seed(1)
