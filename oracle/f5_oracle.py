@@ -412,6 +412,8 @@ def cfm_sample(sd, cfg: DiTConfig, cond, text, duration, *, lens=None, steps=32,
 # --------------------------------------------------------------------------------------
 
 def cfm_loss(sd, cfg: DiTConfig, x1, text, rand_span_mask, x0, time, drop_audio_cond, drop_text, dropout=None):
+    """CFM.forward, model/cfm.py:210-283, with the call's random draws as arguments.  Pinned (loss, pred and autograd gradients)
+    against the reference's own CFM.forward + loss.backward() by tests/test_oracle_golden.py on tests/golden/cfm_forward_*.pt."""
     t = time[:, None, None]
     phi = (1 - t) * x0 + t * x1
     flow = x1 - x0

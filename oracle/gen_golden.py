@@ -73,6 +73,66 @@ def gen_sample(cfg: DiTConfig, tag: str, batch, ref_frames, total, steps, method
                                    sway=-1.0, sample_seed=0, out=out, traj_last=traj[-1], traj_1=traj[1]))
 
 
+GRAD_KEYS = ("transformer.proj_out.weight", "transformer.norm_out.linear.weight", "transformer.transformer_blocks.0.attn.to_q.weight",
+             "transformer.transformer_blocks.0.attn.to_k.bias", "transformer.transformer_blocks.1.attn.to_out.0.weight",
+             "transformer.transformer_blocks.0.attn_norm.linear.weight", "transformer.transformer_blocks.1.ff.ff.0.0.weight",
+             "transformer.transformer_blocks.1.ff.ff.2.bias", "transformer.input_embed.proj.weight",
+             "transformer.input_embed.conv_pos_embed.conv1d.0.weight", "transformer.text_embed.text_embed.weight",
+             "transformer.text_embed.text_blocks.0.grn.gamma", "transformer.time_embed.time_mlp.0.weight")
+
+
+def gen_cfm_forward(cfg: DiTConfig, tag: str, drop_audio_cond: bool, drop_text: bool, batch=3, n=88, seed=0):
+    """The reference's own CFM.forward (cfm.py:210-283) + loss.backward(), with its internal random draws RECORDED (span mask, x0,
+    time) and its two `random()` calls forced, so the oracle's cfm_loss can be pinned on identical draws.  eval() mode: the DiT's
+    nn.Dropout sites are off (parity is defined at dropout 0).  Stored: loss, cond, pred, the L2 norm of EVERY parameter
+    gradient and the first 4096 entries of a representative subset of them."""
+    sd = make_dit_state_dict(cfg, seed)
+    model = ref_shim.build_reference_cfm(cfg, sd)
+    cfmmod = ref_shim.load().cfm
+    g = torch.Generator().manual_seed(21)
+    x1 = (torch.randn(batch, n, cfg.mel_dim, generator=g) * 2 - 1.5).clamp(-11.5, 5)
+    text = torch.randint(0, cfg.text_num_embeds, (batch, 14), generator=g)
+    text[1, 9:] = -1
+    lens = torch.tensor([n, n - 13, n - 40][:batch])
+    rec = {}
+    orig_mask, orig_randn_like, orig_rand, orig_random = cfmmod.mask_from_frac_lengths, torch.randn_like, torch.rand, cfmmod.random
+    draws = iter([0.0 if drop_audio_cond else 0.99, 0.0 if drop_text else 0.99])
+
+    def mask_fn(seq_len, frac):
+        m = orig_mask(seq_len, frac)
+        rec["span_raw"] = m.clone()
+        return m
+
+    def randn_like(t, *a, **k):
+        r = orig_randn_like(t, *a, **k)
+        if t.shape == x1.shape:
+            rec["x0"] = r.clone()
+        return r
+
+    def rand(*a, **k):
+        r = orig_rand(*a, **k)
+        if tuple(r.shape) == (batch,):
+            rec["time"] = r.clone()
+        return r
+
+    cfmmod.mask_from_frac_lengths, torch.randn_like, torch.rand, cfmmod.random = mask_fn, randn_like, rand, lambda: next(draws)
+    try:
+        torch.manual_seed(123)
+        for p_ in model.parameters():
+            p_.requires_grad_(True)
+        loss, cond, pred = model(x1, text, lens=lens)
+        loss.backward()
+    finally:
+        cfmmod.mask_from_frac_lengths, torch.randn_like, torch.rand, cfmmod.random = orig_mask, orig_randn_like, orig_rand, orig_random
+    mask = torch.arange(n)[None, :] < lens[:, None]
+    grads = {k: p_.grad.detach().clone() for k, p_ in model.named_parameters() if p_.grad is not None}
+    assert all(k in grads for k in GRAD_KEYS), [k for k in GRAD_KEYS if k not in grads]
+    _save(f"cfm_forward_{tag}.pt", dict(cfg=asdict(cfg), seed=seed, digest=state_dict_digest(sd), x1=x1, text=text, lens=lens,
+                                        span=rec["span_raw"] & mask, x0=rec["x0"], time=rec["time"], drop_audio_cond=drop_audio_cond,
+                                        drop_text=drop_text, loss=loss.detach(), cond=cond.detach(), pred=pred.detach(),
+                                        grads={k: grads[k].flatten()[:4096].clone() for k in GRAD_KEYS}, grad_norms={k: float(v.norm()) for k, v in grads.items()}))
+
+
 def main():
     if not ref_shim.available():
         sys.exit("reference tree not present; golden vectors can only be generated in the build container")
@@ -83,6 +143,8 @@ def main():
     gen_sample(DiTConfig.tiny(), "tiny_b2", batch=2, ref_frames=40, total=[96, 83], steps=4)
     gen_sample(DiTConfig.tiny(), "tiny_b1", batch=1, ref_frames=40, total=90, steps=4)
     gen_sample(DiTConfig.tiny(), "tiny_mid", batch=2, ref_frames=40, total=[70, 64], steps=3, method="midpoint")
+    gen_cfm_forward(DiTConfig.tiny(), "tiny_cond", False, False)
+    gen_cfm_forward(DiTConfig.tiny(), "tiny_uncond", True, True)
 
 
 if __name__ == "__main__":

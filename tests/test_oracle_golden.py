@@ -91,3 +91,31 @@ def test_oracle_vs_live_reference_sample():
     out, traj = O.cfm_sample(sd, cfg, cond, text, duration, lens=lens, steps=2, cfg_strength=2.0,
                              sway_sampling_coef=-1.0, seed=0)
     assert (out - ref_out).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["tiny_cond", "tiny_uncond"])
+def test_cfm_loss_and_autograd_match_reference_cfm_forward(tag):
+    """oracle.cfm_loss (the checker of the GPU training step) against the reference's own CFM.forward + loss.backward() on the draws
+    that call made (tests/golden/cfm_forward_*.pt, oracle/gen_golden.py::gen_cfm_forward): loss, cond, pred, the norm of every
+    parameter gradient and the leading entries of a representative subset."""
+    import os
+    d = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"cfm_forward_{tag}.pt"))
+    cfg = O.DiTConfig(**d["cfg"])
+    sd = make_dit_state_dict(cfg, d["seed"])
+    leaf = {k: v.clone().float().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    full = dict(sd)
+    full.update(leaf)
+    loss, cond, pred = O.cfm_loss(full, cfg, d["x1"], d["text"], d["span"], d["x0"], d["time"], d["drop_audio_cond"], d["drop_text"])
+    assert abs(float(loss) - float(d["loss"])) <= 1e-5 * float(d["loss"])
+    assert torch.equal(cond, d["cond"])
+    assert float((pred - d["pred"]).abs().max()) <= 1e-4
+    loss.backward()
+    for k, n in d["grad_norms"].items():
+        g = leaf[k].grad
+        if n < 1e-12:
+            assert g is None or float(g.norm()) < 1e-9, k
+            continue
+        assert g is not None and abs(float(g.norm()) - n) <= 2e-3 * n + 1e-9, (k, float(g.norm()), n)
+    for k, r in d["grads"].items():
+        g = leaf[k].grad.flatten()[: r.numel()]
+        assert float((g - r).norm()) <= 2e-3 * float(r.norm()) + 1e-9, k
