@@ -77,6 +77,7 @@ SIGNATURES = {
     "f5b_dit_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
     "f5b_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, sz, vp]),
     "f5b_dit_train_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
+    "f5b_set_dependent_launch": (C.c_int, [C.c_int]),
     "f5b_crossfade_append": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp]),
     "f5b_pcm16": (C.c_int, [vp, vp, C.c_int64, vp]),
     "f5b_align_viterbi": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -155,8 +156,19 @@ def load() -> C.CDLL:
         raise F5bError("libf5b200.so ABI version mismatch; rebuild")
     if os.environ.get("F5B_ATTN_VARIANT"):  # kernel A/B switch for experiments (0 = default)
         lib.f5b_debug_attn_variant(int(os.environ["F5B_ATTN_VARIANT"]))
+    if os.environ.get("F5B_PDL"):  # A/B override of set_dependent_launch() below
+        lib.f5b_set_dependent_launch(int(os.environ["F5B_PDL"]))
     _lib = lib
     return lib
+
+
+PDL_MAX_ROWS = 16384  # fused rows (2B x n) up to which an ODE step is launch-bound enough for dependent launches to pay
+
+
+def set_dependent_launch(on: bool) -> None:
+    """f5b_set_dependent_launch (include/f5b200.h) unless F5B_PDL pins it for an experiment"""
+    if not os.environ.get("F5B_PDL"):
+        load().f5b_set_dependent_launch(int(bool(on)))
 
 
 KERNEL_KINDS = ("gemm", "attention", "convpos", "norm", "elementwise", "spectral")

@@ -161,6 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (kvlen <= 0 || q0 >= kvlen) {
     // whole tile is padding: the reference zeroes these rows after to_out (model/modules.py:499-501)
+    griddep_wait();
     if (warp < 4) {
       const int pos = q0 + warp * 32 + lane;
       if (pos < p.n) {
@@ -199,6 +200,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 64;
+  griddep_wait();  // PDL: q / k / v (the QKV GEMM's output) are first read below
+  griddep_launch_dependents();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -472,7 +475,7 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  F5B_CUDA(launch_dep(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,8 @@
 // Shared device/host helpers for the sm_100a kernels: error plumbing, mbarrier / TMA / tcgen05 PTX wrappers.
 // Everything here is written for sm_100a only (tcgen05, TMEM, TMA); there is no fallback path.
 #pragma once
+#include <utility>
+#include <cstring>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -37,6 +39,38 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
                  bool swizzle128);
 int sm_count();
+
+// Programmatic dependent launch (PDL) for the launch-bound B = 1 ODE step: kernels on the DiT forward path execute
+// griddepcontrol.wait after their prologue (barrier init, TMEM allocation, tensor-map prefetch) and before touching any global
+// memory, so when they are launched with the programmatic-stream-serialization attribute their prologue overlaps the previous
+// kernel's tail.  Without the attribute both instructions are no-ops.  Only kernels that contain the wait may be launched with it.
+extern int g_pdl;  // host.cu; f5b_set_dependent_launch()
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline leg) ------------------------
 enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_CONVPOS = 2, K_NORM = 3, K_ELEMENTWISE = 4, K_SPECTRAL = 5, K_NUM = 6 };
@@ -112,6 +146,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- TMA
+// see launch_dep(): wait = the previous grid in the stream has completed and its writes are visible; launch_dependents = the next
+// grid may start scheduling its CTAs (it still waits for this grid's completion in its own griddepcontrol.wait)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

@@ -167,6 +167,8 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL (common.cuh): the prologue above overlaps the previous kernel's tail
+  griddep_launch_dependents();
   const int total = p.B * n_super * p.groups;  // super-tiles
   const int ks = p.ksize;
   // super-tile u -> (b, st, g), g fastest; number of live 128-row sub-tiles
@@ -287,7 +289,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const int n_super = (p.n + HALO_SUB * BM - 1) / (HALO_SUB * BM);
   const int total = p.B * n_super * p.groups;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, ENGINE_THREADS, HALO_SMEM, stream>>>(tmA, tmB, p, n_super);
+  F5B_CUDA(launch_dep(kern, dim3(grid), dim3(ENGINE_THREADS), HALO_SMEM, stream, 1, tmA, tmB, p, n_super));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           const float* __restrict__ shift, int64_t mod_bstride,
                                                           int batch_mod, __nv_bfloat16* __restrict__ out, int rows,
                                                           int rows_per_batch, int D, float eps) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -69,10 +71,10 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int64_t 
   LaunchScope scope(K_NORM, s, 0, 6.0 * rows * D);
   auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = D / 4;
-  if (nvec <= 32 * 2) ln_modulate_kernel<2><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
-  else if (nvec <= 32 * 4) ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
-  else if (nvec <= 32 * 8) ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
-  else ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps);
+  if (nvec <= 32 * 2) F5B_CUDA(launch_dep(ln_modulate_kernel<2>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else if (nvec <= 32 * 4) F5B_CUDA(launch_dep(ln_modulate_kernel<4>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else if (nvec <= 32 * 8) F5B_CUDA(launch_dep(ln_modulate_kernel<8>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else F5B_CUDA(launch_dep(ln_modulate_kernel<16>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -358,6 +360,8 @@ int ln_affine(const float* x, const float* w, const float* b, float* out_f32, vo
 __global__ void cfg_euler_kernel(float* __restrict__ y, const float* __restrict__ pc, const float* __restrict__ pu, float cfg,
                                  float dt, const float* __restrict__ dev_params, __nv_bfloat16* __restrict__ ybf, int ld_bf,
                                  float* __restrict__ vel, int rows, int C) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * ld_bf) return;
   if (dev_params != nullptr) {  // (cfg, dt) live in device memory so a captured CUDA graph can be replayed for every ODE step
@@ -574,8 +578,8 @@ int f5b_cfg_euler(float* y, const float* pc, const float* pu, float cfg, float d
   F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C, "f5b_cfg_euler: bad shape");
   const int64_t tot = (int64_t)rows * ld_bf;
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
-  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, cfg, dt, nullptr,
-                                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C);
+  F5B_CUDA(launch_dep(cfg_euler_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, ST(stream), 1, y, pc, pu, cfg, dt,
+                      (const float*)nullptr, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -585,8 +589,8 @@ int f5b_cfg_euler_dev(float* y, const float* pc, const float* pu, const float* p
   F5B_CHECK(rows > 0 && C > 0 && ld_bf >= C && params_dev != nullptr, "f5b_cfg_euler_dev: bad argument");
   const int64_t tot = (int64_t)rows * ld_bf;
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (pu ? 16.0 : 12.0) * rows * C + (y_bf16 ? 2.0 * tot : 0.0));
-  cfg_euler_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(y, pc, pu, 0.f, 0.f, params_dev,
-                                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C);
+  F5B_CUDA(launch_dep(cfg_euler_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, ST(stream), 1, y, pc, pu, 0.f, 0.f, params_dev,
+                      reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf, vel_out, rows, C));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -152,6 +152,8 @@ LaunchScope::~LaunchScope() {
   if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], s);
 }
 
+int g_pdl = 0;  // f5b_set_dependent_launch(): the Python host turns it on for the launch-bound regimes (see include/f5b200.h)
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -213,3 +215,8 @@ int f5b_prof_read(double* out, int n_kinds) {
 }
 
 }  // extern "C"
+
+extern "C" int f5b_set_dependent_launch(int on) {
+  f5b::g_pdl = on ? 1 : 0;
+  return 0;
+}

@@ -113,6 +113,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if constexpr (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL: everything above overlapped the previous kernel's tail; nothing global has been touched yet
+  griddep_launch_dependents();
 
   const int total = p.num_units();  // work units: tiles, or vertical tile pairs when CL == 2
   const int kblocks = p.num_kblocks();
@@ -292,24 +294,7 @@ static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   constexpr int CL = P::CLUSTER;
   const int max_clusters = sm_count() / CL;
   const int nclusters = total_units < max_clusters ? total_units : max_clusters;
-  if constexpr (CL == 1) {
-    kern<<<nclusters, ENGINE_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(nclusters * CL);
-    cfg.blockDim = dim3(ENGINE_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    F5B_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
-  }
+  F5B_CUDA(launch_dep(kern, dim3(nclusters * CL), dim3(ENGINE_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmC, p));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

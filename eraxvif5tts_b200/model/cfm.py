@@ -133,6 +133,8 @@ class CFM(nn.Module):
         genv = os.environ.get("F5B_CUDA_GRAPH", "")
         use_graph = (method == "euler" and genv != "0" and (genv == "1" or Bf * n <= GRAPH_MAX_ROWS)
                      and not L.load().f5b_prof_enabled())
+        # dependent launches (kernel prologues under the previous kernel's tail) pay in the launch-bound regime only
+        L.set_dependent_launch(Bf * n <= L.PDL_MAX_ROWS)
         sess = eng.step_session(batch, Bf, n, lens32 is not None) if use_graph else None
         c0 = sess["c0"] if use_graph else torch.empty(Bf, n, eng.dim, dtype=f32, device=device)
         te_c = eng.text_embed(text, n, False)
