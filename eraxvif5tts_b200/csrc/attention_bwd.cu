@@ -90,6 +90,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (kvlen <= 0 || k0 >= kvlen) {
     // masked keys receive no gradient
+    griddep_wait();
     if (warp >= 2 && warp < 10) {
       const int t = threadIdx.x - 64;  // 0..255
       const int row = t >> 1, half = t & 1;
@@ -130,6 +131,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL (common.cuh): prologue under the previous kernel's tail
+  griddep_launch_dependents();
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384,
                  tm_PT = tmem_base + 448;  // P^T as bf16 pairs: 64 columns = 128 queries (A operand of dV, read from tensor memory)
 
@@ -502,7 +505,7 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.rope_heads = rope_heads;
   p.trace = g_attn_bwd_trace;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
-  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  F5B_CUDA(launch_dep(attn_bwd_kernel, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
   F5B_CUDA(cudaGetLastError());
   const long long items = rows * (D >> 3);
   attn_dq_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(dq_ws, p.dqkv, ld_d, rope, rope_heads, rows, n, D);

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
                                                               const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ dz,
                                                               float* __restrict__ dgate, float* __restrict__ dbias, int n, int C,
                                                               const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * CT_ROWS;
   const int p1 = min(n, p0 + CT_ROWS);
@@ -147,6 +149,8 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
 }
 
 __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n8, int act, const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 elements (16-byte accesses)
   if (i >= n8) return;
   const uint4 v = reinterpret_cast<const uint4*>(h)[i];
@@ -173,6 +177,8 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat1
 __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16* du, const __nv_bfloat16* __restrict__ h,
                                                              __nv_bfloat16* dh /* may alias du */, float* __restrict__ dbias, int64_t rows,
                                                              int C, int ld, int act, const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int64_t r0 = (int64_t)blockIdx.x * CT_ROWS;
   const int64_t r1 = min(rows, r0 + CT_ROWS);
   for (int c = threadIdx.x * 4; c < C; c += 4 * CT_THREADS) {
@@ -225,6 +231,8 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
                                                          int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
                                                          int D, float eps, int affine) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   extern __shared__ float4 ln_acc4[];  // [8 warps][2][D/4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -575,6 +583,8 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           int64_t mod_bstride, __nv_bfloat16* __restrict__ out, int n, int D, float eps,
                                                           const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int pos = blockIdx.x * 8 + warp;
@@ -674,9 +684,9 @@ static int gate_add_ln_launch(const float* x, const void* z_bf16, const float* g
   auto* zz = reinterpret_cast<const __nv_bfloat16*>(z_bf16);
   auto* oo = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   const int nvec = D / 4;
-  if (nvec <= 64) gate_add_ln_kernel<2><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
-  else if (nvec <= 128) gate_add_ln_kernel<4><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
-  else gate_add_ln_kernel<8><<<grid, 256, 0, ST(stream)>>>(x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr);
+  if (nvec <= 64) F5B_CUDA(launch_dep(gate_add_ln_kernel<2>, grid, dim3(256), 0, ST(stream), 1, x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr));
+  else if (nvec <= 128) F5B_CUDA(launch_dep(gate_add_ln_kernel<4>, grid, dim3(256), 0, ST(stream), 1, x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr));
+  else F5B_CUDA(launch_dep(gate_add_ln_kernel<8>, grid, dim3(256), 0, ST(stream), 1, x, zz, gate, gate_bstride, lens, x_out, scale, shift, mod_bstride, oo, n, D, eps, dr));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -691,9 +701,9 @@ static int gate_bwd_launch(const float* dx, const void* z_bf16, const float* gat
                            float* dgate, float* dbias, int B, int n, int C, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 3) == 0 && (gate_bstride & 3) == 0, "f5b_gate_bwd: C and the gate stride must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * B * n * C);
-  gate_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), CT_THREADS, 0, ST(stream)>>>(
-      dx, reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16), dgate, dbias,
-      n, C, dr);
+  F5B_CUDA(launch_dep(gate_bwd_kernel, dim3((n + CT_ROWS - 1) / CT_ROWS, B), dim3(CT_THREADS), 0, ST(stream), 1, dx,
+                      reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16),
+                      dgate, dbias, n, C, dr));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -705,8 +715,8 @@ int f5b_gate_bwd(const float* dx, const void* z_bf16, const float* gate, int64_t
 static int act_fwd_launch(const void* h_bf16, void* out_bf16, int64_t count, int act, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(h_bf16 && out_bf16 && count > 0 && (count & 7) == 0, "f5b_act_fwd: count must be a multiple of 8");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * count);
-  act_fwd_kernel<<<(unsigned)((count / 8 + 255) / 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16),
-                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 8, act, dr);
+  F5B_CUDA(launch_dep(act_fwd_kernel, dim3((unsigned)((count / 8 + 255) / 256)), dim3(256), 0, ST(stream), 1,
+                      reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), count / 8, act, dr));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -718,9 +728,9 @@ static int act_bwd_launch(const void* du_bf16, const void* h_bf16, void* dh_bf16
                           const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 3) == 0 && (ld & 3) == 0 && ld >= C, "f5b_act_bwd: C and ld must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * rows * C);
-  act_bwd_kernel<<<(unsigned)((rows + CT_ROWS - 1) / CT_ROWS), CT_THREADS, 0, ST(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<__nv_bfloat16*>(dh_bf16),
-      dbias, rows, C, ld, act, dr);
+  F5B_CUDA(launch_dep(act_bwd_kernel, dim3((unsigned)((rows + CT_ROWS - 1) / CT_ROWS)), dim3(CT_THREADS), 0, ST(stream), 1,
+                      reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16),
+                      reinterpret_cast<__nv_bfloat16*>(dh_bf16), dbias, rows, C, ld, act, dr));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -774,9 +784,9 @@ static int ln_bwd_launch(const void* dy_bf16, const float* x, const float* scale
   }
   auto* d = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   const int nvec = D / 4;
-  if (nvec <= 64) ln_mod_bwd_kernel<2><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
-  else if (nvec <= 128) ln_mod_bwd_kernel<4><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
-  else ln_mod_bwd_kernel<8><<<grid, 256, sm, ST(stream)>>>(d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine);
+  if (nvec <= 64) F5B_CUDA(launch_dep(ln_mod_bwd_kernel<2>, grid, dim3(256), sm, ST(stream), 1, d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine));
+  else if (nvec <= 128) F5B_CUDA(launch_dep(ln_mod_bwd_kernel<4>, grid, dim3(256), sm, ST(stream), 1, d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine));
+  else F5B_CUDA(launch_dep(ln_mod_bwd_kernel<8>, grid, dim3(256), sm, ST(stream), 1, d, x, scale, mod_bstride, dx, accumulate, dscale, dshift, n, D, eps, affine));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -279,7 +279,7 @@ class TrainEngine:
         ws = self.workspace(nbytes)
         rope = self.rope_table(n)
         pred = torch.empty(B, n, C_, dtype=f32, device=dev)
-        L.set_dependent_launch(True)  # 107.4 -> 104.5 ms per cfg-5 step (include/f5b200.h: f5b_set_dependent_launch)
+        L.set_dependent_launch(False)  # GPU-bound: A/B 105.3 / 106.4 ms off vs 106.4 / 105.9 ms on (include/f5b200.h)
         # the dropout masks of this micro-step are a function of this seed; the backward below regenerates them
         seed = int(draws["dropout_seed"]) if "dropout_seed" in draws else int(torch.randint(0, 2 ** 62, (1,)).item())
         L.check(lib.f5b_train_set_dropout(self.dropout, seed), "f5b_train_set_dropout")

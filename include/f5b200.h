@@ -391,9 +391,9 @@ void f5b_prof_add(const double* delta, int n_kinds);
 /* Programmatic dependent launch for the kernels of the DiT forward path (GEMM engine, attention, conv_pos_embed, LN + modulate,
  * CFG / Euler): with on != 0 they are launched with the programmatic-stream-serialization attribute and run their prologue (barrier
  * init, TMEM allocation, tensor-map prefetch) under the previous kernel's tail, waiting (griddepcontrol.wait) before they touch
- * global memory.  Measured on B200: B = 1 ODE step 77.4 -> 75.3 ms per utterance, training step 107.4 -> 104.5 ms, but 22.4 k ->
- * 22.0 k frames/s for the GPU-bound cfg-2 batch, so the Python host switches it on for fused batches of <= 16384 rows and for
- * training, off otherwise.  Process-global; default off. */
+ * global memory.  Measured on B200 (A/B on one box, twice each): B = 1 utterance 77.4 -> 75.3 ms; no measurable change for the
+ * training step (105.3 / 106.4 ms off, 106.4 / 105.9 ms on); 22.4 k -> 22.0 k frames/s for the GPU-bound cfg-2 batch.  So the
+ * Python host switches it on for fused batches of <= 16384 rows only.  Process-global; default off. */
 int f5b_set_dependent_launch(int on);
 
 /* ---- on-device chunk cross-fade + PCM packing ---- */
