@@ -691,6 +691,8 @@ def main():
     launches = launches_timed
     config["cuda_graph"] = ("one captured graph per ODE step (replayed 32x per sample); kernel breakdown from one extra eager step"
                             if graph_mode else "off (GPU-bound batch; launches are event-bracketed live in the timed region)")
+    config["dependent_launch"] = ("on (fused batch <= 16384 rows: kernel prologues overlap the previous kernel's tail)" if 2 * B * total <= L.PDL_MAX_ROWS
+                                  else "off (GPU-bound batch; measured 1.8 % slower with it)")
     fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE * reps
     line = {"metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

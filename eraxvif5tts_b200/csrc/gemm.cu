@@ -236,7 +236,14 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? 2.0 : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
   LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
   const int m_tiles = (g.M + BM - 1) / BM;
-  const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= sm_count()) ? 256 : 128;
+  // 256-wide tiles (CTA pairs) once they fill about two thirds of the machine; below that 128-wide tiles give twice the units to
+  // spread.  Measured on the B = 1 shapes (M = 1880): threshold 148 tiles 75.4 ms per utterance, 98 -> 72.8 ms (FF1, 120 tiles, moves to
+  // pairs), 60 -> 76.5 ms (out-proj / FF2, 60 tiles, are better off with 128-wide tiles).  F5B_GEMM_BN256_MIN_TILES overrides it.
+  static const int min_tiles256 = [] {
+    const char* e = getenv("F5B_GEMM_BN256_MIN_TILES");
+    return e ? atoi(e) : sm_count() * 2 / 3;
+  }();
+  const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= min_tiles256) ? 256 : 128;
   CUtensorMap tmA, tmB;
   if (make_tmap_2d(&tmA, A, 2, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda * 2, BK, BM, true)) return -1;
   if (make_tmap_2d(&tmB, W, 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 2, BK, bn / 2, true)) return -1;  // half tile per CTA
