@@ -345,3 +345,58 @@ def test_dropout_mask_statistics():
         assert abs(both - (1 - p) ** 2) < 4e-3
         nb = float((keep_a[:, 1:] * keep_a[:, :-1]).mean())
         assert abs(nb - (1 - p) ** 2) < 4e-3
+
+
+def test_trainer_batching_and_sharding_host_logic():
+    """model.Trainer's host side without a GPU (the engine is not constructed): frame / sample batching, per-process sharding with
+    equal batch counts on every rank, epoch reshuffling under resumable_with_seed"""
+    import torch
+    from eraxvif5tts_b200.data import DynamicBatchSampler
+    from eraxvif5tts_b200.model.trainer import Trainer
+
+    class DS(torch.utils.data.Dataset):
+        lens = [50 + 7 * (i % 13) for i in range(57)]
+
+        def get_frame_len(self, i):
+            return self.lens[i]
+
+        def __len__(self):
+            return len(self.lens)
+
+        def __getitem__(self, i):
+            return dict(mel_spec=torch.zeros(100, self.lens[i]), text="ab")
+
+    ds = DS()
+
+    def make(rank, world, kind):
+        t = Trainer.__new__(Trainer)
+        t.batch_size_type, t.batch_size_per_gpu, t.max_samples = kind, (400 if kind == "frame" else 5), 6
+        t.rank, t.num_processes = rank, world
+        return t
+
+    ref = DynamicBatchSampler(torch.utils.data.SequentialSampler(ds), 400, max_samples=6, random_seed=3)
+    for world in (1, 2, 3):
+        per_rank = []
+        for r in range(world):
+            t = make(r, world, "frame")
+            sampler, gen = t._batches(ds, 3)
+            assert gen is None and sampler.batches == ref.batches
+            e0 = t._epoch_batches(ds, sampler, gen, 0)
+            e1 = t._epoch_batches(ds, sampler, gen, 1)
+            assert e0 != e1 or len(e0) <= 1  # set_epoch reshuffles
+            assert all(sum(ds.lens[i] for i in b) <= 400 and len(b) <= 6 for b in e0)
+            per_rank.append(e0)
+        assert len({len(p) for p in per_rank}) == 1  # every rank steps the same number of times (the all-reduce never starves)
+        flat = [i for p in per_rank for b in p for i in b]
+        assert len(flat) == len(set(flat))
+        if world == 1:
+            assert sorted(flat) == list(range(len(ds)))
+    t = make(0, 2, "sample")
+    sampler, gen = t._batches(ds, 7)
+    assert sampler is None
+    a = t._epoch_batches(ds, sampler, gen, 0)
+    b = t._epoch_batches(ds, sampler, gen, 1)
+    assert a != b and all(len(x) <= 5 for x in a) and len(a) == (len(ds) + 4) // 5 // 2
+    import pytest
+    with pytest.raises(ValueError):
+        make(0, 1, "tokens")._batches(ds, None)
