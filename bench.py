@@ -168,11 +168,17 @@ def build_product_models(arch, dev):
     return model.to(dev).eval(), voc.to(dev).eval()
 
 
-def cpu_port_measure(arch, ref_frames, total, steps, warmup, quiet=False):
-    """The CPU arm: oracle (fp32 torch restatement of the reference) on the host cores, bounded sample = ONE utterance of the
-    workload x ONE Euler step (cond + uncond DiT forwards) per timed step, + one text-embedding pair + one Vocos decode;
-    frames/s is extrapolated to the full NFE (the 32 steps are identical work)."""
+def cpu_reference_measure(arch, ref_frames, total, steps, warmup, full=False):
+    """The CPU arm.  When the reference's own modules are loadable (oracle/ref_shim: /root/reference in the build container, the
+    byte-compiled oracle/_ref/ on the GPU box) this times the REFERENCE ITSELF: its `CFM` / `DiT` classes, fp32, all host threads
+    (`kind: "reference"`; only the un-vendored third-party pieces — torchdiffeq's fixed-grid solver, x_transformers' rotary
+    embedding, the vocos vocoder — are the restatements of oracle/).  Otherwise the oracle port (`kind: "port"`).
+      full=False: bounded sample = ONE utterance of the workload x ONE Euler step (cond + uncond DiT.forward) per timed step, + one
+                  text-embedding pair + one Vocos decode; frames/s extrapolated to the NFE identical steps;
+      full=True : the complete CFM.sample (NFE steps, CFG, sway) + Vocos decode of one utterance per timed step (cfg-1, as BASELINE.md
+                  section 5.2 promises); at most one timed sample so the run stays within minutes."""
     from oracle import f5_oracle as O
+    from oracle import ref_shim
     from oracle.weights import make_dit_state_dict, make_vocos_state_dict, synthetic_inputs
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = O.DiTConfig(dim=arch.dim, depth=arch.depth, heads=arch.heads)
@@ -181,19 +187,52 @@ def cpu_port_measure(arch, ref_frames, total, steps, warmup, quiet=False):
     vsd = make_vocos_state_dict(vc, 1)
     cond, text, duration, lens = synthetic_inputs(cfg, 1, ref_frames, total, seed=1234)
     n = total
-    step_cond = torch.nn.functional.pad(cond, (0, 0, 0, n - ref_frames))
-    y = torch.randn(1, n, cfg.mel_dim)
+    kind = "reference" if ref_shim.available() else "port"
+    ref_model = ref_shim.build_reference_cfm(cfg, sd) if kind == "reference" else None
+    how = ("the reference's own CFM / DiT modules (fp32 torch CPU), loaded from " +
+           ("/root/reference" if ref_shim.source_available() else "the byte-compiled oracle/_ref/")) if kind == "reference" else "oracle port (fp32 torch CPU)"
     with torch.no_grad():
+        if full:
+            def one_sample(nsteps):
+                if ref_model is not None:
+                    out, _ = ref_model.sample(cond=cond, text=text, duration=duration, lens=lens, steps=nsteps, cfg_strength=CFG,
+                                              sway_sampling_coef=SWAY, seed=0)
+                else:
+                    out, _ = O.cfm_sample(sd, cfg, cond, text, duration, lens=lens, steps=nsteps, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=0)
+                return O.vocos_decode(vsd, vc, out[:, ref_frames:].permute(0, 2, 1))
+            if warmup > 0:
+                one_sample(1)  # page-in / thread-pool warm-up: a 1-step sample
+            times = []
+            for _ in range(max(1, min(steps, 1))):
+                t0 = time.perf_counter()
+                one_sample(NFE)
+                times.append(time.perf_counter() - t0)
+            per_utt = sum(times) / len(times)
+            return dict(value=total / per_utt, pair_s=per_utt / NFE, per_utterance_s=per_utt, cores=torch.get_num_threads(), kind=kind,
+                        sample=f"{how}: the COMPLETE CFM.sample of 1 utterance ({total} frames, NFE {NFE}, CFG, sway) + Vocos decode, "
+                               f"{len(times)} timed run(s) after a 1-step warm-up sample")
+        step_cond = torch.nn.functional.pad(cond, (0, 0, 0, n - ref_frames))
+        y = torch.randn(1, n, cfg.mel_dim)
         t0 = time.perf_counter()
-        te_c = O.text_embedding(sd, cfg, text, n, False)
-        te_u = O.text_embedding(sd, cfg, text, n, True)
+        if ref_model is None:
+            te_c = O.text_embedding(sd, cfg, text, n, False)
+            te_u = O.text_embedding(sd, cfg, text, n, True)
+        else:  # DiT caches both on the first cond / uncond forward (dit.py:202-210); time the two TextEmbedding calls themselves
+            tr = ref_model.transformer
+            tr.clear_cache()
+            tr.text_cond = tr.text_embed(text, n, drop_text=False)
+            tr.text_uncond = tr.text_embed(text, n, drop_text=True)
         t_embed = time.perf_counter() - t0
         times = []
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             t = torch.tensor(0.3)
-            pred = O.dit_forward(sd, cfg, y, step_cond, text, t, False, False, None, text_embed=te_c)
-            null = O.dit_forward(sd, cfg, y, step_cond, text, t, True, True, None, text_embed=te_u)
+            if ref_model is None:
+                pred = O.dit_forward(sd, cfg, y, step_cond, text, t, False, False, None, text_embed=te_c)
+                null = O.dit_forward(sd, cfg, y, step_cond, text, t, True, True, None, text_embed=te_u)
+            else:
+                pred = tr(x=y, cond=step_cond, text=text, time=t, drop_audio_cond=False, drop_text=False, cache=True)
+                null = tr(x=y, cond=step_cond, text=text, time=t, drop_audio_cond=True, drop_text=True, cache=True)
             y = y + 0.03 * (pred + (pred - null) * CFG)
             dt = time.perf_counter() - t0
             if i >= warmup:
@@ -204,9 +243,9 @@ def cpu_port_measure(arch, ref_frames, total, steps, warmup, quiet=False):
     pair = sum(times) / len(times)
     per_utt = NFE * pair + t_embed + t_voc
     return dict(value=total / per_utt, pair_s=pair, embed_s=t_embed, vocos_s=t_voc, per_utterance_s=per_utt,
-                cores=torch.get_num_threads(),
-                sample=f"1 utterance ({total} frames) x 1 of {NFE} Euler steps (cond+uncond forward) per timed step, mean of {len(times)}; "
-                       f"+1 text-embedding pair +1 Vocos decode; extrapolated x{NFE} steps")
+                cores=torch.get_num_threads(), kind=kind,
+                sample=f"{how}: 1 utterance ({total} frames) x 1 of {NFE} Euler steps (cond+uncond DiT.forward) per timed step, mean of "
+                       f"{len(times)}; +1 text-embedding pair +1 Vocos decode; extrapolated x{NFE} steps")
 
 
 def torch_eager_gpu_measure(arch, B, ref_frames, total, dev, steps=3, warmup=2):
@@ -358,15 +397,12 @@ def cpu_train_measure(arch, n, steps, warmup):
 
 
 def run_train(args, cfg, B, n, desc, rank, local_rank, world):
-    """--workload cfg5: one data-parallel optimizer step per timed step"""
+    """--workload cfg5 / cfg5b: one data-parallel optimizer step per timed step"""
     import torch.distributed as dist
-    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
-              "parallelism": f"dp{world} (batch sharded; ONE flat fp32 gradient all-reduce per step over NCCL)",
-              "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2",
-              "profiling": "timed region un-instrumented; kernel classes / roofline from 2 extra event-bracketed steps"}
     if args.impl == "reference":
         if rank != 0:
             return
+        config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "frames_per_utterance": n}
         r = cpu_train_measure(cfg, n, max(1, min(args.steps, 2)), 1)
         print(json.dumps({"impl": "reference", "metric": "train_mel_frames_per_sec", "value": r["value"], "unit": "mel-frames/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True,
@@ -379,6 +415,21 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         init_nccl(dev)
+    line = measure_train(args, args.workload, cfg, B, n, desc, rank, local_rank, world, dev, args.steps, args.warmup)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def measure_train(args, wname, cfg, B, n, desc, rank, local_rank, world, dev, steps, warmup, cpu_baseline=True, eager=None):
+    """one data-parallel optimizer step per timed step (cfg-5): CFM.forward + backward + NCCL gradient all-reduce + clip + AdamW +
+    EMA.  The process group (world > 1) is the caller's.  Returns the JSON line on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    config = {"workload": f"{wname}: {desc}", "batch_per_gpu": B, "frames_per_utterance": n,
+              "parallelism": f"dp{world} (batch sharded; ONE flat fp32 gradient all-reduce per step over NCCL)",
+              "l2": "no flush: one step streams ~30 GB of saved activations, >> 126 MB L2",
+              "profiling": "timed region un-instrumented; kernel classes / roofline from 2 extra event-bracketed steps"}
     from eraxvif5tts_b200 import _lib as L
     from eraxvif5tts_b200.train import TrainEngine
     L.load()
@@ -416,7 +467,7 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         loss = step(mel_d, text_d)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -427,7 +478,7 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step(mel_d, text_d)
     e1.record()
     barrier()
@@ -445,7 +496,7 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -455,9 +506,9 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        dist.destroy_process_group()
     if rank != 0:
-        return
+        eng.release()
+        return None
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -476,26 +527,26 @@ def run_train(args, cfg, B, n, desc, rank, local_rank, world):
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback", "launches": v["launches"],
                     "avg_launch_ms": v["ms"] / v["launches"], "flops_per_launch": v["flops"] / v["launches"]}
-    frames = B * n * args.steps * world
+    frames = B * n * steps * world
     step_flops = 3 * dit_flops_per_forward(cfg, B, n)
-    line = {"metric": "train_mel_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": "train_mel_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "mel-frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": sampler.summary(),
             "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s", "h2d_bytes_per_step": mel_h.numel() * 4 + text_h.numel() * 8,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps},
-            "gpu_launches": int(sum(v["launches"] for v in prof.values()) / prof_steps * args.steps),
-            "model_tflops_per_gpu": step_flops / (ms * 1e-3 / args.steps) / 1e12, "params": eng.n,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / steps},
+            "gpu_launches": int(sum(v["launches"] for v in prof.values()) / prof_steps * steps),
+            "model_tflops_per_gpu": step_flops / (ms * 1e-3 / steps) / 1e12, "params": eng.n,
             "loss": float(loss), "roofline": roofline, "kernels": kinds}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and cpu_baseline and not args.no_cpu_baseline:
         r = cpu_train_measure(cfg, n, 1, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    if world == 1 and args.torch_eager_gpu:
-        eng.release()
-        del eng, model
-        torch.cuda.empty_cache()
+    eng.release()
+    del eng, model
+    torch.cuda.empty_cache()
+    if world == 1 and (args.torch_eager_gpu if eager is None else eager):
         torch.cuda.reset_peak_memory_stats(dev)
         line["torch_eager_gpu"] = torch_eager_gpu_train_measure(cfg, B, n, dev)
-    print(json.dumps(line))
+    return line
 
 
 def main():
@@ -509,8 +560,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ragged", action="store_true", help="inference workloads: per-utterance durations U[0.8, 1] x the nominal length "
                     "(SURVEY.md 8d's ragged cfg-2 variant, U[1500, 1875]); the value counts un-padded frames")
-    ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with CUDA events during the timed region")
-    ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the oracle as stock PyTorch eager bf16 on this GPU (second comparator)")
+    ap.add_argument("--no-profile", action="store_true", help="skip the extra event-bracketed step(s) behind the timed region (no kernel breakdown / roofline)")
+    ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the oracle as stock PyTorch eager bf16 on this GPU (second comparator); "
+                    "on by default for the default workload at 1 GPU")
+    ap.add_argument("--no-eager", action="store_true", help="default workload: skip the PyTorch-eager GPU comparator legs")
+    ap.add_argument("--no-train", action="store_true", help="default workload: skip the cfg-5 training-step sub-record")
+    ap.add_argument("--no-parity", action="store_true", help="default workload: skip the depth-22 / NFE-32 parity leg against the fp32 oracle")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -536,11 +591,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_port_measure(cfg, ref_frames, total, args.steps, args.warmup)
+        r = cpu_reference_measure(cfg, ref_frames, total, args.steps, args.warmup, full=(args.workload == "cfg1"))
         line = {"impl": "reference", "metric": "mel_frames_per_sec", "value": r["value"], "unit": "mel-frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["pair_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "rtf": r["per_utterance_s"] / ((total - ref_frames) * 256 / 24000.0), "gpu_launches": 0}
         print(json.dumps(line))
@@ -596,16 +651,12 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # Launch-bound workloads (small fused batch) replay one captured CUDA graph per ODE step; per-launch CUDA events cannot be
-    # recorded inside a replay, so for those the kernel breakdown comes from one extra eager, event-bracketed step after the
-    # timed region.  GPU-bound workloads (cfg2, cfg3) are event-bracketed live inside the timed region.
+    # The timed region is UN-INSTRUMENTED: no per-launch events, the product's own launch path (small fused batches replay one
+    # captured CUDA graph per ODE step).  The kernel-class breakdown / roofline come from extra event-bracketed steps right behind
+    # it (eager launches: events cannot be recorded inside a graph replay), with the same inputs on the same warm device.
     from eraxvif5tts_b200.model import cfm as cfm_mod
-    graphs_on = os.environ.get("F5B_CUDA_GRAPH", "") != "0" and (2 * B * total <= cfm_mod.GRAPH_MAX_ROWS or os.environ.get("F5B_CUDA_GRAPH") == "1")
-    # GPU-bound batches (>= 16k fused rows): bracket every launch with CUDA events live in the timed region (this turns the graph
-    # replay off for that region; the un-profiled e2e leg below uses it).  Launch-bound batches: time the graph path, profile after.
-    graph_mode = graphs_on and (2 * B * total <= 16384 or args.no_profile)
-    live_profile = (not args.no_profile) and not graph_mode
-    L.prof_reset(live_profile)
+    graph_mode = os.environ.get("F5B_CUDA_GRAPH", "") != "0" and (2 * B * total <= cfm_mod.GRAPH_MAX_ROWS or os.environ.get("F5B_CUDA_GRAPH") == "1")
+    L.prof_reset(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -614,14 +665,13 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    prof = L.prof_read()
-    launches_timed = sum(v["launches"] for v in prof.values())
-    prof_steps = args.steps
-    if graph_mode and not args.no_profile:
+    launches_timed = int(sum(v["launches"] for v in L.prof_read().values()))
+    prof, prof_steps = {}, 1
+    if not args.no_profile:
         L.prof_reset(True)
-        step_device()
+        for _ in range(prof_steps):
+            step_device()
         prof = L.prof_read()
-        prof_steps = 1
     L.prof_reset(False)
     assert torch.isfinite(a).all(), "non-finite audio"
     # e2e through the public API with host buffers
@@ -639,7 +689,13 @@ def main():
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+
+    extras = default_workload_extras if (args.workload == "cfg2" and not args.ragged) else None
     if rank != 0:
+        del model, voc
+        torch.cuda.empty_cache()
+        if extras is not None:
+            extras(args, None, rank, local_rank, world, dev)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -689,8 +745,8 @@ def main():
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / e2e_s
     launches = launches_timed
-    config["cuda_graph"] = ("one captured graph per ODE step (replayed 32x per sample); kernel breakdown from one extra eager step"
-                            if graph_mode else "off (GPU-bound batch; launches are event-bracketed live in the timed region)")
+    config["cuda_graph"] = "one captured graph per ODE step (replayed 32x per sample)" if graph_mode else "off"
+    config["profiling"] = f"timed region un-instrumented; kernel classes / roofline from {prof_steps} extra event-bracketed eager step(s) behind it"
     config["dependent_launch"] = ("on (fused batch <= 16384 rows: kernel prologues overlap the previous kernel's tail)" if 2 * B * total <= L.PDL_MAX_ROWS
                                   else "off (GPU-bound batch; measured 1.8 % slower with it)")
     fwd_flops = dit_flops_per_forward(cfg, 2 * B, total) * NFE * reps
@@ -706,14 +762,58 @@ def main():
             "gen_frames_per_sec": gen_frames_per_step * args.steps * world / (ms * 1e-3),
             "dit_tflops_per_gpu": fwd_flops / (ms * 1e-3 / args.steps) / 1e12,
             "roofline": roofline, "kernels": kinds}
+    del model, voc
+    torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_measure(cfg, ref_frames, total, 2, 1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    if world == 1 and args.torch_eager_gpu:
+        r = cpu_reference_measure(cfg, ref_frames, total, 2, 1, full=(args.workload == "cfg1"))
+        line["cpu_baseline"] = {"value": r["value"], "unit": "mel-frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    if world == 1 and (args.torch_eager_gpu or (extras is not None and not args.no_eager)):
         line["torch_eager_gpu"] = torch_eager_gpu_measure(cfg, B, ref_frames, total, dev)
+    if extras is not None:
+        extras(args, line, rank, local_rank, world, dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def default_workload_extras(args, line, rank, local_rank, world, dev):
+    """Sub-records the default `python bench.py --gpus N` line carries besides the headline (every rank calls this; rank 0 holds
+    `line`):
+      train  : the cfg-5 training step (32 x 1200 frames per GPU; forward + backward + NCCL gradient all-reduce over the N ranks +
+               clip + AdamW + EMA) — ms/step, frames/s, model TFLOP/s, all-reduce mode; at N = 1 with its PyTorch-eager comparator;
+      parity : (N = 1) the north-star acceptance check at the BASELINE configuration — F5TTS_Base depth 22, NFE 32, sway, CFG, ragged
+               batch — product vs the fp32 oracle on this GPU (oracle/acceptance.py; the oracle is the checker, after all timing)."""
+    if not args.no_train:
+        arch_kw, B, _, n, desc = WORKLOADS["cfg5"]
+        t = measure_train(args, "cfg5", Arch(**arch_kw), B, n, desc, rank, local_rank, world, dev, steps=max(args.steps, 3), warmup=3,
+                          cpu_baseline=False, eager=(world == 1 and not args.no_eager))
+        if line is not None:
+            keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
+                    "model_tflops_per_gpu", "params", "loss", "roofline", "kernels", "torch_eager_gpu")
+            line["train"] = {k: t[k] for k in keep if k in t}
+    if line is not None and world == 1 and not args.no_parity:
+        line["parity"] = parity_leg(dev)
+
+
+def parity_leg(dev):
+    from oracle import acceptance as A
+    from oracle import f5_oracle as O
+    from oracle.weights import make_dit_state_dict
+    from eraxvif5tts_b200.model import CFM, DiT
+    cfg = O.DiTConfig()  # F5TTS_Base: dim 1024, depth 22, heads 16
+    sd = make_dit_state_dict(cfg, 0)
+    tr = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, dim_head=cfg.dim_head, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
+             text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, text_mask_padding=cfg.text_mask_padding,
+             conv_layers=cfg.conv_layers, pe_attn_head=cfg.pe_attn_head)
+    model = CFM(transformer=tr, mel_spec_kwargs=dict(n_fft=1024, hop_length=256, win_length=1024, n_mel_channels=cfg.mel_dim,
+                                                     target_sample_rate=24000, mel_spec_type="vocos"), odeint_kwargs=dict(method="euler"))
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    res = A.sample_parity(model, sd, cfg, 563, [1875, 1610], steps=NFE, cfg_strength=CFG, sway=SWAY, device=dev)
+    res["tolerances"] = {"velocity_max_abs_bf16": A.VEL_TOL_BF16, "mel_mean_abs": A.MEL_MEAN_TOL}
+    res["pass"] = bool(res["velocity_max_abs"] <= A.VEL_TOL_BF16 and res["mel_mean_abs_generated"] <= A.MEL_MEAN_TOL)
+    res["oracle"] = "oracle/f5_oracle.py (fp32, cuBLAS / cuDNN without TF32) on the same GPU, identical bf16-exact weights, noise and inputs"
+    return res
 
 
 if __name__ == "__main__":

@@ -95,14 +95,14 @@ SIGNATURES = {
     "f5b_ln_affine_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_grn_gelu_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_dwconv7_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
-    "f5b_text_lookup_bwd": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_text_lookup_bwd": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_pack_convpos_weight_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_convpos_packed_elems": (sz, [C.c_int, C.c_int, C.c_int]),
     "f5b_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
     "f5b_grn": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
-    "f5b_text_lookup": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_text_lookup": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_mask_rows_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "f5b_time_sinus": (C.c_int, [vp, vp, C.c_int, vp]),
     "f5b_silu_bf16": (C.c_int, [vp, vp, i64, vp]),
@@ -214,3 +214,24 @@ def ptr(t) -> int | None:
 def stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_own_device(fn):
+    """Method decorator for every product entry point that launches library kernels: the C library launches on the CURRENT CUDA
+    device and `stream()` is the current device's stream, so an object living on cuda:N must make cuda:N current for the duration
+    of the call (a model on cuda:1 used without torch.cuda.set_device(1) would otherwise launch on device 0 against device-1
+    pointers).  The device is the object's `device` attribute / property, else that of its first parameter."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        import torch
+        dev = getattr(self, "device", None)
+        if dev is None and hasattr(self, "parameters"):
+            dev = next(self.parameters()).device
+        dev = torch.device(dev) if dev is not None else None
+        if dev is None or dev.type != "cuda" or (dev.index is not None and dev.index == torch.cuda.current_device()):
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped

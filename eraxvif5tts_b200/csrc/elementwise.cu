@@ -248,11 +248,15 @@ int grn(const void* h, const float* gamma, const float* beta, void* out, float* 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void text_lookup_kernel(const int64_t* __restrict__ ids, int nt, const float* __restrict__ table,
                                    const float* __restrict__ pos, float* __restrict__ out, uint8_t* __restrict__ mask_out,
-                                   int n, int C, int drop_text, int add_pos) {
+                                   int n, int C, int vocab_rows, int drop_text, int add_pos) {
   const int row = blockIdx.x;  // b*n + p
   const int b = row / n, p = row - b * n;
   long long tok = 0;
   if (p < nt) tok = ids[(size_t)b * nt + p] + 1;  // -1 padding -> filler 0
+  if (tok < 0 || tok >= vocab_rows) {  // nn.Embedding asserts on the device; never read the table out of bounds
+    if (threadIdx.x == 0) printf("f5b_text_lookup: token id %lld (row %d, position %d) outside the embedding table [0, %d)\n", tok - 1, b, p, vocab_rows - 1);
+    __trap();
+  }
   if (mask_out != nullptr && threadIdx.x == 0) mask_out[row] = (tok == 0) ? 1 : 0;
   if (drop_text) tok = 0;
   const float* tr = table + (size_t)tok * C;
@@ -513,10 +517,10 @@ int f5b_grn(const void* h, const float* gamma, const float* beta, void* out, flo
 }
 
 int f5b_text_lookup(const int64_t* ids, int nt, const float* table, const float* pos, float* out, uint8_t* mask_out, int B,
-                    int n, int C, int drop_text, int add_pos, f5b_stream_t stream) {
-  F5B_CHECK(B > 0 && n > 0 && C > 0 && nt >= 0, "f5b_text_lookup: bad shape");
+                    int n, int C, int vocab_rows, int drop_text, int add_pos, f5b_stream_t stream) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && nt >= 0 && vocab_rows > 0, "f5b_text_lookup: bad shape");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * B * n * C);
-  text_lookup_kernel<<<B * n, 128, 0, ST(stream)>>>(ids, nt, table, pos, out, mask_out, n, C, drop_text, add_pos);
+  text_lookup_kernel<<<B * n, 128, 0, ST(stream)>>>(ids, nt, table, pos, out, mask_out, n, C, vocab_rows, drop_text, add_pos);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

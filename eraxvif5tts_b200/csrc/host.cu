@@ -155,12 +155,15 @@ LaunchScope::~LaunchScope() {
 int g_pdl = 0;  // f5b_set_dependent_launch(): the Python host turns it on for the launch-bound regimes (see include/f5b200.h)
 
 int sm_count() {
-  static int n = 0;
+  static int cache[64] = {0};  // per device: a process may drive several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }

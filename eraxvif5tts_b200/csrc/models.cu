@@ -139,7 +139,7 @@ int f5b_dit_text_embed(const F5bDit* h, const int64_t* ids, int nt, int B, int n
   uint8_t* mask = c.take<uint8_t>(rows);
   cudaStream_t s = ST(stream);
   const bool mp = d.text_mask_padding != 0 && d.conv_layers > 0;
-  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, out, mp ? mask : nullptr, B, n, T, drop_text, d.conv_layers > 0,
+  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, out, mp ? mask : nullptr, B, n, T, d.vocab_rows, drop_text, d.conv_layers > 0,
                           stream));
   if (mp) F5B_TRY(f5b_mask_rows_f32(out, mask, (int)rows, T, stream));
   for (int j = 0; j < d.conv_layers; ++j) {

@@ -426,7 +426,7 @@ int f5b_dit_text_embed_train(const F5bDit* h, const int64_t* ids, int nt, int B,
   F5B_CHECK(w.bytes <= ws_bytes, "f5b_dit_text_embed_train: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   cudaStream_t s = ST(stream);
   float* first = d.conv_layers > 0 ? w.L[0].h_in : out;
-  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, first, nullptr, B, n, T, drop_text, d.conv_layers > 0, stream));
+  F5B_TRY(f5b_text_lookup(ids, nt, d.text_table, d.text_pos, first, nullptr, B, n, T, d.vocab_rows, drop_text, d.conv_layers > 0, stream));
   for (int j = 0; j < d.conv_layers; ++j) {
     const TextSave& L = w.L[j];
     float* h_out = (j + 1 < d.conv_layers) ? w.L[j + 1].h_in : out;
@@ -474,7 +474,7 @@ int f5b_dit_text_embed_backward(const F5bDit* h, const int64_t* ids, int nt, int
     F5B_TRY(f5b_dwconv7_bwd(w.dy, L.h_in, d.tb_dw_w + (size_t)j * T * 7, w.dh, off(g.tb_dw_w, (size_t)j * T * 7),
                             off(g.tb_dw_b, (size_t)j * T), B, n, T, stream));
   }
-  if (g.text_table) F5B_TRY(f5b_text_lookup_bwd(w.dh, ids, nt, g.text_table, B, n, T, drop_text, stream));
+  if (g.text_table) F5B_TRY(f5b_text_lookup_bwd(w.dh, ids, nt, g.text_table, B, n, T, d.vocab_rows, drop_text, stream));
   return 0;
 }
 

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256) dwconv7_bwd_kernel(const float* __restric
 // nn.Embedding backward of TextEmbedding (model/backbones/dit.py:49-60): dtable[token(row)] += dh[row]; consecutive rows that hit
 // the same token (the filler tail of every utterance) are summed in registers before the atomic
 __global__ void __launch_bounds__(256) text_lookup_bwd_kernel(const float* __restrict__ dh, const int64_t* __restrict__ ids, int nt,
-                                                              float* __restrict__ dtable, int n, int C, int drop_text) {
+                                                              float* __restrict__ dtable, int n, int C, int vocab_rows, int drop_text) {
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * CT_ROWS, p1 = min(n, p0 + CT_ROWS);
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(256) text_lookup_bwd_kernel(const float* __res
     for (int p = p0; p < p1; ++p) {
       long long tok = 0;
       if (p < nt && !drop_text) tok = ids[(size_t)b * nt + p] + 1;
+      if (tok < 0 || tok >= vocab_rows) __trap();  // the forward lookup reports the offending id; never scatter out of bounds
       if (tok != cur) {
         if (cur >= 0) atomicAdd(dtable + (size_t)cur * C + c, acc);
         cur = tok;
@@ -828,11 +829,11 @@ int f5b_dwconv7_bwd(const float* dy, const float* x, const float* w, float* dx_a
   return 0;
 }
 
-int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int drop_text,
+int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int vocab_rows, int drop_text,
                         f5b_stream_t stream) {
-  F5B_CHECK(dh && ids && dtable && B > 0 && n > 0 && C > 0 && nt > 0, "f5b_text_lookup_bwd: bad argument");
+  F5B_CHECK(dh && ids && dtable && B > 0 && n > 0 && C > 0 && nt > 0 && vocab_rows > 0, "f5b_text_lookup_bwd: bad argument");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * B * n * C);
-  text_lookup_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), 256, 0, ST(stream)>>>(dh, ids, nt, dtable, n, C, drop_text);
+  text_lookup_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), 256, 0, ST(stream)>>>(dh, ids, nt, dtable, n, C, vocab_rows, drop_text);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

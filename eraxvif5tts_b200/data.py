@@ -88,7 +88,9 @@ def collate_token_major(batch, pin: bool = True):
     max_len = int(mel_lengths.amax())
     n_mels = mel_specs[0].shape[0]
     mel = torch.zeros(len(batch), max_len, n_mels, dtype=torch.float32)
-    if pin and torch.cuda.is_available():
+    # never pin inside a DataLoader worker: cudaHostAlloc in a forked child of a CUDA-initialised parent fails; there the batch is
+    # pinned by the loader's pin-memory thread in the main process (Trainer passes pin_memory=True when num_workers > 0)
+    if pin and torch.utils.data.get_worker_info() is None and torch.cuda.is_available():
         mel = mel.pin_memory()
     for i, spec in enumerate(mel_specs):
         mel[i, :spec.shape[-1]] = spec.transpose(0, 1)

@@ -16,6 +16,7 @@ import torch
 
 from ..model import CFM, DiT
 from ..model.utils import get_tokenizer
+from .. import _lib as L
 from .utils_infer import chunk_text, load_checkpoint, load_vocoder, resolve_arch
 
 _CUSTOM_TRANS = str.maketrans({";": ",", "“": '"', "”": '"', "‘": "'", "’": "'"})
@@ -235,6 +236,7 @@ class F5TTSWrapper:
         gen_text_len = len(text_batch.encode("utf-8"))
         return self.ref_audio_len + int(self.ref_audio_len / ref_text_len * gen_text_len / local_speed)
 
+    @L.on_own_device
     def generate(self, text: str, output_path: Optional[str] = None, nfe_step: Optional[int] = None,
                  cfg_strength: Optional[float] = None, sway_sampling_coef: Optional[float] = None, speed: Optional[float] = None,
                  fix_duration: Optional[float] = None, cross_fade_duration: Optional[float] = None,

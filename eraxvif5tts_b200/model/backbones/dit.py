@@ -377,6 +377,7 @@ class DiT(nn.Module):
     def clear_cache(self):
         self.text_cond, self.text_uncond = None, None
 
+    @L.on_own_device
     @torch.no_grad()
     def forward(self, x, cond, text, time, drop_audio_cond, drop_text, mask=None, cache=False):
         """x, cond [b, n, mel]; text int [b, nt]; time [] or [b]; mask bool [b, n] (a prefix / key-padding mask as built by

@@ -50,6 +50,7 @@ class CFM(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    @L.on_own_device
     @torch.no_grad()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None, seed: int | None = None,
                max_duration=4096, vocoder: Callable | None = None, no_ref_audio=False, duplicate_test=False, t_inter=0.1,
@@ -198,6 +199,7 @@ class CFM(nn.Module):
             out = vocoder(out)
         return out, trajectory
 
+    @L.on_own_device
     @torch.no_grad()
     def forward(self, inp, text, *, lens=None, noise_scheduler=None, draws: dict | None = None):
         """Flow-matching loss (cfm.py:210-283): returns (loss, cond, pred) like the reference, computed by the CUDA library.  The

@@ -53,6 +53,7 @@ class DurationPredictor(nn.Module):
                                                 self.filter_channels, self.kernel_size, L.stream()), "f5b_duration_predictor")
         return out
 
+    @L.on_own_device
     @torch.no_grad()
     def forward(self, x, x_mask, g=None):
         """x int [b, nt] text tokens padded with -1 (list_str_to_idx), x_mask [b, nt] -> log-durations [b, 1, nt]"""
@@ -79,6 +80,7 @@ class DurationPredictor(nn.Module):
                 setattr(st, field, p.data_ptr())
         return st
 
+    @L.on_own_device
     @torch.no_grad()
     def loss_and_grads(self, x, x_mask, attn=None, target_logw=None, seed=None, phoneme: bool = False, per_item: bool = False,
                        weight: float = 1.0):

@@ -55,7 +55,8 @@ class MelSpec(nn.Module):
         assert wav.ndim == 2
         if self.fb.device != wav.device:  # the reference moves itself lazily too (modules.py:131-132)
             self.to(wav.device)
-        return ops.melspec(wav.float().contiguous(), self.fb, self.fb_ranges, self.n_mel_channels)
+        with torch.cuda.device(wav.device):  # the library launches on the current device: make it the input's
+            return ops.melspec(wav.float().contiguous(), self.fb, self.fb_ranges, self.n_mel_channels)
 
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
         return self.forward_token_major(wav).permute(0, 2, 1)

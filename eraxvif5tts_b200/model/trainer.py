@@ -85,21 +85,40 @@ class Trainer:
             while len(numbered) > self.keep_last_n_checkpoints:
                 os.remove(os.path.join(self.checkpoint_path, numbered.pop(0)))
 
-    def load_checkpoint(self) -> int:
-        """trainer.py:600-690: model_last.pt first, else the highest-numbered model_<update>.pt; returns the update to resume at"""
+    def find_checkpoint(self):
+        """trainer.py:600-646: model_last.pt first; else the training checkpoint model_<update>.{pt,safetensors} with the highest
+        update; else the first (sorted) pretrained_*.{pt,safetensors} — the fine-tune entry point.  Returns a path or None."""
+        import re
         if not _exists(self.checkpoint_path) or not os.path.isdir(self.checkpoint_path):
+            return None
+        if os.path.exists(os.path.join(self.checkpoint_path, "model_last.pt")):
+            return os.path.join(self.checkpoint_path, "model_last.pt")
+        files = [f for f in os.listdir(self.checkpoint_path)
+                 if (f.startswith("model_") or f.startswith("pretrained_")) and f.endswith((".pt", ".safetensors"))]
+        training = [f for f in files if f.startswith("model_") and f != "model_last.pt"]
+        pretrained = [f for f in files if f.startswith("pretrained_")]
+        name = None
+        if training:
+            best = -1
+            for f in training:
+                m = re.search(r"model_(\d+)", f)
+                if m and int(m.group(1)) > best:
+                    best, name = int(m.group(1)), f
+        elif pretrained:
+            name = sorted(pretrained)[0]
+        if name is None:
+            others = [f for f in os.listdir(self.checkpoint_path) if f.endswith((".pt", ".safetensors"))]
+            if others:  # never start from random init silently next to weight files this search order does not pick up
+                raise FileNotFoundError(f"{self.checkpoint_path} holds {others} but none is model_last.pt, model_<update>.* or pretrained_*")
+            return None
+        return os.path.join(self.checkpoint_path, name)
+
+    def load_checkpoint(self) -> int:
+        """trainer.py:600-827; returns the update to resume at (0 = fresh optimizer on loaded or random weights)"""
+        path = self.find_checkpoint()
+        if path is None:
             return 0
-        files = [f for f in os.listdir(self.checkpoint_path) if f.endswith(".pt")]
-        if not files:
-            return 0
-        if "model_last.pt" in files:
-            name = "model_last.pt"
-        else:
-            numbered = [f for f in files if f.startswith("model_") and f[6:-3].isdigit()]
-            if not numbered:
-                return 0
-            name = max(numbered, key=lambda f: int(f[6:-3]))
-        return int(self.engine.load_checkpoint(os.path.join(self.checkpoint_path, name)))
+        return int(self.engine.load_checkpoint(path, grad_accumulation_steps=self.grad_accumulation_steps))
 
     # ------------------------------------------------------------------------------------------------ loop
     def _batches(self, train_dataset, resumable_with_seed):
@@ -133,9 +152,13 @@ class Trainer:
         accum = self.grad_accumulation_steps
         warmup_updates = self.num_warmup_updates * self.num_processes  # trainer.py:1179-1181
         total_updates = math.ceil(per_epoch / accum) * self.epochs
-        self.scheduler = WarmupLinearDecay(self.learning_rate, warmup_updates, total_updates)
+        # accelerate steps the prepared scheduler num_processes times per optimizer update (see WarmupLinearDecay)
+        self.scheduler = WarmupLinearDecay(self.learning_rate, warmup_updates, total_updates, steps_per_update=self.num_processes)
         start_update = self.load_checkpoint()
         global_update = start_update
+        # the reference restores the scheduler's own state (one step per applied update) while it resumes the update COUNT at
+        # `update + 1` (trainer.py:812): keep the two apart so the learning rate continues exactly where it stopped
+        lr_update = max(start_update - 1, 0)
         skipped_epoch, skipped_batch = 0, 0
         if _exists(resumable_with_seed):
             start_step = start_update * accum
@@ -149,16 +172,17 @@ class Trainer:
             if epoch == skipped_epoch and skipped_batch:
                 batches = batches[skipped_batch:]
             loader = DataLoader(train_dataset, collate_fn=collate_token_major, batch_sampler=batches, num_workers=num_workers,
-                                pin_memory=False, persistent_workers=False, **(dict(prefetch_factor=2) if num_workers > 0 else {}))
+                                pin_memory=num_workers > 0, persistent_workers=False, **(dict(prefetch_factor=2) if num_workers > 0 else {}))
             micro, acc_loss = 0, None
             eng.zero_grad()
 
             def apply_update():
-                nonlocal global_update, acc_loss
+                nonlocal global_update, acc_loss, lr_update
                 scale = eng.allreduce_grads() if self.distributed else 1.0
-                eng.step(lr=self.scheduler.lr(global_update), grad_scale=scale / accum)  # the loss is divided by accum either way
+                eng.step(lr=self.scheduler.lr(lr_update), grad_scale=scale / accum)  # the loss is divided by accum either way
                 eng.zero_grad()
                 global_update += 1
+                lr_update += 1
                 self.losses.append(float(acc_loss) / accum)
                 acc_loss = None
                 if global_update % self.save_per_updates == 0:

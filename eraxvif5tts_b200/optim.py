@@ -15,12 +15,20 @@ from . import _lib as L
 
 class WarmupLinearDecay:
     """SequentialLR(LinearLR(1e-8 -> 1, warmup), LinearLR(1 -> 1e-8, decay)) of trainer.py:1179-1188; `lr(update)` = the rate
-    used BY update number `update` (0-based)."""
+    used BY update number `update` (0-based).
 
-    def __init__(self, base_lr: float, warmup_updates: int, total_updates: int):
+    `steps_per_update`: the reference hands the scheduler to `accelerator.prepare`, and accelerate's AcceleratedScheduler steps
+    the wrapped scheduler `num_processes` times per optimizer update (split_batches=False).  That is why the reference multiplies
+    the warm-up length by num_processes (:1179-1181): in optimizer updates its warm-up lasts `num_warmup_updates` and the decay
+    spans `(total - warmup * P) / P` updates.  Pass `steps_per_update = num_processes` with the reference's (multiplied) lengths to
+    get exactly that: the schedule is evaluated at `update * steps_per_update`."""
+
+    def __init__(self, base_lr: float, warmup_updates: int, total_updates: int, steps_per_update: int = 1):
         self.base_lr, self.warmup, self.decay = base_lr, max(1, warmup_updates), max(1, total_updates - warmup_updates)
+        self.steps_per_update = max(1, int(steps_per_update))
 
     def lr(self, update: int) -> float:
+        update = update * self.steps_per_update
         if update < self.warmup:
             f = 1e-8 + (1.0 - 1e-8) * update / self.warmup
         else:
@@ -37,12 +45,15 @@ class EmaSchedule:
         self.beta, self.after, self.every, self.inv_gamma, self.power, self.min_value = beta, update_after_step, update_every, inv_gamma, power, min_value
 
     def decay_for_call(self, k: int):
-        step = k - 1  # ema_pytorch reads self.step before incrementing
+        """ema_pytorch.EMA.update(): `step = self.step; self.step += 1` — the gating (`update_every`, `update_after_step`) uses the
+        PRE-increment value, then update_moving_average() calls get_current_decay(), which reads self.step AFTER the increment:
+        epoch = (step + 1) - update_after_step - 1 = step - update_after_step."""
+        step = k - 1
         if step % self.every != 0:
             return None
         if step <= self.after:
             return "copy"
-        epoch = max(step - self.after - 1, 0)
+        epoch = max(step - self.after, 0)
         value = 1.0 - (1.0 + epoch / self.inv_gamma) ** (-self.power)
         return 0.0 if epoch <= 0 else min(max(value, self.min_value), self.beta)
 
@@ -59,7 +70,7 @@ class FlatAdamW:
         dev = params[0].device
         if dev.type != "cuda":
             raise L.F5bError("FlatAdamW needs the module on a CUDA device (no CPU fallback)")
-        self.lib = L.load()
+        self.device, self.lib = dev, L.load()
         self.sizes = [p.numel() for p in params]
         self.offsets = [0]
         for s in self.sizes:
@@ -103,6 +114,7 @@ class FlatAdamW:
         L.check(self.lib.f5b_grad_sumsq(self.g.data_ptr(), self.n, self._ws.data_ptr(), self._sumsq.data_ptr(), L.stream()), "f5b_grad_sumsq")
         return self._sumsq.sqrt() * grad_scale
 
+    @L.on_own_device
     def step(self, lr: float | None = None, grad_scale: float = 1.0, update_ema: bool = True):
         """one optimizer.step() (+ ema_model.update() when `with_ema`); gradients are expected in `self.g` / `p.grad`"""
         self.step_count += 1

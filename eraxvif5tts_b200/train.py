@@ -14,6 +14,7 @@ No autograd graph and no PyTorch math is involved; torch provides device memory,
 from __future__ import annotations
 
 import ctypes as C
+import os
 from random import random
 
 import torch
@@ -220,6 +221,7 @@ class TrainEngine:
         self.g_in_wct.zero_()
 
     # ------------------------------------------------------------------------------------------------ forward + backward
+    @L.on_own_device
     @torch.no_grad()
     def loss_and_grads(self, inp, text, *, lens=None, draws: dict | None = None, overlap_allreduce: bool = False, group=None,
                        buckets: int = 4, distill: dict | None = None):
@@ -374,6 +376,7 @@ class TrainEngine:
         broadcast_flat_(self.p, src, group)
         self.sync_from_master()
 
+    @L.on_own_device
     @torch.no_grad()
     def step(self, lr: float | None = None, grad_scale: float = 1.0, update_ema: bool = True):
         """clip_grad_norm_ + AdamW + EMA in one fused pass that also writes the bf16 mirror (trainer.py:1280-1287, 1321)"""
@@ -435,14 +438,71 @@ class TrainEngine:
     def save_checkpoint(self, path: str, update: int, scheduler_state: dict | None = None) -> None:
         torch.save(self.checkpoint(update, scheduler_state), path)
 
+    @staticmethod
+    def _model_state_dict(ckpt: dict):
+        """trainer.py:676-728: the weights live under the first non-empty of `model_state_dict`, `ema_model_state_dict`,
+        `state_dict`, `model` (or the file is a flat .safetensors dict); a prefix carried by >= 80 % of the keys (`ema_model.` for an
+        EMA source, `module.`, `model.`, `_orig_mod.`) is stripped; ema_pytorch's `initted` / `step` entries are dropped."""
+        raw, is_ema = None, False
+        for key in ("model_state_dict", "ema_model_state_dict", "state_dict", "model", "state_dict_loaded_from_safetensors"):
+            v = ckpt.get(key)
+            if isinstance(v, dict) and v:
+                raw, is_ema = v, key == "ema_model_state_dict"
+                break
+        if raw is None:
+            raise KeyError(f"no model state dict in the checkpoint (top-level keys: {list(ckpt.keys())})")
+        prefixes = ["module.", "model.", "_orig_mod."]
+        if is_ema and any(k.startswith("ema_model.") for k in raw):
+            prefixes.insert(0, "ema_model.")
+        used = None
+        first = next(iter(raw))
+        for pre in prefixes:
+            if first.startswith(pre) and sum(1 for k in raw if k.startswith(pre)) >= 0.8 * len(raw):
+                used = pre
+                break
+        out = {}
+        for k, v in raw.items():
+            k2 = k[len(used):] if used and k.startswith(used) else k
+            if k2 not in ("initted", "step"):
+                out[k2] = v
+        return out
+
     @torch.no_grad()
-    def load_checkpoint(self, ckpt) -> int:
-        """resume from a checkpoint in the reference's format (trainer.py:600-690): weights, Adam moments, EMA; returns `update`"""
-        if isinstance(ckpt, str):
-            ckpt = torch.load(ckpt, map_location="cpu", weights_only=True)
+    def load_checkpoint(self, ckpt, grad_accumulation_steps: int = 1) -> int:
+        """Load a checkpoint in any of the reference's formats (trainer.py:600-827).  A full training checkpoint
+        (`optimizer_state_dict` + `update`) restores weights, Adam moments and EMA and returns `update + 1`, the update the
+        reference resumes at (:801-812); weights-only files (pretrained_*.pt / .safetensors, EMA-only, pruned) load the weights
+        (missing keys keep their initial values, like load_state_dict(strict=False)) and return 0."""
+        if isinstance(ckpt, (str, os.PathLike)):
+            path = str(ckpt)
+            if path.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                ckpt = {"state_dict_loaded_from_safetensors": load_file(path, device="cpu")}
+            else:
+                try:
+                    ckpt = torch.load(path, map_location="cpu", weights_only=True)
+                except Exception:  # noqa: BLE001 — reference checkpoints may pickle plain python objects (pruning_info, ...)
+                    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        if not isinstance(ckpt, dict):
+            raise TypeError("checkpoint is not a dictionary")
         cfm = self.cfm
-        sd = ckpt["model_state_dict"]
+        sd = self._model_state_dict(ckpt)
+        full = "optimizer_state_dict" in ckpt and "update" in ckpt
         names = {id(p): k for k, p in cfm.named_parameters()}
+        known = set(names.values())
+        if not any(k in known for k in sd):
+            raise KeyError("the checkpoint's state dict shares no key with the model")
+        if not full:
+            for p, o, n_ in self.params:
+                k = names[id(p)]
+                if k in sd:
+                    if sd[k].numel() != n_:
+                        raise ValueError(f"checkpoint tensor {k} has shape {tuple(sd[k].shape)}, the model expects {tuple(p.shape)}")
+                    self.p[o:o + n_].copy_(sd[k].reshape(-1))
+            if self.ema is not None:
+                self.ema.copy_(self.p)
+            self.sync_from_master()
+            return 0
         plist = list(cfm.parameters())
         index = {id(p): i for i, p in enumerate(plist)}
         opt = ckpt.get("optimizer_state_dict", {}).get("state", {})
@@ -460,7 +520,7 @@ class TrainEngine:
         if ema is not None and "step" in ema:
             self.ema_calls = int(ema["step"])
         self.sync_from_master()
-        return int(ckpt.get("update", ckpt.get("step", 0)))
+        return int(ckpt["update"]) + 1  # trainer.py:812 `start_update += 1`
 
     def ema_state_dict(self) -> dict:
         names = {id(p): k for k, p in self.dit.named_parameters()}

@@ -119,6 +119,7 @@ class Vocos(nn.Module):
         L.check(lib.f5b_vocos_create(C.byref(d), C.byref(h)), "f5b_vocos_create")
         self._engine = dict(handle=h, keep=keep, desc=d, device=torch.device(device), lib=lib, ws=None)
 
+    @L.on_own_device
     @torch.no_grad()
     def decode(self, features_input: torch.Tensor, **kwargs) -> torch.Tensor:
         """mel [b, n_mels, T] -> wav [b, hop (T-1)]"""

@@ -135,9 +135,11 @@ int f5b_grn(const void* h_bf16, const float* gamma, const float* beta, void* out
 
 /* TextEmbedding front (model/backbones/dit.py:49-72): ids int64 [B, nt] (-1 padded) -> +1, truncate / pad with 0 to n,
  * drop_text -> all 0, embedding lookup (table f32 [V+1, C]) + freqs_cis[pos] (pos f32 [4096, C]) -> f32 [B*n, C].
- * mask_out (optional, uint8 [B*n]) = (token == 0) before drop_text, for text_mask_padding. */
+ * mask_out (optional, uint8 [B*n]) = (token == 0) before drop_text, for text_mask_padding.
+ * vocab_rows = rows of `table`: a shifted id outside [0, vocab_rows) traps the kernel (-> CUDA error on the host), like the
+ * device-side assert of the reference's nn.Embedding; it is never read out of bounds. */
 int f5b_text_lookup(const int64_t* ids, int nt, const float* table, const float* pos, float* out, uint8_t* mask_out,
-                    int B, int n, int C, int drop_text, int add_pos, f5b_stream_t stream);
+                    int B, int n, int C, int vocab_rows, int drop_text, int add_pos, f5b_stream_t stream);
 /* rows with mask != 0 are set to 0 (masked_fill, dit.py:74-75) */
 int f5b_mask_rows_f32(float* x, const uint8_t* mask, int rows, int C, f5b_stream_t stream);
 
@@ -301,7 +303,8 @@ int f5b_grn_gelu_bwd(const void* dt3_bf16, const void* t2_bf16, const void* p1_b
                      float* dbeta, float* dbias1, float* stats_ws, int B, int n, int C, f5b_stream_t stream);
 int f5b_dwconv7_bwd(const float* dy, const float* x, const float* w, float* dx_accum, float* dw, float* db, int B, int n, int C,
                     f5b_stream_t stream);
-int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int drop_text,
+/* dtable f32 [vocab_rows, C]; out-of-range ids trap (see f5b_text_lookup) instead of corrupting neighbouring gradients */
+int f5b_text_lookup_bwd(const float* dh, const int64_t* ids, int nt, float* dtable, int B, int n, int C, int vocab_rows, int drop_text,
                         f5b_stream_t stream);
 
 /* rope table for n positions, dim_head 64: f32 [n, 32, 2] = (cos, sin)(pos * 10000^(-2j/64))

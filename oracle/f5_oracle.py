@@ -315,7 +315,7 @@ def dit_forward(sd, cfg: DiTConfig, x, cond, text, time, drop_audio_cond, drop_t
     if text_embed is None:
         text_embed = text_embedding(sd, cfg, text, n, drop_text)
     h = input_embedding(sd, cfg, x, cond, text_embed, drop_audio_cond)
-    rope = rotary_freqs(n, cfg.dim_head)
+    rope = rotary_freqs(n, cfg.dim_head).to(x.device)
     hidden = [h]
     for i in range(cfg.depth):
         h = dit_block(sd, cfg, i, h, t, mask, rope, dropout)
@@ -361,23 +361,29 @@ def sway_time_grid(steps, sway_sampling_coef, dtype=torch.float32, t_start=0.0, 
 
 def cfm_sample(sd, cfg: DiTConfig, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0,
                sway_sampling_coef=None, seed=None, max_duration=4096, method="euler",
-               no_ref_audio=False, edit_mask=None, mel_cfg: MelConfig = MelConfig(), vocab_char_map=None):
-    """CFM.sample, model/cfm.py:82-208 (duplicate_test corner omitted).  Returns (out, trajectory)."""
+               no_ref_audio=False, edit_mask=None, mel_cfg: MelConfig = MelConfig(), vocab_char_map=None,
+               duplicate_test=False, t_inter=0.1):
+    """CFM.sample, model/cfm.py:82-208, incl. the duplicate_test / t_inter corner (:139-140, :188-191).  Runs on the device of
+    `cond` (fp32; the noise is drawn on the CPU generator and moved, so CPU and GPU runs of the oracle share y0).
+    Returns (out, trajectory)."""
     if cond.ndim == 2:
         cond = melspec(cond, mel_cfg).permute(0, 2, 1)
     cond = cond.float()
+    dev = cond.device
     batch, cond_seq_len = cond.shape[:2]
     if lens is None:
-        lens = torch.full((batch,), cond_seq_len, dtype=torch.long)
+        lens = torch.full((batch,), cond_seq_len, dtype=torch.long, device=dev)
     if isinstance(text, list):
-        text = list_str_to_idx(text, vocab_char_map)
+        text = list_str_to_idx(text, vocab_char_map).to(dev)
     cond_mask = lens_to_mask(lens)
     if edit_mask is not None:
         cond_mask = cond_mask & edit_mask
     if isinstance(duration, int):
-        duration = torch.full((batch,), duration, dtype=torch.long)
+        duration = torch.full((batch,), duration, dtype=torch.long, device=dev)
     duration = torch.maximum(torch.maximum((text != -1).sum(dim=-1), lens) + 1, duration).clamp(max=max_duration)
     max_dur = int(duration.amax())
+    if duplicate_test:
+        test_cond = F.pad(cond, (0, 0, cond_seq_len, max_dur - 2 * cond_seq_len), value=0.0)
     cond = F.pad(cond, (0, 0, 0, max_dur - cond_seq_len), value=0.0)
     if no_ref_audio:
         cond = torch.zeros_like(cond)
@@ -396,12 +402,17 @@ def cfm_sample(sd, cfg: DiTConfig, cond, text, duration, *, lens=None, steps=32,
         return pred + (pred - null) * cfg_strength
 
     y0 = []
-    for dur in duration:
+    for dur in duration.tolist():
         if seed is not None:
             torch.manual_seed(seed)
         y0.append(torch.randn(int(dur), cfg.mel_dim))
-    y0 = torch.nn.utils.rnn.pad_sequence(y0, padding_value=0, batch_first=True)
-    t = sway_time_grid(steps, sway_sampling_coef)
+    y0 = torch.nn.utils.rnn.pad_sequence(y0, padding_value=0, batch_first=True).to(dev)
+    t_start = 0.0
+    if duplicate_test:
+        t_start = t_inter
+        y0 = (1 - t_start) * y0 + t_start * test_cond
+        steps = int(steps * (1 - t_start))
+    t = sway_time_grid(steps, sway_sampling_coef, t_start=t_start, device=dev)
     traj = odeint_fixed(fn, y0, t, method)
     out = torch.where(cond_mask, cond, traj[-1])
     return out, traj

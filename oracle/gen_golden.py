@@ -61,16 +61,18 @@ def gen_dit(cfg: DiTConfig, tag: str, batch=2, n=96, seed=0):
                                 text_unc=text_unc, h0=h0, h1=h1))
 
 
-def gen_sample(cfg: DiTConfig, tag: str, batch, ref_frames, total, steps, method="euler", seed=0):
+def gen_sample(cfg: DiTConfig, tag: str, batch, ref_frames, total, steps, method="euler", seed=0, **extra):
+    """`extra`: further keyword arguments of the reference's CFM.sample (duplicate_test / t_inter, cfm.py:96-97), stored in the file"""
     sd = make_dit_state_dict(cfg, seed)
     model = ref_shim.build_reference_cfm(cfg, sd, method=method)
     cond, text, duration, lens = synthetic_inputs(cfg, batch, ref_frames, total, seed=1234)
     with torch.no_grad():
         out, traj = model.sample(cond=cond, text=text, duration=duration, lens=lens, steps=steps, cfg_strength=2.0,
-                                 sway_sampling_coef=-1.0, seed=0)
+                                 sway_sampling_coef=-1.0, seed=0, **extra)
     _save(f"sample_{tag}.pt", dict(cfg=asdict(cfg), seed=seed, digest=state_dict_digest(sd), cond=cond, text=text,
                                    duration=duration, lens=lens, steps=steps, method=method, cfg_strength=2.0,
-                                   sway=-1.0, sample_seed=0, out=out, traj_last=traj[-1], traj_1=traj[1]))
+                                   sway=-1.0, sample_seed=0, out=out, traj_last=traj[-1], traj_1=traj[1], extra=extra,
+                                   traj_len=traj.shape[0]))
 
 
 GRAD_KEYS = ("transformer.proj_out.weight", "transformer.norm_out.linear.weight", "transformer.transformer_blocks.0.attn.to_q.weight",
@@ -133,6 +135,11 @@ def gen_cfm_forward(cfg: DiTConfig, tag: str, drop_audio_cond: bool, drop_text: 
                                         grads={k: grads[k].flatten()[:4096].clone() for k in GRAD_KEYS}, grad_norms={k: float(v.norm()) for k, v in grads.items()}))
 
 
+def gen_dup():
+    # duplicate_test corner (cfm.py:139-140, 188-191): y0 blended with the shifted reference mel, t_start = t_inter, fewer steps
+    gen_sample(DiTConfig.tiny(), "tiny_dup", batch=2, ref_frames=30, total=[96, 83], steps=5, duplicate_test=True, t_inter=0.2)
+
+
 def main():
     if not ref_shim.available():
         sys.exit("reference tree not present; golden vectors can only be generated in the build container")
@@ -143,9 +150,13 @@ def main():
     gen_sample(DiTConfig.tiny(), "tiny_b2", batch=2, ref_frames=40, total=[96, 83], steps=4)
     gen_sample(DiTConfig.tiny(), "tiny_b1", batch=1, ref_frames=40, total=90, steps=4)
     gen_sample(DiTConfig.tiny(), "tiny_mid", batch=2, ref_frames=40, total=[70, 64], steps=3, method="midpoint")
+    gen_dup()
     gen_cfm_forward(DiTConfig.tiny(), "tiny_cond", False, False)
     gen_cfm_forward(DiTConfig.tiny(), "tiny_uncond", True, True)
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-dup" in sys.argv:
+        gen_dup()
+    else:
+        main()

@@ -1,7 +1,8 @@
-"""Load the REAL reference modules (unmodified, by path) in the build container
-(TEST INFRASTRUCTURE; /root/reference does not exist on the GPU box, so nothing on the `-m gpu`
-path, smoke() or bench.py may call this — it is used by oracle/gen_golden.py and by the
-`not gpu` test that pins the restatement, which skips when the tree is absent).
+"""Load the REAL reference modules (unmodified, by path)
+(TEST INFRASTRUCTURE: used by oracle/gen_golden.py, by the `not gpu` test that pins the restatement, and by bench.py's CPU
+arm.  /root/reference does not exist on the GPU box; there the four modules are loaded from the byte-compiled files under
+`oracle/_ref/` that `python -m oracle.make_ref` built from the reference sources in the build container — git-ignored, travels
+with the snapshot like a built .so.)
 
 Recipe: inject tiny stand-ins for the third-party packages that are absent here
 (torchdiffeq, x_transformers, librosa, jieba, pypinyin), register stub parent packages so
@@ -10,6 +11,7 @@ utils.py, modules.py, backbones/dit.py and cfm.py from where they lie.  No refer
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -19,11 +21,17 @@ import torch
 
 REF_ROOT = os.environ.get("F5_REFERENCE_ROOT", "/root/reference")
 _SRC = os.path.join(REF_ROOT, "src", "f5_tts")
+_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "f5_tts")  # built by oracle/make_ref.py
 _loaded = None
 
 
-def available() -> bool:
+def source_available() -> bool:
     return os.path.isfile(os.path.join(_SRC, "model", "cfm.py"))
+
+
+def available() -> bool:
+    """the reference's modules can be loaded: from source (build container) or from oracle/_ref/*.pyc (GPU box)"""
+    return source_available() or os.path.isfile(os.path.join(_PYC, "model", "cfm.pyc"))
 
 
 def _shim_modules():
@@ -78,18 +86,23 @@ def load():
     if _loaded is not None:
         return _loaded
     if not available():
-        raise FileNotFoundError(f"reference tree not found under {REF_ROOT}")
+        raise FileNotFoundError(f"reference tree not found under {REF_ROOT} and no byte-compiled modules under {_PYC}")
+    from_source = source_available()
     sys.dont_write_bytecode = True
     for k, m in _shim_modules().items():
         sys.modules.setdefault(k, m)
     for name, sub in (("f5_tts", ""), ("f5_tts.model", "model"), ("f5_tts.model.backbones", "model/backbones")):
         if name not in sys.modules:
             pkg = types.ModuleType(name)
-            pkg.__path__ = [os.path.join(_SRC, sub)]
+            pkg.__path__ = [os.path.join(_SRC if from_source else _PYC, sub)]
             sys.modules[name] = pkg
 
     def _exec(name, rel):
-        spec = importlib.util.spec_from_file_location(name, os.path.join(_SRC, rel))
+        if from_source:
+            spec = importlib.util.spec_from_file_location(name, os.path.join(_SRC, rel))
+        else:
+            path = os.path.join(_PYC, rel + "c")
+            spec = importlib.util.spec_from_file_location(name, path, loader=importlib.machinery.SourcelessFileLoader(name, path))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[name] = mod
         spec.loader.exec_module(mod)

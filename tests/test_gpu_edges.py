@@ -13,8 +13,6 @@ pytestmark = pytest.mark.gpu
 
 
 def test_attention_and_gemm_at_max_sequence_length():
-    import sys, os
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import gpu_diag as D
     D.RES.clear()
     D.qkv_attn_case(1, 16, 4096, None, rope_heads=1)       # cfm.py:135 clamps durations to 4096

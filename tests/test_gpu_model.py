@@ -54,7 +54,7 @@ def _ref_noise(duration, mel_dim, seed):
     return torch.nn.utils.rnn.pad_sequence(y0, padding_value=0, batch_first=True)
 
 
-@pytest.mark.parametrize("tag", ["tiny_b2", "tiny_b1", "tiny_mid"])
+@pytest.mark.parametrize("tag", ["tiny_b2", "tiny_b1", "tiny_mid", "tiny_dup"])
 def test_cfm_sample_matches_reference_golden(golden, tag):
     g = golden(f"sample_{tag}.pt")
     cfg = _cfg(g["cfg"])
@@ -62,10 +62,11 @@ def test_cfm_sample_matches_reference_golden(golden, tag):
     noise = _ref_noise(g["duration"], cfg.mel_dim, g["sample_seed"])
     out, traj = model.sample(cond=g["cond"].cuda(), text=g["text"].cuda(), duration=g["duration"].cuda(), lens=g["lens"].cuda(),
                              steps=g["steps"], cfg_strength=g["cfg_strength"], sway_sampling_coef=g["sway"], seed=g["sample_seed"],
-                             noise=noise)
+                             noise=noise, **g.get("extra", {}))
     torch.cuda.synchronize()
-    assert out.shape == g["out"].shape and traj.shape[0] == g["steps"] + 1
-    assert maxabs(traj[0], noise) == 0.0
+    assert out.shape == g["out"].shape and traj.shape[0] == g.get("traj_len", g["steps"] + 1)
+    if not g.get("extra"):
+        assert maxabs(traj[0], noise) == 0.0
     # first ODE state: one velocity evaluation scaled by dt
     assert maxabs(traj[1], g["traj_1"]) <= VEL_TOL
     err = (out.cpu() - g["out"]).abs()

@@ -274,7 +274,7 @@ def test_training_checkpoint_round_trip_in_reference_format(tmp_path):
     assert set(ck) == {"model_state_dict", "optimizer_state_dict", "ema_model_state_dict", "scheduler_state_dict", "update"}
     assert {"initted", "step"} <= set(ck["ema_model_state_dict"]) and all(
         k.startswith("ema_model.") for k in ck["ema_model_state_dict"] if k not in ("initted", "step"))
-    assert eng.load_checkpoint(path) == 3
+    assert eng.load_checkpoint(path) == 3 + 1  # the reference resumes at update + 1 (trainer.py:812)
     torch.cuda.synchronize()
     assert torch.equal(eng.p, snap[0]) and torch.equal(eng.m, snap[1]) and torch.equal(eng.v, snap[2]) and torch.equal(eng.ema, snap[3])
     assert (eng.step_count, eng.ema_calls) == snap[4:]
@@ -371,8 +371,8 @@ def test_trainer_loop_checkpoints_and_resume(tmp_path):
     assert ck["update"] == updates and {"model_state_dict", "optimizer_state_dict", "ema_model_state_dict"} <= set(ck)
     # resume: everything is already trained -> no further update, weights equal the checkpoint's
     tr2 = make()
-    assert tr2.load_checkpoint() == updates
-    assert tr2.train(ds, num_workers=0, resumable_with_seed=666) == updates and not tr2.losses
+    assert tr2.load_checkpoint() == updates + 1  # trainer.py:812
+    assert tr2.train(ds, num_workers=0, resumable_with_seed=666) == updates + 1 and not tr2.losses
     w = dict(tr2.model.named_parameters())["transformer.proj_out.weight"]
     assert torch.equal(w.detach().cpu(), ck["model_state_dict"]["transformer.proj_out.weight"])
     # "sample" batching, one epoch, no accumulation
@@ -380,6 +380,6 @@ def test_trainer_loop_checkpoints_and_resume(tmp_path):
     model.vocab_char_map = {chr(97 + i): i for i in range(26)}
     tr3 = Trainer(model, epochs=1, learning_rate=1e-3, num_warmup_updates=1, save_per_updates=1000, checkpoint_path=str(tmp_path / "ck3"),
                   batch_size_per_gpu=6, batch_size_type="sample", keep_last_n_checkpoints=0)
-    assert tr3.train(ds, num_workers=0) == math.ceil(len(ds) / 6)
+    assert tr3.train(ds, num_workers=2) == math.ceil(len(ds) / 6)  # forked loader workers: collate must not pin there
     with pytest.raises(NotImplementedError):
         Trainer(model, epochs=1, learning_rate=1e-3, duration_predictor=object())

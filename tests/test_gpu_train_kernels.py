@@ -154,7 +154,7 @@ def test_grn_gelu_bwd_and_dwconv_bwd_and_lookup_bwd():
     tok[:, :nt] = ids + 1
     F.embedding(tok, table).backward(dh)
     dt = torch.zeros(V, T, device=dev)
-    L.check(lib.f5b_text_lookup_bwd(dh.data_ptr(), ids.data_ptr(), nt, dt.data_ptr(), B, n, T, 0, L.stream()), "text_lookup_bwd")
+    L.check(lib.f5b_text_lookup_bwd(dh.data_ptr(), ids.data_ptr(), nt, dt.data_ptr(), B, n, T, V, 0, L.stream()), "text_lookup_bwd")
     torch.cuda.synchronize()
     assert _rel(dt, table.grad) <= 1e-5
 

@@ -240,9 +240,66 @@ def test_lr_and_ema_schedules_match_torch_and_ema_pytorch_rules():
         sch.step()
     e = EmaSchedule()
     assert e.decay_for_call(2) is None and e.decay_for_call(1) == "copy" and e.decay_for_call(101) == "copy"
-    d = e.decay_for_call(111)  # step 110 -> epoch 9
-    assert abs(d - (1 - (1 + 9) ** (-2 / 3))) < 1e-12
+    # ema_pytorch: update() gates on the pre-increment step, get_current_decay() reads self.step after the increment:
+    # call 111 -> step 110 -> epoch = 111 - 100 - 1 = 10
+    d = e.decay_for_call(111)
+    assert abs(d - (1 - (1 + 10) ** (-2 / 3))) < 1e-12
     assert e.decay_for_call(10 ** 8 + 1) == 0.9999
+    # world > 1: the reference multiplies the warm-up by num_processes (trainer.py:1179-1181) BECAUSE accelerate's prepared scheduler
+    # steps num_processes times per optimizer update; the effective warm-up stays num_warmup_updates updates
+    world, nw, per_proc_total = 4, 3, 10
+    opt = torch.optim.SGD([p], lr=7.5e-5)
+    wu, tot = nw * world, per_proc_total
+    sch = SequentialLR(opt, [LinearLR(opt, 1e-8, 1.0, wu), LinearLR(opt, 1.0, 1e-8, max(tot - wu, 1))], milestones=[wu])
+    ours = WarmupLinearDecay(7.5e-5, wu, tot, steps_per_update=world)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for u in range(per_proc_total):
+            assert abs(opt.param_groups[0]["lr"] - ours.lr(u)) <= 1e-12 + 1e-6 * ours.lr(u), u
+            opt.step()
+            for _ in range(world):
+                sch.step()
+    assert abs(ours.lr(nw) - 7.5e-5) < 1e-12  # full rate after num_warmup_updates optimizer updates, whatever the world size
+
+
+def test_trainer_checkpoint_search_order_and_state_dict_cleaning(tmp_path):
+    """trainer.py:600-728: model_last.pt > latest model_<n> (.pt or .safetensors) > first pretrained_*; weights under
+    model_state_dict / ema_model_state_dict / state_dict / model with ema_model. / module. / _orig_mod. prefixes stripped"""
+    import types
+    from eraxvif5tts_b200.model.trainer import Trainer
+    from eraxvif5tts_b200.train import TrainEngine
+    d = tmp_path / "ck"
+    d.mkdir()
+    find = lambda: Trainer.find_checkpoint(types.SimpleNamespace(checkpoint_path=str(d)))  # noqa: E731
+    assert find() is None
+    (d / "notes.txt").write_text("x")
+    assert find() is None
+    (d / "pretrained_b.safetensors").write_bytes(b"")
+    (d / "pretrained_a.pt").write_bytes(b"")
+    assert find().endswith("pretrained_a.pt")
+    (d / "model_900.pt").write_bytes(b"")
+    (d / "model_1200.safetensors").write_bytes(b"")
+    assert find().endswith("model_1200.safetensors")
+    (d / "model_last.pt").write_bytes(b"")
+    assert find().endswith("model_last.pt")
+    e = tmp_path / "odd"
+    e.mkdir()
+    (e / "weights.pt").write_bytes(b"")
+    with pytest.raises(FileNotFoundError):
+        Trainer.find_checkpoint(types.SimpleNamespace(checkpoint_path=str(e)))
+    t = torch.zeros(1)
+    clean = TrainEngine._model_state_dict
+    assert set(clean({"model_state_dict": {"a.w": t, "b.w": t}})) == {"a.w", "b.w"}
+    ema = {f"ema_model.l{i}.w": t for i in range(10)}  # the prefix must be carried by >= 80 % of the keys (reference rule)
+    ema.update(initted=t, step=t)
+    assert set(clean({"ema_model_state_dict": ema})) == {f"l{i}.w" for i in range(10)}
+    assert set(clean({"state_dict": {"module.a.w": t, "module.b.w": t}})) == {"a.w", "b.w"}
+    assert set(clean({"model": {"_orig_mod.a.w": t}})) == {"a.w"}
+    assert set(clean({"state_dict_loaded_from_safetensors": {"a.w": t}})) == {"a.w"}
+    assert set(clean({"model_state_dict": {}, "ema_model_state_dict": {"ema_model.a.w": t}})) == {"a.w"}  # empty dicts are skipped
+    with pytest.raises(KeyError):
+        clean({"optimizer_state_dict": {}})
 
 
 class _FakeFrames:

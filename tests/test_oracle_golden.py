@@ -48,7 +48,7 @@ def test_dit_forward_matches_reference(golden, tag):
         assert (out - ref).abs().max() <= 1e-3 * ref.abs().max(), name
 
 
-@pytest.mark.parametrize("tag", ["tiny_b2", "tiny_b1", "tiny_mid"])
+@pytest.mark.parametrize("tag", ["tiny_b2", "tiny_b1", "tiny_mid", "tiny_dup"])
 def test_cfm_sample_matches_reference(golden, tag):
     g = golden(f"sample_{tag}.pt")
     cfg = _cfg(g["cfg"])
@@ -56,8 +56,8 @@ def test_cfm_sample_matches_reference(golden, tag):
     assert state_dict_digest(sd) == g["digest"]
     out, traj = O.cfm_sample(sd, cfg, g["cond"], g["text"], g["duration"], lens=g["lens"], steps=g["steps"],
                              cfg_strength=g["cfg_strength"], sway_sampling_coef=g["sway"], seed=g["sample_seed"],
-                             method=g["method"])
-    assert out.shape == g["out"].shape
+                             method=g["method"], **g.get("extra", {}))
+    assert out.shape == g["out"].shape and traj.shape[0] == g.get("traj_len", g["steps"] + 1)
     assert (traj[1] - g["traj_1"]).abs().max() < 1e-3
     assert (out - g["out"]).abs().max() < 2e-3
 

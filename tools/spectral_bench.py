@@ -1,7 +1,7 @@
 """MelSpec / iSTFT-head microbenchmark at the cfg-2 shapes (HBM-bound kernels of the north star)"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from eraxvif5tts_b200 import ops
 from eraxvif5tts_b200.model import MelSpec
 import gpu_diag as D
