@@ -3,7 +3,8 @@
 /root/reference is a Python code base and exists only in the build container.  Like a C reference that is compiled from its
 sources where they lie into `oracle/_ref/*.so`, this recipe BYTE-COMPILES the four files `oracle/ref_shim.py` executes —
 model/utils.py, model/modules.py, model/backbones/dit.py, model/cfm.py — with `py_compile`, straight from /root/reference into
-the git-ignored (NOT gpurun-ignored) `oracle/_ref/f5_tts/...*.pyc`.  No reference source text is copied anywhere; the .pyc
+the git-ignored (NOT gpurun-ignored) `oracle/_ref/f5_tts/...*.code` (CPython code objects, the .pyc format under a
+neutral extension: snapshot tools commonly drop *.pyc).  No reference source text is copied anywhere; the compiled
 files never enter the repository history and the product package never reads them.  With them present, `bench.py --impl
 reference` and `cpu_baseline` on the GPU box (same image, same CPython) time the REFERENCE ITSELF (`kind: "reference"`)
 instead of the oracle port.  Run by `__graft_entry__.build()` whenever /root/reference is present.
@@ -23,7 +24,7 @@ FILES = ("model/utils.py", "model/modules.py", "model/backbones/dit.py", "model/
 
 
 def staged() -> bool:
-    return all(os.path.isfile(os.path.join(DST_ROOT, "f5_tts", rel + "c")) for rel in FILES)
+    return all(os.path.isfile(os.path.join(DST_ROOT, "f5_tts", rel[:-3] + ".code")) for rel in FILES)
 
 
 def stage(quiet: bool = False) -> bool:
@@ -34,7 +35,7 @@ def stage(quiet: bool = False) -> bool:
         return staged()
     digests = {}
     for rel in FILES:
-        src, dst = os.path.join(src_pkg, rel), os.path.join(DST_ROOT, "f5_tts", rel + "c")
+        src, dst = os.path.join(src_pkg, rel), os.path.join(DST_ROOT, "f5_tts", rel[:-3] + ".code")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile=f"<reference>/src/f5_tts/{rel}", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

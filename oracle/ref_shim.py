@@ -30,8 +30,8 @@ def source_available() -> bool:
 
 
 def available() -> bool:
-    """the reference's modules can be loaded: from source (build container) or from oracle/_ref/*.pyc (GPU box)"""
-    return source_available() or os.path.isfile(os.path.join(_PYC, "model", "cfm.pyc"))
+    """the reference's modules can be loaded: from source (build container) or from oracle/_ref/*.code (GPU box)"""
+    return source_available() or os.path.isfile(os.path.join(_PYC, "model", "cfm.code"))
 
 
 def _shim_modules():
@@ -101,7 +101,7 @@ def load():
         if from_source:
             spec = importlib.util.spec_from_file_location(name, os.path.join(_SRC, rel))
         else:
-            path = os.path.join(_PYC, rel + "c")
+            path = os.path.join(_PYC, rel[:-3] + ".code")  # a .pyc under a neutral extension (oracle/make_ref.py)
             spec = importlib.util.spec_from_file_location(name, path, loader=importlib.machinery.SourcelessFileLoader(name, path))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[name] = mod
