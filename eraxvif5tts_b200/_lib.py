@@ -156,6 +156,8 @@ def load() -> C.CDLL:
         raise F5bError("libf5b200.so ABI version mismatch; rebuild")
     if os.environ.get("F5B_ATTN_VARIANT"):  # kernel A/B switch for experiments (0 = default)
         lib.f5b_debug_attn_variant(int(os.environ["F5B_ATTN_VARIANT"]))
+    if os.environ.get("F5B_ATTN_POLY"):
+        lib.f5b_debug_attn_poly(int(os.environ["F5B_ATTN_POLY"]))
     if os.environ.get("F5B_PDL"):  # A/B override of set_dependent_launch() below
         lib.f5b_set_dependent_launch(int(os.environ["F5B_PDL"]))
     _lib = lib

@@ -14,9 +14,12 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-OBJDIR = os.path.join(PKG, "build")
-LIB = os.path.join(LIBDIR, "libf5b200.so")
-UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_ts", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
+# F5B_BUILD_TAG=<tag> (with F5B_NVCC_EXTRA=-D...): an instrumented / experimental build next to the product library
+# (lib/libf5b200_<tag>.so, loaded with F5B_LIB=...), never instead of it
+_TAG = os.environ.get("F5B_BUILD_TAG", "")
+OBJDIR = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(LIBDIR, "libf5b200" + ("_" + _TAG if _TAG else "") + ".so")
+UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_fa", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -442,8 +442,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 long long* g_attn_trace = nullptr;
-int g_attn_variant = 0;  // 0: shared-memory operands (this file), 1: tensor-memory operands (attention_ts.cu)
-int attn_fwd_ts(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B,
+int g_attn_variant = 0;  // 0: first-generation kernel (this file), 1: persistent ping-pong kernel (attention_fa.cu)
+int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B,
                 int H, int n, float scale, cudaStream_t stream);
 
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
@@ -451,7 +451,7 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
-  if (g_attn_variant == 1) return attn_fwd_ts(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, stream);
+  if (g_attn_variant == 1) return attn_fwd_fa(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, stream);
   // q, k, v are token-major matrices [B*n, ld] (e.g. the three column sections of the fused QKV GEMM output); head h of
   // batch row b is the strided box (cols h*64.., rows b*n + pos) — TMA gathers it, no head-major copy exists
   CUtensorMap tmQ, tmK, tmV;

@@ -2,7 +2,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eraxvif5tts_b200 import ops
-B, H, n = 8, 16, 1875
+B, H, n = 32, 16, 1875
 dev = "cuda"
 D = H * 64
 qkv = torch.randn(B * n, 3 * D, device=dev).to(torch.bfloat16)
