@@ -204,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   griddep_launch_dependents();
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {  // (not `lane == 0`: see tile_engine.cuh — ptxas emits plain tcgen05 / TMA sequences in an elected region)
       const uint32_t idesc = idesc_bf16(128, 64, 0, 0);     // S = Q K^T: both operands K-major
       const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);  // O += P V: V is MN-major (d contiguous, keys strided)
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);

@@ -151,7 +151,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < Tq; ++j) {
       const int st = j & 1;
       if (j >= 2) mbar_wait(&bar_free[st], ((j >> 1) - 1) & 1);  // tile j-2 retired (a per-stage barrier cannot run a phase ahead)
-      if (lane == 0) {
+      if (elect_one()) {  // (not `lane == 0`: plain UTMALDG instead of a per-instruction ELECT / BRA.U.ANY loop, see tile_engine.cuh)
         mbar_arrive_expect_tx(&bar_qdo[st], 2 * AB_TILE);
         tma_load_3d(sQ + st * AB_TILE, &tmQ, &bar_qdo[st], h * 64, j * AB_T, b);
         tma_load_3d(sdO + st * AB_TILE, &tmdO, &bar_qdo[st], h * 64, j * AB_T, b);
@@ -167,7 +167,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // the issuing lane is chosen by elect.sync, not `lane == 0`: ptxas then emits plain UTCHMMA sequences (32 small MMAs per tile pair
+    // here; under a lane predicate each sat in its own R2UR + ELECT + BRA.U.ANY loop, ~65 clocks apiece against 32-64 of execution)
+    if (elect_one()) {
       const uint32_t id_sq = idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
       const uint32_t id_acc = idesc_bf16(128, 64, 0, 1);   // dV, dK: B is MN-major
       const uint32_t id_dq = idesc_bf16(128, 64, 1, 1);    // dQ: A (dS^T tile) and B (K) both MN-major
@@ -259,7 +261,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_dqfree);
-      if (lane == 0) bulk_wait_read0();  // the previous boxes have been read out of the staging buffer
+      if (elect_one()) bulk_wait_read0();  // the previous boxes have been read out of the staging buffer
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -270,14 +272,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
 #ifndef AB_EXPERIMENT_NO_DQ_REDUCE
-      if (lane == 0) {
+      if (elect_one()) {
         tma_reduce_add_3d(&tmdQ, my_stg, h * 64, j * AB_T + lq * 32, b);
         tma_reduce_add_3d(&tmdQ, my_stg + 4096, h * 64 + 32, j * AB_T + lq * 32, b);
         bulk_commit();
       }
 #endif
     }
-    if (lane == 0) bulk_wait0();  // the reductions have landed before the CTA retires its shared memory
+    if (elect_one()) bulk_wait0();  // the reductions have landed before the CTA retires its shared memory
   } else {
     // ------------------------------------------------------------------------------------------------ softmax / gradient threads
     const int lq = warp & 3;          // TMEM lane quarter this warp may touch

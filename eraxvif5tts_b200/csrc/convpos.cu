@@ -181,8 +181,10 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     nsub = min(HALO_SUB, (left + BM - 1) / BM);
   };
 
+  // issuing lanes chosen by elect.sync, not `lane == 0` (see tile_engine.cuh: plain UTMALDG / UTCHMMA sequences instead of one
+  // R2UR + ELECT + BRA.U.ANY loop per instruction)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -207,7 +209,7 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16(BM, p.NP, 0, 0);
       int stage = 0;
       uint32_t phase = 0;

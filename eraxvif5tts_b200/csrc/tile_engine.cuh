@@ -119,8 +119,12 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int total = p.num_units();  // work units: tiles, or vertical tile pairs when CL == 2
   const int kblocks = p.num_kblocks();
 
+  // The single issuing lane of the producer / MMA warps is chosen by elect.sync, NOT by `lane == 0`: ptxas then knows the region is
+  // single-threaded and emits plain UTMALDG / UTCHMMA / UTCBAR sequences from uniform registers; under a lane predicate it wraps EVERY
+  // such instruction in an R2UR + ELECT + BRA.U.ANY "waterfall" loop (~65 clocks per tcgen05.mma — twice the execution time of a
+  // 128 x 64 x 16 MMA; measured in profiles/r02_attention_fa_notes.md).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = Cfg::A_BYTES + p.b_tx_bytes();
@@ -144,7 +148,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && (!TWOSM || crank == 0)) {
+    if ((!TWOSM || crank == 0) && elect_one()) {
       uint32_t idesc;
       if constexpr (TWOSM) idesc = p.idesc2();
       else idesc = p.idesc();
@@ -206,7 +210,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // 64-column granules: two TMEM chunks -> one [32 x 64] bf16 staging tile -> one TMA store
 #pragma unroll 1
         for (int g = half; g * 64 < ncols; g += 2) {
-          if (lane == 0) bulk_wait_read0();  // the previous store has drained the staging tile
+          if (elect_one()) bulk_wait_read0();  // the previous store has drained the staging tile
           __syncwarp();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -230,7 +234,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&tmC, stg, p.out_col0(tile) + g * 64, p.out_row0(tile) + quad * 32);
             bulk_commit();
           }
@@ -244,7 +248,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_ld_wait();
           float v[32];
           p.compute(ctx, g * 32, r, v);
-          if (lane == 0) bulk_wait_read0();
+          if (elect_one()) bulk_wait_read0();
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -253,7 +257,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                      __float_as_uint(v[q * 4 + 3])));
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_reduce_add_2d(&tmC, stg, p.out_col0(tile) + g * 32, p.out_row0(tile) + quad * 32);
             bulk_commit();
           }
@@ -267,7 +271,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
     if constexpr (P::STORE != STORE_DIRECT) {
-      if (lane == 0) bulk_wait0();
+      if (elect_one()) bulk_wait0();  // (elect.sync with the full mask picks the same lane every time: the one that committed the groups)
     }
   }
   tc_fence_before();

@@ -25,18 +25,16 @@ torch.cuda.synchronize()
 raw.f5b_debug_set_attn_trace(None)
 t = tr.cpu().view(3, 64, 8)
 t0 = int(t[t > 0].min())
-print("softmax groups: per key tile  [wait S start, S ready, loaded, max done, exps done, P published]  (clk since first stamp); d = deltas")
+print("softmax groups, per 64-key tile: [tile start, gap start, gap done]  (group 0: gap behind the tile; group 1: the previous tile's gap, half way through) (clk since first stamp)")
 for wg in range(2):
-    for i in range(34):
-        r = [int(x) - t0 for x in t[wg, i, :6]]
+    for i in range(40):
+        r = [int(x) - t0 for x in t[wg, i, :3]]
         if r[1] < 0:
             continue
-        d = [r[k + 1] - r[k] for k in range(5)]
-        print(f"  wg{wg} tile {i:2d}: " + " ".join(f"{x:7d}" for x in r) + "   d: wait %5d ld %4d max %4d exp %5d st+arrive %4d" % tuple(d))
-print("MMA thread: per P V issue [wait P start, P seen, operands ready, issued]")
-for i in range(64):
-    r = [int(x) - t0 for x in t[2, i, :6]]
+        print(f"  wg{wg} tile {i:2d}: " + " ".join(f"{x:7d}" for x in r) + "   d: to gap %5d gap %4d" % (r[1] - r[0], r[2] - r[1]))
+print("MMA warp of tile 0, per key tile: [wait P start, P seen, P V issued, S(+3) issued]")
+for i in range(40):
+    r = [int(x) - t0 for x in t[2, i, :4]]
     if r[1] < 0:
         continue
-    r = [r[0], r[1], r[3], r[4]]
-    print(f"  pv {i:2d}: " + " ".join(f"{x:7d}" for x in r) + "   d: waitP %5d waitV %4d issue %4d" % tuple(r[k + 1] - r[k] for k in range(3)))
+    print(f"  step {i:2d}: " + " ".join(f"{x:7d}" for x in r) + "   d: waitP %5d pv %4d s %4d" % (r[1] - r[0], r[2] - r[1], r[3] - r[2]))
