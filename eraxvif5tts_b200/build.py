@@ -19,7 +19,7 @@ LIBDIR = os.path.join(PKG, "lib")
 _TAG = os.environ.get("F5B_BUILD_TAG", "")
 OBJDIR = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(LIBDIR, "libf5b200" + ("_" + _TAG if _TAG else "") + ".so")
-UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_fa", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
+UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 
@@ -40,6 +40,11 @@ def _headers_mtime() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     extra = os.environ.get("F5B_NVCC_EXTRA", "").split()  # e.g. -DATT_TRACE for the instrumented attention build
+    global UNITS
+    if "-DF5B_WITH_ATTN_FA" in extra and "attention_fa" not in UNITS:
+        # the experimental persistent attention forward (slower than attention.cu; kept for its traces and notes,
+        # profiles/r02_attention_fa_notes.md) is only part of tagged experiment builds, never of the product library
+        UNITS = UNITS + ["attention_fa"]
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hm = _headers_mtime()

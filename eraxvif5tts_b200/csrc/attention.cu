@@ -442,16 +442,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 long long* g_attn_trace = nullptr;
-int g_attn_variant = 0;  // 0: first-generation kernel (this file), 1: persistent ping-pong kernel (attention_fa.cu)
+int g_attn_variant = 0;  // 0: this file; 1: the experimental persistent kernel (attention_fa.cu, only in F5B_WITH_ATTN_FA builds)
+#ifdef F5B_WITH_ATTN_FA
 int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B,
                 int H, int n, float scale, cudaStream_t stream);
+#endif
 
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
              int n, float scale, cudaStream_t stream) {
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
+#ifdef F5B_WITH_ATTN_FA
   if (g_attn_variant == 1) return attn_fwd_fa(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, stream);
+#endif
   // q, k, v are token-major matrices [B*n, ld] (e.g. the three column sections of the fused QKV GEMM output); head h of
   // batch row b is the strided box (cols h*64.., rows b*n + pos) — TMA gathers it, no head-major copy exists
   CUtensorMap tmQ, tmK, tmV;
@@ -494,3 +498,6 @@ extern "C" int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }
 extern "C" void f5b_debug_attn_variant(int v) { f5b::g_attn_variant = v; }
+#ifndef F5B_WITH_ATTN_FA
+extern "C" void f5b_debug_attn_poly(int) {}
+#endif

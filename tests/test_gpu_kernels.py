@@ -114,31 +114,3 @@ def test_attention_random_sweep(D):
         lens = None if it % 2 == 0 else [rng.randint(1, n) for _ in range(B)]
         D.qkv_attn_case(B, H, n, lens, rope_heads=rng.choice([0, 1, H]))
     _check(D)
-
-
-def test_attention_tensor_memory_variant():
-    """the experimental tensor-memory-operand forward kernel (attention_ts.cu) stays bit-compatible in behaviour with the default:
-    same outputs within bf16 rounding, same zeroing of padded rows, on ragged and tail shapes"""
-    import ctypes as C
-    import torch
-    from eraxvif5tts_b200 import _lib as L, ops
-    L.load()
-    raw = C.CDLL(L.LIB_PATH)
-    dev = torch.device("cuda", 0)
-    g = torch.Generator().manual_seed(3)
-    try:
-        for B, H, n, lens in ((2, 4, 500, [500, 260]), (1, 3, 1000, None), (3, 2, 130, [130, 1, 64])):
-            D = H * 64
-            qkv = torch.randn(B * n, 3 * D, generator=g).to(dev).bfloat16()
-            lens_t = torch.tensor(lens, dtype=torch.int32, device=dev) if lens else None
-            outs = []
-            for variant in (0, 1):
-                raw.f5b_debug_attn_variant(variant)
-                out = torch.full((B * n, D), float("nan"), dtype=torch.bfloat16, device=dev)
-                ops.attn_fwd(qkv[:, :D], qkv[:, D:], qkv[:, 2 * D:], 3 * D, out, lens_t, 0, B, H, n)
-                torch.cuda.synchronize()
-                outs.append(out.float())
-            assert torch.isfinite(outs[1]).all()
-            assert (outs[0] - outs[1]).abs().max().item() <= 2e-2
-    finally:
-        raw.f5b_debug_attn_variant(0)
