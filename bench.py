@@ -435,8 +435,10 @@ def measure_train(args, wname, cfg, B, n, desc, rank, local_rank, world, dev, st
     L.load()
     model, _ = build_product_models(cfg, dev)
     train_dropout = float(os.environ.get("F5B_TRAIN_DROPOUT", "0"))  # cfg-5 is quoted at dropout 0 (parity setting); 0.1 = the reference's training default
-    eng = TrainEngine(model, with_ema=(rank == 0), dropout=train_dropout)  # EMA only on the main process (trainer.py:179-181)
+    ckpt = os.environ.get("F5B_TRAIN_CHECKPOINT", "0") == "1"  # the reference's checkpoint_activations option (dit.py:221-223)
+    eng = TrainEngine(model, with_ema=(rank == 0), dropout=train_dropout, checkpoint_activations=ckpt)  # EMA only on the main process (trainer.py:179-181)
     config["dropout"] = train_dropout
+    config["checkpoint_activations"] = ckpt
     if train_dropout > 0:
         config["workload"] = config["workload"].replace("dropout 0", f"dropout {train_dropout:g} (FeedForward + to_out sites)")
     if world > 1:

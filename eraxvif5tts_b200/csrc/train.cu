@@ -33,6 +33,11 @@ struct BlockSave {
 };
 
 constexpr int MAX_DEPTH = 64;
+// Activation checkpointing (the reference's `checkpoint_activations`, model/backbones/dit.py:121,158,221-223: one
+// torch.utils.checkpoint per DiT block).  Off: every block keeps its ten intermediate tensors (1.26 GB per block at 32 x 1200 frames,
+// Base).  On: every block keeps only its fp32 input; all blocks share ONE set of intermediates, and the backward re-runs a block's
+// forward (same kernels, same dropout masks: they are a pure function of the seed) right before differentiating it.
+static int g_ckpt = 0;
 
 struct TrainWs {
   // time / modulation chain (M = B rows)
@@ -79,16 +84,22 @@ static TrainWs carve_train(const F5bDitDesc& d, int B, int n, void* ws) {
   for (int i = 0; i < d.depth && i < MAX_DEPTH; ++i) {
     BlockSave& s = w.blk[i];
     s.x_in = x_next;
-    s.x_mid = c.take<float>(rows * D);
-    s.lse = c.take<float>((size_t)B * H * n);
-    s.a = c.take<bf>(rows * D);
-    s.qkv = c.take<bf>(rows * 3 * D);
-    s.o = c.take<bf>(rows * D);
-    s.z1 = c.take<bf>(rows * D);
-    s.f = c.take<bf>(rows * D);
-    s.h1 = c.take<bf>(rows * F);
-    s.u = c.take<bf>(rows * F);
-    s.z2 = c.take<bf>(rows * D);
+    if (g_ckpt && i > 0) {  // checkpointing: the intermediates of every block alias block 0's
+      const float* keep = s.x_in;
+      s = w.blk[0];
+      s.x_in = const_cast<float*>(keep);
+    } else {
+      s.x_mid = c.take<float>(rows * D);
+      s.lse = c.take<float>((size_t)B * H * n);
+      s.a = c.take<bf>(rows * D);
+      s.qkv = c.take<bf>(rows * 3 * D);
+      s.o = c.take<bf>(rows * D);
+      s.z1 = c.take<bf>(rows * D);
+      s.f = c.take<bf>(rows * D);
+      s.h1 = c.take<bf>(rows * F);
+      s.u = c.take<bf>(rows * F);
+      s.z2 = c.take<bf>(rows * D);
+    }
     x_next = c.take<float>(rows * D);
   }
   w.x_fin = x_next;
@@ -195,7 +206,47 @@ static int wgrad(const void* dY, int ldy, const void* X, int ldx, float* dW, int
   return f5b_gemm_tn(dY, ldy, 1, X, ldx, 1, dW, ldw, 1, n_out, k_in, rows, pick_splits(n_out, k_in, rows), s);
 }
 
+// Forward of DiT block i up to z2 (everything the block's backward reads): a = AdaLN(x_in) is expected in b.a unless `with_ln`.
+static int train_block_forward(const F5bDitDesc& d, const TrainWs& w, int i, int B, int n, const int32_t* lens, const float* rope, bool with_ln,
+                               cudaStream_t s) {
+  const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads;
+  const int rows = B * n;
+  const int64_t mod_dim = (int64_t)d.depth * 6 * D + 2 * D;
+  f5b_stream_t stream = reinterpret_cast<f5b_stream_t>(s);
+  const BlockSave& b = w.blk[i];
+  const float* m = w.mod + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (modules.py:312)
+  const bf* qkv_w = reinterpret_cast<const bf*>(d.qkv_w);
+  const bf* out_w = reinterpret_cast<const bf*>(d.out_w);
+  const bf* ff1_w = reinterpret_cast<const bf*>(d.ff1_w);
+  const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
+  if (with_ln) F5B_TRY(ln_modulate(b.x_in, m + D, m, mod_dim, 0, b.a, rows, n, D, 1e-6f, s));
+  F5bGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
+  g.bias = d.qkv_b + (size_t)i * 3 * D;
+  g.out = b.qkv; g.ldc = 3 * D;
+  g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
+  F5B_TRY(gemm(b.a, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
+  F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s));
+  F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
+  // x_mid = x_in + gate_msa * mask(z1);  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
+  // (train mode: to_out's Dropout sits between z1 and the gate -- site 1; FeedForward's follows the GELU -- site 0)
+  F5B_TRY(f5b_gate_add_ln_modulate_site(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D,
+                                        1e-6f, i, 1, stream));
+  F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
+  F5B_TRY(f5b_act_fwd_site(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, i, 0, stream));
+  F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
+  return 0;
+}
+
 extern "C" {
+
+/* activation checkpointing for the f5b_dit_train_* drivers (see g_ckpt above): set it BEFORE f5b_dit_train_ws_bytes / _forward and
+ * leave it unchanged until the matching backward.  Gradients are bit-identical with and without it. */
+int f5b_train_set_checkpoint(int on) {
+  g_ckpt = on ? 1 : 0;
+  return 0;
+}
 
 size_t f5b_dit_train_ws_bytes(const F5bDit* h, int B, int n) {
   if (!h || B <= 0 || n <= 0 || h->d.depth > MAX_DEPTH) return 0;
@@ -238,10 +289,6 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
   F5B_TRY(f5b_act_fwd(w.u2, w.t1, (int64_t)rows * D, F5B_ACT_MISH, stream));
   F5B_TRY(f5b_gate_add(w.h0, w.t1, nullptr, 0, nullptr, w.blk[0].x_in, B, n, D, stream));
 
-  const bf* qkv_w = reinterpret_cast<const bf*>(d.qkv_w);
-  const bf* out_w = reinterpret_cast<const bf*>(d.out_w);
-  const bf* ff1_w = reinterpret_cast<const bf*>(d.ff1_w);
-  const bf* ff2_w = reinterpret_cast<const bf*>(d.ff2_w);
   // the gated residual of each branch is fused with the AdaLN of the next one (f5b_gate_add_ln_modulate): the first AdaLN of block
   // 0 runs alone, the last gated residual feeds AdaLayerNorm_Final
   {
@@ -252,23 +299,8 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
     const BlockSave& b = w.blk[i];
     const bool last = i + 1 == d.depth;
     float* x_out = last ? w.x_fin : w.blk[i + 1].x_in;
-    const float* m = w.mod + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (modules.py:312)
-    F5bGemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
-    g.bias = d.qkv_b + (size_t)i * 3 * D;
-    g.out = b.qkv; g.ldc = 3 * D;
-    g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
-    F5B_TRY(gemm(b.a, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
-    F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s));
-    F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
-    // x_mid = x_in + gate_msa * mask(z1);  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
-    // (train mode: to_out's Dropout sits between z1 and the gate -- site 1; FeedForward's follows the GELU -- site 0)
-    F5B_TRY(f5b_gate_add_ln_modulate_site(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D,
-                                          1e-6f, i, 1, stream));
-    F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
-    F5B_TRY(f5b_act_fwd_site(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, i, 0, stream));
-    F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
+    const float* m = w.mod + (size_t)i * 6 * D;
+    F5B_TRY(train_block_forward(d, w, i, B, n, lens, rope, false, s));
     // x_out = x_mid + gate_mlp * z2;  next AdaLN: block i+1's (shift_msa, scale_msa) or AdaLayerNorm_Final's (scale, shift; :333)
     const float* mn = w.mod + (size_t)(i + 1) * 6 * D;
     const float* nscale = last ? mn : mn + D;
@@ -317,6 +349,7 @@ static int train_backward_impl(const F5bDit* h, const void* dpred_bf16, const vo
     const BlockSave& b = w.blk[i];
     const float* m = w.mod + (size_t)i * 6 * D;
     float* dm = w.dmod + (size_t)i * 6 * D;
+    if (g_ckpt) F5B_TRY(train_block_forward(d, w, i, B, n, lens, rope, true, s));  // re-materialise the block's intermediates
     // ---- x_out = x_mid + gate_mlp * (W2 gelu(W1 f + b1) + b2),  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
     F5B_TRY(f5b_gate_bwd(w.dx, b.z2, m + 5 * D, mod_dim, nullptr, w.t1, dm + 5 * D, off(g.ff2_b, (size_t)i * D), B, n, D, stream));
     F5B_TRY(wgrad(w.t1, D, b.u, F, off(g.ff2_w, (size_t)i * D * F), F, rows, D, F, stream));

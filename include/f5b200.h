@@ -279,6 +279,11 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
  * once per micro-step with a fresh seed BEFORE f5b_dit_train_forward and leave it untouched until the matching backward returns.
  * The dropout inside scaled_dot_product_attention (:490) is not built: the attention kernels always run with p = 0. */
 int f5b_train_set_dropout(float p, uint64_t seed);
+/* Activation checkpointing of the DiT blocks (the reference's `checkpoint_activations`, /root/reference/src/f5_tts/model/backbones/
+ * dit.py:121,158,221-223): on, every block keeps only its fp32 input and the backward re-runs the block's forward before
+ * differentiating it (workspace 4.6 GB instead of 29.6 GB at 32 x 1200 frames, F5TTS_Base; one extra forward per step).  Set it
+ * before f5b_dit_train_ws_bytes / f5b_dit_train_forward and keep it until the matching backward. */
+int f5b_train_set_checkpoint(int on);
 
 /* The same backward in pieces (parts bit 0 = head: proj_out + final AdaLN; bit 1 = blocks [blk_lo, blk_hi) in descending order;
  * bit 2 = tail: input embedding + modulation / time MLP), issued head -> blocks from depth down to 0 -> tail, so the host can start

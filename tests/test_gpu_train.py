@@ -84,6 +84,35 @@ def test_backward_vs_oracle_autograd(da, dt):
     print("worst gradients (fro err, cos, key):", worst[:5])
 
 
+def test_activation_checkpointing_same_gradients_less_memory():
+    """TrainEngine(checkpoint_activations=True) — the reference's DiT(checkpoint_activations=True), dit.py:221-223: every block keeps
+    only its input and its forward is re-run in the backward.  Same loss / prediction bit for bit, gradients equal up to the order of
+    the split-K / reduce-add sums (also with dropout: the masks are regenerated from the seed), and a several times smaller workspace."""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig.tiny(depth=4)
+    B, n = 3, 152
+    x1, x0, time, text, span = _draws(cfg, B, n, 21)
+    for p in (0.0, 0.1):
+        draws = dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False, drop_text=False, dropout_seed=7)
+        res = {}
+        for ck in (False, True):
+            model, sd = build_cfm(cfg, 0)
+            eng = TrainEngine(model, dropout=p, checkpoint_activations=ck)
+            eng.zero_grad()
+            loss, _, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=draws)
+            torch.cuda.synchronize()
+            res[ck] = (float(loss), pred.clone(), eng.g.clone(), eng._ws.numel())
+        assert res[True][0] == res[False][0] and torch.equal(res[True][1], res[False][1])
+        assert float((res[True][2] - res[False][2]).norm()) <= 1e-3 * float(res[False][2].norm())
+        assert res[True][3] < 0.6 * res[False][3], (res[True][3], res[False][3])  # depth 4: fixed buffers weigh in; depth 22: 4.6 vs 29.6 GB
+    # the DiT's own flag is the default
+    from eraxvif5tts_b200.model import CFM, DiT
+    tr = DiT(dim=cfg.dim, depth=2, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim, text_num_embeds=cfg.text_num_embeds,
+             text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, checkpoint_activations=True)
+    m = CFM(transformer=tr, mel_spec_kwargs=dict(n_mel_channels=cfg.mel_dim)).cuda()
+    assert TrainEngine(m).checkpoint_activations is True
+
+
 def test_backward_with_dropout_vs_oracle_autograd():
     """train-mode dropout (p = 0.1 as the reference trains, and a heavy p = 0.5): the oracle applies the SAME masks
     (oracle.dropout_multipliers restates the product's counter-based generator), so forward, loss and every gradient are judged
