@@ -87,6 +87,94 @@ def _read_wav(path: str):
         return torch.from_numpy(a.reshape(-1, ch).T.copy()), sr
 
 
+def _ms_to_samples(ms: float, sr: int) -> int:
+    return int(ms * sr / 1000.0)  # pydub: AudioSegment._parse_position -> int(frame_count(ms=...))
+
+
+def detect_silence(x: torch.Tensor, sr: int, min_silence_len: int = 1000, silence_thresh: float = -16.0, seek_step: int = 1):
+    """pydub.silence.detect_silence (third party, absent offline; restated from its published algorithm) on a mono float signal
+    `x` [samples] in [-1, 1]: windows of `min_silence_len` ms starting every `seek_step` ms whose RMS is at or below
+    10^(silence_thresh / 20) of full scale, merged into [start_ms, end_ms] ranges exactly like pydub does.  The window RMS comes from
+    one cumulative sum of squares (pydub: audioop.rms per slice)."""
+    seg_len = int(round(1000.0 * x.numel() / sr))  # len(AudioSegment) in ms
+    if seg_len < min_silence_len:
+        return []
+    thresh = 10.0 ** (silence_thresh / 20.0)
+    last = seg_len - min_silence_len
+    starts = list(range(0, last + 1, seek_step))
+    if last % seek_step:
+        starts.append(last)
+    csum = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(x.double().square(), 0)))
+    s0 = torch.tensor([_ms_to_samples(i, sr) for i in starts]).clamp(max=x.numel())
+    s1 = torch.tensor([_ms_to_samples(i + min_silence_len, sr) for i in starts]).clamp(max=x.numel())
+    cnt = (s1 - s0).clamp(min=1).double()
+    rms = torch.sqrt((csum[s1] - csum[s0]) / cnt)
+    silent = [starts[k] for k in torch.nonzero(rms <= thresh).flatten().tolist()]
+    if not silent:
+        return []
+    ranges = []
+    prev = silent.pop(0)
+    cur = prev
+    for st in silent:
+        continuous = st == prev + seek_step
+        has_gap = st > prev + min_silence_len
+        if not continuous and has_gap:
+            ranges.append([cur, prev + min_silence_len])
+            cur = st
+        prev = st
+    ranges.append([cur, prev + min_silence_len])
+    return ranges
+
+
+def split_on_silence(x: torch.Tensor, sr: int, min_silence_len: int = 1000, silence_thresh: float = -16.0, keep_silence: int = 100,
+                     seek_step: int = 1):
+    """pydub.silence.split_on_silence restated (see detect_silence): the non-silent stretches, each padded by `keep_silence` ms of the
+    surrounding silence (overlapping paddings meet half way).  Returns the list of signal pieces."""
+    seg_len = int(round(1000.0 * x.numel() / sr))
+    silent = detect_silence(x, sr, min_silence_len, silence_thresh, seek_step)
+    if not silent:
+        nonsilent = [[0, seg_len]]
+    elif silent[0][0] == 0 and silent[0][1] == seg_len:
+        nonsilent = []
+    else:
+        prev_end, nonsilent = 0, []
+        for st, en in silent:
+            nonsilent.append([prev_end, st])
+            prev_end = en
+        if en != seg_len:
+            nonsilent.append([prev_end, seg_len])
+        if nonsilent[0] == [0, 0]:
+            nonsilent.pop(0)
+    out = [[st - keep_silence, en + keep_silence] for st, en in nonsilent]
+    for a_, b_ in zip(out, out[1:]):
+        if b_[0] < a_[1]:
+            a_[1] = (a_[1] + b_[0]) // 2
+            b_[0] = a_[1]
+    return [x[_ms_to_samples(max(st, 0), sr): _ms_to_samples(min(en, seg_len), sr)] for st, en in out]
+
+
+def clip_reference(x: torch.Tensor, sr: int) -> torch.Tensor:
+    """The reference's clip_short rule (f5tts_wrapper.py:272-301): cut at a long silence (>= 1 s below -50 dBFS) once more than 6 s
+    are collected and the next piece would pass 12 s; if that still leaves more than 12 s, the same with short silences (>= 100 ms
+    below -40 dBFS); if that fails too, a hard cut at 12 s."""
+    def ms(t):
+        return int(round(1000.0 * t.numel() / sr))
+
+    def collect(pieces):
+        wave = x[:0]
+        for seg in pieces:
+            if ms(wave) > 6000 and ms(wave) + ms(seg) > 12000:
+                break
+            wave = torch.cat((wave, seg))
+        return wave
+    wave = collect(split_on_silence(x, sr, min_silence_len=1000, silence_thresh=-50, keep_silence=1000, seek_step=10))
+    if ms(wave) > 12000:
+        wave = collect(split_on_silence(x, sr, min_silence_len=100, silence_thresh=-40, keep_silence=1000, seek_step=10))
+    if ms(wave) > 12000:
+        wave = wave[: _ms_to_samples(12000, sr)]
+    return wave
+
+
 def _trim_silence_edges(audio: torch.Tensor, sr: int, threshold_db: float = -42.0) -> torch.Tensor:
     """_remove_silence_edges (f5tts_wrapper.py:356-377) restated on a tensor: drop leading / trailing 1 ms... 10 ms windows whose
     level is below the threshold (pydub measures dBFS on chunks)."""
@@ -169,8 +257,8 @@ class F5TTSWrapper:
         audio = audio.float()
         if audio.shape[0] > 1:
             audio = torch.mean(audio, dim=0, keepdim=True)
-        if clip_short and audio.shape[-1] > 12 * sr:  # the reference clips at silences found by pydub; we clip hard at 12 s
-            audio = audio[:, : 12 * sr]
+        if clip_short:  # silence-aware clipping, f5tts_wrapper.py:272-301 (pydub's split_on_silence restated on the tensor)
+            audio = clip_reference(audio[0], sr).unsqueeze(0)
         audio = _trim_silence_edges(audio, sr)
         audio = torch.cat((audio, torch.zeros(1, int(0.05 * sr))), dim=-1)  # + AudioSegment.silent(duration=50)
         if not ref_text.strip():

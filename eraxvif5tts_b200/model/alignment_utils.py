@@ -49,7 +49,60 @@ def windowed_monotonic_alignment(similarity_matrix, window_size=0.2, return_dura
 
 
 def progressive_monotonic_alignment(similarity_matrix):
-    raise NotImplementedError("the 'progressive' refinement (alignment_utils.py:260-334) is not built; use 'viterbi' or 'window'")
+    """alignment_utils.py:260-334: uniform segmentation refined by two greedy sweeps that move each boundary by up to
+    min(5, mel_len // 20) frames when that raises the score.  The sweep is inherently sequential (every decision changes the state the
+    next one reads) and touches O(nt) boundaries, so it runs on the HOST over a copy of the similarity matrix; the score of a trial
+    is the item's current score plus the change over the moved columns (the reference re-sums the whole [nt, mel_len] product for each
+    of the 11 trials of each boundary).  The reference's bookkeeping is kept literally: a trial of item i is compared against
+    `total_score`, which starts as the sum over the WHOLE batch and becomes the accepted trial's item-level score afterwards
+    (alignment_utils.py:281, 295, 315, 329-330); trial rows are overwritten, not exchanged, so a shift longer than a segment leaves a
+    frame assigned to two tokens, exactly as in the reference."""
+    import numpy as np
+    sim = similarity_matrix.detach().to(torch.float32).cpu().numpy().astype(np.float64)
+    b, nt, T = sim.shape
+    align = np.zeros((b, nt, T), dtype=np.float64)
+    bounds = torch.linspace(0, T, nt + 1).long().tolist()
+    for n in range(nt):
+        if bounds[n] < bounds[n + 1]:
+            align[:, n, bounds[n]:bounds[n + 1]] = 1.0
+    item = (sim * align).sum(axis=(1, 2))
+    total = float(item.sum())
+    shift_range = min(5, T // 20)
+    for _ in range(2):
+        for i in range(b):
+            for n in range(nt - 1):
+                row = align[i, n]
+                edge = np.nonzero((row[:-1] == 1.0) & (row[1:] == 0.0))[0]
+                if edge.size == 0:
+                    continue
+                boundary = int(edge[0])
+                best_score, best_shift, best_delta = total, 0, 0.0
+                for shift in range(-shift_range, shift_range + 1):
+                    nb = boundary + shift
+                    if not (0 <= nb < T - 1):
+                        continue
+                    if shift < 0:    # columns nb+1 .. boundary: row n -> 0, row n+1 -> 1
+                        c = slice(nb + 1, boundary + 1)
+                        delta = float(((0.0 - align[i, n, c]) * sim[i, n, c]).sum() + ((1.0 - align[i, n + 1, c]) * sim[i, n + 1, c]).sum())
+                    elif shift > 0:  # columns boundary+1 .. nb: row n -> 1, row n+1 -> 0
+                        c = slice(boundary + 1, nb + 1)
+                        delta = float(((1.0 - align[i, n, c]) * sim[i, n, c]).sum() + ((0.0 - align[i, n + 1, c]) * sim[i, n + 1, c]).sum())
+                    else:
+                        delta = 0.0
+                    new_score = float(item[i]) + delta
+                    if new_score > best_score:
+                        best_score, best_shift, best_delta = new_score, shift, delta
+                if best_shift != 0:
+                    nb = boundary + best_shift
+                    if best_shift < 0:
+                        align[i, n, nb + 1:boundary + 1] = 0.0
+                        align[i, n + 1, nb + 1:boundary + 1] = 1.0
+                    else:
+                        align[i, n, boundary + 1:nb + 1] = 1.0
+                        align[i, n + 1, boundary + 1:nb + 1] = 0.0
+                    item[i] += best_delta
+                    total = best_score
+    return torch.from_numpy(align).to(device=similarity_matrix.device, dtype=similarity_matrix.dtype)
 
 
 def monotonic_alignment_search(similarity_matrix, algorithm="viterbi"):

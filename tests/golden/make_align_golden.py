@@ -23,7 +23,7 @@ def ref_functions(names):
 
 
 def main():
-    vit, win = ref_functions(["viterbi_vectorized_alignment", "windowed_monotonic_alignment"])
+    vit, win, prog = ref_functions(["viterbi_vectorized_alignment", "windowed_monotonic_alignment", "progressive_monotonic_alignment"])
     g = torch.Generator().manual_seed(2024)
     cases = []
     for (b, nt, T, kind) in [(2, 5, 23, "randn"), (3, 12, 64, "randn"), (1, 1, 9, "randn"), (2, 7, 7, "randn"), (1, 9, 40, "neg"),
@@ -37,7 +37,9 @@ def main():
             n_idx = torch.arange(nt)[:, None].float() / nt
             t_idx = torch.arange(T)[None, :].float() / T
             sim = 3.0 * torch.exp(-((n_idx - t_idx) ** 2) * 60.0)[None].repeat(b, 1, 1) + 0.3 * sim
-        c = dict(sim=sim, viterbi=vit(sim.clone()))
+        c = dict(sim=sim, viterbi=vit(sim.clone()), progressive=prog(sim.clone()))
+        if b > 1:  # the batch-total bookkeeping of the progressive sweep only shows with b > 1; a b = 1 twin shows the plain greedy
+            c["progressive_item0"] = prog(sim[:1].clone())
         try:
             c["window"] = win(sim.clone())
         except Exception as e:  # the reference raises on an empty window

@@ -44,3 +44,23 @@ def test_alignment_properties():
             order = np.argsort(cols, kind="stable")
             assert (np.diff(rows[order]) >= 0).all()
         assert (dur.sum(-1) <= 70).all()
+
+
+def test_progressive_alignment_matches_reference_golden():
+    """progressive_monotonic_alignment (alignment_utils.py:260-334) runs on the host in the product (a sequential greedy sweep); it is
+    bit-exact against the reference's own function on every golden case, including the batch-total score bookkeeping that only shows
+    with b > 1 (the b = 1 twin of the same item refines differently)."""
+    import os
+    import torch
+    from eraxvif5tts_b200.model.alignment_utils import monotonic_alignment_search, progressive_monotonic_alignment
+    d = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "align_golden.pt"), weights_only=False)
+    twins_differ = 0
+    for c in d["cases"]:
+        got = progressive_monotonic_alignment(c["sim"])
+        assert got.dtype == c["sim"].dtype and torch.equal(got, c["progressive"]), tuple(c["sim"].shape)
+        assert torch.equal(monotonic_alignment_search(c["sim"], "progressive"), c["progressive"])
+        if "progressive_item0" in c:
+            one = progressive_monotonic_alignment(c["sim"][:1])
+            assert torch.equal(one, c["progressive_item0"])
+            twins_differ += int(not torch.equal(one[0], c["progressive"][0]))
+    assert twins_differ > 0

@@ -457,3 +457,58 @@ def test_trainer_batching_and_sharding_host_logic():
     import pytest
     with pytest.raises(ValueError):
         make(0, 1, "tokens")._batches(ds, None)
+
+
+def test_silence_aware_reference_clipping_matches_pydub_rules():
+    """preprocess_reference's clip_short (f5tts_wrapper.py:272-301) = pydub.silence.split_on_silence + the 6 s / 12 s collection rule.
+    pydub is absent offline: detect_silence is checked against a literal transcription of pydub's per-slice loop, and the clipping
+    rule on a signal whose silences are known by construction."""
+    import math
+    from eraxvif5tts_b200.infer.f5tts_wrapper import clip_reference, detect_silence, split_on_silence
+
+    def literal(x, sr, min_silence_len, silence_thresh, seek_step):
+        seg_len = int(round(1000.0 * len(x) / sr))
+        if seg_len < min_silence_len:
+            return []
+        th = 10 ** (silence_thresh / 20)
+        last = seg_len - min_silence_len
+        starts = list(range(0, last + 1, seek_step))
+        if last % seek_step:
+            starts.append(last)
+        sil = []
+        for i in starts:
+            sl = x[int(i * sr / 1000): int((i + min_silence_len) * sr / 1000)]
+            if (math.sqrt(float((sl.double() ** 2).mean())) if len(sl) else 0.0) <= th:
+                sil.append(i)
+        if not sil:
+            return []
+        out, prev = [], sil.pop(0)
+        cur = prev
+        for s_ in sil:
+            if not (s_ == prev + seek_step) and s_ > prev + min_silence_len:
+                out.append([cur, prev + min_silence_len])
+                cur = s_
+            prev = s_
+        out.append([cur, prev + min_silence_len])
+        return out
+
+    g = torch.Generator().manual_seed(0)
+    sr = 8000
+    x = torch.cat([torch.randn(int(d * sr), generator=g) * a for d, a in
+                   ((1.3, 0.2), (1.4, 0.0005), (2.2, 0.3), (0.3, 0.001), (3.0, 0.25), (1.2, 0.0), (4.0, 0.2), (1.5, 0.0002), (5.0, 0.3))]).clamp(-1, 1)
+    for args in ((1000, -50, 10), (100, -40, 10), (300, -45, 7)):
+        assert detect_silence(x, sr, *args) == literal(x, sr, *args), args
+    assert detect_silence(x, sr, 1000, -50, 10) == [[1300, 2700], [8200, 9400], [13400, 14900]]
+    pieces = split_on_silence(x, sr, 1000, -50, 1000, 10)
+    assert [round(len(p) / sr, 2) for p in pieces] == [2.0, 6.8, 5.35, 5.75]  # paddings of 1 s meet half way inside shorter silences
+    # rule 1: stop once > 6 s are collected and the next piece would pass 12 s -> 2.0 + 6.8
+    assert abs(len(clip_reference(x, sr)) / sr - 8.8) < 1e-3
+    # no silence at all: hard cut at 12 s (rule 3); short audio: untouched
+    noisy = torch.randn(20 * sr, generator=g) * 0.2
+    assert len(clip_reference(noisy, sr)) == 12 * sr
+    short = torch.randn(3 * sr, generator=g) * 0.2
+    assert torch.equal(clip_reference(short, sr), short)
+    # only short pauses (200 ms below -40 dBFS): rule 2 finds them where rule 1 cannot
+    y = torch.cat([torch.cat((torch.randn(int(2.3 * sr), generator=g) * 0.2, torch.randn(int(0.2 * sr), generator=g) * 0.002)) for _ in range(8)])
+    w = clip_reference(y, sr)
+    assert 6.0 < len(w) / sr <= 12.0 and len(w) < len(y)
