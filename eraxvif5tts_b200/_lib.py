@@ -22,12 +22,13 @@ class GemmArgs(C.Structure):
     _fields_ = [("M", i32), ("N", i32), ("K", i32), ("epi", i32), ("act", i32), ("bias", vp), ("out", vp), ("ldc", i32),
                 ("out2", vp), ("ldc2", i32), ("out3", vp), ("addsrc", vp), ("ld_add", i32), ("rows_per_batch", i32),
                 ("gate", vp), ("gate_bstride", i64), ("lens", vp), ("batch_mod", i32), ("rope", vp), ("rope_heads", i32),
-                ("heads", i32), ("n_pad", i32)]
+                ("heads", i32), ("tf32", i32)]
 
 
 class DitDesc(C.Structure):
     _fields_ = [(k, i32) for k in ("dim", "depth", "heads", "dim_head", "ff_mult", "mel_dim", "text_dim", "conv_layers",
-                                   "rope_heads", "text_mask_padding", "convpos_kernel", "convpos_groups", "vocab_rows")] + \
+                                   "rope_heads", "text_mask_padding", "convpos_kernel", "convpos_groups", "vocab_rows",
+                                   "precision")] + \
                [(k, vp) for k in ("time_w0", "time_b0", "time_w2", "time_b2", "mod_w", "mod_b", "text_table", "text_pos",
                                   "tb_dw_w", "tb_dw_b", "tb_ln_w", "tb_ln_b", "tb_pw1_w", "tb_pw1_b", "tb_grn_g", "tb_grn_b",
                                   "tb_pw2_w", "tb_pw2_b", "in_wx", "in_wct", "in_b", "cp_w1", "cp_b1", "cp_w2", "cp_b2",
@@ -135,6 +136,14 @@ SIGNATURES = {
     "f5b_prof_reset": (None, [C.c_int]),
     "f5b_prof_read": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5b_vocos_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "f5b_ln_modulate_tf32": (C.c_int, [vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_attn_fwd_tf32": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, vp]),
+    "f5b_attn_tf32_ws_floats": (sz, [C.c_int, C.c_int, C.c_int]),
+    "f5b_convpos_tf32": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_pack_convpos_weight_tf32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "f5b_convpos_packed_elems_tf32": (sz, [C.c_int, C.c_int, C.c_int]),
+    "f5b_time_sinus_tf32": (C.c_int, [vp, vp, C.c_int, vp]),
+    "f5b_pack_tf32": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
 }
 
 _lib = None

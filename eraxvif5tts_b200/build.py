@@ -19,7 +19,7 @@ LIBDIR = os.path.join(PKG, "lib")
 _TAG = os.environ.get("F5B_BUILD_TAG", "")
 OBJDIR = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(LIBDIR, "libf5b200" + ("_" + _TAG if _TAG else "") + ".so")
-UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
+UNITS = ["host", "gemm", "gemm_grad", "convpos", "attention", "attention_tf32", "attention_bwd", "elementwise", "spectral", "optim", "train_kernels", "train", "align", "models"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

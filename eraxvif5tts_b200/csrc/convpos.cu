@@ -18,16 +18,26 @@ __device__ __forceinline__ float mish(float x) {
   const float t = e * (e + 2.f);
   return x * __fdividef(t, t + 2.f);
 }
+__device__ __forceinline__ float mish_precise(float x) {  // tf32 operand mode: libm exp and an IEEE division
+  if (x > 20.f) return x;
+  const float e = expf(x);
+  const float t = e * (e + 2.f);
+  return x * (t / (t + 2.f));
+}
 
-template <int MODE>
+// TF32_ (the tf32 operand mode): x and the packed weights are fp32 words rounded to tf32, 32 channels per 128-byte stage row, so a
+// tap takes `kper` = ceil(cpg / 32) k-blocks (input-channel halves); the mode-0 / mode-2 output is fp32 rounded to tf32.
+template <int MODE, bool TF32_ = false>
 struct ConvPosProblem {
   static constexpr int BN = 64;
   static constexpr int STORE = STORE_DIRECT;
   static constexpr int CLUSTER = 1;
+  static constexpr bool TF32 = TF32_;
   int B, n, D, groups, cpg, NP, ksize, pad, n_tiles_seq;
   const float* bias;
-  __nv_bfloat16* out;
+  void* out;  // bf16, or fp32 in the tf32 mode
   float* resid;
+  int kper;   // k-blocks per tap (1 unless TF32 and cpg > 32)
 
   struct RowCtx {
     size_t row_off;  // (b*n + pos) * D + g*cpg
@@ -37,9 +47,9 @@ struct ConvPosProblem {
 
   __device__ __forceinline__ int num_units() const { return B * n_tiles_seq * groups; }
   __device__ __forceinline__ int unit_tile(int unit, uint32_t) const { return unit; }
-  __device__ __forceinline__ int num_kblocks() const { return ksize; }
+  __device__ __forceinline__ int num_kblocks() const { return ksize * kper; }
   __device__ __forceinline__ uint32_t umma_n() const { return NP; }
-  __device__ __forceinline__ uint32_t idesc() const { return idesc_bf16(BM, umma_n(), 0, 0); }
+  __device__ __forceinline__ uint32_t idesc() const { return TF32 ? idesc_tf32(BM, umma_n(), 0, 0) : idesc_bf16(BM, umma_n(), 0, 0); }
   __device__ __forceinline__ uint64_t a_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint64_t b_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return NP * 128; }
@@ -57,8 +67,14 @@ struct ConvPosProblem {
                                        const CUtensorMap* tmB, uint32_t) const {
     int b, nt, g;
     decode(tile, b, nt, g);
-    tma_load_3d(sA, tmA, bar, g * cpg, nt * BM + kb - pad, b);
-    tma_load_2d(sB, tmB, bar, 0, (g * ksize + kb) * NP);
+    if constexpr (TF32) {
+      const int tap = kb / kper, ch = kb - tap * kper;
+      tma_load_3d(sA, tmA, bar, g * cpg + ch * 32, nt * BM + tap - pad, b);
+      tma_load_2d(sB, tmB, bar, 0, ((g * ksize + tap) * kper + ch) * NP);
+    } else {
+      tma_load_3d(sA, tmA, bar, g * cpg, nt * BM + kb - pad, b);
+      tma_load_2d(sB, tmB, bar, 0, (g * ksize + kb) * NP);
+    }
   }
   __device__ __forceinline__ RowCtx row_ctx(int tile, int r) const {
     int b, nt, g;
@@ -79,10 +95,14 @@ struct ConvPosProblem {
       float bb = 0.f;
       if (bias != nullptr && i < left) bb = __ldg(bias + c.ch0 + c0 + i);
       const float t = __uint_as_float(r[i]) + bb;
-      v[i] = MODE == 2 ? t : mish(t);  // mode 2: pre-activation output (training forward / transposed conv of the backward)
+      v[i] = MODE == 2 ? t : (TF32 ? mish_precise(t) : mish(t));  // mode 2: pre-activation output (training forward / transposed conv of the backward)
     }
-    if constexpr (MODE == 0 || MODE == 2) {
-      store_row32_bf16(out + c.row_off + c0, v, left, ((D | cpg) & 7) == 0);
+    if constexpr ((MODE == 0 || MODE == 2) && TF32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
+      store_row32_f32(reinterpret_cast<float*>(out) + c.row_off + c0, v, left, ((D | cpg) & 3) == 0);
+    } else if constexpr (MODE == 0 || MODE == 2) {
+      store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(out) + c.row_off + c0, v, left, ((D | cpg) & 7) == 0);
     } else {
       float* o = resid + c.row_off + c0;
       if (left >= 32 && ((D | cpg) & 3) == 0) {
@@ -335,31 +355,95 @@ int convpos(const void* x, const void* wpk, const float* bias, void* out, float*
   const int total = B * nts * groups;
   if (halo) {
     if (mode == 0) {
-      ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+      ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
       return launch_halo(tmA, tmB, p, stream);
     }
     if (mode == 2) {
-      ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+      ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
       return launch_halo(tmA, tmB, p, stream);
     }
-    ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+    ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
     return launch_halo(tmA, tmB, p, stream);
   }
   if (mode == 0) {
-    ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+    ConvPosProblem<0> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
     return launch_engine(tmA, tmB, tmA, p, total, stream);
   }
   if (mode == 2) {
-    ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+    ConvPosProblem<2> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
     return launch_engine(tmA, tmB, tmA, p, total, stream);
   }
-  ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, reinterpret_cast<__nv_bfloat16*>(out), resid};
+  ConvPosProblem<1> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, 1};
+  return launch_engine(tmA, tmB, tmA, p, total, stream);
+}
+
+// ---- tf32 operand mode: per-tap loads on the generic engine, kind::tf32 (a precision mode, not a throughput one) -------------
+__global__ void pack_convpos_tf32_kernel(const float* __restrict__ w, float* __restrict__ wpk, int groups, int ksize, int cpg, int NP,
+                                         int kper) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)groups * ksize * kper * NP * 32;
+  if (i >= tot) return;
+  const int cl = (int)(i & 31);
+  int64_t t = i >> 5;
+  const int co = (int)(t % NP);
+  t /= NP;
+  const int ch = (int)(t % kper);
+  t /= kper;
+  const int k = (int)(t % ksize);
+  const int g = (int)(t / ksize);
+  const int ci = ch * 32 + cl;
+  float v = 0.f;
+  if (co < cpg && ci < cpg) v = w[((size_t)(g * cpg + co) * cpg + ci) * ksize + k];
+  wpk[i] = tf32_rn(v);
+}
+
+static inline int tf32_kper(int cpg) { return (cpg + 31) / 32; }
+
+int convpos_tf32(const float* x, const float* wpk, const float* bias, float* out, float* resid, int B, int n, int D, int groups, int ksize,
+                 int mode, cudaStream_t stream) {
+  F5B_CHECK(x && wpk && bias, "f5b_convpos_tf32: null pointer");
+  F5B_CHECK(B > 0 && n > 0 && D > 0 && groups > 0 && D % groups == 0 && (ksize & 1) == 1, "f5b_convpos_tf32: bad shape");
+  const int cpg = D / groups;
+  F5B_CHECK(cpg <= 64 && (D & 3) == 0, "f5b_convpos_tf32: channels per group %d must be <= 64 and D a multiple of 4", cpg);
+  F5B_CHECK((mode == 0 && out != nullptr) || (mode == 1 && resid != nullptr), "f5b_convpos_tf32: mode 0 needs out, mode 1 needs resid");
+  const int NP = round16(cpg), kper = tf32_kper(cpg);
+  LaunchScope scope(K_CONVPOS, stream, 2.0 * B * n * (double)D * cpg * ksize, (double)B * n * D * (mode != 1 ? 8.0 : 12.0));
+  CUtensorMap tmA, tmB;
+  if (make_tmap_3d(&tmA, x, 4, (uint64_t)D, (uint64_t)n, (uint64_t)B, (uint64_t)D * 4, (uint64_t)n * D * 4, 32, BM, 1, true)) return -1;
+  if (make_tmap_2d(&tmB, wpk, 4, 32, (uint64_t)groups * ksize * kper * NP, 128, 32, NP, true)) return -1;
+  const int nts = (n + BM - 1) / BM;
+  const int total = B * nts * groups;
+  if (mode == 0) {
+    ConvPosProblem<0, true> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, kper};
+    return launch_engine(tmA, tmB, tmA, p, total, stream);
+  }
+  ConvPosProblem<1, true> p{B, n, D, groups, cpg, NP, ksize, ksize / 2, nts, bias, out, resid, kper};
   return launch_engine(tmA, tmB, tmA, p, total, stream);
 }
 
 }  // namespace f5b
 
 extern "C" {
+
+int f5b_convpos_tf32(const float* x, const float* wpk, const float* bias, float* out, float* resid, int B, int n, int D, int groups,
+                     int ksize, int mode, f5b_stream_t stream) {
+  return f5b::convpos_tf32(x, wpk, bias, out, resid, B, n, D, groups, ksize, mode, static_cast<cudaStream_t>(stream));
+}
+size_t f5b_convpos_packed_elems_tf32(int D, int groups, int ksize) {
+  if (groups <= 0 || D % groups != 0) return 0;
+  const int cpg = D / groups;
+  return (size_t)groups * ksize * f5b::tf32_kper(cpg) * f5b::round16(cpg) * 32;
+}
+int f5b_pack_convpos_weight_tf32(const float* w, float* wpk, int D, int groups, int ksize, f5b_stream_t stream) {
+  using namespace f5b;
+  F5B_CHECK(w && wpk && groups > 0 && D % groups == 0 && D / groups <= 64, "f5b_pack_convpos_weight_tf32: bad shape");
+  const int cpg = D / groups, NP = round16(cpg), kper = tf32_kper(cpg);
+  const int64_t tot = (int64_t)groups * ksize * kper * NP * 32;
+  LaunchScope scope(K_ELEMENTWISE, static_cast<cudaStream_t>(stream), 0, 8.0 * tot);
+  pack_convpos_tf32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wpk, groups, ksize, cpg, NP, kper);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int f5b_convpos(const void* x, const void* wpk, const float* bias, void* out, float* resid, int B, int n, int D, int groups,
                 int ksize, int mode, f5b_stream_t stream) {

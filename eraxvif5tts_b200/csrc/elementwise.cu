@@ -7,14 +7,31 @@
 
 namespace f5b {
 
+// Activation outputs are bf16 (kind::f16 operands of the next GEMM) or, in the tf32 operand mode, fp32 words rounded to tf32.
+__device__ __forceinline__ void store4(__nv_bfloat16* o, int idx, float a, float b, float c, float d) {
+  reinterpret_cast<uint2*>(o)[idx] = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+}
+__device__ __forceinline__ void store4(float* o, int idx, float a, float b, float c, float d) {
+  reinterpret_cast<float4*>(o)[idx] = make_float4(tf32_rn(a), tf32_rn(b), tf32_rn(c), tf32_rn(d));
+}
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return make_float2(__low2float(v), __high2float(v));
+}
+__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(tf32_rn(a), tf32_rn(b)); }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float a) { *p = __float2bfloat16(a); }
+__device__ __forceinline__ void store1(float* p, float a) { *p = tf32_rn(a); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm (no affine, eps) * (1 + scale[b]) + shift[b] -> bf16      AdaLayerNorm.forward model/modules.py:310-315,
 // DiTBlock ff norm :637, AdaLayerNorm_Final :331-336.  One warp per row, row cached in registers (D <= 2048).
 // ---------------------------------------------------------------------------------------------------------------
-template <int VEC>  // float4 per lane
+template <int VEC, class OutT>  // float4 per lane
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int64_t mod_bstride,
-                                                          int batch_mod, __nv_bfloat16* __restrict__ out, int rows,
+                                                          int batch_mod, OutT* __restrict__ out, int rows,
                                                           int rows_per_batch, int D, float eps) {
   griddep_wait();  // PDL (common.cuh)
   griddep_launch_dependents();
@@ -46,7 +63,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   if (batch_mod > 0) b %= batch_mod;
   const float4* sc = scale ? reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride) : nullptr;
   const float4* sh = shift ? reinterpret_cast<const float4*>(shift + (size_t)b * mod_bstride) : nullptr;
-  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * D);
+  OutT* o = out + (size_t)row * D;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int idx = lane + j * 32;
@@ -57,36 +74,42 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
       const float bb = (v[j].y - mean) * rstd * (1.f + g.y) + h.y;
       const float c = (v[j].z - mean) * rstd * (1.f + g.z) + h.z;
       const float d = (v[j].w - mean) * rstd * (1.f + g.w) + h.w;
-      o[idx] = make_uint2(pack_bf16(a, bb), pack_bf16(c, d));
+      store4(o, idx, a, bb, c, d);
     }
   }
 }
 
+template <class OutT>
+static int ln_modulate_t(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, OutT* o, int rows,
+                         int rows_per_batch, int D, float eps, cudaStream_t s) {
+  const int grid = (rows + 7) / 8;
+  const int nvec = D / 4;
+  if (nvec <= 32 * 2) F5B_CUDA(launch_dep(ln_modulate_kernel<2, OutT>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else if (nvec <= 32 * 4) F5B_CUDA(launch_dep(ln_modulate_kernel<4, OutT>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else if (nvec <= 32 * 8) F5B_CUDA(launch_dep(ln_modulate_kernel<8, OutT>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  else F5B_CUDA(launch_dep(ln_modulate_kernel<16, OutT>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, void* out,
-                int rows, int rows_per_batch, int D, float eps, cudaStream_t s) {
+                int rows, int rows_per_batch, int D, float eps, cudaStream_t s, bool tf32) {
   F5B_CHECK(rows > 0 && D > 0 && (D & 3) == 0 && D <= 2048, "f5b_ln_modulate: D=%d must be a multiple of 4 and <= 2048", D);
   F5B_CHECK((mod_bstride & 3) == 0, "f5b_ln_modulate: modulation stride must be a multiple of 4");
   F5B_CHECK(rows_per_batch > 0, "f5b_ln_modulate: rows_per_batch");
-  const int grid = (rows + 7) / 8;
-  LaunchScope scope(K_NORM, s, 0, 6.0 * rows * D);
-  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
-  const int nvec = D / 4;
-  if (nvec <= 32 * 2) F5B_CUDA(launch_dep(ln_modulate_kernel<2>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
-  else if (nvec <= 32 * 4) F5B_CUDA(launch_dep(ln_modulate_kernel<4>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
-  else if (nvec <= 32 * 8) F5B_CUDA(launch_dep(ln_modulate_kernel<8>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
-  else F5B_CUDA(launch_dep(ln_modulate_kernel<16>, dim3(grid), dim3(256), 0, s, 1, x, scale, shift, mod_bstride, batch_mod, o, rows, rows_per_batch, D, eps));
-  F5B_CUDA(cudaGetLastError());
-  return 0;
+  LaunchScope scope(K_NORM, s, 0, (tf32 ? 8.0 : 6.0) * rows * D);
+  if (tf32) return ln_modulate_t(x, scale, shift, mod_bstride, batch_mod, reinterpret_cast<float*>(out), rows, rows_per_batch, D, eps, s);
+  return ln_modulate_t(x, scale, shift, mod_bstride, batch_mod, reinterpret_cast<__nv_bfloat16*>(out), rows, rows_per_batch, D, eps, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // depth-wise Conv1d(k=7, pad 3) + bias + LayerNorm(C, affine, eps) -> bf16    ConvNeXtV2Block model/modules.py:259-262
 // (and the identical Vocos ConvNeXtBlock front).  One warp per output row; the 7 neighbour rows come from L1/L2.
 // ---------------------------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, class OutT>
 __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
-                                                         const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                                                         const float* __restrict__ ln_b, OutT* __restrict__ out,
                                                          int B, int n, int C, float eps, float* __restrict__ y_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -133,40 +156,46 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
       q += a * a + bb * bb + c * c + d * d;
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+  OutT* o = out + (size_t)row * C;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int idx = lane + j * 32;
     if (idx < nvec) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w) + idx);
       const float4 h = __ldg(reinterpret_cast<const float4*>(ln_b) + idx);
-      o[idx] = make_uint2(pack_bf16((acc[j].x - mean) * rstd * g.x + h.x, (acc[j].y - mean) * rstd * g.y + h.y),
-                          pack_bf16((acc[j].z - mean) * rstd * g.z + h.z, (acc[j].w - mean) * rstd * g.w + h.w));
+      store4(o, idx, (acc[j].x - mean) * rstd * g.x + h.x, (acc[j].y - mean) * rstd * g.y + h.y,
+             (acc[j].z - mean) * rstd * g.z + h.z, (acc[j].w - mean) * rstd * g.w + h.w);
     }
   }
 }
 
-int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B, int n,
-               int C, float eps, cudaStream_t s, float* y_out) {
-  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 3) == 0 && C <= 1024, "f5b_dwconv7_ln: C=%d must be a multiple of 4 and <= 1024", C);
+template <class OutT>
+static int dwconv7_ln_t(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, OutT* o, int B, int n, int C,
+                        float eps, cudaStream_t s, float* y_out) {
   const int grid = (B * n + 7) / 8;
-  LaunchScope scope(K_NORM, s, 0, 6.0 * B * n * C);
-  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = C / 4;
-  if (nvec <= 32) dwconv7_ln_kernel<1><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
-  else if (nvec <= 64) dwconv7_ln_kernel<2><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
-  else if (nvec <= 128) dwconv7_ln_kernel<4><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
-  else dwconv7_ln_kernel<8><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  if (nvec <= 32) dwconv7_ln_kernel<1, OutT><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else if (nvec <= 64) dwconv7_ln_kernel<2, OutT><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else if (nvec <= 128) dwconv7_ln_kernel<4, OutT><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
+  else dwconv7_ln_kernel<8, OutT><<<grid, 256, 0, s>>>(x, w, b, ln_w, ln_b, o, B, n, C, eps, y_out);
   F5B_CUDA(cudaGetLastError());
   return 0;
+}
+
+int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B, int n,
+               int C, float eps, cudaStream_t s, float* y_out, bool tf32) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 3) == 0 && C <= 1024, "f5b_dwconv7_ln: C=%d must be a multiple of 4 and <= 1024", C);
+  LaunchScope scope(K_NORM, s, 0, (tf32 ? 8.0 : 6.0) * B * n * C);
+  if (tf32) return dwconv7_ln_t(x, w, b, ln_w, ln_b, reinterpret_cast<float*>(out), B, n, C, eps, s, y_out);
+  return dwconv7_ln_t(x, w, b, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out), B, n, C, eps, s, y_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // GRN  model/modules.py:225-234: Gx = ||h||_2 over the SEQUENCE axis, Nx = Gx / (mean_c Gx + 1e-6),
 // out = gamma * (h * Nx) + beta + h.   Pass 1: deterministic column norms; pass 2: apply.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grn_colnorm_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ gx, int n,
-                                                          int C) {
+template <class T>
+__global__ void __launch_bounds__(256) grn_colnorm_kernel(const T* __restrict__ h, float* __restrict__ gx, int n, int C) {
   // block: 64 channel pairs (128 channels) x 4 row lanes; grid (ceil(C/128), B)
   __shared__ float red[4][128];
   const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
@@ -174,12 +203,11 @@ __global__ void __launch_bounds__(256) grn_colnorm_kernel(const __nv_bfloat16* _
   const int b = blockIdx.y;
   float s0 = 0.f, s1 = 0.f;
   if (c < C) {
-    const __nv_bfloat16* base = h + (size_t)b * n * C + c;
+    const T* base = h + (size_t)b * n * C + c;
     for (int r = rl; r < n; r += 4) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (size_t)r * C);
-      const float a = __low2float(v), d = __high2float(v);
-      s0 += a * a;
-      s1 += d * d;
+      const float2 v = load2(base + (size_t)r * C);
+      s0 += v.x * v.x;
+      s1 += v.y * v.y;
     }
   }
   red[rl][cp * 2] = s0;
@@ -194,9 +222,10 @@ __global__ void __launch_bounds__(256) grn_colnorm_kernel(const __nv_bfloat16* _
   }
 }
 
-__global__ void __launch_bounds__(256) grn_apply_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gx,
+template <class T>
+__global__ void __launch_bounds__(256) grn_apply_kernel(const T* __restrict__ h, const float* __restrict__ gx,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        __nv_bfloat16* __restrict__ out, int n, int C, int rows_per_block) {
+                                                        T* __restrict__ out, int n, int C, int rows_per_block) {
   __shared__ float red[8];
   __shared__ float s_mean;
   const int b = blockIdx.y;
@@ -217,30 +246,34 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(const __nv_bfloat16* __r
   const int r1 = min(n, r0 + rows_per_block);
   const int pairs = C >> 1;
   for (int r = r0; r < r1; ++r) {
-    const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(h + ((size_t)b * n + r) * C);
-    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * n + r) * C);
+    const T* hr = h + ((size_t)b * n + r) * C;
+    T* o = out + ((size_t)b * n + r) * C;
     for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-      const __nv_bfloat162 v = hr[p];
-      const float a = __low2float(v), d = __high2float(v);
+      const float2 v = load2(hr + 2 * p);
+      const float a = v.x, d = v.y;
       const int c = p * 2;
       const float ya = __ldg(gamma + c) * (a * (g[c] * inv)) + __ldg(beta + c) + a;
       const float yd = __ldg(gamma + c + 1) * (d * (g[c + 1] * inv)) + __ldg(beta + c + 1) + d;
-      o[p] = __floats2bfloat162_rn(ya, yd);
+      store2(o + 2 * p, ya, yd);
     }
   }
 }
 
-int grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C, cudaStream_t s) {
-  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_grn: C=%d must be even", C);
-  auto* hh = reinterpret_cast<const __nv_bfloat16*>(h);
-  LaunchScope scope(K_ELEMENTWISE, s, 0, 6.0 * B * n * C, 2);
-  grn_colnorm_kernel<<<dim3((C + 127) / 128, B), 256, 0, s>>>(hh, ws, n, C);
+template <class T>
+static int grn_t(const T* h, const float* gamma, const float* beta, T* out, float* ws, int B, int n, int C, cudaStream_t s) {
+  grn_colnorm_kernel<T><<<dim3((C + 127) / 128, B), 256, 0, s>>>(h, ws, n, C);
   F5B_CUDA(cudaGetLastError());
   const int rpb = 8;
-  grn_apply_kernel<<<dim3((n + rpb - 1) / rpb, B), 256, 0, s>>>(hh, ws, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), n, C,
-                                                                rpb);
+  grn_apply_kernel<T><<<dim3((n + rpb - 1) / rpb, B), 256, 0, s>>>(h, ws, gamma, beta, out, n, C, rpb);
   F5B_CUDA(cudaGetLastError());
   return 0;
+}
+
+int grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C, cudaStream_t s, bool tf32) {
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_grn: C=%d must be even", C);
+  LaunchScope scope(K_ELEMENTWISE, s, 0, (tf32 ? 12.0 : 6.0) * B * n * C, 2);
+  if (tf32) return grn_t(reinterpret_cast<const float*>(h), gamma, beta, reinterpret_cast<float*>(out), ws, B, n, C, s);
+  return grn_t(reinterpret_cast<const __nv_bfloat16*>(h), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), ws, B, n, C, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -273,13 +306,14 @@ __global__ void mask_rows_kernel(float* __restrict__ x, const uint8_t* __restric
 // ---------------------------------------------------------------------------------------------------------------
 // SinusPositionEmbedding(256), model/modules.py:149-161: emb = 1000 * t * exp(-ln(1e4)/(128-1) * k); cat(sin, cos)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void time_sinus_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int M) {
+template <class OutT>
+__global__ void time_sinus_kernel(const float* __restrict__ t, OutT* __restrict__ out, int M) {
   const int m = blockIdx.x;
   const int k = threadIdx.x;  // 0..127
   const float f = expf((float)k * -(9.210340371976184f / 127.0f));
   const float a = 1000.0f * t[m] * f;
-  out[(size_t)m * 256 + k] = __float2bfloat16(sinf(a));
-  out[(size_t)m * 256 + 128 + k] = __float2bfloat16(cosf(a));
+  store1(out + (size_t)m * 256 + k, sinf(a));
+  store1(out + (size_t)m * 256 + 128 + k, cosf(a));
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
@@ -290,12 +324,13 @@ __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
   }
 }
 
-__global__ void pack_bf16_kernel(const float* __restrict__ x, int ld_in, __nv_bfloat16* __restrict__ out, int ld_out, int rows,
-                                 int cols, int width) {
+template <class OutT>
+__global__ void pack_bf16_kernel(const float* __restrict__ x, int ld_in, OutT* __restrict__ out, int ld_out, int rows, int cols,
+                                 int width) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * width) return;
   const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
-  out[(size_t)r * ld_out + c] = __float2bfloat16(c < cols ? x[(size_t)r * ld_in + c] : 0.f);
+  store1(out + (size_t)r * ld_out + c, c < cols ? x[(size_t)r * ld_in + c] : 0.f);
 }
 
 // LayerNorm(D, affine, eps) with f32 and/or bf16 output (Vocos backbone.norm / final_layer_norm); one warp per row
@@ -506,6 +541,11 @@ int f5b_ln_modulate(const float* x, const float* scale, const float* shift, int6
   return ln_modulate(x, scale, shift, mod_bstride, batch_mod, out, rows, rows_per_batch, D, eps, ST(stream));
 }
 
+int f5b_ln_modulate_tf32(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, float* out,
+                         int rows, int rows_per_batch, int D, float eps, f5b_stream_t stream) {
+  return ln_modulate(x, scale, shift, mod_bstride, batch_mod, out, rows, rows_per_batch, D, eps, ST(stream), true);
+}
+
 int f5b_dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out, int B,
                    int n, int C, float eps, f5b_stream_t stream) {
   return dwconv7_ln(x, w, b, ln_w, ln_b, out, B, n, C, eps, ST(stream));
@@ -539,6 +579,13 @@ int f5b_time_sinus(const float* t, void* out, int M, f5b_stream_t stream) {
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
+int f5b_time_sinus_tf32(const float* t, float* out, int M, f5b_stream_t stream) {
+  F5B_CHECK(M > 0, "f5b_time_sinus_tf32: M");
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 1028.0 * M);
+  time_sinus_kernel<<<M, 128, 0, ST(stream)>>>(t, out, M);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int f5b_silu_bf16(const float* x, void* out, int64_t n, f5b_stream_t stream) {
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * n);
@@ -558,6 +605,14 @@ int f5b_pack_bf16(const float* x, int ld_in, void* out, int ld_out, int rows, in
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * rows * cols + 2.0 * tot);
   pack_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out,
                                                                           rows, cols, width);
+  F5B_CUDA(cudaGetLastError());
+  return 0;
+}
+int f5b_pack_tf32(const float* x, int ld_in, float* out, int ld_out, int rows, int cols, int width, f5b_stream_t stream) {
+  F5B_CHECK(rows > 0 && cols >= 0 && cols <= width && width <= ld_out && (x != nullptr || cols == 0), "f5b_pack_tf32: bad shape");
+  const int64_t tot = (int64_t)rows * width;
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 4.0 * rows * cols + 4.0 * tot);
+  pack_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ST(stream)>>>(x, ld_in, out, ld_out, rows, cols, width);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

@@ -10,25 +10,32 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
 
 // convenience wrappers used by the model drivers
 int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
-                int act, cudaStream_t s);
+                int act, cudaStream_t s, bool tf32 = false);
 int linear_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
-               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s);
+               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s, bool tf32 = false);
 int linear_gate_resid(const void* A, int lda, const void* W, int ldw, const float* bias, float* x, int ldc, int M, int N,
                       int K, int rows_per_batch, const float* gate, int64_t gate_bstride, const int32_t* lens,
-                      int batch_mod, cudaStream_t s);
+                      int batch_mod, cudaStream_t s, bool tf32 = false);
 
+// (tf32 = true in the sweeps below: the activation output is fp32 rounded to tf32 instead of bf16 — the tf32 operand mode)
 int ln_modulate(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, void* out_bf16,
-                int rows, int rows_per_batch, int D, float eps, cudaStream_t s);
+                int rows, int rows_per_batch, int D, float eps, cudaStream_t s, bool tf32 = false);
 int ln_affine(const float* x, const float* w, const float* b, float* out_f32, void* out_bf16, int rows, int D, float eps,
               cudaStream_t s);
 int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* out_bf16, int B, int n,
-               int C, float eps, cudaStream_t s, float* y_out = nullptr);
-int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s);
+               int C, float eps, cudaStream_t s, float* y_out = nullptr, bool tf32 = false);
+int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s,
+        bool tf32 = false);
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
              int n, float scale, cudaStream_t stream);
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
              const float* rope, int rope_heads, cudaStream_t stream);
+int attn_fwd_tf32(const float* q, const float* k, const float* v, int ld, float* out, float* vt_ws, const int32_t* lens, int lens_mod,
+                  int B, int H, int n, float scale, cudaStream_t stream);
+size_t attn_tf32_ws_floats(int B, int H, int n);
+int convpos_tf32(const float* x, const float* wpk, const float* bias, float* out, float* resid, int B, int n, int D, int groups, int ksize,
+                 int mode, cudaStream_t stream);
 int convpos(const void* x, const void* wpk, const float* bias, void* out, float* resid, int B, int n, int D, int groups,
             int ksize, int mode, cudaStream_t stream);
 

@@ -11,9 +11,15 @@
 
 namespace f5b {
 
-template <int ACT>
+template <int ACT, bool PRECISE = false>
 __device__ __forceinline__ float activate(float x) {
-  if constexpr (ACT == F5B_ACT_GELU_TANH) {
+  if constexpr (ACT == F5B_ACT_GELU_TANH && PRECISE) {
+    // the tf32 operand mode targets 1e-3 of the fp32 reference: libm tanh instead of the 2^-11 SFU approximation
+    const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+    return 0.5f * x * (1.0f + tanhf(u));
+  } else if constexpr (ACT == F5B_ACT_SILU && PRECISE) {
+    return x / (1.0f + expf(-x));
+  } else if constexpr (ACT == F5B_ACT_GELU_TANH) {
     // nn.GELU(approximate="tanh"), model/modules.py:625; tanh on the SFU (tanh.approx, rel. error ~2^-11 << bf16 output)
     const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
     return 0.5f * x * (1.0f + tanh_approx(u));
@@ -26,10 +32,16 @@ __device__ __forceinline__ float activate(float x) {
   }
 }
 
-template <int BN_, int EPI, int ACT>
+// TF32_: the tf32 operand mode (F5bGemmArgs.tf32): A and W are fp32 words (rounded to tf32 by their producers), 32 per 128-byte
+// stage row, kind::tf32 MMAs; the BF16 / QKV_ROPE epilogues then write fp32 (rounded to tf32: they feed the next tensor-core
+// operand) through STORE_F32, and the F32 epilogue's optional second output is an fp32 tf32-rounded copy.
+template <int BN_, int EPI, int ACT, bool TF32_ = false>
 struct LinearProblem {
   static constexpr int BN = BN_;
-  static constexpr int STORE = (EPI == F5B_EPI_BF16 || EPI == F5B_EPI_QKV_ROPE) ? STORE_BF16 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
+  static constexpr bool TF32 = TF32_;
+  static constexpr int BKE = TF32_ ? 32 : 64;  // elements per k-block (128 bytes)
+  static constexpr int STORE = (EPI == F5B_EPI_BF16 || EPI == F5B_EPI_QKV_ROPE) ? (TF32_ ? STORE_F32 : STORE_BF16)
+                                                                                 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
   static constexpr int CLUSTER = 2;  // CTA pairs on vertically adjacent tiles share the weight tile through TMA multicast
   F5bGemmArgs g;
   int n_tiles, m_tiles, kblocks;
@@ -48,8 +60,10 @@ struct LinearProblem {
   }
   __device__ __forceinline__ int num_kblocks() const { return kblocks; }
   __device__ __forceinline__ uint32_t umma_n() const { return BN; }
-  __device__ __forceinline__ uint32_t idesc() const { return idesc_bf16(BM, umma_n(), 0, 0); }
-  __device__ __forceinline__ uint32_t idesc2() const { return idesc_bf16(2 * BM, umma_n(), 0, 0); }  // CTA pair: 256 rows
+  __device__ __forceinline__ uint32_t idesc() const { return TF32 ? idesc_tf32(BM, umma_n(), 0, 0) : idesc_bf16(BM, umma_n(), 0, 0); }
+  __device__ __forceinline__ uint32_t idesc2() const {  // CTA pair: 256 rows
+    return TF32 ? idesc_tf32(2 * BM, umma_n(), 0, 0) : idesc_bf16(2 * BM, umma_n(), 0, 0);
+  }
   __device__ __forceinline__ uint64_t a_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint64_t b_desc(uint32_t addr, int k) const { return desc_kmajor(addr, k); }
   __device__ __forceinline__ uint32_t b_tx_bytes() const { return EngCfg<BN>::B_BYTES; }
@@ -62,16 +76,16 @@ struct LinearProblem {
   __device__ __forceinline__ void load(int tile, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar, const CUtensorMap* tmA,
                                        const CUtensorMap* tmB, uint32_t rank) const {
     const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-    tma_load_2d(sA, tmA, bar, kb * BK, m_blk * BM);
+    tma_load_2d(sA, tmA, bar, kb * BKE, m_blk * BM);
     // this CTA fetches rows [rank*BN/2, +BN/2) of the weight tile and multicasts them to both CTAs of the pair
-    tma_load_2d_mcast(sB + rank * (EngCfg<BN>::B_BYTES / 2), tmB, bar, kb * BK, n_blk * BN + (int)rank * (BN / 2), (uint16_t)0x3);
+    tma_load_2d_mcast(sB + rank * (EngCfg<BN>::B_BYTES / 2), tmB, bar, kb * BKE, n_blk * BN + (int)rank * (BN / 2), (uint16_t)0x3);
   }
   // CTA-pair mode: this CTA stages its own A rows and rows [rank*BN/2, +BN/2) of the weight tile; both complete on the leader's barrier
   __device__ __forceinline__ void load2(int tile, int kb, uint8_t* sA, uint8_t* sB, uint32_t leader_bar, const CUtensorMap* tmA,
                                         const CUtensorMap* tmB, uint32_t rank) const {
     const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-    tma_load_2d_2sm(sA, tmA, leader_bar, kb * BK, m_blk * BM);
-    tma_load_2d_2sm(sB, tmB, leader_bar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+    tma_load_2d_2sm(sA, tmA, leader_bar, kb * BKE, m_blk * BM);
+    tma_load_2d_2sm(sB, tmB, leader_bar, kb * BKE, n_blk * BN + (int)rank * (BN / 2));
   }
   __device__ __forceinline__ RowCtx row_ctx(int tile, int r) const {
     RowCtx c;
@@ -118,7 +132,7 @@ struct LinearProblem {
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(__uint_as_float(r[i]) + b[i]);
+      for (int i = 0; i < 32; ++i) v[i] = activate<ACT, TF32>(__uint_as_float(r[i]) + b[i]);
       if constexpr (EPI == F5B_EPI_QKV_ROPE) {
         // x_transformers.apply_rotary_pos_emb on the first rope_heads heads of q and k (model/modules.py:470-480): interleaved
         // pairs (2i, 2i+1), angle pos * 10000^(-2i/64), fp32 math.  Output stays token-major [rows, 3D] (q | k | v); the
@@ -139,6 +153,10 @@ struct LinearProblem {
           }
         }
       }
+      if constexpr (TF32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
+      }
     }
   }
 
@@ -152,7 +170,7 @@ struct LinearProblem {
       float b[32];
       load_bias32(g.bias, n0, left, b);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(__uint_as_float(r[i]) + b[i]);
+      for (int i = 0; i < 32; ++i) v[i] = activate<ACT, TF32>(__uint_as_float(r[i]) + b[i]);
     }
     if constexpr (EPI == F5B_EPI_F32) {
       if (g.addsrc != nullptr) {
@@ -172,8 +190,14 @@ struct LinearProblem {
       float* o = reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + n0;
       store_row32_f32(o, v, left, (g.ldc & 3) == 0);
       if (g.out2 != nullptr) {
-        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + (size_t)c.row * g.ldc2 + n0;
-        store_row32_bf16(o2, v, left, (g.ldc2 & 7) == 0);
+        if constexpr (TF32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
+          store_row32_f32(reinterpret_cast<float*>(g.out2) + (size_t)c.row * g.ldc2 + n0, v, left, (g.ldc2 & 3) == 0);
+        } else {
+          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(g.out2) + (size_t)c.row * g.ldc2 + n0;
+          store_row32_bf16(o2, v, left, (g.ldc2 & 7) == 0);
+        }
       }
     }
   }
@@ -181,19 +205,19 @@ struct LinearProblem {
 
 int g_gemm_pair_mode = 1;  // 1 (default): 256-wide tiles run as tcgen05 CTA pairs (cta_group::2); 0: two cta_group::1 tiles + weight multicast
 
-template <int BN, int EPI, int ACT>
+template <int BN, int EPI, int ACT, bool TF32>
 static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F5bGemmArgs& g, cudaStream_t stream) {
-  using P = LinearProblem<BN, EPI, ACT>;
+  using P = LinearProblem<BN, EPI, ACT, TF32>;
   P p;
   p.g = g;
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.N + BN - 1) / BN;
-  p.kblocks = (g.K + BK - 1) / BK;
+  p.kblocks = (g.K + P::BKE - 1) / P::BKE;
   CUtensorMap tmC = tmA;
   if constexpr (P::STORE == STORE_BF16) {
     F5B_CHECK((g.ldc & 7) == 0, "f5b_gemm: bf16 output pitch %d must be a multiple of 8", g.ldc);
     if (make_tmap_2d(&tmC, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, 32, true)) return -1;
-  } else if constexpr (P::STORE == STORE_F32ADD) {
+  } else if constexpr (P::STORE == STORE_F32ADD || P::STORE == STORE_F32) {
     F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
     if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
   }
@@ -203,10 +227,10 @@ static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
   return launch_engine(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
 }
 
-template <int BN>
+template <int BN, bool TF32>
 static int dispatch(const CUtensorMap& a, const CUtensorMap& b, const F5bGemmArgs& g, cudaStream_t s) {
 #define F5B_CASE(E, A) \
-  if (g.epi == E && g.act == A) return launch_linear<BN, E, A>(a, b, g, s);
+  if (g.epi == E && g.act == A) return launch_linear<BN, E, A, TF32>(a, b, g, s);
   F5B_CASE(F5B_EPI_BF16, F5B_ACT_NONE)
   F5B_CASE(F5B_EPI_BF16, F5B_ACT_GELU_TANH)
   F5B_CASE(F5B_EPI_BF16, F5B_ACT_GELU_ERF)
@@ -223,8 +247,10 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   F5B_CHECK(A != nullptr && W != nullptr, "f5b_gemm: null operand");
   F5B_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "f5b_gemm: empty problem %d x %d x %d", g.M, g.N, g.K);
   F5B_CHECK(g.out != nullptr, "f5b_gemm: null output");
-  F5B_CHECK(lda >= g.K && ldw >= g.K && (lda & 7) == 0 && (ldw & 7) == 0,
-            "f5b_gemm: row pitches must be >= K and multiples of 8 elements (lda %d ldw %d K %d)", lda, ldw, g.K);
+  const bool tf32 = g.tf32 != 0;
+  const int pitch_mask = tf32 ? 3 : 7;  // 16-byte rows for TMA
+  F5B_CHECK(lda >= g.K && ldw >= g.K && (lda & pitch_mask) == 0 && (ldw & pitch_mask) == 0,
+            "f5b_gemm: row pitches must be >= K and multiples of %d elements (lda %d ldw %d K %d)", pitch_mask + 1, lda, ldw, g.K);
   if (g.epi == F5B_EPI_QKV_ROPE) {
     F5B_CHECK(g.rope && g.rows_per_batch > 0 && g.heads > 0 && g.N == 3 * g.heads * 64 && g.M % g.rows_per_batch == 0,
               "f5b_gemm: bad QKV_ROPE arguments (N %d heads %d n %d)", g.N, g.heads, g.rows_per_batch);
@@ -233,8 +259,9 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
     F5B_CHECK(g.rows_per_batch > 0 && (g.gate_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.gate) & 15) == 0,
               "f5b_gemm: GATE_RESID needs rows_per_batch > 0 and a 16-byte aligned gate with a stride that is a multiple of 4");
   if (g.bias != nullptr) F5B_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "f5b_gemm: bias must be 16-byte aligned");
-  const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? 2.0 : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
-  LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
+  const double esz = tf32 ? 4.0 : 2.0;
+  const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? esz : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
+  LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, esz * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
   const int m_tiles = (g.M + BM - 1) / BM;
   // 256-wide tiles (CTA pairs) once they fill about two thirds of the machine; below that 128-wide tiles give twice the units to
   // spread.  Measured on the B = 1 shapes (M = 1880): threshold 148 tiles 75.4 ms per utterance, 98 -> 72.8 ms (FF1, 120 tiles, moves to
@@ -245,9 +272,14 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   }();
   const int bn = (g.N % 256 == 0 && m_tiles * (g.N / 256) >= min_tiles256) ? 256 : 128;
   CUtensorMap tmA, tmB;
+  if (tf32) {
+    if (make_tmap_2d(&tmA, A, 4, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda * 4, 32, BM, true)) return -1;
+    if (make_tmap_2d(&tmB, W, 4, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 4, 32, bn / 2, true)) return -1;
+    return bn == 256 ? dispatch<256, true>(tmA, tmB, g, stream) : dispatch<128, true>(tmA, tmB, g, stream);
+  }
   if (make_tmap_2d(&tmA, A, 2, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda * 2, BK, BM, true)) return -1;
   if (make_tmap_2d(&tmB, W, 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldw * 2, BK, bn / 2, true)) return -1;  // half tile per CTA
-  return bn == 256 ? dispatch<256>(tmA, tmB, g, stream) : dispatch<128>(tmA, tmB, g, stream);
+  return bn == 256 ? dispatch<256, false>(tmA, tmB, g, stream) : dispatch<128, false>(tmA, tmB, g, stream);
 }
 
 static F5bGemmArgs base_args(int M, int N, int K, int epi, int act, const float* bias, void* out, int ldc) {
@@ -258,23 +290,26 @@ static F5bGemmArgs base_args(int M, int N, int K, int epi, int act, const float*
 }
 
 int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
-                int act, cudaStream_t s) {
+                int act, cudaStream_t s, bool tf32) {
   F5bGemmArgs g = base_args(M, N, K, F5B_EPI_BF16, act, bias, out, ldc);
+  g.tf32 = tf32;
   return gemm(A, lda, W, ldw, g, s);
 }
 
 int linear_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
-               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s) {
+               int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s, bool tf32) {
   F5bGemmArgs g = base_args(M, N, K, F5B_EPI_F32, act, bias, out, ldc);
   g.addsrc = addsrc; g.ld_add = ld_add; g.out2 = out_bf16; g.ldc2 = ld_bf16;
+  g.tf32 = tf32;
   return gemm(A, lda, W, ldw, g, s);
 }
 
 int linear_gate_resid(const void* A, int lda, const void* W, int ldw, const float* bias, float* x, int ldc, int M, int N,
                       int K, int rows_per_batch, const float* gate, int64_t gate_bstride, const int32_t* lens,
-                      int batch_mod, cudaStream_t s) {
+                      int batch_mod, cudaStream_t s, bool tf32) {
   F5bGemmArgs g = base_args(M, N, K, F5B_EPI_GATE_RESID, F5B_ACT_NONE, bias, x, ldc);
   g.rows_per_batch = rows_per_batch; g.gate = gate; g.gate_bstride = gate_bstride; g.lens = lens; g.batch_mod = batch_mod;
+  g.tf32 = tf32;
   return gemm(A, lda, W, ldw, g, s);
 }
 

@@ -24,6 +24,7 @@ struct GradProblem {
   static constexpr int BN = BN_;
   static constexpr int STORE = STORE_;   // STORE_BF16 or STORE_F32ADD
   static constexpr int CLUSTER = PAIR ? 2 : 1;
+  static constexpr bool TF32 = false;
   GradArgs g;
 
   struct RowCtx {

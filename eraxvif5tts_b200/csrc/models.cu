@@ -30,22 +30,34 @@ struct Carver {
   }
 };
 
+// activation buffers between the kernels: bf16, or fp32 words (rounded to tf32) in the tf32 operand mode (F5bDitDesc.precision 1)
 struct DitWs {
   float* x;
-  __nv_bfloat16 *hb, *qkv, *ab, *fb;
+  uint8_t *hb, *qkv, *ab, *fb;
+  float* vt;
   size_t bytes;
 };
+
+static inline bool is_tf32(const F5bDitDesc& d) { return d.precision == 1; }
+static inline size_t act_bytes(const F5bDitDesc& d) { return is_tf32(d) ? 4 : 2; }
+// element `elems` of a weight array stored in the mode's operand type
+static inline const void* wat(const F5bDitDesc& d, const void* base, size_t elems) {
+  return reinterpret_cast<const uint8_t*>(base) + elems * act_bytes(d);
+}
+static inline uint8_t* aat(const F5bDitDesc& d, uint8_t* base, size_t elems) { return base + elems * act_bytes(d); }
 
 static DitWs carve_dit(const F5bDitDesc& d, int B, int n, void* ws) {
   const size_t rows = (size_t)B * n;
   const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads;
+  const size_t es = act_bytes(d);
   Carver c(ws);
   DitWs w;
   w.x = c.take<float>(rows * D);
-  w.hb = c.take<__nv_bfloat16>(rows * D);
-  w.qkv = c.take<__nv_bfloat16>(rows * (size_t)H * 64 * 3);  // token-major [rows, 3D]: q | k | v
-  w.ab = c.take<__nv_bfloat16>(rows * D);
-  w.fb = c.take<__nv_bfloat16>(rows * F);
+  w.hb = c.take<uint8_t>(rows * D * es);
+  w.qkv = c.take<uint8_t>(rows * (size_t)H * 64 * 3 * es);  // token-major [rows, 3D]: q | k | v
+  w.ab = c.take<uint8_t>(rows * D * es);
+  w.fb = c.take<uint8_t>(rows * F * es);
+  w.vt = is_tf32(d) ? c.take<float>(attn_tf32_ws_floats(B, H, n)) : nullptr;  // V^T of the tf32 attention
   w.bytes = c.off;
   return w;
 }
@@ -72,6 +84,7 @@ int f5b_dit_create(const F5bDitDesc* desc, F5bDit** out) {
   F5B_CHECK(d.dim_head == 64, "f5b_dit_create: dim_head must be 64 (got %d)", d.dim_head);
   F5B_CHECK(d.heads * d.dim_head == d.dim, "f5b_dit_create: heads*dim_head (%d) must equal dim (%d)", d.heads * d.dim_head, d.dim);
   F5B_CHECK(d.dim % 8 == 0 && d.text_dim % 8 == 0, "f5b_dit_create: dim and text_dim must be multiples of 8");
+  F5B_CHECK(d.precision == 0 || d.precision == 1, "f5b_dit_create: precision must be 0 (bf16 operands) or 1 (tf32 operands)");
   F5B_CHECK(d.mel_dim > 0 && d.mel_dim <= 128, "f5b_dit_create: mel_dim must be <= 128");
   F5B_CHECK(d.convpos_groups > 0 && d.dim % d.convpos_groups == 0 && d.dim / d.convpos_groups <= 64,
             "f5b_dit_create: conv_pos_embed needs <= 64 channels per group");
@@ -99,29 +112,34 @@ int f5b_dit_modulation(const F5bDit* h, const float* t, int M, float* mod, void*
   const F5bDitDesc& d = h->d;
   const int D = d.dim;
   const int mod_dim = d.depth * 6 * D + 2 * D;
+  const bool tp = is_tf32(d);
+  const size_t es = act_bytes(d);
   Carver c(ws);
-  __nv_bfloat16* sin_bf = c.take<__nv_bfloat16>((size_t)M * 256);
-  __nv_bfloat16* h1 = c.take<__nv_bfloat16>((size_t)M * D);
-  __nv_bfloat16* h2 = c.take<__nv_bfloat16>((size_t)M * D);
+  uint8_t* sin_bf = c.take<uint8_t>((size_t)M * 256 * es);
+  uint8_t* h1 = c.take<uint8_t>((size_t)M * D * es);
+  uint8_t* h2 = c.take<uint8_t>((size_t)M * D * es);
   cudaStream_t s = ST(stream);
-  F5B_TRY(f5b_time_sinus(t, sin_bf, M, stream));
-  F5B_TRY(linear_bf16(sin_bf, 256, d.time_w0, 256, d.time_b0, h1, D, M, D, 256, F5B_ACT_SILU, s));
+  if (tp) F5B_TRY(f5b_time_sinus_tf32(t, reinterpret_cast<float*>(sin_bf), M, stream));
+  else F5B_TRY(f5b_time_sinus(t, sin_bf, M, stream));
+  F5B_TRY(linear_bf16(sin_bf, 256, d.time_w0, 256, d.time_b0, h1, D, M, D, 256, F5B_ACT_SILU, s, tp));
   // every consumer of the time embedding applies SiLU first (AdaLayerNorm.silu), so it is fused here
-  F5B_TRY(linear_bf16(h1, D, d.time_w2, D, d.time_b2, h2, D, M, D, D, F5B_ACT_SILU, s));
-  F5B_TRY(linear_f32(h2, D, d.mod_w, D, d.mod_b, mod, mod_dim, M, mod_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  F5B_TRY(linear_bf16(h1, D, d.time_w2, D, d.time_b2, h2, D, M, D, D, F5B_ACT_SILU, s, tp));
+  F5B_TRY(linear_f32(h2, D, d.mod_w, D, d.mod_b, mod, mod_dim, M, mod_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s, tp));
   return 0;
 }
 
 size_t f5b_dit_modulation_ws_bytes(const F5bDit* h, int M) {
   if (!h || M <= 0) return 0;
-  return align_up((size_t)M * 256 * 2) + 2 * align_up((size_t)M * h->d.dim * 2);
+  const size_t es = act_bytes(h->d);
+  return align_up((size_t)M * 256 * es) + 2 * align_up((size_t)M * h->d.dim * es);
 }
 
 size_t f5b_dit_text_ws_bytes(const F5bDit* h, int B, int n) {
   if (!h || B <= 0 || n <= 0) return 0;
   const size_t rows = (size_t)B * n;
   const int T = h->d.text_dim;
-  return align_up(rows * T * 2) + 2 * align_up(rows * 2 * T * 2) + align_up((size_t)B * 2 * T * 4) + align_up(rows);
+  const size_t es = act_bytes(h->d);
+  return align_up(rows * T * es) + 2 * align_up(rows * 2 * T * es) + align_up((size_t)B * 2 * T * 4) + align_up(rows);
 }
 
 // TextEmbedding.forward, model/backbones/dit.py:49-79 with ConvNeXtV2Block model/modules.py:241-269
@@ -131,10 +149,12 @@ int f5b_dit_text_embed(const F5bDit* h, const int64_t* ids, int nt, int B, int n
   const F5bDitDesc& d = h->d;
   const int T = d.text_dim, T2 = 2 * d.text_dim;
   const size_t rows = (size_t)B * n;
+  const bool tp = is_tf32(d);
+  const size_t es = act_bytes(d);
   Carver c(ws);
-  __nv_bfloat16* tb = c.take<__nv_bfloat16>(rows * T);
-  __nv_bfloat16* t2 = c.take<__nv_bfloat16>(rows * T2);
-  __nv_bfloat16* t3 = c.take<__nv_bfloat16>(rows * T2);
+  uint8_t* tb = c.take<uint8_t>(rows * T * es);
+  uint8_t* t2 = c.take<uint8_t>(rows * T2 * es);
+  uint8_t* t3 = c.take<uint8_t>(rows * T2 * es);
   float* gx = c.take<float>((size_t)B * T2);
   uint8_t* mask = c.take<uint8_t>(rows);
   cudaStream_t s = ST(stream);
@@ -144,12 +164,12 @@ int f5b_dit_text_embed(const F5bDit* h, const int64_t* ids, int nt, int B, int n
   if (mp) F5B_TRY(f5b_mask_rows_f32(out, mask, (int)rows, T, stream));
   for (int j = 0; j < d.conv_layers; ++j) {
     F5B_TRY(dwconv7_ln(out, d.tb_dw_w + (size_t)j * T * 7, d.tb_dw_b + (size_t)j * T, d.tb_ln_w + (size_t)j * T,
-                       d.tb_ln_b + (size_t)j * T, tb, B, n, T, 1e-6f, s));
-    F5B_TRY(linear_bf16(tb, T, reinterpret_cast<const __nv_bfloat16*>(d.tb_pw1_w) + (size_t)j * T2 * T, T, d.tb_pw1_b + (size_t)j * T2,
-                        t2, T2, (int)rows, T2, T, F5B_ACT_GELU_ERF, s));
-    F5B_TRY(grn(t2, d.tb_grn_g + (size_t)j * T2, d.tb_grn_b + (size_t)j * T2, t3, gx, B, n, T2, s));
-    F5B_TRY(linear_gate_resid(t3, T2, reinterpret_cast<const __nv_bfloat16*>(d.tb_pw2_w) + (size_t)j * T * T2, T2,
-                              d.tb_pw2_b + (size_t)j * T, out, T, (int)rows, T, T2, n, nullptr, 0, nullptr, 0, s));
+                       d.tb_ln_b + (size_t)j * T, tb, B, n, T, 1e-6f, s, nullptr, tp));
+    F5B_TRY(linear_bf16(tb, T, wat(d, d.tb_pw1_w, (size_t)j * T2 * T), T, d.tb_pw1_b + (size_t)j * T2, t2, T2, (int)rows, T2, T,
+                        F5B_ACT_GELU_ERF, s, tp));
+    F5B_TRY(grn(t2, d.tb_grn_g + (size_t)j * T2, d.tb_grn_b + (size_t)j * T2, t3, gx, B, n, T2, s, tp));
+    F5B_TRY(linear_gate_resid(t3, T2, wat(d, d.tb_pw2_w, (size_t)j * T * T2), T2, d.tb_pw2_b + (size_t)j * T, out, T, (int)rows, T, T2,
+                              n, nullptr, 0, nullptr, 0, s, tp));
     if (mp) F5B_TRY(f5b_mask_rows_f32(out, mask, (int)rows, T, stream));
   }
   return 0;
@@ -162,6 +182,13 @@ int f5b_dit_input_const(const F5bDit* h, const float* cond, const float* text_em
   const F5bDitDesc& d = h->d;
   const int T = d.text_dim, K = 128 + T;
   const int rows = B * n;
+  if (is_tf32(d)) {  // ws: rows * (128 + T) fp32
+    float* a = reinterpret_cast<float*>(ws);
+    F5B_TRY(f5b_pack_tf32(cond, d.mel_dim, a, K, rows, cond ? d.mel_dim : 0, 128, stream));
+    F5B_TRY(f5b_pack_tf32(text_embed, T, a + 128, K, rows, T, T, stream));
+    F5B_TRY(linear_f32(a, K, d.in_wct, K, d.in_b, c0, d.dim, rows, d.dim, K, F5B_ACT_NONE, nullptr, 0, nullptr, 0, ST(stream), true));
+    return 0;
+  }
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ws);
   F5B_TRY(f5b_pack_bf16(cond, d.mel_dim, a, K, rows, cond ? d.mel_dim : 0, 128, stream));
   F5B_TRY(f5b_pack_bf16(text_embed, T, a + 128, K, rows, T, T, stream));
@@ -183,42 +210,53 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
   cudaStream_t s = ST(stream);
   const int batch_mod = Bx;
 
+  const bool tp = is_tf32(d);
   // InputEmbedding (dit.py:91-97): x W_x^T + c0, then conv_pos_embed(h) + h (no mask)
   const int hrows = Bx * n;
   for (int half = 0; half < Bf / Bx; ++half) {
     const size_t off = (size_t)half * hrows * D;
-    F5B_TRY(linear_f32(x_bf16, 128, d.in_wx, 128, nullptr, w.x + off, D, hrows, D, 128, F5B_ACT_NONE, c0 + off, D, w.hb + off, D, s));
+    F5B_TRY(linear_f32(x_bf16, 128, d.in_wx, 128, nullptr, w.x + off, D, hrows, D, 128, F5B_ACT_NONE, c0 + off, D, aat(d, w.hb, off), D, s, tp));
   }
-  F5B_TRY(convpos(w.hb, d.cp_w1, d.cp_b1, w.ab, nullptr, Bf, n, D, d.convpos_groups, d.convpos_kernel, 0, s));
-  F5B_TRY(convpos(w.ab, d.cp_w2, d.cp_b2, nullptr, w.x, Bf, n, D, d.convpos_groups, d.convpos_kernel, 1, s));
+  if (tp) {
+    F5B_TRY(convpos_tf32(reinterpret_cast<const float*>(w.hb), reinterpret_cast<const float*>(d.cp_w1), d.cp_b1,
+                         reinterpret_cast<float*>(w.ab), nullptr, Bf, n, D, d.convpos_groups, d.convpos_kernel, 0, s));
+    F5B_TRY(convpos_tf32(reinterpret_cast<const float*>(w.ab), reinterpret_cast<const float*>(d.cp_w2), d.cp_b2, nullptr, w.x, Bf, n, D,
+                         d.convpos_groups, d.convpos_kernel, 1, s));
+  } else {
+    F5B_TRY(convpos(w.hb, d.cp_w1, d.cp_b1, w.ab, nullptr, Bf, n, D, d.convpos_groups, d.convpos_kernel, 0, s));
+    F5B_TRY(convpos(w.ab, d.cp_w2, d.cp_b2, nullptr, w.x, Bf, n, D, d.convpos_groups, d.convpos_kernel, 1, s));
+  }
 
-  const __nv_bfloat16* qkv_w = reinterpret_cast<const __nv_bfloat16*>(d.qkv_w);
-  const __nv_bfloat16* out_w = reinterpret_cast<const __nv_bfloat16*>(d.out_w);
-  const __nv_bfloat16* ff1_w = reinterpret_cast<const __nv_bfloat16*>(d.ff1_w);
-  const __nv_bfloat16* ff2_w = reinterpret_cast<const __nv_bfloat16*>(d.ff2_w);
   for (int i = 0; i < d.depth; ++i) {
     // AdaLayerNorm chunk order (model/modules.py:312): shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
     const float* m = mod + (size_t)i * 6 * D;
-    F5B_TRY(ln_modulate(w.x, m + D, m, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
+    F5B_TRY(ln_modulate(w.x, m + D, m, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s, tp));
     F5bGemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = rows; g.N = 3 * D; g.K = D; g.epi = F5B_EPI_QKV_ROPE; g.act = F5B_ACT_NONE;
     g.bias = d.qkv_b + (size_t)i * 3 * D;
     g.out = w.qkv; g.ldc = 3 * D;
     g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
-    F5B_TRY(gemm(w.hb, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
-    F5B_TRY(attn_fwd(w.qkv, w.qkv + D, w.qkv + 2 * D, 3 * D, w.ab, nullptr, lens, batch_mod, Bf, H, n, 0.125f, s));
-    F5B_TRY(linear_gate_resid(w.ab, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
-                              mod_bstride, lens, batch_mod, s));
-    F5B_TRY(ln_modulate(w.x, m + 4 * D, m + 3 * D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
-    F5B_TRY(linear_bf16(w.hb, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, w.fb, F, rows, F, D, F5B_ACT_GELU_TANH, s));
-    F5B_TRY(linear_gate_resid(w.fb, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, w.x, D, rows, D, F, n, m + 5 * D,
-                              mod_bstride, nullptr, batch_mod, s));
+    g.tf32 = tp;
+    F5B_TRY(gemm(w.hb, D, wat(d, d.qkv_w, (size_t)i * 3 * D * D), D, g, s));
+    if (tp) {
+      const float* q = reinterpret_cast<const float*>(w.qkv);
+      F5B_TRY(attn_fwd_tf32(q, q + D, q + 2 * D, 3 * D, reinterpret_cast<float*>(w.ab), w.vt, lens, batch_mod, Bf, H, n, 0.125f, s));
+    } else {
+      F5B_TRY(attn_fwd(w.qkv, aat(d, w.qkv, D), aat(d, w.qkv, 2 * D), 3 * D, w.ab, nullptr, lens, batch_mod, Bf, H, n, 0.125f, s));
+    }
+    F5B_TRY(linear_gate_resid(w.ab, D, wat(d, d.out_w, (size_t)i * D * D), D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
+                              mod_bstride, lens, batch_mod, s, tp));
+    F5B_TRY(ln_modulate(w.x, m + 4 * D, m + 3 * D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s, tp));
+    F5B_TRY(linear_bf16(w.hb, D, wat(d, d.ff1_w, (size_t)i * F * D), D, d.ff1_b + (size_t)i * F, w.fb, F, rows, F, D, F5B_ACT_GELU_TANH, s,
+                        tp));
+    F5B_TRY(linear_gate_resid(w.fb, F, wat(d, d.ff2_w, (size_t)i * D * F), F, d.ff2_b + (size_t)i * D, w.x, D, rows, D, F, n, m + 5 * D,
+                              mod_bstride, nullptr, batch_mod, s, tp));
   }
   // AdaLayerNorm_Final chunk order (model/modules.py:333): scale, shift; then proj_out (dit.py:231)
   const float* mf = mod + (size_t)d.depth * 6 * D;
-  F5B_TRY(ln_modulate(w.x, mf, mf + D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s));
-  F5B_TRY(linear_f32(w.hb, D, d.proj_w, D, d.proj_b, pred, d.mel_dim, rows, d.mel_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s));
+  F5B_TRY(ln_modulate(w.x, mf, mf + D, mod_bstride, batch_mod, w.hb, rows, n, D, 1e-6f, s, tp));
+  F5B_TRY(linear_f32(w.hb, D, d.proj_w, D, d.proj_b, pred, d.mel_dim, rows, d.mel_dim, D, F5B_ACT_NONE, nullptr, 0, nullptr, 0, s, tp));
   return 0;
 }
 

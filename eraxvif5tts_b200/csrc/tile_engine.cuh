@@ -15,7 +15,9 @@
 //                   STORE_DIRECT : per-thread vectorised global stores (scatter epilogues: QKV head split, conv);
 //                   STORE_BF16   : bf16 tile -> 128B-swizzled per-warp staging smem -> TMA store (coalesced, async);
 //                   STORE_F32ADD : f32 tile -> staging smem -> TMA reduce-add: the residual stream x += tile is
-//                                  accumulated in L2, x is never read into the SM.
+//                                  accumulated in L2, x is never read into the SM;
+//                   STORE_F32    : f32 tile -> staging smem -> TMA store (the tf32 operand mode's activation outputs).
+// P::TF32 selects kind::tf32 (fp32 words in the stages, 32 per 128-byte row) instead of kind::f16 (64 bf16 per row).
 // A "Problem" policy supplies the tile -> coordinate mapping (which TMA boxes feed k-block kb of tile t) and the
 // epilogue math, so the same pipeline serves  C = A W^T  and the 31-tap implicit-GEMM convolution.
 #pragma once
@@ -27,7 +29,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
 constexpr int ENGINE_THREADS = 64 + EPI_WARPS * 32;
-enum { STORE_DIRECT = 0, STORE_BF16 = 1, STORE_F32ADD = 2 };
+enum { STORE_DIRECT = 0, STORE_BF16 = 1, STORE_F32ADD = 2, STORE_F32 = 3 };
 
 template <int BN>
 struct EngCfg {
@@ -168,8 +170,14 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (TWOSM) umma_bf16_2sm(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+            // (P::TF32: the stage holds 32 fp32 elements per 128-byte row, one MMA covers K = 8 of them — the same 32-byte K-step)
+            if constexpr (P::TF32) {
+              if constexpr (TWOSM) umma_tf32_2sm(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+              else umma_tf32(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+            } else {
+              if constexpr (TWOSM) umma_bf16_2sm(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, p.a_desc(a_addr, k), p.b_desc(b_addr, k), idesc, (kb | k) != 0);
+            }
           }
           if constexpr (TWOSM) umma_commit2_mcast(&empty[stage], (uint16_t)0x3);
           else if constexpr (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
@@ -240,7 +248,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       } else {
-        // 32-column f32 granules -> TMA reduce-add into the residual stream
+        // 32-column f32 granules -> TMA reduce-add into the residual stream (STORE_F32ADD) or a plain TMA store (STORE_F32)
 #pragma unroll 1
         for (int g = half; g * 32 < ncols; g += 2) {
           uint32_t r[32];
@@ -258,7 +266,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            tma_reduce_add_2d(&tmC, stg, p.out_col0(tile) + g * 32, p.out_row0(tile) + quad * 32);
+            if constexpr (P::STORE == STORE_F32ADD) tma_reduce_add_2d(&tmC, stg, p.out_col0(tile) + g * 32, p.out_row0(tile) + quad * 32);
+            else tma_store_2d(&tmC, stg, p.out_col0(tile) + g * 32, p.out_row0(tile) + quad * 32);
             bulk_commit();
           }
         }

@@ -261,6 +261,7 @@ int f5b_dit_train_forward(const F5bDit* h, const float* x, const float* cond, co
   F5B_CHECK(h && x && text_embed && time && rope && pred && ws && B > 0 && n > 0, "f5b_dit_train_forward: bad argument");
   const F5bDitDesc& d = h->d;
   F5B_CHECK(d.depth <= MAX_DEPTH && d.dim <= 1024, "f5b_dit_train_forward: depth <= %d and dim <= 1024 supported", MAX_DEPTH);
+  F5B_CHECK(d.precision == 0, "f5b_dit_train_forward: the training drivers run bf16 operands (F5bDitDesc.precision 0) only");
   const int D = d.dim, F = d.ff_mult * d.dim, H = d.heads, T = d.text_dim, mel = d.mel_dim;
   const int rows = B * n;
   const int64_t mod_dim = (int64_t)d.depth * 6 * D + 2 * D;

@@ -121,12 +121,25 @@ class _DiTBlock(_Holder):
 # ----------------------------------------------------------------------------------------------------------------------
 # packed device weights + C handle
 # ----------------------------------------------------------------------------------------------------------------------
-class DiTEngine:
-    """bf16 / fused-layout copies of a DiT's parameters on one CUDA device and the `F5bDit` handle built on them."""
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32 value (10 explicit mantissa bits, ties away from zero = PTX cvt.rna.tf32.f32), kept as fp32: the
+    tcgen05 kind::tf32 MMA ignores the low 13 bits of each operand word, so rounding here makes that truncation exact."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
-    def __init__(self, dit: "DiT", device):
+
+class DiTEngine:
+    """Fused-layout copies of a DiT's parameters on one CUDA device and the `F5bDit` handle built on them: bf16 operands
+    (precision "bf16", the throughput mode) or fp32 words rounded to tf32 (precision "tf32", the fp32-tolerance mode)."""
+
+    def __init__(self, dit: "DiT", device, precision: str = "bf16"):
         from ... import ops
         lib = L.load()
+        if precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+        self.precision = precision
+        tf32 = precision == "tf32"
+        self.act_dtype = f32 if tf32 else bf16
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.F5bError("DiTEngine needs a CUDA device (B200); there is no CPU fallback")
@@ -136,7 +149,10 @@ class DiTEngine:
         self.keep = []  # tensors the handle points into
 
         def dev(t, dtype):
-            t = t.to(device=self.device, dtype=dtype).contiguous()
+            if dtype is bf16 and tf32:  # tensor-core operand: fp32 words rounded to tf32 instead of bf16
+                t = round_tf32(t.to(device=self.device, dtype=f32))
+            else:
+                t = t.to(device=self.device, dtype=dtype).contiguous()
             self.keep.append(t)
             return t
 
@@ -153,6 +169,7 @@ class DiTEngine:
         d.text_mask_padding = int(bool(dit.text_mask_padding))
         d.convpos_kernel, d.convpos_groups = 31, 16
         d.vocab_rows = sd["text_embed.text_embed.weight"].shape[0]
+        d.precision = 1 if tf32 else 0
         P = {}
         P["time_w0"], P["time_b0"] = dev(sd["time_embed.time_mlp.0.weight"], bf16), dev(sd["time_embed.time_mlp.0.bias"], f32)
         P["time_w2"], P["time_b2"] = dev(sd["time_embed.time_mlp.2.weight"], bf16), dev(sd["time_embed.time_mlp.2.bias"], f32)
@@ -181,7 +198,7 @@ class DiTEngine:
         with torch.cuda.device(self.device):
             for j, c in ((1, 0), (2, 2)):
                 w32 = dev(sd[cw.format(c) + "weight"], f32)
-                pk = ops.pack_convpos_weight(w32, 16)
+                pk = ops.pack_convpos_weight_tf32(w32, 16) if tf32 else ops.pack_convpos_weight(w32, 16)
                 self.keep.append(pk)
                 P[f"cp_w{j}"], P[f"cp_b{j}"] = pk, dev(sd[cw.format(c) + "bias"], f32)
             torch.cuda.synchronize()
@@ -246,7 +263,7 @@ class DiTEngine:
             self._sessions.pop(next(iter(self._sessions)))
         dev, mel = self.device, self.mel_dim
         sess = dict(
-            y=torch.zeros(Bx, n, mel, dtype=f32, device=dev), yb=torch.zeros(Bx * n, 128, dtype=bf16, device=dev),
+            y=torch.zeros(Bx, n, mel, dtype=f32, device=dev), yb=torch.zeros(Bx * n, 128, dtype=self.act_dtype, device=dev),
             c0=torch.zeros(Bf, n, self.dim, dtype=f32, device=dev), pred=torch.zeros(Bf, n, mel, dtype=f32, device=dev),
             stepbuf=torch.zeros(self.mod_dim + 2, dtype=f32, device=dev),
             lens=torch.full((Bx,), n, dtype=torch.int32, device=dev) if masked else None, graph=None, delta=None,
@@ -257,8 +274,13 @@ class DiTEngine:
 
         def body():
             self.forward(sess["yb"], Bx, sess["c0"], Bf, n, sess["stepbuf"], 0, sess["lens"], sess["pred"])
-            L.check(self.lib.f5b_cfg_euler_dev(sess["y"].data_ptr(), pc.data_ptr(), L.ptr(pu), params.data_ptr(), sess["yb"].data_ptr(),
-                                               128, None, Bx * n, mel, L.stream()), "f5b_cfg_euler_dev")
+            if self.precision == "tf32":
+                L.check(self.lib.f5b_cfg_euler_dev(sess["y"].data_ptr(), pc.data_ptr(), L.ptr(pu), params.data_ptr(), None, 128, None,
+                                                   Bx * n, mel, L.stream()), "f5b_cfg_euler_dev")
+                self.pack_state(sess["y"], sess["yb"])
+            else:
+                L.check(self.lib.f5b_cfg_euler_dev(sess["y"].data_ptr(), pc.data_ptr(), L.ptr(pu), params.data_ptr(),
+                                                   sess["yb"].data_ptr(), 128, None, Bx * n, mel, L.stream()), "f5b_cfg_euler_dev")
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -301,14 +323,26 @@ class DiTEngine:
         """[cond | text_embed] W^T + b -> f32 [B, n, D]; cond None = drop_audio_cond (dit.py:92-95)."""
         B, n, _ = text_embed.shape
         c0 = out if out is not None else torch.empty(B, n, self.dim, dtype=f32, device=self.device)
-        ws = torch.empty(B * n * (128 + self.text_dim) * 2, dtype=torch.uint8, device=self.device)
+        ws = torch.empty(B * n * (128 + self.text_dim) * (4 if self.precision == "tf32" else 2), dtype=torch.uint8, device=self.device)
         if cond is not None:
             cond = cond.to(device=self.device, dtype=f32).contiguous()
         L.check(self.lib.f5b_dit_input_const(self.handle, L.ptr(cond), text_embed.data_ptr(), B, n, c0.data_ptr(), ws.data_ptr(),
                                              L.stream()), "f5b_dit_input_const")
         return c0
 
+    def pack_state(self, y: torch.Tensor, yb: torch.Tensor | None = None) -> torch.Tensor:
+        """ODE state / DiT input f32 [..., mel] -> the zero-padded [rows, 128] operand of the input GEMM in the engine's operand
+        type (bf16, or fp32 rounded to tf32)."""
+        from ... import ops
+        rows = y.numel() // self.mel_dim
+        if yb is None:
+            yb = torch.empty(rows, 128, dtype=self.act_dtype, device=self.device)
+        (ops.pack_tf32 if self.precision == "tf32" else ops.pack_bf16)(y.view(rows, self.mel_dim), yb, self.mel_dim, 128)
+        return yb
+
     def forward(self, x_bf16, Bx, c0, Bf, n, mod, mod_bstride, lens, pred):
+        """x_bf16: the packed state from `pack_state` (bf16, or fp32 in the tf32 mode)"""
+        assert x_bf16.dtype == self.act_dtype
         nbytes = self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n)
         ws = self.workspace(nbytes)
         L.check(self.lib.f5b_dit_forward(self.handle, x_bf16.data_ptr(), Bx, c0.data_ptr(), Bf, n, mod.data_ptr(), mod_bstride,
@@ -322,7 +356,7 @@ class DiT(nn.Module):
 
     def __init__(self, *, dim, depth=8, heads=8, dim_head=64, dropout=0.1, ff_mult=4, mel_dim=100, text_num_embeds=256,
                  text_dim=None, text_mask_padding=True, qk_norm=None, conv_layers=0, pe_attn_head=None,
-                 long_skip_connection=False, checkpoint_activations=False):
+                 long_skip_connection=False, checkpoint_activations=False, precision="bf16"):
         super().__init__()
         if qk_norm is not None:
             raise NotImplementedError("qk_norm is unused by every F5TTS config of the reference (configs/*.yaml) and is not built")
@@ -345,6 +379,7 @@ class DiT(nn.Module):
         self.norm_out = _AdaLayerNorm(dim, 2)
         self.proj_out = nn.Linear(dim, mel_dim)
         self.checkpoint_activations = checkpoint_activations
+        self.precision = precision  # extension: "bf16" (throughput) or "tf32" (1e-3 of the fp32 reference); set_precision() switches
         self.initialize_weights()
         self._engine = None
         self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
@@ -368,10 +403,19 @@ class DiT(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
+    def set_precision(self, precision: str):
+        """Operand mode of the inference path: "bf16" (default) or "tf32"; the packed weights are rebuilt lazily."""
+        if precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+        if precision != self.precision:
+            self.precision = precision
+            self.invalidate()
+        return self
+
     def engine(self) -> DiTEngine:
         dev = self.proj_out.weight.device
-        if self._engine is None or self._engine.device != dev:
-            self._engine = DiTEngine(self, dev)
+        if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
+            self._engine = DiTEngine(self, dev, self.precision)
         return self._engine
 
     def clear_cache(self):
@@ -399,9 +443,7 @@ class DiT(nn.Module):
         else:
             te = eng.text_embed(text, n, drop_text)
         c0 = eng.input_const(None if drop_audio_cond else cond, te)
-        from ... import ops
-        xb = torch.empty(b * n, 128, dtype=bf16, device=eng.device)
-        ops.pack_bf16(x.to(device=eng.device, dtype=f32).contiguous().view(b * n, self.mel_dim), xb, self.mel_dim, 128)
+        xb = eng.pack_state(x.to(device=eng.device, dtype=f32).contiguous())
         lens = None
         if mask is not None:
             lens = mask.sum(dim=-1).to(torch.int32).contiguous()

@@ -160,9 +160,16 @@ class CFM(nn.Module):
             lens32 = sess["lens"]
         else:
             y = y0.contiguous()
-            yb = torch.empty(rows, 128, dtype=bf16, device=device)
+            yb = torch.empty(rows, 128, dtype=eng.act_dtype, device=device)
             pred = torch.empty(Bf, n, self.num_channels, dtype=f32, device=device)
-        ops.pack_bf16(y.view(rows, self.num_channels), yb, self.num_channels, 128)
+        eng.pack_state(y, yb)
+        tf32 = eng.precision == "tf32"
+
+        def euler(state, step):
+            # CFG combine + Euler update; the bf16 mode refreshes the packed state in the same kernel, the tf32 mode re-packs in fp32
+            ops.cfg_euler(state, pc, pu, cfg_strength, step, None if tf32 else yb)
+            if tf32:
+                eng.pack_state(state, yb)
         pc = pred[:batch]
         pu = pred[batch:] if use_cfg else None
         traj = [y.clone()] if return_trajectory else None
@@ -179,13 +186,13 @@ class CFM(nn.Module):
                 L.prof_add(sess["delta"])
             elif method == "euler":
                 eng.forward(yb, batch, c0, Bf, n, mod[i], 0, lens32, pred)
-                ops.cfg_euler(y, pc, pu, cfg_strength, dt_host[i], yb)
+                euler(y, dt_host[i])
             else:
                 eng.forward(yb, batch, c0, Bf, n, mod[2 * i], 0, lens32, pred)
                 ymid.copy_(y)
-                ops.cfg_euler(ymid, pc, pu, cfg_strength, 0.5 * dt_host[i], yb)
+                euler(ymid, 0.5 * dt_host[i])
                 eng.forward(yb, batch, c0, Bf, n, mod[2 * i + 1], 0, lens32, pred)
-                ops.cfg_euler(y, pc, pu, cfg_strength, dt_host[i], yb)
+                euler(y, dt_host[i])
             if return_trajectory:
                 traj.append(y.clone())
         self.transformer.clear_cache()

@@ -23,11 +23,12 @@ def _chk(t, dtype, name):
 
 
 def gemm(a, w, *, epi, act=L.ACT_NONE, bias=None, out=None, out2=None, out3=None, addsrc=None, rows_per_batch=0, gate=None,
-         gate_bstride=0, lens=None, batch_mod=0, rope=None, rope_heads=0, heads=0, n_pad=0, M=None, N=None, K=None, lda=None,
+         gate_bstride=0, lens=None, batch_mod=0, rope=None, rope_heads=0, heads=0, tf32=False, M=None, N=None, K=None, lda=None,
          ldw=None, ldc=None, ldc2=0):
-    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 2-D (row pitch = shape[1] unless lda/ldw given)."""
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 2-D (row pitch = shape[1] unless lda/ldw given); with tf32=True a, w are
+    f32 tensors whose values were rounded to tf32 (ops.round_tf32) and the BF16 / QKV_ROPE epilogues write f32."""
     lib = L.load()
-    _chk(a, bf16, "a"); _chk(w, bf16, "w"); _chk(bias, f32, "bias"); _chk(addsrc, f32, "addsrc"); _chk(gate, f32, "gate")
+    _chk(a, f32 if tf32 else bf16, "a"); _chk(w, f32 if tf32 else bf16, "w"); _chk(bias, f32, "bias"); _chk(addsrc, f32, "addsrc"); _chk(gate, f32, "gate")
     _chk(lens, torch.int32, "lens"); _chk(rope, f32, "rope")
     g = L.GemmArgs()
     g.M = M if M is not None else a.shape[0]
@@ -48,7 +49,7 @@ def gemm(a, w, *, epi, act=L.ACT_NONE, bias=None, out=None, out2=None, out3=None
     g.lens = L.ptr(lens)
     g.batch_mod = batch_mod
     g.rope = L.ptr(rope)
-    g.rope_heads, g.heads, g.n_pad = rope_heads, heads, n_pad
+    g.rope_heads, g.heads, g.tf32 = rope_heads, heads, int(bool(tf32))
     L.check(lib.f5b_gemm(a.data_ptr(), lda or a.stride(0), w.data_ptr(), ldw or w.stride(0), C.byref(g), L.stream()), "f5b_gemm")
     return out
 
@@ -139,6 +140,62 @@ def pack_bf16(x, out, cols, width):
     rows = out.shape[0]
     L.check(lib.f5b_pack_bf16(L.ptr(x), x.shape[-1] if x is not None else 0, out.data_ptr(), out.shape[-1], rows, cols, width,
                               L.stream()), "f5b_pack_bf16")
+
+
+# ---- tf32 operand mode (include/f5b200.h "tf32 operand mode") ---------------------------------------------------------
+def round_tf32(t):
+    """fp32 -> nearest tf32 value kept as fp32 (what every tf32-mode operand must hold; = PTX cvt.rna.tf32.f32)"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_tf32(x, out, cols, width):
+    lib = L.load()
+    _chk(x, f32, "x"); _chk(out, f32, "out")
+    rows = out.shape[0]
+    L.check(lib.f5b_pack_tf32(L.ptr(x), x.shape[-1] if x is not None else 0, out.data_ptr(), out.shape[-1], rows, cols, width,
+                              L.stream()), "f5b_pack_tf32")
+
+
+def ln_modulate_tf32(x, scale, shift, mod_bstride, batch_mod, rows_per_batch, eps=1e-6, out=None):
+    lib = L.load()
+    _chk(x, f32, "x"); _chk(scale, f32, "scale"); _chk(shift, f32, "shift")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty(rows, D, dtype=f32, device=x.device)
+    L.check(lib.f5b_ln_modulate_tf32(x.data_ptr(), L.ptr(scale), L.ptr(shift), mod_bstride, batch_mod, out.data_ptr(), rows,
+                                     rows_per_batch, D, eps, L.stream()), "f5b_ln_modulate_tf32")
+    return out
+
+
+def attn_fwd_tf32(q, k, v, ld, out, lens, lens_mod, B, H, n, scale=0.125):
+    lib = L.load()
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        if t.dtype != f32 or not t.is_cuda:
+            raise L.F5bError(f"attn_fwd_tf32: {nm} must be a CUDA f32 tensor")
+    _chk(lens, torch.int32, "lens")
+    vt = torch.empty(lib.f5b_attn_tf32_ws_floats(B, H, n), dtype=f32, device=q.device)
+    L.check(lib.f5b_attn_fwd_tf32(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), vt.data_ptr(), L.ptr(lens), lens_mod, B, H,
+                                  n, scale, L.stream()), "f5b_attn_fwd_tf32")
+    return out
+
+
+def pack_convpos_weight_tf32(w, groups):
+    lib = L.load()
+    _chk(w, f32, "w")
+    D, cpg, ks = w.shape
+    n = lib.f5b_convpos_packed_elems_tf32(D, groups, ks)
+    out = torch.empty(n, dtype=f32, device=w.device)
+    L.check(lib.f5b_pack_convpos_weight_tf32(w.data_ptr(), out.data_ptr(), D, groups, ks, L.stream()), "f5b_pack_convpos_weight_tf32")
+    return out
+
+
+def convpos_tf32(x, wpk, bias, B, n, D, groups, ksize, out=None, resid=None):
+    lib = L.load()
+    _chk(x, f32, "x"); _chk(wpk, f32, "wpk"); _chk(bias, f32, "bias"); _chk(out, f32, "out"); _chk(resid, f32, "resid")
+    mode = 0 if resid is None else 1
+    L.check(lib.f5b_convpos_tf32(x.data_ptr(), wpk.data_ptr(), bias.data_ptr(), L.ptr(out), L.ptr(resid), B, n, D, groups, ksize, mode,
+                                 L.stream()), "f5b_convpos_tf32")
+    return out if resid is None else resid
 
 
 def melspec(wav, fb, ranges, n_mels):

@@ -57,7 +57,8 @@ typedef struct F5bGemmArgs {
   const float* rope;         /* QKV_ROPE: f32 [n, 32, 2] (cos, sin) */
   int32_t rope_heads;        /* QKV_ROPE: heads that get the rotary embedding (pe_attn_head; H for all) */
   int32_t heads;             /* QKV_ROPE: H (N must be 3*H*64) */
-  int32_t n_pad;             /* unused (kept for ABI stability) */
+  int32_t tf32;              /* operand mode: 0 = A, W bf16 (kind::f16); 1 = A, W fp32 words rounded to tf32 (kind::tf32) — the
+                                BF16 / QKV_ROPE epilogues then write fp32 rounded to tf32, F32's out2 is an fp32 tf32 copy */
 } F5bGemmArgs;
 
 const char* f5b_last_error(void);
@@ -187,9 +188,37 @@ int f5b_im2col7(const float* mel, void* out_bf16, int B, int T, int n_mels, int 
 
 /* All pointers are device pointers owned by the caller and must outlive the handle.
  * "stack" pointers hold one tensor per DiT block, contiguous: [depth, ...]. */
+/* ---- tf32 operand mode (F5bGemmArgs.tf32 / F5bDitDesc.precision 1): the fp32-tolerance path ------------------------------
+ * Tensor-core operands are fp32 words rounded to tf32 (cvt.rna, 10-bit mantissa), accumulation and all element-wise math fp32.
+ * It replaces the same reference call sites as the bf16 entry points named in each comment; it exists because bf16 operands
+ * cannot hold the 1e-3 relative velocity tolerance against the fp32 reference (measured 3.4e-3; tf32 4e-4). */
+/* f5b_ln_modulate with an fp32 (tf32-rounded) output */
+int f5b_ln_modulate_tf32(const float* x, const float* scale, const float* shift, int64_t mod_bstride, int batch_mod, float* out,
+                         int rows, int rows_per_batch, int D, float eps, f5b_stream_t stream);
+/* f5b_attn_fwd with q, k, v, out fp32 (tf32-rounded values in, tf32-rounded out); ld in elements.  kind::tf32 takes K-major
+ * operands only, so V is transposed into vt_ws (f5b_attn_tf32_ws_floats(B, H, n) floats) first. */
+int f5b_attn_fwd_tf32(const float* q, const float* k, const float* v, int ld, float* out, float* vt_ws, const int32_t* lens,
+                      int lens_mod, int B, int H, int n, float scale, f5b_stream_t stream);
+size_t f5b_attn_tf32_ws_floats(int B, int H, int n);
+/* f5b_convpos with x fp32 [B*n, D] (tf32-rounded), wpk from f5b_pack_convpos_weight_tf32; mode 0: out fp32 = tf32(mish(conv + b)),
+ * mode 1: resid += mish(conv + b) */
+int f5b_convpos_tf32(const float* x, const float* wpk, const float* bias, float* out, float* resid, int B, int n, int D, int groups,
+                     int ksize, int mode, f5b_stream_t stream);
+int f5b_pack_convpos_weight_tf32(const float* w, float* wpk, int D, int groups, int ksize, f5b_stream_t stream);
+size_t f5b_convpos_packed_elems_tf32(int D, int groups, int ksize);
+/* f5b_time_sinus / f5b_pack_bf16 with fp32 (tf32-rounded) outputs */
+int f5b_time_sinus_tf32(const float* t, float* out, int M, f5b_stream_t stream);
+int f5b_pack_tf32(const float* x, int ld_in, float* out, int ld_out, int rows, int cols, int width, f5b_stream_t stream);
+
 typedef struct F5bDitDesc {
   int32_t dim, depth, heads, dim_head, ff_mult, mel_dim, text_dim, conv_layers, rope_heads, text_mask_padding;
   int32_t convpos_kernel, convpos_groups, vocab_rows;
+  /* operand mode of the inference drivers (f5b_dit_modulation / text_embed / input_const / forward):
+   *   0  bf16 tensor-core operands (kind::f16), the throughput mode; every "bf16" weight below is bf16.
+   *   1  tf32 operands (kind::tf32): every "bf16" weight below is instead an fp32 array of the same shape whose values were
+   *      rounded to tf32 (round-to-nearest), cp_w1 / cp_w2 come from f5b_pack_convpos_weight_tf32, the activations between the
+   *      kernels are fp32, and f5b_dit_forward's `x` is fp32 [Bx*n, 128].  Holds 1e-3 of the fp32 reference. */
+  int32_t precision;
   /* TimestepEmbedding (model/modules.py:721-731) */
   const void* time_w0; const float* time_b0;   /* bf16 [D,256] */
   const void* time_w2; const float* time_b2;   /* bf16 [D,D]   */
