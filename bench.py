@@ -815,6 +815,34 @@ def parity_leg(dev):
     res["tolerances"] = {"velocity_max_abs_bf16": A.VEL_TOL_BF16, "mel_mean_abs": A.MEL_MEAN_TOL}
     res["pass"] = bool(res["velocity_max_abs"] <= A.VEL_TOL_BF16 and res["mel_mean_abs_generated"] <= A.MEL_MEAN_TOL)
     res["oracle"] = "oracle/f5_oracle.py (fp32, cuBLAS / cuDNN without TF32) on the same GPU, identical bf16-exact weights, noise and inputs"
+    # the tf32 operand mode (north_star's fp32 clause: 1e-3 relative error of the velocity field): same check, then its throughput on
+    # cfg-2's batch — device-resident inputs, CUDA events, un-instrumented, 2 warm-up + 3 timed sample() calls
+    model.transformer.set_precision("tf32")
+    r32 = A.sample_parity(model, sd, cfg, 563, [1875, 1610], steps=NFE, cfg_strength=CFG, sway=SWAY, device=dev)
+    t = {"precision": "tf32 tensor-core operands (kind::tf32), fp32 activations", "velocity_rel_fro": r32["velocity_rel_fro"],
+         "velocity_max_abs": r32["velocity_max_abs"], "mel_mean_abs_generated": r32["mel_mean_abs_generated"],
+         "tolerance_velocity_rel_fro": A.VEL_RTOL_FP32,
+         "pass": bool(r32["velocity_rel_fro"] <= A.VEL_RTOL_FP32 and r32["mel_mean_abs_generated"] <= A.MEL_MEAN_TOL)}
+    _, B, ref_frames, total, _ = WORKLOADS["cfg2"]
+    cond, text, duration, lens, _ = make_inputs(Arch(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads), B, ref_frames, total, 1234)
+    cond, text, duration, lens = cond.to(dev), text.to(dev), duration.to(dev), lens.to(dev)
+
+    def one():
+        model.sample(cond=cond, text=text, duration=duration, lens=lens, steps=NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=0,
+                     return_trajectory=False)
+    for _ in range(2):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(3):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 3
+    t.update({"workload": "cfg2 sampling (CFM.sample only, no vocoder)", "ms_per_step": ms, "value": B * total / (ms * 1e-3),
+              "unit": "mel-frames/s", "model_tflops": dit_flops_per_forward(cfg, 2 * B, total) * NFE / (ms * 1e-3) / 1e12})
+    res["tf32_mode"] = t
     return res
 
 

@@ -173,3 +173,18 @@ def test_acceptance_tf32_velocity_1e3(tag, cfg, ref_frames, totals):
     _record(tag, res)
     assert res["velocity_rel_fro"] <= A.VEL_RTOL_FP32, res["velocity"]
     assert res["mel_mean_abs_generated"] <= A.MEL_MEAN_TOL / 4, res
+
+
+def test_acceptance_tf32_with_fp32_weights():
+    """The oracle's synthetic weights are bf16-exact (so the bf16 path's weight copies are lossless); a real checkpoint is not.  With
+    weights that need all 24 mantissa bits the tf32 mode also rounds the WEIGHTS (to nearest): same bar, F5TTS_Base depth 22."""
+    cfg = O.DiTConfig()
+    model, sd = build_cfm(cfg, 0)
+    g = torch.Generator().manual_seed(77)
+    sd2 = {k: (v * (1.0 + 1e-3 * torch.randn(v.shape, generator=g)) if v.is_floating_point() and v.ndim >= 2 else v) for k, v in sd.items()}
+    model.load_state_dict(sd2, strict=False)
+    model.transformer.set_precision("tf32")
+    res = A.sample_parity(model, sd2, cfg, 376, [940], steps=32, cfg_strength=2.0, sway=-1.0, seed=0)
+    res["precision"] = "tf32, weights not bf16-exact"
+    _record("tf32_base_d22_b1_n940_fp32_weights", res)
+    assert res["velocity_rel_fro"] <= A.VEL_RTOL_FP32, res["velocity"]
