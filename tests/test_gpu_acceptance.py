@@ -23,11 +23,12 @@ def _record(tag, res):
     path = os.path.join(ROOT, "gpurun_out", "parity_r02.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     data = {}
-    if os.path.exists(path):
-        try:
-            data = json.load(open(path))
-        except Exception:  # noqa: BLE001
-            data = {}
+    for src in (os.path.join(ROOT, "profiles", "r02_parity_acceptance.json"), path):  # start from the committed record
+        if os.path.exists(src):
+            try:
+                data.update(json.load(open(src)))
+            except Exception:  # noqa: BLE001
+                pass
     data[tag] = res
     with open(path, "w") as f:
         json.dump(data, f, indent=1)
