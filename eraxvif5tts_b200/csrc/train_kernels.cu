@@ -148,6 +148,183 @@ __global__ void __launch_bounds__(CT_THREADS) gate_bwd_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 16-byte column-strip forms of gate_bwd / act_bwd (C a multiple of 8).  CTA = 8 warps on a [256 rows x 256 columns] block: a warp
+// streams 32 consecutive rows of the block, lane = 8 adjacent columns (16-byte bf16 / 2 x 16-byte fp32 accesses, 512 B - 1 KB
+// contiguous per warp per row).  Every batch of 4 rows is LOADED IN FULL before anything is computed or stored (act_bwd runs in
+// place — dh aliases du — so without the explicit batching each row's store fences the next row's loads).  The column sums of the 8
+// warps are folded in shared memory and leave the CTA as ONE fp32 atomic per column: rows / 256 atomics per column instead of
+// rows / 64 — measured (ncu, r02) the r01 kernels were bound by the same-address atomics at the L2 (a 32-row variant with twice the
+// atomics ran 2.8 x SLOWER at the same traffic, `drain` as the top stall).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 256;   // rows per CTA
+constexpr int CS_WROWS = 32;   // consecutive rows per warp
+constexpr int CS_COLS = 256;   // columns per CTA = 32 lanes x 8
+constexpr int CS_BATCH = 4;
+
+__device__ __forceinline__ void bf8_to_f32(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+// fold the 8 warps' per-lane column sums and add them to out[c0 + 0..255] (one atomic per column)
+__device__ __forceinline__ void cs_fold_atomic(float (*red)[CS_COLS], const float (&s)[8], float* out, int c0, int C, bool enabled) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  *reinterpret_cast<float4*>(&red[warp][lane * 8]) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(&red[warp][lane * 8 + 4]) = make_float4(s[4], s[5], s[6], s[7]);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (enabled && c0 + t < C) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][t];
+    atomicAdd(out + c0 + t, a);
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_bwd8_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
+                                                        const float* __restrict__ gate, int64_t gate_bstride,
+                                                        const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ dz,
+                                                        float* __restrict__ dgate, float* __restrict__ dbias, int n, int C,
+                                                        const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
+  __shared__ __align__(16) float red[8][CS_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.z * CS_COLS;
+  const int c = c0 + lane * 8;
+  const bool col_ok = c < C;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * CS_ROWS + warp * CS_WROWS;
+  const int p1 = min(n, p0 + CS_WROWS);
+  const int live_end = lens ? min(p1, __ldg(lens + b)) : p1;
+  float gv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gv[i] = 1.f;
+  if (gate && col_ok) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_bstride + c));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_bstride + c) + 1);
+    gv[0] = t0.x; gv[1] = t0.y; gv[2] = t0.z; gv[3] = t0.w; gv[4] = t1.x; gv[5] = t1.y; gv[6] = t1.z; gv[7] = t1.w;
+  }
+  float a[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = s[i] = 0.f;
+  if (col_ok) {
+    for (int pb = p0; pb < p1; pb += CS_BATCH) {
+      float4 d0[CS_BATCH], d1[CS_BATCH];
+      uint4 zz[CS_BATCH];
+#pragma unroll
+      for (int k = 0; k < CS_BATCH; ++k) {
+        const size_t off = ((size_t)b * n + pb + k) * C + c;
+        if (pb + k < live_end) {
+          d0[k] = *reinterpret_cast<const float4*>(dx + off);
+          d1[k] = *reinterpret_cast<const float4*>(dx + off + 4);
+          if (z != nullptr) zz[k] = *reinterpret_cast<const uint4*>(z + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CS_BATCH; ++k) {
+        if (pb + k < p1) {
+          const size_t off = ((size_t)b * n + pb + k) * C + c;
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          if (pb + k < live_end) {
+            float d[8] = {d0[k].x, d0[k].y, d0[k].z, d0[k].w, d1[k].x, d1[k].y, d1[k].z, d1[k].w};
+            if (dr.thr16) {  // z went through dropout before the gate: d(x_out)/d(z) = gate * mask / (1 - p)
+              float m0[4], m1[4];
+              drop_mult4(dr, off, m0);
+              drop_mult4(dr, off + 4, m1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { d[i] *= m0[i]; d[4 + i] *= m1[i]; }
+            }
+            if (z != nullptr) {
+              float zf[8];
+              bf8_to_f32(zz[k], zf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = fmaf(d[i], zf[i], a[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i] = gv[i] * d[i];
+              s[i] += o[i];
+            }
+          }
+          *reinterpret_cast<uint4*>(dz + off) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+    }
+  }
+  if (dgate != nullptr && z != nullptr) cs_fold_atomic(red, a, dgate + (size_t)b * gate_bstride, c0, C, true);
+  if (dbias != nullptr) cs_fold_atomic(red, s, dbias, c0, C, true);
+}
+
+// ACT: compile-time activation (F5B_ACT_*), or -1 = the run-time `act`
+template <int ACT>
+__global__ void __launch_bounds__(256) act_bwd8_kernel(const __nv_bfloat16* du, const __nv_bfloat16* __restrict__ h,
+                                                       __nv_bfloat16* dh /* may alias du */, float* __restrict__ dbias, int64_t rows, int C,
+                                                       int ld, int act, const Drop dr) {
+  griddep_wait();  // PDL (common.cuh)
+  griddep_launch_dependents();
+  __shared__ __align__(16) float red[8][CS_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * CS_COLS;
+  const int c = c0 + lane * 8;
+  const int64_t r0 = (int64_t)blockIdx.x * CS_ROWS + warp * CS_WROWS;
+  const int64_t r1 = min(rows, r0 + CS_WROWS);
+  const int a_ = ACT >= 0 ? ACT : act;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (c < C) {
+    for (int64_t rb = r0; rb < r1; rb += CS_BATCH) {
+      uint4 dv[CS_BATCH], hv[CS_BATCH];
+#pragma unroll
+      for (int k = 0; k < CS_BATCH; ++k) {
+        if (rb + k < r1) {
+          const size_t off = (size_t)(rb + k) * ld + c;
+          dv[k] = *reinterpret_cast<const uint4*>(du + off);
+          if (h != nullptr) hv[k] = *reinterpret_cast<const uint4*>(h + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CS_BATCH; ++k) {
+        if (rb + k < r1) {
+          const size_t off = (size_t)(rb + k) * ld + c;
+          float d[8];
+          bf8_to_f32(dv[k], d);
+          if (h != nullptr) {
+            float hf[8];
+            bf8_to_f32(hv[k], hf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] *= act_grad(a_, hf[i]);
+            if (dr.thr16) {  // the forward's mask (requires ld == C: the element index is the forward's)
+              float m0[4], m1[4];
+              drop_mult4(dr, off, m0);
+              drop_mult4(dr, off + 4, m1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { d[i] *= m0[i]; d[4 + i] *= m1[i]; }
+            }
+          }
+          if (dh != nullptr) {
+            const uint4 pk = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+            *reinterpret_cast<uint4*>(dh + off) = pk;
+            bf8_to_f32(pk, d);  // the bias sees what the GEMMs see
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += d[i];
+        }
+      }
+    }
+  }
+  if (dbias != nullptr) cs_fold_atomic(red, s, dbias, c0, C, true);
+}
+
 __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, int64_t n8, int act, const Drop dr) {
   griddep_wait();  // PDL (common.cuh)
   griddep_launch_dependents();
@@ -222,15 +399,16 @@ __global__ void __launch_bounds__(CT_THREADS) act_bwd_kernel(const __nv_bfloat16
 
 // Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine; AdaLayerNorm model/modules.py:310-315):
 //   dshift[b] += sum_r dy;  dscale[b] += sum_r dy * xhat;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b])
-// One warp per row, 4 rows per warp.  The row is NOT cached in registers: it is streamed four times (mean; variance; the two
-// projections + column sums; output) and passes 2-4 hit L1, which keeps the kernel at ~48 registers -> 5 CTAs / SM of loads in
-// flight instead of 2 (the register-resident version ran at 2.8 TB/s, latency-bound).  The column sums live in a per-warp
-// shared-memory slice (plain load-add-store), folded at the end into one fp32 atomic per column per CTA.
+// One warp per row, 4 rows per warp.  The row lives in registers and ALL of its loads (x, dy and, when accumulating, the old dx)
+// are issued before the first reduction: ~10 KB in flight per warp (the r01 kernel streamed the row four times through L1 / L2 to
+// stay at 48 registers — 30 % / 58 % hit rates, one dependent stream after the other, 3.5 TB/s).  The column sums live in a per-warp
+// shared-memory slice (plain 128-bit load-add-store: shared-memory fp32 atomics compile to CAS loops on sm_100a), folded at the end
+// into one fp32 atomic per column per CTA.
 template <int VEC>
-__global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
-                                                         const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
-                                                         int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
-                                                         int D, float eps, int affine) {
+__global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ scale, int64_t mod_bstride, float* __restrict__ dx,
+                                                            int accumulate, float* __restrict__ dscale, float* __restrict__ dshift, int n,
+                                                            int D, float eps, int affine) {
   griddep_wait();  // PDL (common.cuh)
   griddep_launch_dependents();
   extern __shared__ float4 ln_acc4[];  // [8 warps][2][D/4]
@@ -251,23 +429,30 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     const size_t row = (size_t)b * n + pos;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + row * D);
-    float s = 0.f;
+    float4* o = reinterpret_cast<float4*>(dx + row * D);
+    float4 v[VEC], pz[VEC];
+    uint2 dd[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pz[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dd[j] = make_uint2(0u, 0u);
       if (idx < nvec) {
-        const float4 v = __ldg(xr + idx);
-        s += (v.x + v.y) + (v.z + v.w);
+        v[j] = __ldg(xr + idx);
+        dd[j] = __ldg(dr + idx);
+        if (accumulate) pz[j] = o[idx];
       }
     }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const int idx = lane + j * 32;
-      if (idx < nvec) {
-        const float4 v = __ldg(xr + idx);
-        const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      if (lane + j * 32 < nvec) {
+        const float a0 = v[j].x - mean, a1 = v[j].y - mean, a2 = v[j].z - mean, a3 = v[j].w - mean;
         q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       }
     }
@@ -277,52 +462,44 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
       if (idx < nvec) {
-        const float4 v = __ldg(xr + idx);
-        const uint2 d = __ldg(dr + idx);
-        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
-        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
-        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd, xh2 = (v.z - mean) * rstd, xh3 = (v.w - mean) * rstd;
+        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dd[j].x));
+        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dd[j].y));
+        // xhat replaces x in the register copy of the row
+        v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd; v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
         float4 a = my_sh[idx];
         a.x += d0.x; a.y += d0.y; a.z += d1.x; a.w += d1.y;
         my_sh[idx] = a;
         a = my_sc[idx];
-        a.x = fmaf(d0.x, xh0, a.x); a.y = fmaf(d0.y, xh1, a.y); a.z = fmaf(d1.x, xh2, a.z); a.w = fmaf(d1.y, xh3, a.w);
+        a.x = fmaf(d0.x, v[j].x, a.x); a.y = fmaf(d0.y, v[j].y, a.y); a.z = fmaf(d1.x, v[j].z, a.z); a.w = fmaf(d1.y, v[j].w, a.w);
         my_sc[idx] = a;
         float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
         if (scv != nullptr) {
           const float4 sc = __ldg(scv + idx);
           m = make_float4(o1 + sc.x, o1 + sc.y, o1 + sc.z, o1 + sc.w);
         }
-        const float g0 = d0.x * m.x, g1 = d0.y * m.y, g2 = d1.x * m.z, g3 = d1.y * m.w;
-        s1 += (g0 + g1) + (g2 + g3);
-        s2 += (g0 * xh0 + g1 * xh1) + (g2 * xh2 + g3 * xh3);
+        m.x *= d0.x; m.y *= d0.y; m.z *= d1.x; m.w *= d1.y;  // g = dy * (1 + scale)
+        s1 += (m.x + m.y) + (m.z + m.w);
+        s2 += (m.x * v[j].x + m.y * v[j].y) + (m.z * v[j].z + m.w * v[j].w);
       }
     }
     s1 = warp_sum(s1) / (float)D;
     s2 = warp_sum(s2) / (float)D;
-    float4* o = reinterpret_cast<float4*>(dx + row * D);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int idx = lane + j * 32;
       if (idx < nvec) {
-        const float4 v = __ldg(xr + idx);
-        const uint2 d = __ldg(dr + idx);
-        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
-        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dd[j].x));
+        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dd[j].y));
         float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
         if (scv != nullptr) {
           const float4 sc = __ldg(scv + idx);
           m = make_float4(o1 + sc.x, o1 + sc.y, o1 + sc.z, o1 + sc.w);
         }
         float4 r;
-        r.x = rstd * (d0.x * m.x - s1 - (v.x - mean) * rstd * s2);
-        r.y = rstd * (d0.y * m.y - s1 - (v.y - mean) * rstd * s2);
-        r.z = rstd * (d1.x * m.z - s1 - (v.z - mean) * rstd * s2);
-        r.w = rstd * (d1.y * m.w - s1 - (v.w - mean) * rstd * s2);
-        if (accumulate) {
-          const float4 pz = o[idx];
-          r.x += pz.x; r.y += pz.y; r.z += pz.z; r.w += pz.w;
-        }
+        r.x = rstd * (d0.x * m.x - s1 - v[j].x * s2) + pz[j].x;
+        r.y = rstd * (d0.y * m.y - s1 - v[j].y * s2) + pz[j].y;
+        r.z = rstd * (d1.x * m.z - s1 - v[j].z * s2) + pz[j].z;
+        r.w = rstd * (d1.y * m.w - s1 - v[j].w * s2) + pz[j].w;
         o[idx] = r;
       }
     }
@@ -702,6 +879,13 @@ static int gate_bwd_launch(const float* dx, const void* z_bf16, const float* gat
                            float* dgate, float* dbias, int B, int n, int C, const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(dx && dz_bf16 && B > 0 && n > 0 && C > 0 && (C & 3) == 0 && (gate_bstride & 3) == 0, "f5b_gate_bwd: C and the gate stride must be multiples of 4");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 8.0 * B * n * C);
+  if ((C & 7) == 0 && (gate_bstride & 7) == 0 && B <= 65535) {
+    F5B_CUDA(launch_dep(gate_bwd8_kernel, dim3((n + CS_ROWS - 1) / CS_ROWS, B, (C + CS_COLS - 1) / CS_COLS), dim3(256), 0, ST(stream), 1, dx,
+                        reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16),
+                        dgate, dbias, n, C, dr));
+    F5B_CUDA(cudaGetLastError());
+    return 0;
+  }
   F5B_CUDA(launch_dep(gate_bwd_kernel, dim3((n + CT_ROWS - 1) / CT_ROWS, B), dim3(CT_THREADS), 0, ST(stream), 1, dx,
                       reinterpret_cast<const __nv_bfloat16*>(z_bf16), gate, gate_bstride, lens, reinterpret_cast<__nv_bfloat16*>(dz_bf16),
                       dgate, dbias, n, C, dr));
@@ -728,7 +912,18 @@ int f5b_act_fwd(const void* h_bf16, void* out_bf16, int64_t count, int act, f5b_
 static int act_bwd_launch(const void* du_bf16, const void* h_bf16, void* dh_bf16, float* dbias, int64_t rows, int C, int ld, int act,
                           const Drop dr, f5b_stream_t stream) {
   F5B_CHECK(du_bf16 && rows > 0 && C > 0 && (C & 3) == 0 && (ld & 3) == 0 && ld >= C, "f5b_act_bwd: C and ld must be multiples of 4");
-  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 6.0 * rows * C);
+  LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, (h_bf16 ? 2.0 : 0.0) * rows * C + (dh_bf16 ? 2.0 : 0.0) * rows * C + 2.0 * rows * C);
+  if ((C & 7) == 0 && (ld & 7) == 0) {
+    const dim3 grid((unsigned)((rows + CS_ROWS - 1) / CS_ROWS), (C + CS_COLS - 1) / CS_COLS);
+    auto* du = reinterpret_cast<const __nv_bfloat16*>(du_bf16);
+    auto* hh = reinterpret_cast<const __nv_bfloat16*>(h_bf16);
+    auto* dh = reinterpret_cast<__nv_bfloat16*>(dh_bf16);
+    if (act == F5B_ACT_GELU_TANH) F5B_CUDA(launch_dep(act_bwd8_kernel<F5B_ACT_GELU_TANH>, grid, dim3(256), 0, ST(stream), 1, du, hh, dh, dbias, rows, C, ld, act, dr));
+    else if (act == F5B_ACT_NONE) F5B_CUDA(launch_dep(act_bwd8_kernel<F5B_ACT_NONE>, grid, dim3(256), 0, ST(stream), 1, du, hh, dh, dbias, rows, C, ld, act, dr));
+    else F5B_CUDA(launch_dep(act_bwd8_kernel<-1>, grid, dim3(256), 0, ST(stream), 1, du, hh, dh, dbias, rows, C, ld, act, dr));
+    F5B_CUDA(cudaGetLastError());
+    return 0;
+  }
   F5B_CUDA(launch_dep(act_bwd_kernel, dim3((unsigned)((rows + CT_ROWS - 1) / CT_ROWS)), dim3(CT_THREADS), 0, ST(stream), 1,
                       reinterpret_cast<const __nv_bfloat16*>(du_bf16), reinterpret_cast<const __nv_bfloat16*>(h_bf16),
                       reinterpret_cast<__nv_bfloat16*>(dh_bf16), dbias, rows, C, ld, act, dr));
