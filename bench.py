@@ -736,12 +736,12 @@ def main():
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                         "traffic": None, "peak_source": peak_src, "launches": v["launches"], "avg_launch_ms": v["ms"] / v["launches"]}
 
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if roofline is not None and os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("workload") == args.workload and roofline["kernel"] in tj:
             roofline["traffic"] = tj[roofline["kernel"]]["bytes_per_launch"]
-            roofline["traffic_source"] = "ncu --set full capture, profiles/r01_traffic.json"
+            roofline["traffic_source"] = "ncu --set full capture, profiles/r02_traffic.json"
             roofline["algorithmic_bytes_per_launch"] = prof[roofline["kernel"]]["bytes"] / max(prof[roofline["kernel"]]["launches"], 1)
     total_frames = frames_per_step * args.steps * world
     value = total_frames / (ms * 1e-3)

@@ -416,10 +416,86 @@ class F5TTSWrapper:
             return final_wave, self.target_sample_rate, combined_spectrogram
         return final_wave, self.target_sample_rate
 
+    @L.on_own_device
+    def generate_many(self, texts, nfe_step: Optional[int] = None, cfg_strength: Optional[float] = None,
+                      sway_sampling_coef: Optional[float] = None, speed: Optional[float] = None, fix_duration: Optional[float] = None,
+                      cross_fade_duration: Optional[float] = None, use_duration_predictor: Optional[bool] = None,
+                      seed: Optional[int] = None, return_pcm16: bool = False, max_batch_frames: int = 65536):
+        """Cross-request batcher (no counterpart in the reference, whose servers call `generate` one request at a
+        time): the chunks of ALL `texts` (same voice = this wrapper's preprocessed reference) are sorted by duration and packed into
+        ragged `CFM.sample` batches of at most `max_batch_frames` padded frames (length bucketing bounds the padding waste), vocoded,
+        and cross-faded per request on the GPU.  Returns a list of (wave, sample_rate), float32 or — `return_pcm16` — int16, in the
+        order of `texts`.  Every chunk is sampled exactly as `generate(..., batch_chunks=True)` samples it (same duration rule, same
+        per-item noise for a given seed); only the composition of the batches differs."""
+        from .. import ops
+        if self.ref_audio_processed is None or self.ref_text is None:
+            raise ValueError("Reference audio not preprocessed. Call preprocess_reference() first.")
+        if isinstance(texts, str):
+            raise TypeError("generate_many takes a list of request texts; use generate() for one request")
+        nfe_step = nfe_step if nfe_step is not None else self.nfe_step
+        cfg_strength = cfg_strength if cfg_strength is not None else self.cfg_strength
+        sway_sampling_coef = sway_sampling_coef if sway_sampling_coef is not None else self.sway_sampling_coef
+        speed = speed if speed is not None else self.speed
+        fix_duration = fix_duration if fix_duration is not None else self.fix_duration
+        cross_fade_duration = cross_fade_duration if cross_fade_duration is not None else self.cross_fade_duration
+        use_predictor = use_duration_predictor if use_duration_predictor is not None else self.use_duration_predictor
+        can_use_predictor = bool(use_predictor and self.has_duration_predictor)
+        audio_len = self.ref_audio_processed.shape[-1] / self.target_sample_rate
+        max_chars = int(len(self.ref_text.encode("utf-8")) / audio_len * (22 - audio_len))
+        items = []  # (request, chunk index, chunk text, duration)
+        for r, text in enumerate(texts):
+            chunks = chunk_text(text, max_chars=max_chars)
+            if not chunks:
+                raise RuntimeError(f"No audio generated for request {r}")
+            for ci, tb in enumerate(chunks):
+                items.append((r, ci, tb, int(self._chunk_duration(tb, speed, fix_duration, can_use_predictor))))
+        batches = plan_ragged_batches([it[3] for it in items], max_batch_frames)
+        rms = torch.sqrt(torch.mean(torch.square(self.ref_audio_processed)))
+        cond_frames = self.ref_audio_len + 1
+        waves = [dict() for _ in texts]
+        with torch.inference_mode():
+            for idxs in batches:
+                tbs = [items[i][2] for i in idxs]
+                tx = convert_char_to_pinyin([self.ref_text + tb for tb in tbs])
+                durs = torch.tensor([items[i][3] for i in idxs], dtype=torch.long)
+                generated, _ = self.model.sample(cond=self.ref_audio_processed.expand(len(idxs), -1), text=tx, duration=durs, steps=nfe_step,
+                                                 cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, seed=seed,
+                                                 return_trajectory=False)
+                durs_eff = torch.maximum(durs, torch.tensor([len(t) for t in tx]).clamp(min=cond_frames) + 1)  # cfm.py:132-136
+                for k, i in enumerate(idxs):
+                    g = generated[k:k + 1, : int(min(durs_eff[k], generated.shape[1]))].to(torch.float32)[:, self.ref_audio_len:, :]
+                    wave = self.vocoder.decode(g.permute(0, 2, 1))
+                    if rms < self.target_rms:
+                        wave = wave * rms / self.target_rms
+                    waves[items[i][0]][items[i][1]] = wave.reshape(-1)
+        cfs = int(cross_fade_duration * self.target_sample_rate) if cross_fade_duration > 0 else 0
+        out = []
+        for w in waves:
+            final = ops.crossfade_concat([w[ci] for ci in range(len(w))], cfs)
+            out.append(((ops.pcm16(final) if return_pcm16 else final).cpu().numpy(), self.target_sample_rate))
+        return out
+
     def get_current_audio_length(self):
         if self.ref_audio_processed is None:
             return 0
         return self.ref_audio_processed.shape[-1] / self.target_sample_rate
+
+
+def plan_ragged_batches(durations, max_batch_frames: int):
+    """Length-bucketed packing for the cross-request batcher: items sorted by duration (descending, stable) and cut greedily so that
+    a batch's PADDED size, len(batch) * its longest duration, stays within `max_batch_frames` (a single item longer than the budget
+    is a batch of its own).  Returns lists of item indices; every index appears exactly once."""
+    order = sorted(range(len(durations)), key=lambda i: -int(durations[i]))
+    batches, cur = [], []
+    for i in order:
+        longest = int(durations[cur[0]]) if cur else int(durations[i])
+        if cur and (len(cur) + 1) * longest > max_batch_frames:
+            batches.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        batches.append(cur)
+    return batches
 
 
 def _write_wav(path: str, wave_f32: np.ndarray, sr: int):

@@ -512,3 +512,21 @@ def test_silence_aware_reference_clipping_matches_pydub_rules():
     y = torch.cat([torch.cat((torch.randn(int(2.3 * sr), generator=g) * 0.2, torch.randn(int(0.2 * sr), generator=g) * 0.002)) for _ in range(8)])
     w = clip_reference(y, sr)
     assert 6.0 < len(w) / sr <= 12.0 and len(w) < len(y)
+
+
+def test_plan_ragged_batches_budget_and_coverage():
+    from eraxvif5tts_b200.infer.f5tts_wrapper import plan_ragged_batches
+    import random
+    rnd = random.Random(3)
+    durs = [rnd.randint(300, 1900) for _ in range(57)] + [5000]
+    batches = plan_ragged_batches(durs, 8000)
+    flat = sorted(i for b in batches for i in b)
+    assert flat == list(range(len(durs)))                       # every item exactly once
+    for b in batches:
+        longest = max(durs[i] for i in b)
+        assert len(b) == 1 or len(b) * longest <= 8000          # padded size within the budget
+        assert durs[b[0]] == longest                            # sorted: the first item is the longest
+    # bucketing bounds the padding waste: padded frames within 25 % of the real ones for this spread
+    padded = sum(len(b) * max(durs[i] for i in b) for b in batches)
+    assert padded <= 1.25 * sum(durs)
+    assert plan_ragged_batches([], 100) == [] and plan_ragged_batches([7], 1) == [[0]]
