@@ -183,7 +183,7 @@ def set_dependent_launch(on: bool) -> None:
         load().f5b_set_dependent_launch(int(bool(on)))
 
 
-KERNEL_KINDS = ("gemm", "attention", "convpos", "norm", "elementwise", "spectral")
+KERNEL_KINDS = ("gemm", "attention", "convpos", "norm", "elementwise", "spectral", "vocos")
 
 
 def prof_reset(enable: bool) -> None:

@@ -73,7 +73,14 @@ inline cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py's roofline leg) ------------------------
-enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_CONVPOS = 2, K_NORM = 3, K_ELEMENTWISE = 4, K_SPECTRAL = 5, K_NUM = 6 };
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_CONVPOS = 2, K_NORM = 3, K_ELEMENTWISE = 4, K_SPECTRAL = 5, K_VOCOS = 6, K_NUM = 7 };
+// While alive, every LaunchScope is accounted under `kind` instead of its own class (f5b_vocos_decode: the vocoder's GEMMs and
+// LayerNorm sweeps are reported as the class "vocos", not folded into the DiT's gemm / norm classes).
+struct KindOverride {
+  int prev;
+  explicit KindOverride(int kind);
+  ~KindOverride();
+};
 // RAII: counts the launch(es) of one host-side launcher and, when profiling is on, brackets them with events on `s`.
 struct LaunchScope {
   int kind;

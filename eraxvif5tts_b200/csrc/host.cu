@@ -126,7 +126,12 @@ struct ProfState {
 static ProfState g_prof;
 static std::mutex g_prof_mu;
 
+static thread_local int g_kind_override = -1;
+KindOverride::KindOverride(int kind) : prev(g_kind_override) { g_kind_override = kind; }
+KindOverride::~KindOverride() { g_kind_override = prev; }
+
 LaunchScope::LaunchScope(int kind_, cudaStream_t s_, double fl, double by, int n) : kind(kind_), s(s_), slot(-1) {
+  if (g_kind_override >= 0 && kind != K_SPECTRAL) kind = g_kind_override;  // (the iSTFT stays in "spectral")
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.launches[kind] += n;
   g_prof.flops[kind] += fl;

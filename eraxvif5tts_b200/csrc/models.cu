@@ -309,6 +309,7 @@ int f5b_vocos_decode(const F5bVocos* h, const float* mel, int B, int T, float* w
   VocosWs w = carve_vocos(d, B, T, ws);
   F5B_CHECK(w.bytes <= ws_bytes, "f5b_vocos_decode: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   cudaStream_t s = ST(stream);
+  KindOverride as_vocos(K_VOCOS);
   const int rows = B * T, C = d.dim, I = d.intermediate;
   // backbone.embed Conv1d(n_mels, C, k=7, pad 3) as im2col + GEMM, then backbone.norm
   F5B_TRY(f5b_im2col7(mel, w.a, B, T, d.n_mels, d.ld_embed, stream));
