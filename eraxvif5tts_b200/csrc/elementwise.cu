@@ -194,29 +194,59 @@ int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w
 // GRN  model/modules.py:225-234: Gx = ||h||_2 over the SEQUENCE axis, Nx = Gx / (mean_c Gx + 1e-6),
 // out = gamma * (h * Nx) + beta + h.   Pass 1: deterministic column norms; pass 2: apply.
 // ---------------------------------------------------------------------------------------------------------------
+// CTA = 128 channels x all rows of one batch item: 16 column lanes x 16 row lanes, 8 channels per thread, 4 rows in flight
+// (round 2: the 2-channel / 4-row-lane form ran one dependent load stream per thread, 0.7 TB/s).
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 template <class T>
 __global__ void __launch_bounds__(256) grn_colnorm_kernel(const T* __restrict__ h, float* __restrict__ gx, int n, int C) {
-  // block: 64 channel pairs (128 channels) x 4 row lanes; grid (ceil(C/128), B)
-  __shared__ float red[4][128];
-  const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int c = blockIdx.x * 128 + cp * 2;
+  __shared__ float red[16][128 + 4];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c = blockIdx.x * 128 + cl * 8;
   const int b = blockIdx.y;
-  float s0 = 0.f, s1 = 0.f;
+  float q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = 0.f;
   if (c < C) {
     const T* base = h + (size_t)b * n * C + c;
-    for (int r = rl; r < n; r += 4) {
-      const float2 v = load2(base + (size_t)r * C);
-      s0 += v.x * v.x;
-      s1 += v.y * v.y;
+    for (int r0 = rl; r0 < n; r0 += 64) {
+      float v[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = r0 + 16 * k;
+        if (row < n) load8(base + (size_t)row * C, v[k]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = fmaf(v[k][i], v[k][i], q[i]);
     }
   }
-  red[rl][cp * 2] = s0;
-  red[rl][cp * 2 + 1] = s1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][cl * 8 + i] = q[i];
   __syncthreads();
   if (threadIdx.x < 128) {
     const int cc = blockIdx.x * 128 + threadIdx.x;
     if (cc < C) {
-      const float t = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t += red[j][threadIdx.x];
       gx[(size_t)b * C + cc] = sqrtf(t);
     }
   }
@@ -270,7 +300,7 @@ static int grn_t(const T* h, const float* gamma, const float* beta, T* out, floa
 }
 
 int grn(const void* h, const float* gamma, const float* beta, void* out, float* ws, int B, int n, int C, cudaStream_t s, bool tf32) {
-  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 1) == 0, "f5b_grn: C=%d must be even", C);
+  F5B_CHECK(B > 0 && n > 0 && C > 0 && (C & 7) == 0, "f5b_grn: C=%d must be a multiple of 8", C);
   LaunchScope scope(K_ELEMENTWISE, s, 0, (tf32 ? 12.0 : 6.0) * B * n * C, 2);
   if (tf32) return grn_t(reinterpret_cast<const float*>(h), gamma, beta, reinterpret_cast<float*>(out), ws, B, n, C, s);
   return grn_t(reinterpret_cast<const __nv_bfloat16*>(h), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), ws, B, n, C, s);

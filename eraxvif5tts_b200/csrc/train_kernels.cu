@@ -592,32 +592,60 @@ __global__ void distill_grad_kernel(const float* __restrict__ pred, const float*
 // t3 = gamma * t2 * nx + beta + t2,  nx[b,c] = gx[b,c] / (mean_c gx[b,:] + 1e-6),  gx[b,c] = ||t2[b,:,c]||_2,  t2 = gelu(p1)
 // stats[b][0..2][C]: pass 1 writes (sum t2^2, sum dt3*t2, sum dt3); the per-batch-row kernel turns them into (mult, coef):
 //   dt2 = dt3 * mult + t2 * coef,  mult = gamma*nx + 1,  coef = (gamma*S/(m+eps) - A) / gx,  A = mean_c(gamma*S*gx) / (m+eps)^2
+// CTA = 128 channels x all rows of one batch item: 16 column lanes (8 channels = 16 bytes each) x 16 row lanes, 4 rows in flight per
+// thread (round 2: the 4-byte / 4-row-lane form had 256 CTAs with one dependent load stream per thread and ran at 1.1 TB/s).
 __global__ void __launch_bounds__(256) grn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ d3, const __nv_bfloat16* __restrict__ t2,
                                                             float* __restrict__ stats, int n, int C) {
-  __shared__ float red[3][4][128];
-  const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int c = blockIdx.x * 128 + cp * 2;
+  __shared__ float red[3][16][128 + 4];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c = blockIdx.x * 128 + cl * 8;
   const int b = blockIdx.y;
-  float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f, r0 = 0.f, r1 = 0.f;
-  if (c < C) {
+  float q[8], sd[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = sd[i] = r[i] = 0.f;
+  if (c < C) {  // (C is a multiple of 8: checked by the launcher)
     const size_t base = (size_t)b * n * C + c;
-    for (int r = rl; r < n; r += 4) {
-      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(t2 + base + (size_t)r * C));
-      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d3 + base + (size_t)r * C));
-      q0 = fmaf(t.x, t.x, q0); q1 = fmaf(t.y, t.y, q1);
-      s0 = fmaf(d.x, t.x, s0); s1 = fmaf(d.y, t.y, s1);
-      r0 += d.x; r1 += d.y;
+    for (int r0 = rl; r0 < n; r0 += 64) {
+      uint4 tv[4], dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = r0 + 16 * k;
+        if (row < n) {
+          tv[k] = *reinterpret_cast<const uint4*>(t2 + base + (size_t)row * C);
+          dv[k] = *reinterpret_cast<const uint4*>(d3 + base + (size_t)row * C);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (r0 + 16 * k < n) {
+          float t[8], d[8];
+          bf8_to_f32(tv[k], t);
+          bf8_to_f32(dv[k], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            q[i] = fmaf(t[i], t[i], q[i]);
+            sd[i] = fmaf(d[i], t[i], sd[i]);
+            r[i] += d[i];
+          }
+        }
+      }
     }
   }
-  red[0][rl][cp * 2] = q0; red[0][rl][cp * 2 + 1] = q1;
-  red[1][rl][cp * 2] = s0; red[1][rl][cp * 2 + 1] = s1;
-  red[2][rl][cp * 2] = r0; red[2][rl][cp * 2 + 1] = r1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[0][rl][cl * 8 + i] = q[i];
+    red[1][rl][cl * 8 + i] = sd[i];
+    red[2][rl][cl * 8 + i] = r[i];
+  }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int cc = blockIdx.x * 128 + threadIdx.x;
-    if (cc < C)
-      for (int k = 0; k < 3; ++k)
-        stats[((size_t)b * 3 + k) * C + cc] = red[k][0][threadIdx.x] + red[k][1][threadIdx.x] + red[k][2][threadIdx.x] + red[k][3][threadIdx.x];
+  for (int t = threadIdx.x; t < 3 * 128; t += 256) {
+    const int k = t / 128, cc = t - k * 128;
+    if (blockIdx.x * 128 + cc < C) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a += red[k][j][cc];
+      stats[((size_t)b * 3 + k) * C + blockIdx.x * 128 + cc] = a;
+    }
   }
 }
 
@@ -697,33 +725,59 @@ __global__ void __launch_bounds__(CT_THREADS) grn_bwd_apply_kernel(const __nv_bf
 }
 
 // depth-wise Conv1d(k=7, pad 3) backward: dx[b,p,c] += sum_k w[c,k] dy[b,p-k+3,c];  dw[c,k] += sum dy[b,p,c] x[b,p+k-3,c];  db[c] += sum dy
-__global__ void __launch_bounds__(256) dwconv7_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+// thread = 4 adjacent channels (16-byte accesses), 64 rows per CTA walked with register SLIDING WINDOWS of dy and x (7 rows each):
+// one new row of each per step instead of 14 reloads through L1 (round 2; the scalar form ran 315 us for 315 MB).
+__global__ void __launch_bounds__(128) dwconv7_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                                                           float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int n, int C) {
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * CT_ROWS, p1 = min(n, p0 + CT_ROWS);
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float wk[7], aw[7];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = (blockIdx.z * 128 + threadIdx.x) * 4; c < C; c += 4 * 128 * gridDim.z) {
+    float wk[4][7], aw[4][7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) { wk[k] = __ldg(w + (size_t)c * 7 + k); aw[k] = 0.f; }
-    float ab = 0.f;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { wk[j][k] = __ldg(w + (size_t)(c + j) * 7 + k); aw[j][k] = 0.f; }
+    float4 ab = zero;
     const size_t base = (size_t)b * n * C + c;
+    auto ld = [&](const float* ptr, int row) { return (row >= 0 && row < n) ? *reinterpret_cast<const float4*>(ptr + base + (size_t)row * C) : zero; };
+    // windows: gw[i] = dy[p - 3 + i], xw[i] = x[p - 3 + i]
+    float4 gw[7], xw[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { gw[i] = ld(dy, p0 - 3 + i); xw[i] = ld(x, p0 - 3 + i); }
     for (int p = p0; p < p1; ++p) {
-      const float g = dy[base + (size_t)p * C];
-      ab += g;
-      float acc = 0.f;
+      const float4 gn = ld(dy, p + 4), xn = ld(x, p + 4);  // next step's new rows: issued before this step's math
+      const float4 g = gw[3];
+      ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+      float4 acc = zero;
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        const int q = p + k - 3;   // x position paired with dy[p] under tap k
-        if (q >= 0 && q < n) aw[k] = fmaf(g, x[base + (size_t)q * C], aw[k]);
-        const int r = p - k + 3;   // dy position that reaches x[p] through tap k
-        if (r >= 0 && r < n) acc = fmaf(wk[k], dy[base + (size_t)r * C], acc);
+        // dw[c,k] += dy[p] * x[p + k - 3]   (rows outside the utterance are zero in the window)
+        aw[0][k] = fmaf(g.x, xw[k].x, aw[0][k]); aw[1][k] = fmaf(g.y, xw[k].y, aw[1][k]);
+        aw[2][k] = fmaf(g.z, xw[k].z, aw[2][k]); aw[3][k] = fmaf(g.w, xw[k].w, aw[3][k]);
+        // dx[p] += w[c,k] * dy[p - k + 3]
+        const float4 gr = gw[6 - k];
+        acc.x = fmaf(wk[0][k], gr.x, acc.x); acc.y = fmaf(wk[1][k], gr.y, acc.y);
+        acc.z = fmaf(wk[2][k], gr.z, acc.z); acc.w = fmaf(wk[3][k], gr.w, acc.w);
       }
-      dx[base + (size_t)p * C] += acc;
-    }
-    if (dw)
+      float4* o = reinterpret_cast<float4*>(dx + base + (size_t)p * C);
+      float4 cur = *o;
+      cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+      *o = cur;
 #pragma unroll
-      for (int k = 0; k < 7; ++k) atomicAdd(dw + (size_t)c * 7 + k, aw[k]);
-    if (db) atomicAdd(db + c, ab);
+      for (int i = 0; i < 6; ++i) { gw[i] = gw[i + 1]; xw[i] = xw[i + 1]; }
+      gw[6] = gn;
+      xw[6] = xn;
+    }
+    if (dw) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) atomicAdd(dw + (size_t)(c + j) * 7 + k, aw[j][k]);
+    }
+    if (db) {
+      atomicAdd(db + c, ab.x); atomicAdd(db + c + 1, ab.y); atomicAdd(db + c + 2, ab.z); atomicAdd(db + c + 3, ab.w);
+    }
   }
 }
 
@@ -1000,8 +1054,8 @@ int f5b_ln_affine_bwd(const void* dy_bf16, const float* x, const float* w, float
 
 int f5b_grn_gelu_bwd(const void* dt3_bf16, const void* t2_bf16, const void* p1_bf16, const float* gamma, void* dp1_bf16, float* dgamma,
                      float* dbeta, float* dbias1, float* stats_ws, int B, int n, int C, f5b_stream_t stream) {
-  F5B_CHECK(dt3_bf16 && t2_bf16 && p1_bf16 && gamma && dp1_bf16 && stats_ws && B > 0 && n > 0 && C > 0 && (C & 1) == 0,
-            "f5b_grn_gelu_bwd: bad argument");
+  F5B_CHECK(dt3_bf16 && t2_bf16 && p1_bf16 && gamma && dp1_bf16 && stats_ws && B > 0 && n > 0 && C > 0 && (C & 7) == 0,
+            "f5b_grn_gelu_bwd: bad argument (C must be a multiple of 8)");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 12.0 * B * n * C, 3);
   auto* d3 = reinterpret_cast<const __nv_bfloat16*>(dt3_bf16);
   auto* t2 = reinterpret_cast<const __nv_bfloat16*>(t2_bf16);
@@ -1017,9 +1071,9 @@ int f5b_grn_gelu_bwd(const void* dt3_bf16, const void* t2_bf16, const void* p1_b
 
 int f5b_dwconv7_bwd(const float* dy, const float* x, const float* w, float* dx_accum, float* dw, float* db, int B, int n, int C,
                     f5b_stream_t stream) {
-  F5B_CHECK(dy && x && w && dx_accum && B > 0 && n > 0 && C > 0, "f5b_dwconv7_bwd: bad argument");
+  F5B_CHECK(dy && x && w && dx_accum && B > 0 && n > 0 && C > 0 && (C & 3) == 0, "f5b_dwconv7_bwd: bad argument (C must be a multiple of 4)");
   LaunchScope scope(K_ELEMENTWISE, ST(stream), 0, 16.0 * B * n * C);
-  dwconv7_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B), 256, 0, ST(stream)>>>(dy, x, w, dx_accum, dw, db, n, C);
+  dwconv7_bwd_kernel<<<dim3((n + CT_ROWS - 1) / CT_ROWS, B, (C / 4 + 127) / 128), 128, 0, ST(stream)>>>(dy, x, w, dx_accum, dw, db, n, C);
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
