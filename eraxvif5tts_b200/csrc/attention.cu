@@ -124,9 +124,15 @@ __device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
   return m;
 }
 
+// SPLIT = 2 (small grids, e.g. the B = 1 serving shape: 8 query tiles x 32 batch-heads = 256 CTAs for 444 resident slots, each walking
+// all 15 key tiles serially): the key range of a query tile is cut in two, the two halves run as a CLUSTER of 2 CTAs, and rank 1
+// hands its un-normalised (O, m, l) to rank 0 through distributed shared memory, which merges and writes — flash-decoding's split-KV
+// without a workspace or a combine kernel.  SPLIT = 1 compiles to the single-CTA kernel.
+template <int SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  static_assert(SPLIT == 1 || (SPLIT == 2 && !ATT_P_TMEM), "split-KV is built for two halves on the shared-memory P path");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -151,7 +157,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BQ;
+  const int q0 = (SPLIT > 1 ? blockIdx.x / SPLIT : blockIdx.x) * ATT_BQ;
+  const uint32_t srank = SPLIT > 1 ? cluster_ctarank() : 0u;  // which half of the key range (cluster = SPLIT CTAs along x)
   const int bh = blockIdx.y;
   const int b = bh / p.H;
   const int h = bh - b * p.H;
@@ -173,7 +180,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     return;
   }
-  const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
+  const int T_all = (kvlen + ATT_BKV - 1) / ATT_BKV;
+  int t_begin = 0, T = T_all;  // this CTA's key tiles: [t_begin, t_begin + T)
+  if constexpr (SPLIT > 1) {
+    const int per = (T_all + SPLIT - 1) / SPLIT;
+    t_begin = (int)srank * per;
+    T = max(0, min(T_all, t_begin + per) - t_begin);  // may be empty for rank 1 when there is a single key tile
+  }
 
   if (warp == 4) {
     if (lane == 0) {
@@ -204,17 +217,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   griddep_launch_dependents();
 
   if (warp == 4) {
-    if (elect_one()) {  // (not `lane == 0`: see tile_engine.cuh — ptxas emits plain tcgen05 / TMA sequences in an elected region)
+    if (T > 0 && elect_one()) {  // (not `lane == 0`: see tile_engine.cuh — ptxas emits plain tcgen05 / TMA sequences in an elected region)
       const uint32_t idesc = idesc_bf16(128, 64, 0, 0);     // S = Q K^T: both operands K-major
       const uint32_t idesc_pv = idesc_bf16(128, 64, 0, 1);  // O += P V: V is MN-major (d contiguous, keys strided)
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
       auto load_k = [&](int j) {
         mbar_arrive_expect_tx(&bar_k[j & 1], ATT_K_BYTES);
-        tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], h * 64, j * ATT_BKV, b);
+        tma_load_3d(sK + (j & 1) * ATT_K_BYTES, &tmK, &bar_k[j & 1], h * 64, (t_begin + j) * ATT_BKV, b);
       };
       auto load_v = [&](int j) {
         mbar_arrive_expect_tx(bar_v, ATT_V_BYTES);
-        tma_load_3d(sV, &tmV, bar_v, h * 64, j * ATT_BKV, b);
+        tma_load_3d(sV, &tmV, bar_v, h * 64, (t_begin + j) * ATT_BKV, b);
       };
       auto issue_s = [&](int j) {
         mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
@@ -296,7 +309,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     for (int j = 0; j < T; ++j) {
       uint8_t* p_row = sP + (j & 1) * ATT_P_BYTES + r * 128;
-      const int valid = min(ATT_BKV, kvlen - j * ATT_BKV);  // CTA-uniform, >= 1
+      const int valid = min(ATT_BKV, kvlen - (t_begin + j) * ATT_BKV);  // CTA-uniform, >= 1
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       ATT_MARK(0)
@@ -408,30 +421,98 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 #endif
     // epilogue: O / l
-    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
-    tc_fence_after();
     const int pos = q0 + r;
-    const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
-    if (p.lse != nullptr && pos < p.n) p.lse[(size_t)bh * p.n + pos] = (pos < kvlen) ? m_used + log2f(l_run) : INFINITY;
-    __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
+    if constexpr (SPLIT == 1) {
+      mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
+      tc_fence_after();
+      const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
+      if (p.lse != nullptr && pos < p.n) p.lse[(size_t)bh * p.n + pos] = (pos < kvlen) ? m_used + log2f(l_run) : INFINITY;
+      __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_addr + c * 32, o);
-      tmem_ld_wait();
-      if (pos < p.n) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+        tmem_ld_wait();
+        if (pos < p.n) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
-          pk.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
-          pk.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
-          pk.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = pk;
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            pk.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            pk.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            pk.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            reinterpret_cast<uint4*>(orow + c * 32)[q] = pk;
+          }
         }
       }
+    } else {
+      // the tile buffers (Q, K, V, P: 72 KB from `smem`) are dead once the last product has retired: rank 1 parks its partial there,
+      // column-major [64][128] so that the 128 row-threads store and load without bank conflicts, then (m, l)
+      float* xo = reinterpret_cast<float*>(smem);
+      float* xm = xo + 64 * ATT_BQ;
+      float* xl = xm + ATT_BQ;
+      if (T > 0) {
+        mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      uint32_t o0[32], o1[32];
+      if (T > 0) {
+        tmem_ld32(tmem_O + lane_addr, o0);
+        tmem_ld32(tmem_O + lane_addr + 32, o1);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o0[i] = o1[i] = 0u;
+      }
+      if (srank == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          xo[i * ATT_BQ + r] = __uint_as_float(o0[i]);
+          xo[(32 + i) * ATT_BQ + r] = __uint_as_float(o1[i]);
+        }
+        xm[r] = m_used;
+        xl[r] = l_run;
+      }
+      cluster_sync_all();  // (warp 4 takes part below) rank 1's partial is visible cluster-wide
+      if (srank == 0) {
+        const uint32_t ro = mapa_u32(xo, 1), rm = mapa_u32(xm, 1), rl = mapa_u32(xl, 1);
+        const float m1 = ld_shared_cluster_f32(rm + r * 4), l1 = ld_shared_cluster_f32(rl + r * 4);
+        const float m = fmaxf(m_used, m1);  // rank 0 always owns >= 1 key tile, so m is finite
+        const float f0 = ex2_approx(m_used - m), f1 = (l1 > 0.f) ? ex2_approx(m1 - m) : 0.f;
+        const float l = l_run * f0 + l1 * f1;
+        const float inv = (pos < kvlen) ? 1.f / l : 0.f;
+        const float a0 = f0 * inv, a1 = f1 * inv;
+        __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float mine = __uint_as_float(c == 0 ? o0[i] : o1[i]);
+            v[i] = mine * a0 + ld_shared_cluster_f32(ro + (uint32_t)(((c * 32 + i) * ATT_BQ + r) * 4)) * a1;
+          }
+          if (pos < p.n) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              reinterpret_cast<uint4*>(orow + c * 32)[q] = pk;
+            }
+          }
+        }
+      }
+      cluster_sync_all();  // rank 1's shared memory stays alive until rank 0 has read it
     }
     tc_fence_before();
+  }
+  if constexpr (SPLIT > 1) {
+    if (warp == 4) {  // the cluster barrier counts every thread of both CTAs
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -442,6 +523,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 long long* g_attn_trace = nullptr;
+int g_attn_split = [] { const char* e = getenv("F5B_ATTN_SPLIT"); return e ? atoi(e) : 0; }();  // 1: split-KV wherever it is allowed
 int g_attn_variant = 0;  // 0: this file; 1: the experimental persistent kernel (attention_fa.cu, only in F5B_WITH_ATTN_FA builds)
 #ifdef F5B_WITH_ATTN_FA
 int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B,
@@ -465,7 +547,10 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, ATT_BKV, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
-    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+#if !ATT_P_TMEM
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+#endif
     configured = true;
   }
   AttnParams p;
@@ -479,7 +564,18 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
-  F5B_CUDA(launch_dep(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
+#if !ATT_P_TMEM
+  // split-KV (see the kernel's header) is OPT-IN: F5B_ATTN_SPLIT=1 / f5b_debug_attn_split(1).  Measured on the shape it was built
+  // for (cfg-1: 8 x 32 CTAs, 15 key tiles): attention 16.4 -> 21.9 ms per utterance, the step 68.0 -> 69.7 ms — the cluster
+  // co-scheduling and the distributed-shared-memory merge cost more than the halved key loop saves, so it is not used by default.
+  if (lse == nullptr && n >= 4 * ATT_BKV && g_attn_split == 1) {
+    grid.x *= 2;
+    F5B_CUDA(launch_dep(attn_fwd_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 2, tmQ, tmK, tmV, p));
+    F5B_CUDA(cudaGetLastError());
+    return 0;
+  }
+#endif
+  F5B_CUDA(launch_dep(attn_fwd_kernel<1>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -498,6 +594,7 @@ extern "C" int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }
 extern "C" void f5b_debug_attn_variant(int v) { f5b::g_attn_variant = v; }
+extern "C" void f5b_debug_attn_split(int v) { f5b::g_attn_split = v; }
 #ifndef F5B_WITH_ATTN_FA
 extern "C" void f5b_debug_attn_poly(int) {}
 #endif

@@ -198,6 +198,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {  // address from mapa_u32()
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
 // TMA stores (smem -> global), bulk-group completion.  `reduce_add` accumulates in L2 (f32): x += tile without reading x.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
