@@ -436,8 +436,11 @@ def measure_train(args, wname, cfg, B, n, desc, rank, local_rank, world, dev, st
     model, _ = build_product_models(cfg, dev)
     train_dropout = float(os.environ.get("F5B_TRAIN_DROPOUT", "0"))  # cfg-5 is quoted at dropout 0 (parity setting); 0.1 = the reference's training default
     ckpt = os.environ.get("F5B_TRAIN_CHECKPOINT", "0") == "1"  # the reference's checkpoint_activations option (dit.py:221-223)
-    eng = TrainEngine(model, with_ema=(rank == 0), dropout=train_dropout, checkpoint_activations=ckpt)  # EMA only on the main process (trainer.py:179-181)
+    attn_dropout = float(os.environ.get("F5B_TRAIN_ATTN_DROPOUT", "0"))  # SDPA's own dropout (modules.py:490 hard-codes 0.1); 0 = parity setting
+    eng = TrainEngine(model, with_ema=(rank == 0), dropout=train_dropout, checkpoint_activations=ckpt,
+                      attn_dropout=attn_dropout)  # EMA only on the main process (trainer.py:179-181)
     config["dropout"] = train_dropout
+    config["attn_dropout"] = attn_dropout
     config["checkpoint_activations"] = ckpt
     if train_dropout > 0:
         config["workload"] = config["workload"].replace("dropout 0", f"dropout {train_dropout:g} (FeedForward + to_out sites)")

@@ -18,6 +18,7 @@
 //   K lives in a 2-stage TMA ring, V in one stage (its reload hides behind the next tile's softmax).  Key-padding is a per-batch
 //   length bound: KV tiles past len[b] are never loaded, the last tile is masked by index.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "f5b_internal.h"
 
 namespace f5b {
@@ -50,11 +51,17 @@ struct AttnParams {
   int lens_mod, B, H, n;
   float scale_log2;
   long long* trace;  // debug only (ATT_TRACE builds)
+  Drop dr;           // DROP kernels: mask stream of this layer's SDPA dropout (model/modules.py:490)
+  int n4;            // ceil(n / 4): mask groups per (batch, head, query) row
 };
 
-// P chunk: 32 columns -> exp2 -> bf16 -> swizzled smem row; returns the chunk's row-sum contribution
-template <bool MASKED>
-__device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx) {
+// P chunk: 32 columns -> exp2 -> bf16 -> swizzled smem row; returns the chunk's row-sum contribution.
+// DROP: the probabilities that go into P.V are multiplied by the dropout mask (0 or 1/(1-p)) of their (row, key) element, while the
+// row sum keeps the un-dropped values — dropout acts on the NORMALISED probabilities (torch SDPA semantics).  g0 = mask group of
+// the chunk's first key (4 keys per group).
+template <bool MASKED, bool DROP = false>
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx,
+                                               const Drop* dr = nullptr, uint64_t g0 = 0) {
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -69,6 +76,13 @@ __device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl
     }
     sum0 += (e[0] + e[1]) + (e[2] + e[3]);
     sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+    if constexpr (DROP) {
+      float m0[4], m1[4];
+      drop_mult4(*dr, (g0 + q * 2) << 2, m0);
+      drop_mult4(*dr, (g0 + q * 2 + 1) << 2, m1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { e[i] *= m0[i]; e[4 + i] *= m1[i]; }
+    }
     uint4 pk;
     pk.x = pack_bf16(e[0], e[1]);
     pk.y = pack_bf16(e[2], e[3]);
@@ -128,11 +142,12 @@ __device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
 // all 15 key tiles serially): the key range of a query tile is cut in two, the two halves run as a CLUSTER of 2 CTAs, and rank 1
 // hands its un-normalised (O, m, l) to rank 0 through distributed shared memory, which merges and writes — flash-decoding's split-KV
 // without a workspace or a combine kernel.  SPLIT = 1 compiles to the single-CTA kernel.
-template <int SPLIT>
+template <int SPLIT, bool DROP = false>
 __global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   static_assert(SPLIT == 1 || (SPLIT == 2 && !ATT_P_TMEM), "split-KV is built for two halves on the shared-memory P path");
+  static_assert(!DROP || (SPLIT == 1 && !ATT_P_TMEM), "attention dropout is built for the single-CTA shared-memory P path");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -365,12 +380,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // bar_s(j) was committed after P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing
       // thread), so the P buffer (j & 1) is free.  Exponentials are speculative w.r.t. this tile's maximum (see header).
       float ts;
+      // mask group of this tile's first key in this thread's (batch, head, query) row
+      const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n4 + (uint64_t)((t_begin + j) * (ATT_BKV / 4)) : 0;
       if (valid == ATT_BKV) {
-        ts = softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
-        ts += softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
+        ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
+        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 8);
       } else {
-        ts = softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
-        ts += softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
+        ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
+        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 8);
       }
       ATT_MARK(2)
       // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
@@ -396,11 +413,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
           if (valid == ATT_BKV) {
-            ts = softmax_chunk<false>(s0, sl2, m_used, 32, p_row, 0, rx);
-            ts += softmax_chunk<false>(s1, sl2, m_used, 32, p_row, 4, rx);
+            ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
+            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 8);
           } else {
-            ts = softmax_chunk<true>(s0, sl2, m_used, valid, p_row, 0, rx);
-            ts += softmax_chunk<true>(s1, sl2, m_used, valid - 32, p_row, 4, rx);
+            ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
+            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 8);
           }
         }
       }
@@ -531,7 +548,7 @@ int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, 
 #endif
 
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
-             int n, float scale, cudaStream_t stream) {
+             int n, float scale, cudaStream_t stream, const Drop* drop) {
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
@@ -550,6 +567,7 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
     F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
 #if !ATT_P_TMEM
     F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
 #endif
     configured = true;
   }
@@ -563,8 +581,15 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.n = n;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
+  p.dr = drop ? *drop : Drop{0u, 1.f, 0ull};
+  p.n4 = (n + 3) / 4;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
 #if !ATT_P_TMEM
+  if (p.dr.thr16 != 0) {  // SDPA dropout (training): the forward's mask is regenerated by attn_bwd from the same Drop
+    F5B_CUDA(launch_dep(attn_fwd_kernel<1, true>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
+    F5B_CUDA(cudaGetLastError());
+    return 0;
+  }
   // split-KV (see the kernel's header) is OPT-IN: F5B_ATTN_SPLIT=1 / f5b_debug_attn_split(1).  Measured on the shape it was built
   // for (cfg-1: 8 x 32 CTAs, 15 key tiles): attention 16.4 -> 21.9 ms per utterance, the step 68.0 -> 69.7 ms — the cluster
   // co-scheduling and the distributed-shared-memory merge cost more than the halved key loop saves, so it is not used by default.
@@ -584,12 +609,12 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
 
 extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod,
                             int B, int H, int n, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, v, ld, out, nullptr, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
+  return f5b::attn_fwd(q, k, v, ld, out, nullptr, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 extern "C" int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens,
                                 int lens_mod, int B, int H, int n, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream));
+  return f5b::attn_fwd(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }

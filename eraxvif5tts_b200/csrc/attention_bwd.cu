@@ -21,6 +21,7 @@
 // dK and dV leave as bf16 straight into the dQKV matrix the QKV dgrad/wgrad GEMMs consume (RoPE's transpose applied to dK on the
 // way out); dQ is accumulated across the key-tile CTAs in fp32 and converted (+ RoPE transpose) by attn_dq_finish_kernel.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "f5b_internal.h"
 
 namespace f5b {
@@ -45,12 +46,17 @@ struct AttnBwdParams {
   const float* rope;    // [n, 32] (cos, sin)
   int rope_heads;
   long long* trace;     // debug only (AB_TRACE builds)
+  Drop dr;              // DROP kernels: the forward's SDPA dropout mask stream (regenerated here, never stored)
+  int n4;               // ceil(n / 4)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// DROP: the forward multiplied the normalised probabilities by a mask m (0 or 1/(1-p)) before P.V, so
+//   dV = (P . m)^T dO,   dS = scale * P . (m . dP - delta)   with delta = rowsum(dO . O) of the dropped forward's O.
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -311,7 +317,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 4; ++i) {
             const int e = q4 * 4 + i;
             pv[i] = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
-            dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]), sc, -dls[i]);
+            if constexpr (DROP) {
+              // element (query, key) of this (batch, head): mask group = 4 consecutive keys of one query row
+              const uint64_t qrow = (uint64_t)bh * p.n + (uint64_t)(j * AB_T + ch * 64 + c * 32 + e);
+              const float m = drop_mult1(p.dr, drop_hash(p.dr.key, qrow * p.n4 + (uint64_t)((k0 + r) >> 2)), (k0 + r) & 3);
+              dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]) * m, sc, -dls[i]);
+              pv[i] *= m;  // P^T that feeds dV is the dropped one
+            } else {
+              dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]), sc, -dls[i]);
+            }
           }
           ppk[c * 16 + q4 * 2] = pack_bf16(pv[0], pv[1]);
           ppk[c * 16 + q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
@@ -466,7 +480,7 @@ long long* g_attn_bwd_trace = nullptr;
 
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
-             const float* rope, int rope_heads, cudaStream_t stream) {
+             const float* rope, int rope_heads, cudaStream_t stream, const Drop* drop) {
   F5B_CHECK(q && k && v && out && dout && lse && delta && dq_ws && dqkv, "f5b_attn_bwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0 && ld_o >= H * 64 && (ld_o & 7) == 0 && ld_d >= 3 * H * 64 && (ld_d & 7) == 0,
             "f5b_attn_bwd: bad shape B %d H %d n %d ld %d ld_o %d ld_d %d", B, H, n, ld, ld_o, ld_d);
@@ -487,7 +501,8 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   if (make_tmap_3d(&tmdQ, dq_ws, 4, hw, (uint64_t)n, (uint64_t)B, hw * 4, (uint64_t)n * hw * 4, 32, 32, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
-    F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
+    F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
+    F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
     configured = true;
   }
   AttnBwdParams p;
@@ -506,8 +521,11 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.rope = rope;
   p.rope_heads = rope_heads;
   p.trace = g_attn_bwd_trace;
+  p.dr = drop ? *drop : Drop{0u, 1.f, 0ull};
+  p.n4 = (n + 3) / 4;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
-  F5B_CUDA(launch_dep(attn_bwd_kernel, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  if (p.dr.thr16 != 0) F5B_CUDA(launch_dep(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  else F5B_CUDA(launch_dep(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
   F5B_CUDA(cudaGetLastError());
   const long long items = rows * (D >> 3);
   attn_dq_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(dq_ws, p.dqkv, ld_d, rope, rope_heads, rows, n, D);

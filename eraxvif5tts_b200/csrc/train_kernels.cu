@@ -5,33 +5,12 @@
 // for the few thousand column sums).
 #include "common.cuh"
 #include "f5b_internal.h"
+#include "dropout.cuh"
 
 namespace f5b {
 
 constexpr int CT_ROWS = 64;     // rows per CTA of the column-thread kernels
 constexpr int CT_THREADS = 256; // each thread owns column pairs {2t, 2t+1} + k*512
-
-// Dropout (train mode of the reference's DiT: FeedForward's Dropout after GELU, model/modules.py:342-353, and the Dropout behind
-// attention's to_out, :436-440).  Counter-based: the keep decision of element idx is a pure function of (key, idx), so the backward
-// regenerates the forward's mask instead of storing it.  One splitmix64 hash serves 4 consecutive elements (16 bits each).
-// thr16 == 0 switches it off.  (The dropout inside F.scaled_dot_product_attention, :490, is not built.)
-struct Drop {
-  uint32_t thr16;  // drop if lane bits < thr16 (= p * 65536)
-  float scale;     // 1 / (1 - p)
-  uint64_t key;
-};
-__device__ __forceinline__ uint64_t drop_hash(uint64_t key, uint64_t idx4) {
-  uint64_t z = idx4 * 0x9E3779B97F4A7C15ull + key;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-// multipliers (0 or 1/(1-p)) of the 4 consecutive elements starting at element index idx (a multiple of 4)
-__device__ __forceinline__ void drop_mult4(const Drop& d, uint64_t idx, float (&m)[4]) {
-  const uint64_t z = drop_hash(d.key, idx >> 2);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) m[k] = ((uint32_t)(z >> (16 * k)) & 0xFFFFu) >= d.thr16 ? d.scale : 0.f;
-}
 
 __device__ __forceinline__ float act_eval(int act, float x) {
   if (act == F5B_ACT_GELU_TANH) {
@@ -882,15 +861,18 @@ using namespace f5b;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 namespace f5b {
-static float g_drop_p = 0.f;
+static float g_drop_p = 0.f, g_attn_drop_p = 0.f;
 static uint64_t g_drop_seed = 0;
 static Drop drop_off() { return Drop{0u, 1.f, 0ull}; }
-static Drop drop_for(int layer, int site) {
-  if (!(g_drop_p > 0.f)) return drop_off();
-  uint32_t thr = (uint32_t)(g_drop_p * 65536.0f + 0.5f);
+// site 0 = FeedForward's Dropout, 1 = the Dropout behind to_out, 2 = the dropout inside scaled_dot_product_attention (own probability)
+Drop drop_for_site(int layer, int site) {
+  const float pr = site == 2 ? g_attn_drop_p : g_drop_p;
+  if (!(pr > 0.f)) return drop_off();
+  uint32_t thr = (uint32_t)(pr * 65536.0f + 0.5f);
   if (thr > 65535u) thr = 65535u;
   return Drop{thr, 65536.0f / (65536.0f - (float)thr), g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull};
 }
+static Drop drop_for(int layer, int site) { return drop_for_site(layer, site); }
 }  // namespace f5b
 
 extern "C" {
@@ -996,6 +978,14 @@ int f5b_train_set_dropout(float p, uint64_t seed) {
   F5B_CHECK(p >= 0.f && p < 1.f, "f5b_train_set_dropout: p must be in [0, 1)");
   g_drop_p = p;
   g_drop_seed = seed;
+  return 0;
+}
+/* the third dropout site of a DiT block: F.scaled_dot_product_attention(dropout_p=...) (model/modules.py:490; the fork hard-codes
+ * 0.1).  Applied to the attention probabilities after the softmax normalisation, kept values scaled by 1 / (1 - p); same
+ * counter-based generator and seed as the other two sites (element index = ((b*H + h)*n + query) * 4*ceil(n/4) + key). */
+int f5b_train_set_attn_dropout(float p) {
+  F5B_CHECK(p >= 0.f && p < 1.f, "f5b_train_set_attn_dropout: p must be in [0, 1)");
+  g_attn_drop_p = p;
   return 0;
 }
 /* the training drivers' versions of the four sweeps: site 0 = FeedForward dropout, site 1 = attention-output dropout */

@@ -73,15 +73,19 @@ class TrainEngine:
     """One data-parallel replica of the training step for a `CFM` whose transformer is a `DiT`."""
 
     def __init__(self, cfm, lr: float = 7.5e-5, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0, with_ema=False,
-                 ema_schedule: EmaSchedule | None = None, dropout: float = 0.0, checkpoint_activations: bool | None = None):
+                 ema_schedule: EmaSchedule | None = None, dropout: float = 0.0, checkpoint_activations: bool | None = None,
+                 attn_dropout: float = 0.0):
         """checkpoint_activations (default: the DiT's own `checkpoint_activations` flag, dit.py:121,158,221-223): every block keeps only
         its fp32 input and the backward re-runs the block's forward (4.6 GB of saved activations instead of 29.6 GB at 32 x 1200
         frames; one extra forward per step; gradients bit-identical).
         dropout: the DiT's train-mode dropout (the reference builds DiT(dropout=0.1), model/backbones/dit.py:132), applied after
-        FeedForward's GELU and behind attention's to_out (modules.py:342-353, :436-440); SDPA's internal dropout is not built.
+        FeedForward's GELU and behind attention's to_out (modules.py:342-353, :436-440).
+        attn_dropout: the dropout inside scaled_dot_product_attention (modules.py:490; the fork hard-codes dropout_p = 0.1), on the
+        normalised attention probabilities; default 0 (the parity setting), same counter-based mask generator and seed.
         0 (default) is the setting the gradient-parity tests run at."""
         self.cfm, self.dit = cfm, cfm.transformer
         self.dropout = float(dropout)
+        self.attn_dropout = float(attn_dropout)
         self.checkpoint_activations = bool(getattr(cfm.transformer, "checkpoint_activations", False)
                                            if checkpoint_activations is None else checkpoint_activations)
         self.last_losses = None
@@ -291,6 +295,7 @@ class TrainEngine:
         # the dropout masks of this micro-step are a function of this seed; the backward below regenerates them
         seed = int(draws["dropout_seed"]) if "dropout_seed" in draws else int(torch.randint(0, 2 ** 62, (1,)).item())
         L.check(lib.f5b_train_set_dropout(self.dropout, seed), "f5b_train_set_dropout")
+        L.check(lib.f5b_train_set_attn_dropout(self.attn_dropout), "f5b_train_set_attn_dropout")
         # no mask is passed to the transformer in training (cfm.py:275-277)
         L.check(lib.f5b_dit_train_forward(self.handle, phi.data_ptr(), None if drop_audio_cond else cond.data_ptr(), te.data_ptr(),
                                           time.data_ptr(), B, n, None, rope.data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel(), s),

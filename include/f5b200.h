@@ -308,6 +308,10 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
  * once per micro-step with a fresh seed BEFORE f5b_dit_train_forward and leave it untouched until the matching backward returns.
  * The dropout inside scaled_dot_product_attention (:490) is not built: the attention kernels always run with p = 0. */
 int f5b_train_set_dropout(float p, uint64_t seed);
+/* the dropout inside F.scaled_dot_product_attention (model/modules.py:490, dropout_p = 0.1 in the fork): applied to the normalised
+ * attention probabilities of every block by the f5b_dit_train_* drivers (forward and backward regenerate the same mask from the seed
+ * of f5b_train_set_dropout); p = 0 (default) switches it off.  Inference never applies it. */
+int f5b_train_set_attn_dropout(float p);
 /* Activation checkpointing of the DiT blocks (the reference's `checkpoint_activations`, /root/reference/src/f5_tts/model/backbones/
  * dit.py:121,158,221-223): on, every block keeps only its fp32 input and the backward re-runs the block's forward before
  * differentiating it (workspace 4.6 GB instead of 29.6 GB at 32 x 1200 frames, F5TTS_Base; one extra forward per step).  Set it

@@ -258,9 +258,10 @@ def dropout_multipliers(p: float, seed: int, layer: int, site: int, shape) -> to
     return torch.from_numpy(np.where(lanes >= thr, scale, np.float32(0.0)).astype(np.float32)).reshape(tuple(shape))
 
 
-def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None):
-    """AttnProcessor.__call__, model/modules.py:442-503 (dropout_p forced to 0.0; reference :490 says 0.1).
-    drop: optional callable applied to to_out's result (the Dropout of to_out, :439-440) before the padding mask."""
+def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None, attn_drop=None):
+    """AttnProcessor.__call__, model/modules.py:442-503 (dropout_p 0.0 unless attn_drop is given; reference :490 says 0.1).
+    drop: optional callable applied to to_out's result (the Dropout of to_out, :439-440) before the padding mask.
+    attn_drop: optional callable (b, H, n) -> multipliers [b, H, n, n] applied to the normalised probabilities (SDPA's dropout)."""
     b, n, _ = x.shape
     H, d = cfg.heads, cfg.dim_head
     q = F.linear(x, sd[p + "to_q.weight"], sd[p + "to_q.bias"]).view(b, n, H, d).transpose(1, 2)
@@ -272,7 +273,10 @@ def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None):
     s = (q @ k.transpose(-1, -2)) / math.sqrt(d)
     if mask is not None:
         s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
-    o = torch.softmax(s.float(), dim=-1).to(v.dtype) @ v
+    pr = torch.softmax(s.float(), dim=-1)
+    if attn_drop is not None:
+        pr = pr * attn_drop(b, H, n).to(pr.device)
+    o = pr.to(v.dtype) @ v
     o = o.transpose(1, 2).reshape(b, n, H * d)
     o = F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
     if drop is not None:
@@ -285,17 +289,25 @@ def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None):
 def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope, dropout=None):
     """DiTBlock.forward, model/modules.py:627-641 with AdaLayerNorm :310-315 (chunk order
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) and FeedForward(GELU tanh) :342-353.
-    dropout: None (eval) or (p, seed) -- train mode with the masks of dropout_multipliers."""
+    dropout: None (eval) or (p, seed[, attn_p]) -- train mode with the masks of dropout_multipliers; attn_p (default 0) is the
+    probability of SDPA's own dropout (site 2, :490), whose mask element of (b, h, query, key) sits at index
+    ((b*H + h)*n + query) * 4*ceil(n/4) + key of the site's stream (include/f5b200.h: f5b_train_set_attn_dropout)."""
     def drop(site):
         if dropout is None or not dropout[0] > 0:
             return None
         return lambda a: a * dropout_multipliers(dropout[0], dropout[1], i, site, a.shape).to(a.device)
+
+    attn_drop = None
+    if dropout is not None and len(dropout) > 2 and dropout[2] > 0:
+        def attn_drop(b, H, n):
+            n4 = (n + 3) // 4 * 4
+            return dropout_multipliers(dropout[2], dropout[1], i, 2, (b * H, n, n4))[:, :, :n].reshape(b, H, n, n)
     p = f"transformer.transformer_blocks.{i}."
     D = cfg.dim
     emb = F.linear(F.silu(t), sd[p + "attn_norm.linear.weight"], sd[p + "attn_norm.linear.bias"])
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = torch.chunk(emb, 6, dim=1)
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_msa[:, None]) + shift_msa[:, None]
-    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope, drop(1))
+    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope, drop(1), attn_drop)
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
     h = F.gelu(F.linear(h, sd[p + "ff.ff.0.0.weight"], sd[p + "ff.ff.0.0.bias"]), approximate="tanh")
     if drop(0) is not None:

@@ -154,6 +154,33 @@ def test_backward_with_dropout_vs_oracle_autograd():
     assert maxabs(preds[0.5], pa) > 1e-2
 
 
+@pytest.mark.parametrize("p,attn_p,n", [(0.0, 0.1, 152), (0.1, 0.3, 203)])
+def test_backward_with_attention_dropout_vs_oracle_autograd(p, attn_p, n):
+    """the third dropout site, inside scaled_dot_product_attention (model/modules.py:490): forward and backward regenerate the same
+    counter-based mask on the normalised probabilities; the oracle applies the identical mask, so prediction, loss and every
+    parameter gradient are held to the bars of the p = 0 test.  n = 203 is not a multiple of 4 (mask rows are padded to 4*ceil(n/4))."""
+    from eraxvif5tts_b200.train import TrainEngine
+    cfg = O.DiTConfig.tiny()
+    B = 2
+    x1, x0, time, text, span = _draws(cfg, B, n, 23)
+    base = dict(rand_span_mask=span, x0=x0, time=time, drop_audio_cond=False, drop_text=False)
+    seed = 4321
+    model, sd = build_cfm(cfg, 0)
+    eng = TrainEngine(model, dropout=p, attn_dropout=attn_p)
+    ref_loss, ref_pred, ref = _oracle_grads(sd, cfg, x1, text, span, x0, time, False, False, dropout=(p, seed, attn_p))
+    eng.zero_grad()
+    loss, _, pred = eng.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=seed))
+    eng._fold_split_grads()
+    torch.cuda.synchronize()
+    assert maxabs(pred, ref_pred) <= 2e-2
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    _compare(model, ref)
+    # the mask matters: the same step without SDPA dropout predicts something else
+    e0 = TrainEngine(build_cfm(cfg, 0)[0], dropout=p, attn_dropout=0.0)
+    _, _, pred0 = e0.loss_and_grads(x1.cuda(), text.cuda(), draws=dict(base, dropout_seed=seed))
+    assert maxabs(pred0, pred) > 1e-3
+
+
 @pytest.mark.parametrize("kind,w,da,dt", [("mse", 0.0, False, False), ("l1", 0.0, True, True), ("mse", 0.3, True, False)])
 def test_distillation_step_vs_oracle_autograd(kind, w, da, dt):
     """train/distil_reload.py:1044-1093: frozen deeper teacher + pruned student in one launch sequence; the four losses and every
