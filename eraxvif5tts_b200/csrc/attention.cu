@@ -51,17 +51,17 @@ struct AttnParams {
   int lens_mod, B, H, n;
   float scale_log2;
   long long* trace;  // debug only (ATT_TRACE builds)
-  Drop dr;           // DROP kernels: mask stream of this layer's SDPA dropout (model/modules.py:490)
-  int n4;            // ceil(n / 4): mask groups per (batch, head, query) row
+  AttnDrop dr;       // DROP kernels: mask stream of this layer's SDPA dropout (model/modules.py:490)
+  int n8;            // ceil(n / 8): mask groups per (batch, head, query) row
 };
 
 // P chunk: 32 columns -> exp2 -> bf16 -> swizzled smem row; returns the chunk's row-sum contribution.
-// DROP: the probabilities that go into P.V are multiplied by the dropout mask (0 or 1/(1-p)) of their (row, key) element, while the
-// row sum keeps the un-dropped values — dropout acts on the NORMALISED probabilities (torch SDPA semantics).  g0 = mask group of
-// the chunk's first key (4 keys per group).
+// DROP: the dropped elements of the probabilities that go into P.V are zeroed (an AND on the packed pairs; the 1/(1-p) factor is
+// folded into the final normalisation), while the row sum keeps the un-dropped values — dropout acts on the NORMALISED probabilities
+// (torch SDPA semantics).  g0 = mask group of the chunk's first key (8 keys per group, dropout.cuh).
 template <bool MASKED, bool DROP = false>
 __device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl2, float mb, int lim, uint8_t* prow, int cbase, int rx,
-                                               const Drop* dr = nullptr, uint64_t g0 = 0) {
+                                               const AttnDrop* dr = nullptr, uint64_t g0 = 0) {
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -76,18 +76,19 @@ __device__ __forceinline__ float softmax_chunk(const uint32_t (&s)[32], float sl
     }
     sum0 += (e[0] + e[1]) + (e[2] + e[3]);
     sum1 += (e[4] + e[5]) + (e[6] + e[7]);
-    if constexpr (DROP) {
-      float m0[4], m1[4];
-      drop_mult4(*dr, (g0 + q * 2) << 2, m0);
-      drop_mult4(*dr, (g0 + q * 2 + 1) << 2, m1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { e[i] *= m0[i]; e[4 + i] *= m1[i]; }
-    }
     uint4 pk;
     pk.x = pack_bf16(e[0], e[1]);
     pk.y = pack_bf16(e[2], e[3]);
     pk.z = pack_bf16(e[4], e[5]);
     pk.w = pack_bf16(e[6], e[7]);
+    if constexpr (DROP) {
+      uint32_t w0, w1;
+      attn_drop_words(*dr, g0 + q, w0, w1);
+      pk.x &= attn_drop_pair_mask(w0, 0);
+      pk.y &= attn_drop_pair_mask(w0, 1);
+      pk.z &= attn_drop_pair_mask(w1, 0);
+      pk.w &= attn_drop_pair_mask(w1, 1);
+    }
     *reinterpret_cast<uint4*>(prow + (((cbase + q) ^ rx) << 4)) = pk;
   }
   return sum0 + sum1;
@@ -381,13 +382,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // thread), so the P buffer (j & 1) is free.  Exponentials are speculative w.r.t. this tile's maximum (see header).
       float ts;
       // mask group of this tile's first key in this thread's (batch, head, query) row
-      const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n4 + (uint64_t)((t_begin + j) * (ATT_BKV / 4)) : 0;
+      const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n8 + (uint64_t)((t_begin + j) * (ATT_BKV / 8)) : 0;
       if (valid == ATT_BKV) {
         ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
-        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 8);
+        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 4);
       } else {
         ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
-        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 8);
+        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 4);
       }
       ATT_MARK(2)
       // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
@@ -414,10 +415,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_wait();
           if (valid == ATT_BKV) {
             ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
-            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 8);
+            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 4);
           } else {
             ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
-            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 8);
+            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 4);
           }
         }
       }
@@ -442,7 +443,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if constexpr (SPLIT == 1) {
       mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
       tc_fence_after();
-      const float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
+      float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
+      if constexpr (DROP) inv *= p.dr.scale;  // the kept probabilities' 1 / (1 - p)
       if (p.lse != nullptr && pos < p.n) p.lse[(size_t)bh * p.n + pos] = (pos < kvlen) ? m_used + log2f(l_run) : INFINITY;
       __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
@@ -548,7 +550,7 @@ int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, 
 #endif
 
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
-             int n, float scale, cudaStream_t stream, const Drop* drop) {
+             int n, float scale, cudaStream_t stream, const AttnDrop* drop) {
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
@@ -581,11 +583,11 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.n = n;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
-  p.dr = drop ? *drop : Drop{0u, 1.f, 0ull};
-  p.n4 = (n + 3) / 4;
+  p.dr = drop ? *drop : AttnDrop{0u, 1.f, 0.f, 0u, 0u};
+  p.n8 = (n + 7) / 8;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
 #if !ATT_P_TMEM
-  if (p.dr.thr16 != 0) {  // SDPA dropout (training): the forward's mask is regenerated by attn_bwd from the same Drop
+  if (p.dr.addc != 0) {  // SDPA dropout (training): the forward's mask is regenerated by attn_bwd from the same Drop
     F5B_CUDA(launch_dep(attn_fwd_kernel<1, true>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
     F5B_CUDA(cudaGetLastError());
     return 0;

@@ -31,7 +31,8 @@ constexpr int AB_THREADS = 448;
 constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
 constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
-constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + AB_PT /*dS^T*/ + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + 256 + 1024;
+constexpr uint32_t AB_MASK = 2 * 4 * AB_T * 4;   // SDPA-dropout keep bits of two tiles: [2][4 query chunks of 32][128 keys] words
+constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + AB_PT /*dS^T*/ + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + AB_MASK + 256 + 1024;
 constexpr uint32_t AB_TMEM_COLS = 512;
 
 struct AttnBwdParams {
@@ -46,16 +47,21 @@ struct AttnBwdParams {
   const float* rope;    // [n, 32] (cos, sin)
   int rope_heads;
   long long* trace;     // debug only (AB_TRACE builds)
-  Drop dr;              // DROP kernels: the forward's SDPA dropout mask stream (regenerated here, never stored)
-  int n4;               // ceil(n / 4)
+  AttnDrop dr;          // DROP kernels: the forward's SDPA dropout mask stream (regenerated here, never stored)
+  int n8;               // ceil(n / 8)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// DROP: the forward multiplied the normalised probabilities by a mask m (0 or 1/(1-p)) before P.V, so
+// DROP: the forward multiplied the normalised probabilities by a mask m = keep / (1-p) before P.V, so
 //   dV = (P . m)^T dO,   dS = scale * P . (m . dP - delta)   with delta = rowsum(dO . O) of the dropped forward's O.
+// With P' = P / (1-p) (the producer warp stages L - log2(1/(1-p))) and delta' = delta (1-p) this is dV = (P' . keep)^T dO,
+// dS = scale * P' . (keep . dP - delta'): the softmax threads only need the keep BIT of their elements.  The forward's Philox blocks
+// cover 8 keys of one query, while a thread here owns one key and 64 queries, so the four dQ-drain warps regenerate the tile's bits
+// (lane = query, one block per key octet) and transpose them with warp ballots into shared memory words [query chunk][key] whose
+// bit e is query e of the chunk: every block is computed once per CTA, and a softmax thread reads two words per tile.
 template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -72,7 +78,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sStg = sdST + AB_PT;                         // [8][4096]
   float* sL = reinterpret_cast<float*>(sStg + AB_STG);  // [2][128]
   float* sDl = sL + 2 * AB_T;                          // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * AB_T);
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(sDl + 2 * AB_T);  // [2][4][128] (DROP only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + AB_MASK / 4);
   uint64_t* bar_kv = bars + 0;
   uint64_t* bar_qdo = bars + 1;   // [2] Q_j, dO_j landed
   uint64_t* bar_ld = bars + 3;    // [2] L_j, delta_j staged (32 arrivals)
@@ -82,7 +89,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_free = bars + 8;  // [2] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
   uint64_t* bar_sfree = bars + 10;  // S^T_j / dP^T_j pulled into registers by all 256 threads
   uint64_t* bar_dqfree = bars + 11;  // dQ_j pulled out of TMEM by the 4 drain warps (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_mask = bars + 12;    // [2] DROP: keep bits of the tile that uses buffer s are in shared memory (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +136,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bar_free[1], 1);
       mbar_init(bar_sfree, 256);
       mbar_init(bar_dqfree, 128);
+      mbar_init(&bar_mask[0], 128);
+      mbar_init(&bar_mask[1], 128);
       fence_barrier_init();
     }
     __syncwarp();
@@ -166,8 +176,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int i = 0; i < 4; ++i) {
         const int r = i * 32 + lane;
         const int pos = j * AB_T + r;
-        sL[st * AB_T + r] = pos < p.n ? __ldg(p.lse + row0 + pos) : INFINITY;
-        sDl[st * AB_T + r] = pos < p.n ? __ldg(p.delta + row0 + pos) * p.scale : 0.f;  // pre-scaled: dS = P (dP scale - delta scale)
+        float lv = pos < p.n ? __ldg(p.lse + row0 + pos) : INFINITY;
+        float dlv = pos < p.n ? __ldg(p.delta + row0 + pos) * p.scale : 0.f;  // pre-scaled: dS = P (dP scale - delta scale)
+        if constexpr (DROP) {  // P' = P / (1-p), delta' = delta (1-p): see the kernel's header
+          lv -= p.dr.log2_scale;
+          dlv *= 1.f / p.dr.scale;
+        }
+        sL[st * AB_T + r] = lv;
+        sDl[st * AB_T + r] = dlv;
       }
       mbar_arrive(&bar_ld[st]);
     }
@@ -258,6 +274,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lq = warp & 3;
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
     uint8_t* my_stg = sStg + (warp - 10) * 8192;  // two [32 rows x 32 f32] SW128 boxes
+    // DROP: keep bits of query chunk (warp - 10) of tile jt for the CTA's 128 keys -> sMask[jt & 1][warp - 10][key]
+    auto gen_mask = [&](int jt) {
+      const int qc = warp - 10;
+      const uint64_t g = ((uint64_t)bh * p.n + (uint64_t)(jt * AB_T + qc * 32 + lane)) * p.n8 + (uint64_t)(k0 >> 3);
+      uint32_t* dst = sMask + ((jt & 1) * 4 + qc) * AB_T;
+#pragma unroll 1
+      for (int kb = 0; kb < 4; ++kb) {  // 32 keys: four Philox blocks per lane, 32 ballots; lane k keeps the word of key k
+        uint32_t mine = 0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          uint32_t w0, w1;
+          attn_drop_words(p.dr, g + kb * 4 + o, w0, w1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t v0 = __ballot_sync(0xffffffffu, (w0 >> (8 * i + 7)) & 1u);
+            const uint32_t v1 = __ballot_sync(0xffffffffu, (w1 >> (8 * i + 7)) & 1u);
+            if (lane == o * 8 + i) mine = v0;
+            if (lane == o * 8 + 4 + i) mine = v1;
+          }
+        }
+        dst[kb * 32 + lane] = mine;
+      }
+      mbar_arrive(&bar_mask[jt & 1]);  // release: this lane's words; 128 arrivals complete the buffer
+    };
+    if constexpr (DROP) {
+      gen_mask(0);
+      if (Tq > 1) gen_mask(1);
+    }
     for (int j = 0; j < Tq; ++j) {
       mbar_wait(bar_dq, j & 1);
       tc_fence_after();
@@ -284,6 +328,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bulk_commit();
       }
 #endif
+      // bar_dq(j) above implies that every softmax thread has finished with the bits of tile j: their buffer takes tile j + 2
+      if constexpr (DROP) {
+        if (j + 2 < Tq) gen_mask(j + 2);
+      }
     }
     if (elect_one()) bulk_wait0();  // the reductions have landed before the CTA retires its shared memory
   } else {
@@ -305,7 +353,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float4* L4 = reinterpret_cast<const float4*>(sL + st * AB_T + ch * 64);
       const float4* D4 = reinterpret_cast<const float4*>(sDl + st * AB_T + ch * 64);
       uint32_t ppk[32], dpk[32];  // P^T and dS^T rows of this thread, packed bf16
+      uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu;  // DROP: keep bits of this key for the 2 x 32 queries of this column half
+      if constexpr (DROP) {
+        mbar_wait(&bar_mask[st], (j >> 1) & 1);
+        kb0 = sMask[(st * 4 + ch * 2) * AB_T + r];
+        kb1 = sMask[(st * 4 + ch * 2 + 1) * AB_T + r];
+      }
       auto half = [&](const uint32_t (&sv)[32], const uint32_t (&gv)[32], int c) {
+        const uint32_t kbits = c ? kb1 : kb0;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 l = L4[c * 8 + q4];
@@ -318,11 +373,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int e = q4 * 4 + i;
             pv[i] = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
             if constexpr (DROP) {
-              // element (query, key) of this (batch, head): mask group = 4 consecutive keys of one query row
-              const uint64_t qrow = (uint64_t)bh * p.n + (uint64_t)(j * AB_T + ch * 64 + c * 32 + e);
-              const float m = drop_mult1(p.dr, drop_hash(p.dr.key, qrow * p.n4 + (uint64_t)((k0 + r) >> 2)), (k0 + r) & 3);
-              dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]) * m, sc, -dls[i]);
-              pv[i] *= m;  // P^T that feeds dV is the dropped one
+              const bool keep = (kbits >> e) & 1u;  // pv is P' = P / (1-p), dls is delta' (staged by the producer warp)
+              dv[i] = pv[i] * fmaf(keep ? __uint_as_float(gv[e]) : 0.f, sc, -dls[i]);
+              if (!keep) pv[i] = 0.f;  // P^T that feeds dV is the dropped one
             } else {
               dv[i] = pv[i] * fmaf(__uint_as_float(gv[e]), sc, -dls[i]);
             }
@@ -480,7 +533,7 @@ long long* g_attn_bwd_trace = nullptr;
 
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
-             const float* rope, int rope_heads, cudaStream_t stream, const Drop* drop) {
+             const float* rope, int rope_heads, cudaStream_t stream, const AttnDrop* drop) {
   F5B_CHECK(q && k && v && out && dout && lse && delta && dq_ws && dqkv, "f5b_attn_bwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0 && ld_o >= H * 64 && (ld_o & 7) == 0 && ld_d >= 3 * H * 64 && (ld_d & 7) == 0,
             "f5b_attn_bwd: bad shape B %d H %d n %d ld %d ld_o %d ld_d %d", B, H, n, ld, ld_o, ld_d);
@@ -521,10 +574,10 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.rope = rope;
   p.rope_heads = rope_heads;
   p.trace = g_attn_bwd_trace;
-  p.dr = drop ? *drop : Drop{0u, 1.f, 0ull};
-  p.n4 = (n + 3) / 4;
+  p.dr = drop ? *drop : AttnDrop{0u, 1.f, 0.f, 0u, 0u};
+  p.n8 = (n + 7) / 8;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
-  if (p.dr.thr16 != 0) F5B_CUDA(launch_dep(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  if (p.dr.addc != 0) F5B_CUDA(launch_dep(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
   else F5B_CUDA(launch_dep(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
   F5B_CUDA(cudaGetLastError());
   const long long items = rows * (D >> 3);

@@ -34,4 +34,38 @@ __device__ __forceinline__ float drop_mult1(const Drop& d, uint64_t z, int lane)
 
 Drop drop_for_site(int layer, int site);  // host (train_kernels.cu): the mask stream of (layer, site) under f5b_train_set_*dropout
 
+// Site 2, the dropout inside F.scaled_dot_product_attention (model/modules.py:490), has its own, cheaper stream: the attention kernels
+// spend ~5 instructions per score, so a 64-bit splitmix per 4 scores tripled their cost.  One Philox-2x32 block (7 rounds of
+// mul.wide + 3-input xor) serves the 8 consecutive keys of one query row: group index g = ((b*H + h)*n + query) * ceil(n/8) + key/8,
+// counter = (lo32(g), hi32(g) ^ chi), key = `key`; element `key & 7` owns byte (key & 3) of word (key & 7) >> 2 and is KEPT iff
+// (byte & 0x7f) >= t7, t7 = round(p * 128): the probability is quantised to 1/128 (flash-attention quantises to 1/256) and the kept
+// values are scaled by 128 / (128 - t7), so the expectation is exact.  attn_drop_words returns the two words with the keep flag in
+// the top bit of every byte (a carry-free packed add), ready for a sign-replicating PRMT.
+struct AttnDrop {
+  uint32_t addc;     // (128 - t7) in every byte; 0 = dropout off
+  float scale;       // 128 / (128 - t7)
+  float log2_scale;
+  uint32_t key, chi;
+};
+__device__ __forceinline__ void attn_drop_words(const AttnDrop& d, uint64_t g, uint32_t& w0, uint32_t& w1) {
+  uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32) ^ d.chi, k = d.key;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint64_t pr = (uint64_t)c0 * 0xD256D193u;
+    c0 = (uint32_t)(pr >> 32) ^ k ^ c1;
+    c1 = (uint32_t)pr;
+    k += 0x9E3779B9u;
+  }
+  w0 = (c0 & 0x7f7f7f7fu) + d.addc;
+  w1 = (c1 & 0x7f7f7f7fu) + d.addc;
+}
+// 32-bit AND mask of a packed bf16 pair whose elements own bytes (2*pair, 2*pair + 1) of `w`: the byte's top bit replicated
+__device__ __forceinline__ uint32_t attn_drop_pair_mask(uint32_t w, int pair) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(w), "r"(pair ? 0xBBAAu : 0x9988u));
+  return m;
+}
+
+AttnDrop attn_drop_for_layer(int layer);  // host (train_kernels.cu): f5b_train_set_attn_dropout's stream of one DiT block
+
 }  // namespace f5b

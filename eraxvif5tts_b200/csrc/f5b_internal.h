@@ -26,12 +26,12 @@ int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w
                int C, float eps, cudaStream_t s, float* y_out = nullptr, bool tf32 = false);
 int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s,
         bool tf32 = false);
-struct Drop;  // dropout.cuh: mask stream of one (layer, site); nullptr / thr16 == 0 = no dropout
+struct AttnDrop;  // dropout.cuh: mask stream of one layer's SDPA dropout; nullptr / addc == 0 = no dropout
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
-             int n, float scale, cudaStream_t stream, const Drop* drop = nullptr);
+             int n, float scale, cudaStream_t stream, const AttnDrop* drop = nullptr);
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
-             const float* rope, int rope_heads, cudaStream_t stream, const Drop* drop = nullptr);
+             const float* rope, int rope_heads, cudaStream_t stream, const AttnDrop* drop = nullptr);
 int attn_fwd_tf32(const float* q, const float* k, const float* v, int ld, float* out, float* vt_ws, const int32_t* lens, int lens_mod,
                   int B, int H, int n, float scale, cudaStream_t stream);
 size_t attn_tf32_ws_floats(int B, int H, int n);

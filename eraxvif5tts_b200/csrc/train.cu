@@ -228,7 +228,7 @@ static int train_block_forward(const F5bDitDesc& d, const TrainWs& w, int i, int
   g.out = b.qkv; g.ldc = 3 * D;
   g.rows_per_batch = n; g.rope = rope; g.rope_heads = d.rope_heads; g.heads = H;
   F5B_TRY(gemm(b.a, D, qkv_w + (size_t)i * 3 * D * D, D, g, s));
-  const Drop adrop = drop_for_site(i, 2);  // SDPA dropout (f5b_train_set_attn_dropout); thr16 == 0 when off
+  const AttnDrop adrop = attn_drop_for_layer(i);  // SDPA dropout (f5b_train_set_attn_dropout); addc == 0 when off
   F5B_TRY(attn_fwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, b.lse, lens, 0, B, H, n, 0.125f, s, &adrop));
   F5B_TRY(linear_bf16(b.o, D, out_w + (size_t)i * D * D, D, d.out_b + (size_t)i * D, b.z1, D, rows, D, D, F5B_ACT_NONE, s));
   // x_mid = x_in + gate_msa * mask(z1);  f = LN(x_mid) (1 + scale_mlp) + shift_mlp
@@ -365,7 +365,7 @@ static int train_backward_impl(const F5bDit* h, const void* dpred_bf16, const vo
     F5B_TRY(f5b_gate_bwd_site(w.dx, b.z1, m + 2 * D, mod_dim, lens, w.t1, dm + 2 * D, off(g.out_b, (size_t)i * D), B, n, D, i, 1, stream));
     F5B_TRY(wgrad(w.t1, D, b.o, D, off(g.out_w, (size_t)i * D * D), D, rows, D, D, stream));
     F5B_TRY(dgrad(w.t1, D, out_w + (size_t)i * D * D, D, w.t2, D, rows, D, stream));
-    const Drop adrop = drop_for_site(i, 2);
+    const AttnDrop adrop = attn_drop_for_layer(i);
     F5B_TRY(attn_bwd(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.o, w.t2, D, b.lse, w.delta, w.dq_ws, w.t3, 3 * D, lens, 0, B, H, n, 0.125f,
                      rope, d.rope_heads, s, &adrop));
     F5B_TRY(f5b_act_bwd(w.t3, nullptr, nullptr, off(g.qkv_b, (size_t)i * 3 * D), rows, 3 * D, 3 * D, F5B_ACT_NONE, stream));

@@ -864,15 +864,24 @@ namespace f5b {
 static float g_drop_p = 0.f, g_attn_drop_p = 0.f;
 static uint64_t g_drop_seed = 0;
 static Drop drop_off() { return Drop{0u, 1.f, 0ull}; }
-// site 0 = FeedForward's Dropout, 1 = the Dropout behind to_out, 2 = the dropout inside scaled_dot_product_attention (own probability)
+// site 0 = FeedForward's Dropout, 1 = the Dropout behind to_out (site 2, SDPA's own dropout: attn_drop_for_layer)
 Drop drop_for_site(int layer, int site) {
-  const float pr = site == 2 ? g_attn_drop_p : g_drop_p;
+  const float pr = g_drop_p;
   if (!(pr > 0.f)) return drop_off();
   uint32_t thr = (uint32_t)(pr * 65536.0f + 0.5f);
   if (thr > 65535u) thr = 65535u;
   return Drop{thr, 65536.0f / (65536.0f - (float)thr), g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull};
 }
 static Drop drop_for(int layer, int site) { return drop_for_site(layer, site); }
+// SDPA's dropout (site 2) draws from its own Philox stream (dropout.cuh); same seed, same per-(layer, site) key derivation
+AttnDrop attn_drop_for_layer(int layer) {
+  if (!(g_attn_drop_p > 0.f)) return AttnDrop{0u, 1.f, 0.f, 0u, 0u};
+  int t7 = (int)(g_attn_drop_p * 128.0f + 0.5f);
+  t7 = t7 < 1 ? 1 : (t7 > 127 ? 127 : t7);
+  const float scale = 128.0f / (float)(128 - t7);
+  const uint64_t key = g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + 3) * 0x9E3779B97F4A7C15ull;
+  return AttnDrop{(uint32_t)(128 - t7) * 0x01010101u, scale, log2f(scale), (uint32_t)key, (uint32_t)(key >> 32)};
+}
 }  // namespace f5b
 
 extern "C" {
@@ -982,7 +991,7 @@ int f5b_train_set_dropout(float p, uint64_t seed) {
 }
 /* the third dropout site of a DiT block: F.scaled_dot_product_attention(dropout_p=...) (model/modules.py:490; the fork hard-codes
  * 0.1).  Applied to the attention probabilities after the softmax normalisation, kept values scaled by 1 / (1 - p); same
- * counter-based generator and seed as the other two sites (element index = ((b*H + h)*n + query) * 4*ceil(n/4) + key). */
+ * seed as the other two sites, own Philox-2x32 stream with the probability quantised to 1/128 (dropout.cuh: AttnDrop). */
 int f5b_train_set_attn_dropout(float p) {
   F5B_CHECK(p >= 0.f && p < 1.f, "f5b_train_set_attn_dropout: p must be in [0, 1)");
   g_attn_drop_p = p;

@@ -306,11 +306,14 @@ int f5b_dit_train_backward(const F5bDit* h, const void* dpred_bf16, const void* 
  * model/modules.py:342-353, and the Dropout behind attention's to_out, :436-440).  p = 0 (the default) switches it off.  The keep
  * decision is a counter-based hash of (seed, block, site, element) -- the backward regenerates the forward's mask -- so call this
  * once per micro-step with a fresh seed BEFORE f5b_dit_train_forward and leave it untouched until the matching backward returns.
- * The dropout inside scaled_dot_product_attention (:490) is not built: the attention kernels always run with p = 0. */
+ * The dropout inside scaled_dot_product_attention (:490) has its own switch: f5b_train_set_attn_dropout. */
 int f5b_train_set_dropout(float p, uint64_t seed);
 /* the dropout inside F.scaled_dot_product_attention (model/modules.py:490, dropout_p = 0.1 in the fork): applied to the normalised
  * attention probabilities of every block by the f5b_dit_train_* drivers (forward and backward regenerate the same mask from the seed
- * of f5b_train_set_dropout); p = 0 (default) switches it off.  Inference never applies it. */
+ * of f5b_train_set_dropout); p = 0 (default) switches it off.  Inference never applies it.  The mask stream is the product's own
+ * (one Philox-2x32-7 block per 8 consecutive keys of a query row, p quantised to 1/128 with the kept values scaled by the exact
+ * reciprocal of the quantised keep probability; eraxvif5tts_b200/csrc/dropout.cuh, restated in oracle.attention_dropout_multipliers):
+ * torch's own Philox offsets are an implementation detail, only the distribution is the reference's. */
 int f5b_train_set_attn_dropout(float p);
 /* Activation checkpointing of the DiT blocks (the reference's `checkpoint_activations`, /root/reference/src/f5_tts/model/backbones/
  * dit.py:121,158,221-223): on, every block keeps only its fp32 input and the backward re-runs the block's forward before

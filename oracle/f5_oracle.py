@@ -258,6 +258,32 @@ def dropout_multipliers(p: float, seed: int, layer: int, site: int, shape) -> to
     return torch.from_numpy(np.where(lanes >= thr, scale, np.float32(0.0)).astype(np.float32)).reshape(tuple(shape))
 
 
+def attention_dropout_multipliers(p: float, seed: int, layer: int, BH: int, n: int) -> torch.Tensor:
+    """The product's mask of the dropout inside scaled_dot_product_attention (modules.py:490; include/f5b200.h:
+    f5b_train_set_attn_dropout, eraxvif5tts_b200/csrc/dropout.cuh: AttnDrop), restated for the same reason as dropout_multipliers.
+    One Philox-2x32 block of 7 rounds per 8 consecutive keys of a query row: counter = group index ((bh * n + query) * ceil(n/8)
+    + key // 8), key / counter-high xor from the (seed, layer) key; element key % 8 owns one byte, kept iff (byte & 0x7f) >= t7 with
+    t7 = round(p * 128); kept values are scaled by 128 / (128 - t7).  Returns float32 [BH, n, n]."""
+    import numpy as np
+    n8 = (n + 7) // 8
+    t7 = min(127, max(1, int(np.float32(p) * np.float32(128.0) + np.float32(0.5))))
+    M = (1 << 64) - 1
+    key = (int(seed) * 0xD1342543DE82EF95 + (layer * 8 + 3) * 0x9E3779B97F4A7C15) & M
+    g = np.arange(BH * n * n8, dtype=np.uint64)
+    c0 = (g & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    c1 = (g >> np.uint64(32)) ^ np.uint64(key >> 32)
+    k = key & 0xFFFFFFFF
+    for _ in range(7):
+        pr = c0 * np.uint64(0xD256D193)  # 32 x 32 -> 64 bits: no overflow
+        c0 = (pr >> np.uint64(32)) ^ np.uint64(k) ^ c1
+        c1 = pr & np.uint64(0xFFFFFFFF)
+        k = (k + 0x9E3779B9) & 0xFFFFFFFF
+    lanes = np.stack([((c0 if j < 4 else c1) >> np.uint64(8 * (j & 3))) & np.uint64(0x7F) for j in range(8)], axis=1)  # [groups, 8]
+    scale = np.float32(128.0) / np.float32(128 - t7)
+    m = np.where(lanes >= t7, scale, np.float32(0.0)).astype(np.float32).reshape(BH, n, n8 * 8)[:, :, :n]
+    return torch.from_numpy(np.ascontiguousarray(m))
+
+
 def attention(sd, cfg: DiTConfig, p, x, mask, rope, drop=None, attn_drop=None):
     """AttnProcessor.__call__, model/modules.py:442-503 (dropout_p 0.0 unless attn_drop is given; reference :490 says 0.1).
     drop: optional callable applied to to_out's result (the Dropout of to_out, :439-440) before the padding mask.
@@ -290,8 +316,7 @@ def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope, dropout=None):
     """DiTBlock.forward, model/modules.py:627-641 with AdaLayerNorm :310-315 (chunk order
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) and FeedForward(GELU tanh) :342-353.
     dropout: None (eval) or (p, seed[, attn_p]) -- train mode with the masks of dropout_multipliers; attn_p (default 0) is the
-    probability of SDPA's own dropout (site 2, :490), whose mask element of (b, h, query, key) sits at index
-    ((b*H + h)*n + query) * 4*ceil(n/4) + key of the site's stream (include/f5b200.h: f5b_train_set_attn_dropout)."""
+    probability of SDPA's own dropout (:490), whose mask is attention_dropout_multipliers."""
     def drop(site):
         if dropout is None or not dropout[0] > 0:
             return None
@@ -300,8 +325,7 @@ def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope, dropout=None):
     attn_drop = None
     if dropout is not None and len(dropout) > 2 and dropout[2] > 0:
         def attn_drop(b, H, n):
-            n4 = (n + 3) // 4 * 4
-            return dropout_multipliers(dropout[2], dropout[1], i, 2, (b * H, n, n4))[:, :, :n].reshape(b, H, n, n)
+            return attention_dropout_multipliers(dropout[2], dropout[1], i, b * H, n).reshape(b, H, n, n)
     p = f"transformer.transformer_blocks.{i}."
     D = cfg.dim
     emb = F.linear(F.silu(t), sd[p + "attn_norm.linear.weight"], sd[p + "attn_norm.linear.bias"])
