@@ -751,6 +751,11 @@ def main():
     e2e_value = total_frames / e2e_s
     launches = launches_timed
     config["cuda_graph"] = "one captured graph per ODE step (replayed 32x per sample)" if graph_mode else "off"
+    from eraxvif5tts_b200.model.backbones import dit as _dit
+    _senv = os.environ.get("F5B_SPLIT_CFG", "")
+    config["cfg_branches"] = ("two concurrent chains (cond / uncond forwards forked inside the captured step; launch-bound shapes)"
+                              if graph_mode and _senv != "0" and (_senv == "1" or 2 * B * total <= _dit.SPLIT_CFG_MAX_ROWS)
+                              else "one fused 2B-row batch")
     config["profiling"] = f"timed region un-instrumented; kernel classes / roofline from {prof_steps} extra event-bracketed eager step(s) behind it"
     config["dependent_launch"] = ("on (fused batch <= 16384 rows: kernel prologues overlap the previous kernel's tail)" if 2 * B * total <= L.PDL_MAX_ROWS
                                   else "off (GPU-bound batch; measured 1.8 % slower with it)")

@@ -4,11 +4,18 @@ checkpoints load key-for-key); the math is done by libf5b200.so on bf16 copies p
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
 
 from ... import _lib as L
+
+# fused rows (2B x n) up to which the CFG branches run as two concurrent chains (step_session).  0 = never by default: measured on
+# cfg-1 (B = 1 x 940 frames) the fork costs 67.9 / 68.2 -> 72.9 / 72.7 ms per utterance and on cfg-3 688 -> 700 ms per batch (two
+# 1-CTA-per-SM persistent GEMM grids do not co-reside, and the fork / join edges lose the programmatic dependent launches), so the
+# fused 2B-row batch stays the product path; F5B_SPLIT_CFG=1 selects the fork (bit-identical, tests/test_gpu_edges.py).
+SPLIT_CFG_MAX_ROWS = 0
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -253,7 +260,12 @@ class DiTEngine:
         """Persistent buffers + one captured CUDA graph of {DiT.forward over the fused batch, CFG + Euler update} for a given
         shape.  Per ODE step only `stepbuf` (that step's modulation row followed by (cfg, dt)) changes, so the same graph is
         replayed for all steps and all later sample() calls of this shape."""
-        key = (Bx, Bf, n, masked)
+        # CFG branches as two CONCURRENT chains (opt-in experiment, see SPLIT_CFG_MAX_ROWS): the conditioned and the unconditioned
+        # forward share no data but the read-only state, so the captured step can fork into two B-row forwards on two streams
+        # instead of one fused 2B-row batch (bit-identical results; measured slower)
+        env = os.environ.get("F5B_SPLIT_CFG", "")
+        split = Bf == 2 * Bx and env != "0" and (env == "1" or Bf * n <= SPLIT_CFG_MAX_ROWS)
+        key = (Bx, Bf, n, masked, split)
         sess = self._sessions.get(key)
         if sess is not None:
             self._sessions[key] = self._sessions.pop(key)  # LRU order
@@ -267,13 +279,27 @@ class DiTEngine:
             c0=torch.zeros(Bf, n, self.dim, dtype=f32, device=dev), pred=torch.zeros(Bf, n, mel, dtype=f32, device=dev),
             stepbuf=torch.zeros(self.mod_dim + 2, dtype=f32, device=dev),
             lens=torch.full((Bx,), n, dtype=torch.int32, device=dev) if masked else None, graph=None, delta=None,
-            rope=self.rope_table(n), ws=None)  # the graph bakes these pointers in: the session keeps them alive
-        sess["ws"] = self.workspace(self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n))
+            rope=self.rope_table(n), ws=None, split=split)  # the graph bakes these pointers in: the session keeps them alive
+        if split:
+            nb = self.lib.f5b_dit_workspace_bytes(self.handle, Bx, n)
+            sess["ws"] = torch.empty(nb, dtype=torch.uint8, device=dev)
+            sess["ws2"] = torch.empty(nb, dtype=torch.uint8, device=dev)
+            sess["fork"] = torch.cuda.Stream(device=dev)
+        else:
+            sess["ws"] = self.workspace(self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n))
         pc, pu = sess["pred"][:Bx], (sess["pred"][Bx:] if Bf > Bx else None)
         params = sess["stepbuf"][self.mod_dim:]
 
         def body():
-            self.forward(sess["yb"], Bx, sess["c0"], Bf, n, sess["stepbuf"], 0, sess["lens"], sess["pred"])
+            if split:
+                cur, fork = torch.cuda.current_stream(dev), sess["fork"]
+                fork.wait_stream(cur)
+                self.forward(sess["yb"], Bx, sess["c0"][:Bx], Bx, n, sess["stepbuf"], 0, sess["lens"], pc, ws=sess["ws"])
+                with torch.cuda.stream(fork):
+                    self.forward(sess["yb"], Bx, sess["c0"][Bx:], Bx, n, sess["stepbuf"], 0, sess["lens"], pu, ws=sess["ws2"])
+                cur.wait_stream(fork)
+            else:
+                self.forward(sess["yb"], Bx, sess["c0"], Bf, n, sess["stepbuf"], 0, sess["lens"], sess["pred"])
             if self.precision == "tf32":
                 L.check(self.lib.f5b_cfg_euler_dev(sess["y"].data_ptr(), pc.data_ptr(), L.ptr(pu), params.data_ptr(), None, 128, None,
                                                    Bx * n, mel, L.stream()), "f5b_cfg_euler_dev")
@@ -340,11 +366,14 @@ class DiTEngine:
         (ops.pack_tf32 if self.precision == "tf32" else ops.pack_bf16)(y.view(rows, self.mel_dim), yb, self.mel_dim, 128)
         return yb
 
-    def forward(self, x_bf16, Bx, c0, Bf, n, mod, mod_bstride, lens, pred):
-        """x_bf16: the packed state from `pack_state` (bf16, or fp32 in the tf32 mode)"""
+    def forward(self, x_bf16, Bx, c0, Bf, n, mod, mod_bstride, lens, pred, ws=None):
+        """x_bf16: the packed state from `pack_state` (bf16, or fp32 in the tf32 mode); ws: a private workspace (default: the
+        engine's shared one)"""
         assert x_bf16.dtype == self.act_dtype
         nbytes = self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n)
-        ws = self.workspace(nbytes)
+        if ws is None:
+            ws = self.workspace(nbytes)
+        assert ws.numel() >= nbytes and c0.is_contiguous() and pred.is_contiguous()
         L.check(self.lib.f5b_dit_forward(self.handle, x_bf16.data_ptr(), Bx, c0.data_ptr(), Bf, n, mod.data_ptr(), mod_bstride,
                                          L.ptr(lens), self.rope_table(n).data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel(),
                                          L.stream()), "f5b_dit_forward")

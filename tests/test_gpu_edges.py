@@ -97,6 +97,26 @@ def test_repeated_calls_are_deterministic_and_independent():
     assert torch.equal(r[0], r[2])
 
 
+@pytest.mark.parametrize("B,totals", [(1, 70), (2, [96, 83])])
+def test_cfg_branches_as_concurrent_chains_are_bit_identical(B, totals, monkeypatch):
+    """launch-bound shapes run the conditioned and the unconditioned forward of a CFG step as two concurrent chains inside the
+    captured graph (DiTEngine.step_session) instead of one fused 2B-row batch: same kernels on the same rows, bit-identical"""
+    cfg = O.DiTConfig.tiny()
+    cond, text, duration, lens = synthetic_inputs(cfg, B, 33, totals, seed=5)
+    outs = []
+    for split in ("0", "1"):
+        monkeypatch.setenv("F5B_SPLIT_CFG", split)
+        monkeypatch.setenv("F5B_CUDA_GRAPH", "1")
+        model, _ = build_cfm(cfg, 0)
+        for _ in range(2):  # second call replays the cached session
+            out, traj = model.sample(cond=cond.cuda(), text=text.cuda(), duration=duration.cuda(), lens=lens.cuda(), steps=4,
+                                     cfg_strength=2.0, sway_sampling_coef=-1.0, seed=0)
+        torch.cuda.synchronize()
+        assert any(k[-1] == (split == "1") for k in model.transformer.engine()._sessions)
+        outs.append((out.clone(), traj.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_attention_forward_is_deterministic_with_many_ctas_per_sm():
     """regression: the P.V completion barrier used to be a single mbarrier whose phase advanced once per key tile, while the softmax
     threads waited on it only in the epilogue; a warp running a full tile ahead of the slowest one then saw the parity of a phase
