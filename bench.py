@@ -265,7 +265,7 @@ def torch_eager_gpu_measure(arch, B, ref_frames, total, dev, steps=3, warmup=2):
     sd = {k: v.to(dev, torch.bfloat16) for k, v in sd_cpu.items()}
     rope_cpu, attn_cpu = O.rotary_freqs, O.attention
 
-    def attention_sdpa(sd_, cfg_, p, x, mask, rope, drop=None):
+    def attention_sdpa(sd_, cfg_, p, x, mask, rope, drop=None, attn_drop=None):
         b, n, _ = x.shape
         H, d = cfg_.heads, cfg_.dim_head
         q = F.linear(x, sd_[p + "to_q.weight"], sd_[p + "to_q.bias"]).view(b, n, H, d).transpose(1, 2)
@@ -322,7 +322,7 @@ def torch_eager_gpu_train_measure(arch, B, n, dev, steps=3, warmup=2):
     opt = torch.optim.AdamW(params, lr=7.5e-5, betas=(0.9, 0.98), weight_decay=0.01, fused=True)
     rope_cpu, attn_cpu = O.rotary_freqs, O.attention
 
-    def attention_sdpa(sd_, cfg_, p, x, mask, rope, drop=None):
+    def attention_sdpa(sd_, cfg_, p, x, mask, rope, drop=None, attn_drop=None):
         b, m, _ = x.shape
         H, d = cfg_.heads, cfg_.dim_head
         q = F.linear(x, sd_[p + "to_q.weight"], sd_[p + "to_q.bias"]).view(b, m, H, d).transpose(1, 2)

@@ -331,7 +331,8 @@ def dit_block(sd, cfg: DiTConfig, i: int, x, t, mask, rope, dropout=None):
     emb = F.linear(F.silu(t), sd[p + "attn_norm.linear.weight"], sd[p + "attn_norm.linear.bias"])
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = torch.chunk(emb, 6, dim=1)
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_msa[:, None]) + shift_msa[:, None]
-    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope, drop(1), attn_drop)
+    akw = {} if attn_drop is None else {"attn_drop": attn_drop}  # (bench.py's eager comparator swaps `attention` for an SDPA version)
+    x = x + gate_msa.unsqueeze(1) * attention(sd, cfg, p + "attn.", h, mask, rope, drop(1), **akw)
     h = F.layer_norm(x, (D,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
     h = F.gelu(F.linear(h, sd[p + "ff.ff.0.0.weight"], sd[p + "ff.ff.0.0.bias"]), approximate="tanh")
     if drop(0) is not None:
