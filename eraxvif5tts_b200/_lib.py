@@ -91,6 +91,7 @@ SIGNATURES = {
     "f5b_train_set_dropout": (C.c_int, [C.c_float, C.c_uint64]),
     "f5b_train_set_checkpoint": (C.c_int, [C.c_int]),
     "f5b_train_set_attn_dropout": (C.c_int, [C.c_float]),
+    "f5b_dit_set_attn_dropout": (C.c_int, [C.c_float, C.c_uint64, vp]),
     "f5b_dit_train_backward_part": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, vp]),
     "f5b_dit_text_train_ws_bytes": (sz, [vp, C.c_int, C.c_int]),
     "f5b_dit_text_embed_train": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),

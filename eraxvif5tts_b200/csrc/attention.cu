@@ -52,6 +52,7 @@ struct AttnParams {
   float scale_log2;
   long long* trace;  // debug only (ATT_TRACE builds)
   AttnDrop dr;       // DROP kernels: mask stream of this layer's SDPA dropout (model/modules.py:490)
+  const uint32_t* dr_seed;  // optional device word mixed into the stream's key (a captured graph replays with a fresh mask per step)
   int n8;            // ceil(n / 8): mask groups per (batch, head, query) row
 };
 
@@ -311,6 +312,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     const int r = warp * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    AttnDrop dr = p.dr;
+    if constexpr (DROP) {
+      if (p.dr_seed != nullptr) {  // per-launch word from device memory (graph replays: a fresh mask per ODE step)
+        const uint32_t sw = __ldg(p.dr_seed);
+        dr.key ^= sw * 0x9E3779B9u;
+        dr.chi += sw;
+      }
+    }
     float m_used = -INFINITY;  // log2-domain maximum the exponentials are taken against
     float l_run = 0.f;         // row sum of exp2(s - m_used)
     const float sl2 = p.scale_log2;
@@ -384,11 +393,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // mask group of this tile's first key in this thread's (batch, head, query) row
       const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n8 + (uint64_t)((t_begin + j) * (ATT_BKV / 8)) : 0;
       if (valid == ATT_BKV) {
-        ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
-        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 4);
+        ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
+        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &dr, g0 + 4);
       } else {
-        ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
-        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 4);
+        ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &dr, g0);
+        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &dr, g0 + 4);
       }
       ATT_MARK(2)
       // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
@@ -414,11 +423,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
           if (valid == ATT_BKV) {
-            ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &p.dr, g0);
-            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &p.dr, g0 + 4);
+            ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
+            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &dr, g0 + 4);
           } else {
-            ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &p.dr, g0);
-            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &p.dr, g0 + 4);
+            ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &dr, g0);
+            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &dr, g0 + 4);
           }
         }
       }
@@ -444,7 +453,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
       tc_fence_after();
       float inv = (pos < kvlen) ? 1.f / l_run : 0.f;
-      if constexpr (DROP) inv *= p.dr.scale;  // the kept probabilities' 1 / (1 - p)
+      if constexpr (DROP) inv *= dr.scale;  // the kept probabilities' 1 / (1 - p)
       if (p.lse != nullptr && pos < p.n) p.lse[(size_t)bh * p.n + pos] = (pos < kvlen) ? m_used + log2f(l_run) : INFINITY;
       __nv_bfloat16* orow = p.out + ((size_t)b * p.n + (pos < p.n ? pos : 0)) * D + h * 64;
 #pragma unroll
@@ -550,7 +559,7 @@ int attn_fwd_fa(const void* q, const void* k, const void* v, int ld, void* out, 
 #endif
 
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
-             int n, float scale, cudaStream_t stream, const AttnDrop* drop) {
+             int n, float scale, cudaStream_t stream, const AttnDrop* drop, const uint32_t* drop_seed_dev) {
   F5B_CHECK(q && k && v && out, "f5b_attn_fwd: null pointer");
   F5B_CHECK(B > 0 && H > 0 && n > 0 && ld >= H * 64 && (ld & 7) == 0, "f5b_attn_fwd: bad shape B %d H %d n %d ld %d", B, H, n, ld);
   LaunchScope scope(K_ATTN, stream, 4.0 * B * H * (double)n * n * 64, 2.0 * 4 * B * H * (double)n * 64);
@@ -585,6 +594,7 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.trace = g_attn_trace;
   p.dr = drop ? *drop : AttnDrop{0u, 1.f, 0.f, 0u, 0u};
   p.n8 = (n + 7) / 8;
+  p.dr_seed = drop_seed_dev;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
 #if !ATT_P_TMEM
   if (p.dr.addc != 0) {  // SDPA dropout (training): the forward's mask is regenerated by attn_bwd from the same Drop
@@ -611,12 +621,12 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
 
 extern "C" int f5b_attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, const int32_t* lens, int lens_mod,
                             int B, int H, int n, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, v, ld, out, nullptr, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr);
+  return f5b::attn_fwd(q, k, v, ld, out, nullptr, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 extern "C" int f5b_attn_fwd_lse(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens,
                                 int lens_mod, int B, int H, int n, float scale, f5b_stream_t stream) {
-  return f5b::attn_fwd(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr);
+  return f5b::attn_fwd(q, k, v, ld, out, lse, lens, lens_mod, B, H, n, scale, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 extern "C" void f5b_debug_set_attn_trace(long long* buf) { f5b::g_attn_trace = buf; }

@@ -66,6 +66,7 @@ __device__ __forceinline__ uint32_t attn_drop_pair_mask(uint32_t w, int pair) {
   return m;
 }
 
-AttnDrop attn_drop_for_layer(int layer);  // host (train_kernels.cu): f5b_train_set_attn_dropout's stream of one DiT block
+AttnDrop make_attn_drop(float p, uint64_t seed, int layer);  // host (train_kernels.cu): the stream of one DiT block; p <= 0: off
+AttnDrop attn_drop_for_layer(int layer);  // host: f5b_train_set_attn_dropout's stream (training drivers)
 
 }  // namespace f5b

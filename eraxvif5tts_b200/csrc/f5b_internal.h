@@ -28,7 +28,7 @@ int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf1
         bool tf32 = false);
 struct AttnDrop;  // dropout.cuh: mask stream of one layer's SDPA dropout; nullptr / addc == 0 = no dropout
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
-             int n, float scale, cudaStream_t stream, const AttnDrop* drop = nullptr);
+             int n, float scale, cudaStream_t stream, const AttnDrop* drop = nullptr, const uint32_t* drop_seed_dev = nullptr);
 int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* out, const void* dout, int ld_o, const float* lse,
              float* delta, float* dq_ws, void* dqkv, int ld_d, const int32_t* lens, int lens_mod, int B, int H, int n, float scale,
              const float* rope, int rope_heads, cudaStream_t stream, const AttnDrop* drop = nullptr);

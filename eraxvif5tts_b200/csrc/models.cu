@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "f5b_internal.h"
+#include "dropout.cuh"
 
 struct F5bDit {
   F5bDitDesc d;
@@ -62,6 +63,11 @@ static DitWs carve_dit(const F5bDitDesc& d, int B, int n, void* ws) {
   return w;
 }
 
+// f5b_dit_set_attn_dropout: the reference's SDPA dropout at INFERENCE (model/modules.py:490 passes dropout_p = 0.1 in eval() too)
+static float g_infer_attn_p = 0.f;
+static uint64_t g_infer_attn_seed = 0;
+static const uint32_t* g_infer_attn_seed_dev = nullptr;
+
 }  // namespace f5b
 
 using namespace f5b;
@@ -76,6 +82,14 @@ extern "C" {
 
 const char* f5b_last_error(void) { return f5b::last_error(); }
 int f5b_abi_version(void) { return F5B_ABI_VERSION; }
+
+int f5b_dit_set_attn_dropout(float p, uint64_t seed, const uint32_t* seed_dev) {
+  F5B_CHECK(p >= 0.f && p < 1.f, "f5b_dit_set_attn_dropout: p must be in [0, 1)");
+  g_infer_attn_p = p;
+  g_infer_attn_seed = seed;
+  g_infer_attn_seed_dev = seed_dev;
+  return 0;
+}
 
 int f5b_dit_create(const F5bDitDesc* desc, F5bDit** out) {
   F5B_CHECK(desc && out, "f5b_dit_create: null argument");
@@ -241,9 +255,12 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
     F5B_TRY(gemm(w.hb, D, wat(d, d.qkv_w, (size_t)i * 3 * D * D), D, g, s));
     if (tp) {
       const float* q = reinterpret_cast<const float*>(w.qkv);
+      F5B_CHECK(!(g_infer_attn_p > 0.f), "f5b_dit_forward: attention dropout is built for the bf16 operand mode only");
       F5B_TRY(attn_fwd_tf32(q, q + D, q + 2 * D, 3 * D, reinterpret_cast<float*>(w.ab), w.vt, lens, batch_mod, Bf, H, n, 0.125f, s));
     } else {
-      F5B_TRY(attn_fwd(w.qkv, aat(d, w.qkv, D), aat(d, w.qkv, 2 * D), 3 * D, w.ab, nullptr, lens, batch_mod, Bf, H, n, 0.125f, s));
+      const AttnDrop adrop = make_attn_drop(g_infer_attn_p, g_infer_attn_seed, i);  // off unless f5b_dit_set_attn_dropout asked for it
+      F5B_TRY(attn_fwd(w.qkv, aat(d, w.qkv, D), aat(d, w.qkv, 2 * D), 3 * D, w.ab, nullptr, lens, batch_mod, Bf, H, n, 0.125f, s, &adrop,
+                       g_infer_attn_seed_dev));
     }
     F5B_TRY(linear_gate_resid(w.ab, D, wat(d, d.out_w, (size_t)i * D * D), D, d.out_b + (size_t)i * D, w.x, D, rows, D, D, n, m + 2 * D,
                               mod_bstride, lens, batch_mod, s, tp));

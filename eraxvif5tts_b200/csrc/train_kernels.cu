@@ -874,14 +874,15 @@ Drop drop_for_site(int layer, int site) {
 }
 static Drop drop_for(int layer, int site) { return drop_for_site(layer, site); }
 // SDPA's dropout (site 2) draws from its own Philox stream (dropout.cuh); same seed, same per-(layer, site) key derivation
-AttnDrop attn_drop_for_layer(int layer) {
-  if (!(g_attn_drop_p > 0.f)) return AttnDrop{0u, 1.f, 0.f, 0u, 0u};
-  int t7 = (int)(g_attn_drop_p * 128.0f + 0.5f);
+AttnDrop make_attn_drop(float p, uint64_t seed, int layer) {
+  if (!(p > 0.f)) return AttnDrop{0u, 1.f, 0.f, 0u, 0u};
+  int t7 = (int)(p * 128.0f + 0.5f);
   t7 = t7 < 1 ? 1 : (t7 > 127 ? 127 : t7);
   const float scale = 128.0f / (float)(128 - t7);
-  const uint64_t key = g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + 3) * 0x9E3779B97F4A7C15ull;
+  const uint64_t key = seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + 3) * 0x9E3779B97F4A7C15ull;
   return AttnDrop{(uint32_t)(128 - t7) * 0x01010101u, scale, log2f(scale), (uint32_t)key, (uint32_t)(key >> 32)};
 }
+AttnDrop attn_drop_for_layer(int layer) { return make_attn_drop(g_attn_drop_p, g_drop_seed, layer); }
 }  // namespace f5b
 
 extern "C" {

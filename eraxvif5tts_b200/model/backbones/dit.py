@@ -256,7 +256,7 @@ class DiTEngine:
         return self._rope[n]
 
     # ---- CUDA-graph step sessions (launch-bound regimes: small batches, e.g. the reference's serial B=1 chunks) ----
-    def step_session(self, Bx: int, Bf: int, n: int, masked: bool):
+    def step_session(self, Bx: int, Bf: int, n: int, masked: bool, attn_p: float = 0.0):
         """Persistent buffers + one captured CUDA graph of {DiT.forward over the fused batch, CFG + Euler update} for a given
         shape.  Per ODE step only `stepbuf` (that step's modulation row followed by (cfg, dt)) changes, so the same graph is
         replayed for all steps and all later sample() calls of this shape."""
@@ -264,8 +264,8 @@ class DiTEngine:
         # forward share no data but the read-only state, so the captured step can fork into two B-row forwards on two streams
         # instead of one fused 2B-row batch (bit-identical results; measured slower)
         env = os.environ.get("F5B_SPLIT_CFG", "")
-        split = Bf == 2 * Bx and env != "0" and (env == "1" or Bf * n <= SPLIT_CFG_MAX_ROWS)
-        key = (Bx, Bf, n, masked, split)
+        split = Bf == 2 * Bx and env != "0" and (env == "1" or Bf * n <= SPLIT_CFG_MAX_ROWS) and not attn_p > 0
+        key = (Bx, Bf, n, masked, float(attn_p), split)
         sess = self._sessions.get(key)
         if sess is not None:
             self._sessions[key] = self._sessions.pop(key)  # LRU order
@@ -277,7 +277,7 @@ class DiTEngine:
         sess = dict(
             y=torch.zeros(Bx, n, mel, dtype=f32, device=dev), yb=torch.zeros(Bx * n, 128, dtype=self.act_dtype, device=dev),
             c0=torch.zeros(Bf, n, self.dim, dtype=f32, device=dev), pred=torch.zeros(Bf, n, mel, dtype=f32, device=dev),
-            stepbuf=torch.zeros(self.mod_dim + 2, dtype=f32, device=dev),
+            stepbuf=torch.zeros(self.mod_dim + 3, dtype=f32, device=dev),  # modulation row | cfg | dt | attention-dropout word
             lens=torch.full((Bx,), n, dtype=torch.int32, device=dev) if masked else None, graph=None, delta=None,
             rope=self.rope_table(n), ws=None, split=split)  # the graph bakes these pointers in: the session keeps them alive
         if split:
@@ -289,6 +289,8 @@ class DiTEngine:
             sess["ws"] = self.workspace(self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n))
         pc, pu = sess["pred"][:Bx], (sess["pred"][Bx:] if Bf > Bx else None)
         params = sess["stepbuf"][self.mod_dim:]
+        # SDPA dropout at inference (DiT.set_attn_dropout): p is baked into the graph, the mask stream follows the device word
+        adrop = (float(attn_p), 0, sess["stepbuf"][self.mod_dim + 2:]) if attn_p > 0 else None
 
         def body():
             if split:
@@ -299,7 +301,7 @@ class DiTEngine:
                     self.forward(sess["yb"], Bx, sess["c0"][Bx:], Bx, n, sess["stepbuf"], 0, sess["lens"], pu, ws=sess["ws2"])
                 cur.wait_stream(fork)
             else:
-                self.forward(sess["yb"], Bx, sess["c0"], Bf, n, sess["stepbuf"], 0, sess["lens"], sess["pred"])
+                self.forward(sess["yb"], Bx, sess["c0"], Bf, n, sess["stepbuf"], 0, sess["lens"], sess["pred"], attn_drop=adrop)
             if self.precision == "tf32":
                 L.check(self.lib.f5b_cfg_euler_dev(sess["y"].data_ptr(), pc.data_ptr(), L.ptr(pu), params.data_ptr(), None, 128, None,
                                                    Bx * n, mel, L.stream()), "f5b_cfg_euler_dev")
@@ -366,9 +368,12 @@ class DiTEngine:
         (ops.pack_tf32 if self.precision == "tf32" else ops.pack_bf16)(y.view(rows, self.mel_dim), yb, self.mel_dim, 128)
         return yb
 
-    def forward(self, x_bf16, Bx, c0, Bf, n, mod, mod_bstride, lens, pred, ws=None):
+    def forward(self, x_bf16, Bx, c0, Bf, n, mod, mod_bstride, lens, pred, ws=None, attn_drop=None):
         """x_bf16: the packed state from `pack_state` (bf16, or fp32 in the tf32 mode); ws: a private workspace (default: the
-        engine's shared one)"""
+        engine's shared one); attn_drop: None or (p, seed, device word tensor or None) — the reference's SDPA dropout at inference
+        (modules.py:490), see DiT.set_attn_dropout"""
+        ap, aseed, adev = attn_drop if attn_drop is not None else (0.0, 0, None)
+        L.check(self.lib.f5b_dit_set_attn_dropout(float(ap), int(aseed) & ((1 << 64) - 1), L.ptr(adev)), "f5b_dit_set_attn_dropout")
         assert x_bf16.dtype == self.act_dtype
         nbytes = self.lib.f5b_dit_workspace_bytes(self.handle, Bf, n)
         if ws is None:
@@ -409,6 +414,7 @@ class DiT(nn.Module):
         self.proj_out = nn.Linear(dim, mel_dim)
         self.checkpoint_activations = checkpoint_activations
         self.precision = precision  # extension: "bf16" (throughput) or "tf32" (1e-3 of the fp32 reference); set_precision() switches
+        self.attn_dropout_p = 0.0   # extension: SDPA dropout at inference (set_attn_dropout); 0 = the parity setting
         self.initialize_weights()
         self._engine = None
         self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
@@ -441,6 +447,16 @@ class DiT(nn.Module):
             self.invalidate()
         return self
 
+    def set_attn_dropout(self, p: float):
+        """The reference passes dropout_p = 0.1 to F.scaled_dot_product_attention unconditionally (model/modules.py:490), so its own
+        inference is stochastic in attention even under eval().  Parity is defined at p = 0 (default); p > 0
+        reproduces that behaviour statistically (same distribution, the product's own mask stream; bf16 operand mode).  The training
+        step has its own switch (`TrainEngine(attn_dropout=)`)."""
+        if not 0.0 <= p < 1.0:
+            raise ValueError("attn dropout p must be in [0, 1)")
+        self.attn_dropout_p = float(p)
+        return self
+
     def engine(self) -> DiTEngine:
         dev = self.proj_out.weight.device
         if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
@@ -452,9 +468,10 @@ class DiT(nn.Module):
 
     @L.on_own_device
     @torch.no_grad()
-    def forward(self, x, cond, text, time, drop_audio_cond, drop_text, mask=None, cache=False):
+    def forward(self, x, cond, text, time, drop_audio_cond, drop_text, mask=None, cache=False, attn_dropout_seed: int | None = None):
         """x, cond [b, n, mel]; text int [b, nt]; time [] or [b]; mask bool [b, n] (a prefix / key-padding mask as built by
-        lens_to_mask, cfm.py:152-153) -> [b, n, mel].  No autograd graph: the training step is `train.TrainEngine`."""
+        lens_to_mask, cfm.py:152-153) -> [b, n, mel].  No autograd graph: the training step is `train.TrainEngine`.
+        attn_dropout_seed (extension): fixes the mask stream when set_attn_dropout(p > 0) is active (default: a fresh draw)."""
         eng = self.engine()
         b, n = x.shape[0], x.shape[1]
         time = time.to(device=eng.device, dtype=f32)
@@ -477,5 +494,9 @@ class DiT(nn.Module):
         if mask is not None:
             lens = mask.sum(dim=-1).to(torch.int32).contiguous()
         pred = torch.empty(b, n, self.mel_dim, dtype=f32, device=eng.device)
-        eng.forward(xb, b, c0, b, n, mod, mod_bstride, lens, pred)
+        adrop = None
+        if self.attn_dropout_p > 0:
+            s = int(torch.randint(0, 2 ** 62, (1,)).item()) if attn_dropout_seed is None else int(attn_dropout_seed)
+            adrop = (self.attn_dropout_p, s, None)
+        eng.forward(xb, b, c0, b, n, mod, mod_bstride, lens, pred, attn_drop=adrop)
         return pred.to(x.dtype)

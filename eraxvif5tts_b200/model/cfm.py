@@ -136,7 +136,10 @@ class CFM(nn.Module):
                      and not L.load().f5b_prof_enabled())
         # dependent launches (kernel prologues under the previous kernel's tail) pay in the launch-bound regime only
         L.set_dependent_launch(Bf * n <= L.PDL_MAX_ROWS)
-        sess = eng.step_session(batch, Bf, n, lens32 is not None) if use_graph else None
+        # the reference's SDPA dropout at inference (DiT.set_attn_dropout, default off): one mask stream per ODE evaluation
+        attn_p = float(getattr(self.transformer, "attn_dropout_p", 0.0))
+        attn_base = (int(seed) if exists(seed) else int(torch.randint(0, 2 ** 31, (1,)).item())) if attn_p > 0 else 0
+        sess = eng.step_session(batch, Bf, n, lens32 is not None, attn_p) if use_graph else None
         c0 = sess["c0"] if use_graph else torch.empty(Bf, n, eng.dim, dtype=f32, device=device)
         te_c = eng.text_embed(text, n, False)
         eng.input_const(step_cond, te_c, out=c0[:batch])
@@ -176,7 +179,13 @@ class CFM(nn.Module):
         ymid = torch.empty_like(y) if method == "midpoint" else None
         if use_graph:
             # per step: [modulation row | cfg | dt] -> stepbuf (one small D2D copy), then replay the captured step
-            table = torch.cat((mod, torch.full((steps, 1), float(cfg_strength), device=device), dt.unsqueeze(1)), dim=1).contiguous()
+            # (the dropout word travels as the mantissa of a float in [1, 2): any copy preserves its bits)
+            words = torch.tensor([0x3F800000 | ((attn_base * 0x9E3779B1 + i * 0x85EBCA77) & 0x7FFFFF) for i in range(steps)],
+                                 dtype=torch.int32, device=device).view(f32).unsqueeze(1)
+            table = torch.cat((mod, torch.full((steps, 1), float(cfg_strength), device=device), dt.unsqueeze(1), words), dim=1).contiguous()
+
+        def adrop(k):
+            return (attn_p, attn_base * 1000003 + k, None) if attn_p > 0 else None
 
         # ---- ODE loop (fn closure cfm.py:159-173 + torchdiffeq fixed-grid solver) ---------------------------------------
         for i in range(steps):
@@ -185,13 +194,13 @@ class CFM(nn.Module):
                 sess["graph"].replay()
                 L.prof_add(sess["delta"])
             elif method == "euler":
-                eng.forward(yb, batch, c0, Bf, n, mod[i], 0, lens32, pred)
+                eng.forward(yb, batch, c0, Bf, n, mod[i], 0, lens32, pred, attn_drop=adrop(2 * i))
                 euler(y, dt_host[i])
             else:
-                eng.forward(yb, batch, c0, Bf, n, mod[2 * i], 0, lens32, pred)
+                eng.forward(yb, batch, c0, Bf, n, mod[2 * i], 0, lens32, pred, attn_drop=adrop(2 * i))
                 ymid.copy_(y)
                 euler(ymid, 0.5 * dt_host[i])
-                eng.forward(yb, batch, c0, Bf, n, mod[2 * i + 1], 0, lens32, pred)
+                eng.forward(yb, batch, c0, Bf, n, mod[2 * i + 1], 0, lens32, pred, attn_drop=adrop(2 * i + 1))
                 euler(y, dt_host[i])
             if return_trajectory:
                 traj.append(y.clone())

@@ -280,6 +280,14 @@ int f5b_dit_forward(const F5bDit* h, const void* x_bf16, int Bx, const float* c0
                     int64_t mod_bstride, const int32_t* lens, const float* rope, float* pred, void* ws, size_t ws_bytes,
                     f5b_stream_t stream);
 
+/* The reference's attention dropout at INFERENCE: /root/reference/src/f5_tts/model/modules.py:490 passes dropout_p = 0.1 to
+ * F.scaled_dot_product_attention unconditionally, so the reference's own sampling is stochastic in attention even under eval()
+ * (SURVEY.md 9.1).  Parity is defined at p = 0 (the default here); this switch reproduces the reference's behaviour statistically
+ * (same distribution, the product's own Philox stream — see f5b_train_set_attn_dropout) for the following f5b_dit_forward calls,
+ * bf16 operand mode only.  `seed` selects the stream; `seed_dev` (device uint32, may be NULL) is read by the kernels at run time and
+ * mixed into it, so that a captured CUDA graph replays with a fresh mask whenever the word changes.  p = 0 switches it off. */
+int f5b_dit_set_attn_dropout(float p, uint64_t seed, const uint32_t* seed_dev);
+
 /* ---- training step: DiT.forward with saved activations + hand-written backward (CFM.forward / accelerator.backward,
  * model/cfm.py:210-283, model/trainer.py:1271-1287; dropout 0) ------------------------------------------------------------------
  * F5bDitGrads: f32 gradient buffers, one per F5bDitDesc tensor and of the same shape, except that the conv_pos_embed weight

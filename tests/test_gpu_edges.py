@@ -117,6 +117,55 @@ def test_cfg_branches_as_concurrent_chains_are_bit_identical(B, totals, monkeypa
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_inference_attention_dropout_vs_oracle_and_sampling():
+    """the reference's SDPA dropout is active at inference too (model/modules.py:490); DiT.set_attn_dropout(p) switches
+    it on: one DiT.forward against the oracle with the identical mask, then CFM.sample through the captured-graph path (mask stream
+    driven by a device word per ODE step): deterministic per seed, different across seeds, different from p = 0"""
+    cfg = O.DiTConfig.tiny()
+    model, sd = build_cfm(cfg, 0)
+    B, n = 2, 203
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, n, cfg.mel_dim, generator=g)
+    cond = torch.randn(B, n, cfg.mel_dim, generator=g)
+    text = torch.randint(0, cfg.text_num_embeds - 1, (B, 30), generator=g)
+    time = torch.tensor(0.4)
+    dit = model.transformer
+    base = dit(x=x.cuda(), cond=cond.cuda(), text=text.cuda(), time=time.cuda(), drop_audio_cond=False, drop_text=False)
+    dit.set_attn_dropout(0.5)
+    out = dit(x=x.cuda(), cond=cond.cuda(), text=text.cuda(), time=time.cuda(), drop_audio_cond=False, drop_text=False,
+              attn_dropout_seed=77)
+    ref = O.dit_forward(sd, cfg, x, cond, text, time, False, False, None, dropout=(0.0, 77, 0.5))
+    ref0 = O.dit_forward(sd, cfg, x, cond, text, time, False, False, None)
+    torch.cuda.synchronize()
+    assert maxabs(out, ref) <= 2e-2, maxabs(out, ref)
+    # the mask matters, and it is the oracle's mask: the change it causes on the GPU is the change it causes in the oracle
+    dg, do = (out - base).cpu().flatten().double(), (ref - ref0).flatten().double()
+    cos = float((dg * do).sum() / (dg.norm() * do.norm()))
+    assert float(do.abs().max()) > 2e-3 and cos > 0.8, (float(do.abs().max()), cos)
+    dit.set_attn_dropout(0.2)
+    # sampling: graph path (default) with the per-step device word
+    cond_s, text_s, duration, lens = synthetic_inputs(cfg, 2, 40, [96, 83], seed=1)
+    kw = dict(cond=cond_s.cuda(), text=text_s.cuda(), duration=duration.cuda(), lens=lens.cuda(), steps=4, cfg_strength=2.0,
+              sway_sampling_coef=-1.0)
+    a, _ = model.sample(seed=5, **kw)
+    a = a.clone()
+    b, _ = model.sample(seed=5, **kw)
+    b = b.clone()
+    dit.set_attn_dropout(0.0)
+    z, _ = model.sample(seed=5, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    gen = slice(40, None)
+    d = (a - z)[:, gen].abs()
+    assert float(d.max()) > 1e-3 and float(d.mean()) < 0.5, (float(d.max()), float(d.mean()))
+    dit.set_attn_dropout(0.2)
+    model.transformer.set_precision("tf32")
+    with pytest.raises(Exception):
+        dit(x=x.cuda(), cond=cond.cuda(), text=text.cuda(), time=time.cuda(), drop_audio_cond=False, drop_text=False)
+    model.transformer.set_precision("bf16")
+    dit.set_attn_dropout(0.0)
+
+
 def test_attention_forward_is_deterministic_with_many_ctas_per_sm():
     """regression: the P.V completion barrier used to be a single mbarrier whose phase advanced once per key tile, while the softmax
     threads waited on it only in the epilogue; a warp running a full tile ahead of the slowest one then saw the parity of a phase
