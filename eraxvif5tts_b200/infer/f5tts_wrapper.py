@@ -15,55 +15,10 @@ import numpy as np
 import torch
 
 from ..model import CFM, DiT
-from ..model.utils import get_tokenizer
+from ..model.utils import convert_char_to_pinyin, get_tokenizer  # noqa: F401  (convert_char_to_pinyin: re-exported, older import path)
 from .. import _lib as L
 from .utils_infer import chunk_text, load_checkpoint, load_vocoder, resolve_arch
 
-_CUSTOM_TRANS = str.maketrans({";": ",", "“": '"', "”": '"', "‘": "'", "’": "'"})
-
-
-def convert_char_to_pinyin(text_list, polyphone=True):
-    """model/utils.py:243-284.  With jieba + pypinyin present the reference algorithm runs unchanged; without them (this
-    image) non-CJK text takes the same character-level path the reference produces for Latin / Vietnamese script."""
-    try:
-        import jieba
-        from pypinyin import Style, lazy_pinyin
-        if not hasattr(jieba, "cut"):
-            jieba = None
-    except ImportError:
-        jieba = None
-    out = []
-    for text in text_list:
-        text = text.translate(_CUSTOM_TRANS)
-        if jieba is None:
-            if any("㄀" <= c <= "鿿" for c in text):
-                raise RuntimeError("Chinese text needs jieba + pypinyin, which are not installed in this image")
-            out.append(list(text))
-            continue
-        char_list = []
-        for seg in jieba.cut(text):
-            seg_byte_len = len(bytes(seg, "UTF-8"))
-            if seg_byte_len == len(seg):
-                if char_list and seg_byte_len > 1 and char_list[-1] not in " :'\"":
-                    char_list.append(" ")
-                char_list.extend(seg)
-            elif polyphone and seg_byte_len == 3 * len(seg):
-                seg_ = lazy_pinyin(seg, style=Style.TONE3, tone_sandhi=True)
-                for i, c in enumerate(seg):
-                    if "㄀" <= c <= "鿿":
-                        char_list.append(" ")
-                    char_list.append(seg_[i])
-            else:
-                for c in seg:
-                    if ord(c) < 256:
-                        char_list.extend(c)
-                    elif "㄀" <= c <= "鿿":
-                        char_list.append(" ")
-                        char_list.extend(lazy_pinyin(c, style=Style.TONE3, tone_sandhi=True))
-                    else:
-                        char_list.append(c)
-        out.append(char_list)
-    return out
 
 
 def _read_wav(path: str):
@@ -175,21 +130,39 @@ def clip_reference(x: torch.Tensor, sr: int) -> torch.Tensor:
     return wave
 
 
+def remove_silence_edges(x: torch.Tensor, sr: int, silence_threshold: float = -42.0) -> torch.Tensor:
+    """remove_silence_edges / F5TTSWrapper._remove_silence_edges (utils_infer.py:273-286, f5tts_wrapper.py:356-378) restated on a mono
+    float signal `x` [samples]: pydub's detect_leading_silence walks 10 ms chunks from the start while their level is below the
+    threshold; the tail is walked in 1 ms slices from the end until one is louder than the threshold, and the cut lands on
+    int((duration_seconds - 0.001 * slices) * 1000) ms.  Levels are RMS dBFS of the slice (pydub: audioop.rms on the PCM)."""
+    def levels(sig, step_ms):
+        seg_len = int(round(1000.0 * sig.numel() / sr))
+        if seg_len == 0:
+            return seg_len, torch.empty(0, dtype=torch.float64)
+        csum = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(sig.double().square(), 0)))
+        starts = torch.arange(0, seg_len, step_ms)
+        s0 = torch.tensor([_ms_to_samples(int(i), sr) for i in starts]).clamp(max=sig.numel())
+        s1 = torch.tensor([_ms_to_samples(min(int(i) + step_ms, seg_len), sr) for i in starts]).clamp(max=sig.numel())
+        ms_ = (csum[s1] - csum[s0]) / (s1 - s0).clamp(min=1).double()
+        return seg_len, 10.0 * torch.log10(ms_.clamp(min=1e-30))  # an all-zero slice is -inf dBFS in pydub: far below any threshold
+
+    seg_len, db10 = levels(x, 10)
+    loud = (db10 >= silence_threshold).nonzero()  # the walk continues while dBFS < threshold
+    lead_ms = min(int(loud[0]) * 10 if loud.numel() else ((seg_len + 9) // 10) * 10, seg_len)
+    x = x[_ms_to_samples(lead_ms, sr):]
+    seg_len, db1 = levels(x, 1)
+    loud = (db1 > silence_threshold).nonzero()
+    quiet_tail = seg_len - 1 - int(loud[-1]) if loud.numel() else seg_len
+    dur = x.numel() / sr
+    for _ in range(quiet_tail):  # the reference subtracts 0.001 per slice in floating point; int(dur * 1000) depends on that rounding
+        dur -= 0.001
+    end_ms = int(dur * 1000)
+    return x[: _ms_to_samples(max(end_ms, 0), sr)]
+
+
 def _trim_silence_edges(audio: torch.Tensor, sr: int, threshold_db: float = -42.0) -> torch.Tensor:
-    """_remove_silence_edges (f5tts_wrapper.py:356-377) restated on a tensor: drop leading / trailing 1 ms... 10 ms windows whose
-    level is below the threshold (pydub measures dBFS on chunks)."""
-    x = audio[0]
-    win = max(1, sr // 100)
-    nwin = x.numel() // win
-    if nwin == 0:
-        return audio
-    rms = x[: nwin * win].reshape(nwin, win).square().mean(dim=1).sqrt()
-    db = 20.0 * torch.log10(rms.clamp(min=1e-10))
-    loud = (db > threshold_db).nonzero()
-    if loud.numel() == 0:
-        return audio
-    s, e = int(loud[0]) * win, (int(loud[-1]) + 1) * win
-    return audio[:, s:e]
+    """[1, samples] form of remove_silence_edges"""
+    return remove_silence_edges(audio[0], sr, threshold_db).unsqueeze(0)
 
 
 class F5TTSWrapper:
@@ -278,6 +251,12 @@ class F5TTSWrapper:
         return audio, ref_text
 
     # ------------------------------------------------------------------------------------------------------------------
+    def _remove_silence_edges(self, audio, silence_threshold=-42, sample_rate: Optional[int] = None):
+        """f5tts_wrapper.py:356-378 on a float tensor [samples] or [1, samples] instead of a pydub AudioSegment"""
+        a = torch.as_tensor(audio, dtype=torch.float32)
+        sr = sample_rate or self.target_sample_rate
+        return _trim_silence_edges(a, sr, silence_threshold) if a.ndim == 2 else remove_silence_edges(a, sr, silence_threshold)
+
     def attach_duration_predictor(self, duration_predictor, tokenizer=None, use: bool = True):
         """model/f5tts_wrapper-dur_pred.py:169-230.  `tokenizer(text) -> (ids: list[int], is_phoneme: bool)` turns a text chunk into
         the predictor's input; the reference phonemizes with espeak (alignment_utils.py:39-58, not available offline) and calls

@@ -1,5 +1,6 @@
 """Inference helpers with the reference's names (/root/reference/src/f5_tts/infer/utils_infer.py): defaults, chunk_text,
-load_vocoder, load_checkpoint, load_model.  Host-side glue only."""
+load_vocoder, load_checkpoint, load_model, preprocess_ref_audio_text, remove_silence_edges, remove_silence_for_generated_wav,
+infer_process / infer_batch_process.  Host-side glue only."""
 from __future__ import annotations
 
 import os
@@ -234,3 +235,59 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
         return
     final = ops.crossfade_concat(waves, int(cross_fade_duration * target_sample_rate) if cross_fade_duration > 0 else 0)
     yield final.cpu().numpy(), target_sample_rate, np.concatenate(mels, axis=1)
+
+
+# ---- reference-audio / output-file helpers (utils_infer.py:273-360, 569-578); pydub is absent offline, so these work on PCM wav files
+# and float tensors through the restated silence search of infer/f5tts_wrapper.py -------------------------------------------------
+_ref_audio_cache: dict = {}
+
+
+def remove_silence_edges(audio, silence_threshold=-42, sample_rate: int = target_sample_rate):
+    """utils_infer.py:273-286 on a mono float tensor [samples] (the reference takes a pydub AudioSegment)"""
+    from .f5tts_wrapper import remove_silence_edges as _edges
+    return _edges(torch.as_tensor(audio, dtype=torch.float32).reshape(-1), sample_rate, silence_threshold)
+
+
+def preprocess_ref_audio_text(ref_audio_orig, ref_text, clip_short=True, show_info=print):
+    """utils_infer.py:292-360: clip the reference at a silence so that it stays under 12 s, trim the silent edges, append 50 ms of
+    silence, write the result to a temporary wav and make sure the text ends with sentence punctuation.  Returns (wav path, text).
+    The Whisper transcription of an empty `ref_text` is outside this path (no ASR model offline): it raises."""
+    import hashlib
+    import tempfile
+    from .f5tts_wrapper import _read_wav, _write_wav, clip_reference, remove_silence_edges as _edges
+    show_info("Converting audio...")
+    audio, sr = _read_wav(str(ref_audio_orig))
+    x = audio.float().mean(dim=0) if audio.shape[0] > 1 else audio[0].float()
+    if clip_short:
+        n0 = x.numel()
+        x = clip_reference(x, sr)
+        if x.numel() < n0:
+            show_info("Audio is over 12s, clipping short.")
+    x = torch.cat((_edges(x, sr), torch.zeros(int(0.05 * sr))))
+    with tempfile.NamedTemporaryFile(delete=False, suffix=".wav") as f:
+        ref_audio = f.name
+    _write_wav(ref_audio, x.numpy(), sr)
+    with open(ref_audio, "rb") as fh:
+        audio_hash = hashlib.md5(fh.read()).hexdigest()
+    if not ref_text.strip():
+        if audio_hash in _ref_audio_cache:
+            show_info("Using cached reference text...")
+            ref_text = _ref_audio_cache[audio_hash]
+        else:
+            raise RuntimeError("auto-transcription needs the Whisper pipeline, which is not available offline; pass ref_text")
+    else:
+        show_info("Using custom reference text...")
+    if not ref_text.endswith(". ") and not ref_text.endswith("。"):
+        ref_text += " " if ref_text.endswith(".") else ". "
+    return ref_audio, ref_text
+
+
+def remove_silence_for_generated_wav(filename):
+    """utils_infer.py:569-578: drop every silence of >= 1 s below -50 dBFS from a generated wav file in place, keeping 500 ms on
+    each side of the cuts"""
+    from .f5tts_wrapper import _read_wav, _write_wav, split_on_silence
+    audio, sr = _read_wav(str(filename))
+    x = audio.float().mean(dim=0) if audio.shape[0] > 1 else audio[0].float()
+    pieces = split_on_silence(x, sr, min_silence_len=1000, silence_thresh=-50, keep_silence=500, seek_step=10)
+    out = torch.cat(pieces) if pieces else x[:0]
+    _write_wav(str(filename), out.numpy(), sr)

@@ -60,3 +60,33 @@ class MelSpec(nn.Module):
 
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
         return self.forward_token_major(wav).permute(0, 2, 1)
+
+
+_MELSPEC_CACHE: dict = {}
+
+
+def get_vocos_mel_spectrogram(waveform, n_fft=1024, n_mel_channels=100, target_sample_rate=24000, hop_length=256, win_length=1024):
+    """The functional form the reference's MelSpec delegates to (model/modules.py:75-101): waveform [b, nw] (or [b, 1, nw]) on the
+    GPU -> log-mel [b, n_mels, frames], through the same `f5b_melspec` kernel as `MelSpec`."""
+    key = (n_fft, hop_length, win_length, n_mel_channels, target_sample_rate)
+    if key not in _MELSPEC_CACHE:
+        _MELSPEC_CACHE[key] = MelSpec(n_fft=n_fft, hop_length=hop_length, win_length=win_length, n_mel_channels=n_mel_channels,
+                                      target_sample_rate=target_sample_rate, mel_spec_type="vocos")
+    if waveform.ndim == 3:
+        waveform = waveform.squeeze(1)
+    return _MELSPEC_CACHE[key](waveform)
+
+
+def precompute_freqs_cis(dim: int, end: int, theta: float = 10000.0, theta_rescale_factor=1.0):
+    """model/modules.py:196-207 (the TextEmbedding position table); the DiT engine's own copy lives in backbones/dit.py"""
+    theta = theta * theta_rescale_factor ** (dim / (dim - 2))
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: (dim // 2)].float() / dim))
+    freqs = torch.outer(torch.arange(end), freqs).float()
+    return torch.cat([torch.cos(freqs), torch.sin(freqs)], dim=-1)
+
+
+def get_pos_embed_indices(start, length, max_pos, scale=1.0):
+    """model/modules.py:210-219: start [b] -> position indices [b, length], start + floor(arange * scale), clamped below max_pos"""
+    scale = scale * torch.ones_like(start, dtype=torch.float32)
+    pos = start.unsqueeze(1) + (torch.arange(length, device=start.device, dtype=torch.float32).unsqueeze(0) * scale.unsqueeze(1)).long()
+    return torch.where(pos < max_pos, pos, max_pos - 1)

@@ -514,6 +514,86 @@ def test_silence_aware_reference_clipping_matches_pydub_rules():
     assert 6.0 < len(w) / sr <= 12.0 and len(w) < len(y)
 
 
+def test_silence_edge_trimming_and_reference_file_helpers(tmp_path):
+    """remove_silence_edges (utils_infer.py:273-286 = F5TTSWrapper._remove_silence_edges) against a literal transcription of pydub's
+    two loops (10 ms chunks from the start while dBFS < threshold; 1 ms slices from the end until one is louder), then the file-level
+    mirrors preprocess_ref_audio_text (:292-360) and remove_silence_for_generated_wav (:569-578) on PCM wav files."""
+    import math
+    from eraxvif5tts_b200.infer import utils_infer as UI
+    from eraxvif5tts_b200.infer.f5tts_wrapper import _read_wav, _write_wav, remove_silence_edges
+
+    def literal(x, sr, thr):
+        def seg_len(sig):
+            return int(round(1000.0 * len(sig) / sr))
+
+        def dbfs(sl):
+            r = math.sqrt(float((sl.double() ** 2).mean())) if len(sl) else 0.0
+            return 20 * math.log10(r) if r > 0 else -math.inf
+        trim = 0
+        while trim < seg_len(x) and dbfs(x[int(trim * sr / 1000): int(min(trim + 10, seg_len(x)) * sr / 1000)]) < thr:
+            trim += 10
+        x = x[int(min(trim, seg_len(x)) * sr / 1000):]
+        dur = len(x) / sr
+        for i in range(seg_len(x) - 1, -1, -1):
+            if dbfs(x[int(i * sr / 1000): int((i + 1) * sr / 1000)]) > thr:
+                break
+            dur -= 0.001
+        return x[: int(int(dur * 1000) * sr / 1000)]
+
+    g = torch.Generator().manual_seed(1)
+    sr = 8000
+    for lead, tail, amp in ((0.237, 0.4113, 0.2), (0.0, 0.0, 0.3), (0.055, 1.2, 0.05)):
+        x = torch.cat((torch.randn(int(lead * sr), generator=g) * 1e-4, torch.randn(int(1.7 * sr), generator=g) * amp,
+                       torch.randn(int(tail * sr), generator=g) * 1e-4)).clamp(-1, 1)
+        got, want = remove_silence_edges(x, sr, -42), literal(x, sr, -42)
+        assert got.numel() == want.numel() and torch.equal(got, want), (lead, tail, got.numel(), want.numel())
+        assert abs(got.numel() / sr - 1.7) < 0.02
+    assert remove_silence_edges(torch.zeros(sr), sr, -42).numel() == 0  # all silent
+    assert UI.remove_silence_edges(x, -42, sr).numel() == remove_silence_edges(x, sr, -42).numel()
+    # preprocess_ref_audio_text: 20 s of speech-like noise with a 1.3 s pause after 7 s -> clipped at the pause, edges trimmed, + 50 ms
+    sr = 24000
+    sig = torch.cat((torch.zeros(int(0.2 * sr)), torch.randn(7 * sr, generator=g) * 0.2, torch.zeros(int(1.3 * sr)),
+                     torch.randn(12 * sr, generator=g) * 0.2)).clamp(-1, 1)
+    src = str(tmp_path / "ref.wav")
+    _write_wav(src, sig.numpy(), sr)
+    msgs = []
+    path, text = UI.preprocess_ref_audio_text(src, "xin chào", show_info=msgs.append)
+    out, sr2 = _read_wav(path)
+    assert sr2 == sr and text == "xin chào. " and any("clipping" in m for m in msgs)
+    assert abs(out.shape[-1] / sr - (7.0 + 0.05)) < 0.03  # first piece = lead 0.2 + 7 s + half the pause; both quiet edges trimmed again
+    path2, text2 = UI.preprocess_ref_audio_text(src, "Đã có dấu chấm.", clip_short=False, show_info=lambda m: None)
+    out2, _ = _read_wav(path2)
+    assert text2 == "Đã có dấu chấm. " and abs(out2.shape[-1] / sr - (20.3 + 0.05)) < 0.03
+    import pytest
+    with pytest.raises(RuntimeError):
+        UI.preprocess_ref_audio_text(src, "  ")
+    # remove_silence_for_generated_wav: the 1.3 s pause shrinks to 2 x 500 ms
+    gen = str(tmp_path / "gen.wav")
+    _write_wav(gen, sig[int(0.2 * sr):].numpy(), sr)
+    UI.remove_silence_for_generated_wav(gen)
+    out3, _ = _read_wav(gen)
+    assert abs(out3.shape[-1] / sr - (7 + 1.0 + 12)) < 0.03
+
+
+def test_small_reference_helpers():
+    """model/utils.py: seed_everything, maybe_masked_mean, repetition_found; model/modules.py: get_pos_embed_indices, precompute_freqs_cis"""
+    from eraxvif5tts_b200.model import utils as U
+    from eraxvif5tts_b200.model import modules as M
+    U.seed_everything(3)
+    a = torch.rand(2)
+    U.seed_everything(3)
+    assert torch.equal(a, torch.rand(2))
+    t = torch.arange(24, dtype=torch.float32).reshape(2, 4, 3)
+    mask = torch.tensor([[True, True, False, False], [False, False, False, False]])
+    assert torch.equal(U.maybe_masked_mean(t), t.mean(dim=1))
+    mm = U.maybe_masked_mean(t, mask)
+    assert torch.allclose(mm[0], t[0, :2].mean(dim=0)) and torch.equal(mm[1], torch.zeros(3))
+    assert U.repetition_found("ab" * 12) and not U.repetition_found("the quick brown fox")
+    assert M.get_pos_embed_indices(torch.tensor([0, 5]), 6, 8).tolist() == [[0, 1, 2, 3, 4, 5], [5, 6, 7, 7, 7, 7]]
+    from eraxvif5tts_b200.model.backbones.dit import precompute_freqs_cis as eng_table
+    assert torch.equal(M.precompute_freqs_cis(64, 128), eng_table(64, 128))
+
+
 def test_plan_ragged_batches_budget_and_coverage():
     from eraxvif5tts_b200.infer.f5tts_wrapper import plan_ragged_batches
     import random
