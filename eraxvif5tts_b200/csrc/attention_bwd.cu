@@ -274,27 +274,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lq = warp & 3;
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
     uint8_t* my_stg = sStg + (warp - 10) * 8192;  // two [32 rows x 32 f32] SW128 boxes
-    // DROP: keep bits of query chunk (warp - 10) of tile jt for the CTA's 128 keys -> sMask[jt & 1][warp - 10][key]
+    // DROP: keep bits of query chunk (warp - 10) of tile jt for the CTA's 128 keys -> sMask[jt & 1][warp - 10][key].  Lane = query:
+    // four Philox blocks give the lane its 32 keep bits of a 32-key block (row q of a 32 x 32 bit matrix), five shuffle stages
+    // transpose the matrix across the warp, and lane k stores the word of key k.  (A first version used one warp ballot per key:
+    // 128 ballots per tile whose lane-select chains ran at 0.2 IPC and made this the kernel's critical path, 18 -> 32 ms.)
     auto gen_mask = [&](int jt) {
       const int qc = warp - 10;
       const uint64_t g = ((uint64_t)bh * p.n + (uint64_t)(jt * AB_T + qc * 32 + lane)) * p.n8 + (uint64_t)(k0 >> 3);
       uint32_t* dst = sMask + ((jt & 1) * 4 + qc) * AB_T;
 #pragma unroll 1
-      for (int kb = 0; kb < 4; ++kb) {  // 32 keys: four Philox blocks per lane, 32 ballots; lane k keeps the word of key k
-        uint32_t mine = 0;
+      for (int kb = 0; kb < 4; ++kb) {
+        uint32_t row = 0;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           uint32_t w0, w1;
           attn_drop_words(p.dr, g + kb * 4 + o, w0, w1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t v0 = __ballot_sync(0xffffffffu, (w0 >> (8 * i + 7)) & 1u);
-            const uint32_t v1 = __ballot_sync(0xffffffffu, (w1 >> (8 * i + 7)) & 1u);
-            if (lane == o * 8 + i) mine = v0;
-            if (lane == o * 8 + 4 + i) mine = v1;
-          }
+          row |= attn_drop_nibble(w0) << (8 * o);
+          row |= attn_drop_nibble(w1) << (8 * o + 4);
         }
-        dst[kb * 32 + lane] = mine;
+        dst[kb * 32 + lane] = warp_bit_transpose(row, lane);
       }
       mbar_arrive(&bar_mask[jt & 1]);  // release: this lane's words; 128 arrivals complete the buffer
     };

@@ -66,6 +66,23 @@ __device__ __forceinline__ uint32_t attn_drop_pair_mask(uint32_t w, int pair) {
   return m;
 }
 
+// the four keep flags of one word of attn_drop_words (top bit of every byte) as a nibble: bit i = byte i
+__device__ __forceinline__ uint32_t attn_drop_nibble(uint32_t w) {
+  return (((w >> 7) & 0x01010101u) * 0x01020408u) >> 24;  // bit 8i lands on bit 24 + i; the partial products never collide
+}
+// 32 x 32 bit-matrix transpose across a warp: lane q holds row q (bit k = element (q, k)) -> lane k holds column k (bit q)
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    // m: the columns whose index has bit j clear.  The upper row of a pair (lane bit j clear) keeps those and takes the partner's,
+    // shifted up by j; the lower row keeps the others and takes the partner's others, shifted down: the off-diagonal j x j blocks swap
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t q = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((q & ~m) >> j)) : ((x & m) | ((q & m) << j));
+  }
+  return x;
+}
+
 AttnDrop make_attn_drop(float p, uint64_t seed, int layer);  // host (train_kernels.cu): the stream of one DiT block; p <= 0: off
 AttnDrop attn_drop_for_layer(int layer);  // host: f5b_train_set_attn_dropout's stream (training drivers)
 

@@ -1,6 +1,6 @@
 """One training step (F5TTS_Base, 32 x 1200 frames per GPU, bf16, dropout 0): forward + backward + fused AdamW.
     python tools/train_prof.py [B] [n] [steps]     prints ms/step, frames/s, model TFLOP/s and the per-kernel-class breakdown
-    F5B_TRAIN_DROPOUT=0.1 runs the step with the reference's train-mode dropout."""
+    F5B_TRAIN_DROPOUT=0.1 runs the step with the reference's train-mode dropout, F5B_TRAIN_ATTN_DROPOUT=0.1 with SDPA's own."""
 import os
 import sys
 import time
@@ -19,7 +19,8 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 arch = bench.Arch(dim=1024, depth=22, heads=16)
 dev = torch.device("cuda", 0)
 model, _ = bench.build_product_models(arch, dev)
-eng = TrainEngine(model, with_ema=True, dropout=float(os.environ.get("F5B_TRAIN_DROPOUT", "0")))
+eng = TrainEngine(model, with_ema=True, dropout=float(os.environ.get("F5B_TRAIN_DROPOUT", "0")),
+                  attn_dropout=float(os.environ.get("F5B_TRAIN_ATTN_DROPOUT", "0")))
 g = torch.Generator().manual_seed(0)
 mel = (torch.randn(B, n, 100, generator=g) * 2 - 1.5).clamp(-11.5, 5).to(dev)
 text = torch.randint(0, arch.text_num_embeds, (B, int(0.16 * n)), generator=g).to(dev)
