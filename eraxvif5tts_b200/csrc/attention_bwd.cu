@@ -32,7 +32,11 @@ constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
 constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
 constexpr uint32_t AB_MASK = 2 * 4 * AB_T * 4;   // SDPA-dropout keep bits of two tiles: [2][4 query chunks of 32][128 keys] words
-constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + AB_PT /*dS^T*/ + AB_STG + 2 * 2 * AB_T * 4 /*L, delta x2*/ + AB_MASK + 256 + 1024;
+// Q / dO (+ L, delta) ring depth.  Three, not two: with two, the load of tile j+1 can only be issued once the products of tile j-1
+// have retired (same stage), i.e. about one TMA round trip before S^T_{j+1} is wanted — the in-order MMA thread then sat ~640 clocks
+// per tile inside issue_sdp(j+1) waiting for the data, with the products of tile j (whose operands were ready) queued behind it.
+constexpr int AB_NS = 3;
+constexpr uint32_t AB_SMEM = 2 * AB_TILE /*K,V*/ + 2 * AB_NS * AB_TILE /*Q,dO ring*/ + AB_PT /*dS^T*/ + AB_STG + 2 * AB_NS * AB_T * 4 /*L, delta*/ + AB_MASK + 256 + 1024;
 constexpr uint32_t AB_TMEM_COLS = 512;
 
 struct AttnBwdParams {
@@ -51,6 +55,27 @@ struct AttnBwdParams {
   int n8;               // ceil(n / 8)
 };
 
+#ifndef AB_POLY
+#define AB_POLY 0  // of the 8 groups of 4 scores in a 32-column chunk, this many evaluate their second pair of exponentials on the FMA pipe
+#endif
+// 2^x on the FMA pipe (x <= ~100): n = round(x) through the 1.5 * 2^23 magic add, r = x - n in [-0.5, 0.5], degree-3 minimax
+// polynomial of 2^r (max relative error 7.5e-5, far below the bf16 rounding of P), exponent spliced in as an integer multiply-add
+__device__ __forceinline__ float2 ab_exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 xf = __fadd2_rn(x, magic);
+  const float2 nn = __fadd2_rn(xf, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(nn, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(make_float2(0.0551716648f, 0.0551716648f), r, make_float2(0.2426111251f, 0.2426111251f));
+  q = __ffma2_rn(q, r, make_float2(0.6932609677f, 0.6932609677f));
+  q = __ffma2_rn(q, r, make_float2(0.9999280572f, 0.9999280572f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(xf.x) * (1 << 23) + __float_as_int(q.x));
+  e.y = __int_as_float(__float_as_int(xf.y) * (1 << 23) + __float_as_int(q.y));
+  return e;
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -60,37 +85,42 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // With P' = P / (1-p) (the producer warp stages L - log2(1/(1-p))) and delta' = delta (1-p) this is dV = (P' . keep)^T dO,
 // dS = scale * P' . (keep . dP - delta'): the softmax threads only need the keep BIT of their elements.  The forward's Philox blocks
 // cover 8 keys of one query, while a thread here owns one key and 64 queries, so the four dQ-drain warps regenerate the tile's bits
-// (lane = query, one block per key octet) and transpose them with warp ballots into shared memory words [query chunk][key] whose
+// (lane = query, one block per key octet) and transpose them across the warp into shared memory words [query chunk][key] whose
 // bit e is query e of the chunk: every block is computed once per CTA, and a softmax thread reads two words per tile.
 template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                const __grid_constant__ CUtensorMap tmdQ, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdKV, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+#ifdef AB_TRACE
+  const long long t_entry = clock64();  // CTA timeline (trace[8..13], written by softmax warp 2 of the sampled CTA)
+  long long t_setup = 0, t_sdp0 = 0, t_pds0 = 0, t_loop = 0;
+#endif
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
-  uint8_t* sQ = sV + AB_TILE;        // 2 stages
-  uint8_t* sdO = sQ + 2 * AB_TILE;   // 2 stages
-  uint8_t* sdST = sdO + 2 * AB_TILE;
+  uint8_t* sQ = sV + AB_TILE;            // AB_NS stages
+  uint8_t* sdO = sQ + AB_NS * AB_TILE;   // AB_NS stages
+  uint8_t* sdST = sdO + AB_NS * AB_TILE;
   uint8_t* sStg = sdST + AB_PT;                         // [8][4096]
-  float* sL = reinterpret_cast<float*>(sStg + AB_STG);  // [2][128]
-  float* sDl = sL + 2 * AB_T;                          // [2][128]
-  uint32_t* sMask = reinterpret_cast<uint32_t*>(sDl + 2 * AB_T);  // [2][4][128] (DROP only)
+  float* sL = reinterpret_cast<float*>(sStg + AB_STG);  // [AB_NS][128]
+  float* sDl = sL + AB_NS * AB_T;                       // [AB_NS][128]
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(sDl + AB_NS * AB_T);  // [2][4][128] (DROP only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + AB_MASK / 4);
   uint64_t* bar_kv = bars + 0;
-  uint64_t* bar_qdo = bars + 1;   // [2] Q_j, dO_j landed
-  uint64_t* bar_ld = bars + 3;    // [2] L_j, delta_j staged (32 arrivals)
-  uint64_t* bar_sdp = bars + 5;   // S^T_j and dP^T_j in TMEM
-  uint64_t* bar_pds = bars + 6;   // P^T_j, dS^T_j in smem; S / dP / dQ TMEM drained (256 arrivals)
-  uint64_t* bar_dq = bars + 7;    // dV, dK, dQ_j products retired
-  uint64_t* bar_free = bars + 8;  // [2] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
-  uint64_t* bar_sfree = bars + 10;  // S^T_j / dP^T_j pulled into registers by all 256 threads
-  uint64_t* bar_dqfree = bars + 11;  // dQ_j pulled out of TMEM by the 4 drain warps (128 arrivals)
-  uint64_t* bar_mask = bars + 12;    // [2] DROP: keep bits of the tile that uses buffer s are in shared memory (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_sdp = bars + 1;     // S^T_j and dP^T_j in TMEM
+  uint64_t* bar_pds = bars + 2;     // P^T_j, dS^T_j in smem; S / dP / dQ TMEM drained (256 arrivals)
+  uint64_t* bar_dq = bars + 3;      // dV, dK, dQ_j products retired
+  uint64_t* bar_sfree = bars + 4;   // S^T_j / dP^T_j pulled into registers by all 256 threads
+  uint64_t* bar_dqfree = bars + 5;  // dQ_j pulled out of TMEM by the 4 drain warps (128 arrivals)
+  uint64_t* bar_mask = bars + 6;    // [2] DROP: keep bits of the tile that uses buffer s are in shared memory (128 arrivals)
+  uint64_t* bar_qdo = bars + 8;             // [AB_NS] Q_j, dO_j landed
+  uint64_t* bar_ld = bar_qdo + AB_NS;       // [AB_NS] L_j, delta_j staged (32 arrivals)
+  uint64_t* bar_free = bar_ld + AB_NS;      // [AB_NS] products of the tile that used stage s retired -> Q / dO / L / delta of that stage reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_free + AB_NS);
+  static_assert((8 + 3 * AB_NS) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,15 +155,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(bar_kv, 1);
-      mbar_init(&bar_qdo[0], 1);
-      mbar_init(&bar_qdo[1], 1);
-      mbar_init(&bar_ld[0], 32);
-      mbar_init(&bar_ld[1], 32);
+      for (int i = 0; i < AB_NS; ++i) {
+        mbar_init(&bar_qdo[i], 1);
+        mbar_init(&bar_ld[i], 32);
+        mbar_init(&bar_free[i], 1);
+      }
       mbar_init(bar_sdp, 1);
       mbar_init(bar_pds, 256);
       mbar_init(bar_dq, 1);
-      mbar_init(&bar_free[0], 1);
-      mbar_init(&bar_free[1], 1);
       mbar_init(bar_sfree, 256);
       mbar_init(bar_dqfree, 128);
       mbar_init(&bar_mask[0], 128);
@@ -149,6 +178,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();  // PDL (common.cuh): prologue under the previous kernel's tail
   griddep_launch_dependents();
+#ifdef AB_TRACE
+  t_setup = clock64();
+#endif
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384,
                  tm_PT = tmem_base + 448;  // P^T as bf16 pairs: 64 columns = 128 queries (A operand of dV, read from tensor memory)
 
@@ -159,14 +191,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       prefetch_tmap(&tmK);
       prefetch_tmap(&tmV);
       prefetch_tmap(&tmdO);
+      prefetch_tmap(&tmdKV);
       mbar_arrive_expect_tx(bar_kv, 2 * AB_TILE);
       tma_load_3d(sK, &tmK, bar_kv, h * 64, k0, b);
       tma_load_3d(sV, &tmV, bar_kv, h * 64, k0, b);
     }
     const size_t row0 = (size_t)bh * p.n;
     for (int j = 0; j < Tq; ++j) {
-      const int st = j & 1;
-      if (j >= 2) mbar_wait(&bar_free[st], ((j >> 1) - 1) & 1);  // tile j-2 retired (a per-stage barrier cannot run a phase ahead)
+      const int st = j % AB_NS;
+      if (j >= AB_NS) mbar_wait(&bar_free[st], ((j / AB_NS) - 1) & 1);  // tile j - AB_NS retired (a per-stage barrier cannot run a phase ahead)
       if (elect_one()) {  // (not `lane == 0`: plain UTMALDG instead of a per-instruction ELECT / BRA.U.ANY loop, see tile_engine.cuh)
         mbar_arrive_expect_tx(&bar_qdo[st], 2 * AB_TILE);
         tma_load_3d(sQ + st * AB_TILE, &tmQ, &bar_qdo[st], h * 64, j * AB_T, b);
@@ -198,8 +231,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
       const uint32_t ds_addr = smem_u32(sdST);
       auto issue_sdp = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&bar_qdo[st], (j >> 1) & 1);
+        const int st = j % AB_NS;
+        mbar_wait(&bar_qdo[st], (j / AB_NS) & 1);
         tc_fence_after();
         const uint32_t qa = q_addr + st * AB_TILE, da = do_addr + st * AB_TILE;
 #pragma unroll
@@ -220,7 +253,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #define AB_MARK(i)
 #endif
       for (int j = 0; j < Tq; ++j) {
-        const int st = j & 1;
+        const int st = j % AB_NS;
         // S^T / dP^T of the next tile as soon as this tile's scores sit in registers (overlaps the exponentials)
         mbar_wait(bar_sfree, j & 1);
         tc_fence_after();
@@ -344,18 +377,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* ds_row = sdST + ch * (AB_PT / 2) + r * 128;
 
     for (int j = 0; j < Tq; ++j) {
-      const int st = j & 1;
-      mbar_wait(&bar_ld[st], (j >> 1) & 1);
+      const int st = j % AB_NS;
+      mbar_wait(&bar_ld[st], (j / AB_NS) & 1);
       mbar_wait(bar_sdp, j & 1);
       tc_fence_after();
+#ifdef AB_TRACE
+      if (j == 0) t_sdp0 = clock64();
+#endif
       const float4* L4 = reinterpret_cast<const float4*>(sL + st * AB_T + ch * 64);
       const float4* D4 = reinterpret_cast<const float4*>(sDl + st * AB_T + ch * 64);
       uint32_t ppk[32], dpk[32];  // P^T and dS^T rows of this thread, packed bf16
       uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu;  // DROP: keep bits of this key for the 2 x 32 queries of this column half
       if constexpr (DROP) {
-        mbar_wait(&bar_mask[st], (j >> 1) & 1);
-        kb0 = sMask[(st * 4 + ch * 2) * AB_T + r];
-        kb1 = sMask[(st * 4 + ch * 2 + 1) * AB_T + r];
+        mbar_wait(&bar_mask[j & 1], (j >> 1) & 1);
+        kb0 = sMask[((j & 1) * 4 + ch * 2) * AB_T + r];
+        kb1 = sMask[((j & 1) * 4 + ch * 2 + 1) * AB_T + r];
       }
       auto half = [&](const uint32_t (&sv)[32], const uint32_t (&gv)[32], int c) {
         const uint32_t kbits = c ? kb1 : kb0;
@@ -366,10 +402,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float ls[4] = {l.x, l.y, l.z, l.w};
           const float dls[4] = {dl.x, dl.y, dl.z, dl.w};
           float pv[4], dv[4];
+          if (AB_POLY > 0 && ((q4 + 1) * AB_POLY) / 8 != (q4 * AB_POLY) / 8) {  // (compile-time: q4 is an unrolled index)
+            const float2 e2 = ab_exp2_poly2(make_float2(fmaf(__uint_as_float(sv[q4 * 4 + 2]), c2, -ls[2]),
+                                                        fmaf(__uint_as_float(sv[q4 * 4 + 3]), c2, -ls[3])));
+            pv[2] = e2.x;
+            pv[3] = e2.y;
+          } else {
+            pv[2] = ex2_approx(fmaf(__uint_as_float(sv[q4 * 4 + 2]), c2, -ls[2]));
+            pv[3] = ex2_approx(fmaf(__uint_as_float(sv[q4 * 4 + 3]), c2, -ls[3]));
+          }
+          pv[0] = ex2_approx(fmaf(__uint_as_float(sv[q4 * 4 + 0]), c2, -ls[0]));
+          pv[1] = ex2_approx(fmaf(__uint_as_float(sv[q4 * 4 + 1]), c2, -ls[1]));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int e = q4 * 4 + i;
-            pv[i] = ex2_approx(fmaf(__uint_as_float(sv[e]), c2, -ls[i]));
             if constexpr (DROP) {
               const bool keep = (kbits >> e) & 1u;  // pv is P' = P / (1-p), dls is delta' (staged by the producer warp)
               dv[i] = pv[i] * fmaf(keep ? __uint_as_float(gv[e]) : 0.f, sc, -dls[i]);
@@ -417,59 +463,82 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_pds);
+#ifdef AB_TRACE
+      if (j == 0) t_pds0 = clock64();
+#endif
     }
     mbar_wait(bar_dq, (Tq - 1) & 1);
     tc_fence_after();
-    // dV, dK of this key tile (all products retired: bar_dq of the last tile)
+#ifdef AB_TRACE
+    t_loop = clock64();
+#endif
+    // dV, dK of this key tile (all products retired: bar_dq of the last tile) leave as bf16 through swizzled staging tiles (the
+    // dS^T buffer is free now) and two TMA stores straight into the dQKV matrix; rows past the utterance are clipped by the 3-D map.
+    // (Per-thread 16-byte stores scattered 32 half-sectors per warp instruction: the drain took ~3700 clocks of a ~36 000-clock CTA.)
     const int pos = k0 + r;
+    uint8_t* stV = sdST + r * 128;
+    uint8_t* stK = sdST + AB_TILE + r * 128;
     {
       uint32_t a[32];
       tmem_ld32(tm_dV + lane_addr + ch * 32, a);
       tmem_ld_wait();
-      if (pos < p.n) {
-        __nv_bfloat16* o = p.dqkv + ((size_t)b * p.n + pos) * p.ld_d + 2 * D + h * 64 + ch * 32;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(a[q * 8 + 0]), __uint_as_float(a[q * 8 + 1]));
-          pk.y = pack_bf16(__uint_as_float(a[q * 8 + 2]), __uint_as_float(a[q * 8 + 3]));
-          pk.z = pack_bf16(__uint_as_float(a[q * 8 + 4]), __uint_as_float(a[q * 8 + 5]));
-          pk.w = pack_bf16(__uint_as_float(a[q * 8 + 6]), __uint_as_float(a[q * 8 + 7]));
-          reinterpret_cast<uint4*>(o)[q] = pk;
-        }
+      for (int q = 0; q < 4; ++q) {
+        uint4 pk;
+        pk.x = pack_bf16(__uint_as_float(a[q * 8 + 0]), __uint_as_float(a[q * 8 + 1]));
+        pk.y = pack_bf16(__uint_as_float(a[q * 8 + 2]), __uint_as_float(a[q * 8 + 3]));
+        pk.z = pack_bf16(__uint_as_float(a[q * 8 + 4]), __uint_as_float(a[q * 8 + 5]));
+        pk.w = pack_bf16(__uint_as_float(a[q * 8 + 6]), __uint_as_float(a[q * 8 + 7]));
+        *reinterpret_cast<uint4*>(stV + (((ch * 4 + q) ^ rx) << 4)) = pk;
       }
       tmem_ld32(tm_dK + lane_addr + ch * 32, a);
       tmem_ld_wait();
-      if (pos < p.n) {
-        float v[32];
+      float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
-        if (h < p.rope_heads) {
-          // transpose of the forward rotation (y0 = x0 c - x1 s, y1 = x1 c + x0 s)
-          const float4* cs = reinterpret_cast<const float4*>(p.rope) + (size_t)pos * 16 + ch * 8;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
+      if (h < p.rope_heads && pos < p.n) {
+        // transpose of the forward rotation (y0 = x0 c - x1 s, y1 = x1 c + x0 s)
+        const float4* cs = reinterpret_cast<const float4*>(p.rope) + (size_t)pos * 16 + ch * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = __ldg(cs + i);
-            const float y0 = v[4 * i], y1 = v[4 * i + 1], y2 = v[4 * i + 2], y3 = v[4 * i + 3];
-            v[4 * i] = y0 * t.x + y1 * t.y;
-            v[4 * i + 1] = y1 * t.x - y0 * t.y;
-            v[4 * i + 2] = y2 * t.z + y3 * t.w;
-            v[4 * i + 3] = y3 * t.z - y2 * t.w;
-          }
-        }
-        __nv_bfloat16* o = p.dqkv + ((size_t)b * p.n + pos) * p.ld_d + D + h * 64 + ch * 32;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-          pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-          pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-          pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-          reinterpret_cast<uint4*>(o)[q] = pk;
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(cs + i);
+          const float y0 = v[4 * i], y1 = v[4 * i + 1], y2 = v[4 * i + 2], y3 = v[4 * i + 3];
+          v[4 * i] = y0 * t.x + y1 * t.y;
+          v[4 * i + 1] = y1 * t.x - y0 * t.y;
+          v[4 * i + 2] = y2 * t.z + y3 * t.w;
+          v[4 * i + 3] = y3 * t.z - y2 * t.w;
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 pk;
+        pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(stK + (((ch * 4 + q) ^ rx) << 4)) = pk;
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps: both staging tiles are complete
+    if (warp == 2 && elect_one()) {
+      tma_store_3d(&tmdKV, sdST, 2 * D + h * 64, k0, b);
+      tma_store_3d(&tmdKV, sdST + AB_TILE, D + h * 64, k0, b);
+      bulk_commit();
+      bulk_wait_read0();  // the staging tiles have been read before the CTA retires its shared memory
     }
     tc_fence_before();
+#ifdef AB_TRACE
+    if (p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 37 && warp == 2 && lane == 0) {
+      const long long t_end = clock64();
+      p.trace[8] = t_setup - t_entry;   // barrier init, TMEM alloc, __syncthreads, griddepcontrol.wait
+      p.trace[9] = t_sdp0 - t_setup;    // K / V / Q / dO loads + S^T_0, dP^T_0
+      p.trace[10] = t_pds0 - t_sdp0;    // first softmax pass
+      p.trace[11] = t_loop - t_pds0;    // the rest of the loop up to the last products
+      p.trace[12] = t_end - t_loop;     // dV / dK drain
+      p.trace[13] = t_end - t_entry;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -543,13 +612,15 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(out),
                                                                     reinterpret_cast<const __nv_bfloat16*>(dout), ld_o, delta, B, H, n);
   F5B_CUDA(cudaGetLastError());
-  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ, tmdKV;
   const uint64_t hw = (uint64_t)H * 64, pitch = (uint64_t)ld * 2, pitch_o = (uint64_t)ld_o * 2;
   if (make_tmap_3d(&tmQ, q, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmK, k, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmdO, dout, 2, hw, (uint64_t)n, (uint64_t)B, pitch_o, (uint64_t)n * pitch_o, 64, AB_T, 1, true)) return -1;
   if (make_tmap_3d(&tmdQ, dq_ws, 4, hw, (uint64_t)n, (uint64_t)B, hw * 4, (uint64_t)n * hw * 4, 32, 32, 1, true)) return -1;
+  // dK / dV leave through this map over the whole [B, n, 3D] dQKV matrix ([128 rows x 64 columns] boxes at column D + 64h / 2D + 64h)
+  if (make_tmap_3d(&tmdKV, dqkv, 2, 3 * hw, (uint64_t)n, (uint64_t)B, (uint64_t)ld_d * 2, (uint64_t)n * ld_d * 2, 64, AB_T, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AB_SMEM));
@@ -575,8 +646,8 @@ int attn_bwd(const void* q, const void* k, const void* v, int ld, const void* ou
   p.dr = drop ? *drop : AttnDrop{0u, 1.f, 0.f, 0u, 0u};
   p.n8 = (n + 7) / 8;
   dim3 grid((n + AB_T - 1) / AB_T, B * H);
-  if (p.dr.addc != 0) F5B_CUDA(launch_dep(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
-  else F5B_CUDA(launch_dep(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, p));
+  if (p.dr.addc != 0) F5B_CUDA(launch_dep(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, tmdKV, p));
+  else F5B_CUDA(launch_dep(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, stream, 1, tmQ, tmK, tmV, tmdO, tmdQ, tmdKV, p));
   F5B_CUDA(cudaGetLastError());
   const long long items = rows * (D >> 3);
   attn_dq_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(dq_ws, p.dqkv, ld_d, rope, rope_heads, rows, n, D);

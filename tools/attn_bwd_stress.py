@@ -31,7 +31,7 @@ for i in range(reps):
         assert torch.isfinite(ref.float()).all()
         continue
     same_kv = torch.equal(dqkv[:, D:], ref[:, D:])
-    dq_err = (dqkv[:, :D].float() - ref[:, :D].float()).abs().max().item() / ref[:, :D].float().abs().max().item()
+    dq_err = (dqkv[:, :D].float() - ref[:, :D].float()).abs().max().item() / max(ref[:, :D].float().abs().max().item(), 1e-30)
     if not same_kv or dq_err > 1e-2:
         bad += 1
         diff = (dqkv[:, D:].float() - ref[:, D:].float()).abs()

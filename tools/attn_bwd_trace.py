@@ -25,3 +25,13 @@ t = trace.cpu()
 T = int(t[6]) or 1
 names = ["wait sfree", "issue S/dP(j+1)", "wait pds", "issue dV,dK,dQ + commits", "until dq(j) completes"]
 print("MMA warp per tile: " + "  ".join(f"{nm} {int(t[i]) / T:7.0f}" for i, nm in enumerate(names)) + f"   sum {int(t[:5].sum()) / T:7.0f}")
+names2 = ["setup", "loads + S_0/dP_0", "first softmax pass", "rest of the loop", "dV/dK drain", "CTA total"]
+print("CTA timeline (clocks): " + "  ".join(f"{nm} {int(t[8 + i])}" for i, nm in enumerate(names2)) + f"   tiles {T}")
+import time
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.attn_bwd(qkv[:, :D], qkv[:, D:], qkv[:, 2 * D:], 3 * D, out, dout, lse, dqkv, None, 0, B, H, n)
+e1.record()
+torch.cuda.synchronize()
+print(f"attn_bwd (+ delta, finish) {e0.elapsed_time(e1) / 10:.3f} ms per call; CTAs per SM {((n + 127) // 128) * B * H / 148:.1f}")
