@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("F5B_LIB") or os.path.join(_PKG, "lib", "libf5b200.so"
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
-EPI_BF16, EPI_F32, EPI_QKV_ROPE, EPI_GATE_RESID = 0, 1, 2, 3
+EPI_BF16, EPI_F32, EPI_QKV_ROPE, EPI_GATE_RESID, EPI_BF16_DUAL = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 
 

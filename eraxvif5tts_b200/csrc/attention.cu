@@ -3,14 +3,17 @@
 // (/root/reference/src/f5_tts/model/modules.py:483-493; dropout_p = 0, see DESIGN.md "oracle adjustments").
 //
 // sm_100a design (one CTA = one 128-query tile of one (batch, head); the kernel is latency-bound per CTA — measured: one
-// resident CTA/SM 320 TFLOP/s, two 577 — so it is built for THREE co-resident CTAs: 72 KB smem, 128 TMEM columns, <= 112 regs):
+// resident CTA/SM 320 TFLOP/s, two 577 — so it is built for THREE co-resident CTAs: 40 KB smem (72 KB on the shared-memory P path),
+// 128 + 32 TMEM columns, <= 128 regs):
 //   warp 4 (one elected lane): TMA producer + tcgen05.mma issuer.  KV is consumed in tiles of 64 keys:
 //       S_j[128 x 64] = Q K_j^T    (K-major bf16 tiles, 128B swizzle; fp32 accumulator in TMEM columns 0..63).  The softmax
 //                                   threads pull S_j into registers and release the buffer at once (bar_sfree), so S_{j+1} is
 //                                   computed while the exponentials of tile j run.
-//       O[128 x 64]  += P_j V_j    (P_j written to swizzled smem, double-buffered, by the softmax warps; V_j [64 keys x 64] is
-//                                   fed as an MN-MAJOR B operand straight from the head-major layout the QKV epilogue
-//                                   writes — no transposed copy of V exists; O stays resident in TMEM columns 64..127)
+//       O[128 x 64]  += P_j V_j    (default, PT: P_j is written by the softmax warps into the CTA's own 32 tensor-memory columns — a
+//                                   second tcgen05.alloc — and read as a TMEM A operand; the dropout / split-KV kernels keep the
+//                                   round-1 path, P_j double-buffered in swizzled smem.  V_j [64 keys x 64] is fed as an MN-MAJOR B
+//                                   operand straight from the head-major layout the QKV epilogue writes — no transposed copy of V
+//                                   exists; O stays resident in TMEM columns 64..127)
 //   warps 0..3: online softmax, thread = query row (tcgen05.ld 32x32b -> no cross-lane reductions), exp2 with the
 //       1/sqrt(d)*log2(e) scale folded in, row sum in a register.  The running maximum is updated lazily: O and the row sum
 //       are rescaled only when a row's maximum grew by more than 2^8, and the exponentials are issued speculatively
@@ -35,13 +38,18 @@ constexpr uint32_t ATT_K_BYTES = ATT_BKV * 64 * 2;         // 8 KB per stage, 2 
 constexpr uint32_t ATT_V_BYTES = ATT_BKV * 64 * 2;         // 8 KB, 1 stage: [64 kv rows x 64 d]
 constexpr uint32_t ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer, 2 buffers
 #ifndef ATT_P_TMEM
-#define ATT_P_TMEM 0  // 1: P goes to tensor memory (aliasing the score columns) and feeds P.V as a TMEM A operand
+#define ATT_P_TMEM 1  // default kernel: 1 = P_j goes to the CTA's OWN 32 tensor-memory columns (tcgen05.st) and P.V reads it as a TMEM A
+                      // operand; 0 = P_j through double-buffered swizzled shared memory (the round-1 path; dropout and split-KV kernels
+                      // always use it).  A/B at cfg-2's shape: 726 vs 711 TFLOP/s stand-alone, attention class -1.9 % in situ.
 #endif
 #ifndef ATT_EXTRA_SMEM
 #define ATT_EXTRA_SMEM 0  // experiments: pad shared memory to lower the number of resident CTAs
 #endif
-constexpr uint32_t ATT_SMEM = ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + (ATT_P_TMEM ? 0 : 2 * ATT_P_BYTES) + 1024 + 128 + ATT_EXTRA_SMEM;
+constexpr uint32_t att_smem(bool pt) { return ATT_Q_BYTES + 2 * ATT_K_BYTES + ATT_V_BYTES + (pt ? 0 : 2 * ATT_P_BYTES) + 1024 + 128 + ATT_EXTRA_SMEM; }
+constexpr bool ATT_PT = ATT_P_TMEM != 0;
 constexpr uint32_t ATT_TMEM_COLS = 128;  // S: 0..63, O: 64..127
+constexpr uint32_t ATT_TMEM_P_COLS = 32; // PT kernels: a SECOND allocation for P (64 keys x bf16 = 32 columns): 160 columns per CTA, 480 for three
+                                         // co-resident CTAs — a 256-column power-of-two allocation would cap the SM at two CTAs
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
@@ -144,12 +152,17 @@ __device__ __forceinline__ float row_max32(const uint32_t (&a)[32], int valid) {
 // all 15 key tiles serially): the key range of a query tile is cut in two, the two halves run as a CLUSTER of 2 CTAs, and rank 1
 // hands its un-normalised (O, m, l) to rank 0 through distributed shared memory, which merges and writes — flash-decoding's split-KV
 // without a workspace or a combine kernel.  SPLIT = 1 compiles to the single-CTA kernel.
-template <int SPLIT, bool DROP = false>
+// PT: P in tensor memory.  The score tile S_j is pulled into registers and its columns released exactly as on the shared-memory path
+// (S_{j+1} overlaps the exponentials of tile j); P_j is written by tcgen05.st into the P columns and P.V runs as a TS-mode MMA, which
+// takes the P store (16 KB), the P operand read (16 KB) and the proxy fence out of the 80 KB of shared-memory traffic per key tile and
+// shrinks the CTA to 40 KB.  P is single-buffered: before storing P_j a softmax thread makes sure P_{j-1} V_{j-1} has retired (it was
+// issued a whole tile of exponentials earlier, so the probe succeeds at once).
+template <int SPLIT, bool DROP = false, bool PT = false>
 __global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  static_assert(SPLIT == 1 || (SPLIT == 2 && !ATT_P_TMEM), "split-KV is built for two halves on the shared-memory P path");
-  static_assert(!DROP || (SPLIT == 1 && !ATT_P_TMEM), "attention dropout is built for the single-CTA shared-memory P path");
+  static_assert(SPLIT == 1 || (SPLIT == 2 && !PT), "split-KV is built for two halves on the shared-memory P path");
+  static_assert(!DROP || (SPLIT == 1 && !PT), "attention dropout is built for the single-CTA shared-memory P path");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -157,7 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = sQ + ATT_Q_BYTES;
   uint8_t* sV = sK + 2 * ATT_K_BYTES;
   uint8_t* sP = sV + ATT_V_BYTES;  // 16K + 16K + 8K = 40K: 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (ATT_P_TMEM ? 0 : 2 * ATT_P_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PT ? 0 : 2 * ATT_P_BYTES));
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;      // [2] K_j landed
   uint64_t* bar_v = bars + 3;      // V_j landed
@@ -223,13 +236,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    if constexpr (PT) {
+      tmem_alloc_keep(tmem_slot, ATT_TMEM_COLS);
+      tmem_alloc(tmem_slot + 1, ATT_TMEM_P_COLS);
+    } else {
+      tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 64;
+  const uint32_t tmem_P = PT ? tmem_slot[1] : 0u;
   griddep_wait();  // PDL: q / k / v (the QKV GEMM's output) are first read below
   griddep_launch_dependents();
 
@@ -263,43 +282,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       load_v(0);
       mbar_wait(bar_q, 0);
       issue_s(0);
-#if ATT_P_TMEM
-      for (int j = 0; j < T; ++j) {
-        // P_j sits in tensor memory (over the score columns): O += P_j V_j with the A operand read from TMEM, THEN S_{j+1} into
-        // the same columns (the tensor pipe executes one thread's MMAs in order, so the overwrite follows the read)
-        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        mbar_wait(bar_v, j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tmem_O, tmem_base + kk * 8, smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv, (j | kk) != 0);
-        umma_commit(&bar_pv[j & 1]);
-        if (j + 1 < T) issue_s(j + 1);
-        if (j + 2 < T) load_k(j + 2);  // S_j retired long ago (its scores were consumed before P_j was written)
-        if (j + 1 < T) {
-          mbar_wait(&bar_pv[j & 1], (j >> 1) & 1);  // the single V stage is free once P_j V_j retired
-          load_v(j + 1);
-        }
-      }
-    }
-#else
       for (int j = 0; j < T; ++j) {
         // S_j sits in registers: its TMEM buffer and K stage are free -> S_{j+1} overlaps the exponentials of tile j
         mbar_wait(bar_sfree, j & 1);
         tc_fence_after();
         if (j + 1 < T) issue_s(j + 1);
         if (j + 2 < T) load_k(j + 2);  // stage j&1 held K_j
-        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);  // P_j in smem (and O rescaled if needed)
+        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);  // P_j in place (and O rescaled if needed)
         tc_fence_after();
         mbar_wait(bar_v, j & 1);
         tc_fence_after();
-        const uint32_t pa = p_addr + (j & 1) * ATT_P_BYTES;
+        if constexpr (PT) {
+          // A operand from tensor memory (lane = query row, a 32-bit column = two consecutive keys, a K-step of 16 keys = 8 columns)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          // MN-major SW128 operand: rows = keys (128 B of d each), 8-row groups 1024 B apart (SBO); one UMMA K-step = 16 keys
-          umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv,
-                    (j | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tmem_O, tmem_P + kk * 8, smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv, (j | kk) != 0);
+        } else {
+          const uint32_t pa = p_addr + (j & 1) * ATT_P_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            // MN-major SW128 operand: rows = keys (128 B of d each), 8-row groups 1024 B apart (SBO); one UMMA K-step = 16 keys
+            umma_bf16(tmem_O, smem_desc_sw128(pa + kk * 32, 1024, 16), smem_desc_sw128(v_addr + kk * 2048, 1024, 8192), idesc_pv,
+                      (j | kk) != 0);
+        }
         umma_commit(&bar_pv[j & 1]);
         if (j + 1 < T) {
           mbar_wait(&bar_pv[j & 1], (j >> 1) & 1);  // the single V stage is free once P_j V_j retired
@@ -307,7 +312,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-#endif
     __syncwarp();
   } else {
     const int r = warp * 32 + lane;  // query row in tile == TMEM lane
@@ -346,59 +350,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(bar_sfree);
       ATT_MARK(1)
       if (j == 0) m_used = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
-#if ATT_P_TMEM
-      // exponentials are speculative w.r.t. this tile's maximum (see header); P stays in registers until it is final
-      uint32_t ppk[32];
+      // Exponentials are speculative w.r.t. this tile's maximum (see header).  Shared-memory path: bar_s(j) was committed after
+      // P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing thread), so P buffer (j & 1) is free.
+      // PT: P_j stays in registers (16 packed pairs per 32 keys) until it is final.
       float ts;
+      uint32_t ppk[PT ? 32 : 1];
+      // mask group of this tile's first key in this thread's (batch, head, query) row
+      const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n8 + (uint64_t)((t_begin + j) * (ATT_BKV / 8)) : 0;
       auto make_p = [&]() {
-        if (valid == ATT_BKV) {
-          ts = softmax_chunk_reg<false>(s0, sl2, m_used, 32, ppk);
-          ts += softmax_chunk_reg<false>(s1, sl2, m_used, 32, ppk + 16);
+        if constexpr (PT) {
+          if (valid == ATT_BKV) {
+            ts = softmax_chunk_reg<false>(s0, sl2, m_used, 32, ppk);
+            ts += softmax_chunk_reg<false>(s1, sl2, m_used, 32, ppk + 16);
+          } else {
+            ts = softmax_chunk_reg<true>(s0, sl2, m_used, valid, ppk);
+            ts += softmax_chunk_reg<true>(s1, sl2, m_used, valid - 32, ppk + 16);
+          }
         } else {
-          ts = softmax_chunk_reg<true>(s0, sl2, m_used, valid, ppk);
-          ts += softmax_chunk_reg<true>(s1, sl2, m_used, valid - 32, ppk + 16);
+          if (valid == ATT_BKV) {
+            ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
+            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &dr, g0 + 4);
+          } else {
+            ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &dr, g0);
+            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &dr, g0 + 4);
+          }
         }
       };
       make_p();
-      ATT_MARK(2)
-      if (j > 0) {
-        const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
-        if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
-          const float m_new = fmaxf(m_used, mt);
-          const float f = ex2_approx(m_used - m_new);
-          m_used = m_new;
-          l_run *= f;
-          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);  // P_{j-1} V_{j-1} has landed in O
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_addr + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tmem_O + lane_addr + c * 32, o);
-          }
-          tmem_st_wait();
-          make_p();
-        }
-      }
-      // P_j -> tensor memory, over the first 32 of the 64 score columns (S_j is in registers; S_{j+1} is issued after P_j V_j)
-      tmem_st32(tmem_base + lane_addr, ppk);
-      tmem_st_wait();
-#else
-      // bar_s(j) was committed after P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing
-      // thread), so the P buffer (j & 1) is free.  Exponentials are speculative w.r.t. this tile's maximum (see header).
-      float ts;
-      // mask group of this tile's first key in this thread's (batch, head, query) row
-      const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n8 + (uint64_t)((t_begin + j) * (ATT_BKV / 8)) : 0;
-      if (valid == ATT_BKV) {
-        ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
-        ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &dr, g0 + 4);
-      } else {
-        ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &dr, g0);
-        ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &dr, g0 + 4);
-      }
       ATT_MARK(2)
       // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
       // sum: the 64-way maximum is only evaluated when that cheap necessary condition holds for some row of the warp
@@ -422,21 +400,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st32(tmem_O + lane_addr + c * 32, o);
           }
           tmem_st_wait();
-          if (valid == ATT_BKV) {
-            ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
-            ts += softmax_chunk<false, DROP>(s1, sl2, m_used, 32, p_row, 4, rx, &dr, g0 + 4);
-          } else {
-            ts = softmax_chunk<true, DROP>(s0, sl2, m_used, valid, p_row, 0, rx, &dr, g0);
-            ts += softmax_chunk<true, DROP>(s1, sl2, m_used, valid - 32, p_row, 4, rx, &dr, g0 + 4);
-          }
+          make_p();
         }
       }
-#endif
+      if constexpr (PT) {
+        // the P columns are single-buffered: P_{j-1} V_{j-1} (issued a whole tile of exponentials ago) must have retired
+        if (j > 0) {
+          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st32(tmem_P + lane_addr, ppk);
+        tmem_st_wait();
+      }
       l_run += ts;
       ATT_MARK(3)
-#if !ATT_P_TMEM
-      fence_proxy_async_smem();
-#endif
+      if constexpr (!PT) fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar_p[j & 1]);
       ATT_MARK(4)
@@ -547,6 +525,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    if constexpr (PT) tmem_dealloc(tmem_P, ATT_TMEM_P_COLS);
   }
 }
 
@@ -575,11 +554,9 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   if (make_tmap_3d(&tmV, v, 2, hw, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, ATT_BKV, 1, true)) return -1;
   static bool configured = false;
   if (!configured) {
-    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-#if !ATT_P_TMEM
-    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-#endif
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false, ATT_PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(ATT_PT)));
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(false)));
+    F5B_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(false)));
     configured = true;
   }
   AttnParams p;
@@ -596,9 +573,8 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   p.n8 = (n + 7) / 8;
   p.dr_seed = drop_seed_dev;
   dim3 grid((n + ATT_BQ - 1) / ATT_BQ, B * H);
-#if !ATT_P_TMEM
   if (p.dr.addc != 0) {  // SDPA dropout (training): the forward's mask is regenerated by attn_bwd from the same Drop
-    F5B_CUDA(launch_dep(attn_fwd_kernel<1, true>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
+    F5B_CUDA(launch_dep(attn_fwd_kernel<1, true>, grid, dim3(ATT_THREADS), att_smem(false), stream, 1, tmQ, tmK, tmV, p));
     F5B_CUDA(cudaGetLastError());
     return 0;
   }
@@ -607,12 +583,11 @@ int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, flo
   // co-scheduling and the distributed-shared-memory merge cost more than the halved key loop saves, so it is not used by default.
   if (lse == nullptr && n >= 4 * ATT_BKV && g_attn_split == 1) {
     grid.x *= 2;
-    F5B_CUDA(launch_dep(attn_fwd_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 2, tmQ, tmK, tmV, p));
+    F5B_CUDA(launch_dep(attn_fwd_kernel<2>, grid, dim3(ATT_THREADS), att_smem(false), stream, 2, tmQ, tmK, tmV, p));
     F5B_CUDA(cudaGetLastError());
     return 0;
   }
-#endif
-  F5B_CUDA(launch_dep(attn_fwd_kernel<1>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, p));
+  F5B_CUDA(launch_dep(attn_fwd_kernel<1, false, ATT_PT>, grid, dim3(ATT_THREADS), att_smem(ATT_PT), stream, 1, tmQ, tmK, tmV, p));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }

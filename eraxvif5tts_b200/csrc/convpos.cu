@@ -88,37 +88,42 @@ struct ConvPosProblem {
   }
   __device__ __forceinline__ void epilogue(const RowCtx& c, int c0, const uint32_t (&r)[32]) const {
     if (!c.valid) return;
-    const int left = cpg - c0;
+    const int left = cpg - c0;  // > 0; 32 for whole chunks, 16 for the second chunk of a 48-channel group
+    const bool v4 = ((D | cpg) & 3) == 0;  // 16-byte aligned fp32 groups of 4 (bias, residual)
     float v[32];
+    {
+      float bb[32];
+      if (v4) {
+        load_bias32_groups(bias, c.ch0 + c0, left, bb);
+      } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float bb = 0.f;
-      if (bias != nullptr && i < left) bb = __ldg(bias + c.ch0 + c0 + i);
-      const float t = __uint_as_float(r[i]) + bb;
-      v[i] = MODE == 2 ? t : (TF32 ? mish_precise(t) : mish(t));  // mode 2: pre-activation output (training forward / transposed conv of the backward)
+        for (int i = 0; i < 32; ++i) bb[i] = (bias != nullptr && i < left) ? __ldg(bias + c.ch0 + c0 + i) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float t = __uint_as_float(r[i]) + bb[i];
+        v[i] = MODE == 2 ? t : (TF32 ? mish_precise(t) : mish(t));  // mode 2: pre-activation output (training forward / transposed conv of the backward)
+      }
     }
     if constexpr ((MODE == 0 || MODE == 2) && TF32) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
-      store_row32_f32(reinterpret_cast<float*>(out) + c.row_off + c0, v, left, ((D | cpg) & 3) == 0);
+      store_row32_f32(reinterpret_cast<float*>(out) + c.row_off + c0, v, left, v4);
     } else if constexpr (MODE == 0 || MODE == 2) {
       store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(out) + c.row_off + c0, v, left, ((D | cpg) & 7) == 0);
     } else {
       float* o = resid + c.row_off + c0;
-      if (left >= 32 && ((D | cpg) & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 x = reinterpret_cast<float4*>(o)[q];
-          x.x += v[q * 4];
-          x.y += v[q * 4 + 1];
-          x.z += v[q * 4 + 2];
-          x.w += v[q * 4 + 3];
-          reinterpret_cast<float4*>(o)[q] = x;
+      for (int q = 0; q < 8; ++q) {
+        if (v4 && q * 4 + 4 <= left) {
+          // residual += mish(conv): a 16-byte reduction at the L2 instead of load-add-store (each element is touched once per launch;
+          // the read-modify-write epilogue ran at half the speed of the store-only one: 452 vs 222 us at cfg-2's shape)
+          red_add_v4_f32(o + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = q * 4; i < q * 4 + 4; ++i)
+            if (i < left) o[i] += v[i];
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < left) o[i] += v[i];
       }
     }
   }
@@ -143,9 +148,16 @@ constexpr uint32_t HALO_A_BYTES = HALO_BOXES * HALO_BOX_ROWS * 128;  // 68 KB
 constexpr int HALO_B_STAGES = 8;
 constexpr uint32_t HALO_B_BYTES = 64 * 128;              // 8 KB per stage (NP <= 64 rows)
 constexpr uint32_t HALO_SMEM = 2 * HALO_A_BYTES + HALO_B_STAGES * HALO_B_BYTES + 1024 + 256;
+// warps: 0 TMA producer, 1 and 10 tcgen05.mma issuers (even / odd sub-tiles: ONE issuing thread cannot keep the tensor pipe busy with
+// 33-clock 128 x 64 x 16 MMAs, two threads share the pipe without loss), 2..9 epilogue
+constexpr int HALO_THREADS = ENGINE_THREADS + 32;
+constexpr int HALO_MMA_WARP2 = ENGINE_THREADS / 32;
 
-template <int MODE>
-__global__ void __launch_bounds__(ENGINE_THREADS, 1)
+// KSTEPS: K-steps of 16 input channels per tap that hold real channels (compile time, so the issue loop carries no predicates): the
+// stage rows are 64 channels wide, but a group of 48 (F5TTS_Small, D = 768) fills only three of the four slices — the fourth would
+// multiply the neighbour group's channels by packed zeros.
+template <int MODE, int KSTEPS>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvPosProblem<MODE> p,
                     const int n_super) {
   extern __shared__ uint8_t smem_raw[];
@@ -170,13 +182,13 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&a_full[i], 1);
-        mbar_init(&a_empty[i], 1);
-        mbar_init(&tfull[i], 1);
+        mbar_init(&a_empty[i], 2);  // one tcgen05.commit per issuing warp
+        mbar_init(&tfull[i], 2);
         mbar_init(&tempty[i], EPI_WARPS);
       }
       for (int i = 0; i < HALO_B_STAGES; ++i) {
         mbar_init(&b_full[i], 1);
-        mbar_init(&b_empty[i], 1);
+        mbar_init(&b_empty[i], 2);
       }
       fence_barrier_init();
     }
@@ -228,9 +240,18 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == HALO_MMA_WARP2) {
+    const int mw = warp == 1 ? 0 : 1;  // this issuer's sub-tiles: sblk & 1 == mw
     if (elect_one()) {
       const uint32_t idesc = idesc_bf16(BM, p.NP, 0, 0);
+      // ISSUE COST.  A 128 x 64 x 16 MMA executes in ~33 clocks, so this thread has to issue one every ~30 instructions' worth of
+      // time; building both 64-bit shared-memory descriptors from addresses each time (shift / mask / or on the uniform datapath plus
+      // R2UR moves) took ~90 clocks per MMA and left the tensor pipe 36 % busy (ncu, profiles/r02_convpos_issue.md).  All descriptors
+      // of a super-tile differ only in the 14-bit start-address field, which never carries (shared memory < 256 KB): the low word is
+      // advanced by constants — +8 per tap row (128 B), +1024 per 128-row sub-tile, +2 per K-step (32 B) — and the high word is fixed.
+      const uint64_t d0 = smem_desc_sw128(0, 1024, 16);
+      const uint32_t d_hi = (uint32_t)(d0 >> 32), d_lo0 = (uint32_t)d0;
+      auto mk = [&](uint32_t lo) { return ((uint64_t)d_hi << 32) | (uint64_t)lo; };
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -242,18 +263,21 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty[acc], ph2 ^ 1);
         mbar_wait(&a_full[ab], ph2);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + ab * HALO_A_BYTES);
+        const uint32_t a_lo = d_lo0 + (smem_u32(sA + ab * HALO_A_BYTES) >> 4);
+        const uint32_t d_acc = tmem_base + acc * (HALO_SUB * 64);
         for (int k = 0; k < ks; ++k) {
           mbar_wait(&b_full[stage], phase);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(sB + stage * HALO_B_BYTES);
-          for (int sblk = 0; sblk < nsub; ++sblk) {
-            const uint32_t d_tmem = tmem_base + acc * (HALO_SUB * 64) + sblk * 64;
-            const uint32_t a_addr = a_base + (sblk * BM + k) * 128;  // sub-tile sblk, shifted down by k rows for tap k
+          const uint32_t b_lo = d_lo0 + (smem_u32(sB + stage * HALO_B_BYTES) >> 4);
+          const uint32_t a_lo_k = a_lo + k * 8;  // tap k: the halo rows shifted down by k
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d_tmem, smem_desc_sw128(a_addr + kk * 32, 1024, 16), smem_desc_sw128(b_addr + kk * 32, 1024, 16), idesc,
-                        (k | kk) != 0);
+          for (int half = 0; half < HALO_SUB / 2; ++half) {
+            const int sblk = 2 * half + mw;
+            if (sblk < nsub) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk)
+                umma_bf16(d_acc + sblk * 64, mk(a_lo_k + sblk * (BM * 8) + kk * 2), mk(b_lo + kk * 2), idesc, (k | kk) != 0);
+            }
           }
           umma_commit(&b_empty[stage]);
           if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
@@ -300,10 +324,10 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 int g_convpos_halo = 1;  // 0: per-tap loads on the generic engine (kept for A/B measurements), 1: super-tile halo kernel
 
-template <int MODE>
-static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPosProblem<MODE>& p, cudaStream_t stream) {
+template <int MODE, int KSTEPS>
+static int launch_halo_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPosProblem<MODE>& p, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = convpos_halo_kernel<MODE>;
+  auto kern = convpos_halo_kernel<MODE, KSTEPS>;
   if (!configured) {
     F5B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HALO_SMEM));
     configured = true;
@@ -311,9 +335,14 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   const int n_super = (p.n + HALO_SUB * BM - 1) / (HALO_SUB * BM);
   const int total = p.B * n_super * p.groups;
   const int grid = total < sm_count() ? total : sm_count();
-  F5B_CUDA(launch_dep(kern, dim3(grid), dim3(ENGINE_THREADS), HALO_SMEM, stream, 1, tmA, tmB, p, n_super));
+  F5B_CUDA(launch_dep(kern, dim3(grid), dim3(HALO_THREADS), HALO_SMEM, stream, 1, tmA, tmB, p, n_super));
   F5B_CUDA(cudaGetLastError());
   return 0;
+}
+template <int MODE>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPosProblem<MODE>& p, cudaStream_t stream) {
+  // (any KSTEPS >= ceil(cpg / 16) is correct: the packed weights are zero beyond cpg)
+  return p.cpg <= 48 ? launch_halo_k<MODE, 3>(tmA, tmB, p, stream) : launch_halo_k<MODE, 4>(tmA, tmB, p, stream);
 }
 
 __global__ void pack_convpos_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int D, int groups, int ksize,

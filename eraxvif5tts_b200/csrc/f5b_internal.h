@@ -11,6 +11,9 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
 // convenience wrappers used by the model drivers
 int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
                 int act, cudaStream_t s, bool tf32 = false);
+// out = bf16(A W^T + bias) and out_act = bf16(act(out)) from one accumulator tile (F5B_EPI_BF16_DUAL; act = GELU_TANH)
+int linear_bf16_dual(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, void* out_act, int ldc_act,
+                     int M, int N, int K, int act, cudaStream_t s);
 int linear_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldc, int M, int N, int K,
                int act, const float* addsrc, int ld_add, void* out_bf16, int ld_bf16, cudaStream_t s, bool tf32 = false);
 int linear_gate_resid(const void* A, int lda, const void* W, int ldw, const float* bias, float* x, int ldc, int M, int N,
@@ -26,6 +29,7 @@ int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w
                int C, float eps, cudaStream_t s, float* y_out = nullptr, bool tf32 = false);
 int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s,
         bool tf32 = false);
+bool train_dropout_on();  // train_kernels.cu: f5b_train_set_dropout's p > 0 (sites 0 / 1)
 struct AttnDrop;  // dropout.cuh: mask stream of one layer's SDPA dropout; nullptr / addc == 0 = no dropout
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,
              int n, float scale, cudaStream_t stream, const AttnDrop* drop = nullptr, const uint32_t* drop_seed_dev = nullptr);

@@ -40,8 +40,12 @@ struct LinearProblem {
   static constexpr int BN = BN_;
   static constexpr bool TF32 = TF32_;
   static constexpr int BKE = TF32_ ? 32 : 64;  // elements per k-block (128 bytes)
-  static constexpr int STORE = (EPI == F5B_EPI_BF16 || EPI == F5B_EPI_QKV_ROPE) ? (TF32_ ? STORE_F32 : STORE_BF16)
-                                                                                 : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
+  static constexpr int STORE = (EPI == F5B_EPI_BF16 || EPI == F5B_EPI_QKV_ROPE || EPI == F5B_EPI_BF16_DUAL)
+                                   ? (TF32_ ? STORE_F32 : STORE_BF16)
+                                   : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
+  // BF16_DUAL (training forward): out = bf16(acc + bias), out2 = bf16(act(out)) from one accumulator tile (tile_engine.cuh, P::DUAL)
+  static constexpr bool DUAL = EPI == F5B_EPI_BF16_DUAL;
+  static_assert(!(DUAL && TF32_), "the dual-output epilogue exists in the bf16 operand mode only");
   static constexpr int CLUSTER = 2;  // CTA pairs on vertically adjacent tiles share the weight tile through TMA multicast
   F5bGemmArgs g;
   int n_tiles, m_tiles, kblocks;
@@ -130,6 +134,9 @@ struct LinearProblem {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + b[i];
       }
+    } else if constexpr (DUAL) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + b[i];  // the activation is applied by second()
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = activate<ACT, TF32>(__uint_as_float(r[i]) + b[i]);
@@ -159,6 +166,9 @@ struct LinearProblem {
       }
     }
   }
+
+  // DUAL: the second output as a function of the (bf16-rounded) first one
+  __device__ __forceinline__ float second(float x) const { return activate<ACT, false>(x); }
 
   // STORE_DIRECT epilogues
   __device__ __forceinline__ void epilogue(const RowCtx& c, int c0, const uint32_t (&r)[32]) const {
@@ -221,10 +231,15 @@ static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
     F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
     if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
   }
-  if constexpr (BN == 256) {
-    if (g_gemm_pair_mode) return launch_engine<P, true>(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
+  CUtensorMap tmD = tmC;
+  if constexpr (P::DUAL) {
+    F5B_CHECK(g.out2 != nullptr && (g.ldc2 & 7) == 0, "f5b_gemm: BF16_DUAL needs out2 with a pitch that is a multiple of 8");
+    if (make_tmap_2d(&tmD, g.out2, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc2 * 2, 64, 32, true)) return -1;
   }
-  return launch_engine(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream);
+  if constexpr (BN == 256) {
+    if (g_gemm_pair_mode) return launch_engine<P, true>(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream, &tmD);
+  }
+  return launch_engine(tmA, tmB, tmC, p, p.n_tiles * ((p.m_tiles + 1) / 2), stream, &tmD);
 }
 
 template <int BN, bool TF32>
@@ -238,6 +253,9 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& b, const F5bGemmArg
   F5B_CASE(F5B_EPI_F32, F5B_ACT_NONE)
   F5B_CASE(F5B_EPI_QKV_ROPE, F5B_ACT_NONE)
   F5B_CASE(F5B_EPI_GATE_RESID, F5B_ACT_NONE)
+  if constexpr (!TF32) {
+    F5B_CASE(F5B_EPI_BF16_DUAL, F5B_ACT_GELU_TANH)
+  }
 #undef F5B_CASE
   set_error("f5b_gemm: unsupported epilogue/activation combination (%d, %d)", g.epi, g.act);
   return -1;
@@ -260,7 +278,8 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
               "f5b_gemm: GATE_RESID needs rows_per_batch > 0 and a 16-byte aligned gate with a stride that is a multiple of 4");
   if (g.bias != nullptr) F5B_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "f5b_gemm: bias must be 16-byte aligned");
   const double esz = tf32 ? 4.0 : 2.0;
-  const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? esz : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0);
+  const double out_bytes = (g.epi == F5B_EPI_BF16 || g.epi == F5B_EPI_QKV_ROPE) ? esz
+                           : (g.epi == F5B_EPI_BF16_DUAL ? 2.0 * esz : (g.epi == F5B_EPI_GATE_RESID ? 8.0 : 4.0));
   LaunchScope scope(K_GEMM, stream, 2.0 * g.M * g.N * g.K, esz * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes * g.M * g.N);
   const int m_tiles = (g.M + BM - 1) / BM;
   // 256-wide tiles (CTA pairs) once they fill about two thirds of the machine; below that 128-wide tiles give twice the units to
@@ -293,6 +312,13 @@ int linear_bf16(const void* A, int lda, const void* W, int ldw, const float* bia
                 int act, cudaStream_t s, bool tf32) {
   F5bGemmArgs g = base_args(M, N, K, F5B_EPI_BF16, act, bias, out, ldc);
   g.tf32 = tf32;
+  return gemm(A, lda, W, ldw, g, s);
+}
+
+int linear_bf16_dual(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, void* out_act, int ldc_act,
+                     int M, int N, int K, int act, cudaStream_t s) {
+  F5bGemmArgs g = base_args(M, N, K, F5B_EPI_BF16_DUAL, act, bias, out, ldc);
+  g.out2 = out_act; g.ldc2 = ldc_act;
   return gemm(A, lda, W, ldw, g, s);
 }
 

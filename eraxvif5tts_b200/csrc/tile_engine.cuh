@@ -61,14 +61,22 @@ __device__ __forceinline__ void stage_store16(uint8_t* stg, int lane, int chunk,
   *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
 }
 
+// P::DUAL (optional member, STORE_BF16 problems): the epilogue writes TWO bf16 tiles per accumulator tile — compute()'s values through
+// tmC and P::second() of the same (bf16-rounded) values through tmD — e.g. the pre-activation AND the activated output of a training
+// forward GEMM, which otherwise costs a separate sweep that re-reads the pre-activation from HBM.
+template <class P, class = void> struct engine_is_dual { static constexpr bool value = false; };
+template <class P> struct engine_is_dual<P, decltype((void)P::DUAL)> { static constexpr bool value = P::DUAL; };
+
 // TWOSM: the two CTAs of the cluster form one tcgen05 CTA pair: a 256-row x BN tile per pair, the MMA issued by the leader CTA
 // reads each operand half from each CTA's shared memory, so the shared-memory port of an SM sees half the operand traffic per flop
 // (with cta_group::1 and a 128 x 256 tile the TMA fills + MMA operand reads add up to ~192 B/clk against a 128 B/clk port).
 template <class P, bool TWOSM = false>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1)
 engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const __grid_constant__ CUtensorMap tmC, const P p) {
+              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const P p) {
   constexpr int BN = P::BN;
+  constexpr bool DUAL = engine_is_dual<P>::value;
+  static_assert(!DUAL || P::STORE == STORE_BF16, "dual-output epilogues are built for the bf16 TMA-store path");
   using Cfg = typename EngCfgSel<TWOSM, BN>::type;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -93,6 +101,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if constexpr (P::STORE != STORE_DIRECT) prefetch_tmap(&tmC);
+    if constexpr (DUAL) prefetch_tmap(&tmD);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -220,6 +229,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int g = half; g * 64 < ncols; g += 2) {
           if (elect_one()) bulk_wait_read0();  // the previous store has drained the staging tile
           __syncwarp();
+          uint4 first[DUAL ? 8 : 1];  // DUAL: the packed first output, input of the second
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c0 = g * 64 + cc * 32;
@@ -237,6 +247,7 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
                 pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
                 stage_store16(stg, lane, cc * 4 + q, pk);
+                if constexpr (DUAL) first[cc * 4 + q] = pk;
               }
             }
           }
@@ -245,6 +256,34 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (elect_one()) {
             tma_store_2d(&tmC, stg, p.out_col0(tile) + g * 64, p.out_row0(tile) + quad * 32);
             bulk_commit();
+          }
+          if constexpr (DUAL) {
+            // second output = P::second(what the first output holds, i.e. the bf16-rounded values) through the same staging tile
+            uint4 sec[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (g * 64 + (q >> 2) * 32 < ncols) {
+                const uint32_t w[4] = {first[q].x, first[q].y, first[q].z, first[q].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                  o[k] = pack_bf16(p.second(f.x), p.second(f.y));
+                }
+                sec[q] = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+            if (elect_one()) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (g * 64 + (q >> 2) * 32 < ncols) stage_store16(stg, lane, q, sec[q]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_2d(&tmD, stg, p.out_col0(tile) + g * 64, p.out_row0(tile) + quad * 32);
+              bulk_commit();
+            }
           }
         }
       } else {
@@ -295,7 +334,8 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 template <class P, bool TWOSM = false>
 static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const P& p, int total_units,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const CUtensorMap* tmD_opt = nullptr) {
+  const CUtensorMap& tmD = tmD_opt ? *tmD_opt : tmC;  // second output map of a DUAL problem
   using Cfg = typename EngCfgSel<TWOSM, P::BN>::type;
   static_assert(!TWOSM || P::CLUSTER == 2, "pair mode needs a 2-CTA cluster");
   static bool configured = false;
@@ -307,7 +347,7 @@ static int launch_engine(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   constexpr int CL = P::CLUSTER;
   const int max_clusters = sm_count() / CL;
   const int nclusters = total_units < max_clusters ? total_units : max_clusters;
-  F5B_CUDA(launch_dep(kern, dim3(nclusters * CL), dim3(ENGINE_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmC, p));
+  F5B_CUDA(launch_dep(kern, dim3(nclusters * CL), dim3(ENGINE_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmC, tmD, p));
   F5B_CUDA(cudaGetLastError());
   return 0;
 }
@@ -320,16 +360,23 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k) { ret
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k) { return smem_desc_sw128(tile_addr + k * 2048, 1024, 8192); }
 
 // ---- shared epilogue helpers: 32 consecutive columns of one accumulator row ------------------------------------
+// (partial chunks keep the 16-byte stores for every whole group of 8 / 4 columns: a 48-channel conv group ends with a 16-column chunk)
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* o, const float (&v)[32], int ncols_left, bool vec_ok) {
-  if (ncols_left >= 32 && vec_ok) {
+  if (vec_ok) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      uint4 pk;
-      pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-      pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-      pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-      pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-      reinterpret_cast<uint4*>(o)[q] = pk;
+      if (q * 8 + 8 <= ncols_left) {
+        uint4 pk;
+        pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        reinterpret_cast<uint4*>(o)[q] = pk;
+      } else {
+#pragma unroll
+        for (int i = q * 8; i < q * 8 + 8; ++i)
+          if (i < ncols_left) o[i] = __float2bfloat16(v[i]);
+      }
     }
   } else {
 #pragma unroll
@@ -338,10 +385,17 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* o, const float (
   }
 }
 __device__ __forceinline__ void store_row32_f32(float* o, const float (&v)[32], int ncols_left, bool vec_ok) {
-  if (ncols_left >= 32 && vec_ok) {
+  if (vec_ok) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    for (int q = 0; q < 8; ++q) {
+      if (q * 4 + 4 <= ncols_left) {
+        reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int i = q * 4; i < q * 4 + 4; ++i)
+          if (i < ncols_left) o[i] = v[i];
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -364,6 +418,19 @@ __device__ __forceinline__ void load_bias32(const float* bias, int n0, int left,
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) b[i] = i < left ? __ldg(bias + n0 + i) : 0.f;
+  }
+}
+// same for a chunk that may be partial, 16-byte loads for every whole group of 4 (bias + n0 must be 16-byte aligned)
+__device__ __forceinline__ void load_bias32_groups(const float* bias, int n0, int left, float (&b)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (bias != nullptr && q * 4 + 4 <= left) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n0) + q);
+      b[q * 4] = t.x; b[q * 4 + 1] = t.y; b[q * 4 + 2] = t.z; b[q * 4 + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = q * 4; i < q * 4 + 4; ++i) b[i] = (bias != nullptr && i < left) ? __ldg(bias + n0 + i) : 0.f;
+    }
   }
 }
 

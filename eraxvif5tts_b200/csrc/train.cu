@@ -235,8 +235,13 @@ static int train_block_forward(const F5bDitDesc& d, const TrainWs& w, int i, int
   // (train mode: to_out's Dropout sits between z1 and the gate -- site 1; FeedForward's follows the GELU -- site 0)
   F5B_TRY(f5b_gate_add_ln_modulate_site(b.x_in, b.z1, m + 2 * D, mod_dim, lens, b.x_mid, m + 4 * D, m + 3 * D, mod_dim, b.f, B, n, D,
                                         1e-6f, i, 1, stream));
-  F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
-  F5B_TRY(f5b_act_fwd_site(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, i, 0, stream));
+  if (!train_dropout_on()) {
+    // pre-GELU tensor (kept for the backward) and GELU output from ONE accumulator tile: no sweep that re-reads h1
+    F5B_TRY(linear_bf16_dual(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, b.u, F, rows, F, D, F5B_ACT_GELU_TANH, s));
+  } else {  // FeedForward's Dropout sits between GELU and the second Linear: the masked sweep
+    F5B_TRY(linear_bf16(b.f, D, ff1_w + (size_t)i * F * D, D, d.ff1_b + (size_t)i * F, b.h1, F, rows, F, D, F5B_ACT_NONE, s));
+    F5B_TRY(f5b_act_fwd_site(b.h1, b.u, (int64_t)rows * F, F5B_ACT_GELU_TANH, i, 0, stream));
+  }
   F5B_TRY(linear_bf16(b.u, F, ff2_w + (size_t)i * D * F, F, d.ff2_b + (size_t)i * D, b.z2, D, rows, D, F, F5B_ACT_NONE, s));
   return 0;
 }

@@ -873,6 +873,7 @@ Drop drop_for_site(int layer, int site) {
   return Drop{thr, 65536.0f / (65536.0f - (float)thr), g_drop_seed * 0xD1342543DE82EF95ull + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull};
 }
 static Drop drop_for(int layer, int site) { return drop_for_site(layer, site); }
+bool train_dropout_on() { return g_drop_p > 0.f; }
 // SDPA's dropout (site 2) draws from its own Philox stream (dropout.cuh); same seed, same per-(layer, site) key derivation
 AttnDrop make_attn_drop(float p, uint64_t seed, int layer) {
   if (!(p > 0.f)) return AttnDrop{0u, 1.f, 0.f, 0u, 0u};

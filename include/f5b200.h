@@ -34,7 +34,9 @@ enum {
   F5B_EPI_BF16 = 0,       /* out bf16[M,ldc]  = act(acc + bias)                                               */
   F5B_EPI_F32 = 1,        /* out f32 [M,ldc]  = act(acc + bias) (+ addsrc[row,:])  ; optional bf16 copy in out2 */
   F5B_EPI_QKV_ROPE = 2,   /* out bf16[M,ldc] = acc + bias with rotary embedding on the first rope_heads heads of the q and k sections */
-  F5B_EPI_GATE_RESID = 3  /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
+  F5B_EPI_GATE_RESID = 3, /* out f32[M,ldc] += gate[b,:] * (acc + bias), rows with pos >= lens[b] untouched    */
+  F5B_EPI_BF16_DUAL = 4   /* training forward (FeedForward, model/modules.py:348-353 under autograd): out bf16[M,ldc] = acc + bias (the
+                             pre-activation the backward needs) AND out2 bf16[M,ldc2] = act(out) from one accumulator tile; act = GELU_TANH */
 };
 enum { F5B_ACT_NONE = 0, F5B_ACT_GELU_TANH = 1, F5B_ACT_GELU_ERF = 2, F5B_ACT_SILU = 3, F5B_ACT_MISH = 4 /* f5b_act_fwd/bwd only */ };
 
@@ -44,7 +46,7 @@ typedef struct F5bGemmArgs {
   const float* bias;         /* [N] or NULL */
   void* out;                 /* see epilogue */
   int32_t ldc;
-  void* out2;                /* F32: optional bf16 copy */
+  void* out2;                /* F32: optional bf16 copy; BF16_DUAL: the activated output */
   int32_t ldc2;
   void* out3;                /* unused (kept for ABI stability) */
   const float* addsrc;       /* F32: optional f32 [M,ld_add] added to the result */

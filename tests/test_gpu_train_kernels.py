@@ -108,6 +108,30 @@ def test_act_fwd_bwd(act, fn):
     assert _rel(db, dh.float().sum(0)) <= 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 2048, 1024), (38400, 2048, 1024), (300, 384, 128), (4100, 1536, 768)])
+def test_dual_output_gemm_matches_gemm_plus_activation_sweep(M, N, K):
+    """F5B_EPI_BF16_DUAL (the training forward's FeedForward GEMM, model/modules.py:348-353): pre-activation and GELU output from one
+    accumulator tile must be bit-identical to the plain GEMM followed by the f5b_act_fwd sweep it replaces (128- and 256-wide tiles)."""
+    L, lib = _lib()
+    from eraxvif5tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    h_ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    u_ref = torch.empty_like(h_ref)
+    ops.gemm(a, w, epi=L.EPI_BF16, act=L.ACT_NONE, bias=bias, out=h_ref)
+    L.check(lib.f5b_act_fwd(h_ref.data_ptr(), u_ref.data_ptr(), M * N, L.ACT_GELU_TANH, L.stream()), "act_fwd")
+    h = torch.full_like(h_ref, float("nan"))
+    u = torch.full_like(h_ref, float("nan"))
+    ops.gemm(a, w, epi=L.EPI_BF16_DUAL, act=L.ACT_GELU_TANH, bias=bias, out=h, out2=u)
+    torch.cuda.synchronize()
+    assert torch.equal(h, h_ref)
+    assert torch.equal(u, u_ref)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().t() + bias, approximate="tanh")
+    assert (u.float() - ref).abs().max().item() < 3e-2
+
+
 def test_grn_gelu_bwd_and_dwconv_bwd_and_lookup_bwd():
     L, lib = _lib()
     dev = torch.device("cuda", 0)
