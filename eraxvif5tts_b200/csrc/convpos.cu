@@ -12,11 +12,12 @@
 namespace f5b {
 
 __device__ __forceinline__ float mish(float x) {
-  // x * tanh(softplus(x)); tanh(ln(1+e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = t / (t + 2), t = e (e + 2)
-  if (x > 20.f) return x;
-  const float e = __expf(x);
+  // x * tanh(softplus(x)); tanh(ln(1+e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = t / (t + 2), t = e (e + 2).  Branch-free, nine instructions
+  // (two on the SFU): the argument of the exponential is clamped at 20, where t / (t + 2) already rounds to 1 — the earlier
+  // `if (x > 20) return x` cost a BSSY / BRA / BSYNC triple per ELEMENT in an epilogue that bounded the kernel
+  const float e = ex2_approx(fminf(x, 20.f) * 1.4426950408889634f);
   const float t = e * (e + 2.f);
-  return x * __fdividef(t, t + 2.f);
+  return x * (t * rcp_approx(t + 2.f));
 }
 __device__ __forceinline__ float mish_precise(float x) {  // tf32 operand mode: libm exp and an IEEE division
   if (x > 20.f) return x;
@@ -244,11 +245,12 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int mw = warp == 1 ? 0 : 1;  // this issuer's sub-tiles: sblk & 1 == mw
     if (elect_one()) {
       const uint32_t idesc = idesc_bf16(BM, p.NP, 0, 0);
-      // ISSUE COST.  A 128 x 64 x 16 MMA executes in ~33 clocks, so this thread has to issue one every ~30 instructions' worth of
-      // time; building both 64-bit shared-memory descriptors from addresses each time (shift / mask / or on the uniform datapath plus
-      // R2UR moves) took ~90 clocks per MMA and left the tensor pipe 36 % busy (ncu, profiles/r02_convpos_issue.md).  All descriptors
-      // of a super-tile differ only in the 14-bit start-address field, which never carries (shared memory < 256 KB): the low word is
-      // advanced by constants — +8 per tap row (128 B), +1024 per 128-row sub-tile, +2 per K-step (32 B) — and the high word is fixed.
+      // ISSUE COST.  A 128 x 64 x 16 MMA executes in ~33 clocks, so the issuing side has about 30 instructions per MMA; building both
+      // 64-bit shared-memory descriptors from addresses each time (shift / mask / or on the uniform datapath plus R2UR moves) was ~12
+      // instructions and three R2UR per MMA.  All descriptors of a super-tile differ only in the 14-bit start-address field, which never
+      // carries (shared memory < 256 KB): the low word is advanced by constants — +8 per tap row (128 B), +1024 per 128-row sub-tile,
+      // +2 per K-step (32 B) — and the high word is fixed; the sub-tiles are split over two issuing warps.  (Measured: worth 5 %; what
+      // bounded the kernel was its epilogue, profiles/r02_convpos_epilogue.md.)
       const uint64_t d0 = smem_desc_sw128(0, 1024, 16);
       const uint32_t d_hi = (uint32_t)(d0 >> 32), d_lo0 = (uint32_t)d0;
       auto mk = [&](uint32_t lo) { return ((uint64_t)d_hi << 32) | (uint64_t)lo; };
@@ -301,8 +303,11 @@ convpos_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int w = half; w < nsub * chunks; w += 2) {  // (sub-tile, 32-column chunk) pairs, alternating between the warp pair
         const int sblk = w / chunks, c = w - sblk * chunks;
-        const int tile = (b * p.n_tiles_seq + st * HALO_SUB + sblk) * p.groups + g;
-        const auto ctx = p.row_ctx(tile, quad * 32 + lane);
+        typename ConvPosProblem<MODE>::RowCtx ctx;  // (built from the super-tile's coordinates: no tile-index divisions per visit)
+        const int pos = (st * HALO_SUB + sblk) * BM + quad * 32 + lane;
+        ctx.valid = pos < p.n;
+        ctx.ch0 = g * p.cpg;
+        ctx.row_off = ((size_t)b * p.n + pos) * p.D + ctx.ch0;
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + lane_base + acc * (HALO_SUB * 64) + sblk * 64 + c * 32, r);
