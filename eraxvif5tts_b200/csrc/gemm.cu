@@ -45,6 +45,7 @@ struct LinearProblem {
                                    : (EPI == F5B_EPI_GATE_RESID ? STORE_F32ADD : STORE_DIRECT);
   // BF16_DUAL (training forward): out = bf16(acc + bias), out2 = bf16(act(out)) from one accumulator tile (tile_engine.cuh, P::DUAL)
   static constexpr bool DUAL = EPI == F5B_EPI_BF16_DUAL;
+  static constexpr bool F32ADD_DIRECT = F5B_F32ADD_DIRECT != 0 && EPI == F5B_EPI_GATE_RESID && !TF32_;
   static_assert(!(DUAL && TF32_), "the dual-output epilogue exists in the bf16 operand mode only");
   static constexpr int CLUSTER = 2;  // CTA pairs on vertically adjacent tiles share the weight tile through TMA multicast
   F5bGemmArgs g;
@@ -167,6 +168,10 @@ struct LinearProblem {
     }
   }
 
+  // F32ADD_DIRECT: address of 32 consecutive residual-stream columns of this thread's row (nullptr: nothing to add)
+  __device__ __forceinline__ float* f32add_row(const RowCtx& c, int, int c0) const {
+    return c.valid ? reinterpret_cast<float*>(g.out) + (size_t)c.row * g.ldc + c.n_base + c0 : nullptr;
+  }
   // DUAL: the second output as a function of the (bf16-rounded) first one
   __device__ __forceinline__ float second(float x) const { return activate<ACT, false>(x); }
 
@@ -229,6 +234,7 @@ static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmB, const F
     if (make_tmap_2d(&tmC, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, 32, true)) return -1;
   } else if constexpr (P::STORE == STORE_F32ADD || P::STORE == STORE_F32) {
     F5B_CHECK((g.ldc & 3) == 0, "f5b_gemm: f32 output pitch %d must be a multiple of 4", g.ldc);
+    if constexpr (P::F32ADD_DIRECT) F5B_CHECK((g.N & 31) == 0, "f5b_gemm: the direct-reduction epilogue needs N %% 32 == 0 (N %d)", g.N);
     if (make_tmap_2d(&tmC, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, 32, true)) return -1;
   }
   CUtensorMap tmD = tmC;

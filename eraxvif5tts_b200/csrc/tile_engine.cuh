@@ -25,6 +25,9 @@
 
 namespace f5b {
 
+#ifndef F5B_F32ADD_DIRECT
+#define F5B_F32ADD_DIRECT 0
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
@@ -64,6 +67,9 @@ __device__ __forceinline__ void stage_store16(uint8_t* stg, int lane, int chunk,
 // P::DUAL (optional member, STORE_BF16 problems): the epilogue writes TWO bf16 tiles per accumulator tile — compute()'s values through
 // tmC and P::second() of the same (bf16-rounded) values through tmD — e.g. the pre-activation AND the activated output of a training
 // forward GEMM, which otherwise costs a separate sweep that re-reads the pre-activation from HBM.
+// P::F32ADD_DIRECT (optional member, STORE_F32ADD problems): see the epilogue
+template <class P, class = void> struct engine_f32add_direct { static constexpr bool value = false; };
+template <class P> struct engine_f32add_direct<P, decltype((void)P::F32ADD_DIRECT)> { static constexpr bool value = P::F32ADD_DIRECT; };
 template <class P, class = void> struct engine_is_dual { static constexpr bool value = false; };
 template <class P> struct engine_is_dual<P, decltype((void)P::DUAL)> { static constexpr bool value = P::DUAL; };
 
@@ -295,6 +301,18 @@ engine_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_ld_wait();
           float v[32];
           p.compute(ctx, g * 32, r, v);
+          if constexpr (engine_f32add_direct<P>::value) {
+            // experiment (-DF5B_F32ADD_DIRECT=1, off): the tile leaves as 16-byte reductions straight from the registers (no staging
+            // tile, no TMA) — 128 KB less shared-memory traffic per 128 x 256 tile, but eight times as many, smaller, reduction requests
+            // at the L2, and that rate is what binds: out-proj at cfg-2's shape 129 -> 198 us, FF2 203 -> 227 us, the cfg-2 step
+            // 23.8 k -> 22.8 k frames/s (tools/kernel_ab.py gate).  The full-line TMA reduce-add stays.
+            float* o = p.f32add_row(ctx, tile, g * 32);
+            if (o != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) red_add_v4_f32(o + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+            continue;
+          }
           if (elect_one()) bulk_wait_read0();
           __syncwarp();
 #pragma unroll

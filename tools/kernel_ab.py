@@ -69,6 +69,27 @@ def conv(shapes=((32, 1875, 1024), (64, 1376, 768))):
         print(f"conv: B{B} n{n} D{D}: mish->bf16 {ms0 * 1e3:7.1f} us {fl / ms0 / 1e9:6.1f} TFLOP/s | mish+residual {ms1 * 1e3:7.1f} us {fl / ms1 / 1e9:6.1f} TFLOP/s", flush=True)
 
 
+def gate():
+    """gated-residual GEMMs (out-proj K = D, FF2 K = 2D) at the cfg-2 / cfg-1 / cfg-3 row counts, with a bit-level checksum of x"""
+    for (M, n, N, K) in ((60000, 1875, 1024, 1024), (60000, 1875, 1024, 2048), (1880, 940, 1024, 1024), (1880, 940, 1024, 2048), (88064, 1376, 768, 768),
+                         (88064, 1376, 768, 1536)):
+        g = torch.Generator(device=dev).manual_seed(1)
+        a = (torch.randn(M, K, device=dev, generator=g) * 0.5).to(bf16)
+        w = (torch.randn(N, K, device=dev, generator=g) * 0.03).to(bf16)
+        bias = torch.randn(N, device=dev, generator=g) * 0.1
+        B = M // n
+        gate_t = torch.randn(B, N, device=dev, generator=g)
+        x = torch.zeros(M, N, device=dev)
+        fn = lambda: ops.gemm(a, w, epi=L.EPI_GATE_RESID, bias=bias, out=x, rows_per_batch=n, gate=gate_t, gate_bstride=N)
+        fn()
+        torch.cuda.synchronize()
+        ref = (a[:256].float() @ w.float().t() + bias) * gate_t[0]
+        err = (x[:256] - ref).abs().max().item()
+        chk = x.double().sum().item()
+        ms = timeit(fn)
+        print(f"gate: M{M} N{N} K{K}: {ms * 1e3:8.1f} us {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s  err(first call, 256 rows) {err:.2e} sum {chk:.6e}  (lib {os.environ.get('F5B_LIB', 'default')})", flush=True)
+
+
 def attn():
     for (B, H, n) in ((32, 16, 1875), (32, 16, 1200), (64, 12, 1376), (2, 16, 940)):
         D = H * 64
@@ -80,4 +101,4 @@ def attn():
 
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["dual", "conv", "attn"]:
-        {"dual": dual, "conv": conv, "conv3": lambda: conv(((64, 1376, 768),)), "attn": attn}[what]()
+        {"dual": dual, "conv": conv, "conv3": lambda: conv(((64, 1376, 768),)), "attn": attn, "gate": gate}[what]()
