@@ -807,19 +807,34 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
   const uint2* zr = reinterpret_cast<const uint2*>(z + row * D);
   const float4* gv = gate ? reinterpret_cast<const float4*>(gate + (size_t)b * gate_bstride) : nullptr;
   float4* xo = reinterpret_cast<float4*>(x_out + row * D);
-  float4 v[VEC];
-  float s = 0.f;
+  // ALL loads of the row (x, z, gate) are issued before the first use: the first version loaded, combined and stored one 16-byte chunk
+  // after the other (the `live` branch kept ptxas from hoisting the later loads), i.e. eight dependent round trips per row — 103 us at
+  // cfg-5's shape for 472 MB (4.6 TB/s)
+  float4 v[VEC], gt[VEC];
+  uint2 zz[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int idx = lane + j * 32;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gt[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    zz[j] = make_uint2(0u, 0u);
     if (idx < nvec) {
       v[j] = xr[idx];
       if (live) {
-        const uint2 zz = zr[idx];
-        const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.x));
-        const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz.y));
-        float4 g = gv ? __ldg(gv + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+        zz[j] = zr[idx];
+        if (gv) gt[j] = __ldg(gv + idx);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    if (idx < nvec) {
+      if (live) {
+        const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz[j].x));
+        const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zz[j].y));
+        float4 g = gt[j];
         if (dr.thr16) {
           float m[4];
           drop_mult4(dr, (uint64_t)row * D + (uint64_t)idx * 4, m);
@@ -832,6 +847,19 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
   }
+  // the modulation vectors of the output stage are fetched under the two reductions (z / gate registers are dead by now)
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_bstride);
+  float4 g4[VEC], h4[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int idx = lane + j * 32;
+    g4[j] = h4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < nvec) {
+      g4[j] = __ldg(sc + idx);
+      h4[j] = __ldg(sh + idx);
+    }
+  }
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
@@ -841,14 +869,12 @@ __global__ void __launch_bounds__(256) gate_add_ln_kernel(const float* __restric
       q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_bstride);
-  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_bstride);
   uint2* o = reinterpret_cast<uint2*>(out + row * D);
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int idx = lane + j * 32;
     if (idx < nvec) {
-      const float4 g = __ldg(sc + idx), h = __ldg(sh + idx);
+      const float4 g = g4[j], h = h4[j];
       o[idx] = make_uint2(pack_bf16((v[j].x - mean) * rstd * (1.f + g.x) + h.x, (v[j].y - mean) * rstd * (1.f + g.y) + h.y),
                           pack_bf16((v[j].z - mean) * rstd * (1.f + g.z) + h.z, (v[j].w - mean) * rstd * (1.f + g.w) + h.w));
     }

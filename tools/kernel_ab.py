@@ -90,6 +90,33 @@ def gate():
         print(f"gate: M{M} N{N} K{K}: {ms * 1e3:8.1f} us {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s  err(first call, 256 rows) {err:.2e} sum {chk:.6e}  (lib {os.environ.get('F5B_LIB', 'default')})", flush=True)
 
 
+def sweeps():
+    """the memory-bound sweeps of the training step at cfg-5's shape (32 x 1200 rows of 1024), algorithmic bytes / time"""
+    lib = L.load()
+    B, n, D = 32, 1200, 1024
+    x = torch.randn(B, n, D, device=dev)
+    z = torch.randn(B, n, D, device=dev).to(bf16)
+    mod = torch.randn(B, 6 * D, device=dev) * 0.1
+    lens = torch.full((B,), n, dtype=torch.int32, device=dev)
+    xo = torch.empty_like(x)
+    hb = torch.empty(B, n, D, dtype=bf16, device=dev)
+    S = L.stream
+    ms = timeit(lambda: L.check(lib.f5b_gate_add_ln_modulate(x.data_ptr(), z.data_ptr(), mod.data_ptr(), 6 * D, lens.data_ptr(), xo.data_ptr(),
+                                                             mod.data_ptr() + 4 * D, mod.data_ptr() + 8 * D, 6 * D, hb.data_ptr(), B, n, D, 1e-6, S()), "gal"))
+    print(f"sweep: gate_add_ln_modulate {ms * 1e3:7.1f} us  {12.0 * B * n * D / ms / 1e6:7.1f} GB/s", flush=True)
+    dy = torch.randn(B, n, D, device=dev).to(bf16)
+    dx = torch.zeros(B, n, D, device=dev)
+    dmod = torch.zeros(B, 6 * D, device=dev)
+    ms = timeit(lambda: L.check(lib.f5b_ln_modulate_bwd(dy.data_ptr(), x.data_ptr(), mod.data_ptr() + 4 * D, 6 * D, dx.data_ptr(), 1, dmod.data_ptr() + 4 * D,
+                                                        dmod.data_ptr(), B, n, D, 1e-6, S()), "lnb"))
+    print(f"sweep: ln_modulate_bwd      {ms * 1e3:7.1f} us  {14.0 * B * n * D / ms / 1e6:7.1f} GB/s", flush=True)
+    dz = torch.empty(B, n, D, dtype=bf16, device=dev)
+    dgate, dbias = torch.zeros(B, 6 * D, device=dev), torch.zeros(D, device=dev)
+    ms = timeit(lambda: L.check(lib.f5b_gate_bwd(dx.data_ptr(), z.data_ptr(), mod.data_ptr(), 6 * D, lens.data_ptr(), dz.data_ptr(), dgate.data_ptr(),
+                                                 dbias.data_ptr(), B, n, D, S()), "gb"))
+    print(f"sweep: gate_bwd             {ms * 1e3:7.1f} us  {8.0 * B * n * D / ms / 1e6:7.1f} GB/s", flush=True)
+
+
 def attn():
     for (B, H, n) in ((32, 16, 1875), (32, 16, 1200), (64, 12, 1376), (2, 16, 940)):
         D = H * 64
@@ -101,4 +128,4 @@ def attn():
 
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["dual", "conv", "attn"]:
-        {"dual": dual, "conv": conv, "conv3": lambda: conv(((64, 1376, 768),)), "attn": attn, "gate": gate}[what]()
+        {"dual": dual, "conv": conv, "conv3": lambda: conv(((64, 1376, 768),)), "attn": attn, "gate": gate, "sweeps": sweeps}[what]()
