@@ -29,6 +29,9 @@ int dwconv7_ln(const float* x, const float* w, const float* b, const float* ln_w
                int C, float eps, cudaStream_t s, float* y_out = nullptr, bool tf32 = false);
 int grn(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* ws, int B, int n, int C, cudaStream_t s,
         bool tf32 = false);
+// gemm_grad.cu: weight gradient of one 64-channel group of the grouped position-embedding conv, im2col by TMA coordinates
+int conv_wgrad_implicit(const void* dy_g, const void* x_g, int ld, float* out, int ldc, int B, int n, int cpg, int ks, int splits,
+                        cudaStream_t stream);
 bool train_dropout_on();  // train_kernels.cu: f5b_train_set_dropout's p > 0 (sites 0 / 1)
 struct AttnDrop;  // dropout.cuh: mask stream of one layer's SDPA dropout; nullptr / addc == 0 = no dropout
 int attn_fwd(const void* q, const void* k, const void* v, int ld, void* out, float* lse, const int32_t* lens, int lens_mod, int B, int H,

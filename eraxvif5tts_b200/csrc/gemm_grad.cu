@@ -15,6 +15,10 @@ struct GradArgs {
   int M, N, K;          // output M x N, reduction K
   int m_tiles, n_tiles, kb_per_split, splits;
   float* bias_unused;
+  // implicit grouped-conv weight gradient (conv_cpb > 0; A and B MN-major, 3-D tensor maps [channel, position, batch row]):
+  // the reduction runs over (batch row, 64-position chunk), conv_cpb chunks per batch row, and 64-column chunk c of the B tile is the
+  // layer input shifted by tap (n_blk * BN / 64 + c) - conv_pad positions — im2col by TMA coordinates, zero fill = the conv's padding
+  int conv_cpb, conv_pad;
 };
 
 // PAIR: the unit is a vertical PAIR of m-blocks run by a 2-CTA cluster as one tcgen05 CTA pair (cta_group::2, 256 x BN tile):
@@ -81,6 +85,17 @@ struct GradProblem {
                                        const CUtensorMap* tmB, uint32_t) const {
     int split, m_blk, n_blk;
     decode(unit, split, m_blk, n_blk);
+    if constexpr (A_MN && B_MN) {
+      if (g.conv_cpb > 0) {
+        const int kbg = split * g.kb_per_split + kb;
+        const int b = kbg / g.conv_cpb, p0 = (kbg - b * g.conv_cpb) * BK;  // b past the last batch row: zero fill
+#pragma unroll
+        for (int c = 0; c < BM / 64; ++c) tma_load_3d(sA + c * 8192, tmA, bar, m_blk * BM + c * 64, p0, b);
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c) tma_load_3d(sB + c * 8192, tmB, bar, 0, p0 + n_blk * (BN / 64) + c - g.conv_pad, b);
+        return;
+      }
+    }
     const int k0 = (split * g.kb_per_split + kb) * BK;  // past-the-end K ranges are zero-filled by TMA
     if constexpr (A_MN) {
 #pragma unroll
@@ -121,6 +136,8 @@ static int launch_grad(const void* A, int lda, const void* B, int ldb, void* out
   const int kblocks = (K + BK - 1) / BK;
   p.g.splits = splits;
   p.g.kb_per_split = (kblocks + splits - 1) / splits;
+  p.g.conv_cpb = 0;
+  p.g.conv_pad = 0;
   CUtensorMap tmA, tmB, tmC;
   if (A_MN) {
     if (make_tmap_2d(&tmA, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64, true)) return -1;
@@ -139,6 +156,36 @@ static int launch_grad(const void* A, int lda, const void* B, int ldb, void* out
   }
   const int units = (PAIR ? p.g.m_tiles / 2 : p.g.m_tiles) * p.g.n_tiles * splits;
   return launch_engine<P, PAIR>(tmA, tmB, tmC, p, units, stream);
+}
+
+// Weight gradient of one group of a grouped Conv1d (ConvPositionEmbedding, model/modules.py:167-190) WITHOUT an im2col buffer:
+//   dW_g[co, k * cpg + ci] += sum_{b, t} dY[b, t, co] * X[b, t + k - pad, ci]        (cpg = 64 channels per group)
+// = the MN-major x MN-major split-K GEMM above with M = cpg, N = ks * 64, the reduction over (b, t), where the 64-column chunk of
+// tap k of the B operand is simply the TMA box of X at position offset k - pad (3-D maps clip / zero-fill per batch row).  The
+// materialised k-major im2col this replaces wrote and re-read 152 MB per group (4.9 GB per step at cfg-5).
+int conv_wgrad_implicit(const void* dy_g, const void* x_g, int ld, float* out, int ldc, int B, int n, int cpg, int ks, int splits,
+                        cudaStream_t stream) {
+  F5B_CHECK(cpg == 64 && (ld & 7) == 0 && (ldc & 3) == 0, "conv_wgrad_implicit: 64 channels per group expected (cpg %d)", cpg);
+  using P = GradProblem<256, true, true, STORE_F32ADD, false>;
+  P p;
+  const int N = ks * 64;
+  p.g.M = cpg; p.g.N = N;
+  p.g.conv_cpb = (n + BK - 1) / BK;
+  p.g.conv_pad = ks / 2;
+  const int kblocks = B * p.g.conv_cpb;
+  p.g.K = kblocks * BK;
+  p.g.m_tiles = 1;
+  p.g.n_tiles = (N + 255) / 256;
+  if (splits > kblocks) splits = kblocks;
+  p.g.splits = splits;
+  p.g.kb_per_split = (kblocks + splits - 1) / splits;
+  LaunchScope scope(K_GEMM, stream, 2.0 * cpg * N * (double)B * n, 2.0 * 2.0 * (double)B * n * cpg + 8.0 * cpg * N);
+  CUtensorMap tmA, tmB, tmC;
+  const uint64_t pitch = (uint64_t)ld * 2;
+  if (make_tmap_3d(&tmA, dy_g, 2, (uint64_t)cpg, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, 64, 1, true)) return -1;
+  if (make_tmap_3d(&tmB, x_g, 2, (uint64_t)cpg, (uint64_t)n, (uint64_t)B, pitch, (uint64_t)n * pitch, 64, 64, 1, true)) return -1;
+  if (make_tmap_2d(&tmC, out, 4, (uint64_t)N, (uint64_t)cpg, (uint64_t)ldc * 4, 32, 32, true)) return -1;
+  return launch_engine<P, false>(tmA, tmB, tmC, p, p.g.n_tiles * splits, stream);
 }
 
 int g_grad_pair_mode = 1;  // 1 (default): 256-wide tiles with at least two m-blocks run as tcgen05 CTA pairs

@@ -177,6 +177,8 @@ static TextWs carve_text(const F5bDitDesc& d, int B, int n, void* ws) {
   return w;
 }
 
+int g_conv_wgrad_implicit = [] { const char* e = getenv("F5B_CONV_WGRAD_IM2COL"); return (e && atoi(e)) ? 0 : 1; }();  // A/B switch
+
 static int pick_splits(int M, int N, int K) {
   const int bn = N >= 256 ? 256 : 128;  // f5b_gemm_tn's tile width
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
@@ -388,6 +390,11 @@ static int train_backward_impl(const F5bDit* h, const void* dpred_bf16, const vo
     if (dw == nullptr) return 0;
     F5B_CUDA(cudaMemsetAsync(w.cpw_tmp, 0, sizeof(float) * (size_t)D * ccols, s));
     for (int gi = 0; gi < G; ++gi) {
+      if (cpg == 64 && g_conv_wgrad_implicit) {  // no im2col buffer: the taps are TMA position offsets (gemm_grad.cu)
+        F5B_TRY(conv_wgrad_implicit(dy + gi * cpg, xin + gi * cpg, D, w.cpw_tmp + (size_t)gi * cpg * ccols, ccols, B, n, cpg, ks,
+                                    pick_splits(cpg, ccols, rows), s));
+        continue;
+      }
       {
         LaunchScope scope(K_ELEMENTWISE, s, 0, 4.0 * rows * ccols);
         im2col_convpos_kernel<<<rows, 256, 0, s>>>(xin, w.xcol, n, D, gi, cpg, ks);
@@ -521,3 +528,5 @@ int f5b_dit_text_embed_backward(const F5bDit* h, const int64_t* ids, int nt, int
 }
 
 }  // extern "C"
+
+extern "C" void f5b_debug_conv_wgrad_implicit(int on) { f5b::g_conv_wgrad_implicit = on; }
