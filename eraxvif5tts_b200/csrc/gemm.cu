@@ -291,6 +291,8 @@ int gemm(const void* A, int lda, const void* W, int ldw, const F5bGemmArgs& g, c
   // 256-wide tiles (CTA pairs) once they fill about two thirds of the machine; below that 128-wide tiles give twice the units to
   // spread.  Measured on the B = 1 shapes (M = 1880): threshold 148 tiles 75.4 ms per utterance, 98 -> 72.8 ms (FF1, 120 tiles, moves to
   // pairs), 60 -> 76.5 ms (out-proj / FF2, 60 tiles, are better off with 128-wide tiles).  F5B_GEMM_BN256_MIN_TILES overrides it.
+  // (A wave-quantisation rule — units / clusters rounded up, a 128-wide tile costed at 0.6 of a pair tile — differs from this one for
+  // QKV at M = 1880 only, 96 pair units = 2 waves against 192 narrow units = 3 waves, and measured WORSE: 67.3 vs 66.6 ms per utterance.)
   static const int min_tiles256 = [] {
     const char* e = getenv("F5B_GEMM_BN256_MIN_TILES");
     return e ? atoi(e) : sm_count() * 2 / 3;
