@@ -562,6 +562,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 (default, BASELINE.json's metric config), cfg1, cfg3, cfg3d18, cfg4 (fixed 256-utterance job, strong scaling): inference; cfg5, cfg5b: the training step")
+    ap.add_argument("--batch", type=int, default=0, help="experiments only: override the workload's utterances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ragged", action="store_true", help="inference workloads: per-utterance durations U[0.8, 1] x the nominal length "
                     "(SURVEY.md 8d's ragged cfg-2 variant, U[1500, 1875]); the value counts un-padded frames")
@@ -578,6 +579,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     arch_kw, B, ref_frames, total, desc = WORKLOADS[args.workload]
+    if args.batch > 0:  # experiment knob (sub-batch / L2-residency A/B); the named configurations fix the batch
+        B = args.batch
+        desc += f" [--batch {B} override]"
     cfg = Arch(**arch_kw)
     if args.workload.startswith("cfg5"):
         return run_train(args, cfg, B, total, desc, rank, local_rank, world)
