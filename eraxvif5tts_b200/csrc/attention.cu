@@ -354,18 +354,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // P_{j-2} V_{j-2} had been issued (tcgen05.commit covers every earlier MMA of the issuing thread), so P buffer (j & 1) is free.
       // PT: P_j stays in registers (16 packed pairs per 32 keys) until it is final.
       float ts;
-      uint32_t ppk[PT ? 32 : 1];
       // mask group of this tile's first key in this thread's (batch, head, query) row
       const uint64_t g0 = DROP ? ((uint64_t)bh * p.n + (uint64_t)(q0 + r)) * p.n8 + (uint64_t)((t_begin + j) * (ATT_BKV / 8)) : 0;
-      auto make_p = [&]() {
+      // PT: the tile's P goes to tensor memory in two halves of 32 keys (16 packed columns each), so that only 16 packed registers are
+      // live next to the 64 scores (which stay live for the rare recomputation below): with all 32 the kernel sat at the 128-register
+      // cap with ~6 spill reloads per warp and tile (profiles/r02_ncu_attention_pt.txt).  The P columns are single-buffered: before
+      // the first store P_{j-1} V_{j-1} (issued a whole tile of exponentials ago) must have retired.
+      auto make_p = [&](bool first) {
         if constexpr (PT) {
-          if (valid == ATT_BKV) {
-            ts = softmax_chunk_reg<false>(s0, sl2, m_used, 32, ppk);
-            ts += softmax_chunk_reg<false>(s1, sl2, m_used, 32, ppk + 16);
-          } else {
-            ts = softmax_chunk_reg<true>(s0, sl2, m_used, valid, ppk);
-            ts += softmax_chunk_reg<true>(s1, sl2, m_used, valid - 32, ppk + 16);
+          uint32_t ppk[16];
+          if (valid == ATT_BKV) ts = softmax_chunk_reg<false>(s0, sl2, m_used, 32, ppk);
+          else ts = softmax_chunk_reg<true>(s0, sl2, m_used, valid, ppk);
+          if (first && j > 0) {
+            mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tc_fence_after();
           }
+          tmem_st16(tmem_P + lane_addr, ppk);
+          if (valid == ATT_BKV) ts += softmax_chunk_reg<false>(s1, sl2, m_used, 32, ppk);
+          else ts += softmax_chunk_reg<true>(s1, sl2, m_used, valid - 32, ppk);
+          tmem_st16(tmem_P + lane_addr + 16, ppk);
         } else {
           if (valid == ATT_BKV) {
             ts = softmax_chunk<false, DROP>(s0, sl2, m_used, 32, p_row, 0, rx, &dr, g0);
@@ -376,11 +383,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       };
-      make_p();
+      make_p(true);
       ATT_MARK(2)
       // "the row maximum grew by more than 2^8" implies that some exponential of this tile exceeds 2^8, hence so does the tile's row
       // sum: the 64-way maximum is only evaluated when that cheap necessary condition holds for some row of the warp
-      if (j > 0 && __any_sync(0xffffffffu, ts > 256.0f)) {
+      // (!(ts <= 256) also catches an overflowed sum)
+      if (j > 0 && __any_sync(0xffffffffu, !(ts <= 256.0f))) {
         const float mt = fmaxf(row_max32(s0, min(32, valid)), row_max32(s1, min(32, valid - 32))) * sl2;
         // warp-uniform decision; tcgen05.ld/st are warp-collective
         if (__any_sync(0xffffffffu, mt > m_used + ATT_RESCALE_LOG2)) {
@@ -400,18 +408,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st32(tmem_O + lane_addr + c * 32, o);
           }
           tmem_st_wait();
-          make_p();
+          make_p(false);  // against the new reference (PT: overwrites the P columns; P_j V_j has not been issued yet)
         }
       }
-      if constexpr (PT) {
-        // the P columns are single-buffered: P_{j-1} V_{j-1} (issued a whole tile of exponentials ago) must have retired
-        if (j > 0) {
-          mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after();
-        }
-        tmem_st32(tmem_P + lane_addr, ppk);
-        tmem_st_wait();
-      }
+      if constexpr (PT) tmem_st_wait();
       l_run += ts;
       ATT_MARK(3)
       if constexpr (!PT) fence_proxy_async_smem();
