@@ -166,6 +166,29 @@ def test_inference_attention_dropout_vs_oracle_and_sampling():
     dit.set_attn_dropout(0.0)
 
 
+@pytest.mark.parametrize("B,H,n,std", [(2, 4, 700, 6.0), (2, 16, 1200, 4.0), (1, 2, 333, 2.5)])
+def test_attention_forward_with_overflowing_speculative_exponentials(B, H, n, std):
+    """Scores whose row maximum jumps by more than 2^128 from one key tile to the next: the exponentials the kernel issues speculatively
+    against the old reference overflow to +inf, and the lazy-rescale path must recompute the tile exactly (SDPA handles any finite input;
+    a variant that rescaled P from the row sum returned NaN here).  Checked against fp64 softmax attention, with the log-sum-exp."""
+    from eraxvif5tts_b200 import ops
+    dev = torch.device("cuda", 0)
+    D = H * 64
+    g = torch.Generator().manual_seed(0)
+    qkv = (torch.randn(B * n, 3 * D, generator=g) * std).to(dev).bfloat16()
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().reshape(B, n, H, 64) for i in range(3))
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125
+    ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v).reshape(B * n, D)
+    out = torch.full((B * n, D), float("nan"), dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, H, n, dtype=torch.float32, device=dev)
+    ops.attn_fwd_lse(qkv[:, :D], qkv[:, D:], qkv[:, 2 * D:], 3 * D, out, lse, None, 0, B, H, n)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
+    assert float((out.double() - ref).norm() / ref.norm()) <= 4e-3
+    ref_lse = torch.logsumexp(s, -1) * 1.4426950408889634
+    assert float((lse.double() - ref_lse).abs().max()) <= 1e-3 * max(1.0, float(ref_lse.abs().max()))
+
+
 def test_attention_forward_is_deterministic_with_many_ctas_per_sm():
     """regression: the P.V completion barrier used to be a single mbarrier whose phase advanced once per key tile, while the softmax
     threads waited on it only in the epilogue; a warp running a full tile ahead of the slowest one then saw the parity of a phase

@@ -1,4 +1,5 @@
-"""Attention forward against an fp64 reference on inputs with very large score variance (std up to 6: single-tile jumps of the row maximum\nbeyond 2^128, i.e. speculative exponentials that overflow) — the robustness check that rejected a row-sum-based rescale variant (NaN at std 6)."""
+"""Attention forward against an fp64 reference on inputs with very large score variance (std up to 6: single-tile jumps of the row maximum
+beyond 2^128, i.e. speculative exponentials that overflow) — the robustness check that rejected a row-sum-based rescale variant (NaN at std 6)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eraxvif5tts_b200 import ops
