@@ -27,7 +27,8 @@
 namespace f5b {
 
 constexpr int AB_T = 128;                       // query tile == key tile
-constexpr int AB_THREADS = 448;
+constexpr int AB_THREADS = 448;  // 14 warps: four of them share an SM sub-partition's 16 K registers, hence the 128-register cap (a __maxnreg__(144)
+                                  // build — 64512 registers per CTA on paper — fails to launch); the softmax threads spill ~70 loads / stores
 constexpr uint32_t AB_TILE = AB_T * 64 * 2;     // 16 KB: [128 rows x 64 d] bf16, SW128
 constexpr uint32_t AB_PT = AB_T * AB_T * 2;     // 32 KB: [2 q-atoms][128 keys x 64 q] bf16, SW128
 constexpr uint32_t AB_STG = 8 * 4096;            // dQ staging: one [32 rows x 32 f32] SW128 box per softmax warp
