@@ -25,6 +25,21 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert _lib.load().f5b_abi_version() == 1
 
 
+def test_python_enum_constants_match_the_c_header():
+    """the epilogue / activation codes the Python side passes in F5bGemmArgs are the header's (a drifted constant would select another
+    epilogue silently)"""
+    from eraxvif5tts_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "f5b200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(F5B_(?:EPI|ACT)_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    assert len(enums) >= 9
+    for name, val in enums.items():
+        py = name[len("F5B_"):]
+        if hasattr(_lib, py):
+            assert getattr(_lib, py) == val, (name, val, getattr(_lib, py))
+    for py in ("EPI_BF16", "EPI_F32", "EPI_QKV_ROPE", "EPI_GATE_RESID", "EPI_BF16_DUAL", "ACT_NONE", "ACT_GELU_TANH", "ACT_GELU_ERF", "ACT_SILU"):
+        assert "F5B_" + py in enums and getattr(_lib, py) == enums["F5B_" + py]
+
+
 def test_no_cpu_fallback():
     from eraxvif5tts_b200 import _lib, ops
     with pytest.raises(_lib.F5bError):
