@@ -10,9 +10,9 @@ A "step" = one full pass of the hot path over one batch of synthetic utterances:
   e2e   : the same metric through the public API with HOST buffers (pinned reference waveform + token ids -> device, MelSpec,
           sample, vocoder, audio back to the host), host<->device copies inside the timed region.
   roofline     : dominant kernel class, algorithmic FLOPs / CUDA-event time measured live over the timed steps.
-  cpu_baseline : the oracle (CPU fp32 restatement of the reference) timed on this box's host cores on a bounded sample.
---impl reference times the reference's CPU implementation of the path (the oracle port; /root/reference cannot travel to the GPU
-box) with all host threads on the same workload / metric.
+  cpu_baseline : the reference's own modules (byte-compiled into oracle/_ref/ by oracle/make_ref.py; the oracle port if that directory is
+                 absent) timed on this box's host cores on a bounded sample.
+--impl reference times the same CPU implementation of the path with all host threads on the same workload / metric (cfg-1 in full).
 """
 from __future__ import annotations
 
